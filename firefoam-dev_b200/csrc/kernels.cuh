@@ -1,0 +1,553 @@
+// kernels.cuh -- hand-written sm_100a kernels of the p_rgh PCG hot path.
+//
+// Everything here is HBM-bandwidth-bound fp64 sparse/vector work (arithmetic intensity
+// ~0.1-0.2 flop/B): no tensor cores.  Design rules applied throughout:
+//   * persistent grid-stride kernels, grid = k x SM count, 256-thread blocks;
+//   * every streaming array is read once, coalesced (sliced-ELL for the matrix, double2 for
+//     vectors); gathered x[col] goes through the read-only path;
+//   * reductions are deterministic: warp shuffles -> shared -> one partial per block ->
+//     the LAST block to finish (integer ticket) sums the partials in a fixed order and runs
+//     the scalar step of the CG recurrence on the device (no float atomics, no host sync);
+//   * no FMA contraction (__dmul_rn/__dadd_rn) so that element-wise results are bit-identical
+//     to OpenFOAM's scalar loops (gcc x86-64 without -mfma never fuses); only the order of the
+//     global sums differs from the CPU.
+//
+// Reference algorithm text: SURVEY.md Appendix A (restating OF-dev PCG.C, lduMatrixATmul.C,
+// lduMatrixSolver.C, DICPreconditioner.C, diagonalPreconditioner.C, gaussLaplacianScheme.C).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr int kBlock = 256;
+constexpr int kMaxGrid = 148 * 16;   // upper bound of any reducing grid (partials capacity)
+constexpr int kNSums = 2;
+
+// CG recurrence steps executed on the device by the last block of a reducing kernel
+enum Step : int {
+    STEP_NONE = 0,
+    STEP_SUMPSI,   // xRef = gAverage(psi)
+    STEP_NORM,     // normFactor, initial residual, first convergence check
+    STEP_WARA,     // wArA = (wA, rA); beta
+    STEP_WAPA,     // wApA = (wA, pA); singularity; alpha
+    STEP_RES       // final residual; nIter++; convergence
+};
+
+struct Scalars {
+    // controls (written by the host before each solve)
+    double tol, relTol;
+    double nGlobalCells;
+    int maxIter, minIter, forceIters, nranks;
+    // state
+    double xRef, normFactor, initRes, finalRes;
+    double wArA, wArAold, wApA, alpha, beta;
+    int nIter, done, converged, singular, nonfinite, pad0;
+    // reduction plumbing
+    double acc[kNSums];    // running totals across the kernels of one reduction
+    double sums[kNSums];   // local totals (input of the all-reduce when nranks > 1)
+    double gsums[kNSums];  // global totals (== sums when nranks == 1)
+    unsigned int ticket;
+    unsigned int pad1;
+};
+
+struct Reduce {
+    Scalars* S;
+    double* partials;   // [kNSums][kMaxGrid]
+    int step;           // Step to run when this kernel completes the reduction (STEP_NONE:
+                        // only accumulate into S->acc)
+};
+
+// ---- scalar steps (OF-dev PCG.C, SolverPerformance.C) ---------------
+__device__ __forceinline__ bool check_convergence(const Scalars* S) {
+    // SolverPerformance::checkConvergence: final < Tolerance ||
+    //   (RelTolerance > small_*pTraits::one && final < RelTolerance*initial); small_ = 1e-20
+    return (S->finalRes < S->tol) || (S->relTol > 1e-20 && S->finalRes < S->relTol * S->initRes);
+}
+
+__device__ inline void scalar_step(int step, Scalars* S, const double* g) {
+    switch (step) {
+        case STEP_SUMPSI:
+            S->xRef = g[0] / S->nGlobalCells;
+            break;
+        case STEP_NORM: {
+            S->normFactor = g[0] + 1e-20;   // + small_
+            S->initRes = g[1] / S->normFactor;
+            S->finalRes = S->initRes;
+            S->nIter = 0;
+            S->wArA = 1e20;                 // great_
+            S->wArAold = 1e20;
+            S->singular = 0;
+            S->nonfinite = 0;
+            bool conv = check_convergence(S);
+            S->converged = conv ? 1 : 0;
+            bool enter = S->forceIters > 0 ? true : (S->minIter > 0 || !conv);
+            S->done = enter ? 0 : 1;
+            if (!(S->initRes == S->initRes) || fabs(S->initRes) > 1.7e308) {
+                S->nonfinite = 1;
+                S->done = 1;
+            }
+            break;
+        }
+        case STEP_WARA:
+            S->wArAold = S->wArA;
+            S->wArA = g[0];
+            S->beta = (S->nIter == 0) ? 0.0 : S->wArA / S->wArAold;
+            break;
+        case STEP_WAPA:
+            S->wApA = g[0];
+            // checkSingularity(mag(wApA)/normFactor): singular <=> value <= vSmall_ (1e-300)
+            if (S->forceIters == 0 && !(fabs(S->wApA) / S->normFactor > 1e-300)) {
+                S->singular = 1;
+                S->done = 1;
+            } else {
+                S->alpha = S->wArA / S->wApA;
+            }
+            break;
+        case STEP_RES: {
+            S->finalRes = g[0] / S->normFactor;
+            int old = S->nIter;
+            S->nIter = old + 1;
+            bool conv = check_convergence(S);
+            S->converged = conv ? 1 : 0;
+            bool cont;
+            if (S->forceIters > 0) cont = S->nIter < S->forceIters;
+            else cont = (old < S->maxIter && !conv) || (S->nIter < S->minIter);
+            if (!(S->finalRes == S->finalRes) || fabs(S->finalRes) > 1.7e308) {
+                S->nonfinite = 1;
+                cont = false;
+            }
+            if (!cont) S->done = 1;
+            break;
+        }
+        default:
+            break;
+    }
+}
+
+// After an all-reduce (nranks > 1): one thread runs the scalar step on the global sums.
+__global__ void k_scalar_step(Scalars* S, int step) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
+    scalar_step(step, S, S->gsums);
+}
+
+// ---- deterministic block reduction + last-block finish -----------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double (*sh)[kBlock / 32]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) sh[i][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = (lane < kBlock / 32) ? sh[i][lane] : 0.0;
+            s = warp_sum(s);
+            v[i] = s;   // valid in thread 0
+        }
+    }
+    __syncthreads();
+}
+
+// Every thread of every block must call this (uniformly).
+template <int NV>
+__device__ __forceinline__ void reduce_finish(double (&v)[NV], const Reduce& R) {
+    __shared__ double sh[NV][kBlock / 32];
+    __shared__ bool amLast;
+    block_sum<NV>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) R.partials[i * kMaxGrid + blockIdx.x] = v[i];
+        __threadfence();
+        unsigned int t = atomicAdd(&R.S->ticket, 1u);
+        amLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    double t[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock)
+            s = __dadd_rn(s, __ldcg(&R.partials[i * kMaxGrid + b]));
+        t[i] = s;
+    }
+    block_sum<NV>(t, sh);
+    if (threadIdx.x == 0) {
+        Scalars* S = R.S;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) S->acc[i] = __dadd_rn(S->acc[i], t[i]);
+        if (R.step != STEP_NONE) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                S->sums[i] = S->acc[i];
+                S->acc[i] = 0.0;
+            }
+            if (S->nranks == 1) scalar_step(R.step, S, S->sums);
+        }
+        S->ticket = 0u;
+        __threadfence();
+    }
+}
+
+// ---- gathers / scatters between natural and internal order -------------------------------
+__global__ void k_gather(int n, const int* __restrict__ perm, const double* __restrict__ src,
+                         double* __restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[i] = perm ? __ldg(&src[perm[i]]) : src[i];
+}
+__global__ void k_scatter(int n, const int* __restrict__ perm, const double* __restrict__ src,
+                          double* __restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (perm) dst[perm[i]] = src[i];
+        else dst[i] = src[i];
+    }
+}
+// matrix value fill: sliced-ELL value of entry e is upper[faceOf[e]] (0 for padding)
+__global__ void k_fill_values(int64_t nEntries, const int* __restrict__ faceOf,
+                              const double* __restrict__ upper, double* __restrict__ val) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nEntries;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int f = faceOf[e];
+        val[e] = f >= 0 ? __ldg(&upper[f]) : 0.0;
+    }
+}
+
+// ---- lduMatrix::Amul / sumA (OF-dev lduMatrixATmul.C) ---------------------
+// One row per thread, rows of a warp = one ELL slice -> the j-th loads of a warp are
+// contiguous.  Row sum order: diag*x, then faces in ascending face order with the row as
+// neighbour, then as owner == the order in which OpenFOAM's face loop updates Apsi[row].
+// INIT additionally forms sumA (same loop, x == 1).  DOT accumulates (y, x).
+template <bool INIT, bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+       const int* __restrict__ col, const double* __restrict__ val,
+       const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
+       double* __restrict__ sA, Reduce R) {
+    if (R.S->done) return;
+    double dot[1] = {0.0};
+    const int lane = threadIdx.x & 31;
+    const int nSlices = (N + 31) >> 5;
+    const int warpsPerGrid = (gridDim.x * kBlock) >> 5;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) >> 5; s < nSlices; s += warpsPerGrid) {
+        const int r = (s << 5) + lane;
+        if (r < N) {
+            const int64_t base = sliceBase[s] + lane;
+            const int n = (int)(rowLen[r] >> 16);
+            const double xr = x[r];
+            const double d = diag[r];
+            double acc = __dmul_rn(d, xr);
+            double sa = d;
+            int j = 0;
+            for (; j + 4 <= n; j += 4) {
+                const int64_t e = base + 32 * (int64_t)j;
+                const int c0 = col[e], c1 = col[e + 32], c2 = col[e + 64], c3 = col[e + 96];
+                const double a0 = val[e], a1 = val[e + 32], a2 = val[e + 64], a3 = val[e + 96];
+                const double x0 = __ldg(&x[c0]), x1 = __ldg(&x[c1]), x2 = __ldg(&x[c2]),
+                             x3 = __ldg(&x[c3]);
+                acc = __dadd_rn(acc, __dmul_rn(a0, x0));
+                acc = __dadd_rn(acc, __dmul_rn(a1, x1));
+                acc = __dadd_rn(acc, __dmul_rn(a2, x2));
+                acc = __dadd_rn(acc, __dmul_rn(a3, x3));
+                if (INIT) {
+                    sa = __dadd_rn(sa, a0);
+                    sa = __dadd_rn(sa, a1);
+                    sa = __dadd_rn(sa, a2);
+                    sa = __dadd_rn(sa, a3);
+                }
+            }
+            for (; j < n; ++j) {
+                const int64_t e = base + 32 * (int64_t)j;
+                const int c0 = col[e];
+                const double a0 = val[e];
+                acc = __dadd_rn(acc, __dmul_rn(a0, __ldg(&x[c0])));
+                if (INIT) sa = __dadd_rn(sa, a0);
+            }
+            y[r] = acc;
+            if (INIT) sA[r] = sa;
+            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
+// ---- processor interfaces (OF-dev processorFvPatchField.C, lduMatrixUpdateMatrixInterfaces.C;
+//      SURVEY.md A.4) ------------------------------------------------------------------------
+__global__ void k_pack(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ x,
+                       double* __restrict__ sendbuf, const Scalars* S) {
+    if (S->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x)
+        sendbuf[i] = __ldg(&x[slotRow[i]]);
+}
+// result[faceCells[i]] -= coeffs[i]*nbr[i]; one thread per distinct interface row, its slots
+// in (patch, face) order: a sorted-segment reduction.  MODE 0: Amul fix-up (+ correction of
+// the (y,x) dot product), MODE 1: sumA fix-up (nbr == 1).
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_iface_fix(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bStart,
+            const int* __restrict__ bSlot, const double* __restrict__ bou,
+            const double* __restrict__ recv, const double* __restrict__ x,
+            double* __restrict__ y, Reduce R) {
+    if (R.S->done) return;
+    double dot[1] = {0.0};
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
+        const int r = bRow[b];
+        const double y0 = y[r];
+        double acc = y0;
+        for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
+            const int slot = bSlot[e];
+            if (MODE == 0) acc = __dadd_rn(acc, -__dmul_rn(bou[slot], recv[slot]));
+            else acc = __dadd_rn(acc, -bou[slot]);
+        }
+        y[r] = acc;
+        if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(__dadd_rn(acc, -y0), x[r]));
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
+// ---- vector kernels ------------------------------------------------------------------------
+// All vectors are cudaMalloc'ed (256-byte aligned) -> double2 accesses are aligned.
+#define B200_VEC_LOOP(N, body2, body1)                                                     \
+    {                                                                                      \
+        const int n2 = (N) >> 1;                                                           \
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2;                        \
+             i += gridDim.x * blockDim.x) { body2 }                                        \
+        if (((N) & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const int i = (N)-1; body1 } \
+    }
+
+// gSum(psi) for gAverage (OF-dev FieldFunctions.C)
+__global__ void __launch_bounds__(kBlock)
+k_sum(int N, const double* __restrict__ a, Reduce R) {
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { double2 v = reinterpret_cast<const double2*>(a)[i];
+          s[0] = __dadd_rn(s[0], __dadd_rn(v.x, v.y)); },
+        { s[0] = __dadd_rn(s[0], a[i]); })
+    reduce_finish<1>(s, R);
+}
+
+// rA = source - wA; normFactor and initial residual sums (OF-dev lduMatrixSolver.C normFactor,
+// PCG.C): sums[0] = sum(|wA - xRef*sumA| + |source - xRef*sumA|),
+// sums[1] = sum |rA|
+__global__ void __launch_bounds__(kBlock)
+k_norm_resid(int N, const double* __restrict__ wA, const double* __restrict__ sA,
+             const double* __restrict__ src, double* __restrict__ rA, Reduce R) {
+    double s[2] = {0.0, 0.0};
+    const double xRef = R.S->xRef;
+#define B200_NR1(W, SA, B, ROUT)                                                   \
+    {                                                                              \
+        const double t = __dmul_rn((SA), xRef);                                    \
+        s[0] = __dadd_rn(s[0], __dadd_rn(fabs(__dadd_rn((W), -t)), fabs(__dadd_rn((B), -t)))); \
+        const double rr_ = __dadd_rn((B), -(W));                                   \
+        s[1] = __dadd_rn(s[1], fabs(rr_));                                         \
+        ROUT = rr_;                                                                \
+    }
+    B200_VEC_LOOP(N,
+        { double2 w = reinterpret_cast<const double2*>(wA)[i];
+          double2 a = reinterpret_cast<const double2*>(sA)[i];
+          double2 b = reinterpret_cast<const double2*>(src)[i];
+          double2 r;
+          B200_NR1(w.x, a.x, b.x, r.x)
+          B200_NR1(w.y, a.y, b.y, r.y)
+          reinterpret_cast<double2*>(rA)[i] = r; },
+        { double r; B200_NR1(wA[i], sA[i], src[i], r) rA[i] = r; })
+#undef B200_NR1
+    reduce_finish<2>(s, R);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_recip(int N, const double* d, double* rD) {   // d may alias rD (in-place)
+    B200_VEC_LOOP(N,
+        { double2 v = reinterpret_cast<const double2*>(d)[i];
+          v.x = __ddiv_rn(1.0, v.x); v.y = __ddiv_rn(1.0, v.y);
+          reinterpret_cast<double2*>(rD)[i] = v; },
+        { rD[i] = __ddiv_rn(1.0, d[i]); })
+}
+
+// diagonalPreconditioner::precondition fused with gSumProd(wA, rA)
+// (OF-dev diagonalPreconditioner.C, PCG.C).  PRECOND=false: `none` -> (rA, rA) only.
+template <bool PRECOND>
+__global__ void __launch_bounds__(kBlock)
+k_precond_dot(int N, const double* __restrict__ rD, const double* __restrict__ rA,
+              double* __restrict__ wA, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { double2 r = reinterpret_cast<const double2*>(rA)[i];
+          double2 w = r;
+          if (PRECOND) {
+              double2 d = reinterpret_cast<const double2*>(rD)[i];
+              w.x = __dmul_rn(d.x, r.x); w.y = __dmul_rn(d.y, r.y);
+              reinterpret_cast<double2*>(wA)[i] = w;
+          }
+          s[0] = __dadd_rn(s[0], __dmul_rn(w.x, r.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(w.y, r.y)); },
+        { double r = rA[i]; double w = r;
+          if (PRECOND) { w = __dmul_rn(rD[i], r); wA[i] = w; }
+          s[0] = __dadd_rn(s[0], __dmul_rn(w, r)); })
+    reduce_finish<1>(s, R);
+}
+
+// pA = wA (first iteration) | pA = wA + beta*pA   (OF-dev PCG.C)
+__global__ void __launch_bounds__(kBlock)
+k_pupdate(int N, const double* __restrict__ z, double* __restrict__ pA, const Scalars* S) {
+    if (S->done) return;
+    const bool first = (S->nIter == 0);
+    const double beta = S->beta;
+    B200_VEC_LOOP(N,
+        { double2 w = reinterpret_cast<const double2*>(z)[i];
+          if (!first) {
+              double2 p = reinterpret_cast<const double2*>(pA)[i];
+              w.x = __dadd_rn(w.x, __dmul_rn(beta, p.x));
+              w.y = __dadd_rn(w.y, __dmul_rn(beta, p.y));
+          }
+          reinterpret_cast<double2*>(pA)[i] = w; },
+        { double w = z[i]; if (!first) w = __dadd_rn(w, __dmul_rn(beta, pA[i])); pA[i] = w; })
+}
+
+// psi += alpha*pA; rA -= alpha*wA; gSumMag(rA)   (OF-dev PCG.C)
+__global__ void __launch_bounds__(kBlock)
+k_update(int N, double* __restrict__ psi, double* __restrict__ rA,
+         const double* __restrict__ pA, const double* __restrict__ wA, Reduce R) {
+    if (R.S->done) return;
+    const double alpha = R.S->alpha;
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { double2 x = reinterpret_cast<double2*>(psi)[i];
+          double2 r = reinterpret_cast<double2*>(rA)[i];
+          double2 p = reinterpret_cast<const double2*>(pA)[i];
+          double2 w = reinterpret_cast<const double2*>(wA)[i];
+          x.x = __dadd_rn(x.x, __dmul_rn(alpha, p.x));
+          x.y = __dadd_rn(x.y, __dmul_rn(alpha, p.y));
+          r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
+          r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
+          reinterpret_cast<double2*>(psi)[i] = x;
+          reinterpret_cast<double2*>(rA)[i] = r;
+          s[0] = __dadd_rn(s[0], __dadd_rn(fabs(r.x), fabs(r.y))); },
+        { double x = __dadd_rn(psi[i], __dmul_rn(alpha, pA[i]));
+          double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
+          psi[i] = x; rA[i] = r; s[0] = __dadd_rn(s[0], fabs(r)); })
+    reduce_finish<1>(s, R);
+}
+
+// ---- DIC-class preconditioner (OF-dev DICPreconditioner.C) -----------------
+// Rows are ordered colour-major; "lower" entries of a row = neighbours of an earlier colour
+// (or an earlier dependency level in DIC-exact mode).  One launch per colour, rows of a colour
+// are independent.  Operation order inside a row is OpenFOAM's:
+//   calcReciprocalD:  rD[u] -= upper*upper/rD[l]         (faces ascending)
+//   forward:          wA[u] -= rD[u]*upper*wA[l]         (faces ascending)
+//   backward:         wA[l] -= rD[l]*upper*wA[u]         (faces descending)
+__global__ void __launch_bounds__(kBlock)
+k_dic_calc_rd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+              const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+              const double* __restrict__ val, const double* __restrict__ diag,
+              double* __restrict__ rD) {
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        double d = diag[r];
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            const double a = val[e];
+            // rD of an earlier colour was written by an earlier launch: plain (coherent) load
+            d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(a, a), rD[col[e]]));
+        }
+        rD[r] = d;
+    }
+}
+
+// forward sweep over one colour.  DOT: this colour's wA is final (last colour) -> add (wA, rA).
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_dic_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+          const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+          const double* __restrict__ val, const double* __restrict__ rD,
+          const double* __restrict__ rA, double* wA, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        const double d = rD[r];
+        const double rr = rA[r];
+        double w = __dmul_rn(d, rr);
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[col[e]]));
+        }
+        wA[r] = w;
+        if (DOT) s[0] = __dadd_rn(s[0], __dmul_rn(w, rr));
+    }
+    if (DOT) reduce_finish<1>(s, R);
+}
+
+// backward sweep over one colour; wA of this colour becomes final -> always add (wA, rA).
+__global__ void __launch_bounds__(kBlock)
+k_dic_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+          const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+          const double* __restrict__ val, const double* __restrict__ rD,
+          const double* __restrict__ rA, double* wA, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const uint32_t len = rowLen[r];
+        const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+        const double d = rD[r];
+        double w = wA[r];
+        for (int j = nTotal - 1; j >= nLower; --j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[col[e]]));
+        }
+        wA[r] = w;
+        s[0] = __dadd_rn(s[0], __dmul_rn(w, rA[r]));
+    }
+    reduce_finish<1>(s, R);
+}
+
+// ---- assembly: gaussLaplacianScheme::fvmLaplacianUncorrected + negSumDiag ------------------
+// (OF-dev gaussLaplacianScheme.C, lduMatrixOperations.C)
+__global__ void __launch_bounds__(kBlock)
+k_face_coeff(int F, const double* __restrict__ gamma, const double* __restrict__ magSf,
+             const double* __restrict__ delta, double sign, double* __restrict__ upper) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x)
+        upper[f] = __dmul_rn(sign, __dmul_rn(delta[f], __dmul_rn(gamma[f], magSf[f])));
+}
+// diag[c] += (0 - upper[f1] - upper[f2] ...) over the faces of c in face order: the two
+// sorted segments (neighbour side via losort, then owner side) of the natural-order plan.
+__global__ void __launch_bounds__(kBlock)
+k_neg_sum_diag(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+               const int* __restrict__ faceOf, const double* __restrict__ upper,
+               double* __restrict__ diag) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int n = (int)(rowLen[r] >> 16);
+        double d = 0.0;
+        for (int j = 0; j < n; ++j) d = __dadd_rn(d, -__ldg(&upper[faceOf[base + 32 * (int64_t)j]]));
+        diag[r] = __dadd_rn(diag[r], d);
+    }
+}
+
+// ---- fvMatrix::flux() internal faces (OF-dev fvMatrix.C) --------------------
+__global__ void __launch_bounds__(kBlock)
+k_flux(int F, const int* __restrict__ l, const int* __restrict__ u,
+       const double* __restrict__ upper, const double* __restrict__ psi,
+       double* __restrict__ flux) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        const double a = upper[f];
+        flux[f] = __dadd_rn(__dmul_rn(a, __ldg(&psi[u[f]])), -__dmul_rn(a, __ldg(&psi[l[f]])));
+    }
+}
+
+}  // namespace b200

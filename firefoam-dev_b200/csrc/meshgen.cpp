@@ -1,0 +1,249 @@
+// meshgen.cpp -- synthetic workloads of BASELINE.json as OpenFOAM-style LDU data.
+//
+// Host-only C++ (libb200mesh.so, no CUDA): the harness equivalent of blockMesh + decomposePar +
+// the field set-up of solver/pEqn.H:3-4 (rhorAUf) for synthetic cases.  It produces exactly what
+// fvMatrix<scalar>::solveSegregated hands to lduMatrix::solver: lowerAddr /
+// upperAddr in upper-triangular order, diag WITH boundary internalCoeffs, upper,
+// processor-interface faceCells + interfaceBouCoeffs, totalSource -- plus the face fields
+// (gamma_f, magSf, deltaCoeffs) that fvm::laplacian consumes, so the assembly kernel can be
+// checked against the same matrix.
+//
+// Workload generators are NOT the oracle: they only make inputs.  The CPU restatement of the
+// reference algorithm lives in oracle/.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// uniform in (-1, 1), counter-based
+inline double uni(uint64_t seed, uint64_t counter) {
+    uint64_t r = splitmix64(seed ^ (counter * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
+    return ((double)(r >> 11) + 0.5) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+struct Range { int lo, hi; };
+// decomposePar `simple`/`hierarchical` on an evenly sorted coordinate: n groups of floor(N/n)
+// cells, the first N mod n groups get one extra.
+inline Range split(int N, int n, int g) {
+    int base = N / n, extra = N % n;
+    int lo = g * base + std::min(g, extra);
+    int hi = lo + base + (g < extra ? 1 : 0);
+    return {lo, hi};
+}
+
+struct HexSpec {
+    int NX, NY, NZ, PX, PY, PZ, rank;
+    uint64_t seed;
+    double h, gamma0, psiOverDt;  // psiOverDt = psi/dt (ddt coefficient per unit volume)
+};
+
+struct HexBlock {
+    HexSpec s;
+    Range rx, ry, rz;
+    int gx, gy, gz, lnx, lny, lnz;
+    int32_t N;
+    int32_t F;
+    int nIf;
+    int nbrRank[6];
+    int nbrDir[6];    // 0:-z 1:-y 2:-x 3:+x 4:+y 5:+z
+    int nbrFaces[6];
+};
+
+const double kPi = 3.14159265358979323846;
+
+inline int64_t gid(const HexSpec& s, int i, int j, int k) {
+    return (int64_t)i + (int64_t)s.NX * ((int64_t)j + (int64_t)s.NY * k);
+}
+inline double gamma_cell(const HexSpec& s, int i, int j, int k) {
+    const double x = (i + 0.5) * s.h, y = (j + 0.5) * s.h, z = (k + 0.5) * s.h;
+    const double xi = uni(s.seed, (uint64_t)gid(s, i, j, k));
+    return s.gamma0 * (1.0 + 0.9 * std::sin(2 * kPi * x) * std::sin(2 * kPi * y) * std::sin(2 * kPi * z)) *
+           std::pow(10.0, 0.5 * xi);
+}
+inline double xstar_cell(const HexSpec& s, int i, int j, int k) {
+    const double x = (i + 0.5) * s.h, y = (j + 0.5) * s.h, z = (k + 0.5) * s.h;
+    const double xi = uni(s.seed ^ 0xABCDEF1234567ull, (uint64_t)gid(s, i, j, k));
+    return std::sin(kPi * x) * std::cos(2 * kPi * y) * std::sin(3 * kPi * z) + 0.5 * x + 0.01 * xi;
+}
+
+bool make_block(const HexSpec& s, HexBlock& b) {
+    if (s.NX < 1 || s.NY < 1 || s.NZ < 1 || s.PX < 1 || s.PY < 1 || s.PZ < 1) return false;
+    if (s.PX > s.NX || s.PY > s.NY || s.PZ > s.NZ) return false;
+    if (s.rank < 0 || s.rank >= s.PX * s.PY * s.PZ) return false;
+    b.s = s;
+    b.gx = s.rank % s.PX;
+    b.gy = (s.rank / s.PX) % s.PY;
+    b.gz = s.rank / (s.PX * s.PY);
+    b.rx = split(s.NX, s.PX, b.gx);
+    b.ry = split(s.NY, s.PY, b.gy);
+    b.rz = split(s.NZ, s.PZ, b.gz);
+    b.lnx = b.rx.hi - b.rx.lo;
+    b.lny = b.ry.hi - b.ry.lo;
+    b.lnz = b.rz.hi - b.rz.lo;
+    int64_t N = (int64_t)b.lnx * b.lny * b.lnz;
+    int64_t F = (int64_t)(b.lnx - 1) * b.lny * b.lnz + (int64_t)b.lnx * (b.lny - 1) * b.lnz +
+                (int64_t)b.lnx * b.lny * (b.lnz - 1);
+    if (N > 0x7fffffff || F > 0x7fffffff) return false;
+    b.N = (int32_t)N;
+    b.F = (int32_t)F;
+    b.nIf = 0;
+    auto add = [&](bool present, int dir, int nbr, int nf) {
+        if (!present) return;
+        b.nbrRank[b.nIf] = nbr;
+        b.nbrDir[b.nIf] = dir;
+        b.nbrFaces[b.nIf] = nf;
+        b.nIf++;
+    };
+    // ascending neighbour rank == processor patch order of decomposePar
+    add(b.gz > 0, 0, s.rank - s.PX * s.PY, b.lnx * b.lny);
+    add(b.gy > 0, 1, s.rank - s.PX, b.lnx * b.lnz);
+    add(b.gx > 0, 2, s.rank - 1, b.lny * b.lnz);
+    add(b.gx < s.PX - 1, 3, s.rank + 1, b.lny * b.lnz);
+    add(b.gy < s.PY - 1, 4, s.rank + s.PX, b.lnx * b.lnz);
+    add(b.gz < s.PZ - 1, 5, s.rank + s.PX * s.PY, b.lnx * b.lny);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// sizes[0]=nCells, [1]=nFaces, [2]=nIfaces, [3..8]=faces per interface, [9..14]=neighbour ranks
+int b200mesh_hex_sizes(int NX, int NY, int NZ, int PX, int PY, int PZ, int rank, int64_t* sizes) {
+    HexSpec s{NX, NY, NZ, PX, PY, PZ, rank, 0, 1.0, 1.0, 0.0};
+    HexBlock b;
+    if (!make_block(s, b)) return 1;
+    sizes[0] = b.N;
+    sizes[1] = b.F;
+    sizes[2] = b.nIf;
+    for (int k = 0; k < 6; ++k) {
+        sizes[3 + k] = k < b.nIf ? b.nbrFaces[k] : 0;
+        sizes[9 + k] = k < b.nIf ? b.nbrRank[k] : -1;
+    }
+    return 0;
+}
+
+// Fills the p_rgh-shaped system of SURVEY.md 8d config 3/4 for one rank's sub-block of the global
+// NX x NY x NZ box (cube cells of edge h):
+//   gamma_c = gamma0 (1 + 0.9 sin2pix sin2piy sin2piz) 10^(0.5 xi_c), gamma_f = (gamma_o+gamma_n)/2
+//   A = diag(psi V/dt) - laplacian(gamma)  [SPD M-matrix form of `- fvm::laplacian`, pEqn.H:32]
+//   y = max patch: fixed value 0 (deltaCoeff 2/h); every other physical patch: zero flux
+//   source = A x*, x* smooth + 1 % noise
+// Outputs (caller-allocated):
+//   lower, upper_addr [F]; gamma_f, magSf, delta [F]  (inputs of b200_assemble_laplacian, sign=-1)
+//   diag0 [N]  = ddt diagonal + boundary internalCoeffs of ALL patches (incl. processor patches)
+//   diag [N], upper [F] = the assembled matrix (what the solver receives)
+//   source [N], xstar [N]
+//   faceCells[k] [nFaces_k], bouCoeffs[k] [nFaces_k] for k < nIfaces (pointers in arrays of 6)
+int b200mesh_hex_fill(int NX, int NY, int NZ, int PX, int PY, int PZ, int rank, uint64_t seed, double h,
+                      double gamma0, double psiOverDt, int32_t* lower, int32_t* upper_addr,
+                      double* gamma_f, double* magSf, double* delta, double* diag0, double* diag,
+                      double* upper, double* source, double* xstar, int32_t* const* faceCells,
+                      double* const* bouCoeffs) {
+    HexSpec s{NX, NY, NZ, PX, PY, PZ, rank, seed, h, gamma0, psiOverDt};
+    HexBlock b;
+    if (!make_block(s, b)) return 1;
+    const int lnx = b.lnx, lny = b.lny, lnz = b.lnz;
+    const double S = h * h, dC = 1.0 / h, V = h * h * h;
+    auto lid = [&](int i, int j, int k) { return (int32_t)(i + lnx * (j + lny * k)); };
+
+    // face offsets: count owner faces per cell in order -> prefix.  Faces of cell (i,j,k) in
+    // ascending neighbour order: +x, +y, +z (those inside the block).
+    std::vector<int64_t> fstart((size_t)lnz + 1, 0);  // per k-plane offsets (all rows alike in count)
+    for (int k = 0; k < lnz; ++k) {
+        int64_t perPlane = (int64_t)(lnx - 1) * lny + (int64_t)lnx * (lny - 1) + (k < lnz - 1 ? (int64_t)lnx * lny : 0);
+        fstart[k + 1] = fstart[k] + perPlane;
+    }
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < lnz; ++k) {
+        int64_t f = fstart[k];
+        const int K = b.rz.lo + k;
+        for (int j = 0; j < lny; ++j) {
+            const int J = b.ry.lo + j;
+            for (int i = 0; i < lnx; ++i) {
+                const int I = b.rx.lo + i;
+                const int32_t c = lid(i, j, k);
+                const double gc = gamma_cell(s, I, J, K);
+                const double xc = xstar_cell(s, I, J, K);
+                double d0 = psiOverDt * V;
+                if (J == NY - 1) d0 += gc * S * (2.0 * dC);  // fixed-value top patch, gamma_b = gamma_c
+                xstar[c] = xc;
+                diag0[c] = d0;
+                auto face = [&](int32_t n, double gn) {
+                    lower[f] = c;
+                    upper_addr[f] = n;
+                    gamma_f[f] = 0.5 * (gc + gn);
+                    magSf[f] = S;
+                    delta[f] = dC;
+                    upper[f] = -1.0 * (dC * (gamma_f[f] * S));
+                    ++f;
+                };
+                if (i < lnx - 1) face(lid(i + 1, j, k), gamma_cell(s, I + 1, J, K));
+                if (j < lny - 1) face(lid(i, j + 1, k), gamma_cell(s, I, J + 1, K));
+                if (k < lnz - 1) face(lid(i, j, k + 1), gamma_cell(s, I, J, K + 1));
+            }
+        }
+    }
+    // interfaces
+    for (int p = 0; p < b.nIf; ++p) {
+        const int dir = b.nbrDir[p];
+        int32_t* fc = faceCells[p];
+        double* bc = bouCoeffs[p];
+        int64_t n = 0;
+        auto emit = [&](int i, int j, int k, int di, int dj, int dk) {
+            const int I = b.rx.lo + i, J = b.ry.lo + j, K = b.rz.lo + k;
+            const double gf = 0.5 * (gamma_cell(s, I, J, K) + gamma_cell(s, I + di, J + dj, K + dk));
+            const double coeff = dC * (gf * S);
+            fc[n] = lid(i, j, k);
+            bc[n] = coeff;            // interfaceBouCoeffs (Amul subtracts bou*psi_nbr)
+            diag0[lid(i, j, k)] += coeff;  // interfaceIntCoeffs folded into diag
+            ++n;
+        };
+        if (dir == 0 || dir == 5) {
+            const int k = dir == 0 ? 0 : lnz - 1, dk = dir == 0 ? -1 : 1;
+            for (int j = 0; j < lny; ++j) for (int i = 0; i < lnx; ++i) emit(i, j, k, 0, 0, dk);
+        } else if (dir == 1 || dir == 4) {
+            const int j = dir == 1 ? 0 : lny - 1, dj = dir == 1 ? -1 : 1;
+            for (int k = 0; k < lnz; ++k) for (int i = 0; i < lnx; ++i) emit(i, j, k, 0, dj, 0);
+        } else {
+            const int i = dir == 2 ? 0 : lnx - 1, di = dir == 2 ? -1 : 1;
+            for (int k = 0; k < lnz; ++k) for (int j = 0; j < lny; ++j) emit(i, j, k, di, 0, 0);
+        }
+    }
+    // diag = diag0 - sum(upper) over the faces of each cell, in face order (negSumDiag of the
+    // negated matrix); source = A x* including the processor-coupled neighbours
+    for (int32_t c = 0; c < b.N; ++c) diag[c] = 0.0;
+    for (int64_t f = 0; f < b.F; ++f) {
+        diag[lower[f]] -= upper[f];
+        diag[upper_addr[f]] -= upper[f];
+    }
+    for (int32_t c = 0; c < b.N; ++c) diag[c] += diag0[c];
+    for (int32_t c = 0; c < b.N; ++c) source[c] = diag[c] * xstar[c];
+    for (int64_t f = 0; f < b.F; ++f) {
+        source[upper_addr[f]] += upper[f] * xstar[lower[f]];
+        source[lower[f]] += upper[f] * xstar[upper_addr[f]];
+    }
+    for (int p = 0; p < b.nIf; ++p) {
+        const int dir = b.nbrDir[p];
+        const int di = dir == 2 ? -1 : dir == 3 ? 1 : 0, dj = dir == 1 ? -1 : dir == 4 ? 1 : 0,
+                  dk = dir == 0 ? -1 : dir == 5 ? 1 : 0;
+        for (int n = 0; n < b.nbrFaces[p]; ++n) {
+            const int32_t c = faceCells[p][n];
+            const int i = c % lnx, j = (c / lnx) % lny, k = c / (lnx * lny);
+            const double xn = xstar_cell(s, b.rx.lo + i + di, b.ry.lo + j + dj, b.rz.lo + k + dk);
+            source[c] -= bouCoeffs[p][n] * xn;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

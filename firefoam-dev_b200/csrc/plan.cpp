@@ -1,0 +1,232 @@
+// plan.cpp -- see plan.hpp.  Host-side, once per mesh.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace b200 {
+
+namespace {
+
+// CSR over natural cells: for cell c the faces in OpenFOAM's own visiting order of
+// lduMatrix::Amul (OF-dev lduMatrixATmul.C): first the faces where c is the
+// neighbour (upperAddr == c; ascending face index == losort order), then the faces c owns.
+struct CellFaces {
+    std::vector<int64_t> start;   // [N+1]
+    std::vector<int32_t> face;    // [2F]
+    std::vector<int32_t> other;   // [2F]
+    std::vector<int32_t> nLowerNat;  // [N] number of faces where c is the neighbour
+};
+
+void build_cell_faces(int32_t N, int32_t F, const int32_t* l, const int32_t* u, CellFaces& cf) {
+    cf.start.assign((size_t)N + 1, 0);
+    cf.nLowerNat.assign((size_t)N, 0);
+    for (int32_t f = 0; f < F; ++f) {
+        cf.start[(size_t)l[f] + 1]++;
+        cf.start[(size_t)u[f] + 1]++;
+        cf.nLowerNat[u[f]]++;
+    }
+    for (int32_t c = 0; c < N; ++c) cf.start[(size_t)c + 1] += cf.start[c];
+    cf.face.resize((size_t)2 * F);
+    cf.other.resize((size_t)2 * F);
+    std::vector<int64_t> posLow(cf.start.begin(), cf.start.end() - 1);
+    std::vector<int64_t> posUp((size_t)N);
+    for (int32_t c = 0; c < N; ++c) posUp[c] = cf.start[c] + cf.nLowerNat[c];
+    for (int32_t f = 0; f < F; ++f) {
+        int64_t a = posUp[l[f]]++;
+        cf.face[a] = f;
+        cf.other[a] = u[f];
+        int64_t b = posLow[u[f]]++;
+        cf.face[b] = f;
+        cf.other[b] = l[f];
+    }
+}
+
+// Greedy sequential multicolouring in natural cell order (first-fit).
+int32_t colour_greedy(int32_t N, const CellFaces& cf, std::vector<int32_t>& colour) {
+    colour.assign((size_t)N, -1);
+    int32_t nCol = 0;
+    std::vector<int32_t> mark;  // mark[k] == c  <=> colour k is used by a neighbour of c
+    for (int32_t c = 0; c < N; ++c) {
+        for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e) {
+            int32_t k = colour[cf.other[e]];
+            if (k >= 0) {
+                if ((size_t)k >= mark.size()) mark.resize((size_t)k + 1, -1);
+                mark[k] = c;
+            }
+        }
+        int32_t k = 0;
+        while ((size_t)k < mark.size() && mark[k] == c) ++k;
+        colour[c] = k;
+        if (k + 1 > nCol) nCol = k + 1;
+        if ((size_t)k >= mark.size()) mark.resize((size_t)k + 1, -1);
+    }
+    return nCol;
+}
+
+// Dependency levels of the natural-order recurrences of DICPreconditioner (OF-dev
+// DICPreconditioner.C): row u depends on every row l < u it shares a face
+// with.  level(u) = 1 + max level(l).  Faces are sorted by l, and every face INTO l has a
+// smaller owner, so one ascending pass over the faces is enough.
+int32_t colour_levels(int32_t N, int32_t F, const int32_t* l, const int32_t* u,
+                      std::vector<int32_t>& colour) {
+    colour.assign((size_t)N, 0);
+    int32_t nLev = N > 0 ? 1 : 0;
+    for (int32_t f = 0; f < F; ++f) {
+        int32_t cand = colour[l[f]] + 1;
+        if (cand > colour[u[f]]) {
+            colour[u[f]] = cand;
+            if (cand + 1 > nLev) nLev = cand + 1;
+        }
+    }
+    return nLev;
+}
+
+}  // namespace
+
+std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P) {
+    if (N < 0 || F < 0 || nIfaces < 0) return "negative size";
+    if (F > 0 && (!l || !u)) return "null lowerAddr/upperAddr";
+    if (nIfaces > 0 && !ifaces) return "null interface list";
+    for (int32_t f = 0; f < F; ++f) {
+        if (l[f] < 0 || u[f] >= N || l[f] >= u[f])
+            return "face " + std::to_string(f) + ": need 0 <= lowerAddr < upperAddr < nCells";
+        if (f > 0 && (l[f] < l[f - 1]))
+            return "face " + std::to_string(f) + ": lowerAddr not in upper-triangular (ascending) order";
+    }
+    for (int32_t k = 0; k < nIfaces; ++k) {
+        if (ifaces[k].nFaces < 0 || (ifaces[k].nFaces > 0 && !ifaces[k].faceCells))
+            return "interface " + std::to_string(k) + ": bad size or null faceCells";
+        for (int32_t i = 0; i < ifaces[k].nFaces; ++i)
+            if (ifaces[k].faceCells[i] < 0 || ifaces[k].faceCells[i] >= N)
+                return "interface " + std::to_string(k) + ": faceCells out of range";
+    }
+
+    P = HostPlan();
+    P.ordering = ordering;
+    P.N = N;
+    P.F = F;
+
+    CellFaces cf;
+    build_cell_faces(N, F, l, u, cf);
+
+    // ---- row order ----------------------------------------------------------------------
+    if (ordering == Ordering::Natural) {
+        P.nColours = 1;
+        P.colourStart = {0, N};
+    } else {
+        std::vector<int32_t> colour;
+        P.nColours = (ordering == Ordering::MultiColour) ? colour_greedy(N, cf, colour)
+                                                        : colour_levels(N, F, l, u, colour);
+        if (N == 0) P.nColours = 1;
+        P.colourStart.assign((size_t)P.nColours + 1, 0);
+        for (int32_t c = 0; c < N; ++c) P.colourStart[(size_t)colour[c] + 1]++;
+        for (int32_t k = 0; k < P.nColours; ++k) P.colourStart[k + 1] += P.colourStart[k];
+        P.perm.resize((size_t)N);
+        P.iperm.resize((size_t)N);
+        std::vector<int32_t> pos(P.colourStart.begin(), P.colourStart.end() - 1);
+        for (int32_t c = 0; c < N; ++c) {  // stable: natural order inside a colour
+            int32_t r = pos[colour[c]]++;
+            P.perm[r] = c;
+            P.iperm[c] = r;
+        }
+    }
+    const bool ident = P.perm.empty();
+    auto rowOf = [&](int32_t c) { return ident ? c : P.iperm[c]; };
+    auto cellOf = [&](int32_t r) { return ident ? r : P.perm[r]; };
+
+    // ---- sliced ELL ---------------------------------------------------------------------
+    P.nSlices = (N + 31) / 32;
+    P.sliceBase.assign((size_t)P.nSlices + 1, 0);
+    P.rowLen.assign((size_t)N, 0);
+    for (int32_t s = 0; s < P.nSlices; ++s) {
+        int64_t mx = 0;
+        for (int32_t r = s * 32; r < std::min(N, s * 32 + 32); ++r) {
+            int32_t c = cellOf(r);
+            int64_t len = cf.start[c + 1] - cf.start[c];
+            if (len > 65535) return "row with more than 65535 faces is unsupported";
+            mx = std::max(mx, len);
+        }
+        P.sliceBase[s + 1] = P.sliceBase[s] + mx * 32;
+    }
+    P.nEntries = P.sliceBase[P.nSlices];
+    if (P.nEntries > (int64_t)0x7fffffff0LL) return "matrix too large";
+    P.col.resize((size_t)P.nEntries);
+    P.faceOf.assign((size_t)P.nEntries, -1);
+#pragma omp parallel
+    {
+        std::vector<std::pair<int32_t, int32_t>> ent;  // (face, other row)
+#pragma omp for schedule(static)
+        for (int32_t r = 0; r < N; ++r) {
+            const int32_t c = cellOf(r);
+            const int64_t base = P.sliceBase[r / 32] + (r % 32);
+            const int64_t width = (P.sliceBase[r / 32 + 1] - P.sliceBase[r / 32]) / 32;
+            int32_t j = 0, nLower = 0;
+            // cf lists the faces where c is the neighbour (ascending), then the faces c owns
+            // (ascending).  In natural order that already is [earlier | later], each ascending;
+            // in a permuted order re-sort the few entries by face and split by row index.
+            const int64_t e0 = cf.start[c], e1 = cf.start[c + 1];
+            ent.clear();
+            for (int64_t e = e0; e < e1; ++e) ent.emplace_back(cf.face[e], rowOf(cf.other[e]));
+            if (!ident) std::sort(ent.begin(), ent.end());
+            for (auto& fe : ent)
+                if (fe.second < r) {
+                    P.col[base + 32 * (int64_t)j] = fe.second;
+                    P.faceOf[base + 32 * (int64_t)j] = fe.first;
+                    ++j;
+                    ++nLower;
+                }
+            for (auto& fe : ent)
+                if (fe.second > r) {
+                    P.col[base + 32 * (int64_t)j] = fe.second;
+                    P.faceOf[base + 32 * (int64_t)j] = fe.first;
+                    ++j;
+                }
+            P.rowLen[r] = (uint32_t)nLower | ((uint32_t)j << 16);
+            for (int64_t jj = j; jj < width; ++jj) P.col[base + 32 * jj] = r;
+        }
+    }
+    // padding rows of the last slice
+    for (int64_t r = N; r < (int64_t)P.nSlices * 32; ++r) {
+        const int64_t base = P.sliceBase[r / 32] + (r % 32);
+        const int64_t width = (P.sliceBase[r / 32 + 1] - P.sliceBase[r / 32]) / 32;
+        for (int64_t jj = 0; jj < width; ++jj) P.col[base + 32 * jj] = 0;
+    }
+
+    // ---- interfaces ---------------------------------------------------------------------
+    P.nIfaces = nIfaces;
+    P.nbrRank.resize((size_t)nIfaces);
+    P.patchStart.assign((size_t)nIfaces + 1, 0);
+    for (int32_t k = 0; k < nIfaces; ++k) {
+        P.nbrRank[k] = ifaces[k].nbrRank;
+        P.patchStart[k + 1] = P.patchStart[k] + ifaces[k].nFaces;
+    }
+    const int32_t nSlots = P.patchStart[nIfaces];
+    P.slotRow.resize((size_t)nSlots);
+    for (int32_t k = 0; k < nIfaces; ++k)
+        for (int32_t i = 0; i < ifaces[k].nFaces; ++i)
+            P.slotRow[P.patchStart[k] + i] = rowOf(ifaces[k].faceCells[i]);
+    // CSR row -> slots; stable sort keeps (patch, face) order inside a row, which is the
+    // order of OpenFOAM's updateMatrixInterfaces loop over patches
+    std::vector<int32_t> order((size_t)nSlots);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int32_t a, int32_t b) { return P.slotRow[a] < P.slotRow[b]; });
+    P.bSlot = order;
+    P.bRow.clear();
+    P.bStart.clear();
+    for (int32_t i = 0; i < nSlots; ++i) {
+        int32_t r = P.slotRow[order[i]];
+        if (P.bRow.empty() || P.bRow.back() != r) {
+            P.bRow.push_back(r);
+            P.bStart.push_back(i);
+        }
+    }
+    P.bStart.push_back(nSlots);
+    P.nBRows = (int32_t)P.bRow.size();
+    return std::string();
+}
+
+}  // namespace b200

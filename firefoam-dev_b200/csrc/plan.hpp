@@ -1,0 +1,66 @@
+// plan.hpp -- host-side, once-per-mesh preparation of the device row structure.
+//
+// Replaces the lazily-built parts of OpenFOAM's lduAddressing (ownerStartAddr, losortAddr,
+// losortStartAddr; OF-dev lduAddressing.C) by ONE structure that serves
+// Amul, sumA, negSumDiag, the DIC-class sweeps and the halo fix-up:
+//
+//   * an internal row order: natural (diagonal / none) or colour-major (DIC-class: greedy
+//     multicolouring; DIC-exact: dependency levels of OpenFOAM's own face-order recurrences),
+//   * a full-row sliced-ELL layout (slice height 32 = one warp; entry j of row r lives at
+//     sliceBase[r/32] + 32*j + r%32, so a warp's j-th loads are one contiguous 128/256-byte
+//     line), entries grouped [neighbours earlier in elimination order | later ones], each
+//     group in ascending natural face order so that row sums are formed in exactly the order
+//     of OpenFOAM's face loops,
+//   * for every entry the natural face whose `upper` value it carries (value fill is a pure
+//     gather, once per solve),
+//   * the processor-interface rows as a CSR (row -> (patch-face slot) list) so that the halo
+//     fix-up is a sorted-segment reduction, never an atomic.
+//
+// Pure C++ (no CUDA) so that tests can validate it on a CPU-only box.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+enum class Ordering : int { Natural = 0, MultiColour = 1, Levels = 2 };
+
+struct IfaceIn {
+    int32_t nbrRank;
+    int32_t nFaces;
+    const int32_t* faceCells;
+};
+
+struct HostPlan {
+    Ordering ordering = Ordering::Natural;
+    int32_t N = 0, F = 0;
+    // row order
+    std::vector<int32_t> perm;         // internal row -> natural cell  (empty == identity)
+    std::vector<int32_t> iperm;        // natural cell -> internal row  (empty == identity)
+    int32_t nColours = 1;
+    std::vector<int32_t> colourStart;  // [nColours+1] internal row offsets
+    // sliced ELL, both triangles
+    int32_t nSlices = 0;
+    int64_t nEntries = 0;              // padded
+    std::vector<int64_t> sliceBase;    // [nSlices+1]
+    std::vector<uint32_t> rowLen;      // [N]  nLower | nTotal<<16
+    std::vector<int32_t> col;          // [nEntries] internal column (padding: the row itself)
+    std::vector<int32_t> faceOf;       // [nEntries] natural face index, -1 for padding
+    // interfaces (internal numbering); slot = position in the concatenation of all patches
+    int32_t nIfaces = 0;
+    std::vector<int32_t> nbrRank;      // [nIfaces]
+    std::vector<int32_t> patchStart;   // [nIfaces+1] slot offsets
+    std::vector<int32_t> slotRow;      // [nSlots] internal row of patch face (pack list)
+    int32_t nBRows = 0;
+    std::vector<int32_t> bRow;         // [nBRows] distinct interface rows, ascending
+    std::vector<int32_t> bStart;       // [nBRows+1]
+    std::vector<int32_t> bSlot;        // [nSlots] slots of each row, (patch, face) ascending
+};
+
+// Validates the LDU addressing (sizes, l<u, upper-triangular order) and builds the plan.
+// Returns empty string on success, else an error message.
+std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& out);
+
+}  // namespace b200

@@ -1,0 +1,831 @@
+// solver.cu -- context, device-resident PCG driver and the C ABI of include/b200pcg.h.
+//
+// Host side of the hot path: replaces PCG::solve's control flow (OF-dev PCG.C),
+// lduMatrix::solver::normFactor (lduMatrixSolver.C), the interface update protocol
+// (lduMatrixUpdateMatrixInterfaces.C / processorFvPatchField.C) and Pstream's reduce()
+// (UPstream.C).  The CG scalars (alpha, beta, residuals, iteration counter, convergence flag)
+// live in device memory and are advanced by the kernels themselves; the host only enqueues
+// batches of iterations and polls a 200-byte status block, so the loop stops at exactly the
+// iteration OpenFOAM's do/while would stop at, with no per-iteration host round trip.
+//
+// There is NO CPU fallback: every entry point fails with B200_ENODEVICE / B200_ECUDA when the
+// device is unusable.
+#include "../../include/b200pcg.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_createError;
+
+enum ProfClass : int {
+    PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
+    PC_PRECOND_DOT, PC_PUPDATE, PC_UPDATE, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
+    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_COUNT
+};
+const char* kProfNames[PC_COUNT] = {
+    "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
+    "norm_resid", "recip", "precond_dot", "p_update", "update_psi_r", "dic_calc_rd", "dic_fwd",
+    "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step"};
+
+struct DevPlan {
+    bool built = false;
+    HostPlan h;   // big arrays are released after upload; sizes/colourStart stay
+    int64_t* sliceBase = nullptr;
+    uint32_t* rowLen = nullptr;
+    int* col = nullptr;
+    int* faceOf = nullptr;
+    double* val = nullptr;
+    int* perm = nullptr;
+    int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
+    int nSlots = 0;
+};
+
+struct HostIface {
+    int32_t nbrRank;
+    std::vector<int32_t> faceCells;
+};
+
+}  // namespace
+
+struct b200_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t sc = nullptr, sm = nullptr;
+    cudaEvent_t evPack = nullptr, evRecv = nullptr, ev[6] = {};
+    std::string err;
+    int numSMs = 148;
+    // mesh
+    bool haveMesh = false;
+    uint64_t meshKey = 0;
+    int32_t N = 0, F = 0;
+    double nGlobalCells = 0;
+    std::vector<int32_t> hl, hu;
+    std::vector<HostIface> hif;
+    int *d_l = nullptr, *d_u = nullptr;
+    DevPlan plans[3];
+    int nSlots = 0;
+    // vectors (internal order)
+    double *diag = nullptr, *src = nullptr, *psi = nullptr, *r = nullptr, *p = nullptr,
+           *w = nullptr, *rD = nullptr;
+    double *bou = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
+    // staging for the host entry points (natural order)
+    double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
+           *in_bou = nullptr, *in_f1 = nullptr, *in_f2 = nullptr, *in_f3 = nullptr;
+    Scalars* S = nullptr;
+    Scalars* hS = nullptr;  // pinned
+    double* partials = nullptr;
+    uint64_t launches = 0;
+    int32_t forceIters = 0;
+    // profiling
+    bool prof = false;
+    bool profOpen = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> profRecs;
+    std::vector<cudaEvent_t> profPool;
+    size_t profUsed = 0;
+    double profMs[PC_COUNT] = {};
+    uint64_t profN[PC_COUNT] = {};
+    std::string profJson;
+};
+
+namespace {
+
+int fail(b200_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_createError = msg;
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(ctx, B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define NC(call)                                                                         \
+    do {                                                                                 \
+        ncclResult_t e_ = (call);                                                        \
+        if (e_ != ncclSuccess)                                                           \
+            return fail(ctx, B200_ENCCL, std::string(#call) + ": " + ncclGetErrorString(e_)); \
+    } while (0)
+#define RET(call)                        \
+    do {                                 \
+        int rc_ = (call);                \
+        if (rc_ != B200_OK) return rc_;  \
+    } while (0)
+
+template <class T>
+int dev_alloc(b200_ctx* ctx, T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc((void**)p, n * sizeof(T)));
+    return B200_OK;
+}
+template <class T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+template <class T>
+int upload(b200_ctx* ctx, T** d, const std::vector<T>& h) {
+    RET(dev_alloc(ctx, d, h.size()));
+    if (!h.empty())
+        CU(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->sc));
+    return B200_OK;
+}
+
+void prof_begin(b200_ctx* c, int cls) {
+    c->profOpen = false;
+    if (!c->prof || c->profUsed + 2 > c->profPool.size()) return;
+    c->profOpen = true;
+    b200_ctx::ProfRec r{cls, c->profPool[c->profUsed], c->profPool[c->profUsed + 1]};
+    c->profUsed += 2;
+    cudaEventRecord(r.a, c->sc);
+    c->profRecs.push_back(r);
+}
+void prof_end(b200_ctx* c, int cls) {
+    if (!c->prof || !c->profOpen || c->profRecs.empty()) return;
+    c->profOpen = false;
+    auto& r = c->profRecs.back();
+    if (r.cls == cls && r.b) cudaEventRecord(r.b, c->sc);
+}
+void prof_collect(b200_ctx* c) {
+    if (!c->prof) return;
+    cudaStreamSynchronize(c->sc);
+    for (auto& r : c->profRecs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            c->profMs[r.cls] += ms;
+            c->profN[r.cls]++;
+        }
+    }
+    c->profRecs.clear();
+    c->profUsed = 0;
+}
+
+#define LAUNCH(cls, kern, grid, ...)                             \
+    do {                                                         \
+        prof_begin(ctx, cls);                                    \
+        kern<<<(grid), kBlock, 0, ctx->sc>>>(__VA_ARGS__);       \
+        prof_end(ctx, cls);                                      \
+        ctx->launches++;                                         \
+    } while (0)
+
+inline int grid_for(const b200_ctx* c, int64_t items, int perSM = 8) {
+    int64_t g = (items + kBlock - 1) / kBlock;
+    int64_t cap = (int64_t)c->numSMs * perSM;
+    if (cap > kMaxGrid) cap = kMaxGrid;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+void free_plan(DevPlan& P) {
+    dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
+    dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
+    dev_free(P.bStart); dev_free(P.bSlot);
+    P.built = false;
+    P.h = HostPlan();
+}
+
+void free_mesh(b200_ctx* c) {
+    for (auto& P : c->plans) free_plan(P);
+    dev_free(c->d_l); dev_free(c->d_u);
+    dev_free(c->diag); dev_free(c->src); dev_free(c->psi); dev_free(c->r); dev_free(c->p);
+    dev_free(c->w); dev_free(c->rD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
+    dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
+    dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3);
+    c->haveMesh = false;
+    c->hl.clear(); c->hu.clear(); c->hif.clear();
+}
+
+int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
+    DevPlan& P = ctx->plans[(int)ord];
+    *out = &P;
+    if (P.built) return B200_OK;
+    std::vector<IfaceIn> ifs(ctx->hif.size());
+    for (size_t k = 0; k < ifs.size(); ++k)
+        ifs[k] = IfaceIn{ctx->hif[k].nbrRank, (int32_t)ctx->hif[k].faceCells.size(),
+                         ctx->hif[k].faceCells.data()};
+    std::string e = build_plan(ord, ctx->N, ctx->F, ctx->hl.data(), ctx->hu.data(),
+                               (int32_t)ifs.size(), ifs.data(), P.h);
+    if (!e.empty()) return fail(ctx, B200_EINVAL, "set_addressing: " + e);
+    RET(upload(ctx, &P.sliceBase, P.h.sliceBase));
+    RET(upload(ctx, &P.rowLen, P.h.rowLen));
+    RET(upload(ctx, &P.col, P.h.col));
+    RET(upload(ctx, &P.faceOf, P.h.faceOf));
+    RET(dev_alloc(ctx, &P.val, (size_t)P.h.nEntries));
+    if (!P.h.perm.empty()) RET(upload(ctx, &P.perm, P.h.perm));
+    RET(upload(ctx, &P.slotRow, P.h.slotRow));
+    RET(upload(ctx, &P.bRow, P.h.bRow));
+    RET(upload(ctx, &P.bStart, P.h.bStart));
+    RET(upload(ctx, &P.bSlot, P.h.bSlot));
+    P.nSlots = (int)P.h.slotRow.size();
+    CU(cudaStreamSynchronize(ctx->sc));
+    // release the big host arrays
+    std::vector<int32_t>().swap(P.h.col);
+    std::vector<int32_t>().swap(P.h.faceOf);
+    std::vector<uint32_t>().swap(P.h.rowLen);
+    std::vector<int64_t>().swap(P.h.sliceBase);
+    std::vector<int32_t>().swap(P.h.perm);
+    std::vector<int32_t>().swap(P.h.iperm);
+    std::vector<int32_t>().swap(P.h.slotRow);
+    std::vector<int32_t>().swap(P.h.bSlot);
+    P.built = true;
+    return B200_OK;
+}
+
+int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
+    Scalars& h = *ctx->hS;
+    std::memset(&h, 0, sizeof(Scalars));
+    h.tol = ctl ? ctl->tolerance : 0.0;
+    h.relTol = ctl ? ctl->relTol : 0.0;
+    h.maxIter = ctl ? ctl->maxIter : 0;
+    h.minIter = ctl ? ctl->minIter : 0;
+    h.forceIters = ctx->forceIters;
+    h.nranks = ctx->nranks;
+    h.nGlobalCells = ctx->nGlobalCells;
+    h.wArA = 1e20;
+    h.wArAold = 1e20;
+    CU(cudaMemcpyAsync(ctx->S, ctx->hS, sizeof(Scalars), cudaMemcpyHostToDevice, ctx->sc));
+    return B200_OK;
+}
+
+// after a reducing kernel with a step: all-reduce + scalar step when nranks > 1
+int reduce_post(b200_ctx* ctx, int step) {
+    if (ctx->nranks == 1) return B200_OK;
+    NC(ncclAllReduce(ctx->S->sums, ctx->S->gsums, kNSums, ncclDouble, ncclSum, ctx->comm, ctx->sc));
+    LAUNCH(PC_SCALAR, k_scalar_step, 1, ctx->S, step);
+    return B200_OK;
+}
+
+// y = A x (+ interfaces) [+ (y,x) -> step]; INIT: also sA = sumA
+template <bool INIT, bool DOT>
+int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA, int step) {
+    const int N = ctx->N;
+    const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
+    if (halo) {
+        LAUNCH(PC_PACK, k_pack, grid_for(ctx, P.nSlots), P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
+        CU(cudaEventRecord(ctx->evPack, ctx->sc));
+        CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
+        NC(ncclGroupStart());
+        for (int k = 0; k < P.h.nIfaces; ++k) {
+            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+            if (n == 0) continue;
+            NC(ncclSend(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+            NC(ncclRecv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+        }
+        NC(ncclGroupEnd());
+        CU(cudaEventRecord(ctx->evRecv, ctx->sm));
+    }
+    Reduce R{ctx->S, ctx->partials, halo ? STEP_NONE : step};
+    auto kern = k_spmv<INIT, DOT>;
+    LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.col,
+           P.val, ctx->diag, x, y, sA, R);
+    if (halo) {
+        CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
+        Reduce R2{ctx->S, ctx->partials, step};
+        auto fix = k_iface_fix<0, DOT>;
+        LAUNCH(PC_IFACE, fix, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot,
+               ctx->bou, ctx->recvbuf, x, y, R2);
+        if (INIT) {
+            auto fix1 = k_iface_fix<1, false>;
+            LAUNCH(PC_IFACE, fix1, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart,
+                   P.bSlot, ctx->bou, ctx->recvbuf, x, sA, R2);
+        }
+    }
+    if (DOT) RET(reduce_post(ctx, step));
+    return B200_OK;
+}
+
+int alloc_vectors(b200_ctx* ctx) {
+    const size_t n = (size_t)ctx->N + 2;
+    RET(dev_alloc(ctx, &ctx->diag, n)); RET(dev_alloc(ctx, &ctx->src, n));
+    RET(dev_alloc(ctx, &ctx->psi, n));  RET(dev_alloc(ctx, &ctx->r, n));
+    RET(dev_alloc(ctx, &ctx->p, n));    RET(dev_alloc(ctx, &ctx->w, n));
+    RET(dev_alloc(ctx, &ctx->rD, n));
+    const size_t ns = (size_t)ctx->nSlots;
+    RET(dev_alloc(ctx, &ctx->bou, ns)); RET(dev_alloc(ctx, &ctx->sendbuf, ns));
+    RET(dev_alloc(ctx, &ctx->recvbuf, ns));
+    return B200_OK;
+}
+
+int ensure_staging(b200_ctx* ctx, bool faceTemps) {
+    if (!ctx->in_diag) {
+        RET(dev_alloc(ctx, &ctx->in_diag, (size_t)ctx->N)); RET(dev_alloc(ctx, &ctx->in_src, (size_t)ctx->N));
+        RET(dev_alloc(ctx, &ctx->in_psi, (size_t)ctx->N));  RET(dev_alloc(ctx, &ctx->in_upper, (size_t)ctx->F));
+        RET(dev_alloc(ctx, &ctx->in_bou, (size_t)ctx->nSlots));
+    }
+    if (faceTemps && !ctx->in_f1) {
+        RET(dev_alloc(ctx, &ctx->in_f1, (size_t)ctx->F)); RET(dev_alloc(ctx, &ctx->in_f2, (size_t)ctx->F));
+        RET(dev_alloc(ctx, &ctx->in_f3, (size_t)ctx->F));
+    }
+    return B200_OK;
+}
+
+// gather the matrix/vectors of one solve into the plan's internal layout
+int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* dn_upper,
+                const double* dn_src, const double* dn_psi) {
+    const int N = ctx->N;
+    LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
+    LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_diag, ctx->diag);
+    if (dn_src) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_src, ctx->src);
+    if (dn_psi) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_psi, ctx->psi);
+    return B200_OK;
+}
+
+int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
+    const int N = ctx->N;
+    Scalars* S = ctx->S;
+    const double* z = ctx->w;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    if (precond == B200_PRECOND_NONE) {
+        Reduce R{S, ctx->partials, STEP_WARA};
+        auto k = k_precond_dot<false>;
+        LAUNCH(PC_PRECOND_DOT, k, gv, N, (const double*)nullptr, ctx->r, (double*)nullptr, R);
+        z = ctx->r;
+    } else if (precond == B200_PRECOND_DIAGONAL) {
+        Reduce R{S, ctx->partials, STEP_WARA};
+        auto k = k_precond_dot<true>;
+        LAUNCH(PC_PRECOND_DOT, k, gv, N, ctx->rD, ctx->r, ctx->w, R);
+    } else {
+        const int C = P.h.nColours;
+        for (int k = 0; k < C; ++k) {
+            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+            const bool last = (k == C - 1);
+            Reduce R{S, ctx->partials, (last && C == 1) ? STEP_WARA : STEP_NONE};
+            if (last) {
+                auto kf = k_dic_fwd<true>;
+                LAUNCH(PC_DIC_FWD, kf, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen, P.col,
+                       P.val, ctx->rD, ctx->r, ctx->w, R);
+            } else {
+                auto kf = k_dic_fwd<false>;
+                LAUNCH(PC_DIC_FWD, kf, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen, P.col,
+                       P.val, ctx->rD, ctx->r, ctx->w, R);
+            }
+        }
+        for (int k = C - 2; k >= 0; --k) {
+            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+            Reduce R{S, ctx->partials, k == 0 ? STEP_WARA : STEP_NONE};
+            LAUNCH(PC_DIC_BWD, k_dic_bwd, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen,
+                   P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
+        }
+    }
+    RET(reduce_post(ctx, STEP_WARA));
+    LAUNCH(PC_PUPDATE, k_pupdate, gv, N, z, ctx->p, S);
+    RET((spmv_full<false, true>(ctx, P, ctx->p, ctx->w, nullptr, STEP_WAPA)));
+    Reduce R{S, ctx->partials, STEP_RES};
+    LAUNCH(PC_UPDATE, k_update, gv, N, ctx->psi, ctx->r, ctx->p, ctx->w, R);
+    RET(reduce_post(ctx, STEP_RES));
+    return B200_OK;
+}
+
+int copy_bou(b200_ctx* ctx, DevPlan& P, const double* const* bouPtrs, cudaMemcpyKind kind, double* dst) {
+    for (int k = 0; k < P.h.nIfaces; ++k) {
+        const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+        if (n == 0) continue;
+        if (!bouPtrs || !bouPtrs[k]) return fail(ctx, B200_EINVAL, "null interfaceBouCoeffs entry");
+        CU(cudaMemcpyAsync(dst + off, bouPtrs[k], (size_t)n * sizeof(double), kind, ctx->sc));
+    }
+    return B200_OK;
+}
+
+Ordering ordering_for(int precond) {
+    if (precond == B200_PRECOND_DIC_MC) return Ordering::MultiColour;
+    if (precond == B200_PRECOND_DIC_EXACT) return Ordering::Levels;
+    return Ordering::Natural;
+}
+
+// The solve proper; all pointers are device pointers in natural order; bou already in ctx->bou.
+int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_src,
+               double* dn_psi, const b200_controls* ctl, b200_perf* perf) {
+    if (ctl->precond < 0 || ctl->precond > 3) return fail(ctx, B200_EINVAL, "bad preconditioner code");
+    if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_controls.reserved must be 0");
+    DevPlan* Pp = nullptr;
+    RET(ensure_plan(ctx, ordering_for(ctl->precond), &Pp));
+    DevPlan& P = *Pp;
+    const int N = ctx->N;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    Scalars* S = ctx->S;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    RET(reset_scalars(ctx, ctl));
+    RET(load_system(ctx, P, dn_diag, dn_upper, dn_src, dn_psi));
+    // wA = A psi, sumA -> pA (OpenFOAM also uses pA as the normFactor temporary)
+    RET((spmv_full<true, false>(ctx, P, ctx->psi, ctx->w, ctx->p, STEP_NONE)));
+    {
+        Reduce R{S, ctx->partials, STEP_SUMPSI};
+        LAUNCH(PC_SUM, k_sum, gv, N, ctx->psi, R);
+        RET(reduce_post(ctx, STEP_SUMPSI));
+    }
+    {
+        Reduce R{S, ctx->partials, STEP_NORM};
+        LAUNCH(PC_NORM, k_norm_resid, gv, N, ctx->w, ctx->p, ctx->src, ctx->r, R);
+        RET(reduce_post(ctx, STEP_NORM));
+    }
+    // preconditioner set-up
+    if (ctl->precond == B200_PRECOND_DIAGONAL) {
+        LAUNCH(PC_RECIP, k_recip, gv, N, ctx->diag, ctx->rD);
+    } else if (ctl->precond >= B200_PRECOND_DIC_MC) {
+        for (int k = 0; k < P.h.nColours; ++k) {
+            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+            LAUNCH(PC_DIC_RD, k_dic_calc_rd, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen,
+                   P.col, P.val, ctx->diag, ctx->rD);
+        }
+        LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->sc));
+    CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+
+    // PCG loop: batches of iterations, device decides when to stop
+    int64_t cap = ctx->forceIters > 0 ? ctx->forceIters
+                                      : std::max<int64_t>((int64_t)ctl->maxIter + 1, ctl->minIter);
+    int64_t enq = 0;
+    int chunk = 4;
+    while (!ctx->hS->done && enq < cap) {
+        int n = (int)std::min<int64_t>(chunk, cap - enq);
+        for (int i = 0; i < n; ++i) RET(enqueue_iteration(ctx, P, ctl->precond));
+        enq += n;
+        CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+        CU(cudaStreamSynchronize(ctx->sc));
+        CU(cudaGetLastError());
+        if (chunk < 64) chunk *= 2;
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->sc));
+    LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+
+    const Scalars& h = *ctx->hS;
+    if (perf) {
+        std::memset(perf, 0, sizeof(*perf));
+        perf->initialResidual = h.initRes;
+        perf->finalResidual = h.finalRes;
+        perf->normFactor = h.normFactor;
+        perf->nIterations = h.nIter;
+        perf->converged = h.converged;
+        perf->singular = h.singular;
+        perf->nColours = P.h.nColours;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        perf->setupMs = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+        perf->solveMs = ms;
+    }
+    if (h.nonfinite) return fail(ctx, B200_ENONFINITE, "non-finite residual in PCG");
+    return B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* b200_last_error(const b200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_createError.c_str();
+}
+
+int b200_get_unique_id(void* uid128) {
+    b200_ctx* ctx = nullptr;
+    if (!uid128) return fail(ctx, B200_EINVAL, "null uid buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    std::memcpy(uid128, &id, 128);
+    return B200_OK;
+}
+
+int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200_ctx** out) {
+    b200_ctx* ctx = nullptr;
+    if (!out) return fail(ctx, B200_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, B200_EINVAL, "bad rank/nranks");
+    if (nranks > 1 && !nccl_uid) return fail(ctx, B200_EINVAL, "nranks > 1 needs an NCCL unique id");
+    int ndev = b200_device_count();
+    if (ndev <= 0)
+        return fail(ctx, B200_ENODEVICE, "no CUDA device: libb200pcg has no CPU fallback");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) return fail(ctx, B200_EINVAL, "device index out of range");
+    b200_ctx* c = new b200_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    auto bail = [&](int code, const std::string& m) {
+        g_createError = m;
+        b200_ctx_destroy(c);
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(B200_ECUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return bail(B200_ECUDA, cudaGetErrorString(e));
+    if (prop.major < 10)
+        return bail(B200_ENODEVICE, std::string("device is ") + prop.name +
+                                        " (sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                        "); libb200pcg is built for sm_100a only");
+    c->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->sm, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->evRecv, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(B200_ECUDA, cudaGetErrorString(e));
+    for (auto& ev : c->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(B200_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc((void**)&c->S, sizeof(Scalars))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->partials, sizeof(double) * kNSums * kMaxGrid)) != cudaSuccess ||
+        (e = cudaHostAlloc((void**)&c->hS, sizeof(Scalars), cudaHostAllocDefault)) != cudaSuccess)
+        return bail(B200_ECUDA, cudaGetErrorString(e));
+    cudaMemset(c->S, 0, sizeof(Scalars));
+    cudaMemset(c->partials, 0, sizeof(double) * kNSums * kMaxGrid);
+    if (nranks > 1) {
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_uid, 128);
+        ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) return bail(B200_ENCCL, ncclGetErrorString(r));
+    }
+    *out = c;
+    return B200_OK;
+}
+
+void b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->sc) cudaStreamSynchronize(c->sc);
+    if (c->sm) cudaStreamSynchronize(c->sm);
+    free_mesh(c);
+    if (c->comm) ncclCommDestroy(c->comm);
+    for (auto ev : c->profPool) cudaEventDestroy(ev);
+    dev_free(c->S);
+    dev_free(c->partials);
+    if (c->hS) cudaFreeHost(c->hS);
+    if (c->evPack) cudaEventDestroy(c->evPack);
+    if (c->evRecv) cudaEventDestroy(c->evRecv);
+    for (auto ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->sc) cudaStreamDestroy(c->sc);
+    if (c->sm) cudaStreamDestroy(c->sm);
+    delete c;
+}
+
+int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_t nFaces,
+                        const int32_t* lowerAddr, const int32_t* upperAddr, int32_t nIfaces,
+                        const b200_iface* ifaces) {
+    if (!ctx) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->haveMesh && ctx->meshKey == mesh_key && ctx->N == nCells && ctx->F == nFaces &&
+        (int32_t)ctx->hif.size() == nIfaces)
+        return B200_OK;
+    if (nCells < 0 || nFaces < 0 || nIfaces < 0) return fail(ctx, B200_EINVAL, "negative size");
+    if (nFaces > 0 && (!lowerAddr || !upperAddr)) return fail(ctx, B200_EINVAL, "null addressing");
+    if (nIfaces > 0 && !ifaces) return fail(ctx, B200_EINVAL, "null interface list");
+    if (ctx->nranks == 1 && nIfaces > 0)
+        return fail(ctx, B200_EINVAL, "processor interfaces given but the context has nranks == 1");
+    CU(cudaStreamSynchronize(ctx->sc));
+    free_mesh(ctx);
+    ctx->N = nCells;
+    ctx->F = nFaces;
+    ctx->hl.assign(lowerAddr, lowerAddr + nFaces);
+    ctx->hu.assign(upperAddr, upperAddr + nFaces);
+    ctx->hif.resize((size_t)nIfaces);
+    ctx->nSlots = 0;
+    for (int k = 0; k < nIfaces; ++k) {
+        if (ifaces[k].nFaces < 0 || (ifaces[k].nFaces > 0 && !ifaces[k].faceCells))
+            return fail(ctx, B200_EINVAL, "bad interface");
+        if (ifaces[k].nbrRank < 0 || ifaces[k].nbrRank >= ctx->nranks || ifaces[k].nbrRank == ctx->rank)
+            return fail(ctx, B200_EINVAL, "interface neighbour rank out of range");
+        ctx->hif[k].nbrRank = ifaces[k].nbrRank;
+        ctx->hif[k].faceCells.assign(ifaces[k].faceCells, ifaces[k].faceCells + ifaces[k].nFaces);
+        ctx->nSlots += ifaces[k].nFaces;
+    }
+    DevPlan* P = nullptr;
+    int rc = ensure_plan(ctx, Ordering::Natural, &P);
+    if (rc != B200_OK) { free_mesh(ctx); return rc; }
+    RET(upload(ctx, &ctx->d_l, ctx->hl));
+    RET(upload(ctx, &ctx->d_u, ctx->hu));
+    RET(alloc_vectors(ctx));
+    // global cell count for gAverage
+    ctx->nGlobalCells = (double)nCells;
+    if (ctx->nranks > 1) {
+        double* tmp = ctx->partials;
+        double h = (double)nCells;
+        CU(cudaMemcpyAsync(tmp, &h, sizeof(double), cudaMemcpyHostToDevice, ctx->sc));
+        NC(ncclAllReduce(tmp, tmp + 1, 1, ncclDouble, ncclSum, ctx->comm, ctx->sc));
+        CU(cudaMemcpyAsync(&h, tmp + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
+        CU(cudaStreamSynchronize(ctx->sc));
+        ctx->nGlobalCells = h;
+    }
+    CU(cudaStreamSynchronize(ctx->sc));
+    ctx->meshKey = mesh_key;
+    ctx->haveMesh = true;
+    return B200_OK;
+}
+
+int b200_assemble_laplacian_device(b200_ctx* ctx, const double* g, const double* s, const double* d,
+                                   double sign, double* upper_out, double* diag_inout) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "assemble before set_addressing");
+    if ((ctx->F > 0 && (!g || !s || !d || !upper_out)) || (ctx->N > 0 && !diag_inout))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    DevPlan& P = ctx->plans[0];
+    LAUNCH(PC_ASM_FACE, k_face_coeff, grid_for(ctx, ctx->F, 16), ctx->F, g, s, d, sign, upper_out);
+    LAUNCH(PC_ASM_DIAG, k_neg_sum_diag, grid_for(ctx, ctx->N, 16), ctx->N, P.sliceBase, P.rowLen,
+           P.faceOf, upper_out, diag_inout);
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+    return B200_OK;
+}
+
+int b200_assemble_laplacian(b200_ctx* ctx, const double* g, const double* s, const double* d,
+                            double sign, double* upper_out, double* diag_inout) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "assemble before set_addressing");
+    if ((ctx->F > 0 && (!g || !s || !d || !upper_out)) || (ctx->N > 0 && !diag_inout))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, true));
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    CU(cudaMemcpyAsync(ctx->in_f1, g, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_f2, s, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_f3, d, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_diag, diag_inout, nb, cudaMemcpyHostToDevice, ctx->sc));
+    RET(b200_assemble_laplacian_device(ctx, ctx->in_f1, ctx->in_f2, ctx->in_f3, sign, ctx->in_upper,
+                                       ctx->in_diag));
+    CU(cudaMemcpyAsync(upper_out, ctx->in_upper, fb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaMemcpyAsync(diag_inout, ctx->in_diag, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    return B200_OK;
+}
+
+int b200_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper,
+                      const double* const* d_bou, const double* d_source, double* d_psi,
+                      const b200_controls* ctl, b200_perf* perf) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!d_diag || !d_source || !d_psi)) || (ctx->F > 0 && !d_upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(copy_bou(ctx, ctx->plans[0], d_bou, cudaMemcpyDeviceToDevice, ctx->bou));
+    return solve_core(ctx, d_diag, d_upper, d_source, d_psi, ctl, perf);
+}
+
+int b200_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* const* bou,
+               const double* source, double* psi, const b200_controls* ctl, b200_perf* perf) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!diag || !source || !psi)) || (ctx->F > 0 && !upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, false));
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    CU(cudaEventRecord(ctx->ev[3], ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_upper, upper, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_diag, diag, nb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_src, source, nb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_psi, psi, nb, cudaMemcpyHostToDevice, ctx->sc));
+    RET(copy_bou(ctx, ctx->plans[0], bou, cudaMemcpyHostToDevice, ctx->bou));
+    CU(cudaEventRecord(ctx->ev[4], ctx->sc));
+    int rc = solve_core(ctx, ctx->in_diag, ctx->in_upper, ctx->in_src, ctx->in_psi, ctl, perf);
+    if (rc != B200_OK && rc != B200_ENONFINITE) return rc;
+    CU(cudaEventRecord(ctx->ev[5], ctx->sc));
+    CU(cudaMemcpyAsync(psi, ctx->in_psi, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    if (perf) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+        perf->h2dMs = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]);
+        perf->d2hMs = ms;
+    }
+    return rc;
+}
+
+int b200_amul(b200_ctx* ctx, const double* diag, const double* upper, const double* const* bou,
+              const double* psi, double* Apsi) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "amul before set_addressing");
+    if ((ctx->N > 0 && (!diag || !psi || !Apsi)) || (ctx->F > 0 && !upper))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, false));
+    DevPlan& P = ctx->plans[0];
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    CU(cudaMemcpyAsync(ctx->in_upper, upper, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_diag, diag, nb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_psi, psi, nb, cudaMemcpyHostToDevice, ctx->sc));
+    RET(copy_bou(ctx, P, bou, cudaMemcpyHostToDevice, ctx->bou));
+    RET(reset_scalars(ctx, nullptr));
+    RET(load_system(ctx, P, ctx->in_diag, ctx->in_upper, nullptr, ctx->in_psi));
+    RET((spmv_full<false, false>(ctx, P, ctx->psi, ctx->w, nullptr, STEP_NONE)));
+    CU(cudaMemcpyAsync(Apsi, ctx->w, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+    return B200_OK;
+}
+
+int b200_flux(b200_ctx* ctx, const double* upper, const double* psi, double* flux_out) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "flux before set_addressing");
+    if ((ctx->F > 0 && (!upper || !flux_out)) || (ctx->N > 0 && !psi))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, true));
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    CU(cudaMemcpyAsync(ctx->in_upper, upper, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_psi, psi, nb, cudaMemcpyHostToDevice, ctx->sc));
+    LAUNCH(PC_FLUX, k_flux, grid_for(ctx, ctx->F, 16), ctx->F, ctx->d_l, ctx->d_u, ctx->in_upper,
+           ctx->in_psi, ctx->in_f1);
+    CU(cudaMemcpyAsync(flux_out, ctx->in_f1, fb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+    return B200_OK;
+}
+
+int b200_host_alloc(void** p, size_t bytes) {
+    b200_ctx* ctx = nullptr;
+    if (!p) return fail(ctx, B200_EINVAL, "null pointer");
+    *p = nullptr;
+    if (b200_device_count() <= 0) return fail(ctx, B200_ENODEVICE, "no CUDA device");
+    CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return B200_OK;
+}
+void b200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t b200_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_debug_force_iterations(b200_ctx* ctx, int32_t n) {
+    if (!ctx || n < 0) return B200_EINVAL;
+    ctx->forceIters = n;
+    return B200_OK;
+}
+
+int b200_profile_enable(b200_ctx* ctx, int on) {
+    if (!ctx) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (on && ctx->profPool.empty()) {
+        ctx->profPool.resize(2 * 8192);
+        for (auto& ev : ctx->profPool) CU(cudaEventCreate(&ev));
+    }
+    ctx->prof = on != 0;
+    if (on) {
+        std::memset(ctx->profMs, 0, sizeof(ctx->profMs));
+        std::memset(ctx->profN, 0, sizeof(ctx->profN));
+        ctx->profRecs.clear();
+        ctx->profUsed = 0;
+    }
+    return B200_OK;
+}
+
+const char* b200_profile_json(b200_ctx* ctx) {
+    if (!ctx) return "{}";
+    std::string s = "{";
+    bool first = true;
+    char buf[256];
+    for (int i = 0; i < PC_COUNT; ++i) {
+        if (!ctx->profN[i]) continue;
+        std::snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %llu, \"total_ms\": %.6f, \"avg_us\": %.3f}",
+                      first ? "" : ", ", kProfNames[i], (unsigned long long)ctx->profN[i],
+                      ctx->profMs[i], 1e3 * ctx->profMs[i] / (double)ctx->profN[i]);
+        s += buf;
+        first = false;
+    }
+    s += "}";
+    ctx->profJson = s;
+    return ctx->profJson.c_str();
+}
+
+}  // extern "C"

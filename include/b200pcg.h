@@ -1,0 +1,191 @@
+/*
+ * b200pcg.h -- C ABI of the B200-native p_rgh pressure-correction hot path.
+ *
+ * This is the ONLY boundary between the host application (OpenFOAM/fireFoam through
+ * adapter/B200PCG.C, or the Python ctypes mirror in firefoam-dev_b200/) and the sm_100a
+ * CUDA library libb200pcg.so.  Plain C: pointers, sizes, PODs.  No C++ types, no
+ * exceptions, no torch types.
+ *
+ * Each entry point names the reference interface it replaces.  The reference
+ * (LeiXu84/fireFoam-dev 17.11.10) *calls* that interface at
+ *     solver/pEqn.H:26-39        (assemble p_rghEqn, p_rghEqn.solve(...))
+ *     solver/phrghEqn.H:43-48    (assemble ph_rghEqn, ph_rghEqn.solve())
+ *     solver/pEqn.H:43-44        (p_rghEqn.flux())
+ * and the implementation it reaches lives in un-vendored OpenFOAM-dev @ 940e28f6
+ * (CHANGELOG:1-3): lduMatrix, PCG, DICPreconditioner, diagonalPreconditioner,
+ * gaussLaplacianScheme, processorFvPatchField (restated in SURVEY.md Appendix A and in
+ * oracle/pcg_oracle.c).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a B200_E* code otherwise; the text of the last
+ *     error of a context is available from b200_last_error().
+ *   - "host" entry points take host pointers, copy to the device and back inside the call;
+ *     "_device" entry points take device pointers (same layout) and do no host<->device copy
+ *     except an O(100 B) status read-back.
+ *   - labels are int32 (WM_LABEL_SIZE=32), scalars are IEEE double (WM_PRECISION_OPTION=DP).
+ *   - calls on one context must be serialised by the caller; with nranks > 1 every rank must
+ *     issue the same sequence of collective calls (set_addressing, solve*), as OpenFOAM does.
+ *   - non-convergence within maxIter and singularity are NOT errors; they are reported in
+ *     b200_perf exactly like OpenFOAM's SolverPerformance.
+ */
+#ifndef B200PCG_H
+#define B200PCG_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+/* error codes */
+enum {
+    B200_OK            = 0,
+    B200_EINVAL        = 1,  /* bad argument (NULL, negative size, l>=u, unsorted faces ...)   */
+    B200_ECUDA         = 2,  /* CUDA runtime error (message has cudaGetErrorString)           */
+    B200_ENCCL         = 3,  /* NCCL error                                                    */
+    B200_ENODEVICE     = 4,  /* no usable CUDA device: there is NO CPU fallback               */
+    B200_ESTATE        = 5,  /* call out of order (solve before set_addressing ...)           */
+    B200_EUNSUPPORTED  = 6,  /* unsupported interface type / row too long / label overflow    */
+    B200_ENONFINITE    = 7,  /* non-finite residual encountered                               */
+    B200_ENOMEM        = 8
+};
+
+/* preconditioner selector (fvSolution keyword `preconditioner`,
+ * reference: cases/steckler/system/fvSolution:32) */
+enum {
+    B200_PRECOND_NONE      = 0,  /* `none`      -> noPreconditioner                              */
+    B200_PRECOND_DIAGONAL  = 1,  /* `diagonal`  -> diagonalPreconditioner (bit-comparable path)  */
+    B200_PRECOND_DIC_MC    = 2,  /* `DIC`       -> multicolour-ordered IC0 ("DIC-class")         */
+    B200_PRECOND_DIC_EXACT = 3   /* `DIC` + `B200{dicMode exact;}` -> level-scheduled DIC with
+                                    the SAME elimination order as OpenFOAM's DICPreconditioner  */
+};
+
+typedef struct b200_ctx b200_ctx;
+
+/* One coupled (processor) interface of this rank.  Mirrors what
+ * lduMatrix::solver receives through `interfaces` + lduAddressing::patchAddr(k)
+ * (OF-dev processorLduInterface). */
+typedef struct b200_iface {
+    int32_t        nbrRank;    /* neighbProcNo()                                   */
+    int32_t        nFaces;     /* size of the patch                                */
+    const int32_t* faceCells;  /* [nFaces] local cell of each patch face           */
+    int32_t        tag;        /* message tag; unused by NCCL, kept for the adapter */
+} b200_iface;
+
+/* lduMatrix::solver::readControls (OF-dev lduMatrixSolver.C): maxIter 1000, minIter 0,
+ * tolerance 1e-6, relTol 0 are the defaults the adapter fills in. */
+typedef struct b200_controls {
+    double  tolerance;
+    double  relTol;
+    int32_t maxIter;
+    int32_t minIter;
+    int32_t precond;      /* B200_PRECOND_*                                           */
+    int32_t reserved;     /* must be 0                                                */
+} b200_controls;
+
+/* SolverPerformance<scalar> (OF-dev SolverPerformance.H): what the adapter needs to
+ * build the `DICPCG:  Solving for p_rgh, Initial residual = ..` log line
+ * (format: cases/steckler/original/linux64/log.fireFoam:92). */
+typedef struct b200_perf {
+    double  initialResidual;
+    double  finalResidual;
+    double  normFactor;       /* extra: lduMatrix::solver::normFactor value         */
+    int32_t nIterations;
+    int32_t converged;
+    int32_t singular;
+    int32_t nColours;         /* extra: colours/levels used by the DIC-class sweep   */
+    double  solveMs;          /* extra: device time of the PCG loop (CUDA events)     */
+    double  setupMs;          /* extra: device time of per-solve set-up               */
+    double  h2dMs, d2hMs;     /* extra: copy times of the host entry points          */
+} b200_perf;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Replaces: Pstream/MPI initialisation of the solver's communication (OF-dev UPstream.C).
+ * device < 0 selects the current device.  nccl_uid: 128 bytes from b200_get_unique_id on
+ * rank 0, broadcast by the caller (Pstream::scatter in the adapter, torch.distributed in the
+ * harness); NULL iff nranks == 1. */
+int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200_ctx** out);
+int b200_get_unique_id(void* uid128);
+void b200_ctx_destroy(b200_ctx* ctx);
+const char* b200_last_error(const b200_ctx* ctx);   /* ctx may be NULL: last create error */
+int b200_abi_version(void);
+int b200_device_count(void);                        /* 0 when no GPU/driver: callers must fail */
+
+/* Replaces: lduAddressing (lowerAddr/upperAddr/patchAddr + lazily built losort/ownerStart;
+ * OF-dev lduAddressing.C).  Idempotent for an unchanged mesh_key (upstream constructs a new
+ * solver object per solve, so the adapter calls this every time).  Faces must be in
+ * upper-triangular order (lowerAddr non-decreasing, l < u).  Builds the device-resident row
+ * structure, the colourings (lazily, on first DIC-class solve) and the halo plans. */
+int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key,
+                        int32_t nCells, int32_t nFaces,
+                        const int32_t* lowerAddr, const int32_t* upperAddr,
+                        int32_t nIfaces, const b200_iface* ifaces);
+
+/* ---- assembly: fvm::laplacian(gamma, vf) --------------------------------------------- */
+
+/* Replaces: gaussLaplacianScheme<scalar,scalar>::fvmLaplacianUncorrected + lduMatrix::negSumDiag
+ * (OF-dev gaussLaplacianScheme.C, lduMatrixOperations.C), called from solver/pEqn.H:32 (sign=-1,
+ * because of `- fvm::laplacian`) and solver/phrghEqn.H:45 (sign=+1).
+ *   upper_out[f] = sign * deltaCoeffs[f] * (gamma_f[f] * magSf[f])
+ *   diag_inout[c] += -( sum of upper_out over faces of c )        (sorted-segment sums, no atomics)
+ * diag_inout may hold the ddt contribution already (pass zeros for a pure Laplacian). */
+int b200_assemble_laplacian(b200_ctx* ctx, const double* gamma_f, const double* magSf,
+                            const double* deltaCoeffs, double sign,
+                            double* upper_out, double* diag_inout);
+int b200_assemble_laplacian_device(b200_ctx* ctx, const double* d_gamma_f, const double* d_magSf,
+                                   const double* d_deltaCoeffs, double sign,
+                                   double* d_upper_out, double* d_diag_inout);
+
+/* ---- solve: lduMatrix::solver::solve ------------------------------------------------- */
+
+/* Replaces: PCG::solve(psi, source, cmpt) with its Amul/normFactor/preconditioner/gSum*
+ * calls (OF-dev PCG.C, lduMatrixATmul.C, lduMatrixSolver.C, DICPreconditioner.C,
+ * diagonalPreconditioner.C), reached from solver/pEqn.H:39 and solver/phrghEqn.H:48.
+ *   diag   [nCells]  matrix diagonal WITH boundary internalCoeffs already added
+ *   upper  [nFaces]  symmetric off-diagonal
+ *   ifaceBouCoeffs[k] [ifaces[k].nFaces]  interfaceBouCoeffs of coupled patch k (may be NULL if
+ *                    nIfaces == 0)
+ *   source [nCells]  totalSource
+ *   psi    [nCells]  in: initial guess, out: solution
+ */
+int b200_solve(b200_ctx* ctx, const double* diag, const double* upper,
+               const double* const* ifaceBouCoeffs, const double* source, double* psi,
+               const b200_controls* ctl, b200_perf* perf);
+int b200_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper,
+                      const double* const* d_ifaceBouCoeffs, const double* d_source, double* d_psi,
+                      const b200_controls* ctl, b200_perf* perf);
+
+/* Replaces: lduMatrix::Amul(Apsi, psi, interfaceBouCoeffs, interfaces, cmpt) (OF-dev
+ * lduMatrixATmul.C) -- exposed so that parity tests can check the SpMV alone.  Collective when
+ * nranks > 1.  Row sums are formed in OpenFOAM's face order without FMA contraction, so on one
+ * rank the result is bit-identical to the CPU loop. */
+int b200_amul(b200_ctx* ctx, const double* diag, const double* upper,
+              const double* const* ifaceBouCoeffs, const double* psi, double* Apsi);
+
+/* Replaces: fvMatrix<scalar>::flux() internal-face part (OF-dev fvMatrix.C; used at
+ * solver/pEqn.H:43-44): flux[f] = upper[f]*psi[u[f]] - upper[f]*psi[l[f]]. */
+int b200_flux(b200_ctx* ctx, const double* upper, const double* psi, double* flux_out);
+
+/* ---- harness helpers (not part of the OpenFOAM-facing contract) ---------------------- */
+
+/* pinned host memory for callers that want async H2D at full PCIe rate */
+int  b200_host_alloc(void** p, size_t bytes);
+void b200_host_free(void* p);
+/* number of kernel launches issued by this context since creation (bench "gpu_launches") */
+uint64_t b200_launch_count(const b200_ctx* ctx);
+/* fixed-iteration timing aid: when > 0 the convergence test is ignored and exactly n loop
+ * bodies are executed (bench only; 0 restores OpenFOAM semantics) */
+int b200_debug_force_iterations(b200_ctx* ctx, int32_t n);
+/* profiling aid: when on, every kernel class is timed with CUDA events and the totals are
+ * retrievable as a JSON string (B200PCG_PROFILE=1 in the adapter) */
+int b200_profile_enable(b200_ctx* ctx, int on);
+const char* b200_profile_json(b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PCG_H */

@@ -1,0 +1,145 @@
+"""Shared test helpers: numpy emulation of the device row structure (so the data structure the
+kernels consume can be validated on a CPU-only box), random LDU meshes, hydrostatic KAT loop."""
+import ctypes as C
+
+import numpy as np
+
+from firefoam_dev_b200 import _lib
+from firefoam_dev_b200.ldu import LduAddressing, ProcessorLduInterface
+from firefoam_dev_b200.meshgen import System
+
+
+class PlanView:
+    """HostPlan (csrc/plan.cpp) pulled out through the host-only debug ABI."""
+
+    NAMES = ["perm", "iperm", "colourStart", "sliceBase", "rowLen", "col", "faceOf", "nbrRank",
+             "patchStart", "slotRow", "bRow", "bStart", "bSlot"]
+
+    def __init__(self, ordering, addr):
+        L = _lib.load_pcg()
+        ifs = (_lib.Iface * max(1, len(addr.interfaces)))()
+        # b200_dbg_iface = {nbrRank, nFaces, faceCells} -- same leading layout, pack explicitly
+        class DbgIface(C.Structure):
+            _fields_ = [("nbrRank", C.c_int32), ("nFaces", C.c_int32), ("faceCells", C.c_void_p)]
+        dif = (DbgIface * max(1, len(addr.interfaces)))()
+        for k, itf in enumerate(addr.interfaces):
+            dif[k].nbrRank, dif[k].nFaces = itf.neighbProcNo, itf.faceCells.size
+            dif[k].faceCells = itf.faceCells.ctypes.data
+        h = L.b200_debug_plan_build(ordering, addr.nCells, addr.nFaces, addr.lowerAddr.ctypes.data,
+                                    addr.upperAddr.ctypes.data, len(addr.interfaces),
+                                    C.cast(dif, C.c_void_p))
+        if not h:
+            raise ValueError(L.b200_debug_plan_error().decode())
+        try:
+            self.nColours = L.b200_debug_plan_ncolours(h)
+            self.nEntries = L.b200_debug_plan_nentries(h)
+            for nm in self.NAMES:
+                ptr, eb = C.c_void_p(), C.c_int32()
+                n = L.b200_debug_plan_get(h, nm.encode(), C.byref(ptr), C.byref(eb))
+                assert n >= 0, nm
+                dt = {4: np.int32, 8: np.int64}[eb.value] if nm != "rowLen" else np.uint32
+                if n == 0:
+                    arr = np.empty(0, dtype=dt)
+                else:
+                    arr = np.frombuffer((C.c_char * (n * eb.value)).from_address(ptr.value), dtype=dt).copy()
+                setattr(self, nm, arr)
+        finally:
+            L.b200_debug_plan_free(h)
+        self.N, self.F = addr.nCells, addr.nFaces
+        self.nLower = (self.rowLen & 0xFFFF).astype(np.int64)
+        self.nTotal = (self.rowLen >> 16).astype(np.int64)
+
+    def entry(self, r, j):
+        return int(self.sliceBase[r // 32]) + 32 * j + (r % 32)
+
+    def to_internal(self, v):
+        return v[self.perm] if self.perm.size else v.copy()
+
+    def to_natural(self, v):
+        if not self.perm.size:
+            return v.copy()
+        out = np.empty_like(v)
+        out[self.perm] = v
+        return out
+
+    def values(self, upper):
+        val = np.zeros(self.nEntries)
+        m = self.faceOf >= 0
+        val[m] = upper[self.faceOf[m]]
+        return val
+
+    # --- numpy emulation of the kernels' row loops (same operation order) ------------------
+    def spmv(self, diag_i, val, x_i):
+        y = np.empty(self.N)
+        for r in range(self.N):
+            acc = diag_i[r] * x_i[r]
+            for j in range(self.nTotal[r]):
+                e = self.entry(r, j)
+                acc = acc + val[e] * x_i[self.col[e]]
+            y[r] = acc
+        return y
+
+    def dic_calc_rd(self, diag_i, val):
+        rD = np.empty(self.N)
+        for k in range(self.nColours):
+            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+                d = diag_i[r]
+                for j in range(self.nLower[r]):
+                    e = self.entry(r, j)
+                    d = d - (val[e] * val[e]) / rD[self.col[e]]
+                rD[r] = d
+        return 1.0 / rD
+
+    def dic_precondition(self, rD, val, r_i):
+        w = np.empty(self.N)
+        for k in range(self.nColours):
+            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+                acc = rD[r] * r_i[r]
+                for j in range(self.nLower[r]):
+                    e = self.entry(r, j)
+                    acc = acc - (rD[r] * val[e]) * w[self.col[e]]
+                w[r] = acc
+        for k in range(self.nColours - 2, -1, -1):
+            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+                acc = w[r]
+                for j in range(self.nTotal[r] - 1, self.nLower[r] - 1, -1):
+                    e = self.entry(r, j)
+                    acc = acc - (rD[r] * val[e]) * w[self.col[e]]
+                w[r] = acc
+        return w
+
+
+def random_ldu(N, avg_deg, seed, spd=True):
+    """Random symmetric LDU system (irregular row lengths, including empty rows)."""
+    rng = np.random.default_rng(seed)
+    nF = int(N * avg_deg / 2)
+    a = rng.integers(0, N, size=nF)
+    b = rng.integers(0, N, size=nF)
+    keep = a != b
+    lo, hi = np.minimum(a, b)[keep], np.maximum(a, b)[keep]
+    pairs = np.unique(np.stack([lo, hi], 1), axis=0)   # sorted lexicographically = upper-triangular
+    l, u = pairs[:, 0].astype(np.int32), pairs[:, 1].astype(np.int32)
+    upper = -rng.uniform(0.1, 1.0, size=l.size)
+    diag = np.zeros(N)
+    np.add.at(diag, l, -upper)
+    np.add.at(diag, u, -upper)
+    diag += rng.uniform(0.01, 0.1, size=N)
+    addr = LduAddressing(N, l, u)
+    xstar = rng.standard_normal(N)
+    s = System(addr, diag, upper, np.zeros(N), [], xstar)
+    from oracle import oracle as orc
+    s.source = orc.amul(s, xstar)[0]
+    return s
+
+
+def hydrostatic_loop(case, laplacian, solve):
+    """solver/phrghEqn.H:30-56: returns [(initial, final, iters, variation)] per corrector.
+    solve(matrix, source, psi) -> object with initialResidual/finalResidual/nIterations."""
+    out = []
+    psi = case.ph_rgh.copy()
+    for _ in range(case.N_CORR):
+        m, src = case.assemble(laplacian)
+        perf = solve(m, src, psi)
+        var = case.update(psi)
+        out.append((perf.initialResidual, perf.finalResidual, perf.nIterations, var))
+    return out

@@ -1,0 +1,133 @@
+"""The device row structure (csrc/plan.cpp) validated on the CPU: the numpy emulation of the
+kernels' row loops over the sliced-ELL arrays must reproduce the oracle's Amul and DIC
+bit-for-bit (natural / level order) or to rounding (multicolour order)."""
+import numpy as np
+import pytest
+
+from firefoam_dev_b200 import meshgen as mg
+from firefoam_dev_b200.cases import StecklerHydrostatic
+from firefoam_dev_b200.ldu import LduAddressing
+from oracle import oracle as orc
+from helpers import PlanView, random_ldu
+
+NAT, MC, LEV = 0, 1, 2
+
+
+def systems():
+    yield "hex", mg.hex_block(7, 5, 6)
+    yield "random", random_ldu(300, 5.0, seed=3)
+    yield "random-sparse", random_ldu(257, 1.2, seed=5)   # empty rows, ragged
+
+
+@pytest.mark.parametrize("name,s", list(systems()))
+def test_structure_invariants(name, s):
+    a = s.addr
+    for ordering in (NAT, MC, LEV):
+        P = PlanView(ordering, a)
+        assert P.nTotal.sum() == 2 * a.nFaces
+        m = P.faceOf >= 0
+        # every face appears exactly twice, once in a lower group and once in an upper group
+        assert np.array_equal(np.bincount(P.faceOf[m], minlength=a.nFaces), np.full(a.nFaces, 2))
+        assert P.colourStart[0] == 0 and P.colourStart[-1] == a.nCells
+        if P.perm.size:
+            assert np.array_equal(np.sort(P.perm), np.arange(a.nCells))
+            assert np.array_equal(P.iperm[P.perm], np.arange(a.nCells))
+        for r in range(a.nCells):
+            cols = [P.col[P.entry(r, j)] for j in range(P.nTotal[r])]
+            assert all(c < r for c in cols[:P.nLower[r]]) and all(c > r for c in cols[P.nLower[r]:])
+            fl = [P.faceOf[P.entry(r, j)] for j in range(P.nLower[r])]
+            fu = [P.faceOf[P.entry(r, j)] for j in range(P.nLower[r], P.nTotal[r])]
+            assert fl == sorted(fl) and fu == sorted(fu)
+        # rows of one colour never neighbour each other
+        if ordering != NAT:
+            colour = np.searchsorted(P.colourStart, np.arange(a.nCells), side="right") - 1
+            rl = P.iperm[a.lowerAddr]
+            ru = P.iperm[a.upperAddr]
+            assert np.all(colour[rl] != colour[ru])
+            if ordering == LEV:   # elimination order preserved: owner before neighbour
+                assert np.all(rl < ru)
+
+
+@pytest.mark.parametrize("name,s", list(systems()))
+def test_spmv_emulation_bit_exact_natural(name, s):
+    P = PlanView(NAT, s.addr)
+    x = np.random.default_rng(1).standard_normal(s.addr.nCells)
+    y = P.spmv(s.diag, P.values(s.upper), x)
+    assert np.array_equal(y, orc.amul(s, x)[0])
+
+
+@pytest.mark.parametrize("name,s", list(systems()))
+def test_spmv_emulation_permuted(name, s):
+    x = np.random.default_rng(2).standard_normal(s.addr.nCells)
+    ref = orc.amul(s, x)[0]
+    for ordering in (MC, LEV):
+        P = PlanView(ordering, s.addr)
+        y = P.to_natural(P.spmv(P.to_internal(s.diag), P.values(s.upper), P.to_internal(x)))
+        np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,s", list(systems()))
+def test_level_schedule_is_exact_dic(name, s):
+    """DIC-exact: level-major order + OpenFOAM's per-row operation order == DICPreconditioner."""
+    r = np.random.default_rng(4).standard_normal(s.addr.nCells)
+    rD_ref, w_ref = orc.dic(s, r)
+    P = PlanView(LEV, s.addr)
+    val = P.values(s.upper)
+    rD = P.dic_calc_rd(P.to_internal(s.diag), val)
+    w = P.dic_precondition(rD, val, P.to_internal(r))
+    assert np.array_equal(P.to_natural(rD), rD_ref)
+    assert np.array_equal(P.to_natural(w), w_ref)
+
+
+def test_multicolour_is_a_symmetric_ic0():
+    """DIC-class (multicolour): M^-1 must be symmetric positive definite."""
+    s = mg.hex_block(5, 4, 3)
+    P = PlanView(MC, s.addr)
+    assert P.nColours == 2     # structured hex is bipartite: red-black
+    val = P.values(s.upper)
+    rD = P.dic_calc_rd(P.to_internal(s.diag), val)
+    n = s.addr.nCells
+    M = np.stack([P.dic_precondition(rD, val, e) for e in np.eye(n)], 1)
+    np.testing.assert_allclose(M, M.T, rtol=1e-12, atol=1e-14)
+    assert np.linalg.eigvalsh(0.5 * (M + M.T)).min() > 0
+
+
+def test_steckler_colourings():
+    a = StecklerHydrostatic().addr
+    assert PlanView(MC, a).nColours == 2
+    assert PlanView(LEV, a).nColours == 30 + 15 + 20 - 2   # i+j+k hyperplanes
+
+
+def test_interface_csr():
+    subs = [mg.hex_block(6, 6, 4, 2, 2, 1, r) for r in range(4)]
+    s = subs[0]
+    for ordering in (NAT, MC):
+        P = PlanView(ordering, s.addr)
+        nSlots = sum(i.faceCells.size for i in s.addr.interfaces)
+        assert P.patchStart[-1] == nSlots and P.slotRow.size == nSlots
+        fc = np.concatenate([i.faceCells for i in s.addr.interfaces])
+        rows = P.iperm[fc] if P.iperm.size else fc
+        assert np.array_equal(P.slotRow, rows)
+        assert np.array_equal(np.sort(P.bSlot), np.arange(nSlots))
+        assert np.all(np.diff(P.bRow) > 0)
+        for b in range(P.bRow.size):
+            sl = P.bSlot[P.bStart[b]:P.bStart[b + 1]]
+            assert np.all(P.slotRow[sl] == P.bRow[b]) and np.all(np.diff(sl) > 0)
+        # the corner cell touches two processor patches
+        assert (np.diff(P.bStart) == 2).any()
+
+
+def test_rejects_bad_addressing():
+    with pytest.raises(ValueError):
+        PlanView(NAT, LduAddressing(3, [1, 0], [2, 1]))      # not upper-triangular order
+    with pytest.raises(ValueError):
+        PlanView(NAT, LduAddressing(3, [1], [1]))            # l == u
+    with pytest.raises(ValueError):
+        PlanView(NAT, LduAddressing(3, [0], [3]))            # out of range
+
+
+def test_empty_and_single_cell():
+    P = PlanView(NAT, LduAddressing(0, [], []))
+    assert P.nEntries == 0
+    P = PlanView(LEV, LduAddressing(1, [], []))
+    assert P.nColours == 1 and P.nTotal[0] == 0
