@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- p_rgh pressure-correction hot path on N B200s of one node (BASELINE.json metric:
+p_rgh PCG solve time and GDOF.iter/s, HBM GB/s vs peak).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torchrun)
+  python bench.py --impl reference ...                           (CPU arm: the oracle on host cores)
+
+A "step" is one pass of the hot path over one synthetic system: assemble
+`- fvm::laplacian(rhorAUf, p_rgh)` into LDU form (face coefficients + negSumDiag) and solve it with
+PCG + diagonal preconditioner to tolerance 1e-6 (relTol 0, x0 = 0) -- SURVEY.md 8d config 3.
+Workload (weak scaling): every GPU owns a 256 x 250 x 250 = 16 M-cell block of a uniform hex box
+decomposed `hierarchical` (1 1 1)/(2 1 1)/(2 2 1)/(2 2 2); at N = 8 that is BASELINE config 4's
+128 M-cell mesh.  Processor-patch halos go over NCCL send/recv, the CG scalars over NCCL all-reduce.
+
+value  = N_global * (PCG iterations executed) / device time, inputs resident in HBM.
+e2e    = the same metric through the reference-facing plug-in call B200PCG.solve() with pinned HOST
+         buffers (diag/upper/source/psi/interfaceBouCoeffs H2D and psi D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = (256, 250, 250)          # cells per GPU (config 3)
+PROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+TOL, MAXITER = 1e-6, 5000
+METRIC = "p_rgh PCG solve throughput (assemble + PCG/diagonal to tol 1e-6), fp64"
+UNIT = "GDOF*iter/s"
+
+
+def global_dims(n, block):
+    p = PROCS[n]
+    return tuple(b * q for b, q in zip(block, p)), p
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_leg(block, seconds=12.0, steps=1, warmup=0):
+    """The reference's CPU path for this workload: oracle/ (plain-C restatement of OpenFOAM-dev's
+    PCG + diagonalPreconditioner + Amul + normFactor, `kind: port` -- the reference's own
+    implementation is un-vendored and cannot be built here), R emulated ranks = R host threads, each
+    owning a decomposePar sub-block, like `mpirun -np R fireFoam -parallel`
+    (cases/wallFireSpread2D/runParallel.sh:18).  Bounded sample: a fixed number of PCG iterations of
+    the same 16 M-cell system, sized for ~`seconds` of CPU work per step."""
+    import numpy as np
+    from firefoam_dev_b200 import meshgen as mg
+    from oracle import oracle as orc
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    R = 1
+    while R * 2 <= min(ncpu, 128):
+        R *= 2
+    p = [1, 1, 1]
+    d, r = 0, R
+    while r > 1:
+        p[d % 3] *= 2
+        r //= 2
+        d += 1
+    t0 = time.time()
+    subs = [mg.hex_block(*block, *p, rank) for rank in range(R)]
+    n_global = sum(s.addr.nCells for s in subs)
+    gen_s = time.time() - t0
+
+    def run(iters):
+        psis = [np.zeros(s.addr.nCells) for s in subs]
+        t = time.perf_counter()
+        perf = orc.pcg_solve(subs, psis, "diagonal", 1e-30, 0.0, maxIter=iters - 1)
+        return time.perf_counter() - t, perf.nIterations
+    tc, ic = run(4)                                   # calibration (also warms the page cache)
+    per_iter = tc / max(ic, 1)
+    iters = int(min(400, max(8, seconds / max(per_iter, 1e-6))))
+    times, total_it = [], 0
+    for _ in range(warmup):
+        run(iters)
+    for _ in range(max(1, steps)):
+        t, it = run(iters)
+        times.append(t)
+        total_it += it
+    value = n_global * total_it / sum(times) / 1e9
+    return {"value": value, "unit": UNIT, "cores": R, "kind": "port",
+            "sample": f"{iters} PCG+diagonal iterations of the {block[0]}x{block[1]}x{block[2]} hex system "
+                      f"({n_global} cells) on {R} emulated ranks/threads ({p[0]} {p[1]} {p[2]}); "
+                      f"host has {ncpu} usable cores; {sum(times)/len(times):.2f} s per step",
+            "ms_per_step": 1e3 * sum(times) / len(times), "gen_s": gen_s}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    block = tuple(args.block)
+    dims, procs = global_dims(args.gpus, block)
+    leg = cpu_leg(block, seconds=args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.gpus, block),
+            "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(n, block):
+    dims, procs = global_dims(n, block)
+    return {"workload": f"hex{dims[0]}x{dims[1]}x{dims[2]}_p_rgh_PCG_diagonal"
+                        + ("" if block == BLOCK else "_reduced"),
+            "cells": dims[0] * dims[1] * dims[2], "cells_per_gpu": block[0] * block[1] * block[2],
+            "decomposition": f"hierarchical ({procs[0]} {procs[1]} {procs[2]})",
+            "preconditioner": "diagonal", "tolerance": TOL, "relTol": 0.0, "maxIter": MAXITER,
+            "baseline_config": "configs[2] (16M hex, PCG+diagonal, 1xB200) per GPU; N=8 is configs[3]'s 128M mesh",
+            "l2": "working set (>1.5 GB per GPU) exceeds the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import firefoam_dev_b200 as pkg
+    from firefoam_dev_b200 import meshgen as mg
+
+    n = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != n:
+        raise SystemExit(f"--gpus {n} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {n}")
+    if not torch.cuda.is_available() or pkg.load_pcg().b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    uid = None
+    if n > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if n > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    block = tuple(args.block)
+    dims, procs = global_dims(n, block)
+    keep = []
+
+    def pinned(count, dtype):
+        t = torch.empty(max(1, count), dtype=torch.float64, pin_memory=True)
+        keep.append(t)
+        return t.numpy()[:count]
+
+    t0 = time.time()
+    s = mg.hex_block(*dims, *procs, rank, pinned=pinned)
+    gen_s = time.time() - t0
+    a = s.addr
+    N, F = a.nCells, a.nFaces
+    n_global = dims[0] * dims[1] * dims[2]
+    ctx = pkg.Context(device=local_rank, rank=rank, nranks=n, nccl_uid=uid)
+    t0 = time.time()
+    ctx.set_addressing(a)
+    setaddr_s = time.time() - t0
+    ctl, _ = pkg.make_controls({"preconditioner": "diagonal", "tolerance": TOL, "relTol": 0.0, "maxIter": MAXITER})
+
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    d_gamma, d_magSf, d_delta = up(s.gamma_f), up(s.magSf), up(s.deltaCoeffs)
+    d_diag0, d_src = up(s.diag0), up(s.source)
+    d_bou = [up(b) for b in s.bou]
+    d_diag = torch.empty(N, dtype=torch.float64, device=dev)
+    d_upper = torch.empty(F, dtype=torch.float64, device=dev)
+    d_psi = torch.zeros(N, dtype=torch.float64, device=dev)
+
+    def step_device():
+        # assemble: - fvm::laplacian(rhorAUf, p_rgh) on top of the ddt/boundary diagonal
+        d_diag.copy_(d_diag0)
+        d_psi.zero_()
+        torch.cuda.current_stream().synchronize()
+        ctx.assemble_laplacian_device(d_gamma, d_magSf, d_delta, -1.0, d_upper, d_diag)
+        return ctx.solve_device(d_diag, d_upper, d_bou, d_src, d_psi, ctl)
+
+    for _ in range(args.warmup):
+        perf = step_device()
+    # ---- timed: device-resident ------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    ctx.profile(True)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 0
+    solve_ms = setup_ms = 0.0
+    for _ in range(args.steps):
+        perf = step_device()
+        iters += perf.nIterations
+        solve_ms += perf.solveMs
+        setup_ms += perf.setupMs
+    e1.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if n > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop() if rank == 0 else None
+    prof = ctx.profile_json()
+    ctx.profile(False)
+    converged = bool(perf.converged)
+    err = float(np.abs(d_psi.cpu().numpy() - s.xstar).max())
+    value = n_global * iters / (ms * 1e-3) / 1e9
+
+    # ---- e2e: the reference-facing plug-in call with pinned host buffers ------------------------
+    psi_h = pinned(N, np.float64)
+    solver = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces,
+                         {"preconditioner": "diagonal", "tolerance": TOL, "relTol": 0.0, "maxIter": MAXITER},
+                         context=ctx)
+    psi_h[:] = 0.0
+    solver.solve(psi_h, s.source)                       # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    e_iters = 0
+    h2d_ms = d2h_ms = 0.0
+    for _ in range(args.steps):
+        psi_h[:] = 0.0
+        p = solver.solve(psi_h, s.source)
+        e_iters += p.nIterations
+        h2d_ms += p.h2dMs
+        d2h_ms += p.d2hMs
+    barrier()
+    e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if n > 1:
+        dist.all_reduce(e_s, op=dist.ReduceOp.MAX)
+    e_s = float(e_s.item())
+    e2e_value = n_global * e_iters / e_s / 1e9
+    nslots = sum(b.size for b in s.bou)
+    h2d_bytes = 8 * (F + 3 * N + nslots)
+    d2h_bytes = 8 * N
+    e2e_err = float(np.abs(psi_h - s.xstar).max())
+
+    # ---- fixed 200-iteration timing -------------------------------------
+    ctx.force_iterations(200)
+    step_device()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    pf = step_device()
+    f1.record()
+    barrier()
+    ctx.force_iterations(0)
+    fixed_ms = f0.elapsed_time(f1)
+
+    if rank != 0:
+        if n > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    alg = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N, "p_update": 24 * N,
+           "update_psi_r": 48 * N, "asm_face_coeff": 32 * F, "asm_neg_sum_diag": 16 * N + 16 * F}
+    kernels = {}
+    for k, v in prof.items():
+        ent = {"launches": v["launches"], "avg_us": v["avg_us"]}
+        if k in alg:
+            ent["alg_bytes"] = alg[k]
+            ent["gbs"] = alg[k] / (v["avg_us"] * 1e-6) / 1e9
+            ent["frac"] = ent["gbs"] / peak
+        kernels[k] = ent
+    dom = kernels.get("spmv_dot", {})
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("cells") == N:
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    iter_bytes = 120 * N + 16 * F
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(n, block),
+        "iterations_per_step": iters // args.steps, "converged": converged, "max_err_vs_xstar": err,
+        "solve_ms_per_step": solve_ms / args.steps, "setup_ms_per_step": setup_ms / args.steps,
+        "pcg_iteration": {"avg_us": 1e3 * solve_ms / max(iters, 1), "alg_bytes": iter_bytes,
+                          "gbs": iter_bytes / (1e-3 * solve_ms / max(iters, 1)) / 1e9,
+                          "frac": iter_bytes / (1e-3 * solve_ms / max(iters, 1)) / 1e9 / peak},
+        "fixed_200_iterations": {"ms": fixed_ms, "iters": pf.nIterations,
+                                 "gdof_iter_per_s": n_global * pf.nIterations / (fixed_ms * 1e-3) / 1e9},
+        "roofline": {"kernel": "k_spmv<false,true> (lduMatrix::Amul fused with gSumProd(wA,pA))",
+                     "bound": "hbm", "achieved": dom.get("gbs"), "peak": peak, "unit": "GB/s",
+                     "frac": dom.get("frac"), "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_launch": dom.get("alg_bytes"), "avg_us": dom.get("avg_us")},
+        "kernels": kernels,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e_s / args.steps,
+                "h2d_ms_per_step": h2d_ms / args.steps, "d2h_ms_per_step": d2h_ms / args.steps,
+                "iterations_per_step": e_iters // args.steps, "max_err_vs_xstar": e2e_err,
+                "timing": "host wall clock around blocking B200PCG.solve() calls, max over ranks"},
+        "gpu_launches": launches, "clocks": clk,
+        "host": {"gen_s": gen_s, "set_addressing_s": setaddr_s},
+    }
+    if n == 1 and not args.no_cpu_baseline:
+        leg = cpu_leg(block, seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if n > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--block", type=int, nargs=3, default=list(BLOCK),
+                    help="cells per GPU (development only; the default is the BASELINE workload)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus not in PROCS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

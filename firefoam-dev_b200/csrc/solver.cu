@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "plan.hpp"
 
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -27,6 +28,50 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_createError;
+
+// NCCL is bound lazily with dlopen, only when a multi-rank context is created.  A hard link
+// against libnccl.so.2 would pin whichever copy the loader finds first (the system 2.27 here),
+// and a host process that later loads a newer NCCL of the same soname (PyTorch bundles 2.28)
+// would then fail to resolve its symbols.  dlopen("libnccl.so.2") returns the copy already in
+// the process when there is one.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char* env = getenv("B200_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            error = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define SYM(field, name)                                                      \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, name));           \
+    if (!field) { error = std::string("NCCL symbol missing: ") + name; handle = nullptr; return false; }
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank")
+        SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend")
+        SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+        SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
 
 enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
@@ -116,7 +161,7 @@ int fail(b200_ctx* c, int code, const std::string& msg) {
     do {                                                                                 \
         ncclResult_t e_ = (call);                                                        \
         if (e_ != ncclSuccess)                                                           \
-            return fail(ctx, B200_ENCCL, std::string(#call) + ": " + ncclGetErrorString(e_)); \
+            return fail(ctx, B200_ENCCL, std::string(#call) + ": " + g_nccl.GetErrorString(e_)); \
     } while (0)
 #define RET(call)                        \
     do {                                 \
@@ -264,7 +309,7 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
 // after a reducing kernel with a step: all-reduce + scalar step when nranks > 1
 int reduce_post(b200_ctx* ctx, int step) {
     if (ctx->nranks == 1) return B200_OK;
-    NC(ncclAllReduce(ctx->S->sums, ctx->S->gsums, kNSums, ncclDouble, ncclSum, ctx->comm, ctx->sc));
+    NC(g_nccl.AllReduce(ctx->S->sums, ctx->S->gsums, kNSums, ncclDouble, ncclSum, ctx->comm, ctx->sc));
     LAUNCH(PC_SCALAR, k_scalar_step, 1, ctx->S, step);
     return B200_OK;
 }
@@ -278,14 +323,14 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         LAUNCH(PC_PACK, k_pack, grid_for(ctx, P.nSlots), P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
-        NC(ncclGroupStart());
+        NC(g_nccl.GroupStart());
         for (int k = 0; k < P.h.nIfaces; ++k) {
             const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
             if (n == 0) continue;
-            NC(ncclSend(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-            NC(ncclRecv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
         }
-        NC(ncclGroupEnd());
+        NC(g_nccl.GroupEnd());
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R{ctx->S, ctx->partials, halo ? STEP_NONE : step};
@@ -513,8 +558,9 @@ int b200_get_unique_id(void* uid128) {
     b200_ctx* ctx = nullptr;
     if (!uid128) return fail(ctx, B200_EINVAL, "null uid buffer");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!g_nccl.load()) return fail(ctx, B200_ENCCL, g_nccl.error);
     ncclUniqueId id;
-    NC(ncclGetUniqueId(&id));
+    NC(g_nccl.GetUniqueId(&id));
     std::memcpy(uid128, &id, 128);
     return B200_OK;
 }
@@ -567,8 +613,9 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (nranks > 1) {
         ncclUniqueId id;
         std::memcpy(&id, nccl_uid, 128);
-        ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
-        if (r != ncclSuccess) return bail(B200_ENCCL, ncclGetErrorString(r));
+        if (!g_nccl.load()) return bail(B200_ENCCL, g_nccl.error);
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) return bail(B200_ENCCL, g_nccl.GetErrorString(r));
     }
     *out = c;
     return B200_OK;
@@ -580,7 +627,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (c->sc) cudaStreamSynchronize(c->sc);
     if (c->sm) cudaStreamSynchronize(c->sm);
     free_mesh(c);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
     for (auto ev : c->profPool) cudaEventDestroy(ev);
     dev_free(c->S);
     dev_free(c->partials);
@@ -635,7 +682,7 @@ int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_
         double* tmp = ctx->partials;
         double h = (double)nCells;
         CU(cudaMemcpyAsync(tmp, &h, sizeof(double), cudaMemcpyHostToDevice, ctx->sc));
-        NC(ncclAllReduce(tmp, tmp + 1, 1, ncclDouble, ncclSum, ctx->comm, ctx->sc));
+        NC(g_nccl.AllReduce(tmp, tmp + 1, 1, ncclDouble, ncclSum, ctx->comm, ctx->sc));
         CU(cudaMemcpyAsync(&h, tmp + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
         CU(cudaStreamSynchronize(ctx->sc));
         ctx->nGlobalCells = h;

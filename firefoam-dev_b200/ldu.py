@@ -105,6 +105,10 @@ class Context:
     solver object -- owns everything that must persist."""
 
     def __init__(self, device=-1, rank=0, nranks=1, nccl_uid=None):
+        if nranks > 1:
+            # make sure the process-wide NCCL is the one PyTorch bundles (the library binds
+            # NCCL lazily with dlopen and picks up whichever libnccl.so.2 is already loaded)
+            import torch  # noqa: F401
         self.lib = _lib.load_pcg()
         self.handle = C.c_void_p()
         uid = None
@@ -118,6 +122,7 @@ class Context:
 
     @staticmethod
     def unique_id():
+        import torch  # noqa: F401  (see __init__)
         lib = _lib.load_pcg()
         buf = (C.c_char * 128)()
         rc = lib.b200_get_unique_id(buf)
