@@ -26,6 +26,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line)
+# torchrun exports OMP_NUM_THREADS=1; the host-side set-up (plan build, workload generation) is
+# OpenMP code that should use the cores this rank is entitled to
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    _n = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    os.environ["OMP_NUM_THREADS"] = str(min(_n, 32))
 
 BLOCK = (256, 250, 250)          # cells per GPU (config 3)
 PROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}

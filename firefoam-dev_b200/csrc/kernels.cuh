@@ -31,7 +31,8 @@ enum Step : int {
     STEP_NORM,     // normFactor, initial residual, first convergence check
     STEP_WARA,     // wArA = (wA, rA); beta
     STEP_WAPA,     // wApA = (wA, pA); singularity; alpha
-    STEP_RES       // final residual; nIter++; convergence
+    STEP_RES,      // final residual; nIter++; convergence
+    STEP_RES_WARA  // STEP_RES, then (if the loop continues) STEP_WARA of the next iteration
 };
 
 struct Scalars {
@@ -42,7 +43,7 @@ struct Scalars {
     // state
     double xRef, normFactor, initRes, finalRes;
     double wArA, wArAold, wApA, alpha, beta;
-    int nIter, done, converged, singular, nonfinite, pad0;
+    int nIter, done, converged, singular, nonfinite, pendingPsi;
     // reduction plumbing
     double acc[kNSums];    // running totals across the kernels of one reduction
     double sums[kNSums];   // local totals (input of the all-reduce when nranks > 1)
@@ -79,6 +80,7 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
             S->wArAold = 1e20;
             S->singular = 0;
             S->nonfinite = 0;
+            S->pendingPsi = 0;
             bool conv = check_convergence(S);
             S->converged = conv ? 1 : 0;
             bool enter = S->forceIters > 0 ? true : (S->minIter > 0 || !conv);
@@ -100,11 +102,14 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
             if (S->forceIters == 0 && !(fabs(S->wApA) / S->normFactor > 1e-300)) {
                 S->singular = 1;
                 S->done = 1;
+                S->pendingPsi = 0;
             } else {
                 S->alpha = S->wArA / S->wApA;
+                S->pendingPsi = 1;   // psi += alpha*pA is applied by the next k_p / k_psi_final
             }
             break;
-        case STEP_RES: {
+        case STEP_RES:
+        case STEP_RES_WARA: {
             S->finalRes = g[0] / S->normFactor;
             int old = S->nIter;
             S->nIter = old + 1;
@@ -118,6 +123,11 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
                 cont = false;
             }
             if (!cont) S->done = 1;
+            else if (step == STEP_RES_WARA) {
+                S->wArAold = S->wArA;
+                S->wArA = g[1];
+                S->beta = S->wArA / S->wArAold;
+            }
             break;
         }
         default:
@@ -273,6 +283,93 @@ k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict_
                 const double a0 = val[e];
                 acc = __dadd_rn(acc, __dmul_rn(a0, __ldg(&x[c0])));
                 if (INIT) sa = __dadd_rn(sa, a0);
+            }
+            y[r] = acc;
+            if (INIT) sA[r] = sa;
+            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
+// Symmetric single-read Amul (SymPlan in plan.hpp): each coefficient is streamed from HBM once.
+// Upper entries: coalesced sliced-ELL (value, column).  Lower entries: 32-bit references
+// (owner row << 5 | q) -> the value is re-read from the owner's q-th upper entry (an L2 hit on
+// banded cell orders; rows of a warp reference consecutive owners, so the re-read is coalesced
+// too).  Row-sum order == OpenFOAM's face order: bit-identical to the CPU loop.
+// Loads are issued in three dependent levels, each as one batch of up to B independent loads per
+// thread (references + upper (col, value); then x gathers + referenced values; then the FP chain),
+// so a warp keeps ~4B loads in flight instead of one dependent chain at a time.
+constexpr int kSymBatch = 4;
+template <bool INIT, bool DOT>
+__global__ void __launch_bounds__(kBlock, 4)
+k_spmv_sym(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
+           const int* __restrict__ uCol, const double* __restrict__ uVal,
+           const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
+           const double* __restrict__ x, double* __restrict__ y, double* __restrict__ sA, Reduce R) {
+    if (R.S->done) return;
+    constexpr int B = kSymBatch;
+    double dot[1] = {0.0};
+    const uint32_t lane = threadIdx.x & 31;
+    const int nSlices = (N + 31) >> 5;
+    const int warpsPerGrid = (gridDim.x * kBlock) >> 5;
+    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) >> 5; s < nSlices; s += warpsPerGrid) {
+        const int r = (s << 5) + (int)lane;
+        if (r < N) {
+            const uint32_t len = rowLen[r];
+            const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
+            const uint32_t lb = (uint32_t)s * strideL + lane, ub = (uint32_t)s * strideU + lane;
+            // level 1
+            uint32_t pk[B];
+            int uc[B];
+            double uv[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) pk[k] = (k < nL) ? lRef[lb + 32u * k] : 0u;
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                uc[k] = (k < nU) ? uCol[ub + 32u * k] : r;
+                uv[k] = (k < nU) ? uVal[ub + 32u * k] : 0.0;
+            }
+            const double xr = x[r];
+            const double d = diag[r];
+            // level 2
+            double lv[B], lx[B], ux[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const uint32_t a = pk[k] >> 5;
+                const uint32_t pos = (a >> 5) * strideU + ((pk[k] & 31u) << 5) + (a & 31u);
+                lv[k] = (k < nL) ? uVal[pos] : 0.0;
+                lx[k] = (k < nL) ? __ldg(&x[a]) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k) ux[k] = (k < nU) ? __ldg(&x[uc[k]]) : 0.0;
+            // level 3: row sum in OpenFOAM's face order (lower faces ascending, then upper)
+            double acc = __dmul_rn(d, xr);
+            double sa = d;
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                if (k < nL) {
+                    acc = __dadd_rn(acc, __dmul_rn(lv[k], lx[k]));
+                    if (INIT) sa = __dadd_rn(sa, lv[k]);
+                }
+            for (int j = B; j < nL; ++j) {
+                const uint32_t p0 = lRef[lb + 32u * j];
+                const uint32_t a = p0 >> 5;
+                const double v0 = uVal[(a >> 5) * strideU + ((p0 & 31u) << 5) + (a & 31u)];
+                acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[a])));
+                if (INIT) sa = __dadd_rn(sa, v0);
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                if (k < nU) {
+                    acc = __dadd_rn(acc, __dmul_rn(uv[k], ux[k]));
+                    if (INIT) sa = __dadd_rn(sa, uv[k]);
+                }
+            for (int j = B; j < nU; ++j) {
+                const double v0 = uVal[ub + 32u * j];
+                acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[uCol[ub + 32u * j]])));
+                if (INIT) sa = __dadd_rn(sa, v0);
             }
             y[r] = acc;
             if (INIT) sA[r] = sa;
@@ -439,6 +536,96 @@ k_update(int N, double* __restrict__ psi, double* __restrict__ rA,
           double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
           psi[i] = x; rA[i] = r; s[0] = __dadd_rn(s[0], fabs(r)); })
     reduce_finish<1>(s, R);
+}
+
+// ---- fused PCG vector kernels ---------------------------------------------------------------
+// The loop body of OF-dev PCG.C is regrouped so that every vector is touched as few times as
+// possible, WITHOUT changing any element-wise operation or its rounding:
+//   k_p : psi += alpha_prev*pA (deferred from the previous iteration)      [if nIter > 0]
+//         pA  = z + beta*pA, z = rD*rA | rA | wA        (ZMODE 1 diagonal | 0 none | 2 DIC-class)
+//   Amul: wA = A pA, wApA                                                  (k_spmv*)
+//   k_r : rA -= alpha*wA; sum|rA|; and for ZMODE 0/1 the NEXT iteration's wArA = sum(z*rA)
+//   k_psi_final: the last deferred psi update, once, after the loop.
+// diagonal: 48N + 32N bytes of vector traffic per iteration instead of 24N + 24N + 48N.
+#define B200_Z(R_, D_, Z_) (ZMODE == 0 ? (R_) : (ZMODE == 1 ? __dmul_rn((D_), (R_)) : (Z_)))
+template <int ZMODE>
+__global__ void __launch_bounds__(kBlock)
+k_p(int N, double* __restrict__ psi, double* __restrict__ pA, const double* __restrict__ rA,
+    const double* __restrict__ rD, const double* __restrict__ zbuf, const Scalars* S) {
+    if (S->done) return;
+    const bool first = (S->nIter == 0);
+    const double beta = S->beta, alpha = S->alpha;
+    B200_VEC_LOOP(N,
+        { double2 r = make_double2(0.0, 0.0); double2 d = r; double2 z = r;
+          if (ZMODE != 2) r = reinterpret_cast<const double2*>(rA)[i];
+          if (ZMODE == 1) d = reinterpret_cast<const double2*>(rD)[i];
+          if (ZMODE == 2) z = reinterpret_cast<const double2*>(zbuf)[i];
+          double2 p;
+          p.x = B200_Z(r.x, d.x, z.x); p.y = B200_Z(r.y, d.y, z.y);
+          if (!first) {
+              const double2 po = reinterpret_cast<const double2*>(pA)[i];
+              double2 x = reinterpret_cast<double2*>(psi)[i];
+              x.x = __dadd_rn(x.x, __dmul_rn(alpha, po.x));
+              x.y = __dadd_rn(x.y, __dmul_rn(alpha, po.y));
+              reinterpret_cast<double2*>(psi)[i] = x;
+              p.x = __dadd_rn(p.x, __dmul_rn(beta, po.x));
+              p.y = __dadd_rn(p.y, __dmul_rn(beta, po.y));
+          }
+          reinterpret_cast<double2*>(pA)[i] = p; },
+        { const double r1 = (ZMODE != 2) ? rA[i] : 0.0;
+          const double d1 = (ZMODE == 1) ? rD[i] : 0.0;
+          const double z1 = (ZMODE == 2) ? zbuf[i] : 0.0;
+          double p = B200_Z(r1, d1, z1);
+          if (!first) {
+              const double po = pA[i];
+              psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, po));
+              p = __dadd_rn(p, __dmul_rn(beta, po));
+          }
+          pA[i] = p; })
+}
+#undef B200_Z
+
+template <int ZMODE>
+__global__ void __launch_bounds__(kBlock)
+k_r(int N, double* __restrict__ rA, const double* __restrict__ wA, const double* __restrict__ rD,
+    Reduce R) {
+    if (R.S->done) return;
+    const double alpha = R.S->alpha;
+    double s[2] = {0.0, 0.0};
+    B200_VEC_LOOP(N,
+        { double2 r = reinterpret_cast<double2*>(rA)[i];
+          const double2 w = reinterpret_cast<const double2*>(wA)[i];
+          r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
+          r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
+          reinterpret_cast<double2*>(rA)[i] = r;
+          s[0] = __dadd_rn(s[0], __dadd_rn(fabs(r.x), fabs(r.y)));
+          if (ZMODE == 1) {
+              const double2 d = reinterpret_cast<const double2*>(rD)[i];
+              s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(d.x, r.x), r.x));
+              s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(d.y, r.y), r.y));
+          } else if (ZMODE == 0) {
+              s[1] = __dadd_rn(s[1], __dmul_rn(r.x, r.x));
+              s[1] = __dadd_rn(s[1], __dmul_rn(r.y, r.y));
+          } },
+        { const double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
+          rA[i] = r;
+          s[0] = __dadd_rn(s[0], fabs(r));
+          if (ZMODE == 1) s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(rD[i], r), r));
+          else if (ZMODE == 0) s[1] = __dadd_rn(s[1], __dmul_rn(r, r)); })
+    reduce_finish<2>(s, R);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_psi_final(int N, double* __restrict__ psi, const double* __restrict__ pA, const Scalars* S) {
+    if (!S->pendingPsi) return;
+    const double alpha = S->alpha;
+    B200_VEC_LOOP(N,
+        { double2 x = reinterpret_cast<double2*>(psi)[i];
+          const double2 p = reinterpret_cast<const double2*>(pA)[i];
+          x.x = __dadd_rn(x.x, __dmul_rn(alpha, p.x));
+          x.y = __dadd_rn(x.y, __dmul_rn(alpha, p.y));
+          reinterpret_cast<double2*>(psi)[i] = x; },
+        { psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, pA[i])); })
 }
 
 // ---- DIC-class preconditioner (OF-dev DICPreconditioner.C) -----------------

@@ -195,6 +195,53 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
         for (int64_t jj = 0; jj < width; ++jj) P.col[base + 32 * jj] = 0;
     }
 
+    // ---- symmetric single-read layout -----------------------------------------------------
+    {
+        SymPlan& Sp = P.sym;
+        int64_t wU = 0, wL = 0;
+        for (int32_t r = 0; r < N; ++r) {
+            const int64_t nL = P.rowLen[r] & 0xffffu, nT = P.rowLen[r] >> 16;
+            wU = std::max(wU, nT - nL);
+            wL = std::max(wL, nL);
+        }
+        const int64_t nU = (int64_t)P.nSlices * 32 * wU, nL = (int64_t)P.nSlices * 32 * wL;
+        const bool ok = (N > 0) && (N <= (1 << 27)) && wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL;
+        if (ok) {
+            Sp.WU = (int32_t)wU;
+            Sp.WL = (int32_t)wL;
+            Sp.nU = nU;
+            Sp.nL = nL;
+            Sp.uCol.assign((size_t)nU, 0);
+            Sp.uFace.assign((size_t)nU, -1);
+            Sp.lRef.assign((size_t)nL, 0);
+#pragma omp parallel for schedule(static)
+            for (int32_t r = 0; r < N; ++r) {
+                const int64_t fb = P.sliceBase[r / 32] + (r % 32);
+                const int32_t nLo = (int32_t)(P.rowLen[r] & 0xffffu), nT = (int32_t)(P.rowLen[r] >> 16);
+                const int64_t ub = (int64_t)(r / 32) * 32 * wU + (r % 32);
+                const int64_t lb = (int64_t)(r / 32) * 32 * wL + (r % 32);
+                for (int32_t j = nLo; j < nT; ++j) {
+                    Sp.uCol[ub + 32 * (int64_t)(j - nLo)] = P.col[fb + 32 * (int64_t)j];
+                    Sp.uFace[ub + 32 * (int64_t)(j - nLo)] = P.faceOf[fb + 32 * (int64_t)j];
+                }
+                for (int64_t jj = nT - nLo; jj < wU; ++jj) Sp.uCol[ub + 32 * jj] = r;
+                for (int32_t j = 0; j < nLo; ++j) {
+                    const int32_t a = P.col[fb + 32 * (int64_t)j], f = P.faceOf[fb + 32 * (int64_t)j];
+                    // q = position of face f among the upper entries of row a
+                    const int64_t ab = P.sliceBase[a / 32] + (a % 32);
+                    const int32_t aL = (int32_t)(P.rowLen[a] & 0xffffu), aT = (int32_t)(P.rowLen[a] >> 16);
+                    int32_t q = 0;
+                    for (int32_t k = aL; k < aT; ++k)
+                        if (P.faceOf[ab + 32 * (int64_t)k] == f) { q = k - aL; break; }
+                    Sp.lRef[lb + 32 * (int64_t)j] = ((uint32_t)a << 5) | (uint32_t)q;
+                }
+            }
+            Sp.valid = true;
+        } else {
+            P.sym = SymPlan();
+        }
+    }
+
     // ---- interfaces ---------------------------------------------------------------------
     P.nIfaces = nIfaces;
     P.nbrRank.resize((size_t)nIfaces);

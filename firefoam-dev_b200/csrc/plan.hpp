@@ -32,8 +32,28 @@ struct IfaceIn {
     const int32_t* faceCells;
 };
 
+// Symmetric "single-read" Amul layout.  The matrix is stored ONCE: the later-in-order ("upper")
+// entries of every row in a sliced ELL (value + column, coalesced).  A row's earlier ("lower")
+// entries are 32-bit references (owner row a << 5 | q): the value is re-read from a's q-th upper
+// entry, which was streamed moments earlier by a's own thread and is served by the 126 MB L2 on
+// any bandwidth-reducing cell order (for the 16 M-cell hex box the reuse distance is < 5 MB).
+// DRAM bytes per Amul: 16 F + 24 N + 4 N (row lengths) -- the algorithmic LDU minimum + 4 N --
+// with no shared memory, no barriers, no atomics, and the row-sum order of OpenFOAM's face loop.
+// Slices have a uniform width (global max row length) so that the position of an owner's entry
+// is pure arithmetic (no offset-table lookup in the dependent-load chain); padded entries are
+// never loaded, so the padding costs address space, not bandwidth.
+struct SymPlan {
+    bool valid = false;
+    int32_t WU = 0, WL = 0;       // uniform slice widths: entry j of row r at (r/32)*32*W + 32*j + r%32
+    int64_t nU = 0, nL = 0;       // padded entry counts (< 2^31: 32-bit positions on the device)
+    std::vector<int32_t> uCol;    // [nU] column (padding: the row itself)
+    std::vector<int32_t> uFace;   // [nU] natural face, -1 padding
+    std::vector<uint32_t> lRef;   // [nL] (owner row << 5) | q
+};
+
 struct HostPlan {
     Ordering ordering = Ordering::Natural;
+    SymPlan sym;
     int32_t N = 0, F = 0;
     // row order
     std::vector<int32_t> perm;         // internal row -> natural cell  (empty == identity)

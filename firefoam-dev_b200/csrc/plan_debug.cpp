@@ -47,9 +47,14 @@ int64_t b200_debug_plan_get(void* h, const char* name, const void** ptr, int32_t
     V("sliceBase", P.sliceBase) V("rowLen", P.rowLen) V("col", P.col) V("faceOf", P.faceOf)
     V("nbrRank", P.nbrRank) V("patchStart", P.patchStart) V("slotRow", P.slotRow)
     V("bRow", P.bRow) V("bStart", P.bStart) V("bSlot", P.bSlot)
+    V("sym.uCol", P.sym.uCol)
+    V("sym.uFace", P.sym.uFace) V("sym.lRef", P.sym.lRef)
 #undef V
     return -1;
 }
+int32_t b200_debug_plan_sym_valid(void* h) { return ((HostPlan*)h)->sym.valid ? 1 : 0; }
+int32_t b200_debug_plan_sym_wu(void* h) { return ((HostPlan*)h)->sym.WU; }
+int32_t b200_debug_plan_sym_wl(void* h) { return ((HostPlan*)h)->sym.WL; }
 int32_t b200_debug_plan_ncolours(void* h) { return ((HostPlan*)h)->nColours; }
 int64_t b200_debug_plan_nentries(void* h) { return ((HostPlan*)h)->nEntries; }
 }

@@ -76,12 +76,13 @@ NcclApi g_nccl;
 enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_PUPDATE, PC_UPDATE, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
-    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_COUNT
+    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
     "norm_resid", "recip", "precond_dot", "p_update", "update_psi_r", "dic_calc_rd", "dic_fwd",
-    "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step"};
+    "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
+    "r_update_dots", "psi_final"};
 
 struct DevPlan {
     bool built = false;
@@ -94,6 +95,13 @@ struct DevPlan {
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
     int nSlots = 0;
+    // symmetric single-read layout (SymPlan)
+    bool sym = false;
+    int64_t symNU = 0;
+    int symWU = 0, symWL = 0;
+    int *sUCol = nullptr, *sUFace = nullptr;
+    double* sUVal = nullptr;
+    uint32_t* sLRef = nullptr;
 };
 
 struct HostIface {
@@ -132,6 +140,7 @@ struct b200_ctx {
     double* partials = nullptr;
     uint64_t launches = 0;
     int32_t forceIters = 0;
+    bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
     // profiling
     bool prof = false;
     bool profOpen = false;
@@ -239,6 +248,9 @@ void free_plan(DevPlan& P) {
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot);
+    dev_free(P.sUCol); dev_free(P.sUFace);
+    dev_free(P.sUVal); dev_free(P.sLRef);
+    P.sym = false;
     P.built = false;
     P.h = HostPlan();
 }
@@ -276,7 +288,22 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     RET(upload(ctx, &P.bStart, P.h.bStart));
     RET(upload(ctx, &P.bSlot, P.h.bSlot));
     P.nSlots = (int)P.h.slotRow.size();
+    // permuted (colour-major) orders put a row's earlier neighbours hundreds of MB upstream: the
+    // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
+    if (P.h.sym.valid && !ctx->disableSym && ord == Ordering::Natural) {
+        SymPlan& Y = P.h.sym;
+        RET(upload(ctx, &P.sUCol, Y.uCol));
+        RET(upload(ctx, &P.sUFace, Y.uFace));
+        RET(upload(ctx, &P.sLRef, Y.lRef));
+        RET(dev_alloc(ctx, &P.sUVal, (size_t)Y.nU));
+        P.symNU = Y.nU;
+        P.symWU = Y.WU;
+        P.symWL = Y.WL;
+        P.sym = true;
+    }
     CU(cudaStreamSynchronize(ctx->sc));
+    P.h.sym = SymPlan();
+
     // release the big host arrays
     std::vector<int32_t>().swap(P.h.col);
     std::vector<int32_t>().swap(P.h.faceOf);
@@ -334,9 +361,15 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R{ctx->S, ctx->partials, halo ? STEP_NONE : step};
-    auto kern = k_spmv<INIT, DOT>;
-    LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.col,
-           P.val, ctx->diag, x, y, sA, R);
+    if (P.sym) {
+        auto kern = k_spmv_sym<INIT, DOT>;
+        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.rowLen,
+               P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
+    } else {
+        auto kern = k_spmv<INIT, DOT>;
+        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen,
+               P.col, P.val, ctx->diag, x, y, sA, R);
+    }
     if (halo) {
         CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
         Reduce R2{ctx->S, ctx->partials, step};
@@ -383,22 +416,24 @@ int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* 
                 const double* dn_src, const double* dn_psi) {
     const int N = ctx->N;
     LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
+    if (P.sym)
+        LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.symNU, 16), P.symNU, P.sUFace, dn_upper, P.sUVal);
     LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_diag, ctx->diag);
     if (dn_src) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_src, ctx->src);
     if (dn_psi) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_psi, ctx->psi);
     return B200_OK;
 }
 
-int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
+// precondition rA -> wA and form wArA = (wA, rA) [STEP_WARA]; used once before the loop for every
+// mode and, for the DIC-class modes, after every iteration (none/diagonal fuse it into k_r).
+int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
     const int N = ctx->N;
     Scalars* S = ctx->S;
-    const double* z = ctx->w;
     const int gv = grid_for(ctx, (N + 1) / 2);
     if (precond == B200_PRECOND_NONE) {
         Reduce R{S, ctx->partials, STEP_WARA};
         auto k = k_precond_dot<false>;
         LAUNCH(PC_PRECOND_DOT, k, gv, N, (const double*)nullptr, ctx->r, (double*)nullptr, R);
-        z = ctx->r;
     } else if (precond == B200_PRECOND_DIAGONAL) {
         Reduce R{S, ctx->partials, STEP_WARA};
         auto k = k_precond_dot<true>;
@@ -427,11 +462,43 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
         }
     }
     RET(reduce_post(ctx, STEP_WARA));
-    LAUNCH(PC_PUPDATE, k_pupdate, gv, N, z, ctx->p, S);
+    return B200_OK;
+}
+
+// One loop body of PCG::solve, regrouped (see kernels.cuh "fused PCG vector kernels"):
+//   k_p -> Amul+wApA -> k_r (+ next wArA) [-> DIC-class sweeps + next wArA]
+int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
+    const int N = ctx->N;
+    Scalars* S = ctx->S;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    if (precond == B200_PRECOND_NONE) {
+        auto k = k_p<0>;
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+    } else if (precond == B200_PRECOND_DIAGONAL) {
+        auto k = k_p<1>;
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+    } else {
+        auto k = k_p<2>;
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+    }
     RET((spmv_full<false, true>(ctx, P, ctx->p, ctx->w, nullptr, STEP_WAPA)));
-    Reduce R{S, ctx->partials, STEP_RES};
-    LAUNCH(PC_UPDATE, k_update, gv, N, ctx->psi, ctx->r, ctx->p, ctx->w, R);
-    RET(reduce_post(ctx, STEP_RES));
+    if (precond == B200_PRECOND_NONE) {
+        Reduce R{S, ctx->partials, STEP_RES_WARA};
+        auto k = k_r<0>;
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        RET(reduce_post(ctx, STEP_RES_WARA));
+    } else if (precond == B200_PRECOND_DIAGONAL) {
+        Reduce R{S, ctx->partials, STEP_RES_WARA};
+        auto k = k_r<1>;
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        RET(reduce_post(ctx, STEP_RES_WARA));
+    } else {
+        Reduce R{S, ctx->partials, STEP_RES};
+        auto k = k_r<2>;
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        RET(reduce_post(ctx, STEP_RES));
+        RET(enqueue_precondition(ctx, P, precond));
+    }
     return B200_OK;
 }
 
@@ -489,6 +556,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         }
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
     }
+    RET(enqueue_precondition(ctx, P, ctl->precond));   // early-exits on the device if converged
     CU(cudaEventRecord(ctx->ev[1], ctx->sc));
     CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
@@ -508,6 +576,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         CU(cudaGetLastError());
         if (chunk < 64) chunk *= 2;
     }
+    LAUNCH(PC_PSI_FINAL, k_psi_final, gv, N, ctx->psi, ctx->p, S);
     CU(cudaEventRecord(ctx->ev[2], ctx->sc));
     LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
     CU(cudaStreamSynchronize(ctx->sc));
@@ -597,6 +666,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
                                         " (sm_" + std::to_string(prop.major * 10 + prop.minor) +
                                         "); libb200pcg is built for sm_100a only");
     c->numSMs = prop.multiProcessorCount;
+    if (const char* e2 = getenv("B200PCG_SPMV")) c->disableSym = (std::string(e2) == "ell");
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->sm, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming)) != cudaSuccess ||

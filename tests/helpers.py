@@ -31,6 +31,17 @@ class PlanView:
         if not h:
             raise ValueError(L.b200_debug_plan_error().decode())
         try:
+            L.b200_debug_plan_sym_valid.argtypes = [C.c_void_p]
+            self.symValid = bool(L.b200_debug_plan_sym_valid(h))
+            self.sym = {}
+            L.b200_debug_plan_sym_wu.argtypes = [C.c_void_p]
+            L.b200_debug_plan_sym_wl.argtypes = [C.c_void_p]
+            self.symWU, self.symWL = L.b200_debug_plan_sym_wu(h), L.b200_debug_plan_sym_wl(h)
+            for nm, dt in (("uCol", np.int32), ("uFace", np.int32), ("lRef", np.uint32)):
+                ptr, eb = C.c_void_p(), C.c_int32()
+                n = L.b200_debug_plan_get(h, ("sym." + nm).encode(), C.byref(ptr), C.byref(eb))
+                self.sym[nm] = (np.empty(0, dtype=dt) if n <= 0 else
+                                np.frombuffer((C.c_char * (n * eb.value)).from_address(ptr.value), dtype=dt).copy())
             self.nColours = L.b200_debug_plan_ncolours(h)
             self.nEntries = L.b200_debug_plan_nentries(h)
             for nm in self.NAMES:
@@ -78,6 +89,30 @@ class PlanView:
                 acc = acc + val[e] * x_i[self.col[e]]
             y[r] = acc
         return y
+
+    def spmv_sym(self, diag_i, upper, x_i):
+        """numpy emulation of k_spmv_sym: upper entries streamed, lower entries by reference."""
+        y = self.sym
+        uv = np.zeros(y["uCol"].size)
+        m = y["uFace"] >= 0
+        uv[m] = upper[y["uFace"][m]]
+        out = np.empty(self.N)
+        for r in range(self.N):
+            nL, nU = int(self.nLower[r]), int(self.nTotal[r] - self.nLower[r])
+            acc = diag_i[r] * x_i[r]
+            lb = (r // 32) * 32 * self.symWL + (r % 32)
+            for j in range(nL):
+                pk = int(y["lRef"][lb + 32 * j])
+                a, q = pk >> 5, pk & 31
+                assert a < r
+                acc = acc + uv[(a // 32) * 32 * self.symWU + 32 * q + (a % 32)] * x_i[a]
+            ub = (r // 32) * 32 * self.symWU + (r % 32)
+            for j in range(nU):
+                c = y["uCol"][ub + 32 * j]
+                assert c > r
+                acc = acc + uv[ub + 32 * j] * x_i[c]
+            out[r] = acc
+        return out
 
     def dic_calc_rd(self, diag_i, val):
         rD = np.empty(self.N)

@@ -1,0 +1,66 @@
+"""Worker of tests/test_multigpu.py: one process per GPU (torchrun), NCCL halos + all-reduces
+through libb200pcg, checked on rank 0 against the N-rank CPU oracle and the 1-rank oracle."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import firefoam_dev_b200 as pkg  # noqa: E402
+from firefoam_dev_b200 import meshgen as mg  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    buf.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
+dist.broadcast(buf, 0)
+ctx = pkg.Context(device=local, rank=rank, nranks=world, nccl_uid=buf.cpu().numpy().tobytes())
+
+PROCS = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+DIMS = (24, 20, 16)
+results = {}
+s = mg.hex_block(*DIMS, *PROCS, rank)
+ctx.set_addressing(s.addr)
+
+# Amul with halo exchange
+x = np.random.default_rng(100 + rank).standard_normal(s.addr.nCells)
+y = ctx.amul(s.matrix, s.bou, x)
+ys = [torch.zeros(1)] * world
+gather = [None] * world
+dist.all_gather_object(gather, (x, y))
+if rank == 0:
+    subs = [mg.hex_block(*DIMS, *PROCS, r) for r in range(world)]
+    ref = orc.amul(subs, [g[0] for g in gather])
+    results["amul_bit_exact"] = all(np.array_equal(ref[r], gather[r][1]) for r in range(world))
+
+for pre, exact in (("diagonal", False), ("none", False), ("DIC", True), ("DIC", False)):
+    ctl = {"preconditioner": pre, "tolerance": 1e-8, "relTol": 0.0, "maxIter": 3000}
+    if exact:
+        ctl["B200"] = {"dicMode": "exact"}
+    psi = np.zeros(s.addr.nCells)
+    perf = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, ctl, context=ctx).solve(psi, s.source)
+    allpsi = [None] * world
+    dist.all_gather_object(allpsi, psi)
+    if rank == 0:
+        key = pre + ("-exact" if exact else "")
+        subs = [mg.hex_block(*DIMS, *PROCS, r) for r in range(world)]
+        ref = [np.zeros(x_.addr.nCells) for x_ in subs]
+        pr = orc.pcg_solve(subs, ref, "DIC" if pre == "DIC" else pre, 1e-8, 0.0, 3000)
+        err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
+        xerr = max(np.abs(a - x_.xstar).max() for a, x_ in zip(allpsi, subs))
+        results[key] = {"iters": perf.nIterations, "oracle_iters": pr.nIterations, "relerr_vs_oracle": err,
+                        "err_vs_xstar": xerr, "converged": bool(perf.converged),
+                        "init": perf.initialResidual, "oracle_init": pr.initialResidual}
+if rank == 0:
+    print("MGPU_RESULT " + json.dumps(results))
+ctx.close()
+dist.destroy_process_group()

@@ -1,0 +1,43 @@
+"""Multi-GPU parity (needs >= 2 GPUs: run with `gpurun --gpus 2`): NCCL send/recv halos overlapped
+with the interior Amul, NCCL all-reduce of the CG scalars, against the N-rank CPU oracle (pthreads,
+rank-ascending sums).  Rank-local DIC (block-Jacobi, like upstream) makes DIC iteration counts
+depend on the decomposition -- the N-rank oracle has the same decomposition."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    try:
+        from firefoam_dev_b200 import _lib
+        return _lib.load_pcg().b200_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multigpu_parity(world):
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
+           os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
+    res = json.loads(line[len("MGPU_RESULT "):])
+    assert res["amul_bit_exact"]
+    for key in ("diagonal", "DIC-exact"):
+        assert res[key]["iters"] == res[key]["oracle_iters"], (key, res[key])
+        assert res[key]["relerr_vs_oracle"] < 1e-11, (key, res[key])
+        assert res[key]["init"] == pytest.approx(res[key]["oracle_init"], rel=1e-12)
+    assert res["none"]["converged"] and res["none"]["relerr_vs_oracle"] < 1e-5
+    assert res["DIC"]["converged"] and res["DIC"]["relerr_vs_oracle"] < 1e-6
+    assert res["DIC"]["iters"] < res["diagonal"]["iters"]

@@ -56,6 +56,24 @@ def test_spmv_emulation_bit_exact_natural(name, s):
     assert np.array_equal(y, orc.amul(s, x)[0])
 
 
+@pytest.mark.parametrize("name,s", list(systems()) + [("hex-larger", mg.hex_block(40, 9, 8))])
+def test_symmetric_single_read_layout(name, s):
+    """SymPlan: every face stored once; same row-sum order as OpenFOAM -> bit-identical Amul."""
+    x = np.random.default_rng(6).standard_normal(s.addr.nCells)
+    ref = orc.amul(s, x)[0]
+    for ordering in (NAT, MC, LEV):
+        P = PlanView(ordering, s.addr)
+        assert P.symValid
+        m = P.sym["uFace"] >= 0
+        assert np.array_equal(np.bincount(P.sym["uFace"][m], minlength=s.addr.nFaces),
+                              np.ones(s.addr.nFaces, dtype=np.int64))
+        y = P.to_natural(P.spmv_sym(P.to_internal(s.diag), s.upper, P.to_internal(x)))
+        if ordering == NAT:
+            assert np.array_equal(y, ref)
+        else:
+            np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-15)
+
+
 @pytest.mark.parametrize("name,s", list(systems()))
 def test_spmv_emulation_permuted(name, s):
     x = np.random.default_rng(2).standard_normal(s.addr.nCells)

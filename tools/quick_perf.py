@@ -44,6 +44,8 @@ for k, v in prof.items():
     print(line)
 ctx.force_iterations(0)
 ctx.profile(False)
+if len(sys.argv) > 6 and sys.argv[6] == "noconv":
+    sys.exit(0)
 psi = np.zeros(N)
 t0 = time.time()
 perf = ctx.solve(s.diag, s.upper, [], s.source, psi, ctl)
