@@ -1,0 +1,260 @@
+/*---------------------------------------------------------------------------*\
+  B200PCG.C -- see B200PCG.H.  Thin glue: OpenFOAM objects -> C ABI of
+  include/b200pcg.h -> solverPerformance.  No arithmetic here.
+\*---------------------------------------------------------------------------*/
+
+#include "B200PCG.H"
+#include "processorLduInterface.H"
+#include "processorLduInterfaceField.H"
+#include "Pstream.H"
+#include "DynamicList.H"
+
+#include "b200pcg.h"
+
+#include <cstdlib>
+#include <cstdint>
+
+// * * * * * * * * * * * * * * Static Data Members * * * * * * * * * * * * * //
+
+namespace Foam
+{
+    defineTypeNameAndDebug(B200PCG, 0);
+
+    lduMatrix::solver::addsymMatrixConstructorToTable<B200PCG>
+        addB200PCGSymMatrixConstructorToTable_;
+
+    // labels are handed to the library as int32, scalars as double
+    static_assert(sizeof(label) == 4, "B200PCG needs WM_LABEL_SIZE=32");
+    static_assert(sizeof(scalar) == 8, "B200PCG needs WM_PRECISION_OPTION=DP");
+}
+
+
+// * * * * * * * * * * * * * * * Local Functions * * * * * * * * * * * * * * //
+
+namespace
+{
+
+//- One library context per MPI rank, created on first use.
+//  rank r drives GPU (r mod deviceCount); the NCCL unique id is made on the
+//  master and scattered with OpenFOAM's own Pstream.
+b200_ctx* context()
+{
+    static b200_ctx* ctx = nullptr;
+    if (ctx) return ctx;
+
+    using namespace Foam;
+
+    const int nDev = b200_device_count();
+    if (nDev < 1)
+    {
+        FatalErrorInFunction
+            << "B200PCG: no CUDA device visible; this solver has no CPU fallback"
+            << exit(FatalError);
+    }
+
+    List<char> uid(128, '\0');
+    if (Pstream::parRun())
+    {
+        if (Pstream::master())
+        {
+            if (b200_get_unique_id(uid.begin()) != B200_OK)
+            {
+                FatalErrorInFunction
+                    << "B200PCG: " << b200_last_error(nullptr) << exit(FatalError);
+            }
+        }
+        Pstream::scatter(uid);
+    }
+
+    const int rank = Pstream::parRun() ? Pstream::myProcNo() : 0;
+    const int nRanks = Pstream::parRun() ? Pstream::nProcs() : 1;
+
+    if
+    (
+        b200_ctx_create
+        (
+            rank % nDev, rank, nRanks,
+            nRanks > 1 ? uid.begin() : nullptr,
+            &ctx
+        ) != B200_OK
+    )
+    {
+        FatalErrorInFunction
+            << "B200PCG: " << b200_last_error(nullptr) << exit(FatalError);
+    }
+
+    if (std::getenv("B200PCG_PROFILE")) b200_profile_enable(ctx, 1);
+
+    return ctx;
+}
+
+} // End anonymous namespace
+
+
+// * * * * * * * * * * * * * * * * Constructors  * * * * * * * * * * * * * * //
+
+Foam::B200PCG::B200PCG
+(
+    const word& fieldName,
+    const lduMatrix& matrix,
+    const FieldField<Field, scalar>& interfaceBouCoeffs,
+    const FieldField<Field, scalar>& interfaceIntCoeffs,
+    const lduInterfaceFieldPtrsList& interfaces,
+    const dictionary& solverControls
+)
+:
+    lduMatrix::solver
+    (
+        fieldName,
+        matrix,
+        interfaceBouCoeffs,
+        interfaceIntCoeffs,
+        interfaces,
+        solverControls
+    )
+{}
+
+
+// * * * * * * * * * * * * * * * Member Functions  * * * * * * * * * * * * * //
+
+Foam::solverPerformance Foam::B200PCG::solve
+(
+    scalarField& psi,
+    const scalarField& source,
+    const direction cmpt
+) const
+{
+    const word preconditionerName(lduMatrix::preconditioner::getName(controlDict_));
+
+    // --- Setup class containing solver performance data
+    solverPerformance solverPerf(preconditionerName + typeName, fieldName_);
+
+    b200_controls ctl;
+    ctl.tolerance = tolerance_;
+    ctl.relTol = relTol_;
+    ctl.maxIter = maxIter_;
+    ctl.minIter = minIter_;
+    ctl.reserved = 0;
+
+    if (preconditionerName == "none")
+    {
+        ctl.precond = B200_PRECOND_NONE;
+    }
+    else if (preconditionerName == "diagonal")
+    {
+        ctl.precond = B200_PRECOND_DIAGONAL;
+    }
+    else if (preconditionerName == "DIC" || preconditionerName == "FDIC")
+    {
+        const word mode
+        (
+            controlDict_.subOrEmptyDict("B200").lookupOrDefault<word>
+            (
+                "dicMode", "multicolour"
+            )
+        );
+        ctl.precond =
+            (mode == "exact") ? B200_PRECOND_DIC_EXACT : B200_PRECOND_DIC_MC;
+    }
+    else
+    {
+        FatalErrorInFunction
+            << "B200PCG: unsupported preconditioner " << preconditionerName
+            << "; valid: none diagonal DIC" << exit(FatalError);
+    }
+
+    if (!matrix_.symmetric() && !matrix_.diagonal())
+    {
+        FatalErrorInFunction
+            << "B200PCG: matrix is not symmetric" << exit(FatalError);
+    }
+
+    // --- coupled (processor) interfaces; the UPtrList has null slots for
+    //     non-coupled patches
+    const lduAddressing& addr = matrix_.lduAddr();
+    DynamicList<b200_iface> ifaces(interfaces_.size());
+    DynamicList<const double*> bou(interfaces_.size());
+
+    forAll(interfaces_, patchi)
+    {
+        if (!interfaces_.set(patchi)) continue;
+
+        if (!isA<processorLduInterfaceField>(interfaces_[patchi]))
+        {
+            FatalErrorInFunction
+                << "B200PCG: unsupported coupled interface "
+                << interfaces_[patchi].type() << " on patch " << patchi
+                << " (only processor interfaces are supported)"
+                << exit(FatalError);
+        }
+
+        const processorLduInterface& pi =
+            refCast<const processorLduInterface>
+            (
+                interfaces_[patchi].interface()
+            );
+
+        const labelUList& faceCells = addr.patchAddr(patchi);
+
+        b200_iface itf;
+        itf.nbrRank = pi.neighbProcNo();
+        itf.nFaces = faceCells.size();
+        itf.faceCells = faceCells.begin();
+        itf.tag = pi.tag();
+        ifaces.append(itf);
+        bou.append(interfaceBouCoeffs_[patchi].begin());
+    }
+
+    b200_ctx* ctx = context();
+
+    // idempotent per mesh: keyed by the address of the lduAddressing object
+    if
+    (
+        b200_set_addressing
+        (
+            ctx,
+            uint64_t(uintptr_t(&addr)),
+            addr.size(),
+            addr.lowerAddr().size(),
+            addr.lowerAddr().begin(),
+            addr.upperAddr().begin(),
+            ifaces.size(),
+            ifaces.begin()
+        ) != B200_OK
+    )
+    {
+        FatalErrorInFunction
+            << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    b200_perf perf;
+
+    const int rc = b200_solve
+    (
+        ctx,
+        matrix_.diag().begin(),
+        matrix_.upper().begin(),
+        bou.begin(),
+        source.begin(),
+        psi.begin(),
+        &ctl,
+        &perf
+    );
+
+    if (rc != B200_OK)
+    {
+        FatalErrorInFunction
+            << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    solverPerf.initialResidual() = perf.initialResidual;
+    solverPerf.finalResidual() = perf.finalResidual;
+    solverPerf.nIterations() = perf.nIterations;
+    solverPerf.checkConvergence(tolerance_, relTol_);
+    if (perf.singular)
+    {
+        solverPerf.checkSingularity(0);   // flags the component as singular
+    }
+
+    return solverPerf;
+}
