@@ -361,7 +361,7 @@ def run_gpu(args):
                           "frac": iter_bytes / (1e-3 * solve_ms / max(iters, 1)) / 1e9 / peak},
         "fixed_200_iterations": {"ms": fixed_ms, "iters": pf.nIterations,
                                  "gdof_iter_per_s": n_global * pf.nIterations / (fixed_ms * 1e-3) / 1e9},
-        "roofline": {"kernel": "k_spmv<false,true> (lduMatrix::Amul fused with gSumProd(wA,pA))",
+        "roofline": {"kernel": "k_spmv_sym_tma<true,2> (lduMatrix::Amul fused with gSumProd(wA,pA); symmetric single-read layout, bulk-copy staged)",
                      "bound": "hbm", "achieved": dom.get("gbs"), "peak": peak, "unit": "GB/s",
                      "frac": dom.get("frac"), "traffic": traffic, "peak_source": peak_src,
                      "alg_bytes_per_launch": dom.get("alg_bytes"), "avg_us": dom.get("avg_us")},

@@ -125,6 +125,8 @@ def load_mesh():
     vp = C.c_void_p
     L.b200mesh_hex_sizes.argtypes = [C.c_int] * 7 + [vp]
     L.b200mesh_hex_fill.argtypes = [C.c_int] * 7 + [C.c_uint64, C.c_double, C.c_double, C.c_double] + [vp] * 12
+    L.b200mesh_bcc_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, vp]
+    L.b200mesh_bcc_fill.argtypes = [C.c_uint64, C.c_double, C.c_double, C.c_double] + [vp] * 11
     L.b200mesh_partition_simple.argtypes = [C.c_int32, vp, C.c_int, C.c_int, C.c_int, vp]
     L.b200mesh_partition_hierarchical.argtypes = [C.c_int32, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.b200mesh_partition_rcb.argtypes = [C.c_int32, vp, C.c_int, vp]

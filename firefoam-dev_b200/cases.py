@@ -1,50 +1,71 @@
 """Restated reference cases for the hot path (no OpenFOAM here, so the case files are turned into
-LDU systems by hand; SURVEY.md Appendix B).
+LDU systems by hand; SURVEY.md Appendix B and 8d).
 
-StecklerHydrostatic: the hydrostatic-initialisation loop of solver/phrghEqn.H:19-60 on
-cases/steckler (30 x 15 x 20 box, constant/polyMesh/blockMeshDict:50; compartment baffles from
-system/topoSetDictCompartment + system/createBafflesDict), which is the reference's only pinned
-instance of PCG results: cases/steckler/original/linux64/log.fireFoam:92-100.
+HydrostaticBox        the hydrostatic-initialisation loop of solver/phrghEqn.H:19-60 on a uniform box
+                      mesh with optional internal baffles.
+StecklerHydrostatic   cases/steckler (30 x 15 x 20, constant/polyMesh/blockMeshDict:50; compartment
+                      baffles from system/topoSetDictCompartment + system/createBafflesDict): the
+                      reference's only pinned instance of PCG results,
+                      cases/steckler/original/linux64/log.fireFoam:92-100.            (BASELINE config 2)
+SingleBoxHydrostatic  the 7 x 5 x 7 base block of cases/singleBox/constant/polyMesh/blockMeshDict:53
+                      with the BCs of cases/singleBox/0/ph_rgh.orig (snappyHexMesh refinement is not
+                      reproducible here); PCG + diagonal plumbing case.                 (BASELINE config 1)
+steckler_p_rgh_system synthetic p_rgh-shaped system on the steckler topology:
+                      no per-time-step matrix dumps exist in the reference.
 """
 import numpy as np
 
 from .ldu import LduAddressing, LduMatrix
 
 
-class StecklerHydrostatic:
-    NX, NY, NZ = 30, 15, 20
-    H = 0.2
-    # 0/T, 0/O2, 0/N2, constant/thermo.compressibleGas, constant/g, constant/hRef, constant/pRef
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def uniform_pm1(seed, counters):
+    """counter-based U(-1, 1) (splitmix64), same recipe as csrc/meshgen.cpp"""
+    with np.errstate(over="ignore"):
+        c = np.asarray(counters, dtype=np.uint64)
+        r = _splitmix64(np.uint64(seed) ^ (c * np.uint64(0xD1342543DE82EF95) + np.uint64(0x2545F4914F6CDD1D)))
+    return ((r >> np.uint64(11)).astype(np.float64) + 0.5) * (2.0 / 9007199254740992.0) - 1.0
+
+
+class HydrostaticBox:
+    # 0/T, 0/O2, 0/N2, constant/thermo.compressibleGas, constant/g, constant/pRef (same in both cases)
     T, Y_O2, Y_N2 = 298.15, 0.23301, 0.76699
     W_O2, W_N2, RR = 31.9988, 28.0134, 8314.47
-    G, HREF, PREF = 9.81, 3.0, 101325.0
-    # cases/steckler/system/fvSolution:43-46 (ph_rgh: $p_rgh -> tolerance 1e-6, relTol 0.01)
-    TOL, RELTOL = 1e-6, 0.01
-    N_CORR = 5  # nHydrostaticCorrectors, fvSolution:92
+    G, PREF = 9.81, 101325.0
+    TOL, RELTOL = 1e-6, 0.01   # fvSolution ph_rgh { $p_rgh; }
+    N_CORR = 5                 # nHydrostaticCorrectors
 
-    def __init__(self):
-        nx, ny, nz, h = self.NX, self.NY, self.NZ, self.H
+    def __init__(self, nx, ny, nz, dx, dy, dz, href, baffle=None):
+        self.dims, self.d = (nx, ny, nz), (dx, dy, dz)
+        self.HREF = href
         N = nx * ny * nz
         c = np.arange(N)
         i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
-        inside = (i >= 3) & (i <= 16) & (j >= 0) & (j <= 10) & (k >= 3) & (k <= 16)
+        self.ijk = (i, j, k)
+        area = (dy * dz, dx * dz, dx * dy)
+        dist = (dx, dy, dz)
         faces = []
         for d, (di, dj, dk, stride) in enumerate(((1, 0, 0, 1), (0, 1, 0, nx), (0, 0, 1, nx * ny))):
             ok = (i + di < nx) & (j + dj < ny) & (k + dk < nz)
             own = c[ok]
             nei = own + stride
-            baffle = inside[own] != inside[nei]
-            if d == 0:  # doorway: faces on the x = 1.4 plane (between i=16 and i=17)
-                door = (i[own] == 16) & (j[own] <= 4) & (k[own] >= 7) & (k[own] <= 12)
-                baffle &= ~door
-            own, nei = own[~baffle], nei[~baffle]
+            if baffle is not None:
+                keep = ~baffle(d, own, nei, i, j, k)
+                own, nei = own[keep], nei[keep]
             faces.append(np.stack([own, nei, np.full(own.size, d)], axis=1))
         fa = np.concatenate(faces)
-        order = np.lexsort((fa[:, 1], fa[:, 0]))   # upper-triangular order
-        fa = fa[order]
+        fa = fa[np.lexsort((fa[:, 1], fa[:, 0]))]     # upper-triangular order
         self.addr = LduAddressing(N, fa[:, 0].astype(np.int32), fa[:, 1].astype(np.int32))
         self.N, self.F = N, fa.shape[0]
-        self.y_cell = (j + 0.5) * h
+        self.magSf = np.array(area)[fa[:, 2]]
+        self.deltaCoeffs = 1.0 / np.array(dist)[fa[:, 2]]
+        self.y_cell = (j + 0.5) * dy
         yl, yu = self.y_cell[fa[:, 0]], self.y_cell[fa[:, 1]]
         self.ghf = self.G * (self.HREF - 0.5 * (yl + yu))
         self.gh = self.G * (self.HREF - self.y_cell)
@@ -61,15 +82,17 @@ class StecklerHydrostatic:
         """One corrector's ph_rghEqn: fvm::laplacian(rhof, ph_rgh) == fvc::div(phig)
         (phrghEqn.H:32-46).  `laplacian(gamma_f, magSf, deltaCoeffs, sign, diag0) -> (upper, diag)`
         is the assembly under test (oracle or CUDA)."""
-        h = self.H
+        dy = self.d[1]
         l, u = self.addr.lowerAddr, self.addr.upperAddr
         rhof = 0.5 * (self.rho[l] + self.rho[u])
-        snGrad = (self.rho[u] - self.rho[l]) / h
-        phig = -rhof * self.ghf * snGrad * (h * h)
-        # top patch fixedValue 0: internalCoeffs = -rho_b*magSf*deltaCoeffs_b, deltaCoeffs_b = 2/h
+        snGrad = (self.rho[u] - self.rho[l]) * self.deltaCoeffs
+        phig = -rhof * self.ghf * snGrad * self.magSf
+        # top patch fixedValue 0: internalCoeffs = -rho_b*magSf_b*deltaCoeffs_b, deltaCoeffs_b = 2/dy;
+        # the fixedFluxPressure patches contribute nothing (their gradient cancels fvc::div's
+        # boundary flux, SURVEY.md Appendix B.3)
         diag0 = np.zeros(self.N)
-        diag0[self.top] += -self.rho0 * (h * h) * (2.0 / h)
-        upper, diag = laplacian(rhof, np.full(self.F, h * h), np.full(self.F, 1.0 / h), 1.0, diag0)
+        diag0[self.top] += -self.rho0 * (self.d[0] * self.d[2]) * (2.0 / dy)
+        upper, diag = laplacian(rhof, self.magSf, self.deltaCoeffs, 1.0, diag0)
         source = np.zeros(self.N)
         np.add.at(source, l, phig)
         np.subtract.at(source, u, phig)
@@ -82,3 +105,52 @@ class StecklerHydrostatic:
         p = ph_rgh + self.rho * self.gh + self.PREF
         self.rho = self.psi_thermo * p
         return float(ph_rgh.max() - ph_rgh.min())
+
+
+class StecklerHydrostatic(HydrostaticBox):
+    NX, NY, NZ, H = 30, 15, 20, 0.2
+
+    def __init__(self):
+        def baffle(d, own, nei, i, j, k):
+            inside = (i >= 3) & (i <= 16) & (j >= 0) & (j <= 10) & (k >= 3) & (k <= 16)
+            b = inside[own] != inside[nei]
+            if d == 0:  # doorway: faces on the x = 1.4 plane (between i=16 and i=17)
+                b &= ~((i[own] == 16) & (j[own] <= 4) & (k[own] >= 7) & (k[own] <= 12))
+            return b
+        super().__init__(self.NX, self.NY, self.NZ, self.H, self.H, self.H, 3.0, baffle)
+
+
+class SingleBoxHydrostatic(HydrostaticBox):
+    def __init__(self):
+        inch = 0.0254   # convertToMeters, blockMeshDict:18; box 120 x 80 x 120 in, hRef 2.032 = 80 in
+        super().__init__(7, 5, 7, 120 * inch / 7, 80 * inch / 5, 120 * inch / 7, 2.032)
+
+
+def steckler_p_rgh_system(seed=1711, psi=1.17e-5, dt=0.0667):
+    """A = diag(psi V/dt) - L(gamma) on the steckler topology,
+    gamma_f = linear interpolate(rho*rAU), rho*rAU = dt (1 + 0.3 xi_c); `top` + `sides` fixed value,
+    other patches zero flux; source = A x*, x* smooth + 1 % noise.  Returns meshgen.System."""
+    from .meshgen import System
+    case = StecklerHydrostatic()
+    a, h = case.addr, case.H
+    i, j, k = case.ijk
+    nx, ny, nz = case.dims
+    N = case.N
+    g_c = dt * (1.0 + 0.3 * uniform_pm1(seed, np.arange(N)))
+    l, u = a.lowerAddr, a.upperAddr
+    gamma_f = 0.5 * (g_c[l] + g_c[u])
+    magSf, delta = np.full(case.F, h * h), np.full(case.F, 1.0 / h)
+    diag0 = np.full(N, psi * h ** 3 / dt)
+    nb = (j == ny - 1).astype(float) + (i == 0) + (i == nx - 1) + (k == 0) + (k == nz - 1)
+    diag0 += nb * g_c * (h * h) * (2.0 / h)
+    upper = -1.0 * (delta * (gamma_f * magSf))
+    # negSumDiag in face order (owner and neighbour interleaved, like OpenFOAM's loop)
+    diag = np.zeros(N)
+    np.subtract.at(diag, np.stack([l, u], 1).ravel(), np.repeat(upper, 2))
+    diag = diag0 + diag
+    x, y, z = (i + 0.5) * h - 2.0, (j + 0.5) * h, (k + 0.5) * h - 2.0
+    xstar = np.sin(0.7 * x) * np.cos(1.1 * y) * np.sin(0.9 * z) + 0.01 * uniform_pm1(seed ^ 0x5EED, np.arange(N))
+    source = diag * xstar
+    np.add.at(source, u, upper * xstar[l])
+    np.add.at(source, l, upper * xstar[u])
+    return System(a, diag, upper, source, [], xstar, gamma_f, magSf, delta, diag0, -1.0)

@@ -379,6 +379,152 @@ k_spmv_sym(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
     if (DOT) reduce_finish<1>(dot, R);
 }
 
+// ---- TMA-staged variant of the symmetric Amul -------------------------------------------------
+// Same arithmetic and row order as k_spmv_sym, but the streaming operands of a chunk of 256 rows
+// (row lengths, lower references, upper columns + values, x, diag: all contiguous in the sliced
+// layout) are brought into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier
+// complete_tx), kSymStages chunks ahead of the math.  The DRAM latency of the first load level is
+// thereby taken off the warps' dependent chain: a warp only waits for the L2-served gathers
+// (referenced values, x of neighbours).  One elected thread issues the copies; all 256 threads
+// consume; one __syncthreads per chunk recycles the stage.
+constexpr int kSymStagesMax = 4;
+constexpr int kChunkRows = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// bytes of one stage for given widths (host + device)
+__host__ __device__ inline size_t sym_stage_bytes(int WU, int WL) {
+    return (size_t)kChunkRows * ((size_t)WU * 12 + (size_t)WL * 4 + 4 + 16);
+}
+
+template <bool DOT, int kSymStages>
+__global__ void __launch_bounds__(kBlock)
+k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
+               const int* __restrict__ uCol, const double* __restrict__ uVal,
+               const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
+               const double* __restrict__ x, double* __restrict__ y, Reduce R) {
+    if (R.S->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int B = kSymBatch;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t stageBytes = sym_stage_bytes(WU, WL);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // [kSymStages]
+    unsigned char* stage0 = smem_raw + 128;
+    // per-stage layout: uVal | x | diag | uCol | lRef | rowLen  (sizes are multiples of 16 B)
+    const size_t oVal = 0, oX = (size_t)kChunkRows * WU * 8, oDiag = oX + kChunkRows * 8,
+                 oCol = oDiag + kChunkRows * 8, oRef = oCol + (size_t)kChunkRows * WU * 4,
+                 oLen = oRef + (size_t)kChunkRows * WL * 4;
+    const int nChunks = (N + kChunkRows - 1) / kChunkRows;
+    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
+
+    if (tid == 0) {
+        for (int s = 0; s < kSymStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int chunk, int s) {
+        unsigned char* st = stage0 + (size_t)s * stageBytes;
+        const size_t r0 = (size_t)chunk * kChunkRows;
+        mbar_expect_tx(&bars[s], (uint32_t)stageBytes);
+        bulk_g2s(st + oVal, uVal + r0 * WU, (uint32_t)(kChunkRows * WU * 8), &bars[s]);
+        bulk_g2s(st + oX, x + r0, kChunkRows * 8, &bars[s]);
+        bulk_g2s(st + oDiag, diag + r0, kChunkRows * 8, &bars[s]);
+        bulk_g2s(st + oCol, uCol + r0 * WU, (uint32_t)(kChunkRows * WU * 4), &bars[s]);
+        if (WL > 0) bulk_g2s(st + oRef, lRef + r0 * WL, (uint32_t)(kChunkRows * WL * 4), &bars[s]);
+        bulk_g2s(st + oLen, rowLen + r0, kChunkRows * 4, &bars[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < kSymStages; ++s) {
+            const int c = blockIdx.x + s * gridDim.x;
+            if (c < nChunks) issue(c, s);
+        }
+
+    double dot[1] = {0.0};
+    int it = 0;
+    for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x, ++it) {
+        const int s = it % kSymStages;
+        mbar_wait(&bars[s], (uint32_t)((it / kSymStages) & 1));
+        const unsigned char* st = stage0 + (size_t)s * stageBytes;
+        const double* sVal = reinterpret_cast<const double*>(st + oVal);
+        const double* sX = reinterpret_cast<const double*>(st + oX);
+        const double* sDiag = reinterpret_cast<const double*>(st + oDiag);
+        const int* sCol = reinterpret_cast<const int*>(st + oCol);
+        const uint32_t* sRef = reinterpret_cast<const uint32_t*>(st + oRef);
+        const uint32_t* sLen = reinterpret_cast<const uint32_t*>(st + oLen);
+        const int r = chunk * kChunkRows + (int)tid;
+        if (r < N) {
+            const uint32_t len = sLen[tid];
+            const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
+            const uint32_t lb = warp * strideL + lane, ub = warp * strideU + lane;
+            // gathers served by L2/L1 (the only exposed latency)
+            double lv[B], lx[B], ux[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const uint32_t pk = (k < nL) ? sRef[lb + 32u * k] : 0u;
+                const uint32_t a = pk >> 5;
+                const uint32_t pos = (a >> 5) * strideU + ((pk & 31u) << 5) + (a & 31u);
+                lv[k] = (k < nL) ? uVal[pos] : 0.0;
+                lx[k] = (k < nL) ? __ldg(&x[a]) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k) ux[k] = (k < nU) ? __ldg(&x[sCol[ub + 32u * k]]) : 0.0;
+            const double xr = sX[tid];
+            double acc = __dmul_rn(sDiag[tid], xr);
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                if (k < nL) acc = __dadd_rn(acc, __dmul_rn(lv[k], lx[k]));
+            for (int j = B; j < nL; ++j) {
+                const uint32_t p0 = sRef[lb + 32u * j];
+                const uint32_t a = p0 >> 5;
+                const double v0 = uVal[(a >> 5) * strideU + ((p0 & 31u) << 5) + (a & 31u)];
+                acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[a])));
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                if (k < nU) acc = __dadd_rn(acc, __dmul_rn(sVal[ub + 32u * k], ux[k]));
+            for (int j = B; j < nU; ++j)
+                acc = __dadd_rn(acc, __dmul_rn(sVal[ub + 32u * j], __ldg(&x[sCol[ub + 32u * j]])));
+            y[r] = acc;
+            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+        }
+        __syncthreads();   // every thread is done with stage s
+        if (tid == 0) {
+            const int next = chunk + kSymStages * gridDim.x;
+            if (next < nChunks) issue(next, s);
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
 // ---- processor interfaces (OF-dev processorFvPatchField.C, lduMatrixUpdateMatrixInterfaces.C;
 //      SURVEY.md A.4) ------------------------------------------------------------------------
 __global__ void k_pack(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ x,

@@ -246,4 +246,171 @@ int b200mesh_hex_fill(int NX, int NY, int NZ, int PX, int PY, int PZ, int rank, 
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// BCC-lattice Voronoi mesh (truncated octahedra, 14 faces per interior cell): SURVEY.md 8d config 5.
+// Sub-lattice A at (i,j,k)a, B at (i+1/2,j+1/2,k+1/2)a; 8 hexagonal faces to the other sub-lattice
+// (area 3*sqrt(3)/16 a^2, distance sqrt(3)/2 a), 6 square faces to the same sub-lattice (area a^2/8,
+// distance a); cell volume a^3/2.  Cells are numbered in Morton order of the doubled integer
+// coordinates, then shuffled (seeded) inside blocks of `shuffleBlock` cells, so lowerAddr segment
+// lengths are irregular (0..14) and strides non-constant.  Faces are emitted in upper-triangular
+// order.  Same gamma / boundary / manufactured-solution recipe as the hex workload.
+namespace {
+inline uint64_t part1by2(uint64_t x) {
+    x &= 0x1fffff;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+struct Bcc {
+    int nx, ny, nz;
+    int64_t N;
+    std::vector<int32_t> siteOfCell, cellOfSite;   // site = 2*(i + nx*(j + ny*k)) + sub
+    int neighbours(int64_t site, int64_t* out, int* isHex) const {
+        const int sub = (int)(site & 1);
+        const int64_t q = site >> 1;
+        const int i = (int)(q % nx), j = (int)((q / nx) % ny), k = (int)(q / ((int64_t)nx * ny));
+        int n = 0;
+        auto add = [&](int I, int J, int K, int S, int hex) {
+            if (I < 0 || J < 0 || K < 0 || I >= nx || J >= ny || K >= nz) return;
+            out[n] = 2 * ((int64_t)I + (int64_t)nx * (J + (int64_t)ny * K)) + S;
+            isHex[n] = hex;
+            ++n;
+        };
+        for (int d = 0; d < 8; ++d) {
+            const int di = d & 1, dj = (d >> 1) & 1, dk = (d >> 2) & 1;
+            if (sub == 0) add(i - 1 + di, j - 1 + dj, k - 1 + dk, 1, 1);
+            else add(i + di, j + dj, k + dk, 0, 1);
+        }
+        add(i - 1, j, k, sub, 0); add(i + 1, j, k, sub, 0);
+        add(i, j - 1, k, sub, 0); add(i, j + 1, k, sub, 0);
+        add(i, j, k - 1, sub, 0); add(i, j, k + 1, sub, 0);
+        return n;
+    }
+};
+bool make_bcc(int nx, int ny, int nz, uint64_t seed, int shuffleBlock, Bcc& b) {
+    if (nx < 1 || ny < 1 || nz < 1) return false;
+    const int64_t N = 2ll * nx * ny * nz;
+    if (N > 0x7fffffff) return false;
+    b.nx = nx; b.ny = ny; b.nz = nz; b.N = N;
+    std::vector<std::pair<uint64_t, int32_t>> key((size_t)N);
+#pragma omp parallel for schedule(static)
+    for (int64_t site = 0; site < N; ++site) {
+        const int sub = (int)(site & 1);
+        const int64_t q = site >> 1;
+        const uint64_t X = 2 * (q % nx) + sub, Y = 2 * ((q / nx) % ny) + sub, Z = 2 * (q / ((int64_t)nx * ny)) + sub;
+        key[site] = {part1by2(X) | (part1by2(Y) << 1) | (part1by2(Z) << 2), (int32_t)site};
+    }
+    std::sort(key.begin(), key.end());
+    b.siteOfCell.resize((size_t)N);
+    for (int64_t c = 0; c < N; ++c) b.siteOfCell[c] = key[c].second;
+    if (shuffleBlock > 1)
+        for (int64_t b0 = 0; b0 < N; b0 += shuffleBlock) {
+            const int64_t n = std::min<int64_t>(shuffleBlock, N - b0);
+            for (int64_t i = n - 1; i > 0; --i) {
+                const uint64_t r = splitmix64(seed ^ (uint64_t)(b0 + i) * 0x9E3779B97F4A7C15ull) % (uint64_t)(i + 1);
+                std::swap(b.siteOfCell[b0 + i], b.siteOfCell[b0 + (int64_t)r]);
+            }
+        }
+    b.cellOfSite.resize((size_t)N);
+    for (int64_t c = 0; c < N; ++c) b.cellOfSite[b.siteOfCell[c]] = (int32_t)c;
+    return true;
+}
+inline void site_xyz(const Bcc& b, int64_t site, double a, double* p) {
+    const int sub = (int)(site & 1);
+    const int64_t q = site >> 1;
+    p[0] = ((double)(q % b.nx) + 0.5 * sub) * a;
+    p[1] = ((double)((q / b.nx) % b.ny) + 0.5 * sub) * a;
+    p[2] = ((double)(q / ((int64_t)b.nx * b.ny)) + 0.5 * sub) * a;
+}
+Bcc* g_bcc = nullptr;
+}  // namespace
+
+// two-phase: sizes (builds and caches the numbering), then fill
+int b200mesh_bcc_sizes(int nx, int ny, int nz, uint64_t seed, int shuffleBlock, int64_t* sizes) {
+    delete g_bcc;
+    g_bcc = new Bcc();
+    if (!make_bcc(nx, ny, nz, seed, shuffleBlock, *g_bcc)) { delete g_bcc; g_bcc = nullptr; return 1; }
+    const Bcc& b = *g_bcc;
+    int64_t F = 0;
+#pragma omp parallel for schedule(static) reduction(+ : F)
+    for (int64_t c = 0; c < b.N; ++c) {
+        int64_t nb[14]; int hx[14];
+        const int n = b.neighbours(b.siteOfCell[c], nb, hx);
+        for (int k = 0; k < n; ++k) if (b.cellOfSite[nb[k]] > c) ++F;
+    }
+    if (F > 0x7fffffff) return 2;
+    sizes[0] = b.N;
+    sizes[1] = F;
+    return 0;
+}
+
+int b200mesh_bcc_fill(uint64_t seed, double a, double gamma0, double psiOverDt, int32_t* lower,
+                      int32_t* upper_addr, double* gamma_f, double* magSf, double* delta, double* diag0,
+                      double* diag, double* upper, double* source, double* xstar, double* xyz) {
+    if (!g_bcc) return 1;
+    const Bcc& b = *g_bcc;
+    const int64_t N = b.N;
+    const double Shex = 3.0 * std::sqrt(3.0) / 16.0 * a * a, Ssq = a * a / 8.0;
+    const double dhex = 1.0 / (std::sqrt(3.0) / 2.0 * a), dsq = 1.0 / a, V = 0.5 * a * a * a;
+    std::vector<double> gam((size_t)N);
+    std::vector<int64_t> fstart((size_t)N + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < N; ++c) {
+        const int64_t site = b.siteOfCell[c];
+        double p[3];
+        site_xyz(b, site, a, p);
+        xyz[3 * c] = p[0]; xyz[3 * c + 1] = p[1]; xyz[3 * c + 2] = p[2];
+        const double xi = uni(seed, (uint64_t)site), xj = uni(seed ^ 0xABCDEF1234567ull, (uint64_t)site);
+        gam[c] = gamma0 * (1.0 + 0.9 * std::sin(2 * kPi * p[0]) * std::sin(2 * kPi * p[1]) * std::sin(2 * kPi * p[2])) *
+                 std::pow(10.0, 0.5 * xi);
+        xstar[c] = std::sin(kPi * p[0]) * std::cos(2 * kPi * p[1]) * std::sin(3 * kPi * p[2]) + 0.5 * p[0] + 0.01 * xj;
+        int64_t nb[14]; int hx[14];
+        const int n = b.neighbours(site, nb, hx);
+        int cnt = 0;
+        for (int k = 0; k < n; ++k) if (b.cellOfSite[nb[k]] > c) ++cnt;
+        fstart[c + 1] = cnt;
+        const int j = (int)((site >> 1) / b.nx % b.ny);
+        diag0[c] = psiOverDt * V;
+        if (j == b.ny - 1) diag0[c] += 0.0;   // filled below once gamma is known
+    }
+    for (int64_t c = 0; c < N; ++c) fstart[c + 1] += fstart[c];
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < N; ++c) {
+        const int64_t site = b.siteOfCell[c];
+        const int j = (int)((site >> 1) / b.nx % b.ny);
+        if (j == b.ny - 1) diag0[c] += gam[c] * Ssq * (2.0 * dsq);   // fixed-value top patch
+        int64_t nb[14]; int hx[14];
+        const int n = b.neighbours(site, nb, hx);
+        std::pair<int32_t, int> up[16];
+        int cnt = 0;
+        for (int k = 0; k < n; ++k) {
+            const int32_t o = b.cellOfSite[nb[k]];
+            if (o > c) up[cnt++] = {o, hx[k]};
+        }
+        std::sort(up, up + cnt);
+        int64_t f = fstart[c];
+        for (int k = 0; k < cnt; ++k, ++f) {
+            lower[f] = (int32_t)c;
+            upper_addr[f] = up[k].first;
+            gamma_f[f] = 0.5 * (gam[c] + gam[up[k].first]);
+            magSf[f] = up[k].second ? Shex : Ssq;
+            delta[f] = up[k].second ? dhex : dsq;
+            upper[f] = -1.0 * (delta[f] * (gamma_f[f] * magSf[f]));
+        }
+    }
+    const int64_t F = fstart[N];
+    for (int64_t c = 0; c < N; ++c) diag[c] = 0.0;
+    for (int64_t f = 0; f < F; ++f) { diag[lower[f]] -= upper[f]; diag[upper_addr[f]] -= upper[f]; }
+    for (int64_t c = 0; c < N; ++c) { diag[c] += diag0[c]; source[c] = diag[c] * xstar[c]; }
+    for (int64_t f = 0; f < F; ++f) {
+        source[upper_addr[f]] += upper[f] * xstar[lower[f]];
+        source[lower[f]] += upper[f] * xstar[upper_addr[f]];
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -99,6 +99,9 @@ struct DevPlan {
     bool sym = false;
     int64_t symNU = 0;
     int symWU = 0, symWL = 0;
+    bool symTma = false;
+    size_t symStage = 0;
+    uint32_t* sRowLen = nullptr;
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
     uint32_t* sLRef = nullptr;
@@ -140,6 +143,11 @@ struct b200_ctx {
     double* partials = nullptr;
     uint64_t launches = 0;
     int32_t forceIters = 0;
+    // bulk-copy pipeline depth / CTAs per SM (B200PCG_STAGES, B200PCG_CTAS).  Measured on the 16 M hex
+    // box (profiles/r01_tma_sweep.md): 2 stages x 4 CTAs/SM is the optimum -- deeper pipelines or more
+    // CTAs shrink the L1 carve-out that serves the neighbour gathers.
+    int symStages = 2, symPerSM = 0;
+    bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
     // profiling
     bool prof = false;
@@ -249,7 +257,7 @@ void free_plan(DevPlan& P) {
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot);
     dev_free(P.sUCol); dev_free(P.sUFace);
-    dev_free(P.sUVal); dev_free(P.sLRef);
+    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen);
     P.sym = false;
     P.built = false;
     P.h = HostPlan();
@@ -292,11 +300,34 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
     if (P.h.sym.valid && !ctx->disableSym && ord == Ordering::Natural) {
         SymPlan& Y = P.h.sym;
+        // arrays padded to whole 256-row chunks for the bulk-copy (TMA) staging
+        const size_t rowsPad = (((size_t)ctx->N + kChunkRows - 1) / kChunkRows) * kChunkRows;
+        Y.uCol.resize(rowsPad * Y.WU, 0);
+        Y.uFace.resize(rowsPad * Y.WU, -1);
+        Y.lRef.resize(rowsPad * Y.WL, 0);
         RET(upload(ctx, &P.sUCol, Y.uCol));
         RET(upload(ctx, &P.sUFace, Y.uFace));
         RET(upload(ctx, &P.sLRef, Y.lRef));
-        RET(dev_alloc(ctx, &P.sUVal, (size_t)Y.nU));
-        P.symNU = Y.nU;
+        RET(dev_alloc(ctx, &P.sUVal, rowsPad * Y.WU));
+        {
+            std::vector<uint32_t> rl(rowsPad, 0u);
+            // rowLen was uploaded un-padded for the ELL kernels; the staged kernel reads whole chunks
+            CU(cudaMemcpyAsync(rl.data(), P.rowLen, (size_t)ctx->N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->sc));
+            CU(cudaStreamSynchronize(ctx->sc));
+            RET(upload(ctx, &P.sRowLen, rl));
+            CU(cudaStreamSynchronize(ctx->sc));
+        }
+        P.symNU = (int64_t)(rowsPad * Y.WU);
+        P.symStage = sym_stage_bytes(Y.WU, Y.WL);
+        P.symTma = !ctx->disableTma && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
+        if (P.symTma) {
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        }
         P.symWU = Y.WU;
         P.symWL = Y.WL;
         P.sym = true;
@@ -361,7 +392,28 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R{ctx->S, ctx->partials, halo ? STEP_NONE : step};
-    if (P.sym) {
+    if (P.sym && P.symTma && !INIT) {
+        const size_t smem = 128 + ctx->symStages * P.symStage;
+        int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
+        if (perSM > 8) perSM = 8;
+        if (perSM < 1) perSM = 1;
+        if (ctx->symPerSM > 0 && perSM > ctx->symPerSM) perSM = ctx->symPerSM;
+        const int nChunks = (N + kChunkRows - 1) / kChunkRows;
+        int g = std::min(nChunks, perSM * ctx->numSMs);
+        if (g > kMaxGrid) g = kMaxGrid;
+        prof_begin(ctx, PC_SPMV);
+        if (ctx->symStages == 2)
+            k_spmv_sym_tma<DOT, 2><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
+                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
+        else if (ctx->symStages == 3)
+            k_spmv_sym_tma<DOT, 3><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
+                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
+        else
+            k_spmv_sym_tma<DOT, 4><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
+                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
+        prof_end(ctx, PC_SPMV);
+        ctx->launches++;
+    } else if (P.sym) {
         auto kern = k_spmv_sym<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.rowLen,
                P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
@@ -387,7 +439,8 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
 }
 
 int alloc_vectors(b200_ctx* ctx) {
-    const size_t n = (size_t)ctx->N + 2;
+    // rounded up to whole 256-row chunks (+1 chunk): the bulk-copy Amul stages whole chunks
+    const size_t n = (((size_t)ctx->N + kChunkRows - 1) / kChunkRows + 1) * kChunkRows;
     RET(dev_alloc(ctx, &ctx->diag, n)); RET(dev_alloc(ctx, &ctx->src, n));
     RET(dev_alloc(ctx, &ctx->psi, n));  RET(dev_alloc(ctx, &ctx->r, n));
     RET(dev_alloc(ctx, &ctx->p, n));    RET(dev_alloc(ctx, &ctx->w, n));
@@ -666,7 +719,12 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
                                         " (sm_" + std::to_string(prop.major * 10 + prop.minor) +
                                         "); libb200pcg is built for sm_100a only");
     c->numSMs = prop.multiProcessorCount;
-    if (const char* e2 = getenv("B200PCG_SPMV")) c->disableSym = (std::string(e2) == "ell");
+    if (const char* e3 = getenv("B200PCG_STAGES")) c->symStages = std::max(2, std::min(4, atoi(e3)));
+    if (const char* e4 = getenv("B200PCG_CTAS")) c->symPerSM = atoi(e4);
+    if (const char* e2 = getenv("B200PCG_SPMV")) {
+        c->disableSym = (std::string(e2) == "ell");
+        c->disableTma = (std::string(e2) == "sym");
+    }
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->sm, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming)) != cudaSuccess ||

@@ -83,6 +83,34 @@ def hex_block(NX, NY, NZ, PX=1, PY=1, PZ=1, rank=0, seed=SEED, h=None, gamma0=1e
     return System(addr, diag, upper, source, bcs, xstar, gamma_f, magSf, delta, diag0, -1.0)
 
 
+def bcc_poly(nx, ny, nz, seed=SEED, a=None, gamma0=1e-3, psi=1.17e-5, dt=1e-3, shuffle_block=4096):
+    """Polyhedral workload: BCC-lattice Voronoi mesh of truncated octahedra
+    (2*nx*ny*nz cells, up to 14 faces per cell), Morton + block-shuffled numbering.  Returns a
+    single-rank System; `.xyz` holds the cell centres (for the partitioners)."""
+    L = _lib.load_mesh()
+    sz = np.zeros(2, dtype=np.int64)
+    if L.b200mesh_bcc_sizes(nx, ny, nz, seed, shuffle_block, sz.ctypes.data) != 0:
+        raise ValueError("bad BCC specification")
+    N, F = int(sz[0]), int(sz[1])
+    if a is None:
+        a = 1.0 / nx
+    i32 = lambda n: np.empty(n, dtype=np.int32)
+    f64 = lambda n: np.empty(n, dtype=np.float64)
+    lower, upper_addr = i32(F), i32(F)
+    gamma_f, magSf, delta, upper = f64(F), f64(F), f64(F), f64(F)
+    diag0, diag, source, xstar, xyz = f64(N), f64(N), f64(N), f64(N), f64(3 * N)
+    rc = L.b200mesh_bcc_fill(seed, float(a), float(gamma0), float(psi / dt), lower.ctypes.data,
+                             upper_addr.ctypes.data, gamma_f.ctypes.data, magSf.ctypes.data,
+                             delta.ctypes.data, diag0.ctypes.data, diag.ctypes.data, upper.ctypes.data,
+                             source.ctypes.data, xstar.ctypes.data, xyz.ctypes.data)
+    if rc != 0:
+        raise ValueError("bcc_fill failed")
+    s = System(LduAddressing(N, lower, upper_addr), diag, upper, source, [], xstar, gamma_f, magSf,
+               delta, diag0, -1.0)
+    s.xyz = xyz.reshape(N, 3)
+    return s
+
+
 # ---- partitioners + decomposition ----------------------------------------------------------------
 def partition_simple(xyz, n):
     L = _lib.load_mesh()

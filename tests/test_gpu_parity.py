@@ -274,3 +274,43 @@ def test_medium_hex_all_preconditioners(ctx):
         assert relmax(xg, xc) < 1e-11, (pre, relmax(xg, xc))
     xg, pg = solve_gpu(ctx, s, "DIC", tol=1e-6, maxIter=5000)
     assert pg.converged and relmax(xg, s.xstar) < 1e-3
+
+
+def test_singlebox_config1_on_gpu(ctx):
+    from firefoam_dev_b200.cases import SingleBoxHydrostatic
+    case = SingleBoxHydrostatic()
+    ctx.set_addressing(case.addr)
+    lap = lambda g, s, d, sign, d0: ctx.assemble_laplacian(g, s, d, sign, d0)
+    ctl = {"preconditioner": "diagonal", "tolerance": case.TOL, "relTol": case.RELTOL}
+    solve = lambda m, b, psi: B200PCG("ph_rgh", m, [], None, [], ctl, context=ctx).solve(psi, b)
+    res = hydrostatic_loop(case, lap, solve)
+    assert [r[2] for r in res] == [12, 8, 9, 0, 0]
+
+
+def test_steckler_p_rgh_replay_config2_on_gpu(ctx):
+    from firefoam_dev_b200.cases import steckler_p_rgh_system
+    s = steckler_p_rgh_system()
+    for pre, exact in (("diagonal", False), ("DIC", True)):
+        for rt in (0.01, 0.0):
+            xg, pg = solve_gpu(ctx, s, pre, tol=1e-6, relTol=rt, exact=exact)
+            xc, pc = solve_cpu(s, pre, tol=1e-6, relTol=rt)
+            assert pg.nIterations == pc.nIterations and relmax(xg, xc) < 1e-12
+
+
+def test_polyhedral_config5_small(ctx):
+    """BCC truncated-octahedron mesh (up to 14 faces per cell, irregular lowerAddr segments)."""
+    s = mg.bcc_poly(12, 12, 16)
+    a = s.addr
+    ctx.set_addressing(a)
+    up, dg = ctx.assemble_laplacian(s.gamma_f, s.magSf, s.deltaCoeffs, -1.0, s.diag0)
+    assert np.array_equal(up, s.upper) and np.array_equal(dg, s.diag)
+    x = np.random.default_rng(5).standard_normal(a.nCells)
+    assert np.array_equal(ctx.amul(s.matrix, [], x), orc.amul(s, x)[0])
+    for pre, exact in (("diagonal", False), ("DIC", True)):
+        xg, pg = solve_gpu(ctx, s, pre, tol=1e-6, maxIter=5000, exact=exact)
+        xc, pc = solve_cpu(s, pre, tol=1e-6, maxIter=5000)
+        assert pg.nIterations == pc.nIterations and relmax(xg, xc) < 1e-12
+    xg, pg = solve_gpu(ctx, s, "DIC", tol=1e-11, maxIter=5000)
+    xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
+    assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
+    assert pg.nColours >= 4

@@ -82,3 +82,38 @@ def test_oracle_controls_semantics():
     psi = s.xstar.copy()
     p = orc.pcg_solve(s, psi, "diagonal", 1e-6, 0.0, minIter=2)
     assert p.singular and p.nIterations == 0
+
+
+def test_singlebox_config1_diagonal_plumbing():
+    """BASELINE config 1: singleBox base block (7 x 5 x 7), PCG + diagonal, 1 rank, oracle only.
+    Nothing in the reference pins these numbers (self-derived regression values)."""
+    from firefoam_dev_b200.cases import SingleBoxHydrostatic
+    case = SingleBoxHydrostatic()
+    assert (case.N, case.F) == (245, 616)
+    a = case.addr
+    lap = lambda g, s, d, sign, d0: orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, g, s, d, sign, d0)
+    solve = lambda m, b, psi: orc.pcg_solve(System(a, m.diag, m.upper, b), psi, "diagonal", case.TOL, case.RELTOL)
+    res = hydrostatic_loop(case, lap, solve)
+    assert [r[2] for r in res] == [12, 8, 9, 0, 0]
+    # hydrostatic variation ~ rho0 * g * psi*... small and positive; converged value stable
+    assert res[4][3] == pytest.approx(0.0021817037, rel=1e-6)
+
+
+def test_steckler_p_rgh_synthetic_config2():
+    """BASELINE config 2 (replay stand-in): p_rgh-shaped systems on the steckler topology."""
+    from firefoam_dev_b200.cases import steckler_p_rgh_system
+    s = steckler_p_rgh_system()
+    a = s.addr
+    up, dg = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf, s.deltaCoeffs, -1.0, s.diag0)
+    assert np.array_equal(up, s.upper) and np.array_equal(dg, s.diag)
+    its = {}
+    for pre in ("diagonal", "DIC"):
+        for rt in (0.01, 0.0):
+            psi = np.zeros(a.nCells)
+            p = orc.pcg_solve(s, psi, pre, 1e-6, rt)
+            assert p.converged
+            its[(pre, rt)] = p.nIterations
+    assert its[("DIC", 0.01)] < its[("diagonal", 0.01)] < its[("diagonal", 0.0)]
+    # same order of magnitude as the reference's real p_rgh solves (9-21 / 22-28 DICPCG iterations,
+    # cases/steckler/original/linux64/log.fireFoam:220-1231)
+    assert 3 <= its[("DIC", 0.01)] <= 30 and 15 <= its[("DIC", 0.0)] <= 60
