@@ -37,6 +37,7 @@ BLOCK = (256, 250, 250)          # cells per GPU (config 3)
 PROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 TOL, MAXITER = 1e-6, 5000
 METRIC = "p_rgh PCG solve throughput (assemble + PCG/diagonal to tol 1e-6), fp64"
+PRECOND = "diagonal"   # --precond overrides (DIC = multicolour IC0, BASELINE config 4)
 UNIT = "GDOF*iter/s"
 
 
@@ -233,7 +234,10 @@ def run_gpu(args):
     t0 = time.time()
     ctx.set_addressing(a)
     setaddr_s = time.time() - t0
-    ctl, _ = pkg.make_controls({"preconditioner": "diagonal", "tolerance": TOL, "relTol": 0.0, "maxIter": MAXITER})
+    sctl = {"preconditioner": "DIC" if args.precond.startswith("DIC") else args.precond, "tolerance": TOL,
+            "relTol": 0.0, "maxIter": MAXITER,
+            "B200": {"dicMode": "exact" if args.precond == "DIC-exact" else "multicolour"}}
+    ctl, _ = pkg.make_controls(sctl)
 
     up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     d_gamma, d_magSf, d_delta = up(s.gamma_f), up(s.magSf), up(s.deltaCoeffs)
@@ -285,9 +289,7 @@ def run_gpu(args):
 
     # ---- e2e: the reference-facing plug-in call with pinned host buffers ------------------------
     psi_h = pinned(N, np.float64)
-    solver = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces,
-                         {"preconditioner": "diagonal", "tolerance": TOL, "relTol": 0.0, "maxIter": MAXITER},
-                         context=ctx)
+    solver = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, sctl, context=ctx)
     psi_h[:] = 0.0
     solver.solve(psi_h, s.source)                       # warm-up (allocates staging)
     barrier()
@@ -348,12 +350,13 @@ def run_gpu(args):
                 traffic = tj.get("dram_bytes_per_launch")
     except Exception:
         pass
-    iter_bytes = 120 * N + 16 * F
+    # algorithmic bytes of one PCG iteration: diagonal 120N+16F, DIC-class 136N+48F
+    iter_bytes = (136 * N + 48 * F) if args.precond.startswith("DIC") else (120 * N + 16 * F)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "metric": METRIC.replace("diagonal", args.precond), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(n, block),
+        "config": dict(config_dict(n, block), preconditioner=args.precond, colours=perf.nColours),
         "iterations_per_step": iters // args.steps, "converged": converged, "max_err_vs_xstar": err,
         "solve_ms_per_step": solve_ms / args.steps, "setup_ms_per_step": setup_ms / args.steps,
         "pcg_iteration": {"avg_us": 1e3 * solve_ms / max(iters, 1), "alg_bytes": iter_bytes,
@@ -393,6 +396,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block", type=int, nargs=3, default=list(BLOCK),
                     help="cells per GPU (development only; the default is the BASELINE workload)")
+    ap.add_argument("--precond", default=PRECOND, choices=["none", "diagonal", "DIC", "DIC-exact"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

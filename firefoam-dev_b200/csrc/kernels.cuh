@@ -142,6 +142,71 @@ __global__ void k_scalar_step(Scalars* S, int step) {
     scalar_step(step, S, S->gsums);
 }
 
+// ---- one-shot all-reduce over NVLink peer memory, fused with the scalar step ------------------
+// Replaces reduce(scalar, sumOp) of OF-dev UPstream.C for the 2-double CG reductions.  Every rank
+// owns a PeerBuf in its HBM, mapped into all other ranks with CUDA IPC.  One warp per rank: lane r
+// stores this rank's partial sums + a sequence flag into rank r's buffer (P2P stores through
+// NVSwitch), then waits for rank r's contribution to arrive in the local buffer, and lane 0 adds
+// the contributions in ASCENDING RANK ORDER -- the order of Pstream's linear gather for
+// <= nProcsSimpleSum ranks -- so every rank forms bit-identical totals, and runs
+// the scalar step.  One ~5 us kernel instead of ncclAllReduce + a scalar kernel (~25 us).
+constexpr int kMaxRanks = 32;
+struct PeerBuf {
+    double vals[2][kMaxRanks][kNSums];
+    unsigned long long flags[2][kMaxRanks];
+};
+
+__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
+                                 unsigned long long seq, int step) {
+    if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
+    const int lane = threadIdx.x;
+    const int par = (int)(seq & 1ull);
+    if (lane < nranks) {
+        PeerBuf* dst = peers[lane];
+#pragma unroll
+        for (int i = 0; i < kNSums; ++i) dst->vals[par][rank][i] = S->sums[i];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&dst->flags[par][rank]) = seq;
+    }
+    double v[kNSums];
+#pragma unroll
+    for (int i = 0; i < kNSums; ++i) v[i] = 0.0;
+    bool timedOut = false;
+    if (lane < nranks) {
+        PeerBuf* me = peers[rank];
+        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(&me->flags[par][lane]);
+        unsigned long long spins = 0;
+        while (*f != seq) {
+            if (++spins > 400000000ull) { timedOut = true; break; }
+        }
+        __threadfence_system();
+#pragma unroll
+        for (int i = 0; i < kNSums; ++i)
+            v[i] = *reinterpret_cast<volatile double*>(&me->vals[par][lane][i]);
+    }
+    const bool anyTimeout = __any_sync(0xffffffffu, timedOut);
+    double tot[kNSums];
+#pragma unroll
+    for (int i = 0; i < kNSums; ++i) {
+        double t = 0.0;
+        for (int r = 0; r < nranks; ++r) {
+            const double vr = __shfl_sync(0xffffffffu, v[i], r);
+            t = (r == 0) ? vr : __dadd_rn(t, vr);      // ((v0+v1)+v2)+...
+        }
+        tot[i] = t;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kNSums; ++i) S->gsums[i] = tot[i];
+        if (anyTimeout) {
+            S->nonfinite = 2;   // peer never arrived: reported as an error by the host
+            S->done = 1;
+        } else {
+            scalar_step(step, S, S->gsums);
+        }
+    }
+}
+
 // ---- deterministic block reduction + last-block finish -----------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -41,6 +41,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -64,7 +65,7 @@ struct NcclApi {
     field = reinterpret_cast<decltype(field)>(dlsym(handle, name));           \
     if (!field) { error = std::string("NCCL symbol missing: ") + name; handle = nullptr; return false; }
         SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank")
-        SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend")
+        SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend")
         SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
         SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
@@ -138,6 +139,12 @@ struct b200_ctx {
     // staging for the host entry points (natural order)
     double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
            *in_bou = nullptr, *in_f1 = nullptr, *in_f2 = nullptr, *in_f3 = nullptr;
+    // one-shot peer-memory all-reduce (k_allreduce_step)
+    bool p2pReduce = false;
+    PeerBuf* peerLocal = nullptr;
+    std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)
+    PeerBuf** d_peers = nullptr;
+    unsigned long long reduceSeq = 0;
     Scalars* S = nullptr;
     Scalars* hS = nullptr;  // pinned
     double* partials = nullptr;
@@ -367,6 +374,15 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
 // after a reducing kernel with a step: all-reduce + scalar step when nranks > 1
 int reduce_post(b200_ctx* ctx, int step) {
     if (ctx->nranks == 1) return B200_OK;
+    if (ctx->p2pReduce) {
+        ++ctx->reduceSeq;
+        prof_begin(ctx, PC_SCALAR);
+        k_allreduce_step<<<1, 32, 0, ctx->sc>>>(ctx->S, ctx->d_peers, ctx->rank, ctx->nranks,
+                                               ctx->reduceSeq, step);
+        prof_end(ctx, PC_SCALAR);
+        ctx->launches++;
+        return B200_OK;
+    }
     NC(g_nccl.AllReduce(ctx->S->sums, ctx->S->gsums, kNSums, ncclDouble, ncclSum, ctx->comm, ctx->sc));
     LAUNCH(PC_SCALAR, k_scalar_step, 1, ctx->S, step);
     return B200_OK;
@@ -378,9 +394,11 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
     const int N = ctx->N;
     const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
     if (halo) {
-        LAUNCH(PC_PACK, k_pack, grid_for(ctx, P.nSlots), P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
+        // pack + exchange run on the comm stream, concurrently with the interior Amul
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
+        k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
+        ctx->launches++;
         NC(g_nccl.GroupStart());
         for (int k = 0; k < P.h.nIfaces; ++k) {
             const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
@@ -652,8 +670,46 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
         perf->solveMs = ms;
     }
+    if (h.nonfinite == 2) return fail(ctx, B200_ENCCL, "peer-memory all-reduce timed out (a rank never arrived)");
     if (h.nonfinite) return fail(ctx, B200_ENONFINITE, "non-finite residual in PCG");
     return B200_OK;
+}
+
+// Map every rank's PeerBuf into this process (CUDA IPC; handles exchanged with ncclAllGather).
+bool setup_peer_reduce(b200_ctx* c, std::string& why) {
+    const int n = c->nranks;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&c->peerLocal, sizeof(PeerBuf))) != cudaSuccess) { why = cudaGetErrorString(e); return false; }
+    cudaMemset(c->peerLocal, 0, sizeof(PeerBuf));
+    cudaIpcMemHandle_t mine;
+    if ((e = cudaIpcGetMemHandle(&mine, c->peerLocal)) != cudaSuccess) { why = cudaGetErrorString(e); cudaGetLastError(); return false; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    unsigned char *d_send = nullptr, *d_recv = nullptr;
+    if (cudaMalloc((void**)&d_send, 64) != cudaSuccess || cudaMalloc((void**)&d_recv, 64 * (size_t)n) != cudaSuccess) { why = "cudaMalloc"; return false; }
+    cudaMemcpyAsync(d_send, &mine, 64, cudaMemcpyHostToDevice, c->sc);
+    ncclResult_t r = g_nccl.AllGather(d_send, d_recv, 64, ncclUint8, c->comm, c->sc);
+    std::vector<cudaIpcMemHandle_t> all((size_t)n);
+    cudaMemcpyAsync(all.data(), d_recv, 64 * (size_t)n, cudaMemcpyDeviceToHost, c->sc);
+    cudaStreamSynchronize(c->sc);
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (r != ncclSuccess) { why = g_nccl.GetErrorString(r); return false; }
+    std::vector<PeerBuf*> ptrs((size_t)n, nullptr);
+    bool ok = true;
+    for (int k = 0; k < n; ++k) {
+        if (k == c->rank) { ptrs[k] = c->peerLocal; continue; }
+        void* p = nullptr;
+        e = cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); ok = false; break; }
+        c->peerMapped.push_back(p);
+        ptrs[k] = (PeerBuf*)p;
+    }
+    if (ok) {
+        if (cudaMalloc((void**)&c->d_peers, sizeof(PeerBuf*) * (size_t)n) != cudaSuccess) { why = "cudaMalloc"; ok = false; }
+        else cudaMemcpy(c->d_peers, ptrs.data(), sizeof(PeerBuf*) * (size_t)n, cudaMemcpyHostToDevice);
+    }
+    c->p2pReduce = ok;
+    return ok;
 }
 
 }  // namespace
@@ -744,6 +800,24 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         if (!g_nccl.load()) return bail(B200_ENCCL, g_nccl.error);
         ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
         if (r != ncclSuccess) return bail(B200_ENCCL, g_nccl.GetErrorString(r));
+        const char* ar = getenv("B200PCG_ALLREDUCE");
+        if (!(ar && std::string(ar) == "nccl") && nranks <= kMaxRanks) {
+            std::string why;
+            if (!setup_peer_reduce(c, why)) {
+                // not fatal: fall back to ncclAllReduce, but every rank must take the same path
+                fprintf(stderr, "b200pcg[%d]: peer-memory all-reduce unavailable (%s); using NCCL\n", rank, why.c_str());
+            }
+            // agree across ranks (min over ranks of the local success flag)
+            int ok = c->p2pReduce ? 1 : 0;
+            int* d_ok = reinterpret_cast<int*>(c->partials);
+            cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->sc);
+            g_nccl.AllReduce(d_ok, d_ok + 1, 1, ncclInt, ncclMin, c->comm, c->sc);
+            cudaMemcpyAsync(&ok, d_ok + 1, sizeof(int), cudaMemcpyDeviceToHost, c->sc);
+            cudaStreamSynchronize(c->sc);
+            c->p2pReduce = (ok == 1);
+            cudaMemsetAsync(c->partials, 0, sizeof(double) * 4, c->sc);
+            cudaStreamSynchronize(c->sc);
+        }
     }
     *out = c;
     return B200_OK;
@@ -755,7 +829,10 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (c->sc) cudaStreamSynchronize(c->sc);
     if (c->sm) cudaStreamSynchronize(c->sm);
     free_mesh(c);
+    for (void* p : c->peerMapped) cudaIpcCloseMemHandle(p);
+    if (c->d_peers) cudaFree(c->d_peers);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->peerLocal) cudaFree(c->peerLocal);
     for (auto ev : c->profPool) cudaEventDestroy(ev);
     dev_free(c->S);
     dev_free(c->partials);

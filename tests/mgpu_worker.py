@@ -60,6 +60,28 @@ for pre, exact in (("diagonal", False), ("none", False), ("DIC", True), ("DIC", 
         results[key] = {"iters": perf.nIterations, "oracle_iters": pr.nIterations, "relerr_vs_oracle": err,
                         "err_vs_xstar": xerr, "converged": bool(perf.converged),
                         "init": perf.initialResidual, "oracle_init": pr.initialResidual}
+# polyhedral mesh, RCB ("scotch-class") decomposition: irregular processor patches, cells with
+# several processor faces, several neighbours per rank
+poly = mg.bcc_poly(10, 10, 12)
+c2p = mg.partition_rcb(poly.xyz, world)
+subs = mg.decompose(poly, c2p, world)
+ps = subs[rank]
+ctx.set_addressing(ps.addr)
+for pre, exact in (("diagonal", False), ("DIC", True)):
+    ctl = {"preconditioner": pre, "tolerance": 1e-8, "relTol": 0.0, "maxIter": 3000}
+    if exact:
+        ctl["B200"] = {"dicMode": "exact"}
+    psi = np.zeros(ps.addr.nCells)
+    perf = pkg.B200PCG("p_rgh", ps.matrix, ps.bou, None, ps.interfaces, ctl, context=ctx).solve(psi, ps.source)
+    allpsi = [None] * world
+    dist.all_gather_object(allpsi, psi)
+    if rank == 0:
+        ref = [np.zeros(x_.addr.nCells) for x_ in subs]
+        pr = orc.pcg_solve(subs, ref, pre, 1e-8, 0.0, 3000)
+        err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
+        results["poly-" + pre + ("-exact" if exact else "")] = {
+            "iters": perf.nIterations, "oracle_iters": pr.nIterations, "relerr_vs_oracle": err,
+            "nbrs": [len(x_.bou) for x_ in subs]}
 if rank == 0:
     print("MGPU_RESULT " + json.dumps(results))
 ctx.close()

@@ -41,3 +41,6 @@ def test_multigpu_parity(world):
     assert res["none"]["converged"] and res["none"]["relerr_vs_oracle"] < 1e-5
     assert res["DIC"]["converged"] and res["DIC"]["relerr_vs_oracle"] < 1e-6
     assert res["DIC"]["iters"] < res["diagonal"]["iters"]
+    for key in ("poly-diagonal", "poly-DIC-exact"):
+        assert res[key]["iters"] == res[key]["oracle_iters"], (key, res[key])
+        assert res[key]["relerr_vs_oracle"] < 1e-11, (key, res[key])
