@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200_abi_version", "b200_device_count", "b200_set_addressing", "b200_assemble_laplacian",
     "b200_assemble_laplacian_device", "b200_solve", "b200_solve_device", "b200_amul", "b200_flux",
     "b200_host_alloc", "b200_host_free", "b200_launch_count", "b200_debug_force_iterations",
-    "b200_profile_enable", "b200_profile_json",
+    "b200_profile_enable", "b200_profile_json", "b200_describe",
 ]
 
 
@@ -99,6 +99,8 @@ def load_pcg():
     L.b200_profile_enable.argtypes = [vp, C.c_int]
     L.b200_profile_json.argtypes = [vp]
     L.b200_profile_json.restype = C.c_char_p
+    L.b200_describe.argtypes = [vp]
+    L.b200_describe.restype = C.c_char_p
     # host-only plan inspection (plan_debug.cpp)
     L.b200_debug_plan_build.argtypes = [C.c_int, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
     L.b200_debug_plan_build.restype = vp

@@ -52,11 +52,17 @@ struct Scalars {
     unsigned int pad1;
 };
 
+struct PeerBuf;
 struct Reduce {
     Scalars* S;
     double* partials;   // [kNSums][kMaxGrid]
     int step;           // Step to run when this kernel completes the reduction (STEP_NONE:
                         // only accumulate into S->acc)
+    // nranks > 1 with peer-memory reductions: the last block of the reducing kernel performs the
+    // cross-rank sum itself (peer_allreduce_step); peers == nullptr -> host issues ncclAllReduce
+    PeerBuf* const* peers;
+    int rank;
+    unsigned long long seq;
 };
 
 // ---- scalar steps (OF-dev PCG.C, SolverPerformance.C) ---------------
@@ -156,10 +162,10 @@ struct PeerBuf {
     unsigned long long flags[2][kMaxRanks];
 };
 
-__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
-                                 unsigned long long seq, int step) {
-    if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
-    const int lane = threadIdx.x;
+// one warp (all 32 lanes must call)
+__device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
+                                                    unsigned long long seq, int step) {
+    const int lane = threadIdx.x & 31;
     const int par = (int)(seq & 1ull);
     if (lane < nranks) {
         PeerBuf* dst = peers[lane];
@@ -205,6 +211,13 @@ __global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, in
             scalar_step(step, S, S->gsums);
         }
     }
+}
+
+// stand-alone form (one warp), for reductions whose local sums were produced without a fused finish
+__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
+                                 unsigned long long seq, int step) {
+    if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
+    peer_allreduce_step(S, peers, rank, nranks, seq, step);
 }
 
 // ---- deterministic block reduction + last-block finish -----------------------------------
@@ -259,8 +272,8 @@ __device__ __forceinline__ void reduce_finish(double (&v)[NV], const Reduce& R) 
         t[i] = s;
     }
     block_sum<NV>(t, sh);
+    Scalars* S = R.S;
     if (threadIdx.x == 0) {
-        Scalars* S = R.S;
 #pragma unroll
         for (int i = 0; i < NV; ++i) S->acc[i] = __dadd_rn(S->acc[i], t[i]);
         if (R.step != STEP_NONE) {
@@ -269,8 +282,17 @@ __device__ __forceinline__ void reduce_finish(double (&v)[NV], const Reduce& R) 
                 S->sums[i] = S->acc[i];
                 S->acc[i] = 0.0;
             }
+#pragma unroll
+            for (int i = NV; i < kNSums; ++i) S->sums[i] = 0.0;
             if (S->nranks == 1) scalar_step(R.step, S, S->sums);
         }
+    }
+    if (R.step != STEP_NONE && R.peers != nullptr) {
+        // cross-rank sum over NVLink peer memory + scalar step, by the first warp of this (last) block
+        __syncthreads();
+        if (threadIdx.x < 32) peer_allreduce_step(S, R.peers, R.rank, S->nranks, R.seq, R.step);
+    }
+    if (threadIdx.x == 0) {
         S->ticket = 0u;
         __threadfence();
     }
@@ -490,7 +512,11 @@ __host__ __device__ inline size_t sym_stage_bytes(int WU, int WL) {
     return (size_t)kChunkRows * ((size_t)WU * 12 + (size_t)WL * 4 + 4 + 16);
 }
 
-template <bool DOT, int kSymStages>
+// BL/BU: number of lower/upper entries handled by the unrolled, batched-load path.  TAIL = false
+// asserts WL <= BL and WU <= BU (every row fits the unrolled path), which removes the tail loops
+// and the unused predicated slots: the kernel is ~50 % issue-bound (ncu: 237 instructions per
+// 32 rows with BL = BU = 4 on the 3+3-entry hex rows), so instructions matter as much as bytes.
+template <bool DOT, int kSymStages, int BL, int BU, bool TAIL>
 __global__ void __launch_bounds__(kBlock)
 k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
                const int* __restrict__ uCol, const double* __restrict__ uVal,
@@ -498,7 +524,6 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
                const double* __restrict__ x, double* __restrict__ y, Reduce R) {
     if (R.S->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int B = kSymBatch;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t stageBytes = sym_stage_bytes(WU, WL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // [kSymStages]
@@ -551,9 +576,9 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
             const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
             const uint32_t lb = warp * strideL + lane, ub = warp * strideU + lane;
             // gathers served by L2/L1 (the only exposed latency)
-            double lv[B], lx[B], ux[B];
+            double lv[BL > 0 ? BL : 1], lx[BL > 0 ? BL : 1], ux[BU > 0 ? BU : 1];
 #pragma unroll
-            for (int k = 0; k < B; ++k) {
+            for (int k = 0; k < BL; ++k) {
                 const uint32_t pk = (k < nL) ? sRef[lb + 32u * k] : 0u;
                 const uint32_t a = pk >> 5;
                 const uint32_t pos = (a >> 5) * strideU + ((pk & 31u) << 5) + (a & 31u);
@@ -561,23 +586,25 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
                 lx[k] = (k < nL) ? __ldg(&x[a]) : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < B; ++k) ux[k] = (k < nU) ? __ldg(&x[sCol[ub + 32u * k]]) : 0.0;
+            for (int k = 0; k < BU; ++k) ux[k] = (k < nU) ? __ldg(&x[sCol[ub + 32u * k]]) : 0.0;
             const double xr = sX[tid];
             double acc = __dmul_rn(sDiag[tid], xr);
 #pragma unroll
-            for (int k = 0; k < B; ++k)
+            for (int k = 0; k < BL; ++k)
                 if (k < nL) acc = __dadd_rn(acc, __dmul_rn(lv[k], lx[k]));
-            for (int j = B; j < nL; ++j) {
-                const uint32_t p0 = sRef[lb + 32u * j];
-                const uint32_t a = p0 >> 5;
-                const double v0 = uVal[(a >> 5) * strideU + ((p0 & 31u) << 5) + (a & 31u)];
-                acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[a])));
-            }
+            if (TAIL)
+                for (int j = BL; j < nL; ++j) {
+                    const uint32_t p0 = sRef[lb + 32u * j];
+                    const uint32_t a = p0 >> 5;
+                    const double v0 = uVal[(a >> 5) * strideU + ((p0 & 31u) << 5) + (a & 31u)];
+                    acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[a])));
+                }
 #pragma unroll
-            for (int k = 0; k < B; ++k)
+            for (int k = 0; k < BU; ++k)
                 if (k < nU) acc = __dadd_rn(acc, __dmul_rn(sVal[ub + 32u * k], ux[k]));
-            for (int j = B; j < nU; ++j)
-                acc = __dadd_rn(acc, __dmul_rn(sVal[ub + 32u * j], __ldg(&x[sCol[ub + 32u * j]])));
+            if (TAIL)
+                for (int j = BU; j < nU; ++j)
+                    acc = __dadd_rn(acc, __dmul_rn(sVal[ub + 32u * j], __ldg(&x[sCol[ub + 32u * j]])));
             y[r] = acc;
             if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
         }
@@ -585,6 +612,170 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
         if (tid == 0) {
             const int next = chunk + kSymStages * gridDim.x;
             if (next < nChunks) issue(next, s);
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
+// ---- shared-memory-window variant of the symmetric Amul -----------------------------------------
+// ncu on k_spmv_sym_tma (profiles/r01_v4_ncu_full.md): 1.09 GB of bulk copies + 37.5 M gather
+// sectors (1.2 GB) per launch = 2.3 GB through the L2 in 205 us = 11.2 TB/s, which IS the L2->SM
+// throughput cap of the part (~6300 B/clk): the kernel is bound by the L2-served neighbour gathers,
+// not by HBM.  This variant removes most of them.  A CTA walks RUNS of `runLen` consecutive 256-row
+// chunks and keeps three rings in shared memory, filled by the bulk-copy engine:
+//     X ring (depth 4): x of chunks k-1, k, k+1 (+ k+2 in flight)
+//     V ring (depth 3): upper values of chunks k-1, k (+ k+1 in flight)
+//     B ring (depth 2): upper columns, lower references, row lengths, diag of chunk k (+ k+1)
+// so that every neighbour whose row lies in the previous / current / next chunk -- on a banded
+// (bandwidth-reduced) cell order that is most of them -- is served from shared memory at no extra
+// L2 traffic: the data was staged for its own row anyway.  Only out-of-window neighbours go to
+// L1/L2.  Runs are interleaved across CTAs (run j of CTA b = b + j*grid) so the whole grid still
+// sweeps the matrix as one front and far neighbours (+-nx*ny) stay L2 hits.
+// Arithmetic and row-sum order are those of k_spmv_sym: bit-identical results.
+constexpr int kWinX = 4, kWinV = 3, kWinB = 2;
+
+__host__ __device__ inline size_t win_b_bytes(int WU, int WL) {
+    return (size_t)kChunkRows * ((size_t)WU * 4 + (size_t)WL * 4 + 4 + 8);
+}
+__host__ __device__ inline size_t win_smem_bytes(int WU, int WL) {
+    return 128 + (size_t)kWinX * kChunkRows * 8 + (size_t)kWinV * kChunkRows * WU * 8 +
+           (size_t)kWinB * win_b_bytes(WU, WL);
+}
+
+template <bool DOT, bool NEXT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv_sym_win(int N, int WU, int WL, int runLen, const uint32_t* __restrict__ rowLen,
+               const int* __restrict__ uCol, const double* __restrict__ uVal,
+               const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
+               const double* __restrict__ x, double* __restrict__ y, Reduce R) {
+    if (R.S->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int B = kSymBatch;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t* barX = reinterpret_cast<uint64_t*>(smem_raw);   // [kWinX]
+    uint64_t* barV = barX + kWinX;                            // [kWinV]
+    uint64_t* barB = barV + kWinV;                            // [kWinB]
+    double* ringX = reinterpret_cast<double*>(smem_raw + 128);
+    double* ringV = ringX + kWinX * kChunkRows;
+    const size_t vElems = (size_t)kChunkRows * WU;
+    unsigned char* ringB = reinterpret_cast<unsigned char*>(ringV + kWinV * vElems);
+    const size_t bBytes = win_b_bytes(WU, WL);
+    // B slot layout: diag | uCol | lRef | rowLen
+    const size_t oCol = (size_t)kChunkRows * 8, oRef = oCol + (size_t)kChunkRows * WU * 4,
+                 oLen = oRef + (size_t)kChunkRows * WL * 4;
+    const int nChunks = (N + kChunkRows - 1) / kChunkRows;
+    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
+
+    // this CTA's chunk sequence: run j = blockIdx + j*grid, chunks (run*runLen ..+runLen)
+    int T = 0;
+    for (int64_t base = (int64_t)blockIdx.x * runLen; base < nChunks; base += (int64_t)gridDim.x * runLen)
+        T += (int)min((int64_t)runLen, (int64_t)nChunks - base);
+    auto chunkAt = [&](int k) -> int {
+        return (int)(((int64_t)blockIdx.x + (int64_t)(k / runLen) * gridDim.x) * runLen + (k % runLen));
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kWinX + kWinV + kWinB; ++s) mbar_init(&barX[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issueX = [&](int k) {
+        const int s = k & (kWinX - 1);
+        mbar_expect_tx(&barX[s], kChunkRows * 8);
+        bulk_g2s(ringX + s * kChunkRows, x + (size_t)chunkAt(k) * kChunkRows, kChunkRows * 8, &barX[s]);
+    };
+    auto issueV = [&](int k) {
+        const int s = k % kWinV;
+        mbar_expect_tx(&barV[s], (uint32_t)(vElems * 8));
+        bulk_g2s(ringV + s * vElems, uVal + (size_t)chunkAt(k) * vElems, (uint32_t)(vElems * 8), &barV[s]);
+    };
+    auto issueB = [&](int k) {
+        const int s = k & (kWinB - 1);
+        unsigned char* st = ringB + (size_t)s * bBytes;
+        const size_t r0 = (size_t)chunkAt(k) * kChunkRows;
+        mbar_expect_tx(&barB[s], (uint32_t)bBytes);
+        bulk_g2s(st, diag + r0, kChunkRows * 8, &barB[s]);
+        bulk_g2s(st + oCol, uCol + r0 * WU, (uint32_t)(kChunkRows * WU * 4), &barB[s]);
+        if (WL > 0) bulk_g2s(st + oRef, lRef + r0 * WL, (uint32_t)(kChunkRows * WL * 4), &barB[s]);
+        bulk_g2s(st + oLen, rowLen + r0, kChunkRows * 4, &barB[s]);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < kWinB && k < T; ++k) { issueB(k); issueV(k); }
+        for (int k = 0; k < kWinX - 1 && k < T; ++k) issueX(k);
+    }
+
+    double dot[1] = {0.0};
+    for (int k = 0; k < T; ++k) {
+        const int chunk = chunkAt(k);
+        const int kin = k % runLen;
+        const int lo = (kin != 0) ? -1 : 0;                                   // previous chunk staged?
+        const int hi = (NEXT && kin != runLen - 1 && k + 1 < T) ? 1 : 0;      // next chunk's x staged?
+        mbar_wait(&barB[k & (kWinB - 1)], (uint32_t)((k / kWinB) & 1));
+        mbar_wait(&barV[k % kWinV], (uint32_t)((k / kWinV) & 1));
+        mbar_wait(&barX[k & (kWinX - 1)], (uint32_t)((k / kWinX) & 1));
+        if (hi) mbar_wait(&barX[(k + 1) & (kWinX - 1)], (uint32_t)(((k + 1) / kWinX) & 1));
+        const unsigned char* st = ringB + (size_t)(k & (kWinB - 1)) * bBytes;
+        const double* sDiag = reinterpret_cast<const double*>(st);
+        const int* sCol = reinterpret_cast<const int*>(st + oCol);
+        const uint32_t* sRef = reinterpret_cast<const uint32_t*>(st + oRef);
+        const uint32_t* sLen = reinterpret_cast<const uint32_t*>(st + oLen);
+        const double* sVcur = ringV + (size_t)(k % kWinV) * vElems;
+        const double* sVprev = ringV + (size_t)((k + kWinV - 1) % kWinV) * vElems;
+        const double* sXcur = ringX + (k & (kWinX - 1)) * kChunkRows;
+        const int r = chunk * kChunkRows + (int)tid;
+
+        // x of column c: shared-memory ring when its chunk is staged, else L1/L2
+        auto getX = [&](uint32_t c) -> double {
+            const int d = (int)(c >> 8) - chunk;
+            return (d >= lo && d <= hi) ? ringX[(((uint32_t)(k + d)) & (kWinX - 1)) * kChunkRows + (c & 255u)]
+                                        : __ldg(&x[c]);
+        };
+        // value of the q-th upper entry of owner row a (a < r)
+        auto getV = [&](uint32_t a, uint32_t q) -> double {
+            const int d = (int)(a >> 8) - chunk;
+            const uint32_t loc = a & 255u;
+            const uint32_t sp = (loc >> 5) * strideU + (q << 5) + (loc & 31u);
+            if (d == 0) return sVcur[sp];
+            if (d >= lo) return sVprev[sp];      // d == -1 and the previous chunk is staged
+            return uVal[(a >> 5) * strideU + (q << 5) + (a & 31u)];
+        };
+
+        if (r < N) {
+            const uint32_t len = sLen[tid];
+            const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
+            const uint32_t lb = warp * strideL + lane, ub = warp * strideU + lane;
+            double lv[B], lx[B], ux[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const uint32_t pk = (j < nL) ? sRef[lb + 32u * j] : ((uint32_t)r << 5);
+                lv[j] = (j < nL) ? getV(pk >> 5, pk & 31u) : 0.0;
+                lx[j] = (j < nL) ? getX(pk >> 5) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) ux[j] = (j < nU) ? getX((uint32_t)sCol[ub + 32u * j]) : 0.0;
+            const double xr = sXcur[tid];
+            double acc = __dmul_rn(sDiag[tid], xr);
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (j < nL) acc = __dadd_rn(acc, __dmul_rn(lv[j], lx[j]));
+            for (int j = B; j < nL; ++j) {
+                const uint32_t p0 = sRef[lb + 32u * j];
+                acc = __dadd_rn(acc, __dmul_rn(getV(p0 >> 5, p0 & 31u), getX(p0 >> 5)));
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (j < nU) acc = __dadd_rn(acc, __dmul_rn(sVcur[ub + 32u * j], ux[j]));
+            for (int j = B; j < nU; ++j)
+                acc = __dadd_rn(acc, __dmul_rn(sVcur[ub + 32u * j], getX((uint32_t)sCol[ub + 32u * j])));
+            y[r] = acc;
+            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+        }
+        __syncthreads();   // every thread is done with chunk k (and with the previous chunk's slots)
+        if (tid == 0) {
+            if (k + kWinB < T) { issueB(k + kWinB); }
+            if (k + kWinV - 1 < T) issueV(k + kWinV - 1);
+            if (k + kWinX - 1 < T) issueX(k + kWinX - 1);
         }
     }
     if (DOT) reduce_finish<1>(dot, R);
@@ -926,14 +1117,36 @@ k_face_coeff(int F, const double* __restrict__ gamma, const double* __restrict__
 // sorted segments (neighbour side via losort, then owner side) of the natural-order plan.
 __global__ void __launch_bounds__(kBlock)
 k_neg_sum_diag(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
-               const int* __restrict__ faceOf, const double* __restrict__ upper,
-               double* __restrict__ diag) {
+               const int* __restrict__ faceOf, const int* __restrict__ perm,
+               const double* __restrict__ upper, double* __restrict__ diag) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const int n = (int)(rowLen[r] >> 16);
+        const int cell = perm ? perm[r] : r;   // diag is in the caller's (natural) cell order
+        const double d0 = diag[cell];
         double d = 0.0;
-        for (int j = 0; j < n; ++j) d = __dadd_rn(d, -__ldg(&upper[faceOf[base + 32 * (int64_t)j]]));
-        diag[r] = __dadd_rn(diag[r], d);
+        int j = 0;
+        // batches of 4 independent (index, value) load pairs; the adds stay in face order
+        for (; j + 4 <= n; j += 4) {
+            const int64_t e = base + 32 * (int64_t)j;
+            const int f0 = faceOf[e], f1 = faceOf[e + 32], f2 = faceOf[e + 64], f3 = faceOf[e + 96];
+            const double u0 = __ldg(&upper[f0]), u1 = __ldg(&upper[f1]), u2 = __ldg(&upper[f2]),
+                         u3 = __ldg(&upper[f3]);
+            d = __dadd_rn(d, -u0);
+            d = __dadd_rn(d, -u1);
+            d = __dadd_rn(d, -u2);
+            d = __dadd_rn(d, -u3);
+        }
+        if (j + 2 <= n) {
+            const int64_t e = base + 32 * (int64_t)j;
+            const int f0 = faceOf[e], f1 = faceOf[e + 32];
+            const double u0 = __ldg(&upper[f0]), u1 = __ldg(&upper[f1]);
+            d = __dadd_rn(d, -u0);
+            d = __dadd_rn(d, -u1);
+            j += 2;
+        }
+        if (j < n) d = __dadd_rn(d, -__ldg(&upper[faceOf[base + 32 * (int64_t)j]]));
+        diag[cell] = __dadd_rn(d0, d);
     }
 }
 

@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 
@@ -43,12 +44,121 @@ void build_cell_faces(int32_t N, int32_t F, const int32_t* l, const int32_t* u, 
     }
 }
 
-// Greedy sequential multicolouring in natural cell order (first-fit).
-int32_t colour_greedy(int32_t N, const CellFaces& cf, std::vector<int32_t>& colour) {
+// Reverse Cuthill-McKee order of the cell-cell graph: order[k] = k-th cell.  Every connected
+// component is started from a pseudo-peripheral cell (two BFS sweeps from its first unvisited
+// cell), neighbours are visited in ascending degree.
+void rcm_order(int32_t N, const CellFaces& cf, std::vector<int32_t>& order) {
+    order.clear();
+    order.reserve((size_t)N);
+    std::vector<uint8_t> seen((size_t)N, 0);
+    std::vector<int32_t> level, nbrs;
+    auto deg = [&](int32_t c) { return (int32_t)(cf.start[c + 1] - cf.start[c]); };
+    // BFS from s over unseen cells without marking them permanently; returns a far, low-degree cell
+    std::vector<int32_t> queue, touched;
+    std::vector<int32_t> dist((size_t)N, -1);
+    auto far_cell = [&](int32_t s) {
+        queue.clear();
+        touched.clear();
+        queue.push_back(s);
+        dist[s] = 0;
+        touched.push_back(s);
+        size_t head = 0;
+        while (head < queue.size()) {
+            const int32_t c = queue[head++];
+            for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e) {
+                const int32_t o = cf.other[e];
+                if (!seen[o] && dist[o] < 0) {
+                    dist[o] = dist[c] + 1;
+                    queue.push_back(o);
+                    touched.push_back(o);
+                }
+            }
+        }
+        const int32_t dmax = dist[queue.back()];
+        int32_t best = queue.back();
+        for (size_t i = queue.size(); i-- > 0 && dist[queue[i]] == dmax;)
+            if (deg(queue[i]) < deg(best)) best = queue[i];
+        for (int32_t c : touched) dist[c] = -1;
+        return best;
+    };
+    for (int32_t s0 = 0; s0 < N; ++s0) {
+        if (seen[s0]) continue;
+        int32_t s = far_cell(s0);
+        s = far_cell(s);
+        size_t head = order.size();
+        order.push_back(s);
+        seen[s] = 1;
+        while (head < order.size()) {
+            const int32_t c = order[head++];
+            nbrs.clear();
+            for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e) {
+                const int32_t o = cf.other[e];
+                if (!seen[o]) {
+                    seen[o] = 1;
+                    nbrs.push_back(o);
+                }
+            }
+            std::sort(nbrs.begin(), nbrs.end(), [&](int32_t a, int32_t b) {
+                const int32_t da = deg(a), db = deg(b);
+                return da != db ? da < db : a < b;
+            });
+            for (int32_t o : nbrs) order.push_back(o);
+        }
+    }
+    std::reverse(order.begin(), order.end());
+}
+
+// mean |pos(l) - pos(u)| over the faces (pos == nullptr: natural numbering)
+double mean_span(int32_t F, const int32_t* l, const int32_t* u, const int32_t* pos) {
+    if (F == 0) return 0.0;
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (int32_t f = 0; f < F; ++f) {
+        const int64_t a = pos ? pos[l[f]] : l[f], b = pos ? pos[u[f]] : u[f];
+        s += (double)(a > b ? a - b : b - a);
+    }
+    return s / F;
+}
+
+// Coalescing metric of a row order: the kernels run one row per thread, a warp = 32 consecutive rows,
+// and the j-th neighbour gathers of a warp form one memory request.  Returns the mean number of
+// distinct 32-byte sectors (4 doubles) per such request over a sample of warps: ~8-9 on a
+// lexicographic hex mesh, ~30 (of 32) on a locally shuffled numbering.
+// order: position -> cell (nullptr: natural), pos: cell -> position (nullptr: natural).
+double sectors_per_gather(int32_t N, const CellFaces& cf, const int32_t* order, const int32_t* pos) {
+    const int32_t nSlices = (N + 31) / 32;
+    if (nSlices == 0) return 0.0;
+    const int32_t step = std::max(1, nSlices / 4096);
+    double total = 0.0, requests = 0.0;
+#pragma omp parallel for reduction(+ : total, requests) schedule(static)
+    for (int32_t s = 0; s < nSlices; s += step) {
+        int32_t sec[32];
+        for (int32_t j = 0;; ++j) {
+            int n = 0;
+            for (int32_t k = s * 32; k < std::min(N, s * 32 + 32); ++k) {
+                const int32_t c = order ? order[k] : k;
+                if (cf.start[c] + j < cf.start[c + 1]) {
+                    const int32_t o = cf.other[cf.start[c] + j];
+                    sec[n++] = (pos ? pos[o] : o) >> 2;
+                }
+            }
+            if (n == 0) break;
+            std::sort(sec, sec + n);
+            total += (double)(std::unique(sec, sec + n) - sec);
+            requests += 1.0;
+        }
+    }
+    return requests > 0 ? total / requests : 0.0;
+}
+
+// Greedy sequential multicolouring (first-fit), cells visited in `base` order (natural if empty).
+int32_t colour_greedy(int32_t N, const CellFaces& cf, const std::vector<int32_t>& base,
+                      std::vector<int32_t>& colour) {
     colour.assign((size_t)N, -1);
     int32_t nCol = 0;
     std::vector<int32_t> mark;  // mark[k] == c  <=> colour k is used by a neighbour of c
-    for (int32_t c = 0; c < N; ++c) {
+    for (int32_t k0 = 0; k0 < N; ++k0) {
+        const int32_t c = base.empty() ? k0 : base[k0];
         for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e) {
             int32_t k = colour[cf.other[e]];
             if (k >= 0) {
@@ -86,7 +196,7 @@ int32_t colour_levels(int32_t N, int32_t F, const int32_t* l, const int32_t* u,
 }  // namespace
 
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
-                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P) {
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P, Renumber renumber) {
     if (N < 0 || F < 0 || nIfaces < 0) return "negative size";
     if (F > 0 && (!l || !u)) return "null lowerAddr/upperAddr";
     if (nIfaces > 0 && !ifaces) return "null interface list";
@@ -112,13 +222,46 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
     CellFaces cf;
     build_cell_faces(N, F, l, u, cf);
 
+    // ---- baseOrder order: natural, or reverse Cuthill-McKee when the given numbering is cache-hostile ----
+    // (never for Levels: DIC-exact reproduces the recurrences of the NATURAL face order)
+    std::vector<int32_t> baseOrder;   // baseOrder position -> cell (empty == natural)
+    P.spanNatural = P.spanUsed = mean_span(F, l, u, nullptr);
+    if (ordering != Ordering::Levels && renumber != Renumber::Off && N > 1 && F > 0) {
+        // Two symptoms of a cache-hostile numbering: a mean face span far above a mesh plane
+        // (~N^(2/3): long-range jumps, L2 misses), or warps whose gathers do not coalesce (local
+        // shuffles: L1 sector-throughput bound).  RCM is kept only if it clearly improves either.
+        const double banded = 4.0 * std::pow((double)N, 2.0 / 3.0) + 64.0;
+        P.sectorsNatural = P.sectorsUsed = sectors_per_gather(N, cf, nullptr, nullptr);
+        if (renumber == Renumber::Force || P.spanNatural > banded || P.sectorsNatural > 12.0) {
+            rcm_order(N, cf, baseOrder);
+            std::vector<int32_t> pos((size_t)N);
+            for (int32_t k = 0; k < N; ++k) pos[baseOrder[k]] = k;
+            const double spanRcm = mean_span(F, l, u, pos.data());
+            const double secRcm = sectors_per_gather(N, cf, baseOrder.data(), pos.data());
+            const bool better = (P.spanNatural > banded && spanRcm < 0.5 * P.spanNatural && secRcm < 1.1 * P.sectorsNatural) ||
+                                (secRcm < 0.85 * P.sectorsNatural && spanRcm < 2.0 * std::max(P.spanNatural, banded));
+            if (renumber == Renumber::Force || better) {
+                P.renumbered = true;
+                P.spanUsed = spanRcm;
+                P.sectorsUsed = secRcm;
+            } else {
+                baseOrder.clear();
+            }
+        }
+    }
+
     // ---- row order ----------------------------------------------------------------------
     if (ordering == Ordering::Natural) {
         P.nColours = 1;
         P.colourStart = {0, N};
+        if (P.renumbered) {
+            P.perm = baseOrder;
+            P.iperm.resize((size_t)N);
+            for (int32_t k = 0; k < N; ++k) P.iperm[baseOrder[k]] = k;
+        }
     } else {
         std::vector<int32_t> colour;
-        P.nColours = (ordering == Ordering::MultiColour) ? colour_greedy(N, cf, colour)
+        P.nColours = (ordering == Ordering::MultiColour) ? colour_greedy(N, cf, baseOrder, colour)
                                                         : colour_levels(N, F, l, u, colour);
         if (N == 0) P.nColours = 1;
         P.colourStart.assign((size_t)P.nColours + 1, 0);
@@ -127,7 +270,8 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
         P.perm.resize((size_t)N);
         P.iperm.resize((size_t)N);
         std::vector<int32_t> pos(P.colourStart.begin(), P.colourStart.end() - 1);
-        for (int32_t c = 0; c < N; ++c) {  // stable: natural order inside a colour
+        for (int32_t k = 0; k < N; ++k) {  // stable: baseOrder (natural / RCM) order inside a colour
+            const int32_t c = baseOrder.empty() ? k : baseOrder[k];
             int32_t r = pos[colour[c]]++;
             P.perm[r] = c;
             P.iperm[c] = r;
@@ -171,15 +315,19 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             ent.clear();
             for (int64_t e = e0; e < e1; ++e) ent.emplace_back(cf.face[e], rowOf(cf.other[e]));
             if (!ident) std::sort(ent.begin(), ent.end());
+            // A renumbered Natural plan serves Amul / sumA / negSumDiag only: keep the whole row in
+            // ascending face order (OpenFOAM's visiting order) -- no [earlier | later] grouping,
+            // which would change the order of the row sum.
+            const bool grouped = !(ordering == Ordering::Natural && !ident);
             for (auto& fe : ent)
-                if (fe.second < r) {
+                if (grouped && fe.second < r) {
                     P.col[base + 32 * (int64_t)j] = fe.second;
                     P.faceOf[base + 32 * (int64_t)j] = fe.first;
                     ++j;
                     ++nLower;
                 }
             for (auto& fe : ent)
-                if (fe.second > r) {
+                if (!grouped || fe.second > r) {
                     P.col[base + 32 * (int64_t)j] = fe.second;
                     P.faceOf[base + 32 * (int64_t)j] = fe.first;
                     ++j;
@@ -205,7 +353,9 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             wL = std::max(wL, nL);
         }
         const int64_t nU = (int64_t)P.nSlices * 32 * wU, nL = (int64_t)P.nSlices * 32 * wL;
-        const bool ok = (N > 0) && (N <= (1 << 27)) && wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL;
+        // (a renumbered Natural plan has no [lower | upper] split to build the references from)
+        const bool ok = (N > 0) && (N <= (1 << 27)) && wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL &&
+                        !(ordering == Ordering::Natural && !ident);
         if (ok) {
             Sp.WU = (int32_t)wU;
             Sp.WL = (int32_t)wL;

@@ -51,8 +51,19 @@ struct SymPlan {
     std::vector<uint32_t> lRef;   // [nL] (owner row << 5) | q
 };
 
+// Base cell order the row orders are derived from.  OpenFOAM meshes are normally bandwidth-reduced
+// (renumberMesh), but nothing guarantees it: on a cache-hostile numbering a warp's neighbour gathers
+// touch 32 different sectors per request and Amul drops to a quarter of the HBM roofline (measured on
+// the block-shuffled polyhedral workload).  The plan may therefore renumber rows by reverse
+// Cuthill-McKee.  Results do not change: every row still sums its faces in ascending natural face
+// order (the order of OpenFOAM's face loop); only the order of the global dot-product sums differs.
+enum class Renumber : int { Off = 0, Auto = -1, Force = 1 };
+
 struct HostPlan {
     Ordering ordering = Ordering::Natural;
+    bool renumbered = false;           // rows follow an RCM base order
+    double spanNatural = 0, spanUsed = 0;   // mean |row(l) - row(u)| over faces, before / after
+    double sectorsNatural = 0, sectorsUsed = 0;   // mean 32-B sectors per warp gather request (sampled)
     SymPlan sym;
     int32_t N = 0, F = 0;
     // row order
@@ -81,6 +92,7 @@ struct HostPlan {
 // Validates the LDU addressing (sizes, l<u, upper-triangular order) and builds the plan.
 // Returns empty string on success, else an error message.
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
-                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& out);
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& out,
+                       Renumber renumber = Renumber::Off);
 
 }  // namespace b200

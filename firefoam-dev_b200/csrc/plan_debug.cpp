@@ -31,6 +31,20 @@ void* b200_debug_plan_build(int ordering, int32_t N, int32_t F, const int32_t* l
     }
     return P;
 }
+void* b200_debug_plan_build2(int ordering, int renumber, int32_t N, int32_t F, const int32_t* l,
+                             const int32_t* u, int32_t nIfaces, const b200_dbg_iface* ifaces) {
+    auto* P = new HostPlan();
+    g_err = build_plan((Ordering)ordering, N, F, l, u, nIfaces, (const IfaceIn*)ifaces, *P, (Renumber)renumber);
+    if (!g_err.empty()) {
+        delete P;
+        return nullptr;
+    }
+    return P;
+}
+int32_t b200_debug_plan_renumbered(void* h) { return ((HostPlan*)h)->renumbered ? 1 : 0; }
+double b200_debug_plan_span(void* h, int which) {
+    return which ? ((HostPlan*)h)->spanUsed : ((HostPlan*)h)->spanNatural;
+}
 const char* b200_debug_plan_error(void) { return g_err.c_str(); }
 void b200_debug_plan_free(void* h) { delete (HostPlan*)h; }
 

@@ -101,7 +101,8 @@ struct DevPlan {
     int64_t symNU = 0;
     int symWU = 0, symWL = 0;
     bool symTma = false;
-    size_t symStage = 0;
+    bool symWin = false;
+    size_t symStage = 0, symWinBytes = 0;
     uint32_t* sRowLen = nullptr;
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
@@ -154,6 +155,16 @@ struct b200_ctx {
     // box (profiles/r01_tma_sweep.md): 2 stages x 4 CTAs/SM is the optimum -- deeper pipelines or more
     // CTAs shrink the L1 carve-out that serves the neighbour gathers.
     int symStages = 2, symPerSM = 0;
+    // shared-memory-window Amul (k_spmv_sym_win): run length in 256-row chunks (B200PCG_RUN), whether
+    // the next chunk's x is part of the window (B200PCG_NEXT), CTAs per SM (B200PCG_CTAS)
+    // Opt-in (B200PCG_SPMV=win): measured SLOWER than k_spmv_sym_tma on the 16 M hex box (275 vs 205 us,
+    // profiles/r01_v5_spmv_win_vs_tma.md): it removes the L2-latency stalls but needs 1.7x the
+    // instructions, and both kernels are issue-bound.
+    int winRun = 8;
+    bool winNext = true;
+    bool disableWin = true;
+    int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
+    bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
     // profiling
@@ -290,7 +301,7 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         ifs[k] = IfaceIn{ctx->hif[k].nbrRank, (int32_t)ctx->hif[k].faceCells.size(),
                          ctx->hif[k].faceCells.data()};
     std::string e = build_plan(ord, ctx->N, ctx->F, ctx->hl.data(), ctx->hu.data(),
-                               (int32_t)ifs.size(), ifs.data(), P.h);
+                               (int32_t)ifs.size(), ifs.data(), P.h, (Renumber)ctx->renumber);
     if (!e.empty()) return fail(ctx, B200_EINVAL, "set_addressing: " + e);
     RET(upload(ctx, &P.sliceBase, P.h.sliceBase));
     RET(upload(ctx, &P.rowLen, P.h.rowLen));
@@ -327,13 +338,22 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         P.symNU = (int64_t)(rowsPad * Y.WU);
         P.symStage = sym_stage_bytes(Y.WU, Y.WL);
         P.symTma = !ctx->disableTma && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
+        P.symWinBytes = win_smem_bytes(Y.WU, Y.WL);
+        P.symWin = !ctx->disableTma && !ctx->disableWin && P.symWinBytes <= 100 * 1024;
+        if (P.symWin) {
+            const int smemMax = 200 * 1024;
+            CU(cudaFuncSetAttribute(k_spmv_sym_win<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+            CU(cudaFuncSetAttribute(k_spmv_sym_win<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+            CU(cudaFuncSetAttribute(k_spmv_sym_win<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+            CU(cudaFuncSetAttribute(k_spmv_sym_win<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+        }
         if (P.symTma) {
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CU(cudaFuncSetAttribute(k_spmv_sym_tma<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+#define B200_TMA_ATTR(...) CU(cudaFuncSetAttribute(k_spmv_sym_tma<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024))
+            B200_TMA_ATTR(true, 2, 4, 4, true); B200_TMA_ATTR(false, 2, 4, 4, true);
+            B200_TMA_ATTR(true, 3, 4, 4, true); B200_TMA_ATTR(false, 3, 4, 4, true);
+            B200_TMA_ATTR(true, 2, 3, 3, false); B200_TMA_ATTR(false, 2, 3, 3, false);
+            B200_TMA_ATTR(true, 2, 2, 2, false); B200_TMA_ATTR(false, 2, 2, 2, false);
+#undef B200_TMA_ATTR
         }
         P.symWU = Y.WU;
         P.symWL = Y.WL;
@@ -371,18 +391,22 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
     return B200_OK;
 }
 
-// after a reducing kernel with a step: all-reduce + scalar step when nranks > 1
-int reduce_post(b200_ctx* ctx, int step) {
-    if (ctx->nranks == 1) return B200_OK;
-    if (ctx->p2pReduce) {
-        ++ctx->reduceSeq;
-        prof_begin(ctx, PC_SCALAR);
-        k_allreduce_step<<<1, 32, 0, ctx->sc>>>(ctx->S, ctx->d_peers, ctx->rank, ctx->nranks,
-                                               ctx->reduceSeq, step);
-        prof_end(ctx, PC_SCALAR);
-        ctx->launches++;
-        return B200_OK;
+// Reduction descriptor of a reducing kernel.  With nranks > 1 and peer-memory reductions, the
+// kernel that completes the reduction (step != STEP_NONE) also performs the cross-rank sum and the
+// scalar step in its last block: it gets the peer table and the next sequence number.
+Reduce mkR(b200_ctx* ctx, int step) {
+    Reduce R{ctx->S, ctx->partials, step, nullptr, ctx->rank, 0ull};
+    if (step != STEP_NONE && ctx->nranks > 1 && ctx->p2pReduce) {
+        R.peers = ctx->d_peers;
+        R.seq = ++ctx->reduceSeq;
     }
+    return R;
+}
+
+// after a reducing kernel with a step: all-reduce + scalar step when nranks > 1 (nothing to do when
+// the kernel's last block already did both over peer memory)
+int reduce_post(b200_ctx* ctx, int step) {
+    if (ctx->nranks == 1 || ctx->p2pReduce) return B200_OK;
     NC(g_nccl.AllReduce(ctx->S->sums, ctx->S->gsums, kNSums, ncclDouble, ncclSum, ctx->comm, ctx->sc));
     LAUNCH(PC_SCALAR, k_scalar_step, 1, ctx->S, step);
     return B200_OK;
@@ -409,8 +433,28 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         NC(g_nccl.GroupEnd());
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
-    Reduce R{ctx->S, ctx->partials, halo ? STEP_NONE : step};
-    if (P.sym && P.symTma && !INIT) {
+    Reduce R = mkR(ctx, halo ? STEP_NONE : step);
+    if (P.sym && P.symWin && !INIT) {
+        const size_t smem = P.symWinBytes;
+        int perSM = (int)((size_t)220 * 1024 / (smem + 1024));
+        if (perSM > 4) perSM = 4;
+        if (perSM < 1) perSM = 1;
+        if (ctx->symPerSM > 0) perSM = std::min(ctx->symPerSM, (int)((size_t)226 * 1024 / (smem + 1024)));
+        const int nChunks = (N + kChunkRows - 1) / kChunkRows;
+        const int nRuns = (nChunks + ctx->winRun - 1) / ctx->winRun;
+        int g = std::min(nRuns, perSM * ctx->numSMs);
+        if (g > kMaxGrid) g = kMaxGrid;
+        if (g < 1) g = 1;
+        prof_begin(ctx, PC_SPMV);
+        if (ctx->winNext)
+            k_spmv_sym_win<DOT, true><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, ctx->winRun, P.sRowLen, P.sUCol,
+                                                                   P.sUVal, P.sLRef, ctx->diag, x, y, R);
+        else
+            k_spmv_sym_win<DOT, false><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, ctx->winRun, P.sRowLen, P.sUCol,
+                                                                    P.sUVal, P.sLRef, ctx->diag, x, y, R);
+        prof_end(ctx, PC_SPMV);
+        ctx->launches++;
+    } else if (P.sym && P.symTma && !INIT) {
         const size_t smem = 128 + ctx->symStages * P.symStage;
         int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
         if (perSM > 8) perSM = 8;
@@ -420,15 +464,14 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         int g = std::min(nChunks, perSM * ctx->numSMs);
         if (g > kMaxGrid) g = kMaxGrid;
         prof_begin(ctx, PC_SPMV);
-        if (ctx->symStages == 2)
-            k_spmv_sym_tma<DOT, 2><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
-                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
-        else if (ctx->symStages == 3)
-            k_spmv_sym_tma<DOT, 3><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
-                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
-        else
-            k_spmv_sym_tma<DOT, 4><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol,
-                                                                P.sUVal, P.sLRef, ctx->diag, x, y, R);
+#define B200_TMA_LAUNCH(...) k_spmv_sym_tma<DOT, __VA_ARGS__><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol, \
+                                                                                   P.sUVal, P.sLRef, ctx->diag, x, y, R)
+        // exact-width instantiations (no tail loops, no idle slots) for the common narrow rows
+        if (ctx->symStages == 3) B200_TMA_LAUNCH(3, 4, 4, true);
+        else if (ctx->exactWidth && P.symWU <= 2 && P.symWL <= 2) B200_TMA_LAUNCH(2, 2, 2, false);
+        else if (ctx->exactWidth && P.symWU <= 3 && P.symWL <= 3) B200_TMA_LAUNCH(2, 3, 3, false);
+        else B200_TMA_LAUNCH(2, 4, 4, true);
+#undef B200_TMA_LAUNCH
         prof_end(ctx, PC_SPMV);
         ctx->launches++;
     } else if (P.sym) {
@@ -442,7 +485,7 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
     }
     if (halo) {
         CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
-        Reduce R2{ctx->S, ctx->partials, step};
+        Reduce R2 = mkR(ctx, step);
         auto fix = k_iface_fix<0, DOT>;
         LAUNCH(PC_IFACE, fix, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot,
                ctx->bou, ctx->recvbuf, x, y, R2);
@@ -499,14 +542,13 @@ int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* 
 // mode and, for the DIC-class modes, after every iteration (none/diagonal fuse it into k_r).
 int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
     const int N = ctx->N;
-    Scalars* S = ctx->S;
     const int gv = grid_for(ctx, (N + 1) / 2);
     if (precond == B200_PRECOND_NONE) {
-        Reduce R{S, ctx->partials, STEP_WARA};
+        Reduce R = mkR(ctx, STEP_WARA);
         auto k = k_precond_dot<false>;
         LAUNCH(PC_PRECOND_DOT, k, gv, N, (const double*)nullptr, ctx->r, (double*)nullptr, R);
     } else if (precond == B200_PRECOND_DIAGONAL) {
-        Reduce R{S, ctx->partials, STEP_WARA};
+        Reduce R = mkR(ctx, STEP_WARA);
         auto k = k_precond_dot<true>;
         LAUNCH(PC_PRECOND_DOT, k, gv, N, ctx->rD, ctx->r, ctx->w, R);
     } else {
@@ -514,7 +556,7 @@ int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
         for (int k = 0; k < C; ++k) {
             const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
             const bool last = (k == C - 1);
-            Reduce R{S, ctx->partials, (last && C == 1) ? STEP_WARA : STEP_NONE};
+            Reduce R = mkR(ctx, (last && C == 1) ? STEP_WARA : STEP_NONE);
             if (last) {
                 auto kf = k_dic_fwd<true>;
                 LAUNCH(PC_DIC_FWD, kf, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen, P.col,
@@ -527,7 +569,7 @@ int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
         }
         for (int k = C - 2; k >= 0; --k) {
             const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
-            Reduce R{S, ctx->partials, k == 0 ? STEP_WARA : STEP_NONE};
+            Reduce R = mkR(ctx, k == 0 ? STEP_WARA : STEP_NONE);
             LAUNCH(PC_DIC_BWD, k_dic_bwd, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen,
                    P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
         }
@@ -554,17 +596,17 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
     }
     RET((spmv_full<false, true>(ctx, P, ctx->p, ctx->w, nullptr, STEP_WAPA)));
     if (precond == B200_PRECOND_NONE) {
-        Reduce R{S, ctx->partials, STEP_RES_WARA};
+        Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<0>;
         LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else if (precond == B200_PRECOND_DIAGONAL) {
-        Reduce R{S, ctx->partials, STEP_RES_WARA};
+        Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<1>;
         LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else {
-        Reduce R{S, ctx->partials, STEP_RES};
+        Reduce R = mkR(ctx, STEP_RES);
         auto k = k_r<2>;
         LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
         RET(reduce_post(ctx, STEP_RES));
@@ -607,12 +649,12 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     // wA = A psi, sumA -> pA (OpenFOAM also uses pA as the normFactor temporary)
     RET((spmv_full<true, false>(ctx, P, ctx->psi, ctx->w, ctx->p, STEP_NONE)));
     {
-        Reduce R{S, ctx->partials, STEP_SUMPSI};
+        Reduce R = mkR(ctx, STEP_SUMPSI);
         LAUNCH(PC_SUM, k_sum, gv, N, ctx->psi, R);
         RET(reduce_post(ctx, STEP_SUMPSI));
     }
     {
-        Reduce R{S, ctx->partials, STEP_NORM};
+        Reduce R = mkR(ctx, STEP_NORM);
         LAUNCH(PC_NORM, k_norm_resid, gv, N, ctx->w, ctx->p, ctx->src, ctx->r, R);
         RET(reduce_post(ctx, STEP_NORM));
     }
@@ -775,12 +817,18 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
                                         " (sm_" + std::to_string(prop.major * 10 + prop.minor) +
                                         "); libb200pcg is built for sm_100a only");
     c->numSMs = prop.multiProcessorCount;
-    if (const char* e3 = getenv("B200PCG_STAGES")) c->symStages = std::max(2, std::min(4, atoi(e3)));
+    if (const char* e3 = getenv("B200PCG_STAGES")) c->symStages = std::max(2, std::min(3, atoi(e3)));
     if (const char* e4 = getenv("B200PCG_CTAS")) c->symPerSM = atoi(e4);
     if (const char* e2 = getenv("B200PCG_SPMV")) {
         c->disableSym = (std::string(e2) == "ell");
         c->disableTma = (std::string(e2) == "sym");
+        c->disableWin = (std::string(e2) != "win");
     }
+    if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
+    if (const char* e8 = getenv("B200PCG_RENUMBER"))
+        c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
+    if (const char* e5 = getenv("B200PCG_RUN")) c->winRun = std::max(1, std::min(4096, atoi(e5)));
+    if (const char* e6 = getenv("B200PCG_NEXT")) c->winNext = atoi(e6) != 0;
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->sm, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming)) != cudaSuccess ||
@@ -908,7 +956,7 @@ int b200_assemble_laplacian_device(b200_ctx* ctx, const double* g, const double*
     DevPlan& P = ctx->plans[0];
     LAUNCH(PC_ASM_FACE, k_face_coeff, grid_for(ctx, ctx->F, 16), ctx->F, g, s, d, sign, upper_out);
     LAUNCH(PC_ASM_DIAG, k_neg_sum_diag, grid_for(ctx, ctx->N, 16), ctx->N, P.sliceBase, P.rowLen,
-           P.faceOf, upper_out, diag_inout);
+           P.faceOf, P.perm, upper_out, diag_inout);
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
     prof_collect(ctx);
@@ -999,7 +1047,12 @@ int b200_amul(b200_ctx* ctx, const double* diag, const double* upper, const doub
     RET(reset_scalars(ctx, nullptr));
     RET(load_system(ctx, P, ctx->in_diag, ctx->in_upper, nullptr, ctx->in_psi));
     RET((spmv_full<false, false>(ctx, P, ctx->psi, ctx->w, nullptr, STEP_NONE)));
-    CU(cudaMemcpyAsync(Apsi, ctx->w, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    const double* out = ctx->w;
+    if (P.perm) {   // renumbered plan: back to the caller's cell order
+        LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, ctx->N), ctx->N, P.perm, ctx->w, ctx->in_src);
+        out = ctx->in_src;
+    }
+    CU(cudaMemcpyAsync(Apsi, out, nb, cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
     prof_collect(ctx);
@@ -1077,6 +1130,28 @@ const char* b200_profile_json(b200_ctx* ctx) {
     }
     s += "}";
     ctx->profJson = s;
+    return ctx->profJson.c_str();
+}
+
+const char* b200_describe(b200_ctx* ctx) {
+    if (!ctx) return "{}";
+    char buf[1536];
+    const DevPlan& P = ctx->plans[0];
+    const char* amul = !P.built ? "none"
+                       : (P.sym && P.symWin) ? (ctx->winNext ? "k_spmv_sym_win<DOT,NEXT=1>" : "k_spmv_sym_win<DOT,NEXT=0>")
+                       : (P.sym && P.symTma) ? "k_spmv_sym_tma<DOT,STAGES>"
+                       : P.sym ? "k_spmv_sym<INIT,DOT>" : "k_spmv<INIT,DOT>";
+    std::snprintf(buf, sizeof(buf),
+                  "{\"amul_natural\": \"%s\", \"amul_permuted\": \"k_spmv<INIT,DOT>\", \"symWU\": %d, \"symWL\": %d, "
+                  "\"win_smem_bytes\": %zu, \"win_run_chunks\": %d, \"chunk_rows\": %d, \"tma_stages\": %d, "
+                  "\"nranks\": %d, \"peer_allreduce\": %s, \"nCells\": %d, \"nFaces\": %d, \"nSlots\": %d, \"sms\": %d, "
+                  "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
+                  "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f}",
+                  amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
+                  ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
+                  P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
+                  P.h.sectorsUsed);
+    ctx->profJson = buf;
     return ctx->profJson.c_str();
 }
 

@@ -225,6 +225,10 @@ class Context:
         import json
         return json.loads(self.lib.b200_profile_json(self.handle).decode())
 
+    def describe(self):
+        import json
+        return json.loads(self.lib.b200_describe(self.handle).decode())
+
 
 def _ptr(x):
     if x is None:

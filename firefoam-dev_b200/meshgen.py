@@ -175,6 +175,15 @@ def decompose(system: System, cellToProc, nProcs):
                          system.source[cells].copy(), bou,
                          None if system.xstar is None else system.xstar[cells].copy())
             sub.cells, sub.faces = cells, faces
+            if system.gamma_f is not None:
+                # inputs of fvm::laplacian on the sub-mesh; the cut faces enter the sub-mesh diagonal
+                # through the processor patches' internalCoeffs (= -upper of the cut face), which
+                # solveSegregated adds to diag before the solver sees it
+                sub.gamma_f, sub.magSf = system.gamma_f[faces].copy(), system.magSf[faces].copy()
+                sub.deltaCoeffs, sub.sign = system.deltaCoeffs[faces].copy(), system.sign
+                sub.diag0 = system.diag0[cells].copy()
+                if ifFC.size:
+                    np.subtract.at(sub.diag0, ifFC, system.upper[ifGF])
             out.append(sub)
     finally:
         L.b200mesh_decompose_free(h)

@@ -184,6 +184,9 @@ int b200_debug_force_iterations(b200_ctx* ctx, int32_t n);
  * retrievable as a JSON string (B200PCG_PROFILE=1 in the adapter) */
 int b200_profile_enable(b200_ctx* ctx, int on);
 const char* b200_profile_json(b200_ctx* ctx);
+/* which kernel variants / launch geometry the context selected for the current mesh, as a JSON
+ * string (bench "roofline.kernel"; valid until the next call on this context) */
+const char* b200_describe(b200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,8 @@ class PlanView:
     NAMES = ["perm", "iperm", "colourStart", "sliceBase", "rowLen", "col", "faceOf", "nbrRank",
              "patchStart", "slotRow", "bRow", "bStart", "bSlot"]
 
-    def __init__(self, ordering, addr):
+    def __init__(self, ordering, addr, renumber=0):
+        """renumber: 0 off (the default of the host-only debug ABI), -1 auto, 1 force RCM."""
         L = _lib.load_pcg()
         ifs = (_lib.Iface * max(1, len(addr.interfaces)))()
         # b200_dbg_iface = {nbrRank, nFaces, faceCells} -- same leading layout, pack explicitly
@@ -25,9 +26,12 @@ class PlanView:
         for k, itf in enumerate(addr.interfaces):
             dif[k].nbrRank, dif[k].nFaces = itf.neighbProcNo, itf.faceCells.size
             dif[k].faceCells = itf.faceCells.ctypes.data
-        h = L.b200_debug_plan_build(ordering, addr.nCells, addr.nFaces, addr.lowerAddr.ctypes.data,
-                                    addr.upperAddr.ctypes.data, len(addr.interfaces),
-                                    C.cast(dif, C.c_void_p))
+        L.b200_debug_plan_build2.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_int32, C.c_void_p]
+        L.b200_debug_plan_build2.restype = C.c_void_p
+        h = L.b200_debug_plan_build2(ordering, renumber, addr.nCells, addr.nFaces,
+                                     addr.lowerAddr.ctypes.data, addr.upperAddr.ctypes.data,
+                                     len(addr.interfaces), C.cast(dif, C.c_void_p))
         if not h:
             raise ValueError(L.b200_debug_plan_error().decode())
         try:
@@ -42,6 +46,11 @@ class PlanView:
                 n = L.b200_debug_plan_get(h, ("sym." + nm).encode(), C.byref(ptr), C.byref(eb))
                 self.sym[nm] = (np.empty(0, dtype=dt) if n <= 0 else
                                 np.frombuffer((C.c_char * (n * eb.value)).from_address(ptr.value), dtype=dt).copy())
+            L.b200_debug_plan_renumbered.argtypes = [C.c_void_p]
+            L.b200_debug_plan_span.argtypes = [C.c_void_p, C.c_int]
+            L.b200_debug_plan_span.restype = C.c_double
+            self.renumbered = bool(L.b200_debug_plan_renumbered(h))
+            self.spanNatural, self.spanUsed = L.b200_debug_plan_span(h, 0), L.b200_debug_plan_span(h, 1)
             self.nColours = L.b200_debug_plan_ncolours(h)
             self.nEntries = L.b200_debug_plan_nentries(h)
             for nm in self.NAMES:

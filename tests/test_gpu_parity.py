@@ -55,6 +55,37 @@ def test_amul_bit_exact(ctx, name, s):
     assert np.array_equal(y, orc.amul(s, x)[0])
 
 
+AMUL_VARIANTS = [{"B200PCG_SPMV": "ell"}, {"B200PCG_SPMV": "sym"}, {"B200PCG_SPMV": "tma"},
+                 {"B200PCG_SPMV": "tma", "B200PCG_EXACT": "0"}, {"B200PCG_SPMV": "tma", "B200PCG_STAGES": "3"},
+                 {"B200PCG_SPMV": "win", "B200PCG_RUN": "1"},
+                 {"B200PCG_SPMV": "win", "B200PCG_RUN": "3", "B200PCG_NEXT": "0"},
+                 {"B200PCG_SPMV": "win", "B200PCG_RUN": "3", "B200PCG_NEXT": "1", "B200PCG_CTAS": "1"},
+                 {"B200PCG_SPMV": "win", "B200PCG_RUN": "8"},
+                 {"B200PCG_SPMV": "win", "B200PCG_RUN": "64", "B200PCG_CTAS": "2"}]
+
+
+@pytest.mark.parametrize("env", AMUL_VARIANTS, ids=lambda e: ",".join(f"{k[8:]}={v}" for k, v in e.items()))
+def test_amul_variants_bit_exact(env):
+    """Every Amul kernel variant (full-row ELL, symmetric direct, bulk-copy staged, shared-memory
+    window with different run lengths / grid sizes) against the oracle, on systems that span many
+    256-row chunks and runs: banded hex (window hits), a mesh whose last chunk is partial, and a
+    random graph (almost every neighbour outside the window).  Also the solve on top of it."""
+    c = _ctx_with_env(env)
+    try:
+        for s in (mg.hex_block(64, 40, 33), mg.hex_block(37, 23, 11), random_ldu(20011, 6.0, seed=3),
+                  mg.hex_block(5, 3, 2)):
+            c.set_addressing(s.addr)
+            x = np.random.default_rng(5).standard_normal(s.addr.nCells)
+            assert np.array_equal(c.amul(s.matrix, s.bou, x), orc.amul(s, x)[0])
+        s = mg.hex_block(64, 40, 33)
+        psi, perf = solve_gpu(c, s, "diagonal", maxIter=3000)
+        ref, pref = solve_cpu(s, "diagonal", maxIter=3000)
+        assert perf.nIterations == pref.nIterations
+        assert relmax(psi, ref) < 1e-12
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("sign", [-1.0, 1.0])
 def test_assembly_bit_exact(ctx, sign):
     s = mg.hex_block(20, 11, 9)
@@ -314,3 +345,46 @@ def test_polyhedral_config5_small(ctx):
     xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
     assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
     assert pg.nColours >= 4
+
+
+def _ctx_with_env(env):
+    from firefoam_dev_b200 import Context
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Context()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_rcm_renumbering_does_not_change_results(mode):
+    """Rows renumbered by reverse Cuthill-McKee (forced) or not at all: assembly, Amul and flux stay
+    bit-identical to the oracle, PCG + diagonal keeps the oracle's iteration counts, DIC-exact is
+    unaffected (never renumbered), multicolour DIC still converges to the same solution."""
+    c = _ctx_with_env({"B200PCG_RENUMBER": mode})
+    try:
+        for s in (mg.bcc_poly(9, 8, 10), mg.hex_block(24, 20, 16), random_ldu(5001, 6.0, seed=7)):
+            a = s.addr
+            c.set_addressing(a)
+            assert c.describe()["renumbered_rcm"] == (mode == "1")
+            if s.gamma_f is not None:
+                up, dg = c.assemble_laplacian(s.gamma_f, s.magSf, s.deltaCoeffs, -1.0, s.diag0)
+                up_ref, dg_ref = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf,
+                                                        s.deltaCoeffs, -1.0, s.diag0)
+                assert np.array_equal(up, up_ref) and np.array_equal(dg, dg_ref)
+            x = np.random.default_rng(5).standard_normal(a.nCells)
+            assert np.array_equal(c.amul(s.matrix, [], x), orc.amul(s, x)[0])
+            for pre, exact in (("diagonal", False), ("DIC", True)):
+                xg, pg = solve_gpu(c, s, pre, tol=1e-7, maxIter=5000, exact=exact)
+                xc, pc = solve_cpu(s, pre, tol=1e-7, maxIter=5000)
+                assert pg.nIterations == pc.nIterations and relmax(xg, xc) < 1e-12
+            xg, pg = solve_gpu(c, s, "DIC", tol=1e-11, maxIter=5000)
+            xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
+            assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
+    finally:
+        c.close()

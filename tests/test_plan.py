@@ -84,6 +84,42 @@ def test_spmv_emulation_permuted(name, s):
         np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-15)
 
 
+def test_rcm_renumbering_decision():
+    """Auto mode renumbers a cache-hostile numbering (block-shuffled polyhedra) and leaves banded
+    ones (lexicographic hex) alone; Levels (DIC-exact) is never renumbered."""
+    poly = mg.bcc_poly(12, 12, 14)
+    P = PlanView(NAT, poly.addr, renumber=-1)
+    assert P.renumbered and P.spanUsed < 0.5 * P.spanNatural
+    assert np.array_equal(np.sort(P.perm), np.arange(poly.addr.nCells))
+    assert not P.symValid
+    assert PlanView(MC, poly.addr, renumber=-1).renumbered
+    assert not PlanView(LEV, poly.addr, renumber=1).renumbered
+    hexm = mg.hex_block(24, 20, 16)
+    P = PlanView(NAT, hexm.addr, renumber=-1)
+    assert not P.renumbered and P.perm.size == 0 and P.symValid
+
+
+@pytest.mark.parametrize("name,s", list(systems()) + [("poly", mg.bcc_poly(5, 4, 6))])
+def test_renumbered_natural_plan_is_bit_exact(name, s):
+    """Rows in RCM order, but every row still sums its faces in ascending natural face order: Amul
+    through the renumbered plan is bit-identical to the oracle's face loop."""
+    a = s.addr
+    P = PlanView(NAT, a, renumber=1)
+    assert P.renumbered
+    assert np.array_equal(np.sort(P.perm), np.arange(a.nCells))
+    assert np.array_equal(P.iperm[P.perm], np.arange(a.nCells))
+    for r in range(a.nCells):
+        f = [P.faceOf[P.entry(r, j)] for j in range(P.nTotal[r])]
+        assert f == sorted(f) and P.nLower[r] == 0
+    x = np.random.default_rng(11).standard_normal(a.nCells)
+    y = P.to_natural(P.spmv(P.to_internal(s.diag), P.values(s.upper), P.to_internal(x)))
+    assert np.array_equal(y, orc.amul(s, x)[0])
+    # multicolour on top of the RCM base order: still a proper colouring
+    Q = PlanView(MC, a, renumber=1)
+    colour = np.searchsorted(Q.colourStart, np.arange(a.nCells), side="right") - 1
+    assert np.all(colour[Q.iperm[a.lowerAddr]] != colour[Q.iperm[a.upperAddr]])
+
+
 @pytest.mark.parametrize("name,s", list(systems()))
 def test_level_schedule_is_exact_dic(name, s):
     """DIC-exact: level-major order + OpenFOAM's per-row operation order == DICPreconditioner."""
