@@ -13,6 +13,8 @@
 
 #include <cstdlib>
 #include <cstdint>
+#include <cstdio>
+#include <string>
 
 // * * * * * * * * * * * * * * Static Data Members * * * * * * * * * * * * * //
 
@@ -227,6 +229,13 @@ Foam::solverPerformance Foam::B200PCG::solve
             << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
     }
 
+    // --- B200PCG_DUMP=<dir>: keep the initial guess so that the system can be written out after the
+    //     solve together with what the solver reported (include/b200pcg.h b200_dump; replayed with
+    //     b200replay / firefoam-dev_b200/replay.py)
+    const char* dumpDir = std::getenv("B200PCG_DUMP");
+    scalarField psi0;
+    if (dumpDir) psi0 = psi;
+
     b200_perf perf;
 
     const int rc = b200_solve
@@ -245,6 +254,43 @@ Foam::solverPerformance Foam::B200PCG::solve
     {
         FatalErrorInFunction
             << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    if (dumpDir)
+    {
+        static int solveIndex = 0;
+        b200_dump d;
+        d.fieldName = fieldName_.c_str();
+        d.rank = Pstream::parRun() ? Pstream::myProcNo() : 0;
+        d.nranks = Pstream::parRun() ? Pstream::nProcs() : 1;
+        d.nCells = addr.size();
+        d.nFaces = addr.lowerAddr().size();
+        d.lowerAddr = addr.lowerAddr().begin();
+        d.upperAddr = addr.upperAddr().begin();
+        d.diag = matrix_.diag().begin();
+        d.upper = matrix_.upper().begin();
+        d.source = source.begin();
+        d.psi0 = psi0.begin();
+        d.psiSolution = psi.begin();
+        d.nIfaces = ifaces.size();
+        d.ifaces = ifaces.begin();
+        d.ifaceBouCoeffs = bou.begin();
+        d.controls = ctl;
+        d.havePerf = 1;
+        d.perf = perf;
+        const std::string name(preconditionerName + typeName);
+        d.solverName = name.c_str();
+        d.solveIndex = solveIndex;
+        d.time = matrix_.mesh().thisDb().time().value();
+
+        char file[64];
+        std::snprintf(file, sizeof(file), "_%06d_p%d.b200sys", solveIndex++, d.rank);
+        const std::string path(std::string(dumpDir) + "/" + fieldName_ + file);
+        if (b200_dump_write(path.c_str(), &d) != B200_OK)
+        {
+            WarningInFunction
+                << "B200PCG: " << b200_dump_last_error() << endl;
+        }
     }
 
     solverPerf.initialResidual() = perf.initialResidual;

@@ -23,9 +23,12 @@ PRECOND = {"none": 0, "diagonal": 1, "DIC": 2, "DIC-exact": 3}
 ABI_SYMBOLS = [
     "b200_ctx_create", "b200_get_unique_id", "b200_ctx_destroy", "b200_last_error",
     "b200_abi_version", "b200_device_count", "b200_set_addressing", "b200_assemble_laplacian",
-    "b200_assemble_laplacian_device", "b200_solve", "b200_solve_device", "b200_amul", "b200_flux",
+    "b200_assemble_laplacian_device", "b200_set_boundary_faces", "b200_assemble_p_rgh",
+    "b200_assemble_p_rgh_device", "b200_solve", "b200_solve_device", "b200_amul", "b200_flux",
     "b200_host_alloc", "b200_host_free", "b200_launch_count", "b200_debug_force_iterations",
     "b200_profile_enable", "b200_profile_json", "b200_describe",
+    "b200_dump_write", "b200_dump_read", "b200_dump_get", "b200_dump_header_json", "b200_dump_free",
+    "b200_dump_last_error",
 ]
 
 
@@ -50,6 +53,29 @@ class Perf(C.Structure):
                 ("normFactor", C.c_double), ("nIterations", C.c_int32), ("converged", C.c_int32),
                 ("singular", C.c_int32), ("nColours", C.c_int32), ("solveMs", C.c_double),
                 ("setupMs", C.c_double), ("h2dMs", C.c_double), ("d2hMs", C.c_double)]
+
+
+class PrghTerms(C.Structure):
+    """b200_prgh_terms (include/b200pcg.h)"""
+    _fields_ = [("rDeltaT", C.c_double), ("V", C.c_void_p), ("psi", C.c_void_p), ("psi0", C.c_void_p),
+                ("p0", C.c_void_p), ("nExplicit", C.c_int32), ("pad0", C.c_int32),
+                ("explicitFields", C.c_void_p), ("phi", C.c_void_p), ("divSign", C.c_double),
+                ("gamma_f", C.c_void_p), ("magSf", C.c_void_p), ("deltaCoeffs", C.c_void_p),
+                ("lapSign", C.c_double), ("Su", C.c_void_p), ("nB", C.c_int32), ("pad1", C.c_int32),
+                ("bCells", C.c_void_p), ("bPhi", C.c_void_p), ("bInternal", C.c_void_p),
+                ("bBoundary", C.c_void_p)]
+
+
+class Dump(C.Structure):
+    """b200_dump (include/b200pcg.h)"""
+    _fields_ = [("fieldName", C.c_char_p), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("nCells", C.c_int32), ("nFaces", C.c_int32),
+                ("lowerAddr", C.c_void_p), ("upperAddr", C.c_void_p), ("diag", C.c_void_p),
+                ("upper", C.c_void_p), ("source", C.c_void_p), ("psi0", C.c_void_p),
+                ("psiSolution", C.c_void_p), ("nIfaces", C.c_int32), ("ifaces", C.POINTER(Iface)),
+                ("ifaceBouCoeffs", C.POINTER(C.c_void_p)), ("controls", Controls),
+                ("havePerf", C.c_int32), ("perf", Perf), ("solverName", C.c_char_p),
+                ("solveIndex", C.c_int32), ("time", C.c_double)]
 
 
 def build(verbose=False):
@@ -86,6 +112,9 @@ def load_pcg():
     L.b200_set_addressing.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
     L.b200_assemble_laplacian.argtypes = [vp, f64p, f64p, f64p, C.c_double, f64p, f64p]
     L.b200_assemble_laplacian_device.argtypes = [vp, f64p, f64p, f64p, C.c_double, f64p, f64p]
+    L.b200_set_boundary_faces.argtypes = [vp, C.c_int32, vp]
+    L.b200_assemble_p_rgh.argtypes = [vp, vp, f64p, f64p, f64p]
+    L.b200_assemble_p_rgh_device.argtypes = [vp, vp, f64p, f64p, f64p]
     L.b200_solve.argtypes = [vp, f64p, f64p, vp, f64p, f64p, C.POINTER(Controls), C.POINTER(Perf)]
     L.b200_solve_device.argtypes = L.b200_solve.argtypes
     L.b200_amul.argtypes = [vp, f64p, f64p, vp, f64p, f64p]
@@ -101,6 +130,15 @@ def load_pcg():
     L.b200_profile_json.restype = C.c_char_p
     L.b200_describe.argtypes = [vp]
     L.b200_describe.restype = C.c_char_p
+    L.b200_dump_write.argtypes = [C.c_char_p, C.POINTER(Dump)]
+    L.b200_dump_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200_dump_get.argtypes = [vp]
+    L.b200_dump_get.restype = C.POINTER(Dump)
+    L.b200_dump_header_json.argtypes = [vp]
+    L.b200_dump_header_json.restype = C.c_char_p
+    L.b200_dump_free.argtypes = [vp]
+    L.b200_dump_free.restype = None
+    L.b200_dump_last_error.restype = C.c_char_p
     # host-only plan inspection (plan_debug.cpp)
     L.b200_debug_plan_build.argtypes = [C.c_int, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
     L.b200_debug_plan_build.restype = vp

@@ -16,6 +16,7 @@
 // lduMatrixSolver.C, DICPreconditioner.C, diagonalPreconditioner.C, gaussLaplacianScheme.C).
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace b200 {
@@ -1148,6 +1149,320 @@ k_neg_sum_diag(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __r
         if (j < n) d = __dadd_rn(d, -__ldg(&upper[faceOf[base + 32 * (int64_t)j]]));
         diag[cell] = __dadd_rn(d0, d);
     }
+}
+
+// ---- whole p_rghEqn: ddt + explicit terms + fvc::div + laplacian diagonal + boundary fold ------
+// (reference solver/pEqn.H:26-37, solver/phrghEqn.H:43-46; OF-dev EulerDdtScheme.C,
+// fvMatrix.C, surfaceIntegrate.C, lduMatrixOperations.C).  One row per thread: the face -> cell sums
+// of fvc::div and negSumDiag are gathers over the row's faces in ascending face order (== the order
+// in which OpenFOAM's face loops update the cell), the patch sums are gathers over the cell's
+// boundary faces in patch order (CSR built by b200_set_boundary_faces): sorted segments, no atomics.
+constexpr int kMaxExplicit = 8;
+struct PrghDev {
+    double rDeltaT, divSign;
+    const double *V, *psi, *psi0, *p0, *phi, *Su, *bPhi, *bInt, *bBou;
+    const double* ex[kMaxExplicit];
+    int nExplicit;
+    const int *bfStart, *bfOrder;   // [N+1], [nB]: boundary faces of each cell, patch order
+};
+
+__global__ void __launch_bounds__(kBlock)
+k_prgh_cell(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+            const int* __restrict__ faceOf, const int* __restrict__ perm, const int* __restrict__ lowerAddr,
+            const double* __restrict__ upper, PrghDev t, double* __restrict__ diag, double* __restrict__ source) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+        const int c = perm ? perm[r] : r;
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int n = (int)(rowLen[r] >> 16);
+        const double V = t.V[c];
+        double dsum = 0.0, ivf = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const int f = faceOf[base + 32 * (int64_t)j];
+            dsum = __dadd_rn(dsum, -__ldg(&upper[f]));
+            if (t.phi) {
+                const double ph = __ldg(&t.phi[f]);
+                ivf = __dadd_rn(ivf, (__ldg(&lowerAddr[f]) == c) ? ph : -ph);   // owner += phi, neighbour -= phi
+            }
+        }
+        const int b0 = t.bfStart ? t.bfStart[c] : 0, b1 = t.bfStart ? t.bfStart[c + 1] : 0;
+        double d = 0.0, s = 0.0;
+        if (t.psi) {
+            d = __dmul_rn(__dmul_rn(t.rDeltaT, t.psi[c]), V);
+            s = __dmul_rn(__dmul_rn(__dmul_rn(t.rDeltaT, t.psi0[c]), t.p0[c]), V);
+        }
+        for (int k = 0; k < t.nExplicit; ++k) s = __dadd_rn(s, -__dmul_rn(V, t.ex[k][c]));
+        if (t.phi) {
+            if (t.bPhi)
+                for (int b = b0; b < b1; ++b) ivf = __dadd_rn(ivf, t.bPhi[t.bfOrder[b]]);
+            ivf = __ddiv_rn(ivf, V);
+            const double q = __dmul_rn(V, ivf);
+            s = __dadd_rn(s, t.divSign < 0 ? -q : q);
+        }
+        d = __dadd_rn(d, dsum);
+        if (t.Su) s = __dadd_rn(s, __dmul_rn(V, t.Su[c]));
+        if (t.bInt)
+            for (int b = b0; b < b1; ++b) d = __dadd_rn(d, t.bInt[t.bfOrder[b]]);
+        if (t.bBou)
+            for (int b = b0; b < b1; ++b) s = __dadd_rn(s, t.bBou[t.bfOrder[b]]);
+        diag[c] = d;
+        source[c] = s;
+    }
+}
+
+// ---- whole-solve kernel for small systems (one thread-block cluster) ---------------------------
+// The reference's own cases are small (cases/steckler: 9 000 cells): there the multi-kernel loop is
+// pure launch latency (~50 us per iteration = 3 launches + device-side scalar steps), no faster
+// than one host core.  k_pcg_small runs the WHOLE of PCG::solve (OF-dev PCG.C) --
+// initial residual, normFactor, preconditioner set-up, the iteration loop and its convergence
+// test -- in ONE launch of one thread-block cluster (8 or 16 CTAs x 1024 threads, co-scheduled on
+// one GPC).  Phases are separated by hardware cluster barriers (~0.2 us, release/acquire at
+// cluster scope) instead of kernel boundaries; every CTA forms the global sums from the per-CTA
+// partials in the same fixed order and advances its own copy of the CG scalars, so no broadcast
+// is needed and every CTA takes the same branch.  Vectors and matrix stay L2-resident.
+// Same row-sum order, same element-wise arithmetic and the same scalar_step() as the large path.
+namespace cgx = cooperative_groups;
+constexpr int kSmallBlock = 1024;
+constexpr int kSmallMaxCtas = 16;
+
+struct SmallArgs {
+    int N, precond /* B200_PRECOND_* */, nColours;
+    const int* colourStart;        // [nColours+1] (device)
+    const int64_t* sliceBase;
+    const uint32_t* rowLen;
+    const int* col;
+    const double* val;
+    const double* diag;
+    const double* src;
+    double *psi, *rA, *pA, *wA, *rD;
+    Scalars* S;
+    double* partials;              // [2][kSmallMaxCtas][kNSums]
+};
+
+struct SmallCtx {
+    cgx::cluster_group cluster;
+    Scalars* sS;                   // this CTA's copy (shared memory)
+    double* partials;
+    double (*sh)[kSmallBlock / 32];
+    unsigned nred;
+    int nCtas, cta, gtid, nThreads;
+};
+
+// cluster-wide sum of NV per-thread values + scalar step; every thread of the cluster calls it
+template <int NV>
+__device__ __forceinline__ void small_reduce(SmallCtx& c, double (&v)[NV], int step) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) c.sh[i][w] = s;
+    }
+    __syncthreads();
+    double* buf = c.partials + (size_t)(c.nred & 1u) * kSmallMaxCtas * kNSums;
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = c.sh[i][lane];      // kSmallBlock / 32 == 32 warps
+            s = warp_sum(s);
+            if (lane == 0) buf[c.cta * kNSums + i] = s;
+        }
+    }
+    c.cluster.sync();                      // partials of every CTA visible (release/acquire)
+    if (threadIdx.x == 0) {
+        double g[kNSums];
+#pragma unroll
+        for (int i = 0; i < kNSums; ++i) g[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double t = 0.0;
+            for (int b = 0; b < c.nCtas; ++b) t = __dadd_rn(t, __ldcg(&buf[b * kNSums + i]));
+            g[i] = t;
+        }
+        scalar_step(step, c.sS, g);
+    }
+    c.nred++;
+    __syncthreads();
+}
+
+// (x is rewritten between phases of the same launch: plain coherent loads, never the read-only path)
+__device__ __forceinline__ double small_row_amul(const SmallArgs& a, int r, const double* x,
+                                                 double xr, double d, double* sa) {
+    const int64_t base = a.sliceBase[r >> 5] + (r & 31);
+    const int n = (int)(a.rowLen[r] >> 16);
+    double acc = __dmul_rn(d, xr);
+    double s = d;
+    for (int j = 0; j < n; ++j) {
+        const int64_t e = base + 32 * (int64_t)j;
+        const double v = a.val[e];
+        acc = __dadd_rn(acc, __dmul_rn(v, x[a.col[e]]));
+        s = __dadd_rn(s, v);
+    }
+    if (sa) *sa = s;
+    return acc;
+}
+
+// DIC-class apply (rank-local), colour by colour with a cluster barrier between colours; returns
+// this thread's share of (wA, rA)
+__device__ __forceinline__ double small_dic_apply(SmallCtx& c, const SmallArgs& a) {
+    double dot = 0.0;
+    const int C = a.nColours;
+    for (int k = 0; k < C; ++k) {
+        for (int r = a.colourStart[k] + c.gtid; r < a.colourStart[k + 1]; r += c.nThreads) {
+            const int64_t base = a.sliceBase[r >> 5] + (r & 31);
+            const int nLower = (int)(a.rowLen[r] & 0xffffu);
+            const double d = a.rD[r], rr = a.rA[r];
+            double w = __dmul_rn(d, rr);
+            for (int j = 0; j < nLower; ++j) {
+                const int64_t e = base + 32 * (int64_t)j;
+                w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, a.val[e]), a.wA[a.col[e]]));
+            }
+            a.wA[r] = w;
+            if (k == C - 1) dot = __dadd_rn(dot, __dmul_rn(w, rr));
+        }
+        if (k + 1 < C) c.cluster.sync();
+    }
+    for (int k = C - 2; k >= 0; --k) {
+        c.cluster.sync();
+        for (int r = a.colourStart[k] + c.gtid; r < a.colourStart[k + 1]; r += c.nThreads) {
+            const int64_t base = a.sliceBase[r >> 5] + (r & 31);
+            const uint32_t len = a.rowLen[r];
+            const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+            const double d = a.rD[r];
+            double w = a.wA[r];
+            for (int j = nTotal - 1; j >= nLower; --j) {
+                const int64_t e = base + 32 * (int64_t)j;
+                w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, a.val[e]), a.wA[a.col[e]]));
+            }
+            a.wA[r] = w;
+            dot = __dadd_rn(dot, __dmul_rn(w, a.rA[r]));
+        }
+    }
+    return dot;
+}
+
+__global__ void __launch_bounds__(kSmallBlock, 1) k_pcg_small(SmallArgs a) {
+    __shared__ Scalars sS;
+    __shared__ double sh[kNSums][kSmallBlock / 32];
+    SmallCtx c{cgx::this_cluster(), &sS, a.partials, sh, 0u, 0, 0, 0, 0};
+    c.nCtas = (int)c.cluster.num_blocks();
+    c.cta = (int)c.cluster.block_rank();
+    c.nThreads = c.nCtas * kSmallBlock;
+    c.gtid = c.cta * kSmallBlock + (int)threadIdx.x;
+    if (threadIdx.x == 0) sS = *a.S;          // controls written by the host
+    __syncthreads();
+    const int N = a.N, T = c.nThreads, t0 = c.gtid;
+    const bool dic = a.precond >= 2, diagp = a.precond == 1;
+
+    // wA = A psi, sumA -> pA (lduMatrix::Amul + sumA);  gSum(psi)
+    {
+        double s[1] = {0.0};
+        for (int r = t0; r < N; r += T) {
+            const double xr = a.psi[r];
+            double sa;
+            a.wA[r] = small_row_amul(a, r, a.psi, xr, a.diag[r], &sa);
+            a.pA[r] = sa;
+            s[0] = __dadd_rn(s[0], xr);
+        }
+        small_reduce<1>(c, s, STEP_SUMPSI);
+    }
+    // rA = source - wA; normFactor; initial residual
+    {
+        double s[2] = {0.0, 0.0};
+        const double xRef = sS.xRef;
+        for (int r = t0; r < N; r += T) {
+            const double w = a.wA[r], b = a.src[r];
+            const double t = __dmul_rn(a.pA[r], xRef);
+            s[0] = __dadd_rn(s[0], __dadd_rn(fabs(__dadd_rn(w, -t)), fabs(__dadd_rn(b, -t))));
+            const double rr = __dadd_rn(b, -w);
+            s[1] = __dadd_rn(s[1], fabs(rr));
+            a.rA[r] = rr;
+        }
+        small_reduce<2>(c, s, STEP_NORM);
+    }
+    if (!sS.done) {
+        // preconditioner set-up
+        if (diagp) {
+            for (int r = t0; r < N; r += T) a.rD[r] = __ddiv_rn(1.0, a.diag[r]);
+        } else if (dic) {
+            for (int k = 0; k < a.nColours; ++k) {      // calcReciprocalD, colour by colour
+                for (int r = a.colourStart[k] + t0; r < a.colourStart[k + 1]; r += T) {
+                    const int64_t base = a.sliceBase[r >> 5] + (r & 31);
+                    const int nLower = (int)(a.rowLen[r] & 0xffffu);
+                    double d = a.diag[r];
+                    for (int j = 0; j < nLower; ++j) {
+                        const int64_t e = base + 32 * (int64_t)j;
+                        const double v = a.val[e];
+                        d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(v, v), a.rD[a.col[e]]));
+                    }
+                    a.rD[r] = d;
+                }
+                c.cluster.sync();
+            }
+            for (int r = t0; r < N; r += T) a.rD[r] = __ddiv_rn(1.0, a.rD[r]);
+            c.cluster.sync();
+        }
+        // first wArA = (precondition(rA), rA)
+        {
+            double s[1] = {0.0};
+            if (dic) s[0] = small_dic_apply(c, a);
+            else
+                for (int r = t0; r < N; r += T) {
+                    const double rr = a.rA[r];
+                    const double w = diagp ? __dmul_rn(a.rD[r], rr) : rr;
+                    s[0] = __dadd_rn(s[0], __dmul_rn(w, rr));
+                }
+            small_reduce<1>(c, s, STEP_WARA);
+        }
+    }
+    // PCG loop (regrouped like the large path: psi update deferred into the next p update)
+    while (!sS.done) {
+        {
+            const bool first = (sS.nIter == 0);
+            const double beta = sS.beta, alpha = sS.alpha;
+            for (int r = t0; r < N; r += T) {
+                double p = dic ? a.wA[r] : (diagp ? __dmul_rn(a.rD[r], a.rA[r]) : a.rA[r]);
+                if (!first) {
+                    const double po = a.pA[r];
+                    a.psi[r] = __dadd_rn(a.psi[r], __dmul_rn(alpha, po));
+                    p = __dadd_rn(p, __dmul_rn(beta, po));
+                }
+                a.pA[r] = p;
+            }
+        }
+        c.cluster.sync();                    // pA complete before anyone gathers it
+        {
+            double s[1] = {0.0};
+            for (int r = t0; r < N; r += T) {
+                const double xr = a.pA[r];
+                const double y = small_row_amul(a, r, a.pA, xr, a.diag[r], nullptr);
+                a.wA[r] = y;
+                s[0] = __dadd_rn(s[0], __dmul_rn(y, xr));
+            }
+            small_reduce<1>(c, s, STEP_WAPA);
+        }
+        if (sS.done) break;                  // singular
+        {
+            const double alpha = sS.alpha;
+            double s[2] = {0.0, 0.0};
+            for (int r = t0; r < N; r += T) {
+                const double rr = __dadd_rn(a.rA[r], -__dmul_rn(alpha, a.wA[r]));
+                a.rA[r] = rr;
+                s[0] = __dadd_rn(s[0], fabs(rr));
+                if (diagp) s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(a.rD[r], rr), rr));
+                else if (!dic) s[1] = __dadd_rn(s[1], __dmul_rn(rr, rr));
+            }
+            small_reduce<2>(c, s, dic ? STEP_RES : STEP_RES_WARA);
+        }
+        if (dic && !sS.done) {
+            double s[1];
+            s[0] = small_dic_apply(c, a);
+            small_reduce<1>(c, s, STEP_WARA);
+        }
+    }
+    if (sS.pendingPsi) {
+        const double alpha = sS.alpha;
+        for (int r = t0; r < N; r += T) a.psi[r] = __dadd_rn(a.psi[r], __dmul_rn(alpha, a.pA[r]));
+    }
+    if (c.cta == 0 && threadIdx.x == 0) *a.S = sS;
 }
 
 // ---- fvMatrix::flux() internal faces (OF-dev fvMatrix.C) --------------------

@@ -77,13 +77,13 @@ NcclApi g_nccl;
 enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_PUPDATE, PC_UPDATE, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
-    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_COUNT
+    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
     "norm_resid", "recip", "precond_dot", "p_update", "update_psi_r", "dic_calc_rd", "dic_fwd",
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
-    "r_update_dots", "psi_final"};
+    "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells"};
 
 struct DevPlan {
     bool built = false;
@@ -95,6 +95,7 @@ struct DevPlan {
     double* val = nullptr;
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
+    int* colourStart = nullptr;   // device copy of h.colourStart (k_pcg_small)
     int nSlots = 0;
     // symmetric single-read layout (SymPlan)
     bool sym = false;
@@ -140,6 +141,12 @@ struct b200_ctx {
     // staging for the host entry points (natural order)
     double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
            *in_bou = nullptr, *in_f1 = nullptr, *in_f2 = nullptr, *in_f3 = nullptr;
+    // boundary faces (b200_set_boundary_faces): CSR cell -> boundary faces in patch order
+    int32_t nB = 0;
+    std::vector<int32_t> hbCells;
+    int *bfStart = nullptr, *bfOrder = nullptr;
+    double* scratch = nullptr;      // staging arena of the host entry point b200_assemble_p_rgh
+    size_t scratchElems = 0;
     // one-shot peer-memory all-reduce (k_allreduce_step)
     bool p2pReduce = false;
     PeerBuf* peerLocal = nullptr;
@@ -163,6 +170,10 @@ struct b200_ctx {
     int winRun = 8;
     bool winNext = true;
     bool disableWin = true;
+    // single-launch cluster kernel for small systems (k_pcg_small): up to this many cells
+    // (B200PCG_SMALL_N, 0 disables), cluster size 8 or 16 (B200PCG_SMALL_CTAS)
+    int smallN = 65536, smallCtas = 8;
+    bool usedSmall = false;
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
@@ -273,7 +284,7 @@ inline int grid_for(const b200_ctx* c, int64_t items, int perSM = 8) {
 void free_plan(DevPlan& P) {
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
-    dev_free(P.bStart); dev_free(P.bSlot);
+    dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart);
     dev_free(P.sUCol); dev_free(P.sUFace);
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen);
     P.sym = false;
@@ -288,6 +299,8 @@ void free_mesh(b200_ctx* c) {
     dev_free(c->w); dev_free(c->rD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
     dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
     dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3);
+    dev_free(c->bfStart); dev_free(c->bfOrder); dev_free(c->scratch);
+    c->nB = 0; c->hbCells.clear(); c->scratchElems = 0;
     c->haveMesh = false;
     c->hl.clear(); c->hu.clear(); c->hif.clear();
 }
@@ -313,6 +326,7 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     RET(upload(ctx, &P.bRow, P.h.bRow));
     RET(upload(ctx, &P.bStart, P.h.bStart));
     RET(upload(ctx, &P.bSlot, P.h.bSlot));
+    RET(upload(ctx, &P.colourStart, P.h.colourStart));
     P.nSlots = (int)P.h.slotRow.size();
     // permuted (colour-major) orders put a row's earlier neighbours hundreds of MB upstream: the
     // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
@@ -631,6 +645,29 @@ Ordering ordering_for(int precond) {
     return Ordering::Natural;
 }
 
+// fill b200_perf from the status block read back after the loop
+int finish_solve(b200_ctx* ctx, DevPlan& P, b200_perf* perf) {
+    const Scalars& h = *ctx->hS;
+    if (perf) {
+        std::memset(perf, 0, sizeof(*perf));
+        perf->initialResidual = h.initRes;
+        perf->finalResidual = h.finalRes;
+        perf->normFactor = h.normFactor;
+        perf->nIterations = h.nIter;
+        perf->converged = h.converged;
+        perf->singular = h.singular;
+        perf->nColours = P.h.nColours;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        perf->setupMs = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+        perf->solveMs = ms;
+    }
+    if (h.nonfinite == 2) return fail(ctx, B200_ENCCL, "peer-memory all-reduce timed out (a rank never arrived)");
+    if (h.nonfinite) return fail(ctx, B200_ENONFINITE, "non-finite residual in PCG");
+    return B200_OK;
+}
+
 // The solve proper; all pointers are device pointers in natural order; bou already in ctx->bou.
 int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_src,
                double* dn_psi, const b200_controls* ctl, b200_perf* perf) {
@@ -646,6 +683,42 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     CU(cudaEventRecord(ctx->ev[0], ctx->sc));
     RET(reset_scalars(ctx, ctl));
     RET(load_system(ctx, P, dn_diag, dn_upper, dn_src, dn_psi));
+    ctx->usedSmall = false;
+    if (ctx->nranks == 1 && N > 0 && N <= ctx->smallN) {
+        // small system: the whole solve in one launch of one thread-block cluster
+        ctx->usedSmall = true;
+        SmallArgs a{N, ctl->precond, P.h.nColours, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
+                    ctx->diag, ctx->src, ctx->psi, ctx->r, ctx->p, ctx->w, ctx->rD, S, ctx->partials};
+        int nCtas = std::min(ctx->smallCtas, (N + kSmallBlock - 1) / kSmallBlock);
+        if (nCtas > 8) {
+            nCtas = 16;
+            CU(cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        } else if (nCtas > 4) nCtas = 8;
+        else if (nCtas > 2) nCtas = 4;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)nCtas);
+        cfg.blockDim = dim3(kSmallBlock);
+        cfg.stream = ctx->sc;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)nCtas;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CU(cudaEventRecord(ctx->ev[1], ctx->sc));
+        prof_begin(ctx, PC_SMALL);
+        CU(cudaLaunchKernelEx(&cfg, k_pcg_small, a));
+        prof_end(ctx, PC_SMALL);
+        ctx->launches++;
+        CU(cudaEventRecord(ctx->ev[2], ctx->sc));
+        CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+        LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
+        CU(cudaStreamSynchronize(ctx->sc));
+        CU(cudaGetLastError());
+        prof_collect(ctx);
+        return finish_solve(ctx, P, perf);
+    }
     // wA = A psi, sumA -> pA (OpenFOAM also uses pA as the normFactor temporary)
     RET((spmv_full<true, false>(ctx, P, ctx->psi, ctx->w, ctx->p, STEP_NONE)));
     {
@@ -696,25 +769,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     CU(cudaGetLastError());
     prof_collect(ctx);
 
-    const Scalars& h = *ctx->hS;
-    if (perf) {
-        std::memset(perf, 0, sizeof(*perf));
-        perf->initialResidual = h.initRes;
-        perf->finalResidual = h.finalRes;
-        perf->normFactor = h.normFactor;
-        perf->nIterations = h.nIter;
-        perf->converged = h.converged;
-        perf->singular = h.singular;
-        perf->nColours = P.h.nColours;
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        perf->setupMs = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
-        perf->solveMs = ms;
-    }
-    if (h.nonfinite == 2) return fail(ctx, B200_ENCCL, "peer-memory all-reduce timed out (a rank never arrived)");
-    if (h.nonfinite) return fail(ctx, B200_ENONFINITE, "non-finite residual in PCG");
-    return B200_OK;
+    return finish_solve(ctx, P, perf);
 }
 
 // Map every rank's PeerBuf into this process (CUDA IPC; handles exchanged with ncclAllGather).
@@ -824,6 +879,8 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         c->disableTma = (std::string(e2) == "sym");
         c->disableWin = (std::string(e2) != "win");
     }
+    if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
+    if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
@@ -980,6 +1037,129 @@ int b200_assemble_laplacian(b200_ctx* ctx, const double* g, const double* s, con
                                        ctx->in_diag));
     CU(cudaMemcpyAsync(upper_out, ctx->in_upper, fb, cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaMemcpyAsync(diag_inout, ctx->in_diag, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    return B200_OK;
+}
+
+int b200_set_boundary_faces(b200_ctx* ctx, int32_t nB, const int32_t* bCells) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "set_boundary_faces before set_addressing");
+    if (nB < 0 || (nB > 0 && !bCells)) return fail(ctx, B200_EINVAL, "bad boundary face list");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->bfStart && ctx->nB == nB && (nB == 0 || std::memcmp(ctx->hbCells.data(), bCells, sizeof(int32_t) * (size_t)nB) == 0))
+        return B200_OK;
+    const int32_t N = ctx->N;
+    std::vector<int32_t> start((size_t)N + 1, 0), order((size_t)nB);
+    for (int32_t b = 0; b < nB; ++b) {
+        if (bCells[b] < 0 || bCells[b] >= N) return fail(ctx, B200_EINVAL, "boundary faceCells out of range");
+        start[(size_t)bCells[b] + 1]++;
+    }
+    for (int32_t c = 0; c < N; ++c) start[(size_t)c + 1] += start[c];
+    std::vector<int32_t> pos(start.begin(), start.end() - 1);
+    for (int32_t b = 0; b < nB; ++b) order[(size_t)pos[bCells[b]]++] = b;   // stable: patch order inside a cell
+    CU(cudaStreamSynchronize(ctx->sc));
+    dev_free(ctx->bfStart);
+    dev_free(ctx->bfOrder);
+    RET(upload(ctx, &ctx->bfStart, start));
+    RET(upload(ctx, &ctx->bfOrder, order));
+    CU(cudaStreamSynchronize(ctx->sc));
+    ctx->hbCells.assign(bCells, bCells + nB);
+    ctx->nB = nB;
+    return B200_OK;
+}
+
+int b200_assemble_p_rgh_device(b200_ctx* ctx, const b200_prgh_terms* t, double* upper_out, double* diag_out,
+                               double* source_out) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "assemble before set_addressing");
+    if (!t) return fail(ctx, B200_EINVAL, "null terms");
+    const int N = ctx->N, F = ctx->F;
+    if ((F > 0 && (!t->gamma_f || !t->magSf || !t->deltaCoeffs || !upper_out)) ||
+        (N > 0 && (!t->V || !diag_out || !source_out)))
+        return fail(ctx, B200_EINVAL, "null argument");
+    if (t->psi && (!t->psi0 || !t->p0)) return fail(ctx, B200_EINVAL, "ddt term needs psi, psi0 and p0");
+    if (t->nExplicit < 0 || t->nExplicit > kMaxExplicit || (t->nExplicit > 0 && !t->explicitFields))
+        return fail(ctx, B200_EINVAL, "0 <= nExplicit <= 8");
+    const bool needB = t->bPhi || t->bInternal || t->bBoundary;
+    if (needB && (!ctx->bfStart || t->nB != ctx->nB))
+        return fail(ctx, B200_ESTATE, "boundary arrays given but b200_set_boundary_faces was not called with the same nB");
+    CU(cudaSetDevice(ctx->device));
+    DevPlan& P = ctx->plans[0];
+    PrghDev d;
+    std::memset(&d, 0, sizeof(d));
+    d.rDeltaT = t->rDeltaT; d.divSign = t->divSign;
+    d.V = t->V; d.psi = t->psi; d.psi0 = t->psi0; d.p0 = t->p0; d.phi = t->phi; d.Su = t->Su;
+    d.bPhi = t->bPhi; d.bInt = t->bInternal; d.bBou = t->bBoundary;
+    d.nExplicit = t->nExplicit;
+    for (int k = 0; k < t->nExplicit; ++k) {
+        if (!t->explicitFields[k]) return fail(ctx, B200_EINVAL, "null explicit field");
+        d.ex[k] = t->explicitFields[k];
+    }
+    d.bfStart = needB ? ctx->bfStart : nullptr;
+    d.bfOrder = needB ? ctx->bfOrder : nullptr;
+    LAUNCH(PC_ASM_FACE, k_face_coeff, grid_for(ctx, F, 16), F, t->gamma_f, t->magSf, t->deltaCoeffs,
+           t->lapSign < 0 ? -1.0 : 1.0, upper_out);
+    LAUNCH(PC_ASM_PRGH, k_prgh_cell, grid_for(ctx, N, 16), N, P.sliceBase, P.rowLen, P.faceOf, P.perm, ctx->d_l,
+           upper_out, d, diag_out, source_out);
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+    return B200_OK;
+}
+
+int b200_assemble_p_rgh(b200_ctx* ctx, const b200_prgh_terms* t, double* upper_out, double* diag_out,
+                        double* source_out) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "assemble before set_addressing");
+    if (!t) return fail(ctx, B200_EINVAL, "null terms");
+    const size_t N = (size_t)ctx->N, F = (size_t)ctx->F;
+    if (t->nExplicit < 0 || t->nExplicit > kMaxExplicit || (t->nExplicit > 0 && !t->explicitFields))
+        return fail(ctx, B200_EINVAL, "0 <= nExplicit <= 8");
+    if ((F > 0 && (!t->gamma_f || !t->magSf || !t->deltaCoeffs || !upper_out)) || (N > 0 && (!t->V || !diag_out || !source_out)))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const bool needB = t->bPhi || t->bInternal || t->bBoundary;
+    if (needB) {
+        if (!t->bCells && t->nB > 0) return fail(ctx, B200_EINVAL, "boundary arrays given without bCells");
+        RET(b200_set_boundary_faces(ctx, t->nB, t->bCells));
+    }
+    const size_t nB = needB ? (size_t)t->nB : 0;
+    // staging arena: every array is padded to a multiple of 32 doubles
+    auto pad = [](size_t n) { return (n + 31) & ~(size_t)31; };
+    const size_t need = (7 + (size_t)t->nExplicit) * pad(N) + 5 * pad(F) + 3 * pad(nB) + 64;
+    if (need > ctx->scratchElems) {
+        CU(cudaStreamSynchronize(ctx->sc));
+        dev_free(ctx->scratch);
+        RET(dev_alloc(ctx, &ctx->scratch, need));
+        ctx->scratchElems = need;
+    }
+    double* cur = ctx->scratch;
+    cudaError_t cpErr = cudaSuccess;
+    auto stage = [&](const double* h, size_t n) -> const double* {
+        if (!h) return nullptr;
+        double* d = cur;
+        cur += pad(n);
+        if (n && cpErr == cudaSuccess)
+            cpErr = cudaMemcpyAsync(d, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->sc);
+        return d;
+    };
+    b200_prgh_terms dt = *t;
+    const double* exs[kMaxExplicit] = {};
+    dt.V = stage(t->V, N); dt.psi = stage(t->psi, N); dt.psi0 = stage(t->psi0, N); dt.p0 = stage(t->p0, N);
+    for (int k = 0; k < t->nExplicit; ++k) exs[k] = stage(t->explicitFields[k], N);
+    dt.explicitFields = exs;
+    dt.phi = stage(t->phi, F);
+    dt.gamma_f = stage(t->gamma_f, F); dt.magSf = stage(t->magSf, F); dt.deltaCoeffs = stage(t->deltaCoeffs, F);
+    dt.Su = stage(t->Su, N);
+    dt.bPhi = stage(t->bPhi, nB); dt.bInternal = stage(t->bInternal, nB); dt.bBoundary = stage(t->bBoundary, nB);
+    double* d_upper = cur; cur += pad(F);
+    double* d_diag = cur; cur += pad(N);
+    double* d_src = cur; cur += pad(N);
+    if (cpErr != cudaSuccess) return fail(ctx, B200_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(cpErr));
+    RET(b200_assemble_p_rgh_device(ctx, &dt, d_upper, d_diag, d_src));
+    CU(cudaMemcpyAsync(upper_out, d_upper, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaMemcpyAsync(diag_out, d_diag, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaMemcpyAsync(source_out, d_src, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
     return B200_OK;
 }
@@ -1146,11 +1326,12 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"win_smem_bytes\": %zu, \"win_run_chunks\": %d, \"chunk_rows\": %d, \"tma_stages\": %d, "
                   "\"nranks\": %d, \"peer_allreduce\": %s, \"nCells\": %d, \"nFaces\": %d, \"nSlots\": %d, \"sms\": %d, "
                   "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
-                  "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f}",
+                  "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
+                  "\"small_system_cluster_kernel\": %s, \"small_n_max\": %d}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
-                  P.h.sectorsUsed);
+                  P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->smallN);
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

@@ -174,6 +174,59 @@ class Context:
             self.handle, _ptr(d_gamma), _ptr(d_magSf), _ptr(d_delta), float(sign), _ptr(d_upper_out),
             _ptr(d_diag_inout)))
 
+    # ---- the whole p_rghEqn (solver/pEqn.H:26-37) + solveSegregated boundary fold ---------------
+    def set_boundary_faces(self, bCells):
+        b = _i32(bCells)
+        self._check(self.lib.b200_set_boundary_faces(self.handle, b.size, b.ctypes.data))
+
+    def _prgh_terms(self, terms, device):
+        """dict -> b200_prgh_terms.  Keys: rDeltaT, V, psi, psi0, p0, explicit (list of cell fields),
+        phi, divSign, gamma_f, magSf, deltaCoeffs, lapSign, Su, bCells, bPhi, bInternal, bBoundary."""
+        t = _lib.PrghTerms()
+        keep = []
+
+        def addr(v, dtype=np.float64):
+            if v is None:
+                return None
+            if device:
+                keep.append(v)
+                return _ptr(v)
+            a = np.ascontiguousarray(v, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+        t.rDeltaT = float(terms.get("rDeltaT", 0.0))
+        for n in ("V", "psi", "psi0", "p0", "phi", "gamma_f", "magSf", "deltaCoeffs", "Su", "bPhi",
+                  "bInternal", "bBoundary"):
+            setattr(t, n, addr(terms.get(n)))
+        ex = list(terms.get("explicit") or [])
+        arr = (C.c_void_p * max(1, len(ex)))(*[addr(e) for e in ex])
+        keep.append(arr)
+        t.nExplicit, t.explicitFields = len(ex), C.cast(arr, C.c_void_p)
+        t.divSign, t.lapSign = float(terms.get("divSign", -1.0)), float(terms.get("lapSign", -1.0))
+        bc = terms.get("bCells")
+        if bc is not None:
+            bc = _i32(bc)
+            keep.append(bc)
+            t.nB, t.bCells = bc.size, bc.ctypes.data
+        return t, keep
+
+    def assemble_p_rgh(self, terms):
+        """Host arrays in, (upper, diag with internalCoeffs, totalSource) out."""
+        addr = self._addr
+        t, keep = self._prgh_terms(terms, device=False)
+        upper, diag, src = np.empty(addr.nFaces), np.empty(addr.nCells), np.empty(addr.nCells)
+        self._check(self.lib.b200_assemble_p_rgh(self.handle, C.addressof(t), upper.ctypes.data,
+                                                 diag.ctypes.data, src.ctypes.data))
+        return upper, diag, src
+
+    def assemble_p_rgh_device(self, terms, d_upper_out, d_diag_out, d_source_out):
+        """Device tensors in `terms` (bCells stays a host array, set once with set_boundary_faces)."""
+        if terms.get("bCells") is not None:
+            self.set_boundary_faces(terms["bCells"])
+        t, keep = self._prgh_terms(terms, device=True)
+        self._check(self.lib.b200_assemble_p_rgh_device(self.handle, C.addressof(t), _ptr(d_upper_out),
+                                                        _ptr(d_diag_out), _ptr(d_source_out)))
+
     # ---- lduMatrix::Amul / fvMatrix::flux ----------------------------------------------------
     def amul(self, matrix, interfaceBouCoeffs, psi):
         psi = _f64(psi)

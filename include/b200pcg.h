@@ -140,6 +140,47 @@ int b200_assemble_laplacian_device(b200_ctx* ctx, const double* d_gamma_f, const
                                    const double* d_deltaCoeffs, double sign,
                                    double* d_upper_out, double* d_diag_inout);
 
+/* ---- assembly of the whole p_rghEqn -------------------------------------- */
+
+/* Replaces, on the device, the fvMatrix algebra of solver/pEqn.H:26-37
+ *     fvm::ddt(psi, p_rgh) + fvc::ddt(psi, rho)*gh + fvc::ddt(psi)*pRef + fvc::div(phiHbyA)
+ *   - fvm::laplacian(rhorAUf, p_rgh) == parcels.Srho() + surfaceFilm.Srho() + fvOptions(...)
+ * (OF-dev EulerDdtScheme.C fvmDdt, fvMatrix.C operator+/-/==, surfaceIntegrate.C,
+ * gaussLaplacianScheme.C, lduMatrixOperations.C negSumDiag) AND the boundary fold of
+ * fvMatrix::solveSegregated (addBoundaryDiag / addBoundarySource), so that what comes
+ * out is exactly what lduMatrix::solver::solve receives: upper, diag (with internalCoeffs) and
+ * totalSource.  With psi == NULL, phi = phig, divSign = +1, lapSign = +1 it is the ph_rghEqn of
+ * solver/phrghEqn.H:43-46.  Every sum is formed in OpenFOAM's face / patch order (sorted segments, no
+ * atomics): bit-identical to the CPU operator sequence.
+ *   diag   = rDeltaT*psi*V  -/+ negSumDiag(laplacian)  + sum internalCoeffs
+ *   source = rDeltaT*psi0*p0*V - sum_k V*explicit_k  -/+ V*(surfaceIntegrate(phi)/V) + V*Su + sum boundaryCoeffs
+ * The adapter evaluates the explicit cell fields (fvc::ddt(psi,rho)*gh, ...) and the patch coefficients
+ * with OpenFOAM itself; they arrive as plain arrays.  At most 8 explicit fields. */
+typedef struct b200_prgh_terms {
+    double rDeltaT;                       /* 1/deltaT (Euler)                                      */
+    const double *V, *psi, *psi0, *p0;    /* [nCells] mesh.V(), psi, psi.oldTime(), p_rgh.oldTime();
+                                             psi == NULL: no ddt term                              */
+    int32_t nExplicit, pad0;
+    const double* const* explicitFields;  /* [nExplicit] pointers to [nCells]: source -= V*field   */
+    const double* phi;                    /* [nFaces] flux of the fvc::div term, or NULL           */
+    double divSign;                       /* -1: `+ fvc::div(phi)` on the left, +1: `== fvc::div(phi)` */
+    const double *gamma_f, *magSf, *deltaCoeffs;   /* [nFaces] laplacian inputs                    */
+    double lapSign;                       /* -1: `- fvm::laplacian`, +1: `fvm::laplacian`          */
+    const double* Su;                     /* [nCells] explicit source `== Su` (source += V*Su), or NULL */
+    int32_t nB, pad1;                     /* boundary faces (b200_set_boundary_faces)              */
+    const int32_t* bCells;                /* unused by the device entry point (set once per mesh)  */
+    const double *bPhi, *bInternal, *bBoundary;   /* [nB] boundary flux of phi, internalCoeffs (all
+                                             patches), boundaryCoeffs (0 on coupled patches); NULL = none */
+} b200_prgh_terms;
+
+/* faceCells of every boundary face, patch by patch (mesh constant; idempotent for unchanged input) */
+int b200_set_boundary_faces(b200_ctx* ctx, int32_t nB, const int32_t* bCells);
+int b200_assemble_p_rgh(b200_ctx* ctx, const b200_prgh_terms* t, double* upper_out, double* diag_out,
+                        double* source_out);
+/* all array pointers inside *t are DEVICE pointers (the struct and explicitFields[] live on the host) */
+int b200_assemble_p_rgh_device(b200_ctx* ctx, const b200_prgh_terms* t, double* d_upper_out,
+                               double* d_diag_out, double* d_source_out);
+
 /* ---- solve: lduMatrix::solver::solve ------------------------------------------------- */
 
 /* Replaces: PCG::solve(psi, source, cmpt) with its Amul/normFactor/preconditioner/gSum*
@@ -187,6 +228,44 @@ const char* b200_profile_json(b200_ctx* ctx);
 /* which kernel variants / launch geometry the context selected for the current mesh, as a JSON
  * string (bench "roofline.kernel"; valid until the next call on this context) */
 const char* b200_describe(b200_ctx* ctx);
+
+/* ---- matrix dump / replay format (layout in csrc/dump.cpp) ---------------- */
+
+/* What lduMatrix::solver::solve receives on one rank (reference call sites solver/pEqn.H:39,
+ * solver/phrghEqn.H:48), plus what it reported.  Written by the adapter when B200PCG_DUMP=<dir>
+ * is set, one file per rank and solve; read back by tools/b200replay and
+ * firefoam-dev_b200/replay.py.  Host-only: needs no GPU. */
+typedef struct b200_dump {
+    const char*    fieldName;       /* "p_rgh", "ph_rgh", ...                                  */
+    int32_t        rank, nranks;
+    int32_t        nCells, nFaces;
+    const int32_t* lowerAddr;       /* [nFaces]                                                */
+    const int32_t* upperAddr;       /* [nFaces]                                                */
+    const double*  diag;            /* [nCells] with boundary internalCoeffs   */
+    const double*  upper;           /* [nFaces]                                                */
+    const double*  source;          /* [nCells] totalSource                                    */
+    const double*  psi0;            /* [nCells] initial guess                                  */
+    const double*  psiSolution;     /* [nCells] solution, or NULL                              */
+    int32_t        nIfaces;
+    const b200_iface* ifaces;       /* [nIfaces]                                               */
+    const double* const* ifaceBouCoeffs;   /* [nIfaces][ifaces[k].nFaces]                      */
+    b200_controls  controls;
+    int32_t        havePerf;        /* perf + solverName below are valid                       */
+    b200_perf      perf;            /* what the solver that ran in the host application reported */
+    const char*    solverName;      /* e.g. "DICPCG"                                           */
+    int32_t        solveIndex;      /* running number of the solve on this rank                */
+    double         time;            /* runTime.value()                                         */
+} b200_dump;
+
+typedef struct b200_dump_file b200_dump_file;
+
+int b200_dump_write(const char* path, const b200_dump* d);
+/* reads a dump; the arrays of b200_dump_get() point into memory owned by *out */
+int b200_dump_read(const char* path, b200_dump_file** out);
+const b200_dump* b200_dump_get(const b200_dump_file* f);
+const char* b200_dump_header_json(const b200_dump_file* f);
+void b200_dump_free(b200_dump_file* f);
+const char* b200_dump_last_error(void);
 
 #ifdef __cplusplus
 }

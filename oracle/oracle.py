@@ -87,6 +87,63 @@ def laplacian_assemble(lowerAddr, upperAddr, nCells, gamma_f, magSf, deltaCoeffs
     return upper, diag
 
 
+class PrghTerms(C.Structure):
+    """orc_prgh_terms (pcg_oracle.c) == b200_prgh_terms (include/b200pcg.h): same layout."""
+    _fields_ = [("rDeltaT", C.c_double), ("V", C.c_void_p), ("psi", C.c_void_p), ("psi0", C.c_void_p),
+                ("p0", C.c_void_p), ("nExplicit", C.c_int32), ("pad0", C.c_int32),
+                ("explicitFields", C.c_void_p), ("phi", C.c_void_p), ("divSign", C.c_double),
+                ("gamma_f", C.c_void_p), ("magSf", C.c_void_p), ("deltaCoeffs", C.c_void_p),
+                ("lapSign", C.c_double), ("Su", C.c_void_p), ("nB", C.c_int32), ("pad1", C.c_int32),
+                ("bCells", C.c_void_p), ("bPhi", C.c_void_p), ("bInternal", C.c_void_p),
+                ("bBoundary", C.c_void_p)]
+
+
+def pack_prgh_terms(terms, ptr=lambda a: a.ctypes.data):
+    """dict -> (PrghTerms, keep-alive list).  Keys: rDeltaT, V, psi, psi0, p0, explicit (list), phi,
+    divSign, gamma_f, magSf, deltaCoeffs, lapSign, Su, bCells, bPhi, bInternal, bBoundary (absent = NULL).
+    `ptr` maps an array to its address (device tensors: lambda t: t.data_ptr())."""
+    t = PrghTerms()
+    keep = []
+
+    def put(name, key, dtype=np.float64):
+        v = terms.get(key)
+        if v is None:
+            return
+        if isinstance(v, np.ndarray) or isinstance(v, (list, tuple)):
+            v = np.ascontiguousarray(v, dtype=dtype)
+        keep.append(v)
+        setattr(t, name, ptr(v))
+    t.rDeltaT = float(terms.get("rDeltaT", 0.0))
+    for n in ("V", "psi", "psi0", "p0", "phi", "gamma_f", "magSf", "deltaCoeffs", "Su", "bPhi", "bInternal", "bBoundary"):
+        put(n, n)
+    put("bCells", "bCells", np.int32)
+    ex = terms.get("explicit") or []
+    ex = [np.ascontiguousarray(e, dtype=np.float64) if isinstance(e, (np.ndarray, list, tuple)) else e for e in ex]
+    arr = (C.c_void_p * max(1, len(ex)))(*[ptr(e) for e in ex])
+    keep += [ex, arr]
+    t.nExplicit = len(ex)
+    t.explicitFields = C.cast(arr, C.c_void_p)
+    t.divSign = float(terms.get("divSign", -1.0))
+    t.lapSign = float(terms.get("lapSign", -1.0))
+    bc = terms.get("bCells")
+    t.nB = 0 if bc is None else int(len(bc))
+    return t, keep
+
+
+def assemble_p_rgh(lowerAddr, upperAddr, nCells, terms):
+    """Restatement of the p_rghEqn assembly + solveSegregated boundary fold; returns (upper, diag, source)."""
+    l, u = _i32(lowerAddr), _i32(upperAddr)
+    t, keep = pack_prgh_terms(terms)
+    upper, diag, src = np.empty(l.size), np.empty(nCells), np.empty(nCells)
+    L = lib()
+    L.orc_assemble_p_rgh.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    L.orc_assemble_p_rgh.restype = None
+    L.orc_assemble_p_rgh(nCells, l.size, l.ctypes.data, u.ctypes.data, C.addressof(t), upper.ctypes.data,
+                         diag.ctypes.data, src.ctypes.data)
+    return upper, diag, src
+
+
 def flux(lowerAddr, upperAddr, upper, psi):
     l, u, a, x = _i32(lowerAddr), _i32(upperAddr), _f64(upper), _f64(psi)
     out = np.empty(l.size, dtype=np.float64)

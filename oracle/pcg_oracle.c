@@ -86,6 +86,85 @@ void orc_laplacian_assemble(int32_t N, int32_t F, const int32_t* l, const int32_
     free(d);
 }
 
+/* ---- the whole p_rghEqn of solver/pEqn.H:26-37 (and ph_rghEqn of solver/phrghEqn.H:43-46) as the
+ *      solver sees it after fvMatrix::solveSegregated's boundary fold.
+ *      Literal restatement, operator by operator, of OF-dev
+ *        EulerDdtScheme<scalar>::fvmDdt(rho, vf)      diag = rDeltaT*rho*Vsc; source = rDeltaT*rho0*vf0*Vsc
+ *        operator+(tmp<fvMatrix>, tmp<volScalarField>)  source -= V*su        (fvc::ddt(psi,rho)*gh, fvc::ddt(psi)*pRef)
+ *        fvc::surfaceIntegrate (fvc::div(phiHbyA))      owner += phi, neighbour -= phi, boundary += phi_b, /= Vsc
+ *        gaussLaplacianScheme::fvmLaplacianUncorrected + negSumDiag, operator-(tmp, tmp) / operator==
+ *        operator==(tmp<fvMatrix>, tmp<volScalarField::Internal>)   source += V*su   (parcels.Srho() + ...)
+ *        fvMatrix::addBoundaryDiag / addBoundarySource   diag[faceCells] += internalCoeffs, source[..] += boundaryCoeffs
+ *      in the face-loop (scatter) form OpenFOAM uses.  lapSign = -1: `- fvm::laplacian` on the left
+ *      (pEqn.H:32); +1: `fvm::laplacian ==` (phrghEqn.H:45).  divSign = -1: `+ fvc::div(phi)` on the left
+ *      (pEqn.H:31); +1: `== fvc::div(phig)` on the right (phrghEqn.H:45). ------------------------------ */
+typedef struct orc_prgh_terms {
+    double rDeltaT;
+    const double *V, *psi, *psi0, *p0;        /* psi == NULL: no ddt term (diag = source = 0)        */
+    int32_t nExplicit, pad0;
+    const double* const* explicitFields;      /* [nExplicit][N]                                      */
+    const double* phi;                        /* [F] or NULL                                         */
+    double divSign;
+    const double *gamma_f, *magSf, *deltaCoeffs;
+    double lapSign;
+    const double* Su;                         /* [N] or NULL                                         */
+    int32_t nB, pad1;                         /* boundary faces, patch by patch                      */
+    const int32_t* bCells;                    /* [nB] faceCells                                      */
+    const double *bPhi, *bInternal, *bBoundary;   /* [nB] each or NULL                               */
+} orc_prgh_terms;
+
+void orc_assemble_p_rgh(int32_t N, int32_t F, const int32_t* l, const int32_t* u, const orc_prgh_terms* t,
+                        double* upper_out, double* diag_out, double* source_out) {
+    const double* V = t->V;
+    for (int32_t c = 0; c < N; ++c) {
+        if (t->psi) {
+            diag_out[c] = t->rDeltaT * t->psi[c] * V[c];
+            source_out[c] = t->rDeltaT * t->psi0[c] * t->p0[c] * V[c];
+        } else {
+            diag_out[c] = 0.0;
+            source_out[c] = 0.0;
+        }
+    }
+    for (int32_t k = 0; k < t->nExplicit; ++k)
+        for (int32_t c = 0; c < N; ++c) source_out[c] -= V[c] * t->explicitFields[k][c];
+    if (t->phi) {
+        double* ivf = (double*)calloc((size_t)(N > 0 ? N : 1), sizeof(double));
+        for (int32_t f = 0; f < F; ++f) {
+            ivf[l[f]] += t->phi[f];
+            ivf[u[f]] -= t->phi[f];
+        }
+        if (t->bPhi)
+            for (int32_t b = 0; b < t->nB; ++b) ivf[t->bCells[b]] += t->bPhi[b];
+        for (int32_t c = 0; c < N; ++c) ivf[c] /= V[c];
+        for (int32_t c = 0; c < N; ++c) {
+            if (t->divSign < 0) source_out[c] -= V[c] * ivf[c];
+            else source_out[c] += V[c] * ivf[c];
+        }
+        free(ivf);
+    }
+    {
+        double* d = (double*)calloc((size_t)(N > 0 ? N : 1), sizeof(double));
+        for (int32_t f = 0; f < F; ++f) upper_out[f] = t->deltaCoeffs[f] * (t->gamma_f[f] * t->magSf[f]);
+        for (int32_t f = 0; f < F; ++f) {
+            d[l[f]] -= upper_out[f];
+            d[u[f]] -= upper_out[f];
+        }
+        if (t->lapSign < 0) {   /* lduMatrix::operator-=: diag -= L.diag; upper (absent: 0) -= L.upper */
+            for (int32_t c = 0; c < N; ++c) diag_out[c] -= d[c];
+            for (int32_t f = 0; f < F; ++f) upper_out[f] = 0.0 - upper_out[f];
+        } else {
+            for (int32_t c = 0; c < N; ++c) diag_out[c] += d[c];
+        }
+        free(d);
+    }
+    if (t->Su)
+        for (int32_t c = 0; c < N; ++c) source_out[c] += V[c] * t->Su[c];
+    if (t->bInternal)
+        for (int32_t b = 0; b < t->nB; ++b) diag_out[t->bCells[b]] += t->bInternal[b];
+    if (t->bBoundary)
+        for (int32_t b = 0; b < t->nB; ++b) source_out[t->bCells[b]] += t->bBoundary[b];
+}
+
 /* ---- fvMatrix<scalar>::flux(), internal faces (OF-dev fvMatrix.C) ---------- */
 void orc_flux(int32_t F, const int32_t* l, const int32_t* u, const double* upper, const double* psi,
               double* flux) {

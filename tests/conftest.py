@@ -31,9 +31,20 @@ def has_gpu():
         return False
 
 
-@pytest.fixture(scope="session")
-def ctx():
+@pytest.fixture(scope="session", params=["multi-kernel", "cluster-kernel"])
+def ctx(request):
+    """Every parity test runs twice: through the multi-kernel PCG loop (the path large systems
+    take; forced here with B200PCG_SMALL_N=0) and through the single-launch thread-block-cluster
+    kernel that systems of up to 65 536 cells take by default."""
     from firefoam_dev_b200 import Context
-    c = Context()
+    old = os.environ.get("B200PCG_SMALL_N")
+    os.environ["B200PCG_SMALL_N"] = "0" if request.param == "multi-kernel" else "65536"
+    try:
+        c = Context()
+    finally:
+        if old is None:
+            os.environ.pop("B200PCG_SMALL_N", None)
+        else:
+            os.environ["B200PCG_SMALL_N"] = old
     yield c
     c.close()

@@ -1,0 +1,44 @@
+"""Generates the committed `.b200sys` fixtures (format regression corpus) with the
+CPU oracle as the dumping solver:
+
+  singlebox_ph_rgh_c1.b200sys   first hydrostatic corrector of the restated cases/singleBox base block
+                                (245 cells, PCG + diagonal; BASELINE config 1)
+  steckler_ph_rgh_c1.b200sys    first hydrostatic corrector of cases/steckler (9 000 cells, DICPCG,
+                                tol 1e-6 relTol 0.01: the system behind log.fireFoam:92, 29 iterations)
+
+The systems come from firefoam-dev_b200/cases.py (the case files restated by hand: no OpenFOAM here),
+the recorded reference lines from oracle/ (plain-C restatement of OpenFOAM's PCG).  Run from the repo
+root: python tests/golden/make_dumps.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from firefoam_dev_b200 import replay  # noqa: E402
+from firefoam_dev_b200.cases import SingleBoxHydrostatic, StecklerHydrostatic  # noqa: E402
+from firefoam_dev_b200.meshgen import System  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def first_corrector(case, pre, name):
+    m, src = case.assemble(lambda g, s, d, sign, d0: orc.laplacian_assemble(
+        case.addr.lowerAddr, case.addr.upperAddr, case.N, g, s, d, sign, d0))
+    sysm = System(case.addr, m.diag, m.upper, src, [])
+    psi0 = case.ph_rgh.copy()
+    psi = psi0.copy()
+    perf = orc.pcg_solve(sysm, psi, pre, case.TOL, case.RELTOL, 1000)
+    ctl = {"preconditioner": pre, "tolerance": case.TOL, "relTol": case.RELTOL, "maxIter": 1000}
+    if pre == "DIC":
+        ctl["B200"] = {"dicMode": "exact"}     # the dumped reference is OpenFOAM's DIC, not the multicolour IC0
+    ref = {"initialResidual": perf.initialResidual, "finalResidual": perf.finalResidual,
+           "nIterations": perf.nIterations, "converged": perf.converged, "singular": perf.singular}
+    path = os.path.join(HERE, name)
+    replay.write_dump(path, sysm, psi0, ctl, fieldName="ph_rgh", psi=psi, reference=ref,
+                      solverName=pre + "PCG", solveIndex=0, time=0.0)
+    print(name, os.path.getsize(path), "bytes;", pre + "PCG", perf.nIterations, "iterations")
+
+
+first_corrector(SingleBoxHydrostatic(), "diagonal", "singlebox_ph_rgh_c1.b200sys")
+first_corrector(StecklerHydrostatic(), "DIC", "steckler_ph_rgh_c1.b200sys")

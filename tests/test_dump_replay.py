@@ -1,0 +1,129 @@
+"""Matrix dump / replay format: the C-ABI writer/reader (csrc/dump.cpp, the code
+the OpenFOAM adapter calls), the pure-numpy reader, the committed fixtures, and -- on a GPU -- the
+replay of the fixtures through the CUDA path and the native tools/b200replay binary."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from firefoam_dev_b200 import _lib, meshgen as mg, replay
+from oracle import oracle as orc
+from conftest import ROOT, has_gpu
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_fixture_steckler_pins_the_golden_log_count():
+    """The committed steckler dump is the system behind log.fireFoam:92: the oracle needs the log's 29
+    DICPCG iterations on exactly the bytes in the file, and reproduces the stored solution."""
+    d = replay.read_dump(os.path.join(GOLD, "steckler_ph_rgh_c1.b200sys"))
+    log = json.load(open(os.path.join(GOLD, "steckler_log.json")))
+    assert d.fieldName == "ph_rgh" and d.system.addr.nCells == 9000 and d.system.addr.nFaces == 24868
+    assert d.reference["nIterations"] == log["ph_rgh"][0]["iters"] == 29
+    assert d.controls["preconditioner"] == "DIC" and d.controls["relTol"] == 0.01
+    psi = d.psi0.copy()
+    perf = orc.pcg_solve(d.system, psi, "DIC", d.controls["tolerance"], d.controls["relTol"], d.controls["maxIter"])
+    assert perf.nIterations == 29
+    assert perf.finalResidual == d.reference["finalResidual"]
+    assert np.array_equal(psi, d.psi)
+
+
+def test_fixture_singlebox():
+    d = replay.read_dump(os.path.join(GOLD, "singlebox_ph_rgh_c1.b200sys"))
+    assert d.system.addr.nCells == 245 and d.controls["preconditioner"] == "diagonal"
+    psi = d.psi0.copy()
+    perf = orc.pcg_solve(d.system, psi, "diagonal", d.controls["tolerance"], d.controls["relTol"], d.controls["maxIter"])
+    assert perf.nIterations == d.reference["nIterations"] and np.array_equal(psi, d.psi)
+
+
+def test_roundtrip_multirank_with_interfaces(tmp_path):
+    """write (C ABI) -> read (numpy) and read (C ABI): every array bit-identical, including processor
+    interfaces; arrays 64-byte aligned; empty patches and ragged sizes survive."""
+    subs = [mg.hex_block(7, 6, 5, 2, 2, 1, r) for r in range(4)]
+    L = _lib.load_pcg()
+    for r, s in enumerate(subs):
+        p = tmp_path / f"p_rgh_3_p{r}.b200sys"
+        psi0 = np.random.default_rng(r).standard_normal(s.addr.nCells)
+        ctl = {"preconditioner": "diagonal", "tolerance": 1e-7, "relTol": 0.05, "maxIter": 321, "minIter": 2}
+        replay.write_dump(p, s, psi0, ctl, fieldName="p_rgh", rank=r, nranks=4, solveIndex=3, time=0.125,
+                          reference={"initialResidual": 0.5, "finalResidual": 1e-8, "nIterations": 17},
+                          solverName="diagonalPCG")
+        d = replay.read_dump(p)
+        assert (d.rank, d.nranks, d.fieldName) == (r, 4, "p_rgh")
+        assert d.header["solveIndex"] == 3 and d.header["time"] == 0.125
+        assert d.controls == ctl and d.reference["nIterations"] == 17 and d.psi is None
+        a, b = d.system.addr, s.addr
+        assert np.array_equal(a.lowerAddr, b.lowerAddr) and np.array_equal(a.upperAddr, b.upperAddr)
+        for x, y in ((d.system.diag, s.diag), (d.system.upper, s.upper), (d.system.source, s.source), (d.psi0, psi0)):
+            assert np.array_equal(x, y)
+        assert len(a.interfaces) == len(b.interfaces) > 0
+        for k, (ia, ib) in enumerate(zip(a.interfaces, b.interfaces)):
+            assert ia.neighbProcNo == ib.neighbProcNo and np.array_equal(ia.faceCells, ib.faceCells)
+            assert np.array_equal(d.system.bou[k], s.bou[k])
+        assert all(int(x["offset"]) % 64 == 0 for x in d.header["arrays"])
+        # C reader
+        h = C.c_void_p()
+        assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0, L.b200_dump_last_error()
+        dd = L.b200_dump_get(h).contents
+        assert (dd.nCells, dd.nFaces, dd.nIfaces, dd.rank, dd.nranks) == (b.nCells, b.nFaces, len(b.interfaces), r, 4)
+        assert dd.controls.maxIter == 321 and dd.controls.minIter == 2 and dd.controls.precond == 1
+        assert dd.perf.nIterations == 17 and dd.solverName == b"diagonalPCG" and dd.havePerf == 1
+        got = np.ctypeslib.as_array(C.cast(dd.diag, C.POINTER(C.c_double)), shape=(b.nCells,))
+        assert np.array_equal(got, s.diag)
+        fc = np.ctypeslib.as_array(C.cast(dd.ifaces[0].faceCells, C.POINTER(C.c_int32)), shape=(dd.ifaces[0].nFaces,))
+        assert np.array_equal(fc, b.interfaces[0].faceCells)
+        assert json.loads(L.b200_dump_header_json(h).decode())["nCells"] == b.nCells
+        L.b200_dump_free(h)
+
+
+def test_edge_cases_and_errors(tmp_path):
+    L = _lib.load_pcg()
+    # empty system
+    from firefoam_dev_b200.ldu import LduAddressing
+    from firefoam_dev_b200.meshgen import System
+    e = System(LduAddressing(0, [], []), np.zeros(0), np.zeros(0), np.zeros(0), [])
+    p = tmp_path / "empty.b200sys"
+    replay.write_dump(p, e, np.zeros(0), {"preconditioner": "none"})
+    d = replay.read_dump(p)
+    assert d.system.addr.nCells == 0 and d.reference is None
+    # not a dump / truncated
+    bad = tmp_path / "bad.b200sys"
+    bad.write_bytes(b"FoamFile { version 2.0; }")
+    with pytest.raises(ValueError):
+        replay.read_dump(bad)
+    h = C.c_void_p()
+    assert L.b200_dump_read(str(bad).encode(), C.byref(h)) != 0 and not h
+    assert b"not a b200 system dump" in L.b200_dump_last_error()
+    good = open(os.path.join(GOLD, "singlebox_ph_rgh_c1.b200sys"), "rb").read()
+    cut = tmp_path / "cut.b200sys"
+    cut.write_bytes(good[:len(good) // 2])
+    with pytest.raises(ValueError):
+        replay.read_dump(cut)
+    assert L.b200_dump_read(str(cut).encode(), C.byref(h)) != 0
+    assert L.b200_dump_write(None, None) != 0
+    assert L.b200_dump_read(str(tmp_path / "missing.b200sys").encode(), C.byref(h)) != 0
+
+
+@pytest.mark.gpu
+def test_replay_fixtures_on_gpu(ctx):
+    for name in ("steckler_ph_rgh_c1.b200sys", "singlebox_ph_rgh_c1.b200sys"):
+        psi, perf, d = replay.replay(os.path.join(GOLD, name), context=ctx)
+        assert perf.nIterations == d.reference["nIterations"]
+        assert abs(perf.finalResidual - d.reference["finalResidual"]) <= 1e-9 * d.reference["finalResidual"]
+        assert np.abs(psi - d.psi).max() <= 1e-12 * np.abs(d.psi).max()
+    assert "DICB200PCG" in str(replay.replay(os.path.join(GOLD, "steckler_ph_rgh_c1.b200sys"), context=ctx)[1])
+
+
+@pytest.mark.gpu
+def test_native_replay_tool():
+    exe = os.path.join(ROOT, "firefoam-dev_b200", "b200replay")
+    if not os.path.exists(exe):
+        pytest.skip("b200replay not built")
+    r = subprocess.run([exe, os.path.join(GOLD, "steckler_ph_rgh_c1.b200sys"),
+                        os.path.join(GOLD, "singlebox_ph_rgh_c1.b200sys")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DICB200PCG:  Solving for ph_rgh, Initial residual = 1, " in r.stdout
+    assert r.stdout.count("No Iterations 29") == 2 and "MISMATCH" not in r.stdout

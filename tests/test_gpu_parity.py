@@ -361,12 +361,12 @@ def _ctx_with_env(env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("mode", ["0", "1"])
-def test_rcm_renumbering_does_not_change_results(mode):
+@pytest.mark.parametrize("mode,small", [("0", "0"), ("1", "0"), ("1", "65536")])
+def test_rcm_renumbering_does_not_change_results(mode, small):
     """Rows renumbered by reverse Cuthill-McKee (forced) or not at all: assembly, Amul and flux stay
     bit-identical to the oracle, PCG + diagonal keeps the oracle's iteration counts, DIC-exact is
     unaffected (never renumbered), multicolour DIC still converges to the same solution."""
-    c = _ctx_with_env({"B200PCG_RENUMBER": mode})
+    c = _ctx_with_env({"B200PCG_RENUMBER": mode, "B200PCG_SMALL_N": small})
     try:
         for s in (mg.bcc_poly(9, 8, 10), mg.hex_block(24, 20, 16), random_ldu(5001, 6.0, seed=7)):
             a = s.addr
@@ -386,5 +386,29 @@ def test_rcm_renumbering_does_not_change_results(mode):
             xg, pg = solve_gpu(c, s, "DIC", tol=1e-11, maxIter=5000)
             xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
             assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("ctas", ["1", "4", "8", "16"])
+def test_cluster_kernel_sizes(ctas):
+    """k_pcg_small with every cluster size (16 is the non-portable maximum), on systems from one
+    cell to the 65 536-cell limit, all preconditioners, against the oracle."""
+    c = _ctx_with_env({"B200PCG_SMALL_CTAS": ctas, "B200PCG_SMALL_N": "65536"})
+    try:
+        for s in (mg.hex_block(40, 40, 40), mg.hex_block(7, 5, 3), random_ldu(1000, 1.5, seed=9),
+                  mg.bcc_poly(9, 8, 10)):
+            for pre, exact in (("diagonal", False), ("none", False), ("DIC", True)):
+                xg, pg = solve_gpu(c, s, pre, tol=1e-7, maxIter=4000, exact=exact)
+                xc, pc = solve_cpu(s, pre, tol=1e-7, maxIter=4000)
+                if pre != "none":
+                    assert pg.nIterations == pc.nIterations, (pre, pg.nIterations, pc.nIterations)
+                    assert relmax(xg, xc) < 1e-12
+                else:
+                    assert pg.converged and relmax(xg, xc) < 1e-5
+            xg, pg = solve_gpu(c, s, "DIC", tol=1e-11, maxIter=5000)
+            xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
+            assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
+        assert c.describe()["small_system_cluster_kernel"]
     finally:
         c.close()
