@@ -175,22 +175,41 @@ def make_system(args, n, rank, pinned=None, dist=None):
         s = mg.bcc_poly(nx, ny, nz)
         return s, s.addr.nCells, time.time() - t0
     box = [None]
+    cache = args.poly_cache and os.path.join(args.poly_cache, f"b200poly_{nx}_{ny}_{nz}_{n}")
     if rank == 0:
-        full = mg.bcc_poly(nx, ny, nz)
-        c2p = mg.partition_rcb(full.xyz, n)
-        subs = mg.decompose(full, c2p, n)
-        del full
-        d = tempfile.mkdtemp(prefix="b200poly_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-        for r, sub in enumerate(subs):
-            with open(os.path.join(d, f"rank{r}.pkl"), "wb") as f:
-                pickle.dump(sub, f, protocol=4)
-        box[0] = d
-        del subs
+        if cache and os.path.exists(os.path.join(cache, "DONE")):
+            box[0] = cache
+        else:
+            # the other ranks wait: give the generator every host core (torchrun pins OMP to 1/N of them)
+            try:
+                import ctypes
+                gomp = ctypes.CDLL("libgomp.so.1")
+                nthr_old = gomp.omp_get_max_threads()
+                gomp.omp_set_num_threads(min(os.cpu_count() or 1, 64))
+            except Exception:
+                gomp = None
+            full = mg.bcc_poly(nx, ny, nz)
+            c2p = mg.partition_rcb(full.xyz, n)
+            subs = mg.decompose(full, c2p, n)
+            del full
+            if gomp is not None:
+                gomp.omp_set_num_threads(nthr_old)
+            if cache:
+                os.makedirs(cache, exist_ok=True)
+                d = cache
+            else:
+                d = tempfile.mkdtemp(prefix="b200poly_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            for r, sub in enumerate(subs):
+                with open(os.path.join(d, f"rank{r}.pkl"), "wb") as f:
+                    pickle.dump(sub, f, protocol=4)
+            open(os.path.join(d, "DONE"), "w").close()
+            box[0] = d
+            del subs
     dist.broadcast_object_list(box, src=0)
     with open(os.path.join(box[0], f"rank{rank}.pkl"), "rb") as f:
         s = pickle.load(f)
     dist.barrier()
-    if rank == 0:
+    if rank == 0 and not cache:
         import shutil
         shutil.rmtree(box[0], ignore_errors=True)
     return s, 2 * nx * ny * nz, time.time() - t0
@@ -518,6 +537,8 @@ def main():
     ap.add_argument("--block", type=int, nargs=3, default=None,
                     help="development only: cells per GPU (weak) / global mesh (strong) instead of the BASELINE sizes")
     ap.add_argument("--poly", type=int, nargs=3, default=list(POLY_LATTICE), help="BCC lattice of --workload poly")
+    ap.add_argument("--poly-cache", default=None,
+                    help="directory in which the decomposed --workload poly sub-meshes are kept between runs")
     ap.add_argument("--precond", default=PRECOND, choices=["none", "diagonal", "DIC", "DIC-exact"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

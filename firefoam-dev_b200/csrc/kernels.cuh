@@ -1465,6 +1465,313 @@ __global__ void __launch_bounds__(kSmallBlock, 1) k_pcg_small(SmallArgs a) {
     if (c.cta == 0 && threadIdx.x == 0) *a.S = sS;
 }
 
+// ---- on-chip variant of the whole-solve kernel -------------------------------------------------
+// k_pcg_small keeps matrix and vectors in L2: every phase pays 1-3 dependent L2 round trips after the
+// L1 flush of the cluster barrier (measured 9.3 us per PCG iteration on the 9 000-cell steckler
+// system).  When the system fits the cluster's shared memory (<= RPT*1024 rows per CTA, RPT <= 2) the
+// matrix rows (packed column + value), diag, rD and the two gathered vectors (pA, and wA for the
+// DIC-class sweeps) live in SHARED memory for the whole solve, the thread-private vectors (rA, A*pA,
+// previous pA) in registers, and neighbour values are read from the owning CTA's shared memory
+// over DSMEM (cluster.map_shared_rank).  Reductions push each CTA's partial into every CTA's shared
+// memory before the barrier, so after it every CTA sums local data.  Global memory is touched only
+// to load the system, to update psi (off the critical path) and to store the status block.
+// Row r is owned by thread (r mod T) of the cluster, slot r / T;  T = nCtas*1024.
+// Same arithmetic, same row-sum order, same scalar_step() as every other path.
+struct FastArgs {
+    int N, precond, nColours, W;   // W = max faces per row
+    const int* colourStart;
+    const int64_t* sliceBase;
+    const uint32_t* rowLen;
+    const int* col;
+    const double* val;
+    const double* diag;
+    const double* src;
+    double* psi;
+    Scalars* S;
+};
+
+__host__ __device__ inline size_t fast_smem_bytes(int RPT, int W) {
+    const size_t S = (size_t)RPT * kSmallBlock;
+    return S * ((size_t)W * 12 + 32) + sizeof(double) * 2 * kSmallMaxCtas * kNSums + 16;
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kSmallBlock, 1) k_pcg_small_fast(FastArgs a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ Scalars sS;
+    __shared__ double sh[kNSums][kSmallBlock / 32];
+    cgx::cluster_group cluster = cgx::this_cluster();
+    constexpr int S = RPT * kSmallBlock;
+    const int W = a.W, N = a.N;
+    double* sVal = reinterpret_cast<double*>(fsm);            // [W][S]
+    double* sP = sVal + (size_t)W * S;                        // [S] pA   (gathered by neighbours)
+    double* sW = sP + S;                                      // [S] wA / rD scratch (DIC-class sweeps)
+    double* sDg = sW + S;                                     // [S] diag
+    double* sRD = sDg + S;                                    // [S] rD
+    double* sPart = sRD + S;                                  // [2][kSmallMaxCtas][kNSums]
+    uint32_t* sCol = reinterpret_cast<uint32_t*>(sPart + 2 * kSmallMaxCtas * kNSums);   // [W][S] packed
+    const int nCtas = (int)cluster.num_blocks(), cta = (int)cluster.block_rank();
+    const int T = nCtas * kSmallBlock, tid = (int)threadIdx.x, gtid = cta * kSmallBlock + tid;
+    const bool dic = a.precond >= 2, diagp = a.precond == 1;
+    unsigned nred = 0;
+    if (tid == 0) sS = *a.S;
+
+    int nTot[RPT], nLow[RPT];
+    double rA[RPT], wv[RPT], pOwn[RPT];
+    // ---- load this thread's rows into shared memory ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+        nTot[k] = nLow[k] = 0;
+        rA[k] = wv[k] = pOwn[k] = 0.0;
+        sP[slot] = 0.0;
+        sW[slot] = 0.0;
+        sDg[slot] = 1.0;
+        sRD[slot] = 0.0;
+        if (r < N) {
+            const int64_t base = a.sliceBase[r >> 5] + (r & 31);
+            const uint32_t len = a.rowLen[r];
+            nTot[k] = (int)(len >> 16);
+            nLow[k] = (int)(len & 0xffffu);
+            for (int j = 0; j < nTot[k]; ++j) {
+                const int64_t e = base + 32 * (int64_t)j;
+                const int c = a.col[e];
+                const int kk = c / T, g = c - kk * T;
+                sCol[(size_t)j * S + slot] = ((uint32_t)(g >> 10) << 20) | (uint32_t)(kk * kSmallBlock + (g & (kSmallBlock - 1)));
+                sVal[(size_t)j * S + slot] = a.val[e];
+            }
+            sDg[slot] = a.diag[r];
+            sP[slot] = a.psi[r];            // first Amul gathers psi
+        }
+    }
+    cluster.sync();
+
+    auto gather = [&](double* arr, uint32_t packed) -> double {
+        return cluster.map_shared_rank(arr, packed >> 20)[packed & 0xfffffu];
+    };
+    // cluster-wide sums: push this CTA's partial into every CTA, barrier, sum locally in CTA order
+    auto reduce = [&](double* v, int nv, int step) {
+        const int lane = tid & 31, w = tid >> 5;
+        for (int i = 0; i < nv; ++i) {
+            const double s_ = warp_sum(v[i]);
+            if (lane == 0) sh[i][w] = s_;
+        }
+        __syncthreads();
+        double* buf = sPart + (size_t)(nred & 1u) * kSmallMaxCtas * kNSums;
+        if (w == 0) {
+            for (int i = 0; i < nv; ++i) {
+                double s_ = sh[i][lane];
+                s_ = warp_sum(s_);
+                s_ = __shfl_sync(0xffffffffu, s_, 0);
+                if (lane < nCtas) cluster.map_shared_rank(buf, lane)[cta * kNSums + i] = s_;
+            }
+        }
+        cluster.sync();
+        if (tid == 0) {
+            double g[kNSums];
+            for (int i = 0; i < kNSums; ++i) g[i] = 0.0;
+            for (int i = 0; i < nv; ++i) {
+                double t_ = 0.0;
+                for (int b = 0; b < nCtas; ++b) t_ = __dadd_rn(t_, buf[b * kNSums + i]);
+                g[i] = t_;
+            }
+            scalar_step(step, &sS, g);
+        }
+        nred++;
+        __syncthreads();
+    };
+    // DIC-class apply: wA -> sW (own slots), returns this thread's share of (wA, rA)
+    auto dic_apply = [&]() -> double {
+        double dot = 0.0;
+        const int C = a.nColours;
+        for (int c = 0; c < C; ++c) {
+            const int r0 = a.colourStart[c], r1 = a.colourStart[c + 1];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+                if (r >= r0 && r < r1) {
+                    const double d = sRD[slot];
+                    double w = __dmul_rn(d, rA[k]);
+                    for (int j = 0; j < nLow[k]; ++j)
+                        w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, sVal[(size_t)j * S + slot]),
+                                                    gather(sW, sCol[(size_t)j * S + slot])));
+                    sW[slot] = w;
+                    if (c == C - 1) dot = __dadd_rn(dot, __dmul_rn(w, rA[k]));
+                }
+            }
+            if (c + 1 < C) cluster.sync();
+        }
+        for (int c = C - 2; c >= 0; --c) {
+            cluster.sync();
+            const int r0 = a.colourStart[c], r1 = a.colourStart[c + 1];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+                if (r >= r0 && r < r1) {
+                    const double d = sRD[slot];
+                    double w = sW[slot];
+                    for (int j = nTot[k] - 1; j >= nLow[k]; --j)
+                        w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, sVal[(size_t)j * S + slot]),
+                                                    gather(sW, sCol[(size_t)j * S + slot])));
+                    sW[slot] = w;
+                    dot = __dadd_rn(dot, __dmul_rn(w, rA[k]));
+                }
+            }
+        }
+        return dot;
+    };
+
+    // ---- wA = A psi, sumA; gSum(psi) ------------------------------------------------------------------
+    double sa[RPT];
+    {
+        double s_[1] = {0.0};
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+            sa[k] = 0.0;
+            if (r < N) {
+                const double xr = sP[slot], d = sDg[slot];
+                double acc = __dmul_rn(d, xr), q = d;
+                for (int j = 0; j < nTot[k]; ++j) {
+                    const double v = sVal[(size_t)j * S + slot];
+                    acc = __dadd_rn(acc, __dmul_rn(v, gather(sP, sCol[(size_t)j * S + slot])));
+                    q = __dadd_rn(q, v);
+                }
+                wv[k] = acc;
+                sa[k] = q;
+                s_[0] = __dadd_rn(s_[0], xr);
+            }
+        }
+        reduce(s_, 1, STEP_SUMPSI);
+    }
+    {
+        double s_[2] = {0.0, 0.0};
+        const double xRef = sS.xRef;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = k * T + gtid;
+            if (r < N) {
+                const double w = wv[k], b = a.src[r];
+                const double t_ = __dmul_rn(sa[k], xRef);
+                s_[0] = __dadd_rn(s_[0], __dadd_rn(fabs(__dadd_rn(w, -t_)), fabs(__dadd_rn(b, -t_))));
+                const double rr = __dadd_rn(b, -w);
+                s_[1] = __dadd_rn(s_[1], fabs(rr));
+                rA[k] = rr;
+            }
+        }
+        reduce(s_, 2, STEP_NORM);
+    }
+    if (!sS.done) {
+        if (diagp) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int slot = k * kSmallBlock + tid;
+                if (k * T + gtid < N) sRD[slot] = __ddiv_rn(1.0, sDg[slot]);
+            }
+        } else if (dic) {
+            for (int c = 0; c < a.nColours; ++c) {      // calcReciprocalD: un-inverted rD staged in sW
+                const int r0 = a.colourStart[c], r1 = a.colourStart[c + 1];
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+                    if (r >= r0 && r < r1) {
+                        double d = sDg[slot];
+                        for (int j = 0; j < nLow[k]; ++j) {
+                            const double v = sVal[(size_t)j * S + slot];
+                            d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(v, v), gather(sW, sCol[(size_t)j * S + slot])));
+                        }
+                        sW[slot] = d;
+                    }
+                }
+                cluster.sync();
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int slot = k * kSmallBlock + tid;
+                if (k * T + gtid < N) sRD[slot] = __ddiv_rn(1.0, sW[slot]);
+            }
+            cluster.sync();      // everyone has consumed sW as rD scratch before the first sweep rewrites it
+        }
+        double s_[1] = {0.0};
+        if (dic) s_[0] = dic_apply();
+        else {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (k * T + gtid < N) {
+                    const double w = diagp ? __dmul_rn(sRD[k * kSmallBlock + tid], rA[k]) : rA[k];
+                    s_[0] = __dadd_rn(s_[0], __dmul_rn(w, rA[k]));
+                }
+        }
+        reduce(s_, 1, STEP_WARA);
+    }
+    // ---- PCG loop ------------------------------------------------------------------------------------
+    while (!sS.done) {
+        {
+            const bool first = (sS.nIter == 0);
+            const double beta = sS.beta, alpha = sS.alpha;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = k * T + gtid, slot = k * kSmallBlock + tid;
+                if (r < N) {
+                    double p = dic ? sW[slot] : (diagp ? __dmul_rn(sRD[slot], rA[k]) : rA[k]);
+                    if (!first) {
+                        a.psi[r] = __dadd_rn(a.psi[r], __dmul_rn(alpha, pOwn[k]));
+                        p = __dadd_rn(p, __dmul_rn(beta, pOwn[k]));
+                    }
+                    pOwn[k] = p;
+                    sP[slot] = p;
+                }
+            }
+        }
+        cluster.sync();
+        {
+            double s_[1] = {0.0};
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int slot = k * kSmallBlock + tid;
+                if (k * T + gtid < N) {
+                    double acc = __dmul_rn(sDg[slot], pOwn[k]);
+                    for (int j = 0; j < nTot[k]; ++j)
+                        acc = __dadd_rn(acc, __dmul_rn(sVal[(size_t)j * S + slot], gather(sP, sCol[(size_t)j * S + slot])));
+                    wv[k] = acc;
+                    s_[0] = __dadd_rn(s_[0], __dmul_rn(acc, pOwn[k]));
+                }
+            }
+            reduce(s_, 1, STEP_WAPA);
+        }
+        if (sS.done) break;
+        {
+            const double alpha = sS.alpha;
+            double s_[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (k * T + gtid < N) {
+                    const double rr = __dadd_rn(rA[k], -__dmul_rn(alpha, wv[k]));
+                    rA[k] = rr;
+                    s_[0] = __dadd_rn(s_[0], fabs(rr));
+                    if (diagp) s_[1] = __dadd_rn(s_[1], __dmul_rn(__dmul_rn(sRD[k * kSmallBlock + tid], rr), rr));
+                    else if (!dic) s_[1] = __dadd_rn(s_[1], __dmul_rn(rr, rr));
+                }
+            reduce(s_, 2, dic ? STEP_RES : STEP_RES_WARA);
+        }
+        if (dic && !sS.done) {
+            double s_[1];
+            s_[0] = dic_apply();
+            reduce(s_, 1, STEP_WARA);
+        }
+    }
+    if (sS.pendingPsi) {
+        const double alpha = sS.alpha;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = k * T + gtid;
+            if (r < N) a.psi[r] = __dadd_rn(a.psi[r], __dmul_rn(alpha, pOwn[k]));
+        }
+    }
+    if (cta == 0 && tid == 0) *a.S = sS;
+    cluster.sync();     // no CTA may exit while others can still read its shared memory
+}
+
 // ---- fvMatrix::flux() internal faces (OF-dev fvMatrix.C) --------------------
 __global__ void __launch_bounds__(kBlock)
 k_flux(int F, const int* __restrict__ l, const int* __restrict__ u,

@@ -96,6 +96,7 @@ struct DevPlan {
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
     int* colourStart = nullptr;   // device copy of h.colourStart (k_pcg_small)
+    int maxRowLen = 0;            // widest row (faces per cell)
     int nSlots = 0;
     // symmetric single-read layout (SymPlan)
     bool sym = false;
@@ -172,8 +173,9 @@ struct b200_ctx {
     bool disableWin = true;
     // single-launch cluster kernel for small systems (k_pcg_small): up to this many cells
     // (B200PCG_SMALL_N, 0 disables), cluster size 8 or 16 (B200PCG_SMALL_CTAS)
-    int smallN = 65536, smallCtas = 8;
-    bool usedSmall = false;
+    int smallN = 150000, smallCtas = 16;
+    bool usedSmall = false, usedFast = false;
+    bool disableFast = false;     // B200PCG_SMALL_FAST=0: always the L2-resident k_pcg_small
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
@@ -327,6 +329,9 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     RET(upload(ctx, &P.bStart, P.h.bStart));
     RET(upload(ctx, &P.bSlot, P.h.bSlot));
     RET(upload(ctx, &P.colourStart, P.h.colourStart));
+    P.maxRowLen = 0;
+    for (size_t sl = 0; sl + 1 < P.h.sliceBase.size(); ++sl)
+        P.maxRowLen = std::max(P.maxRowLen, (int)((P.h.sliceBase[sl + 1] - P.h.sliceBase[sl]) / 32));
     P.nSlots = (int)P.h.slotRow.size();
     // permuted (colour-major) orders put a row's earlier neighbours hundreds of MB upstream: the
     // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
@@ -687,18 +692,45 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     if (ctx->nranks == 1 && N > 0 && N <= ctx->smallN) {
         // small system: the whole solve in one launch of one thread-block cluster
         ctx->usedSmall = true;
+        ctx->usedFast = false;
+        // on-chip variant: matrix + gathered vectors in the cluster's shared memory (<= 2 rows per thread)
+        int fastCtas = 0, fastRpt = 0;
+        if (!ctx->disableFast) {
+            for (int nc : {1, 2, 4, 8, 16}) {
+                const int rpt = (N + nc * kSmallBlock - 1) / (nc * kSmallBlock);
+                if (rpt <= 2 && fast_smem_bytes(rpt, P.maxRowLen) <= (size_t)225 * 1024) {
+                    // prefer one row per thread when a larger cluster offers it
+                    if (fastCtas == 0 || (fastRpt == 2 && rpt == 1)) { fastCtas = nc; fastRpt = rpt; }
+                    if (rpt == 1) break;
+                }
+            }
+        }
         SmallArgs a{N, ctl->precond, P.h.nColours, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
                     ctx->diag, ctx->src, ctx->psi, ctx->r, ctx->p, ctx->w, ctx->rD, S, ctx->partials};
+        FastArgs fa{N, ctl->precond, P.h.nColours, P.maxRowLen, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
+                    ctx->diag, ctx->src, ctx->psi, S};
         int nCtas = std::min(ctx->smallCtas, (N + kSmallBlock - 1) / kSmallBlock);
-        if (nCtas > 8) {
-            nCtas = 16;
-            CU(cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        } else if (nCtas > 4) nCtas = 8;
+        if (nCtas > 8) nCtas = 16;
+        else if (nCtas > 4) nCtas = 8;
         else if (nCtas > 2) nCtas = 4;
+        size_t dynSmem = 0;
+        if (fastCtas) {
+            ctx->usedFast = true;
+            nCtas = fastCtas;
+            dynSmem = fast_smem_bytes(fastRpt, P.maxRowLen);
+            if (fastRpt == 1) CU(cudaFuncSetAttribute(k_pcg_small_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
+            else CU(cudaFuncSetAttribute(k_pcg_small_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
+        }
+        if (nCtas > 8) {
+            CU(cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CU(cudaFuncSetAttribute(k_pcg_small_fast<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CU(cudaFuncSetAttribute(k_pcg_small_fast<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)nCtas);
         cfg.blockDim = dim3(kSmallBlock);
         cfg.stream = ctx->sc;
+        cfg.dynamicSmemBytes = dynSmem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)nCtas;
@@ -708,7 +740,9 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         cfg.numAttrs = 1;
         CU(cudaEventRecord(ctx->ev[1], ctx->sc));
         prof_begin(ctx, PC_SMALL);
-        CU(cudaLaunchKernelEx(&cfg, k_pcg_small, a));
+        if (fastCtas && fastRpt == 1) CU(cudaLaunchKernelEx(&cfg, k_pcg_small_fast<1>, fa));
+        else if (fastCtas) CU(cudaLaunchKernelEx(&cfg, k_pcg_small_fast<2>, fa));
+        else CU(cudaLaunchKernelEx(&cfg, k_pcg_small, a));
         prof_end(ctx, PC_SMALL);
         ctx->launches++;
         CU(cudaEventRecord(ctx->ev[2], ctx->sc));
@@ -880,6 +914,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         c->disableWin = (std::string(e2) != "win");
     }
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
+    if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
@@ -1327,11 +1362,11 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"nranks\": %d, \"peer_allreduce\": %s, \"nCells\": %d, \"nFaces\": %d, \"nSlots\": %d, \"sms\": %d, "
                   "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
                   "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
-                  "\"small_system_cluster_kernel\": %s, \"small_n_max\": %d}",
+                  "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
-                  P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->smallN);
+                  P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN);
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

@@ -31,20 +31,25 @@ def has_gpu():
         return False
 
 
-@pytest.fixture(scope="session", params=["multi-kernel", "cluster-kernel"])
+@pytest.fixture(scope="session", params=["multi-kernel", "cluster-on-chip", "cluster-l2"])
 def ctx(request):
-    """Every parity test runs twice: through the multi-kernel PCG loop (the path large systems
-    take; forced here with B200PCG_SMALL_N=0) and through the single-launch thread-block-cluster
-    kernel that systems of up to 65 536 cells take by default."""
+    """Every parity test runs three times: through the multi-kernel PCG loop (the path large systems
+    take; forced here with B200PCG_SMALL_N=0), through the single-launch thread-block-cluster kernel
+    with the system in shared memory / DSMEM (what systems of up to ~32 K cells take by default), and
+    through the cluster kernel with the system in L2 (what systems of up to 150 K cells take)."""
     from firefoam_dev_b200 import Context
-    old = os.environ.get("B200PCG_SMALL_N")
-    os.environ["B200PCG_SMALL_N"] = "0" if request.param == "multi-kernel" else "65536"
+    env = {"multi-kernel": {"B200PCG_SMALL_N": "0"},
+           "cluster-on-chip": {"B200PCG_SMALL_N": "150000", "B200PCG_SMALL_FAST": "1"},
+           "cluster-l2": {"B200PCG_SMALL_N": "150000", "B200PCG_SMALL_FAST": "0"}}[request.param]
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         c = Context()
     finally:
-        if old is None:
-            os.environ.pop("B200PCG_SMALL_N", None)
-        else:
-            os.environ["B200PCG_SMALL_N"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     yield c
     c.close()

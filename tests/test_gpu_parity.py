@@ -361,7 +361,7 @@ def _ctx_with_env(env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("mode,small", [("0", "0"), ("1", "0"), ("1", "65536")])
+@pytest.mark.parametrize("mode,small", [("0", "0"), ("1", "0"), ("1", "150000")])
 def test_rcm_renumbering_does_not_change_results(mode, small):
     """Rows renumbered by reverse Cuthill-McKee (forced) or not at all: assembly, Amul and flux stay
     bit-identical to the oracle, PCG + diagonal keeps the oracle's iteration counts, DIC-exact is
@@ -390,14 +390,15 @@ def test_rcm_renumbering_does_not_change_results(mode, small):
         c.close()
 
 
-@pytest.mark.parametrize("ctas", ["1", "4", "8", "16"])
-def test_cluster_kernel_sizes(ctas):
-    """k_pcg_small with every cluster size (16 is the non-portable maximum), on systems from one
-    cell to the 65 536-cell limit, all preconditioners, against the oracle."""
-    c = _ctx_with_env({"B200PCG_SMALL_CTAS": ctas, "B200PCG_SMALL_N": "65536"})
+@pytest.mark.parametrize("ctas,fast", [("1", "0"), ("4", "0"), ("8", "0"), ("16", "0"), ("16", "1")])
+def test_cluster_kernel_sizes(ctas, fast):
+    """k_pcg_small with every cluster size (16 is the non-portable maximum) and k_pcg_small_fast (one and
+    two rows per thread, 1..16 CTAs), on systems from a handful of cells to 64 000, all preconditioners,
+    against the oracle."""
+    c = _ctx_with_env({"B200PCG_SMALL_CTAS": ctas, "B200PCG_SMALL_N": "150000", "B200PCG_SMALL_FAST": fast})
     try:
         for s in (mg.hex_block(40, 40, 40), mg.hex_block(7, 5, 3), random_ldu(1000, 1.5, seed=9),
-                  mg.bcc_poly(9, 8, 10)):
+                  mg.bcc_poly(9, 8, 10), mg.hex_block(32, 31, 30), mg.hex_block(30, 20, 20), mg.bcc_poly(20, 20, 18)):
             for pre, exact in (("diagonal", False), ("none", False), ("DIC", True)):
                 xg, pg = solve_gpu(c, s, pre, tol=1e-7, maxIter=4000, exact=exact)
                 xc, pc = solve_cpu(s, pre, tol=1e-7, maxIter=4000)
