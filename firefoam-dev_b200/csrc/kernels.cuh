@@ -988,10 +988,12 @@ k_p(int N, double* __restrict__ psi, double* __restrict__ pA, const double* __re
 }
 #undef B200_Z
 
+// ZMODE 2 (DIC-class) with nFirst > 0 additionally runs the forward sweep of the FIRST colour (rows
+// [0, nFirst): no earlier neighbours, wA = rD*rA) in place, saving a launch and a pass over rA/rD;
+// wA (which held A*pA) is only overwritten after its own element has been consumed.
 template <int ZMODE>
 __global__ void __launch_bounds__(kBlock)
-k_r(int N, double* __restrict__ rA, const double* __restrict__ wA, const double* __restrict__ rD,
-    Reduce R) {
+k_r(int N, double* __restrict__ rA, double* wA, const double* __restrict__ rD, int nFirst, Reduce R) {
     if (R.S->done) return;
     const double alpha = R.S->alpha;
     double s[2] = {0.0, 0.0};
@@ -1001,6 +1003,13 @@ k_r(int N, double* __restrict__ rA, const double* __restrict__ wA, const double*
           r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
           r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
           reinterpret_cast<double2*>(rA)[i] = r;
+          if (ZMODE == 2 && 2 * i < nFirst) {
+              const double2 d = reinterpret_cast<const double2*>(rD)[i];
+              double2 z = w;
+              z.x = __dmul_rn(d.x, r.x);
+              if (2 * i + 1 < nFirst) z.y = __dmul_rn(d.y, r.y);
+              reinterpret_cast<double2*>(wA)[i] = z;
+          }
           s[0] = __dadd_rn(s[0], __dadd_rn(fabs(r.x), fabs(r.y)));
           if (ZMODE == 1) {
               const double2 d = reinterpret_cast<const double2*>(rD)[i];
@@ -1012,6 +1021,7 @@ k_r(int N, double* __restrict__ rA, const double* __restrict__ wA, const double*
           } },
         { const double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
           rA[i] = r;
+          if (ZMODE == 2 && i < nFirst) wA[i] = __dmul_rn(rD[i], r);
           s[0] = __dadd_rn(s[0], fabs(r));
           if (ZMODE == 1) s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(rD[i], r), r));
           else if (ZMODE == 0) s[1] = __dadd_rn(s[1], __dmul_rn(r, r)); })

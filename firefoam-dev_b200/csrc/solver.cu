@@ -177,6 +177,7 @@ struct b200_ctx {
     bool usedSmall = false, usedFast = false;
     bool disableFast = false;     // B200PCG_SMALL_FAST=0: always the L2-resident k_pcg_small
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
+    bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
@@ -559,7 +560,7 @@ int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* 
 
 // precondition rA -> wA and form wArA = (wA, rA) [STEP_WARA]; used once before the loop for every
 // mode and, for the DIC-class modes, after every iteration (none/diagonal fuse it into k_r).
-int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
+int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond, bool firstColourDone = false) {
     const int N = ctx->N;
     const int gv = grid_for(ctx, (N + 1) / 2);
     if (precond == B200_PRECOND_NONE) {
@@ -572,7 +573,7 @@ int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond) {
         LAUNCH(PC_PRECOND_DOT, k, gv, N, ctx->rD, ctx->r, ctx->w, R);
     } else {
         const int C = P.h.nColours;
-        for (int k = 0; k < C; ++k) {
+        for (int k = firstColourDone ? 1 : 0; k < C; ++k) {   // (first colour: fused into k_r<2>)
             const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
             const bool last = (k == C - 1);
             Reduce R = mkR(ctx, (last && C == 1) ? STEP_WARA : STEP_NONE);
@@ -617,19 +618,21 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
     if (precond == B200_PRECOND_NONE) {
         Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<0>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, 0, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else if (precond == B200_PRECOND_DIAGONAL) {
         Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<1>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, 0, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else {
         Reduce R = mkR(ctx, STEP_RES);
+        // with >= 2 colours the first colour's forward sweep (wA = rD*rA) rides along in k_r
+        const bool fuse = P.h.nColours >= 2 && !ctx->noFuseFirst;
         auto k = k_r<2>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, fuse ? P.h.colourStart[1] : 0, R);
         RET(reduce_post(ctx, STEP_RES));
-        RET(enqueue_precondition(ctx, P, precond));
+        RET(enqueue_precondition(ctx, P, precond, fuse));
     }
     return B200_OK;
 }
@@ -916,6 +919,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
+    if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
