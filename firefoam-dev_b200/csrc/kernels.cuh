@@ -467,6 +467,90 @@ k_spmv_sym(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
     if (DOT) reduce_finish<1>(dot, R);
 }
 
+// ---- ranked variant of the symmetric Amul (renumbered natural plans) ---------------------------
+// Rows follow the plan's RCM order, so the [lower | upper] split of the single-read layout is not
+// OpenFOAM's visiting order of the row.  Every entry carries the rank of its face among the row's
+// faces (ascending face index = the order in which lduMatrix::Amul's face loop updates the cell):
+// the products are staged by rank in a thread-private shared-memory column and added in rank order,
+// which makes the row sum bit-identical to the CPU loop on ANY row order.  <= 16 faces per row.
+constexpr int kMaxRanked = 16;
+template <bool INIT, bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv_sym_ranked(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
+                  const int* __restrict__ uCol, const double* __restrict__ uVal,
+                  const uint32_t* __restrict__ lRef, const uint8_t* __restrict__ lRank,
+                  const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
+                  double* __restrict__ sA, Reduce R) {
+    if (R.S->done) return;
+    __shared__ double stage[kBlock / 32][kMaxRanked][32];   // 32 KB; column [.][.][lane] is private to a thread
+    constexpr int B = kSymBatch;
+    double dot[1] = {0.0};
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*my)[32] = stage[warp];
+    const int nSlices = (N + 31) >> 5;
+    const int warpsPerGrid = (gridDim.x * kBlock) >> 5;
+    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) >> 5; s < nSlices; s += warpsPerGrid) {
+        const int r = (s << 5) + (int)lane;
+        if (r < N) {
+            const uint32_t len = rowLen[r];
+            const int nL = (int)(len & 0xffffu), nT = (int)(len >> 16), nU = nT - nL;
+            const uint32_t lb = (uint32_t)s * strideL + lane, ub = (uint32_t)s * strideU + lane;
+            const double xr = x[r];
+            const double d = diag[r];
+            for (int pass = 0; pass < (INIT ? 2 : 1); ++pass) {   // pass 1 (INIT): sumA, values by rank
+                for (int j0 = 0; j0 < nL; j0 += B) {
+                    uint32_t pk[B], rk[B];
+                    double v[B], xv[B];
+#pragma unroll
+                    for (int k = 0; k < B; ++k) {
+                        const bool on = j0 + k < nL;
+                        pk[k] = on ? lRef[lb + 32u * (j0 + k)] : 0u;
+                        rk[k] = on ? (uint32_t)lRank[lb + 32u * (j0 + k)] : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < B; ++k) {
+                        const bool on = j0 + k < nL;
+                        const uint32_t a = pk[k] >> 5;
+                        v[k] = on ? uVal[(a >> 5) * strideU + ((pk[k] & 31u) << 5) + (a & 31u)] : 0.0;
+                        xv[k] = (on && pass == 0) ? __ldg(&x[a]) : 1.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < B; ++k)
+                        if (j0 + k < nL) my[rk[k]][lane] = pass == 0 ? __dmul_rn(v[k], xv[k]) : v[k];
+                }
+                for (int j0 = 0; j0 < nU; j0 += B) {
+                    int cc[B];
+                    double v[B], xv[B];
+#pragma unroll
+                    for (int k = 0; k < B; ++k) {
+                        const bool on = j0 + k < nU;
+                        cc[k] = on ? uCol[ub + 32u * (j0 + k)] : 0;
+                        v[k] = on ? uVal[ub + 32u * (j0 + k)] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < B; ++k)
+                        xv[k] = (j0 + k < nU && pass == 0) ? __ldg(&x[cc[k] & 0x7ffffff]) : 1.0;
+#pragma unroll
+                    for (int k = 0; k < B; ++k)
+                        if (j0 + k < nU) my[(uint32_t)cc[k] >> 27][lane] = pass == 0 ? __dmul_rn(v[k], xv[k]) : v[k];
+                }
+                if (pass == 0) {
+                    double acc = __dmul_rn(d, xr);
+                    for (int j = 0; j < nT; ++j) acc = __dadd_rn(acc, my[j][lane]);
+                    y[r] = acc;
+                    if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+                } else {
+                    double sa = d;
+                    for (int j = 0; j < nT; ++j) sa = __dadd_rn(sa, my[j][lane]);
+                    sA[r] = sa;
+                }
+            }
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
 // ---- TMA-staged variant of the symmetric Amul -------------------------------------------------
 // Same arithmetic and row order as k_spmv_sym, but the streaming operands of a chunk of 256 rows
 // (row lengths, lower references, upper columns + values, x, diag: all contiguous in the sliced
@@ -991,9 +1075,19 @@ k_p(int N, double* __restrict__ psi, double* __restrict__ pA, const double* __re
 // ZMODE 2 (DIC-class) with nFirst > 0 additionally runs the forward sweep of the FIRST colour (rows
 // [0, nFirst): no earlier neighbours, wA = rD*rA) in place, saving a launch and a pass over rA/rD;
 // wA (which held A*pA) is only overwritten after its own element has been consumed.
+// Rows of the first colour: [segStart[t*C], segStart[t*C + 1]) in every tile t = row >> tileShift
+// (one tile: tileShift = 31).  segStart == nullptr: no fusion.
+struct FirstColour {
+    const int* segStart;
+    int C, tileShift;
+    __device__ __forceinline__ bool has(int row) const {
+        return segStart != nullptr && row < __ldg(&segStart[(row >> tileShift) * C + 1]);
+    }
+};
+
 template <int ZMODE>
 __global__ void __launch_bounds__(kBlock)
-k_r(int N, double* __restrict__ rA, double* wA, const double* __restrict__ rD, int nFirst, Reduce R) {
+k_r(int N, double* __restrict__ rA, double* wA, const double* __restrict__ rD, FirstColour fc, Reduce R) {
     if (R.S->done) return;
     const double alpha = R.S->alpha;
     double s[2] = {0.0, 0.0};
@@ -1003,12 +1097,16 @@ k_r(int N, double* __restrict__ rA, double* wA, const double* __restrict__ rD, i
           r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
           r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
           reinterpret_cast<double2*>(rA)[i] = r;
-          if (ZMODE == 2 && 2 * i < nFirst) {
-              const double2 d = reinterpret_cast<const double2*>(rD)[i];
-              double2 z = w;
-              z.x = __dmul_rn(d.x, r.x);
-              if (2 * i + 1 < nFirst) z.y = __dmul_rn(d.y, r.y);
-              reinterpret_cast<double2*>(wA)[i] = z;
+          if (ZMODE == 2) {
+              const bool f0 = fc.has(2 * i);
+              const bool f1 = fc.has(2 * i + 1);
+              if (f0 || f1) {
+                  const double2 d = reinterpret_cast<const double2*>(rD)[i];
+                  double2 z = w;
+                  if (f0) z.x = __dmul_rn(d.x, r.x);
+                  if (f1) z.y = __dmul_rn(d.y, r.y);
+                  reinterpret_cast<double2*>(wA)[i] = z;
+              }
           }
           s[0] = __dadd_rn(s[0], __dadd_rn(fabs(r.x), fabs(r.y)));
           if (ZMODE == 1) {
@@ -1021,7 +1119,7 @@ k_r(int N, double* __restrict__ rA, double* wA, const double* __restrict__ rD, i
           } },
         { const double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
           rA[i] = r;
-          if (ZMODE == 2 && i < nFirst) wA[i] = __dmul_rn(rD[i], r);
+          if (ZMODE == 2 && fc.has(i)) wA[i] = __dmul_rn(rD[i], r);
           s[0] = __dadd_rn(s[0], fabs(r));
           if (ZMODE == 1) s[1] = __dadd_rn(s[1], __dmul_rn(__dmul_rn(rD[i], r), r));
           else if (ZMODE == 0) s[1] = __dadd_rn(s[1], __dmul_rn(r, r)); })
@@ -1048,12 +1146,25 @@ k_psi_final(int N, double* __restrict__ psi, const double* __restrict__ pA, cons
 //   calcReciprocalD:  rD[u] -= upper*upper/rD[l]         (faces ascending)
 //   forward:          wA[u] -= rD[u]*upper*wA[l]         (faces ascending)
 //   backward:         wA[l] -= rD[l]*upper*wA[u]         (faces descending)
+// Rows of one colour: segment (tile t, colour c) = [segStart[t*C + c], segStart[t*C + c + 1]) for every
+// tile (plan.hpp); work item w = (tile, block-in-segment), `bps` blocks share one segment.  With one
+// tile and bps == gridDim.x this is the plain grid-stride loop over the colour's row range.
+struct ColourRows {
+    const int* segStart;
+    int C, c, nTiles, bps;
+};
+#define B200_FOR_COLOUR_ROWS(CR, r)                                                                  \
+    for (int w_ = blockIdx.x; w_ < (CR).nTiles * (CR).bps; w_ += gridDim.x)                          \
+        for (int t_ = w_ / (CR).bps, e_ = (CR).segStart[t_ * (CR).C + (CR).c + 1],                    \
+                 r = (CR).segStart[t_ * (CR).C + (CR).c] + (w_ - t_ * (CR).bps) * kBlock + (int)threadIdx.x; \
+             r < e_; r += (CR).bps * kBlock)
+
 __global__ void __launch_bounds__(kBlock)
-k_dic_calc_rd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+k_dic_calc_rd(ColourRows cr, const int64_t* __restrict__ sliceBase,
               const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
               const double* __restrict__ val, const double* __restrict__ diag,
               double* __restrict__ rD) {
-    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+    B200_FOR_COLOUR_ROWS(cr, r) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const int nLower = (int)(rowLen[r] & 0xffffu);
         double d = diag[r];
@@ -1070,13 +1181,13 @@ k_dic_calc_rd(int r0, int r1, const int64_t* __restrict__ sliceBase,
 // forward sweep over one colour.  DOT: this colour's wA is final (last colour) -> add (wA, rA).
 template <bool DOT>
 __global__ void __launch_bounds__(kBlock)
-k_dic_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+k_dic_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
           const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
           const double* __restrict__ val, const double* __restrict__ rD,
           const double* __restrict__ rA, double* wA, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
-    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+    B200_FOR_COLOUR_ROWS(cr, r) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const int nLower = (int)(rowLen[r] & 0xffffu);
         const double d = rD[r];
@@ -1094,13 +1205,13 @@ k_dic_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase,
 
 // backward sweep over one colour; wA of this colour becomes final -> always add (wA, rA).
 __global__ void __launch_bounds__(kBlock)
-k_dic_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase,
+k_dic_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
           const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
           const double* __restrict__ val, const double* __restrict__ rD,
           const double* __restrict__ rA, double* wA, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
-    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+    B200_FOR_COLOUR_ROWS(cr, r) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const uint32_t len = rowLen[r];
         const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);

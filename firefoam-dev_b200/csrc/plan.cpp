@@ -196,7 +196,7 @@ int32_t colour_levels(int32_t N, int32_t F, const int32_t* l, const int32_t* u,
 }  // namespace
 
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
-                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P, Renumber renumber) {
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P, Renumber renumber, int32_t tileRows) {
     if (N < 0 || F < 0 || nIfaces < 0) return "negative size";
     if (F > 0 && (!l || !u)) return "null lowerAddr/upperAddr";
     if (nIfaces > 0 && !ifaces) return "null interface list";
@@ -269,12 +269,30 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
         for (int32_t k = 0; k < P.nColours; ++k) P.colourStart[k + 1] += P.colourStart[k];
         P.perm.resize((size_t)N);
         P.iperm.resize((size_t)N);
-        std::vector<int32_t> pos(P.colourStart.begin(), P.colourStart.end() - 1);
-        for (int32_t k = 0; k < N; ++k) {  // stable: baseOrder (natural / RCM) order inside a colour
+        // tiles of `tileRows` consecutive base-order cells (multicolour only, power of two, >= 2 tiles)
+        const int32_t C = P.nColours;
+        int32_t tr = 0;
+        if (ordering == Ordering::MultiColour && tileRows > 0 && N > 2 * (int64_t)tileRows) {
+            tr = 32;
+            while (tr < tileRows) tr <<= 1;
+        }
+        P.tileRows = tr;
+        P.nTiles = tr ? (int32_t)(((int64_t)N + tr - 1) / tr) : 1;
+        P.segStart.assign((size_t)P.nTiles * C + 1, 0);
+        auto tileOf = [&](int32_t k) { return tr ? k / tr : 0; };
+        for (int32_t k = 0; k < N; ++k) {
             const int32_t c = baseOrder.empty() ? k : baseOrder[k];
-            int32_t r = pos[colour[c]]++;
+            P.segStart[(size_t)tileOf(k) * C + colour[c] + 1]++;
+        }
+        for (size_t i = 0; i + 1 < P.segStart.size(); ++i) P.segStart[i + 1] += P.segStart[i];
+        std::vector<int32_t> pos(P.segStart.begin(), P.segStart.end() - 1);
+        P.rowColour.resize((size_t)N);
+        for (int32_t k = 0; k < N; ++k) {  // stable: base (natural / RCM) order inside a (tile, colour) segment
+            const int32_t c = baseOrder.empty() ? k : baseOrder[k];
+            int32_t r = pos[(size_t)tileOf(k) * C + colour[c]]++;
             P.perm[r] = c;
             P.iperm[c] = r;
+            P.rowColour[r] = colour[c];
         }
     }
     const bool ident = P.perm.empty();
@@ -319,15 +337,21 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             // ascending face order (OpenFOAM's visiting order) -- no [earlier | later] grouping,
             // which would change the order of the row sum.
             const bool grouped = !(ordering == Ordering::Natural && !ident);
+            // "earlier" = eliminated earlier: smaller row index, or -- in a (tiled) multicolour order,
+            // where storage order and elimination order differ -- an earlier colour
+            const bool byColour = !P.rowColour.empty();
+            auto earlier = [&](int32_t other) {
+                return byColour ? P.rowColour[other] < P.rowColour[r] : other < r;
+            };
             for (auto& fe : ent)
-                if (grouped && fe.second < r) {
+                if (grouped && earlier(fe.second)) {
                     P.col[base + 32 * (int64_t)j] = fe.second;
                     P.faceOf[base + 32 * (int64_t)j] = fe.first;
                     ++j;
                     ++nLower;
                 }
             for (auto& fe : ent)
-                if (!grouped || fe.second > r) {
+                if (!grouped || !earlier(fe.second)) {
                     P.col[base + 32 * (int64_t)j] = fe.second;
                     P.faceOf[base + 32 * (int64_t)j] = fe.first;
                     ++j;
@@ -344,19 +368,32 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
     }
 
     // ---- symmetric single-read layout -----------------------------------------------------
-    {
+    // Built from the cell-face lists, split by ROW INDEX (lower = smaller index: that row's thread
+    // streamed the value moments earlier), whatever grouping the full-row ELL above uses.  Each group
+    // in ascending face order: in the natural order that is OpenFOAM's visiting order of the whole row.
+    // Not for level orders (neighbours far upstream) nor renumbered natural plans (the row sum must
+    // stay in pure face order there, which a [lower | upper] split does not give).
+    const bool ranked = (ordering == Ordering::Natural && !ident);
+    if (N > 0 && N <= (1 << 27) && ordering != Ordering::Levels) {
         SymPlan& Sp = P.sym;
+        Sp.rowLen.assign((size_t)N, 0u);
         int64_t wU = 0, wL = 0;
+#pragma omp parallel for schedule(static) reduction(max : wU, wL)
         for (int32_t r = 0; r < N; ++r) {
-            const int64_t nL = P.rowLen[r] & 0xffffu, nT = P.rowLen[r] >> 16;
-            wU = std::max(wU, nT - nL);
-            wL = std::max(wL, nL);
+            const int32_t c = cellOf(r);
+            int32_t nLo = 0, nT = 0;
+            for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e, ++nT)
+                if (rowOf(cf.other[e]) < r) ++nLo;
+            Sp.rowLen[r] = (uint32_t)nLo | ((uint32_t)nT << 16);
+            wU = std::max<int64_t>(wU, nT - nLo);
+            wL = std::max<int64_t>(wL, nLo);
         }
         const int64_t nU = (int64_t)P.nSlices * 32 * wU, nL = (int64_t)P.nSlices * 32 * wL;
-        // (a renumbered Natural plan has no [lower | upper] split to build the references from)
-        const bool ok = (N > 0) && (N <= (1 << 27)) && wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL &&
-                        !(ordering == Ordering::Natural && !ident);
-        if (ok) {
+        int64_t wT = 0;
+        for (int32_t r = 0; r < N && ranked; ++r) wT = std::max<int64_t>(wT, Sp.rowLen[r] >> 16);
+        if (wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL && (!ranked || wT <= 16)) {
+            Sp.ranked = ranked;
+            if (ranked) Sp.lRank.assign((size_t)nL, 0);
             Sp.WU = (int32_t)wU;
             Sp.WL = (int32_t)wL;
             Sp.nU = nU;
@@ -364,26 +401,55 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             Sp.uCol.assign((size_t)nU, 0);
             Sp.uFace.assign((size_t)nU, -1);
             Sp.lRef.assign((size_t)nL, 0);
-#pragma omp parallel for schedule(static)
-            for (int32_t r = 0; r < N; ++r) {
-                const int64_t fb = P.sliceBase[r / 32] + (r % 32);
-                const int32_t nLo = (int32_t)(P.rowLen[r] & 0xffffu), nT = (int32_t)(P.rowLen[r] >> 16);
-                const int64_t ub = (int64_t)(r / 32) * 32 * wU + (r % 32);
-                const int64_t lb = (int64_t)(r / 32) * 32 * wL + (r % 32);
-                for (int32_t j = nLo; j < nT; ++j) {
-                    Sp.uCol[ub + 32 * (int64_t)(j - nLo)] = P.col[fb + 32 * (int64_t)j];
-                    Sp.uFace[ub + 32 * (int64_t)(j - nLo)] = P.faceOf[fb + 32 * (int64_t)j];
+#pragma omp parallel
+            {
+                std::vector<std::pair<int32_t, int32_t>> ent;  // (face, other row)
+                // pass 1: upper entries of every row
+#pragma omp for schedule(static)
+                for (int32_t r = 0; r < N; ++r) {
+                    const int32_t c = cellOf(r);
+                    ent.clear();
+                    for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e)
+                        ent.emplace_back(cf.face[e], rowOf(cf.other[e]));
+                    if (!ident) std::sort(ent.begin(), ent.end());
+                    const int64_t ub = (int64_t)(r / 32) * 32 * wU + (r % 32);
+                    int64_t j = 0;
+                    uint32_t rank = 0;
+                    for (auto& fe : ent) {
+                        if (fe.second > r) {
+                            Sp.uCol[ub + 32 * j] = fe.second | (ranked ? (int32_t)(rank << 27) : 0);
+                            Sp.uFace[ub + 32 * j] = fe.first;
+                            ++j;
+                        }
+                        ++rank;
+                    }
+                    for (; j < wU; ++j) Sp.uCol[ub + 32 * j] = r;
                 }
-                for (int64_t jj = nT - nLo; jj < wU; ++jj) Sp.uCol[ub + 32 * jj] = r;
-                for (int32_t j = 0; j < nLo; ++j) {
-                    const int32_t a = P.col[fb + 32 * (int64_t)j], f = P.faceOf[fb + 32 * (int64_t)j];
-                    // q = position of face f among the upper entries of row a
-                    const int64_t ab = P.sliceBase[a / 32] + (a % 32);
-                    const int32_t aL = (int32_t)(P.rowLen[a] & 0xffffu), aT = (int32_t)(P.rowLen[a] >> 16);
-                    int32_t q = 0;
-                    for (int32_t k = aL; k < aT; ++k)
-                        if (P.faceOf[ab + 32 * (int64_t)k] == f) { q = k - aL; break; }
-                    Sp.lRef[lb + 32 * (int64_t)j] = ((uint32_t)a << 5) | (uint32_t)q;
+                // pass 2: lower entries as references (owner row a << 5 | q-th upper entry of a)
+#pragma omp for schedule(static)
+                for (int32_t r = 0; r < N; ++r) {
+                    const int32_t c = cellOf(r);
+                    ent.clear();
+                    for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e)
+                        ent.emplace_back(cf.face[e], rowOf(cf.other[e]));
+                    if (!ident) std::sort(ent.begin(), ent.end());
+                    const int64_t lb = (int64_t)(r / 32) * 32 * wL + (r % 32);
+                    int64_t j = 0;
+                    uint32_t rank = 0;
+                    for (auto& fe : ent) {
+                        if (fe.second < r) {
+                            const int32_t a = fe.second;
+                            const int64_t ab = (int64_t)(a / 32) * 32 * wU + (a % 32);
+                            const int32_t aU = (int32_t)(Sp.rowLen[a] >> 16) - (int32_t)(Sp.rowLen[a] & 0xffffu);
+                            int32_t q = 0;
+                            for (int32_t k = 0; k < aU; ++k)
+                                if (Sp.uFace[ab + 32 * (int64_t)k] == fe.first) { q = k; break; }
+                            Sp.lRef[lb + 32 * j] = ((uint32_t)a << 5) | (uint32_t)q;
+                            if (ranked) Sp.lRank[lb + 32 * j] = (uint8_t)rank;
+                            ++j;
+                        }
+                        ++rank;
+                    }
                 }
             }
             Sp.valid = true;

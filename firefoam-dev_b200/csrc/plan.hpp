@@ -46,9 +46,18 @@ struct SymPlan {
     bool valid = false;
     int32_t WU = 0, WL = 0;       // uniform slice widths: entry j of row r at (r/32)*32*W + 32*j + r%32
     int64_t nU = 0, nL = 0;       // padded entry counts (< 2^31: 32-bit positions on the device)
+    std::vector<uint32_t> rowLen; // [N] nLower | nTotal<<16 with lower == smaller ROW INDEX (the full-row
+                                  // ELL of a tiled multicolour plan splits by colour instead)
     std::vector<int32_t> uCol;    // [nU] column (padding: the row itself)
     std::vector<int32_t> uFace;   // [nU] natural face, -1 padding
     std::vector<uint32_t> lRef;   // [nL] (owner row << 5) | q
+    // Ranked form (renumbered natural plans): the [lower | upper] split follows the RCM row index, which
+    // is NOT OpenFOAM's visiting order of the row, so every entry carries its rank = position of its face
+    // among the row's faces in ascending order; the kernel stages the products by rank and adds them in
+    // rank order: bit-identical row sums on a renumbered mesh.  Upper ranks ride in the top 5 bits of
+    // uCol (rows < 2^27), lower ranks in lRank.  Needs <= 16 faces per row.
+    bool ranked = false;
+    std::vector<uint8_t> lRank;   // [nL]
 };
 
 // Base cell order the row orders are derived from.  OpenFOAM meshes are normally bandwidth-reduced
@@ -70,7 +79,19 @@ struct HostPlan {
     std::vector<int32_t> perm;         // internal row -> natural cell  (empty == identity)
     std::vector<int32_t> iperm;        // natural cell -> internal row  (empty == identity)
     int32_t nColours = 1;
-    std::vector<int32_t> colourStart;  // [nColours+1] internal row offsets
+    std::vector<int32_t> colourStart;  // [nColours+1] cumulative rows per colour; the colour's row range
+                                       // when nTiles == 1
+    // Tiled multicolour order (DIC-class on large meshes): rows are ordered (tile of tileRows
+    // consecutive base-order cells, colour, base position) instead of colour-major, so that a row and
+    // its neighbours of the other colours stay a few thousand rows apart.  That keeps the symmetric
+    // single-read Amul layout usable in the DIC-class modes (a row's earlier neighbours were streamed
+    // moments ago: L2 hits), which a colour-major order (neighbours hundreds of MB upstream) does not.
+    // The preconditioner is unchanged: elimination order = colour order, whatever the storage order.
+    int32_t tileRows = 0;              // 0: one tile (plain colour-major)
+    int32_t nTiles = 1;
+    std::vector<int32_t> segStart;     // [nTiles*nColours + 1]: rows of (tile t, colour c) =
+                                       // [segStart[t*nColours + c], segStart[t*nColours + c + 1])
+    std::vector<int32_t> rowColour;    // [N] colour of every internal row (empty for Natural)
     // sliced ELL, both triangles
     int32_t nSlices = 0;
     int64_t nEntries = 0;              // padded
@@ -93,6 +114,6 @@ struct HostPlan {
 // Returns empty string on success, else an error message.
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
                        int32_t nIfaces, const IfaceIn* ifaces, HostPlan& out,
-                       Renumber renumber = Renumber::Off);
+                       Renumber renumber = Renumber::Off, int32_t tileRows = 0);
 
 }  // namespace b200

@@ -32,9 +32,10 @@ void* b200_debug_plan_build(int ordering, int32_t N, int32_t F, const int32_t* l
     return P;
 }
 void* b200_debug_plan_build2(int ordering, int renumber, int32_t N, int32_t F, const int32_t* l,
-                             const int32_t* u, int32_t nIfaces, const b200_dbg_iface* ifaces) {
+                             const int32_t* u, int32_t nIfaces, const b200_dbg_iface* ifaces, int32_t tileRows) {
     auto* P = new HostPlan();
-    g_err = build_plan((Ordering)ordering, N, F, l, u, nIfaces, (const IfaceIn*)ifaces, *P, (Renumber)renumber);
+    g_err = build_plan((Ordering)ordering, N, F, l, u, nIfaces, (const IfaceIn*)ifaces, *P, (Renumber)renumber,
+                       tileRows);
     if (!g_err.empty()) {
         delete P;
         return nullptr;
@@ -61,6 +62,8 @@ int64_t b200_debug_plan_get(void* h, const char* name, const void** ptr, int32_t
     V("sliceBase", P.sliceBase) V("rowLen", P.rowLen) V("col", P.col) V("faceOf", P.faceOf)
     V("nbrRank", P.nbrRank) V("patchStart", P.patchStart) V("slotRow", P.slotRow)
     V("bRow", P.bRow) V("bStart", P.bStart) V("bSlot", P.bSlot)
+    V("segStart", P.segStart) V("rowColour", P.rowColour) V("sym.rowLen", P.sym.rowLen)
+    V("sym.lRank", P.sym.lRank)
     V("sym.uCol", P.sym.uCol)
     V("sym.uFace", P.sym.uFace) V("sym.lRef", P.sym.lRef)
 #undef V
@@ -69,6 +72,8 @@ int64_t b200_debug_plan_get(void* h, const char* name, const void** ptr, int32_t
 int32_t b200_debug_plan_sym_valid(void* h) { return ((HostPlan*)h)->sym.valid ? 1 : 0; }
 int32_t b200_debug_plan_sym_wu(void* h) { return ((HostPlan*)h)->sym.WU; }
 int32_t b200_debug_plan_sym_wl(void* h) { return ((HostPlan*)h)->sym.WL; }
+int32_t b200_debug_plan_sym_ranked(void* h) { return ((HostPlan*)h)->sym.ranked ? 1 : 0; }
+int32_t b200_debug_plan_ntiles(void* h) { return ((HostPlan*)h)->nTiles; }
 int32_t b200_debug_plan_ncolours(void* h) { return ((HostPlan*)h)->nColours; }
 int64_t b200_debug_plan_nentries(void* h) { return ((HostPlan*)h)->nEntries; }
 }

@@ -96,6 +96,8 @@ struct DevPlan {
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
     int* colourStart = nullptr;   // device copy of h.colourStart (k_pcg_small)
+    int* segStart = nullptr;      // device copy of h.segStart ((tile, colour) row segments)
+    int tileShift = 31;           // log2(tileRows) of a tiled multicolour plan, else 31
     int maxRowLen = 0;            // widest row (faces per cell)
     int nSlots = 0;
     // symmetric single-read layout (SymPlan)
@@ -109,6 +111,8 @@ struct DevPlan {
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
     uint32_t* sLRef = nullptr;
+    uint8_t* sLRank = nullptr;    // ranked form (renumbered natural plans)
+    bool symRanked = false;
 };
 
 struct HostIface {
@@ -173,10 +177,14 @@ struct b200_ctx {
     bool disableWin = true;
     // single-launch cluster kernel for small systems (k_pcg_small): up to this many cells
     // (B200PCG_SMALL_N, 0 disables), cluster size 8 or 16 (B200PCG_SMALL_CTAS)
+    int tileRows = 0;             // B200PCG_TILE: rows per tile of large multicolour plans (0: colour-major).
+                                  // Opt-in: measured slower (profiles/r01_v7_dic_tiles.md) -- in a red-black order rows are
+                                  // all-upper or all-lower, so the uniform-width single-read layout is half padding
     int smallN = 150000, smallCtas = 16;
     bool usedSmall = false, usedFast = false;
     bool disableFast = false;     // B200PCG_SMALL_FAST=0: always the L2-resident k_pcg_small
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
+    bool enableRanked = false;  // B200PCG_SPMV=ranked
     bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
@@ -287,9 +295,10 @@ inline int grid_for(const b200_ctx* c, int64_t items, int perSM = 8) {
 void free_plan(DevPlan& P) {
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
-    dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart);
+    dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
     dev_free(P.sUCol); dev_free(P.sUFace);
-    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen);
+    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sLRank);
+    P.symRanked = false;
     P.sym = false;
     P.built = false;
     P.h = HostPlan();
@@ -316,8 +325,11 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     for (size_t k = 0; k < ifs.size(); ++k)
         ifs[k] = IfaceIn{ctx->hif[k].nbrRank, (int32_t)ctx->hif[k].faceCells.size(),
                          ctx->hif[k].faceCells.data()};
+    // large multicolour plans are tiled (plan.hpp); small ones stay colour-major (cluster kernels)
+    const int32_t tile = (ord == Ordering::MultiColour && ctx->tileRows > 0 &&
+                          ctx->N > std::max(ctx->nranks == 1 ? ctx->smallN : 0, 4 * ctx->tileRows)) ? ctx->tileRows : 0;
     std::string e = build_plan(ord, ctx->N, ctx->F, ctx->hl.data(), ctx->hu.data(),
-                               (int32_t)ifs.size(), ifs.data(), P.h, (Renumber)ctx->renumber);
+                               (int32_t)ifs.size(), ifs.data(), P.h, (Renumber)ctx->renumber, tile);
     if (!e.empty()) return fail(ctx, B200_EINVAL, "set_addressing: " + e);
     RET(upload(ctx, &P.sliceBase, P.h.sliceBase));
     RET(upload(ctx, &P.rowLen, P.h.rowLen));
@@ -330,13 +342,27 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     RET(upload(ctx, &P.bStart, P.h.bStart));
     RET(upload(ctx, &P.bSlot, P.h.bSlot));
     RET(upload(ctx, &P.colourStart, P.h.colourStart));
+    if (P.h.segStart.empty()) P.h.segStart = P.h.colourStart;   // Natural: one segment
+    RET(upload(ctx, &P.segStart, P.h.segStart));
+    P.tileShift = 31;
+    if (P.h.nTiles > 1) {
+        P.tileShift = 0;
+        while ((1 << P.tileShift) < P.h.tileRows) ++P.tileShift;
+    }
     P.maxRowLen = 0;
     for (size_t sl = 0; sl + 1 < P.h.sliceBase.size(); ++sl)
         P.maxRowLen = std::max(P.maxRowLen, (int)((P.h.sliceBase[sl + 1] - P.h.sliceBase[sl]) / 32));
     P.nSlots = (int)P.h.slotRow.size();
     // permuted (colour-major) orders put a row's earlier neighbours hundreds of MB upstream: the
     // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
-    if (P.h.sym.valid && !ctx->disableSym && ord == Ordering::Natural) {
+    // the symmetric single-read Amul needs a row's earlier neighbours close upstream (L2 hits): natural
+    // order, or a multicolour order that is tiled (or small enough to be L2-resident anyway)
+    // Both extensions are opt-in because they measured slower than the full-row ELL they replace
+    // (profiles/r01_v7_dic_tiles.md): the ranked form on renumbered natural plans (B200PCG_SPMV=ranked)
+    // and the single-read layout on tiled multicolour plans (B200PCG_TILE=<rows>).
+    const bool symOrder = (ord == Ordering::Natural && (!P.h.sym.ranked || ctx->enableRanked)) ||
+                          (ord == Ordering::MultiColour && P.h.nTiles > 1);
+    if (P.h.sym.valid && !ctx->disableSym && symOrder) {
         SymPlan& Y = P.h.sym;
         // arrays padded to whole 256-row chunks for the bulk-copy (TMA) staging
         const size_t rowsPad = (((size_t)ctx->N + kChunkRows - 1) / kChunkRows) * kChunkRows;
@@ -346,20 +372,24 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         RET(upload(ctx, &P.sUCol, Y.uCol));
         RET(upload(ctx, &P.sUFace, Y.uFace));
         RET(upload(ctx, &P.sLRef, Y.lRef));
+        P.symRanked = Y.ranked;
+        if (Y.ranked) {
+            Y.lRank.resize(rowsPad * Y.WL, 0);
+            RET(upload(ctx, &P.sLRank, Y.lRank));
+        }
         RET(dev_alloc(ctx, &P.sUVal, rowsPad * Y.WU));
         {
+            // the layout's own row lengths (split by row index), padded: the staged kernel reads whole chunks
             std::vector<uint32_t> rl(rowsPad, 0u);
-            // rowLen was uploaded un-padded for the ELL kernels; the staged kernel reads whole chunks
-            CU(cudaMemcpyAsync(rl.data(), P.rowLen, (size_t)ctx->N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->sc));
-            CU(cudaStreamSynchronize(ctx->sc));
+            std::copy(Y.rowLen.begin(), Y.rowLen.end(), rl.begin());
             RET(upload(ctx, &P.sRowLen, rl));
             CU(cudaStreamSynchronize(ctx->sc));
         }
         P.symNU = (int64_t)(rowsPad * Y.WU);
         P.symStage = sym_stage_bytes(Y.WU, Y.WL);
-        P.symTma = !ctx->disableTma && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
+        P.symTma = !ctx->disableTma && !Y.ranked && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
         P.symWinBytes = win_smem_bytes(Y.WU, Y.WL);
-        P.symWin = !ctx->disableTma && !ctx->disableWin && P.symWinBytes <= 100 * 1024;
+        P.symWin = !ctx->disableTma && !ctx->disableWin && !Y.ranked && P.symWinBytes <= 100 * 1024;
         if (P.symWin) {
             const int smemMax = 200 * 1024;
             CU(cudaFuncSetAttribute(k_spmv_sym_win<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
@@ -494,9 +524,13 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
 #undef B200_TMA_LAUNCH
         prof_end(ctx, PC_SPMV);
         ctx->launches++;
+    } else if (P.sym && P.symRanked) {
+        auto kern = k_spmv_sym_ranked<INIT, DOT>;
+        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
+               P.sUCol, P.sUVal, P.sLRef, P.sLRank, ctx->diag, x, y, sA, R);
     } else if (P.sym) {
         auto kern = k_spmv_sym<INIT, DOT>;
-        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.rowLen,
+        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
                P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
     } else {
         auto kern = k_spmv<INIT, DOT>;
@@ -558,6 +592,23 @@ int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* 
     return B200_OK;
 }
 
+// launch geometry of a sweep over the rows of colour c (kernels.cuh ColourRows)
+ColourRows colour_rows(const b200_ctx* ctx, const DevPlan& P, int c, int* grid) {
+    ColourRows cr{P.segStart, P.h.nColours, c, P.h.nTiles, 1};
+    const int rows = P.h.colourStart[c + 1] - P.h.colourStart[c];
+    if (P.h.nTiles == 1) {
+        *grid = grid_for(ctx, rows);
+        cr.bps = *grid;
+    } else {
+        // ~4 rows per thread inside a segment; the grid strides over (tile, block-in-segment) items
+        const int segRows = std::max(1, rows / P.h.nTiles);
+        cr.bps = std::max(1, std::min(8, (segRows + 4 * kBlock - 1) / (4 * kBlock)));
+        const int64_t items = (int64_t)P.h.nTiles * cr.bps;
+        *grid = (int)std::min<int64_t>(items, std::min(kMaxGrid, ctx->numSMs * 8));
+    }
+    return cr;
+}
+
 // precondition rA -> wA and form wArA = (wA, rA) [STEP_WARA]; used once before the loop for every
 // mode and, for the DIC-class modes, after every iteration (none/diagonal fuse it into k_r).
 int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond, bool firstColourDone = false) {
@@ -574,24 +625,23 @@ int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond, bool firstColou
     } else {
         const int C = P.h.nColours;
         for (int k = firstColourDone ? 1 : 0; k < C; ++k) {   // (first colour: fused into k_r<2>)
-            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+            int g;
+            const ColourRows cr = colour_rows(ctx, P, k, &g);
             const bool last = (k == C - 1);
             Reduce R = mkR(ctx, (last && C == 1) ? STEP_WARA : STEP_NONE);
             if (last) {
                 auto kf = k_dic_fwd<true>;
-                LAUNCH(PC_DIC_FWD, kf, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen, P.col,
-                       P.val, ctx->rD, ctx->r, ctx->w, R);
+                LAUNCH(PC_DIC_FWD, kf, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
             } else {
                 auto kf = k_dic_fwd<false>;
-                LAUNCH(PC_DIC_FWD, kf, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen, P.col,
-                       P.val, ctx->rD, ctx->r, ctx->w, R);
+                LAUNCH(PC_DIC_FWD, kf, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
             }
         }
         for (int k = C - 2; k >= 0; --k) {
-            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+            int g;
+            const ColourRows cr = colour_rows(ctx, P, k, &g);
             Reduce R = mkR(ctx, k == 0 ? STEP_WARA : STEP_NONE);
-            LAUNCH(PC_DIC_BWD, k_dic_bwd, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen,
-                   P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
+            LAUNCH(PC_DIC_BWD, k_dic_bwd, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
         }
     }
     RET(reduce_post(ctx, STEP_WARA));
@@ -618,19 +668,20 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
     if (precond == B200_PRECOND_NONE) {
         Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<0>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, 0, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, FirstColour{nullptr, 1, 31}, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else if (precond == B200_PRECOND_DIAGONAL) {
         Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<1>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, 0, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, FirstColour{nullptr, 1, 31}, R);
         RET(reduce_post(ctx, STEP_RES_WARA));
     } else {
         Reduce R = mkR(ctx, STEP_RES);
         // with >= 2 colours the first colour's forward sweep (wA = rD*rA) rides along in k_r
         const bool fuse = P.h.nColours >= 2 && !ctx->noFuseFirst;
         auto k = k_r<2>;
-        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD, fuse ? P.h.colourStart[1] : 0, R);
+        LAUNCH(PC_KR, k, gv, N, ctx->r, ctx->w, ctx->rD,
+               FirstColour{fuse ? P.segStart : nullptr, P.h.nColours, P.tileShift}, R);
         RET(reduce_post(ctx, STEP_RES));
         RET(enqueue_precondition(ctx, P, precond, fuse));
     }
@@ -773,9 +824,9 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->diag, ctx->rD);
     } else if (ctl->precond >= B200_PRECOND_DIC_MC) {
         for (int k = 0; k < P.h.nColours; ++k) {
-            const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
-            LAUNCH(PC_DIC_RD, k_dic_calc_rd, grid_for(ctx, r1 - r0), r0, r1, P.sliceBase, P.rowLen,
-                   P.col, P.val, ctx->diag, ctx->rD);
+            int g;
+            const ColourRows cr = colour_rows(ctx, P, k, &g);
+            LAUNCH(PC_DIC_RD, k_dic_calc_rd, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->diag, ctx->rD);
         }
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
     }
@@ -915,10 +966,12 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         c->disableSym = (std::string(e2) == "ell");
         c->disableTma = (std::string(e2) == "sym");
         c->disableWin = (std::string(e2) != "win");
+        c->enableRanked = (std::string(e2) == "ranked");
     }
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
+    if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
@@ -1354,11 +1407,12 @@ const char* b200_profile_json(b200_ctx* ctx) {
 
 const char* b200_describe(b200_ctx* ctx) {
     if (!ctx) return "{}";
-    char buf[1536];
+    char buf[2048];
     const DevPlan& P = ctx->plans[0];
     const char* amul = !P.built ? "none"
                        : (P.sym && P.symWin) ? (ctx->winNext ? "k_spmv_sym_win<DOT,NEXT=1>" : "k_spmv_sym_win<DOT,NEXT=0>")
                        : (P.sym && P.symTma) ? "k_spmv_sym_tma<DOT,STAGES>"
+                       : (P.sym && P.symRanked) ? "k_spmv_sym_ranked<INIT,DOT>"
                        : P.sym ? "k_spmv_sym<INIT,DOT>" : "k_spmv<INIT,DOT>";
     std::snprintf(buf, sizeof(buf),
                   "{\"amul_natural\": \"%s\", \"amul_permuted\": \"k_spmv<INIT,DOT>\", \"symWU\": %d, \"symWL\": %d, "
@@ -1366,11 +1420,14 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"nranks\": %d, \"peer_allreduce\": %s, \"nCells\": %d, \"nFaces\": %d, \"nSlots\": %d, \"sms\": %d, "
                   "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
                   "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
-                  "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d}",
+                  "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d, "
+                  "\"multicolour_tiles\": %d, \"multicolour_tile_rows\": %d, \"multicolour_amul\": \"%s\"}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
-                  P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN);
+                  P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN,
+                  ctx->plans[1].built ? ctx->plans[1].h.nTiles : 0, ctx->plans[1].built ? ctx->plans[1].h.tileRows : 0,
+                  !ctx->plans[1].built ? "n/a" : (ctx->plans[1].sym ? (ctx->plans[1].symTma ? "k_spmv_sym_tma" : "k_spmv_sym") : "k_spmv"));
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

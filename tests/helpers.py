@@ -13,10 +13,11 @@ class PlanView:
     """HostPlan (csrc/plan.cpp) pulled out through the host-only debug ABI."""
 
     NAMES = ["perm", "iperm", "colourStart", "sliceBase", "rowLen", "col", "faceOf", "nbrRank",
-             "patchStart", "slotRow", "bRow", "bStart", "bSlot"]
+             "patchStart", "slotRow", "bRow", "bStart", "bSlot", "segStart", "rowColour"]
 
-    def __init__(self, ordering, addr, renumber=0):
-        """renumber: 0 off (the default of the host-only debug ABI), -1 auto, 1 force RCM."""
+    def __init__(self, ordering, addr, renumber=0, tileRows=0):
+        """renumber: 0 off (the default of the host-only debug ABI), -1 auto, 1 force RCM;
+        tileRows > 0: tiled multicolour order (rows ordered by tile, colour, base position)."""
         L = _lib.load_pcg()
         ifs = (_lib.Iface * max(1, len(addr.interfaces)))()
         # b200_dbg_iface = {nbrRank, nFaces, faceCells} -- same leading layout, pack explicitly
@@ -27,11 +28,11 @@ class PlanView:
             dif[k].nbrRank, dif[k].nFaces = itf.neighbProcNo, itf.faceCells.size
             dif[k].faceCells = itf.faceCells.ctypes.data
         L.b200_debug_plan_build2.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                             C.c_int32, C.c_void_p]
+                                             C.c_int32, C.c_void_p, C.c_int32]
         L.b200_debug_plan_build2.restype = C.c_void_p
         h = L.b200_debug_plan_build2(ordering, renumber, addr.nCells, addr.nFaces,
                                      addr.lowerAddr.ctypes.data, addr.upperAddr.ctypes.data,
-                                     len(addr.interfaces), C.cast(dif, C.c_void_p))
+                                     len(addr.interfaces), C.cast(dif, C.c_void_p), tileRows)
         if not h:
             raise ValueError(L.b200_debug_plan_error().decode())
         try:
@@ -41,7 +42,12 @@ class PlanView:
             L.b200_debug_plan_sym_wu.argtypes = [C.c_void_p]
             L.b200_debug_plan_sym_wl.argtypes = [C.c_void_p]
             self.symWU, self.symWL = L.b200_debug_plan_sym_wu(h), L.b200_debug_plan_sym_wl(h)
-            for nm, dt in (("uCol", np.int32), ("uFace", np.int32), ("lRef", np.uint32)):
+            L.b200_debug_plan_ntiles.argtypes = [C.c_void_p]
+            self.nTiles = L.b200_debug_plan_ntiles(h)
+            L.b200_debug_plan_sym_ranked.argtypes = [C.c_void_p]
+            self.symRanked = bool(L.b200_debug_plan_sym_ranked(h))
+            for nm, dt in (("uCol", np.int32), ("uFace", np.int32), ("lRef", np.uint32), ("rowLen", np.uint32),
+                           ("lRank", np.uint8)):
                 ptr, eb = C.c_void_p(), C.c_int32()
                 n = L.b200_debug_plan_get(h, ("sym." + nm).encode(), C.byref(ptr), C.byref(eb))
                 self.sym[nm] = (np.empty(0, dtype=dt) if n <= 0 else
@@ -68,6 +74,16 @@ class PlanView:
         self.N, self.F = addr.nCells, addr.nFaces
         self.nLower = (self.rowLen & 0xFFFF).astype(np.int64)
         self.nTotal = (self.rowLen >> 16).astype(np.int64)
+        self.symNLower = (self.sym["rowLen"] & 0xFFFF).astype(np.int64)
+        self.symNTotal = (self.sym["rowLen"] >> 16).astype(np.int64)
+
+    def rows_of_colour(self, k):
+        """internal rows of colour k, ascending (all tiles)"""
+        C = self.nColours
+        out = []
+        for t in range(self.nTiles):
+            out.extend(range(int(self.segStart[t * C + k]), int(self.segStart[t * C + k + 1])))
+        return out
 
     def entry(self, r, j):
         return int(self.sliceBase[r // 32]) + 32 * j + (r % 32)
@@ -107,26 +123,40 @@ class PlanView:
         uv[m] = upper[y["uFace"][m]]
         out = np.empty(self.N)
         for r in range(self.N):
-            nL, nU = int(self.nLower[r]), int(self.nTotal[r] - self.nLower[r])
+            nL, nU = int(self.symNLower[r]), int(self.symNTotal[r] - self.symNLower[r])
             acc = diag_i[r] * x_i[r]
             lb = (r // 32) * 32 * self.symWL + (r % 32)
+            ub = (r // 32) * 32 * self.symWU + (r % 32)
+            staged = {}     # ranked form (k_spmv_sym_ranked): products staged by rank, added in rank order
             for j in range(nL):
                 pk = int(y["lRef"][lb + 32 * j])
                 a, q = pk >> 5, pk & 31
                 assert a < r
-                acc = acc + uv[(a // 32) * 32 * self.symWU + 32 * q + (a % 32)] * x_i[a]
-            ub = (r // 32) * 32 * self.symWU + (r % 32)
+                prod = uv[(a // 32) * 32 * self.symWU + 32 * q + (a % 32)] * x_i[a]
+                if self.symRanked:
+                    staged[int(y["lRank"][lb + 32 * j])] = prod
+                else:
+                    acc = acc + prod
             for j in range(nU):
-                c = y["uCol"][ub + 32 * j]
+                cc = int(y["uCol"][ub + 32 * j])
+                c = cc & 0x7ffffff if self.symRanked else cc
                 assert c > r
-                acc = acc + uv[ub + 32 * j] * x_i[c]
+                prod = uv[ub + 32 * j] * x_i[c]
+                if self.symRanked:
+                    staged[cc >> 27] = prod
+                else:
+                    acc = acc + prod
+            if self.symRanked:
+                assert sorted(staged) == list(range(nL + nU))
+                for k in range(nL + nU):
+                    acc = acc + staged[k]
             out[r] = acc
         return out
 
     def dic_calc_rd(self, diag_i, val):
         rD = np.empty(self.N)
         for k in range(self.nColours):
-            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+            for r in self.rows_of_colour(k):
                 d = diag_i[r]
                 for j in range(self.nLower[r]):
                     e = self.entry(r, j)
@@ -137,14 +167,14 @@ class PlanView:
     def dic_precondition(self, rD, val, r_i):
         w = np.empty(self.N)
         for k in range(self.nColours):
-            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+            for r in self.rows_of_colour(k):
                 acc = rD[r] * r_i[r]
                 for j in range(self.nLower[r]):
                     e = self.entry(r, j)
                     acc = acc - (rD[r] * val[e]) * w[self.col[e]]
                 w[r] = acc
         for k in range(self.nColours - 2, -1, -1):
-            for r in range(self.colourStart[k], self.colourStart[k + 1]):
+            for r in self.rows_of_colour(k):
                 acc = w[r]
                 for j in range(self.nTotal[r] - 1, self.nLower[r] - 1, -1):
                     e = self.entry(r, j)

@@ -26,6 +26,7 @@ dist.broadcast(buf, 0)
 ctx = pkg.Context(device=local, rank=rank, nranks=world, nccl_uid=buf.cpu().numpy().tobytes())
 
 PROCS = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+# (B200PCG_TILE / B200PCG_SMALL_N are inherited from the environment: test_multigpu.py runs the worker both ways)
 DIMS = (24, 20, 16)
 results = {}
 s = mg.hex_block(*DIMS, *PROCS, rank)

@@ -361,17 +361,22 @@ def _ctx_with_env(env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("mode,small", [("0", "0"), ("1", "0"), ("1", "150000")])
-def test_rcm_renumbering_does_not_change_results(mode, small):
+@pytest.mark.parametrize("mode,small,spmv", [("0", "0", ""), ("1", "0", ""), ("1", "150000", ""), ("1", "0", "ranked")])
+def test_rcm_renumbering_does_not_change_results(mode, small, spmv):
     """Rows renumbered by reverse Cuthill-McKee (forced) or not at all: assembly, Amul and flux stay
     bit-identical to the oracle, PCG + diagonal keeps the oracle's iteration counts, DIC-exact is
     unaffected (never renumbered), multicolour DIC still converges to the same solution."""
-    c = _ctx_with_env({"B200PCG_RENUMBER": mode, "B200PCG_SMALL_N": small})
+    env = {"B200PCG_RENUMBER": mode, "B200PCG_SMALL_N": small}
+    if spmv:
+        env["B200PCG_SPMV"] = spmv     # ranked single-read layout (opt-in)
+    c = _ctx_with_env(env)
     try:
         for s in (mg.bcc_poly(9, 8, 10), mg.hex_block(24, 20, 16), random_ldu(5001, 6.0, seed=7)):
             a = s.addr
             c.set_addressing(a)
             assert c.describe()["renumbered_rcm"] == (mode == "1")
+            if spmv == "ranked" and s.gamma_f is not None:
+                assert c.describe()["amul_natural"].startswith("k_spmv_sym_ranked")
             if s.gamma_f is not None:
                 up, dg = c.assemble_laplacian(s.gamma_f, s.magSf, s.deltaCoeffs, -1.0, s.diag0)
                 up_ref, dg_ref = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf,
@@ -413,3 +418,40 @@ def test_cluster_kernel_sizes(ctas, fast):
         assert c.describe()["small_system_cluster_kernel"]
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("tile,spmv", [("64", ""), ("256", ""), ("64", "ell"), ("0", "")])
+def test_tiled_multicolour_dic_class(tile, spmv):
+    """DIC-class on a tiled multicolour order (rows = tile, colour, base position) with the symmetric
+    single-read Amul: the preconditioner is the same IC0 as in the colour-major order, so iteration
+    counts agree (to the +-1 that a different Amul summation order can cause) and the solution meets
+    the 1e-8 bar; the first-colour sweep fused into k_r and the segment sweeps are exercised."""
+    env = {"B200PCG_TILE": tile, "B200PCG_SMALL_N": "0"}
+    if spmv:
+        env["B200PCG_SPMV"] = spmv
+    c = _ctx_with_env(env)
+    ref_ctx = _ctx_with_env({"B200PCG_TILE": "0", "B200PCG_SMALL_N": "0", "B200PCG_FUSE_FIRST": "0",
+                             "B200PCG_SPMV": "ell"})
+    try:
+        for s in (mg.hex_block(24, 20, 16), mg.bcc_poly(9, 8, 10), random_ldu(5001, 6.0, seed=7),
+                  mg.hex_block(64, 40, 33)):
+            xg, pg = solve_gpu(c, s, "DIC", tol=1e-11, maxIter=5000)
+            xr, pr = solve_gpu(ref_ctx, s, "DIC", tol=1e-11, maxIter=5000)
+            xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
+            assert pg.converged and abs(pg.nIterations - pr.nIterations) <= 1, (pg.nIterations, pr.nIterations)
+            assert pg.nColours == pr.nColours
+            assert np.linalg.norm(xg - xc) / np.linalg.norm(xc) < 1e-8
+            assert np.linalg.norm(xg - xr) / np.linalg.norm(xr) < 1e-9
+            d = c.describe()
+            if tile != "0" and s.addr.nCells > 4 * int(tile):
+                assert d["multicolour_tiles"] > 1
+                assert d["multicolour_amul"] == ("k_spmv" if spmv == "ell" else d["multicolour_amul"])
+                if not spmv:
+                    assert d["multicolour_amul"].startswith("k_spmv_sym")
+            # diagonal / DIC-exact on the same context are untouched by the tiling
+            xg, pg = solve_gpu(c, s, "diagonal", tol=1e-7, maxIter=5000)
+            xc, pc = solve_cpu(s, "diagonal", tol=1e-7, maxIter=5000)
+            assert pg.nIterations == pc.nIterations and relmax(xg, xc) < 1e-12
+    finally:
+        c.close()
+        ref_ctx.close()

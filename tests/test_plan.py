@@ -61,9 +61,12 @@ def test_symmetric_single_read_layout(name, s):
     """SymPlan: every face stored once; same row-sum order as OpenFOAM -> bit-identical Amul."""
     x = np.random.default_rng(6).standard_normal(s.addr.nCells)
     ref = orc.amul(s, x)[0]
-    for ordering in (NAT, MC, LEV):
-        P = PlanView(ordering, s.addr)
+    assert not PlanView(LEV, s.addr).symValid          # level orders keep the full-row ELL
+    for ordering, tile in ((NAT, 0), (MC, 0), (MC, 32), (MC, 64)):
+        P = PlanView(ordering, s.addr, tileRows=tile)
         assert P.symValid
+        if tile and s.addr.nCells > 2 * tile:
+            assert P.nTiles == -(-s.addr.nCells // tile)
         m = P.sym["uFace"] >= 0
         assert np.array_equal(np.bincount(P.sym["uFace"][m], minlength=s.addr.nFaces),
                               np.ones(s.addr.nFaces, dtype=np.int64))
@@ -91,7 +94,7 @@ def test_rcm_renumbering_decision():
     P = PlanView(NAT, poly.addr, renumber=-1)
     assert P.renumbered and P.spanUsed < 0.5 * P.spanNatural
     assert np.array_equal(np.sort(P.perm), np.arange(poly.addr.nCells))
-    assert not P.symValid
+    assert P.symValid and P.symRanked          # single-read layout with per-entry face ranks
     assert PlanView(MC, poly.addr, renumber=-1).renumbered
     assert not PlanView(LEV, poly.addr, renumber=1).renumbered
     hexm = mg.hex_block(24, 20, 16)
@@ -114,10 +117,59 @@ def test_renumbered_natural_plan_is_bit_exact(name, s):
     x = np.random.default_rng(11).standard_normal(a.nCells)
     y = P.to_natural(P.spmv(P.to_internal(s.diag), P.values(s.upper), P.to_internal(x)))
     assert np.array_equal(y, orc.amul(s, x)[0])
+    # ranked symmetric single-read layout: split by RCM row index, summed by face rank -> still bit-exact
+    if P.nTotal.max() <= 16:
+        assert P.symValid and P.symRanked
+        y = P.to_natural(P.spmv_sym(P.to_internal(s.diag), s.upper, P.to_internal(x)))
+        assert np.array_equal(y, orc.amul(s, x)[0])
+    else:
+        assert not P.symValid
     # multicolour on top of the RCM base order: still a proper colouring
     Q = PlanView(MC, a, renumber=1)
     colour = np.searchsorted(Q.colourStart, np.arange(a.nCells), side="right") - 1
     assert np.all(colour[Q.iperm[a.lowerAddr]] != colour[Q.iperm[a.upperAddr]])
+
+
+@pytest.mark.parametrize("name,s", list(systems()) + [("poly", mg.bcc_poly(5, 4, 6)), ("hex-larger", mg.hex_block(12, 9, 8))])
+def test_tiled_multicolour_order(name, s):
+    """Rows ordered (tile, colour, base position): same colouring, same IC0 preconditioner as the
+    colour-major order (elimination order = colour order) -- only the storage order differs."""
+    a = s.addr
+    P0 = PlanView(MC, a)
+    r = np.random.default_rng(8).standard_normal(a.nCells)
+    v0 = P0.values(s.upper)
+    rD0 = P0.dic_calc_rd(P0.to_internal(s.diag), v0)
+    w0 = P0.to_natural(P0.dic_precondition(rD0, v0, P0.to_internal(r)))
+    for tile in (32, 64, 128):
+        P = PlanView(MC, a, tileRows=tile)
+        C = P.nColours
+        assert C == P0.nColours
+        if a.nCells <= 2 * tile:
+            assert P.nTiles == 1
+            continue
+        assert P.segStart.size == P.nTiles * C + 1 and P.segStart[0] == 0 and P.segStart[-1] == a.nCells
+        assert np.array_equal(np.sort(P.perm), np.arange(a.nCells))
+        # a tile holds `tile` consecutive base-order cells; inside a segment rows ascend in base order
+        for t in range(P.nTiles):
+            rows = np.arange(P.segStart[t * C], P.segStart[(t + 1) * C])
+            assert np.array_equal(np.sort(P.perm[rows]), np.arange(t * tile, min(a.nCells, (t + 1) * tile)))
+            for k in range(C):
+                seg = P.perm[P.segStart[t * C + k]:P.segStart[t * C + k + 1]]
+                assert np.all(np.diff(seg) > 0) and np.all(P.rowColour[P.segStart[t * C + k]:P.segStart[t * C + k + 1]] == k)
+        # same colouring as the untiled plan
+        col0 = np.empty(a.nCells, dtype=np.int64)
+        col0[P0.perm] = np.searchsorted(P0.colourStart, np.arange(a.nCells), side="right") - 1
+        assert np.array_equal(P.rowColour, col0[P.perm])
+        # full-row ELL groups by COLOUR (elimination order), each group in ascending face order
+        for row in range(a.nCells):
+            cols = [P.col[P.entry(row, j)] for j in range(P.nTotal[row])]
+            assert all(P.rowColour[c] < P.rowColour[row] for c in cols[:P.nLower[row]])
+            assert all(P.rowColour[c] > P.rowColour[row] for c in cols[P.nLower[row]:])
+        # identical preconditioner (bit for bit: same per-row operation order)
+        v = P.values(s.upper)
+        rD = P.dic_calc_rd(P.to_internal(s.diag), v)
+        w = P.to_natural(P.dic_precondition(rD, v, P.to_internal(r)))
+        assert np.array_equal(P.to_natural(rD), P0.to_natural(rD0)) and np.array_equal(w, w0)
 
 
 @pytest.mark.parametrize("name,s", list(systems()))
