@@ -51,6 +51,12 @@ struct Scalars {
     double gsums[kNSums];  // global totals (== sums when nranks == 1)
     unsigned int ticket;
     unsigned int pad1;
+    // number of cross-rank reductions this rank has EXECUTED (peer_allreduce_step).  Every rank
+    // executes the same sequence (identical totals -> identical `done` decisions), so the counters
+    // stay equal across ranks, and consecutive executed reductions strictly alternate buffer parity --
+    // which is what makes the two-slot PeerBuf safe (a host-side launch counter would not: launches
+    // skipped by `done` would let two executed reductions share a parity).
+    unsigned long long redSeq;
 };
 
 struct PeerBuf;
@@ -63,7 +69,6 @@ struct Reduce {
     // cross-rank sum itself (peer_allreduce_step); peers == nullptr -> host issues ncclAllReduce
     PeerBuf* const* peers;
     int rank;
-    unsigned long long seq;
 };
 
 // ---- scalar steps (OF-dev PCG.C, SolverPerformance.C) ---------------
@@ -165,8 +170,14 @@ struct PeerBuf {
 
 // one warp (all 32 lanes must call)
 __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
-                                                    unsigned long long seq, int step) {
+                                                    int step) {
     const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0;
+    if (lane == 0) {
+        seq = S->redSeq + 1ull;
+        S->redSeq = seq;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
     const int par = (int)(seq & 1ull);
     if (lane < nranks) {
         PeerBuf* dst = peers[lane];
@@ -215,10 +226,9 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
 }
 
 // stand-alone form (one warp), for reductions whose local sums were produced without a fused finish
-__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
-                                 unsigned long long seq, int step) {
+__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks, int step) {
     if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
-    peer_allreduce_step(S, peers, rank, nranks, seq, step);
+    peer_allreduce_step(S, peers, rank, nranks, step);
 }
 
 // ---- deterministic block reduction + last-block finish -----------------------------------
@@ -291,7 +301,7 @@ __device__ __forceinline__ void reduce_finish(double (&v)[NV], const Reduce& R) 
     if (R.step != STEP_NONE && R.peers != nullptr) {
         // cross-rank sum over NVLink peer memory + scalar step, by the first warp of this (last) block
         __syncthreads();
-        if (threadIdx.x < 32) peer_allreduce_step(S, R.peers, R.rank, S->nranks, R.seq, R.step);
+        if (threadIdx.x < 32) peer_allreduce_step(S, R.peers, R.rank, S->nranks, R.step);
     }
     if (threadIdx.x == 0) {
         S->ticket = 0u;
@@ -593,8 +603,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // bytes of one stage for given widths (host + device)
+// (row lengths travel as one byte per row, nL | nU << 4: 4 % less Amul traffic than the 32-bit form)
 __host__ __device__ inline size_t sym_stage_bytes(int WU, int WL) {
-    return (size_t)kChunkRows * ((size_t)WU * 12 + (size_t)WL * 4 + 4 + 16);
+    return (size_t)kChunkRows * ((size_t)WU * 12 + (size_t)WL * 4 + 1 + 16);
 }
 
 // BL/BU: number of lower/upper entries handled by the unrolled, batched-load path.  TAIL = false
@@ -603,7 +614,7 @@ __host__ __device__ inline size_t sym_stage_bytes(int WU, int WL) {
 // 32 rows with BL = BU = 4 on the 3+3-entry hex rows), so instructions matter as much as bytes.
 template <bool DOT, int kSymStages, int BL, int BU, bool TAIL>
 __global__ void __launch_bounds__(kBlock)
-k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
+k_spmv_sym_tma(int N, int WU, int WL, const uint8_t* __restrict__ rowLen8,
                const int* __restrict__ uCol, const double* __restrict__ uVal,
                const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
                const double* __restrict__ x, double* __restrict__ y, Reduce R) {
@@ -635,7 +646,7 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
         bulk_g2s(st + oDiag, diag + r0, kChunkRows * 8, &bars[s]);
         bulk_g2s(st + oCol, uCol + r0 * WU, (uint32_t)(kChunkRows * WU * 4), &bars[s]);
         if (WL > 0) bulk_g2s(st + oRef, lRef + r0 * WL, (uint32_t)(kChunkRows * WL * 4), &bars[s]);
-        bulk_g2s(st + oLen, rowLen + r0, kChunkRows * 4, &bars[s]);
+        bulk_g2s(st + oLen, rowLen8 + r0, kChunkRows, &bars[s]);
     };
     if (tid == 0)
         for (int s = 0; s < kSymStages; ++s) {
@@ -654,11 +665,11 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
         const double* sDiag = reinterpret_cast<const double*>(st + oDiag);
         const int* sCol = reinterpret_cast<const int*>(st + oCol);
         const uint32_t* sRef = reinterpret_cast<const uint32_t*>(st + oRef);
-        const uint32_t* sLen = reinterpret_cast<const uint32_t*>(st + oLen);
+        const uint8_t* sLen = st + oLen;
         const int r = chunk * kChunkRows + (int)tid;
         if (r < N) {
             const uint32_t len = sLen[tid];
-            const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
+            const int nL = (int)(len & 15u), nU = (int)(len >> 4);
             const uint32_t lb = warp * strideL + lane, ub = warp * strideU + lane;
             // gathers served by L2/L1 (the only exposed latency)
             double lv[BL > 0 ? BL : 1], lx[BL > 0 ? BL : 1], ux[BU > 0 ? BU : 1];

@@ -18,6 +18,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -108,6 +109,7 @@ struct DevPlan {
     bool symWin = false;
     size_t symStage = 0, symWinBytes = 0;
     uint32_t* sRowLen = nullptr;
+    uint8_t* sRowLen8 = nullptr;  // nL | nU << 4 per row (bulk-copy staged kernel)
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
     uint32_t* sLRef = nullptr;
@@ -157,7 +159,6 @@ struct b200_ctx {
     PeerBuf* peerLocal = nullptr;
     std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)
     PeerBuf** d_peers = nullptr;
-    unsigned long long reduceSeq = 0;
     Scalars* S = nullptr;
     Scalars* hS = nullptr;  // pinned
     double* partials = nullptr;
@@ -297,7 +298,7 @@ void free_plan(DevPlan& P) {
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
     dev_free(P.sUCol); dev_free(P.sUFace);
-    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sLRank);
+    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8); dev_free(P.sLRank);
     P.symRanked = false;
     P.sym = false;
     P.built = false;
@@ -383,11 +384,19 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
             std::vector<uint32_t> rl(rowsPad, 0u);
             std::copy(Y.rowLen.begin(), Y.rowLen.end(), rl.begin());
             RET(upload(ctx, &P.sRowLen, rl));
+            if (Y.WU <= 15 && Y.WL <= 15) {
+                std::vector<uint8_t> rl8(rowsPad, 0);
+                for (size_t r = 0; r < Y.rowLen.size(); ++r) {
+                    const uint32_t nLo = Y.rowLen[r] & 0xffffu, nUp = (Y.rowLen[r] >> 16) - nLo;
+                    rl8[r] = (uint8_t)(nLo | (nUp << 4));
+                }
+                RET(upload(ctx, &P.sRowLen8, rl8));
+            }
             CU(cudaStreamSynchronize(ctx->sc));
         }
         P.symNU = (int64_t)(rowsPad * Y.WU);
         P.symStage = sym_stage_bytes(Y.WU, Y.WL);
-        P.symTma = !ctx->disableTma && !Y.ranked && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
+        P.symTma = !ctx->disableTma && !Y.ranked && P.sRowLen8 && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
         P.symWinBytes = win_smem_bytes(Y.WU, Y.WL);
         P.symWin = !ctx->disableTma && !ctx->disableWin && !Y.ranked && P.symWinBytes <= 100 * 1024;
         if (P.symWin) {
@@ -437,7 +446,9 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
     h.nGlobalCells = ctx->nGlobalCells;
     h.wArA = 1e20;
     h.wArAold = 1e20;
-    CU(cudaMemcpyAsync(ctx->S, ctx->hS, sizeof(Scalars), cudaMemcpyHostToDevice, ctx->sc));
+    // everything but redSeq: the count of executed cross-rank reductions lives on the device for the
+    // lifetime of the context (kernels.cuh Scalars)
+    CU(cudaMemcpyAsync(ctx->S, ctx->hS, offsetof(Scalars, redSeq), cudaMemcpyHostToDevice, ctx->sc));
     return B200_OK;
 }
 
@@ -445,11 +456,8 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
 // kernel that completes the reduction (step != STEP_NONE) also performs the cross-rank sum and the
 // scalar step in its last block: it gets the peer table and the next sequence number.
 Reduce mkR(b200_ctx* ctx, int step) {
-    Reduce R{ctx->S, ctx->partials, step, nullptr, ctx->rank, 0ull};
-    if (step != STEP_NONE && ctx->nranks > 1 && ctx->p2pReduce) {
-        R.peers = ctx->d_peers;
-        R.seq = ++ctx->reduceSeq;
-    }
+    Reduce R{ctx->S, ctx->partials, step, nullptr, ctx->rank};
+    if (step != STEP_NONE && ctx->nranks > 1 && ctx->p2pReduce) R.peers = ctx->d_peers;
     return R;
 }
 
@@ -509,12 +517,12 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
         if (perSM > 8) perSM = 8;
         if (perSM < 1) perSM = 1;
-        if (ctx->symPerSM > 0 && perSM > ctx->symPerSM) perSM = ctx->symPerSM;
+        if (ctx->symPerSM > 0) perSM = std::min(ctx->symPerSM, (int)((size_t)224 * 1024 / (smem + 1024)));
         const int nChunks = (N + kChunkRows - 1) / kChunkRows;
         int g = std::min(nChunks, perSM * ctx->numSMs);
         if (g > kMaxGrid) g = kMaxGrid;
         prof_begin(ctx, PC_SPMV);
-#define B200_TMA_LAUNCH(...) k_spmv_sym_tma<DOT, __VA_ARGS__><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen, P.sUCol, \
+#define B200_TMA_LAUNCH(...) k_spmv_sym_tma<DOT, __VA_ARGS__><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen8, P.sUCol, \
                                                                                    P.sUVal, P.sLRef, ctx->diag, x, y, R)
         // exact-width instantiations (no tail loops, no idle slots) for the common narrow rows
         if (ctx->symStages == 3) B200_TMA_LAUNCH(3, 4, 4, true);
