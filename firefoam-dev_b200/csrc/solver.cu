@@ -184,6 +184,7 @@ struct b200_ctx {
     int smallN = 150000, smallCtas = 16;
     bool usedSmall = false, usedFast = false;
     bool disableFast = false;     // B200PCG_SMALL_FAST=0: always the L2-resident k_pcg_small
+    int fastMaxCtas = 16;         // B200PCG_FAST_CTAS: largest cluster the on-chip kernel may use
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool enableRanked = false;  // B200PCG_SPMV=ranked
     bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
@@ -759,6 +760,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         int fastCtas = 0, fastRpt = 0;
         if (!ctx->disableFast) {
             for (int nc : {1, 2, 4, 8, 16}) {
+                if (nc > ctx->fastMaxCtas) break;
                 const int rpt = (N + nc * kSmallBlock - 1) / (nc * kSmallBlock);
                 if (rpt <= 2 && fast_smem_bytes(rpt, P.maxRowLen) <= (size_t)225 * 1024) {
                     // prefer one row per thread when a larger cluster offers it
@@ -978,6 +980,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     }
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
+    if (const char* e14 = getenv("B200PCG_FAST_CTAS")) c->fastMaxCtas = std::max(1, atoi(e14));
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
