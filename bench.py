@@ -454,8 +454,8 @@ def run_gpu(args):
 
     peak, peak_src = measured_peak()
     dic = args.precond.startswith("DIC")
-    alg = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N, "p_update": 24 * N,
-           "update_psi_r": 48 * N, "asm_face_coeff": 32 * F, "asm_neg_sum_diag": 16 * N + 16 * F,
+    alg = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N,
+           "asm_face_coeff": 32 * F, "asm_neg_sum_diag": 16 * N + 16 * F,
            # the fused vector kernels move fewer bytes than the unfused loop SURVEY.md 8d counts:
            # k_p: psi, pA read+write, rA (+rD | z) read; k_r: rA read+write, wA (+rD) read
            "p_psi_update": (40 if dic else 48) * N, "r_update_dots": (24 if dic else 32) * N,

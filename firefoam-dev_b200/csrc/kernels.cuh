@@ -161,7 +161,8 @@ __global__ void k_scalar_step(Scalars* S, int step) {
 // NVSwitch), then waits for rank r's contribution to arrive in the local buffer, and lane 0 adds
 // the contributions in ASCENDING RANK ORDER -- the order of Pstream's linear gather for
 // <= nProcsSimpleSum ranks -- so every rank forms bit-identical totals, and runs
-// the scalar step.  One ~5 us kernel instead of ncclAllReduce + a scalar kernel (~25 us).
+// the scalar step.  Executed by the first warp of the LAST block of the kernel that completes the
+// reduction (reduce_finish): no extra launch, instead of ncclAllReduce + a scalar kernel (~25 us).
 constexpr int kMaxRanks = 32;
 struct PeerBuf {
     double vals[2][kMaxRanks][kNSums];
@@ -223,12 +224,6 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
             scalar_step(step, S, S->gsums);
         }
     }
-}
-
-// stand-alone form (one warp), for reductions whose local sums were produced without a fused finish
-__global__ void k_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks, int step) {
-    if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
-    peer_allreduce_step(S, peers, rank, nranks, step);
 }
 
 // ---- deterministic block reduction + last-block finish -----------------------------------
@@ -991,48 +986,6 @@ k_precond_dot(int N, const double* __restrict__ rD, const double* __restrict__ r
         { double r = rA[i]; double w = r;
           if (PRECOND) { w = __dmul_rn(rD[i], r); wA[i] = w; }
           s[0] = __dadd_rn(s[0], __dmul_rn(w, r)); })
-    reduce_finish<1>(s, R);
-}
-
-// pA = wA (first iteration) | pA = wA + beta*pA   (OF-dev PCG.C)
-__global__ void __launch_bounds__(kBlock)
-k_pupdate(int N, const double* __restrict__ z, double* __restrict__ pA, const Scalars* S) {
-    if (S->done) return;
-    const bool first = (S->nIter == 0);
-    const double beta = S->beta;
-    B200_VEC_LOOP(N,
-        { double2 w = reinterpret_cast<const double2*>(z)[i];
-          if (!first) {
-              double2 p = reinterpret_cast<const double2*>(pA)[i];
-              w.x = __dadd_rn(w.x, __dmul_rn(beta, p.x));
-              w.y = __dadd_rn(w.y, __dmul_rn(beta, p.y));
-          }
-          reinterpret_cast<double2*>(pA)[i] = w; },
-        { double w = z[i]; if (!first) w = __dadd_rn(w, __dmul_rn(beta, pA[i])); pA[i] = w; })
-}
-
-// psi += alpha*pA; rA -= alpha*wA; gSumMag(rA)   (OF-dev PCG.C)
-__global__ void __launch_bounds__(kBlock)
-k_update(int N, double* __restrict__ psi, double* __restrict__ rA,
-         const double* __restrict__ pA, const double* __restrict__ wA, Reduce R) {
-    if (R.S->done) return;
-    const double alpha = R.S->alpha;
-    double s[1] = {0.0};
-    B200_VEC_LOOP(N,
-        { double2 x = reinterpret_cast<double2*>(psi)[i];
-          double2 r = reinterpret_cast<double2*>(rA)[i];
-          double2 p = reinterpret_cast<const double2*>(pA)[i];
-          double2 w = reinterpret_cast<const double2*>(wA)[i];
-          x.x = __dadd_rn(x.x, __dmul_rn(alpha, p.x));
-          x.y = __dadd_rn(x.y, __dmul_rn(alpha, p.y));
-          r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
-          r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
-          reinterpret_cast<double2*>(psi)[i] = x;
-          reinterpret_cast<double2*>(rA)[i] = r;
-          s[0] = __dadd_rn(s[0], __dadd_rn(fabs(r.x), fabs(r.y))); },
-        { double x = __dadd_rn(psi[i], __dmul_rn(alpha, pA[i]));
-          double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
-          psi[i] = x; rA[i] = r; s[0] = __dadd_rn(s[0], fabs(r)); })
     reduce_finish<1>(s, R);
 }
 

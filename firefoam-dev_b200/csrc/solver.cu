@@ -77,12 +77,12 @@ NcclApi g_nccl;
 
 enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
-    PC_PRECOND_DOT, PC_PUPDATE, PC_UPDATE, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
+    PC_PRECOND_DOT, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
     PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
-    "norm_resid", "recip", "precond_dot", "p_update", "update_psi_r", "dic_calc_rd", "dic_fwd",
+    "norm_resid", "recip", "precond_dot", "dic_calc_rd", "dic_fwd",
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
     "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells"};
 
@@ -154,7 +154,7 @@ struct b200_ctx {
     int *bfStart = nullptr, *bfOrder = nullptr;
     double* scratch = nullptr;      // staging arena of the host entry point b200_assemble_p_rgh
     size_t scratchElems = 0;
-    // one-shot peer-memory all-reduce (k_allreduce_step)
+    // one-shot peer-memory all-reduce (peer_allreduce_step in the reducing kernels' last block)
     bool p2pReduce = false;
     PeerBuf* peerLocal = nullptr;
     std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)

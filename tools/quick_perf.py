@@ -35,7 +35,7 @@ for rep in range(3):
           f"h2d={perf.h2dMs:.2f} d2h={perf.d2hMs:.2f} wall={wall*1e3:.1f}ms  per-iter={perf.solveMs/max(1,perf.nIterations)*1e3:.1f}us "
           f"colours={perf.nColours}", flush=True)
 prof = ctx.profile_json()
-bytes_per = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N, "p_update": 24 * N, "update_psi_r": 48 * N,
+bytes_per = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N, "p_psi_update": 48 * N, "r_update_dots": 32 * N,
              "dic_fwd": (20 * N + 16 * F), "dic_bwd": (20 * N + 16 * F)}
 for k, v in prof.items():
     line = f"  {k:16s} n={v['launches']:6d} avg={v['avg_us']:9.2f}us"
