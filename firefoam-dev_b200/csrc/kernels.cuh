@@ -327,15 +327,33 @@ __global__ void k_fill_values(int64_t nEntries, const int* __restrict__ faceOf,
     }
 }
 
+// ---- column of a full-row ELL entry ----------------------------------------------------------
+// 32-bit column, or (plan.hpp) per-(slice, j) base + 16-bit offset: entry e = sliceBase + 32 j + lane,
+// so e >> 5 indexes the base table.  The kernels that are bound by the bytes of the full-row ELL read
+// 10 instead of 12 bytes per entry.  The 16-bit form is used only when EVERY slice entry of the plan
+// fits: two independent loads and an add, no branch -- a per-entry fall-back to the 32-bit column was
+// measured 50 % SLOWER than plain 32-bit columns (the test on the base puts a fourth dependent load
+// and a branch into the gather chain).
+struct EllCols {
+    const int* col;             // [nEntries]
+    const uint16_t* col16;      // [nEntries] or nullptr
+    const int* colBase;         // [nEntries/32]
+};
+template <bool C16>
+__device__ __forceinline__ int ell_col(const EllCols& E, int64_t e) {
+    if (!C16) return __ldg(&E.col[e]);      // (read-only path: the struct members carry no __restrict__)
+    return __ldg(&E.colBase[e >> 5]) + (int)__ldg(&E.col16[e]);
+}
+
 // ---- lduMatrix::Amul / sumA (OF-dev lduMatrixATmul.C) ---------------------
 // One row per thread, rows of a warp = one ELL slice -> the j-th loads of a warp are
 // contiguous.  Row sum order: diag*x, then faces in ascending face order with the row as
 // neighbour, then as owner == the order in which OpenFOAM's face loop updates Apsi[row].
 // INIT additionally forms sumA (same loop, x == 1).  DOT accumulates (y, x).
-template <bool INIT, bool DOT>
+template <bool INIT, bool DOT, bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
-       const int* __restrict__ col, const double* __restrict__ val,
+       EllCols E, const double* __restrict__ val,
        const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
        double* __restrict__ sA, Reduce R) {
     if (R.S->done) return;
@@ -355,7 +373,8 @@ k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict_
             int j = 0;
             for (; j + 4 <= n; j += 4) {
                 const int64_t e = base + 32 * (int64_t)j;
-                const int c0 = col[e], c1 = col[e + 32], c2 = col[e + 64], c3 = col[e + 96];
+                const int c0 = ell_col<C16>(E, e), c1 = ell_col<C16>(E, e + 32), c2 = ell_col<C16>(E, e + 64),
+                          c3 = ell_col<C16>(E, e + 96);
                 const double a0 = val[e], a1 = val[e + 32], a2 = val[e + 64], a3 = val[e + 96];
                 const double x0 = __ldg(&x[c0]), x1 = __ldg(&x[c1]), x2 = __ldg(&x[c2]),
                              x3 = __ldg(&x[c3]);
@@ -372,7 +391,7 @@ k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict_
             }
             for (; j < n; ++j) {
                 const int64_t e = base + 32 * (int64_t)j;
-                const int c0 = col[e];
+                const int c0 = ell_col<C16>(E, e);
                 const double a0 = val[e];
                 acc = __dadd_rn(acc, __dmul_rn(a0, __ldg(&x[c0])));
                 if (INIT) sa = __dadd_rn(sa, a0);
@@ -1123,9 +1142,10 @@ struct ColourRows {
                  r = (CR).segStart[t_ * (CR).C + (CR).c] + (w_ - t_ * (CR).bps) * kBlock + (int)threadIdx.x; \
              r < e_; r += (CR).bps * kBlock)
 
+template <bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_dic_calc_rd(ColourRows cr, const int64_t* __restrict__ sliceBase,
-              const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+              const uint32_t* __restrict__ rowLen, EllCols E,
               const double* __restrict__ val, const double* __restrict__ diag,
               double* __restrict__ rD) {
     B200_FOR_COLOUR_ROWS(cr, r) {
@@ -1136,17 +1156,17 @@ k_dic_calc_rd(ColourRows cr, const int64_t* __restrict__ sliceBase,
             const int64_t e = base + 32 * (int64_t)j;
             const double a = val[e];
             // rD of an earlier colour was written by an earlier launch: plain (coherent) load
-            d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(a, a), rD[col[e]]));
+            d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(a, a), rD[ell_col<C16>(E, e)]));
         }
         rD[r] = d;
     }
 }
 
 // forward sweep over one colour.  DOT: this colour's wA is final (last colour) -> add (wA, rA).
-template <bool DOT>
+template <bool DOT, bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_dic_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
-          const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+          const uint32_t* __restrict__ rowLen, EllCols E,
           const double* __restrict__ val, const double* __restrict__ rD,
           const double* __restrict__ rA, double* wA, Reduce R) {
     if (R.S->done) return;
@@ -1159,7 +1179,7 @@ k_dic_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
         double w = __dmul_rn(d, rr);
         for (int j = 0; j < nLower; ++j) {
             const int64_t e = base + 32 * (int64_t)j;
-            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[col[e]]));
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[ell_col<C16>(E, e)]));
         }
         wA[r] = w;
         if (DOT) s[0] = __dadd_rn(s[0], __dmul_rn(w, rr));
@@ -1168,9 +1188,10 @@ k_dic_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
 }
 
 // backward sweep over one colour; wA of this colour becomes final -> always add (wA, rA).
+template <bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_dic_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
-          const uint32_t* __restrict__ rowLen, const int* __restrict__ col,
+          const uint32_t* __restrict__ rowLen, EllCols E,
           const double* __restrict__ val, const double* __restrict__ rD,
           const double* __restrict__ rA, double* wA, Reduce R) {
     if (R.S->done) return;
@@ -1183,7 +1204,7 @@ k_dic_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
         double w = wA[r];
         for (int j = nTotal - 1; j >= nLower; --j) {
             const int64_t e = base + 32 * (int64_t)j;
-            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[col[e]]));
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), wA[ell_col<C16>(E, e)]));
         }
         wA[r] = w;
         s[0] = __dadd_rn(s[0], __dmul_rn(w, rA[r]));

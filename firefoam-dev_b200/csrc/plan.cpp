@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -365,6 +366,42 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
         const int64_t base = P.sliceBase[r / 32] + (r % 32);
         const int64_t width = (P.sliceBase[r / 32 + 1] - P.sliceBase[r / 32]) / 32;
         for (int64_t jj = 0; jj < width; ++jj) P.col[base + 32 * jj] = 0;
+    }
+
+    // ---- 16-bit column offsets per (slice, entry) ---------------------------------------------
+    if (N > 0 && P.nEntries > 0) {
+        P.colBase.assign((size_t)(P.nEntries / 32), -1);
+        P.col16.assign((size_t)P.nEntries, 0);
+        int64_t fit = 0, total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : fit, total)
+        for (int32_t sl = 0; sl < P.nSlices; ++sl) {
+            const int64_t b0 = P.sliceBase[sl];
+            const int64_t width = (P.sliceBase[sl + 1] - b0) / 32;
+            const int32_t r0 = sl * 32, r1 = std::min(N, sl * 32 + 32);
+            for (int64_t j = 0; j < width; ++j) {
+                int32_t lo = INT32_MAX, hi = -1;
+                for (int32_t r = r0; r < r1; ++r)
+                    if ((int64_t)(P.rowLen[r] >> 16) > j) {
+                        const int32_t c = P.col[b0 + 32 * j + (r - r0)];
+                        lo = std::min(lo, c);
+                        hi = std::max(hi, c);
+                    }
+                if (hi < 0) continue;          // no row of the slice has a j-th entry
+                ++total;
+                if ((int64_t)hi - lo < 65536) {
+                    ++fit;
+                    P.colBase[(size_t)(b0 / 32 + j)] = lo;
+                    for (int32_t r = r0; r < r1; ++r)
+                        if ((int64_t)(P.rowLen[r] >> 16) > j)
+                            P.col16[b0 + 32 * j + (r - r0)] = (uint16_t)(P.col[b0 + 32 * j + (r - r0)] - lo);
+                }
+            }
+        }
+        P.col16Fraction = total ? (double)fit / (double)total : 0.0;
+        if (fit == 0) {
+            std::vector<int32_t>().swap(P.colBase);
+            std::vector<uint16_t>().swap(P.col16);
+        }
     }
 
     // ---- symmetric single-read layout -----------------------------------------------------

@@ -99,6 +99,15 @@ struct HostPlan {
     std::vector<uint32_t> rowLen;      // [N]  nLower | nTotal<<16
     std::vector<int32_t> col;          // [nEntries] internal column (padding: the row itself)
     std::vector<int32_t> faceOf;       // [nEntries] natural face index, -1 for padding
+    // 16-bit columns: the j-th neighbours of the 32 rows of a slice usually lie within 65 536 rows of
+    // each other (banded / RCM / colour-major orders), so the kernels that are bound by the bytes of
+    // the full-row ELL (Amul on permuted orders, DIC-class sweeps) read a 2-byte offset from a
+    // per-(slice, j) base instead of the 4-byte column: 10 instead of 12 bytes per entry.
+    // colBase[sliceBase[s]/32 + j] = smallest column of that slice entry, or -1 when the range does not
+    // fit (the kernel then reads `col`).  Empty when no slice entry fits.
+    std::vector<int32_t> colBase;      // [nEntries/32]
+    std::vector<uint16_t> col16;       // [nEntries]
+    double col16Fraction = 0;          // share of the slice entries that use the 16-bit form
     // interfaces (internal numbering); slot = position in the concatenation of all patches
     int32_t nIfaces = 0;
     std::vector<int32_t> nbrRank;      // [nIfaces]

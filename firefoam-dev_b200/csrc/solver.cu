@@ -96,6 +96,10 @@ struct DevPlan {
     double* val = nullptr;
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
+    // 16-bit column offsets (plan.hpp colBase / col16) for the ELL-bound kernels
+    uint16_t* col16 = nullptr;
+    int* colBase = nullptr;
+    bool c16 = false;
     int* colourStart = nullptr;   // device copy of h.colourStart (k_pcg_small)
     int* segStart = nullptr;      // device copy of h.segStart ((tile, colour) row segments)
     int tileShift = 31;           // log2(tileRows) of a tiled multicolour plan, else 31
@@ -186,6 +190,7 @@ struct b200_ctx {
     bool disableFast = false;     // B200PCG_SMALL_FAST=0: always the L2-resident k_pcg_small
     int fastMaxCtas = 16;         // B200PCG_FAST_CTAS: largest cluster the on-chip kernel may use
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
+    bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
     bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
@@ -298,6 +303,7 @@ void free_plan(DevPlan& P) {
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
+    dev_free(P.col16); dev_free(P.colBase); P.c16 = false;
     dev_free(P.sUCol); dev_free(P.sUFace);
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8); dev_free(P.sLRank);
     P.symRanked = false;
@@ -343,6 +349,11 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     RET(upload(ctx, &P.bRow, P.h.bRow));
     RET(upload(ctx, &P.bStart, P.h.bStart));
     RET(upload(ctx, &P.bSlot, P.h.bSlot));
+    if (!P.h.colBase.empty() && P.h.col16Fraction == 1.0 && !ctx->disableCol16) {   // all-or-nothing (kernels.cuh)
+        RET(upload(ctx, &P.col16, P.h.col16));
+        RET(upload(ctx, &P.colBase, P.h.colBase));
+        P.c16 = true;
+    }
     RET(upload(ctx, &P.colourStart, P.h.colourStart));
     if (P.h.segStart.empty()) P.h.segStart = P.h.colourStart;   // Natural: one segment
     RET(upload(ctx, &P.segStart, P.h.segStart));
@@ -424,6 +435,8 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
 
     // release the big host arrays
     std::vector<int32_t>().swap(P.h.col);
+    std::vector<uint16_t>().swap(P.h.col16);
+    std::vector<int32_t>().swap(P.h.colBase);
     std::vector<int32_t>().swap(P.h.faceOf);
     std::vector<uint32_t>().swap(P.h.rowLen);
     std::vector<int64_t>().swap(P.h.sliceBase);
@@ -542,9 +555,16 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
                P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
     } else {
-        auto kern = k_spmv<INIT, DOT>;
-        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen,
-               P.col, P.val, ctx->diag, x, y, sA, R);
+        const EllCols E{P.col, P.col16, P.colBase};
+        if (P.c16) {
+            auto kern = k_spmv<INIT, DOT, true>;
+            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val,
+                   ctx->diag, x, y, sA, R);
+        } else {
+            auto kern = k_spmv<INIT, DOT, false>;
+            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val,
+                   ctx->diag, x, y, sA, R);
+        }
     }
     if (halo) {
         CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
@@ -638,19 +658,30 @@ int enqueue_precondition(b200_ctx* ctx, DevPlan& P, int precond, bool firstColou
             const ColourRows cr = colour_rows(ctx, P, k, &g);
             const bool last = (k == C - 1);
             Reduce R = mkR(ctx, (last && C == 1) ? STEP_WARA : STEP_NONE);
-            if (last) {
-                auto kf = k_dic_fwd<true>;
-                LAUNCH(PC_DIC_FWD, kf, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
-            } else {
-                auto kf = k_dic_fwd<false>;
-                LAUNCH(PC_DIC_FWD, kf, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
-            }
+            const EllCols E{P.col, P.col16, P.colBase};
+#define B200_FWD(DOT_, C16_)                                                                             \
+    do {                                                                                                 \
+        auto kf = k_dic_fwd<DOT_, C16_>;                                                                 \
+        LAUNCH(PC_DIC_FWD, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->w, R);       \
+    } while (0)
+            if (last && P.c16) B200_FWD(true, true);
+            else if (last) B200_FWD(true, false);
+            else if (P.c16) B200_FWD(false, true);
+            else B200_FWD(false, false);
+#undef B200_FWD
         }
         for (int k = C - 2; k >= 0; --k) {
             int g;
             const ColourRows cr = colour_rows(ctx, P, k, &g);
             Reduce R = mkR(ctx, k == 0 ? STEP_WARA : STEP_NONE);
-            LAUNCH(PC_DIC_BWD, k_dic_bwd, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->rD, ctx->r, ctx->w, R);
+            const EllCols E{P.col, P.col16, P.colBase};
+            if (P.c16) {
+                auto kb = k_dic_bwd<true>;
+                LAUNCH(PC_DIC_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->w, R);
+            } else {
+                auto kb = k_dic_bwd<false>;
+                LAUNCH(PC_DIC_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->w, R);
+            }
         }
     }
     RET(reduce_post(ctx, STEP_WARA));
@@ -836,7 +867,14 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         for (int k = 0; k < P.h.nColours; ++k) {
             int g;
             const ColourRows cr = colour_rows(ctx, P, k, &g);
-            LAUNCH(PC_DIC_RD, k_dic_calc_rd, g, cr, P.sliceBase, P.rowLen, P.col, P.val, ctx->diag, ctx->rD);
+            const EllCols E{P.col, P.col16, P.colBase};
+            if (P.c16) {
+                auto kd = k_dic_calc_rd<true>;
+                LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->rD);
+            } else {
+                auto kd = k_dic_calc_rd<false>;
+                LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->rD);
+            }
         }
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
     }
@@ -982,6 +1020,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
     if (const char* e14 = getenv("B200PCG_FAST_CTAS")) c->fastMaxCtas = std::max(1, atoi(e14));
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
+    if (const char* e15 = getenv("B200PCG_COL16")) c->disableCol16 = atoi(e15) == 0;
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
@@ -1432,13 +1471,15 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
                   "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
                   "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d, "
-                  "\"multicolour_tiles\": %d, \"multicolour_tile_rows\": %d, \"multicolour_amul\": \"%s\"}",
+                  "\"multicolour_tiles\": %d, \"multicolour_tile_rows\": %d, \"multicolour_amul\": \"%s\", "
+                  "\"ell_col16_fraction_natural\": %.3f, \"ell_col16_fraction_multicolour\": %.3f}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
                   P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN,
                   ctx->plans[1].built ? ctx->plans[1].h.nTiles : 0, ctx->plans[1].built ? ctx->plans[1].h.tileRows : 0,
-                  !ctx->plans[1].built ? "n/a" : (ctx->plans[1].sym ? (ctx->plans[1].symTma ? "k_spmv_sym_tma" : "k_spmv_sym") : "k_spmv"));
+                  !ctx->plans[1].built ? "n/a" : (ctx->plans[1].sym ? (ctx->plans[1].symTma ? "k_spmv_sym_tma" : "k_spmv_sym") : "k_spmv"),
+                  P.c16 ? P.h.col16Fraction : 0.0, ctx->plans[1].c16 ? ctx->plans[1].h.col16Fraction : 0.0);
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

@@ -13,7 +13,7 @@ class PlanView:
     """HostPlan (csrc/plan.cpp) pulled out through the host-only debug ABI."""
 
     NAMES = ["perm", "iperm", "colourStart", "sliceBase", "rowLen", "col", "faceOf", "nbrRank",
-             "patchStart", "slotRow", "bRow", "bStart", "bSlot", "segStart", "rowColour"]
+             "patchStart", "slotRow", "bRow", "bStart", "bSlot", "segStart", "rowColour", "colBase", "col16"]
 
     def __init__(self, ordering, addr, renumber=0, tileRows=0):
         """renumber: 0 off (the default of the host-only debug ABI), -1 auto, 1 force RCM;
@@ -63,7 +63,7 @@ class PlanView:
                 ptr, eb = C.c_void_p(), C.c_int32()
                 n = L.b200_debug_plan_get(h, nm.encode(), C.byref(ptr), C.byref(eb))
                 assert n >= 0, nm
-                dt = {4: np.int32, 8: np.int64}[eb.value] if nm != "rowLen" else np.uint32
+                dt = {2: np.uint16, 4: np.int32, 8: np.int64}[eb.value] if nm != "rowLen" else np.uint32
                 if n == 0:
                     arr = np.empty(0, dtype=dt)
                 else:

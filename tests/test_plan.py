@@ -87,6 +87,29 @@ def test_spmv_emulation_permuted(name, s):
         np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-15)
 
 
+@pytest.mark.parametrize("name,s", list(systems()) + [("poly", mg.bcc_poly(5, 4, 6)), ("hex-larger", mg.hex_block(40, 9, 8))])
+def test_16bit_column_offsets(name, s):
+    """colBase[slice entry] + col16[entry] reproduces the 32-bit column wherever the slice entry is marked
+    as fitting; wide entries (-1) keep the 32-bit column; padding lanes are never marked."""
+    for ordering, ren in ((NAT, 0), (NAT, 1), (MC, 0), (MC, 1), (LEV, 0)):
+        P = PlanView(ordering, s.addr, renumber=ren)
+        if P.colBase.size == 0:
+            continue
+        assert P.colBase.size == P.nEntries // 32 and P.col16.size == P.nEntries
+        for r in range(s.addr.nCells):
+            for j in range(P.nTotal[r]):
+                e = P.entry(r, j)
+                b = P.colBase[e >> 5]
+                if b >= 0:
+                    assert b + int(P.col16[e]) == P.col[e]
+        # on these small meshes every entry fits
+        used = np.zeros(P.nEntries // 32, dtype=bool)
+        for r in range(s.addr.nCells):
+            for j in range(P.nTotal[r]):
+                used[P.entry(r, j) >> 5] = True
+        assert np.all(P.colBase[used] >= 0) and np.all(P.colBase[~used] == -1)
+
+
 def test_rcm_renumbering_decision():
     """Auto mode renumbers a cache-hostile numbering (block-shuffled polyhedra) and leaves banded
     ones (lexicographic hex) alone; Levels (DIC-exact) is never renumbered."""
