@@ -74,3 +74,19 @@ def test_rcb_on_irregular_graph_amul():
             L[(p, itf.neighbProcNo)] = sub.bou[k]
     for (p, q), b in L.items():
         assert np.array_equal(b, L[(q, p)])
+
+
+def test_decomposed_submeshes_carry_the_laplacian_inputs():
+    """decompose() hands every rank the fvm::laplacian inputs of its sub-mesh (bench.py --workload poly at
+    N > 1): assembling them with the oracle reproduces the rank's share of the global matrix -- upper
+    bit for bit, diag to rounding (the cut faces enter through the processor patches' internalCoeffs)."""
+    full = mg.bcc_poly(6, 5, 7)
+    subs = mg.decompose(full, mg.partition_rcb(full.xyz, 4), 4)
+    assert sum(s.addr.nCells for s in subs) == full.addr.nCells
+    for s in subs:
+        a = s.addr
+        up, dg = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf, s.deltaCoeffs,
+                                        s.sign, s.diag0)
+        assert np.array_equal(up, s.upper)
+        np.testing.assert_allclose(dg, s.diag, rtol=1e-13)
+        assert len(s.bou) == len(a.interfaces) > 0
