@@ -156,7 +156,9 @@ Foam::solverPerformance Foam::B200PCG::solve
             )
         );
         ctl.precond =
-            (mode == "exact") ? B200_PRECOND_DIC_EXACT : B200_PRECOND_DIC_MC;
+            (mode == "exact") ? B200_PRECOND_DIC_EXACT
+          : (mode == "eisenstat") ? B200_PRECOND_DIC_MC_EIS
+          : B200_PRECOND_DIC_MC;
     }
     else
     {

@@ -66,6 +66,7 @@ const char* precond_name(int p) {
         case B200_PRECOND_DIAGONAL: return "diagonal";
         case B200_PRECOND_DIC_MC: return "DIC";
         case B200_PRECOND_DIC_EXACT: return "DIC";
+        case B200_PRECOND_DIC_MC_EIS: return "DIC";
         default: return "unknown";
     }
 }

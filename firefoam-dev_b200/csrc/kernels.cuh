@@ -33,8 +33,17 @@ enum Step : int {
     STEP_WARA,     // wArA = (wA, rA); beta
     STEP_WAPA,     // wApA = (wA, pA); singularity; alpha
     STEP_RES,      // final residual; nIter++; convergence
-    STEP_RES_WARA  // STEP_RES, then (if the loop continues) STEP_WARA of the next iteration
+    STEP_RES_WARA, // STEP_RES, then (if the loop continues) STEP_WARA of the next iteration
+    // Eisenstat form of the DIC-class PCG (k_eis_* kernels)
+    STEP_EIS_RHO0, // rho_0 = (r^, D~ r^); calibrates the true-residual predictor
+    STEP_EIS_RHO,  // rho_k; beta; nIter++; decides whether this iteration needs a true-residual check
+    STEP_EIS_RES   // true residual |(D~+L) r^|_1 / normFactor; convergence; loop condition
 };
+
+// Eisenstat form: the true residual is evaluated when the predictor cRatio*sqrt(|rho|) is within
+// kEisMargin of the convergence threshold, and at least every kEisEvery iterations (re-calibration).
+constexpr double kEisMargin = 8.0;
+constexpr int kEisEvery = 32;
 
 struct Scalars {
     // controls (written by the host before each solve)
@@ -51,6 +60,10 @@ struct Scalars {
     double gsums[kNSums];  // global totals (== sums when nranks == 1)
     unsigned int ticket;
     unsigned int pad1;
+    // Eisenstat form (STEP_EIS_*): predictor ratio  true residual / sqrt(|rho|)  at the last check,
+    // iterations since that check, and whether the current iteration's check kernel has to run
+    double cRatio;
+    int sinceCheck, needCheck;
     // number of cross-rank reductions this rank has EXECUTED (peer_allreduce_step).  Every rank
     // executes the same sequence (identical totals -> identical `done` decisions), so the counters
     // stay equal across ranks, and consecutive executed reductions strictly alternate buffer parity --
@@ -142,6 +155,55 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
             }
             break;
         }
+        case STEP_EIS_RHO0: {
+            S->wArA = g[0];
+            S->beta = 0.0;
+            const double a = sqrt(fabs(g[0]));
+            S->cRatio = a > 0.0 ? S->finalRes / a : 0.0;   // 0: predictor says "converged" -> always check
+            S->sinceCheck = 0;
+            S->needCheck = 0;
+            break;
+        }
+        case STEP_EIS_RHO: {
+            S->wArAold = S->wArA;
+            S->wArA = g[0];
+            S->beta = S->wArA / S->wArAold;
+            const int old = S->nIter;
+            S->nIter = old + 1;
+            S->sinceCheck += 1;
+            if (!(g[0] == g[0]) || fabs(g[0]) > 1.7e308) {
+                S->nonfinite = 1;
+                S->needCheck = 0;
+                S->done = 1;
+                break;
+            }
+            // the do/while cannot continue whatever the residual turns out to be -> final check
+            const bool mustStop = S->forceIters > 0 ? (S->nIter >= S->forceIters) : !(old < S->maxIter);
+            double thr = S->tol;
+            if (S->relTol > 1e-20 && S->relTol * S->initRes > thr) thr = S->relTol * S->initRes;
+            const bool nearThr = S->forceIters > 0 ? false : (S->cRatio * sqrt(fabs(g[0])) < kEisMargin * thr);
+            S->needCheck = (mustStop || nearThr || S->sinceCheck >= kEisEvery) ? 1 : 0;
+            break;
+        }
+        case STEP_EIS_RES: {
+            S->finalRes = g[0] / S->normFactor;
+            const bool conv = check_convergence(S);
+            S->converged = conv ? 1 : 0;
+            const int old = S->nIter - 1;
+            bool cont;
+            if (S->forceIters > 0) cont = S->nIter < S->forceIters;
+            else cont = (old < S->maxIter && !conv) || (S->nIter < S->minIter);
+            if (!(S->finalRes == S->finalRes) || fabs(S->finalRes) > 1.7e308) {
+                S->nonfinite = 1;
+                cont = false;
+            }
+            if (!cont) S->done = 1;
+            const double a = sqrt(fabs(S->wArA));
+            S->cRatio = a > 0.0 ? S->finalRes / a : 0.0;
+            S->sinceCheck = 0;
+            S->needCheck = 0;
+            break;
+        }
         default:
             break;
     }
@@ -151,6 +213,7 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
 __global__ void k_scalar_step(Scalars* S, int step) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (S->done && step != STEP_SUMPSI && step != STEP_NORM) return;
+    if (step == STEP_EIS_RES && !S->needCheck) return;   // the check kernel did not run
     scalar_step(step, S, S->gsums);
 }
 
@@ -1208,6 +1271,246 @@ k_dic_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
         }
         wA[r] = w;
         s[0] = __dadd_rn(s[0], __dmul_rn(w, rA[r]));
+    }
+    reduce_finish<1>(s, R);
+}
+
+// ---- Eisenstat form of the DIC-class PCG (B200_PRECOND_DIC_MC_EIS) ----------------------------
+// The DIC-class preconditioner is M = (D~ + L) D~^-1 (D~ + L^T): L = the matrix's OWN strictly-lower
+// part in the colour-major elimination order, D~ = the DIC diagonal (rD = 1/D~).  For exactly that
+// shape Eisenstat's identity removes the separate Amul from the iteration: with
+//     r^ = (D~+L)^-1 r,   p^ = (D~+L^T) p,   A = (D~+L) + (D - 2 D~) + (D~+L^T) [+ B: processor interfaces]
+// PCG on A preconditioned by M is PCG on A^ = (D~+L)^-1 A (D~+L^T)^-1 preconditioned by D~, and
+//     t  = (D~+L^T)^-1 p^                         backward sweep (t IS the untransformed search direction p)
+//     w^ = A^ p^ = t + (D~+L)^-1 (p^ + (D - 2D~) t [+ B t])      forward sweep
+// so one iteration is   k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps -> k_eis_r,
+// every matrix entry is read ONCE per sweep, and psi += alpha*t is updated directly in the
+// untransformed variable.  Same iterates as the three-kernel DIC-class loop in exact arithmetic
+// (same preconditioner, same Krylov space); the rounding differs, which the DIC-class parity bar
+// (solution within 1e-8 relative L2 at the same residual tolerance) allows.
+// OpenFOAM's convergence test needs |r|_1 of the TRUE residual r = (D~+L) r^, a third pass over L.  It is
+// evaluated by k_eis_res only when the device-side predictor  cRatio * sqrt(|rho|)  (rho = (r^, D~ r^) is
+// free; cRatio is re-calibrated at every evaluation) comes within kEisMargin of the threshold, and at
+// least every kEisEvery iterations; the solve only ever stops on an evaluated true residual.
+// Vectors: rh = r^, ph = p^, t, y (= (D~+L)^-1 rhs for the rows of all colours but the last; the last
+// colour's rows, which no sweep gathers, hold w^ = t + y), dT = D~, e = D - 2 D~.
+
+// once per solve: rD = 1/D~, e = D - 2 D~
+__global__ void __launch_bounds__(kBlock)
+k_eis_setup(int N, const double* __restrict__ diag, const double* __restrict__ dT,
+            double* __restrict__ rD, double* __restrict__ e) {
+    B200_VEC_LOOP(N,
+        { const double2 d = reinterpret_cast<const double2*>(diag)[i];
+          const double2 dt = reinterpret_cast<const double2*>(dT)[i];
+          reinterpret_cast<double2*>(rD)[i] = make_double2(__ddiv_rn(1.0, dt.x), __ddiv_rn(1.0, dt.y));
+          reinterpret_cast<double2*>(e)[i] = make_double2(__dadd_rn(d.x, -__dmul_rn(2.0, dt.x)),
+                                                          __dadd_rn(d.y, -__dmul_rn(2.0, dt.y))); },
+        { rD[i] = __ddiv_rn(1.0, dT[i]); e[i] = __dadd_rn(diag[i], -__dmul_rn(2.0, dT[i])); })
+}
+
+// once per solve, one launch per colour, in place: rh = (D~+L)^-1 r
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_init_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+               EllCols E, const double* __restrict__ val, const double* __restrict__ rD, double* rh,
+               const Scalars* S) {
+    if (S->done) return;
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        const double d = rD[r];
+        double w = __dmul_rn(d, rh[r]);
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), rh[ell_col<C16>(E, e)]));
+        }
+        rh[r] = w;
+    }
+}
+
+// rho_0 = (r^, D~ r^)
+__global__ void __launch_bounds__(kBlock)
+k_eis_rho0(int N, const double* __restrict__ dT, const double* __restrict__ rh, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { const double2 r = reinterpret_cast<const double2*>(rh)[i];
+          const double2 d = reinterpret_cast<const double2*>(dT)[i];
+          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.x, r.x), r.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.y, r.y), r.y)); },
+        { s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(dT[i], rh[i]), rh[i])); })
+    reduce_finish<1>(s, R);
+}
+
+// psi += alpha_prev * t_prev (deferred, as in k_p);  p^ = D~ r^ + beta p^;  and the backward sweep of the
+// LAST colour (rows >= lastStart have no later neighbours): t = rD * p^.
+__global__ void __launch_bounds__(kBlock)
+k_eis_p(int N, int lastStart, double* __restrict__ psi, double* __restrict__ ph,
+        const double* __restrict__ rh, const double* __restrict__ dT, const double* __restrict__ rD,
+        double* t, const Scalars* S) {
+    if (S->done) return;
+    const bool first = (S->nIter == 0);
+    const double beta = S->beta;
+    const double alpha = S->alpha;
+    B200_VEC_LOOP(N,
+        { const double2 r = reinterpret_cast<const double2*>(rh)[i];
+          const double2 d = reinterpret_cast<const double2*>(dT)[i];
+          double2 p;
+          p.x = __dmul_rn(d.x, r.x); p.y = __dmul_rn(d.y, r.y);
+          if (!first) {
+              const double2 po = reinterpret_cast<const double2*>(ph)[i];
+              const double2 tv = reinterpret_cast<const double2*>(t)[i];
+              double2 x = reinterpret_cast<double2*>(psi)[i];
+              x.x = __dadd_rn(x.x, __dmul_rn(alpha, tv.x));
+              x.y = __dadd_rn(x.y, __dmul_rn(alpha, tv.y));
+              reinterpret_cast<double2*>(psi)[i] = x;
+              p.x = __dadd_rn(p.x, __dmul_rn(beta, po.x));
+              p.y = __dadd_rn(p.y, __dmul_rn(beta, po.y));
+          }
+          reinterpret_cast<double2*>(ph)[i] = p;
+          if (2 * i + 1 >= lastStart) {
+              const double2 rd = reinterpret_cast<const double2*>(rD)[i];
+              if (2 * i >= lastStart)
+                  reinterpret_cast<double2*>(t)[i] = make_double2(__dmul_rn(rd.x, p.x), __dmul_rn(rd.y, p.y));
+              else
+                  t[2 * i + 1] = __dmul_rn(rd.y, p.y);
+          } },
+        { double p = __dmul_rn(dT[i], rh[i]);
+          if (!first) {
+              psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, t[i]));
+              p = __dadd_rn(p, __dmul_rn(beta, ph[i]));
+          }
+          ph[i] = p;
+          if (i >= lastStart) t[i] = __dmul_rn(rD[i], p); })
+}
+
+// backward sweep over one colour: t = rD*(p^ - L^T t).  FWD0 (first colour, single rank): its rows have
+// no earlier neighbours, so their forward sweep y = rD*(p^ + e t) and their share of (p^, w^) ride along.
+template <bool FWD0, bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          EllCols E, const double* __restrict__ val, const double* __restrict__ rD,
+          const double* __restrict__ ph, const double* __restrict__ ev, double* t, double* __restrict__ y,
+          Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const uint32_t len = rowLen[r];
+        const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+        const double d = rD[r];
+        const double p = ph[r];
+        double w = __dmul_rn(d, p);
+        for (int j = nTotal - 1; j >= nLower; --j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), t[ell_col<C16>(E, e)]));
+        }
+        t[r] = w;
+        if (FWD0) {
+            const double yv = __dmul_rn(d, __dadd_rn(p, __dmul_rn(ev[r], w)));
+            y[r] = yv;
+            s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(w, yv)));
+        }
+    }
+    if (FWD0) reduce_finish<1>(s, R);
+}
+
+// halo term of the forward right-hand side (nranks > 1): hb[b] = (B t)[bRow[b]] = -sum bou*t_nbr over the
+// row's processor faces in (patch, face) order (the sorted-segment form of updateMatrixInterfaces)
+__global__ void __launch_bounds__(kBlock)
+k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ bSlot,
+           const double* __restrict__ bou, const double* __restrict__ recv, double* __restrict__ hb,
+           const Scalars* S) {
+    if (S->done) return;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
+            const int slot = bSlot[e];
+            acc = __dadd_rn(acc, -__dmul_rn(bou[slot], recv[slot]));
+        }
+        hb[b] = acc;
+    }
+}
+
+// forward sweep over one colour: y = rD*(p^ + e t [+ B t] - L y); every colour adds its share of
+// (p^, w^), w^ = t + y.  LAST: rows of the last colour are gathered by no sweep and store w^.
+template <bool LAST, bool HALO, bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          EllCols E, const double* __restrict__ val, const double* __restrict__ rD,
+          const double* __restrict__ ph, const double* __restrict__ ev, const double* __restrict__ t,
+          double* y, const int* __restrict__ rowB, const double* __restrict__ hb, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        const double d = rD[r];
+        const double p = ph[r];
+        const double tv = t[r];
+        double rhs = __dadd_rn(p, __dmul_rn(ev[r], tv));
+        if (HALO) {
+            const int b = rowB[r];
+            if (b >= 0) rhs = __dadd_rn(rhs, hb[b]);
+        }
+        double w = __dmul_rn(d, rhs);
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), y[ell_col<C16>(E, e)]));
+        }
+        const double wh = __dadd_rn(tv, w);
+        y[r] = LAST ? wh : w;
+        s[0] = __dadd_rn(s[0], __dmul_rn(p, wh));
+    }
+    reduce_finish<1>(s, R);
+}
+
+// r^ -= alpha w^ (w^ = t + y below lastStart, stored as such from lastStart on); rho = (r^, D~ r^)
+__global__ void __launch_bounds__(kBlock)
+k_eis_r(int N, int lastStart, double* __restrict__ rh, const double* __restrict__ y,
+        const double* __restrict__ t, const double* __restrict__ dT, Reduce R) {
+    if (R.S->done) return;
+    const double alpha = R.S->alpha;
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { double2 r = reinterpret_cast<double2*>(rh)[i];
+          double2 w = reinterpret_cast<const double2*>(y)[i];
+          if (2 * i < lastStart) {
+              const double2 tv = reinterpret_cast<const double2*>(t)[i];
+              w.x = __dadd_rn(tv.x, w.x);
+              if (2 * i + 1 < lastStart) w.y = __dadd_rn(tv.y, w.y);
+          }
+          const double2 d = reinterpret_cast<const double2*>(dT)[i];
+          r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
+          r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
+          reinterpret_cast<double2*>(rh)[i] = r;
+          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.x, r.x), r.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.y, r.y), r.y)); },
+        { double w = y[i];
+          if (i < lastStart) w = __dadd_rn(t[i], w);
+          const double r = __dadd_rn(rh[i], -__dmul_rn(alpha, w));
+          rh[i] = r;
+          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(dT[i], r), r)); })
+    reduce_finish<1>(s, R);
+}
+
+// true residual of the iteration, only when the scalar step asked for it: sum |(D~ + L) r^|
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_res(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
+          const double* __restrict__ val, const double* __restrict__ dT, const double* __restrict__ rh,
+          Reduce R) {
+    if (R.S->done || !R.S->needCheck) return;
+    double s[1] = {0.0};
+    for (int r = blockIdx.x * kBlock + threadIdx.x; r < N; r += gridDim.x * kBlock) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        double acc = __dmul_rn(dT[r], rh[r]);
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            acc = __dadd_rn(acc, __dmul_rn(val[e], __ldg(&rh[ell_col<C16>(E, e)])));
+        }
+        s[0] = __dadd_rn(s[0], fabs(acc));
     }
     reduce_finish<1>(s, R);
 }

@@ -78,13 +78,15 @@ NcclApi g_nccl;
 enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
-    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH, PC_COUNT
+    PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH,
+    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
     "norm_resid", "recip", "precond_dot", "dic_calc_rd", "dic_fwd",
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
-    "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells"};
+    "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells",
+    "eis_setup", "eis_p_psi_update", "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual"};
 
 struct DevPlan {
     bool built = false;
@@ -119,6 +121,9 @@ struct DevPlan {
     uint32_t* sLRef = nullptr;
     uint8_t* sLRank = nullptr;    // ranked form (renumbered natural plans)
     bool symRanked = false;
+    // Eisenstat form, nranks > 1: interface-row index of every row (-1: none) and the halo term B t
+    int* rowB = nullptr;
+    double* hb = nullptr;
 };
 
 struct HostIface {
@@ -148,6 +153,7 @@ struct b200_ctx {
     // vectors (internal order)
     double *diag = nullptr, *src = nullptr, *psi = nullptr, *r = nullptr, *p = nullptr,
            *w = nullptr, *rD = nullptr;
+    double *t = nullptr, *dT = nullptr, *eD = nullptr;   // Eisenstat form: t, D~, D - 2 D~ (allocated on first use)
     double *bou = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
     // staging for the host entry points (natural order)
     double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
@@ -306,6 +312,7 @@ void free_plan(DevPlan& P) {
     dev_free(P.col16); dev_free(P.colBase); P.c16 = false;
     dev_free(P.sUCol); dev_free(P.sUFace);
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8); dev_free(P.sLRank);
+    dev_free(P.rowB); dev_free(P.hb);
     P.symRanked = false;
     P.sym = false;
     P.built = false;
@@ -316,7 +323,7 @@ void free_mesh(b200_ctx* c) {
     for (auto& P : c->plans) free_plan(P);
     dev_free(c->d_l); dev_free(c->d_u);
     dev_free(c->diag); dev_free(c->src); dev_free(c->psi); dev_free(c->r); dev_free(c->p);
-    dev_free(c->w); dev_free(c->rD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
+    dev_free(c->w); dev_free(c->rD); dev_free(c->t); dev_free(c->dT); dev_free(c->eD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
     dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
     dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3);
     dev_free(c->bfStart); dev_free(c->bfOrder); dev_free(c->scratch);
@@ -728,6 +735,152 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
     return B200_OK;
 }
 
+// ---- Eisenstat form of the DIC-class loop (kernels.cuh "Eisenstat form") ----------------------
+int ensure_eis_buffers(b200_ctx* ctx, DevPlan& P) {
+    if (!ctx->t) {
+        const size_t n = (((size_t)ctx->N + kChunkRows - 1) / kChunkRows + 1) * kChunkRows;
+        RET(dev_alloc(ctx, &ctx->t, n)); RET(dev_alloc(ctx, &ctx->dT, n)); RET(dev_alloc(ctx, &ctx->eD, n));
+        CU(cudaMemsetAsync(ctx->t, 0, n * sizeof(double), ctx->sc));
+    }
+    if (ctx->nranks > 1 && P.nSlots > 0 && !P.rowB) {
+        std::vector<int32_t> rb((size_t)ctx->N, -1);
+        for (int b = 0; b < P.h.nBRows; ++b) rb[(size_t)P.h.bRow[b]] = b;
+        RET(upload(ctx, &P.rowB, rb));
+        RET(dev_alloc(ctx, &P.hb, (size_t)P.h.nBRows));
+        CU(cudaStreamSynchronize(ctx->sc));   // rb goes out of scope
+    }
+    return B200_OK;
+}
+
+// per solve: D~ (DIC recurrence, one launch per colour), rD = 1/D~, e = D - 2 D~, r^ = (D~+L)^-1 r, rho_0
+int eis_setup(b200_ctx* ctx, DevPlan& P) {
+    if (P.h.nTiles > 1)
+        return fail(ctx, B200_EUNSUPPORTED, "dicMode eisenstat needs the colour-major plan (unset B200PCG_TILE)");
+    RET(ensure_eis_buffers(ctx, P));
+    const int N = ctx->N;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    const EllCols E{P.col, P.col16, P.colBase};
+    for (int k = 0; k < P.h.nColours; ++k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        if (P.c16) {
+            auto kd = k_dic_calc_rd<true>;
+            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
+        } else {
+            auto kd = k_dic_calc_rd<false>;
+            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
+        }
+    }
+    LAUNCH(PC_EIS_SETUP, k_eis_setup, gv, N, ctx->diag, ctx->dT, ctx->rD, ctx->eD);
+    for (int k = 0; k < P.h.nColours; ++k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        if (P.c16) {
+            auto kf = k_eis_init_fwd<true>;
+            LAUNCH(PC_EIS_SETUP, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->S);
+        } else {
+            auto kf = k_eis_init_fwd<false>;
+            LAUNCH(PC_EIS_SETUP, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->S);
+        }
+    }
+    Reduce R = mkR(ctx, STEP_EIS_RHO0);
+    LAUNCH(PC_EIS_SETUP, k_eis_rho0, gv, N, ctx->dT, ctx->r, R);
+    RET(reduce_post(ctx, STEP_EIS_RHO0));
+    return B200_OK;
+}
+
+// One loop body: k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps (+ (p^, w^)) ->
+// k_eis_r (+ rho) -> k_eis_res (true residual, device-gated)
+int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
+    const int N = ctx->N;
+    Scalars* S = ctx->S;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    const int C = P.h.nColours;
+    const int lastStart = P.h.colourStart[C - 1];
+    const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
+    const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
+    const EllCols E{P.col, P.col16, P.colBase};
+    LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->psi, ctx->p, ctx->r, ctx->dT, ctx->rD, ctx->t, S);
+    for (int k = C - 2; k >= 0; --k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        Reduce R = mkR(ctx, STEP_NONE);
+#define B200_EBWD(F0_, C16_)                                                                            \
+    do {                                                                                                \
+        auto kb = k_eis_bwd<F0_, C16_>;                                                                 \
+        LAUNCH(PC_EIS_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->eD, ctx->t, \
+               ctx->w, R);                                                                              \
+    } while (0)
+        const bool f0 = fuse0 && k == 0;
+        if (f0 && P.c16) B200_EBWD(true, true);
+        else if (f0) B200_EBWD(true, false);
+        else if (P.c16) B200_EBWD(false, true);
+        else B200_EBWD(false, false);
+#undef B200_EBWD
+    }
+    if (halo) {
+        // t is complete on every rank: pack + exchange on the comm stream, then the halo term B t
+        CU(cudaEventRecord(ctx->evPack, ctx->sc));
+        CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
+        k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, ctx->t, ctx->sendbuf, S);
+        ctx->launches++;
+        NC(g_nccl.GroupStart());
+        for (int k = 0; k < P.h.nIfaces; ++k) {
+            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+            if (n == 0) continue;
+            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+        }
+        NC(g_nccl.GroupEnd());
+        CU(cudaEventRecord(ctx->evRecv, ctx->sm));
+        CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
+        LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
+               ctx->recvbuf, P.hb, S);
+    }
+    for (int k = fuse0 ? 1 : 0; k < C; ++k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        const bool last = (k == C - 1);
+        Reduce R = mkR(ctx, last ? STEP_WAPA : STEP_NONE);
+#define B200_EFWD(L_, H_, C16_)                                                                          \
+    do {                                                                                                 \
+        auto kf = k_eis_fwd<L_, H_, C16_>;                                                               \
+        LAUNCH(PC_EIS_FWD, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->eD, ctx->t,  \
+               ctx->w, P.rowB, P.hb, R);                                                                 \
+    } while (0)
+        const int sel = (last ? 4 : 0) | (halo ? 2 : 0) | (P.c16 ? 1 : 0);
+        switch (sel) {
+            case 0: B200_EFWD(false, false, false); break;
+            case 1: B200_EFWD(false, false, true); break;
+            case 2: B200_EFWD(false, true, false); break;
+            case 3: B200_EFWD(false, true, true); break;
+            case 4: B200_EFWD(true, false, false); break;
+            case 5: B200_EFWD(true, false, true); break;
+            case 6: B200_EFWD(true, true, false); break;
+            default: B200_EFWD(true, true, true); break;
+        }
+#undef B200_EFWD
+    }
+    RET(reduce_post(ctx, STEP_WAPA));
+    {
+        Reduce R = mkR(ctx, STEP_EIS_RHO);
+        LAUNCH(PC_EIS_R, k_eis_r, gv, N, lastStart, ctx->r, ctx->w, ctx->t, ctx->dT, R);
+        RET(reduce_post(ctx, STEP_EIS_RHO));
+    }
+    {
+        Reduce R = mkR(ctx, STEP_EIS_RES);
+        if (P.c16) {
+            auto kr = k_eis_res<true>;
+            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+        } else {
+            auto kr = k_eis_res<false>;
+            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+        }
+        RET(reduce_post(ctx, STEP_EIS_RES));
+    }
+    return B200_OK;
+}
+
 int copy_bou(b200_ctx* ctx, DevPlan& P, const double* const* bouPtrs, cudaMemcpyKind kind, double* dst) {
     for (int k = 0; k < P.h.nIfaces; ++k) {
         const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
@@ -739,7 +892,7 @@ int copy_bou(b200_ctx* ctx, DevPlan& P, const double* const* bouPtrs, cudaMemcpy
 }
 
 Ordering ordering_for(int precond) {
-    if (precond == B200_PRECOND_DIC_MC) return Ordering::MultiColour;
+    if (precond == B200_PRECOND_DIC_MC || precond == B200_PRECOND_DIC_MC_EIS) return Ordering::MultiColour;
     if (precond == B200_PRECOND_DIC_EXACT) return Ordering::Levels;
     return Ordering::Natural;
 }
@@ -770,7 +923,11 @@ int finish_solve(b200_ctx* ctx, DevPlan& P, b200_perf* perf) {
 // The solve proper; all pointers are device pointers in natural order; bou already in ctx->bou.
 int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_src,
                double* dn_psi, const b200_controls* ctl, b200_perf* perf) {
-    if (ctl->precond < 0 || ctl->precond > 3) return fail(ctx, B200_EINVAL, "bad preconditioner code");
+    if (ctl->precond < 0 || ctl->precond > 4) return fail(ctx, B200_EINVAL, "bad preconditioner code");
+    // Eisenstat form of the DIC-class loop: same preconditioner as B200_PRECOND_DIC_MC.  Systems small enough
+    // for the single-launch cluster kernels are latency-bound, not bandwidth-bound: they take that path
+    const bool eis = (ctl->precond == B200_PRECOND_DIC_MC_EIS);
+    const int32_t smallPrecond = eis ? (int32_t)B200_PRECOND_DIC_MC : ctl->precond;
     if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_controls.reserved must be 0");
     DevPlan* Pp = nullptr;
     RET(ensure_plan(ctx, ordering_for(ctl->precond), &Pp));
@@ -800,9 +957,9 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
                 }
             }
         }
-        SmallArgs a{N, ctl->precond, P.h.nColours, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
+        SmallArgs a{N, smallPrecond, P.h.nColours, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
                     ctx->diag, ctx->src, ctx->psi, ctx->r, ctx->p, ctx->w, ctx->rD, S, ctx->partials};
-        FastArgs fa{N, ctl->precond, P.h.nColours, P.maxRowLen, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
+        FastArgs fa{N, smallPrecond, P.h.nColours, P.maxRowLen, P.colourStart, P.sliceBase, P.rowLen, P.col, P.val,
                     ctx->diag, ctx->src, ctx->psi, S};
         int nCtas = std::min(ctx->smallCtas, (N + kSmallBlock - 1) / kSmallBlock);
         if (nCtas > 8) nCtas = 16;
@@ -863,6 +1020,8 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     // preconditioner set-up
     if (ctl->precond == B200_PRECOND_DIAGONAL) {
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->diag, ctx->rD);
+    } else if (eis) {
+        RET(eis_setup(ctx, P));
     } else if (ctl->precond >= B200_PRECOND_DIC_MC) {
         for (int k = 0; k < P.h.nColours; ++k) {
             int g;
@@ -878,7 +1037,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         }
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
     }
-    RET(enqueue_precondition(ctx, P, ctl->precond));   // early-exits on the device if converged
+    if (!eis) RET(enqueue_precondition(ctx, P, ctl->precond));   // early-exits on the device if converged
     CU(cudaEventRecord(ctx->ev[1], ctx->sc));
     CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
@@ -891,14 +1050,17 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     int chunk = 4;
     while (!ctx->hS->done && enq < cap) {
         int n = (int)std::min<int64_t>(chunk, cap - enq);
-        for (int i = 0; i < n; ++i) RET(enqueue_iteration(ctx, P, ctl->precond));
+        for (int i = 0; i < n; ++i) {
+            if (eis) RET(enqueue_eis_iteration(ctx, P));
+            else RET(enqueue_iteration(ctx, P, ctl->precond));
+        }
         enq += n;
         CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
         CU(cudaStreamSynchronize(ctx->sc));
         CU(cudaGetLastError());
         if (chunk < 64) chunk *= 2;
     }
-    LAUNCH(PC_PSI_FINAL, k_psi_final, gv, N, ctx->psi, ctx->p, S);
+    LAUNCH(PC_PSI_FINAL, k_psi_final, gv, N, ctx->psi, eis ? ctx->t : ctx->p, S);   // last deferred psi += alpha*p
     CU(cudaEventRecord(ctx->ev[2], ctx->sc));
     LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
     CU(cudaStreamSynchronize(ctx->sc));

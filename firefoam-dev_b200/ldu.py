@@ -308,8 +308,9 @@ def make_controls(solverControls):
     pre = d.get("preconditioner", "none")
     if isinstance(pre, dict):
         pre = pre.get("preconditioner", "none")
-    if pre == "DIC" and d.get("B200", {}).get("dicMode", "multicolour") == "exact":
-        pre = "DIC-exact"
+    mode = d.get("B200", {}).get("dicMode", "multicolour")
+    if pre == "DIC" and mode in ("exact", "eisenstat"):
+        pre = "DIC-" + mode
     if pre not in PRECOND:
         raise ValueError(f"Unknown symmetric matrix preconditioner {pre}; valid: {sorted(PRECOND)}")
     c = Controls()
@@ -364,5 +365,5 @@ class B200PCG:
         m = self.matrix
         self.ctx.set_addressing(m.lduAddr)
         perf = self.ctx.solve(m.diag, m.upper, self.bou, _f64(source), psi, self.controls)
-        pre = {"none": "none", "diagonal": "diagonal", "DIC": "DIC", "DIC-exact": "DIC"}[self.preconditionerName]
+        pre = {"none": "none", "diagonal": "diagonal", "DIC": "DIC", "DIC-exact": "DIC", "DIC-eisenstat": "DIC"}[self.preconditionerName]
         return SolverPerformance(pre + self.typeName, self.fieldName, perf)

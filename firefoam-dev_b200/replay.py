@@ -17,7 +17,7 @@ from .ldu import LduAddressing, ProcessorLduInterface
 from .meshgen import System
 
 MAGIC = b"B200LDU\x01"
-PRECOND_NAMES = {0: "none", 1: "diagonal", 2: "DIC", 3: "DIC"}
+PRECOND_NAMES = {0: "none", 1: "diagonal", 2: "DIC", 3: "DIC", 4: "DIC"}
 
 
 class DumpedSolve:
@@ -41,8 +41,8 @@ class DumpedSolve:
         self.controls = {"preconditioner": c.get("preconditioner", "none"), "tolerance": c.get("tolerance", 1e-6),
                          "relTol": c.get("relTol", 0.0), "maxIter": c.get("maxIter", 1000),
                          "minIter": c.get("minIter", 0)}
-        if c.get("precondCode") == 3:
-            self.controls["B200"] = {"dicMode": "exact"}
+        if c.get("precondCode") in (3, 4):
+            self.controls["B200"] = {"dicMode": {3: "exact", 4: "eisenstat"}[c["precondCode"]]}
         self.reference = h.get("reference")
         self.fieldName = h.get("fieldName", "")
         self.rank, self.nranks = h.get("rank", 0), h.get("nranks", 1)

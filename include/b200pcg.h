@@ -59,8 +59,12 @@ enum {
     B200_PRECOND_NONE      = 0,  /* `none`      -> noPreconditioner                              */
     B200_PRECOND_DIAGONAL  = 1,  /* `diagonal`  -> diagonalPreconditioner (bit-comparable path)  */
     B200_PRECOND_DIC_MC    = 2,  /* `DIC`       -> multicolour-ordered IC0 ("DIC-class")         */
-    B200_PRECOND_DIC_EXACT = 3   /* `DIC` + `B200{dicMode exact;}` -> level-scheduled DIC with
+    B200_PRECOND_DIC_EXACT = 3,  /* `DIC` + `B200{dicMode exact;}` -> level-scheduled DIC with
                                     the SAME elimination order as OpenFOAM's DICPreconditioner  */
+    B200_PRECOND_DIC_MC_EIS = 4  /* `DIC` + `B200{dicMode eisenstat;}` -> the multicolour IC0 of code 2
+                                    applied in Eisenstat's form: the two triangular sweeps also
+                                    deliver A*p, so the iteration has no separate Amul (same iterates
+                                    as code 2 up to rounding; 1e-8 solution parity bar)            */
 };
 
 typedef struct b200_ctx b200_ctx;

@@ -217,3 +217,175 @@ def hydrostatic_loop(case, laplacian, solve):
         var = case.update(psi)
         out.append((perf.initialResidual, perf.finalResidual, perf.nIterations, var))
     return out
+
+
+# ---- numpy transliteration of the Eisenstat-form DIC-class loop (kernels.cuh k_eis_*) --------------
+EIS_MARGIN, EIS_EVERY = 8.0, 32    # kEisMargin, kEisEvery
+
+
+def _norm_factor(pv, diag_i, val, psi_i, src_i, halo_sumA=None):
+    """lduMatrix::solver::normFactor on the plan's row structure (one rank)."""
+    wA = pv.spmv(diag_i, val, psi_i)
+    sumA = pv.spmv(diag_i, val, np.ones(pv.N))
+    xRef = psi_i.sum() / pv.N
+    nf = (np.abs(wA - sumA * xRef) + np.abs(src_i - sumA * xRef)).sum() + 1e-20
+    return wA, nf
+
+
+def pcg_multicolour_reference(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, minIter=0):
+    """The three-kernel DIC-class loop (PCG.C control flow, multicolour IC0 preconditioner) on the
+    plan's row structure: what B200_PRECOND_DIC_MC computes.  Returns (psi natural, nIter, finalRes)."""
+    val = pv.values(upper)
+    d, b, x = pv.to_internal(diag), pv.to_internal(source), pv.to_internal(psi0)
+    wA, nf = _norm_factor(pv, d, val, x, b)
+    r = b - wA
+    init = final = np.abs(r).sum() / nf
+    conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
+    n = 0
+    if minIter > 0 or not conv():
+        rD = pv.dic_calc_rd(d, val)
+        rho = 1e20
+        p = None
+        while True:
+            rho_old = rho
+            w = pv.dic_precondition(rD, val, r)
+            rho = w @ r
+            p = w.copy() if n == 0 else w + (rho / rho_old) * p
+            w = pv.spmv(d, val, p)
+            alpha = rho / (w @ p)
+            x = x + alpha * p
+            r = r - alpha * w
+            final = np.abs(r).sum() / nf
+            n += 1
+            if not ((n - 1 < maxIter and not conv()) or n < minIter):
+                break
+    return pv.to_natural(x), n, final
+
+
+def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+                           halo=False):
+    """Kernel-by-kernel transliteration of B200_PRECOND_DIC_MC_EIS (solver.cu eis_setup /
+    enqueue_eis_iteration, kernels.cuh k_eis_* and the STEP_EIS_* scalar steps), one rank.
+    halo=True takes the multi-rank kernel selection (no first-colour fusion) with an empty halo term.
+    Returns (psi natural, nIter, finalRes, number of true-residual evaluations)."""
+    N, C = pv.N, pv.nColours
+    val = pv.values(upper)
+    diag_i, src, psi = pv.to_internal(diag), pv.to_internal(source), pv.to_internal(psi0)
+    lastStart = int(pv.colourStart[C - 1])
+    S = dict(done=0, nIter=0, converged=0, singular=0, pendingPsi=0, wArA=1e20, wArAold=1e20, beta=0.0,
+             alpha=0.0, cRatio=0.0, sinceCheck=0, needCheck=0)
+    conv = lambda: S["finalRes"] < tol or (relTol > 1e-20 and S["finalRes"] < relTol * S["initRes"])
+    # spmv_full<INIT> + k_sum + k_norm_resid (STEP_NORM)
+    wA, nf = _norm_factor(pv, diag_i, val, psi, src)
+    rh = src - wA
+    S["normFactor"] = nf
+    S["initRes"] = S["finalRes"] = np.abs(rh).sum() / nf
+    S["converged"] = int(conv())
+    S["done"] = 0 if (minIter > 0 or not S["converged"]) else 1
+    # eis_setup: k_dic_calc_rd per colour -> dT; k_eis_setup; k_eis_init_fwd per colour; k_eis_rho0
+    dT = np.empty(N)
+    for k in range(C):
+        for r in pv.rows_of_colour(k):
+            d = diag_i[r]
+            for j in range(pv.nLower[r]):
+                e = pv.entry(r, j)
+                d = d - (val[e] * val[e]) / dT[pv.col[e]]
+            dT[r] = d
+    rD = 1.0 / dT
+    eD = diag_i - 2.0 * dT
+    if not S["done"]:
+        for k in range(C):
+            for r in pv.rows_of_colour(k):
+                w = rD[r] * rh[r]
+                for j in range(pv.nLower[r]):
+                    e = pv.entry(r, j)
+                    w = w - (rD[r] * val[e]) * rh[pv.col[e]]
+                rh[r] = w
+        g = ((dT * rh) * rh).sum()
+        S["wArA"], S["beta"] = g, 0.0                      # STEP_EIS_RHO0
+        a = np.sqrt(abs(g))
+        S["cRatio"] = S["finalRes"] / a if a > 0 else 0.0
+    ph, t, y = np.zeros(N), np.zeros(N), np.zeros(N)
+    checks = 0
+    fuse0 = (not halo) and C >= 2
+    enq, cap = 0, max(maxIter + 1, minIter)
+    while not S["done"] and enq < cap:
+        enq += 1
+        # k_eis_p
+        first = S["nIter"] == 0
+        p = dT * rh
+        if not first:
+            psi = psi + S["alpha"] * t
+            p = p + S["beta"] * ph
+        ph = p
+        t = t.copy()
+        t[lastStart:] = rD[lastStart:] * ph[lastStart:]
+        dot = 0.0
+        # k_eis_bwd, colours C-2 .. 0
+        for k in range(C - 2, -1, -1):
+            for r in pv.rows_of_colour(k):
+                w = rD[r] * ph[r]
+                for j in range(pv.nTotal[r] - 1, pv.nLower[r] - 1, -1):
+                    e = pv.entry(r, j)
+                    w = w - (rD[r] * val[e]) * t[pv.col[e]]
+                t[r] = w
+                if fuse0 and k == 0:
+                    assert pv.nLower[r] == 0
+                    yv = rD[r] * (ph[r] + eD[r] * w)
+                    y[r] = yv
+                    dot += ph[r] * (w + yv)
+        # k_eis_fwd
+        for k in range(1 if fuse0 else 0, C):
+            last = k == C - 1
+            for r in pv.rows_of_colour(k):
+                rhs = ph[r] + eD[r] * t[r]
+                w = rD[r] * rhs
+                for j in range(pv.nLower[r]):
+                    e = pv.entry(r, j)
+                    assert pv.col[e] < lastStart     # a gathered y is never a stored w^
+                    w = w - (rD[r] * val[e]) * y[pv.col[e]]
+                wh = t[r] + w
+                y[r] = wh if last else w
+                dot += ph[r] * wh
+        # STEP_WAPA
+        S["wApA"] = dot
+        if not (abs(dot) / nf > 1e-300):
+            S["singular"], S["done"], S["pendingPsi"] = 1, 1, 0
+            break
+        S["alpha"] = S["wArA"] / dot
+        S["pendingPsi"] = 1
+        # k_eis_r + STEP_EIS_RHO
+        w = y.copy()
+        w[:lastStart] = t[:lastStart] + y[:lastStart]
+        rh = rh - S["alpha"] * w
+        g = ((dT * rh) * rh).sum()
+        S["wArAold"], S["wArA"] = S["wArA"], g
+        S["beta"] = S["wArA"] / S["wArAold"]
+        old = S["nIter"]
+        S["nIter"] = old + 1
+        S["sinceCheck"] += 1
+        mustStop = not (old < maxIter)
+        thr = max(tol, relTol * S["initRes"]) if relTol > 1e-20 else tol
+        near = S["cRatio"] * np.sqrt(abs(g)) < EIS_MARGIN * thr
+        S["needCheck"] = int(mustStop or near or S["sinceCheck"] >= EIS_EVERY)
+        # k_eis_res + STEP_EIS_RES
+        if S["needCheck"]:
+            checks += 1
+            tot = 0.0
+            for r in range(N):
+                acc = dT[r] * rh[r]
+                for j in range(pv.nLower[r]):
+                    e = pv.entry(r, j)
+                    acc = acc + val[e] * rh[pv.col[e]]
+                tot += abs(acc)
+            S["finalRes"] = tot / nf
+            S["converged"] = int(conv())
+            cont = (S["nIter"] - 1 < maxIter and not S["converged"]) or S["nIter"] < minIter
+            if not cont:
+                S["done"] = 1
+            a = np.sqrt(abs(S["wArA"]))
+            S["cRatio"] = S["finalRes"] / a if a > 0 else 0.0
+            S["sinceCheck"], S["needCheck"] = 0, 0
+    if S["pendingPsi"]:
+        psi = psi + S["alpha"] * t          # k_psi_final
+    return pv.to_natural(psi), S["nIter"], S["finalRes"], checks

@@ -43,16 +43,18 @@ if rank == 0:
     ref = orc.amul(subs, [g[0] for g in gather])
     results["amul_bit_exact"] = all(np.array_equal(ref[r], gather[r][1]) for r in range(world))
 
-for pre, exact in (("diagonal", False), ("none", False), ("DIC", True), ("DIC", False)):
+for pre, exact in (("diagonal", False), ("none", False), ("DIC", True), ("DIC", False), ("DIC", "eisenstat")):
+    if exact == "eisenstat" and os.environ.get("B200PCG_TILE"):
+        continue                      # the Eisenstat form needs the colour-major plan
     ctl = {"preconditioner": pre, "tolerance": 1e-8, "relTol": 0.0, "maxIter": 3000}
     if exact:
-        ctl["B200"] = {"dicMode": "exact"}
+        ctl["B200"] = {"dicMode": "exact" if exact is True else exact}
     psi = np.zeros(s.addr.nCells)
     perf = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, ctl, context=ctx).solve(psi, s.source)
     allpsi = [None] * world
     dist.all_gather_object(allpsi, psi)
     if rank == 0:
-        key = pre + ("-exact" if exact else "")
+        key = pre + ("" if not exact else "-exact" if exact is True else "-" + exact)
         subs = [mg.hex_block(*DIMS, *PROCS, r) for r in range(world)]
         ref = [np.zeros(x_.addr.nCells) for x_ in subs]
         pr = orc.pcg_solve(subs, ref, "DIC" if pre == "DIC" else pre, 1e-8, 0.0, 3000)
@@ -68,10 +70,12 @@ c2p = mg.partition_rcb(poly.xyz, world)
 subs = mg.decompose(poly, c2p, world)
 ps = subs[rank]
 ctx.set_addressing(ps.addr)
-for pre, exact in (("diagonal", False), ("DIC", True)):
+for pre, exact in (("diagonal", False), ("DIC", True), ("DIC", False), ("DIC", "eisenstat")):
+    if exact == "eisenstat" and os.environ.get("B200PCG_TILE"):
+        continue                      # the Eisenstat form needs the colour-major plan
     ctl = {"preconditioner": pre, "tolerance": 1e-8, "relTol": 0.0, "maxIter": 3000}
     if exact:
-        ctl["B200"] = {"dicMode": "exact"}
+        ctl["B200"] = {"dicMode": "exact" if exact is True else exact}
     psi = np.zeros(ps.addr.nCells)
     perf = pkg.B200PCG("p_rgh", ps.matrix, ps.bou, None, ps.interfaces, ctl, context=ctx).solve(psi, ps.source)
     allpsi = [None] * world
@@ -80,7 +84,8 @@ for pre, exact in (("diagonal", False), ("DIC", True)):
         ref = [np.zeros(x_.addr.nCells) for x_ in subs]
         pr = orc.pcg_solve(subs, ref, pre, 1e-8, 0.0, 3000)
         err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
-        results["poly-" + pre + ("-exact" if exact else "")] = {
+        results["poly-" + pre + ("" if not exact else "-exact" if exact is True else "-" + exact)] = {
+            "converged": bool(perf.converged),
             "iters": perf.nIterations, "oracle_iters": pr.nIterations, "relerr_vs_oracle": err,
             "nbrs": [len(x_.bou) for x_ in subs]}
 if rank == 0:
