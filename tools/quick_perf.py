@@ -14,6 +14,7 @@ NX, NY, NZ = (int(a) for a in sys.argv[1:4])
 pre = sys.argv[4] if len(sys.argv) > 4 else "diagonal"
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 200
 exact = pre == "DIC-exact"
+mode = {"DIC-exact": "exact", "DIC-eisenstat": "eisenstat"}.get(pre, "multicolour")
 t0 = time.time()
 s = mg.hex_block(NX, NY, NZ)
 print(f"generated N={s.addr.nCells} F={s.addr.nFaces} in {time.time()-t0:.1f}s", flush=True)
@@ -21,8 +22,8 @@ ctx = pkg.Context(device=0)
 t0 = time.time()
 ctx.set_addressing(s.addr)
 print(f"set_addressing {time.time()-t0:.2f}s", flush=True)
-ctl, _ = pkg.make_controls({"preconditioner": "DIC" if exact else pre, "tolerance": 1e-6, "maxIter": 5000,
-                            "B200": {"dicMode": "exact" if exact else "multicolour"}})
+ctl, _ = pkg.make_controls({"preconditioner": "DIC" if pre.startswith("DIC") else pre, "tolerance": 1e-6, "maxIter": 5000,
+                            "B200": {"dicMode": mode}})
 N, F = s.addr.nCells, s.addr.nFaces
 for rep in range(3):
     psi = np.zeros(N)
@@ -36,7 +37,10 @@ for rep in range(3):
           f"colours={perf.nColours}", flush=True)
 prof = ctx.profile_json()
 bytes_per = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N, "p_psi_update": 48 * N, "r_update_dots": 32 * N,
-             "dic_fwd": (20 * N + 16 * F), "dic_bwd": (20 * N + 16 * F)}
+             "dic_fwd": (20 * N + 16 * F), "dic_bwd": (20 * N + 16 * F),
+             # Eisenstat form: each sweep does half of Amul + half of the preconditioner apply
+             "eis_bwd": 32 * N + 24 * F, "eis_fwd_dot": 32 * N + 24 * F, "eis_p_psi_update": 40 * N,
+             "eis_r_update_rho": 24 * N}
 for k, v in prof.items():
     line = f"  {k:16s} n={v['launches']:6d} avg={v['avg_us']:9.2f}us"
     if k in bytes_per:
