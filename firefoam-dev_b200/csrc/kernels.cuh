@@ -1357,9 +1357,16 @@ k_eis_p(int N, int lastStart, double* __restrict__ psi, double* __restrict__ ph,
           const double2 d = reinterpret_cast<const double2*>(dT)[i];
           double2 p;
           p.x = __dmul_rn(d.x, r.x); p.y = __dmul_rn(d.y, r.y);
+          const bool anyLast = (2 * i + 1 >= lastStart);
+          const bool bothLast = (2 * i >= lastStart);
+          double2 rd = make_double2(0.0, 0.0);
+          if (anyLast) rd = reinterpret_cast<const double2*>(rD)[i];
           if (!first) {
               const double2 po = reinterpret_cast<const double2*>(ph)[i];
-              const double2 tv = reinterpret_cast<const double2*>(t)[i];
+              double2 tv;
+              // the previous t of a last-colour row is rD * (previous p^): recomputed, not re-read
+              if (bothLast) tv = make_double2(__dmul_rn(rd.x, po.x), __dmul_rn(rd.y, po.y));
+              else tv = reinterpret_cast<const double2*>(t)[i];
               double2 x = reinterpret_cast<double2*>(psi)[i];
               x.x = __dadd_rn(x.x, __dmul_rn(alpha, tv.x));
               x.y = __dadd_rn(x.y, __dmul_rn(alpha, tv.y));
@@ -1368,13 +1375,10 @@ k_eis_p(int N, int lastStart, double* __restrict__ psi, double* __restrict__ ph,
               p.y = __dadd_rn(p.y, __dmul_rn(beta, po.y));
           }
           reinterpret_cast<double2*>(ph)[i] = p;
-          if (2 * i + 1 >= lastStart) {
-              const double2 rd = reinterpret_cast<const double2*>(rD)[i];
-              if (2 * i >= lastStart)
-                  reinterpret_cast<double2*>(t)[i] = make_double2(__dmul_rn(rd.x, p.x), __dmul_rn(rd.y, p.y));
-              else
-                  t[2 * i + 1] = __dmul_rn(rd.y, p.y);
-          } },
+          if (bothLast)
+              reinterpret_cast<double2*>(t)[i] = make_double2(__dmul_rn(rd.x, p.x), __dmul_rn(rd.y, p.y));
+          else if (anyLast)
+              t[2 * i + 1] = __dmul_rn(rd.y, p.y); },
         { double p = __dmul_rn(dT[i], rh[i]);
           if (!first) {
               psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, t[i]));
@@ -1390,8 +1394,7 @@ template <bool FWD0, bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_eis_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ rD,
-          const double* __restrict__ ph, const double* __restrict__ ev, double* t, double* __restrict__ y,
-          Reduce R) {
+          const double* __restrict__ ph, double* t, double* __restrict__ y, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
     B200_FOR_COLOUR_ROWS(cr, r) {
@@ -1407,7 +1410,8 @@ k_eis_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* 
         }
         t[r] = w;
         if (FWD0) {
-            const double yv = __dmul_rn(d, __dadd_rn(p, __dmul_rn(ev[r], w)));
+            // first colour: no earlier neighbours, D~ == D, e == -D~  ->  y = rD*(p^ - D~ t) = rD*p^ - t
+            const double yv = __dadd_rn(__dmul_rn(d, p), -w);
             y[r] = yv;
             s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(w, yv)));
         }
@@ -1447,7 +1451,8 @@ k_eis_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* 
         const int nLower = (int)(rowLen[r] & 0xffffu);
         const double d = rD[r];
         const double p = ph[r];
-        const double tv = t[r];
+        // rows of the last colour: t = rD*p^ (k_eis_p), recomputed bit-identically instead of re-read
+        const double tv = LAST ? __dmul_rn(d, p) : t[r];
         double rhs = __dadd_rn(p, __dmul_rn(ev[r], tv));
         if (HALO) {
             const int b = rowB[r];

@@ -198,6 +198,7 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    int sweepPerSM = 8;         // B200PCG_SWEEP_CTAS: CTAs per SM of the colour sweeps (DIC-class, Eisenstat form)
     bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
@@ -633,7 +634,7 @@ ColourRows colour_rows(const b200_ctx* ctx, const DevPlan& P, int c, int* grid) 
     ColourRows cr{P.segStart, P.h.nColours, c, P.h.nTiles, 1};
     const int rows = P.h.colourStart[c + 1] - P.h.colourStart[c];
     if (P.h.nTiles == 1) {
-        *grid = grid_for(ctx, rows);
+        *grid = grid_for(ctx, rows, ctx->sweepPerSM);
         cr.bps = *grid;
     } else {
         // ~4 rows per thread inside a segment; the grid strides over (tile, block-in-segment) items
@@ -808,8 +809,7 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
 #define B200_EBWD(F0_, C16_)                                                                            \
     do {                                                                                                \
         auto kb = k_eis_bwd<F0_, C16_>;                                                                 \
-        LAUNCH(PC_EIS_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->eD, ctx->t, \
-               ctx->w, R);                                                                              \
+        LAUNCH(PC_EIS_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->t, ctx->w, R); \
     } while (0)
         const bool f0 = fuse0 && k == 0;
         if (f0 && P.c16) B200_EBWD(true, true);
@@ -1185,6 +1185,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e15 = getenv("B200PCG_COL16")) c->disableCol16 = atoi(e15) == 0;
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
+    if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);

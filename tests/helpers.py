@@ -331,14 +331,16 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                 t[r] = w
                 if fuse0 and k == 0:
                     assert pv.nLower[r] == 0
-                    yv = rD[r] * (ph[r] + eD[r] * w)
+                    yv = rD[r] * ph[r] - w           # D~ == D, e == -D~ on first-colour rows
                     y[r] = yv
                     dot += ph[r] * (w + yv)
         # k_eis_fwd
         for k in range(1 if fuse0 else 0, C):
             last = k == C - 1
             for r in pv.rows_of_colour(k):
-                rhs = ph[r] + eD[r] * t[r]
+                tv = rD[r] * ph[r] if last else t[r]
+                assert tv == t[r]
+                rhs = ph[r] + eD[r] * tv
                 w = rD[r] * rhs
                 for j in range(pv.nLower[r]):
                     e = pv.entry(r, j)
