@@ -35,7 +35,8 @@ enum Step : int {
     STEP_RES,      // final residual; nIter++; convergence
     STEP_RES_WARA, // STEP_RES, then (if the loop continues) STEP_WARA of the next iteration
     // Eisenstat form of the DIC-class PCG (k_eis_* kernels)
-    STEP_EIS_RHO0, // rho_0 = (r^, D~ r^); calibrates the true-residual predictor
+    STEP_EIS_SIGN, // sign of the DIC pivots (sigma), or "unusable"
+    STEP_EIS_RHO0, // rho_0 = (r^, r^); calibrates the true-residual predictor
     STEP_EIS_RHO,  // rho_k; beta; nIter++; decides whether this iteration needs a true-residual check
     STEP_EIS_RES   // true residual |(D~+L) r^|_1 / normFactor; convergence; loop condition
 };
@@ -63,6 +64,7 @@ struct Scalars {
     // Eisenstat form (STEP_EIS_*): predictor ratio  true residual / sqrt(|rho|)  at the last check,
     // iterations since that check, and whether the current iteration's check kernel has to run
     double cRatio;
+    double sigma;          // +1 / -1: common sign of the DIC pivots (0: mixed or zero pivots -> error)
     int sinceCheck, needCheck;
     // number of cross-rank reductions this rank has EXECUTED (peer_allreduce_step).  Every rank
     // executes the same sequence (identical totals -> identical `done` decisions), so the counters
@@ -152,6 +154,19 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
                 S->wArAold = S->wArA;
                 S->wArA = g[1];
                 S->beta = S->wArA / S->wArAold;
+            }
+            break;
+        }
+        case STEP_EIS_SIGN: {
+            // g[0] = number of negative DIC pivots, g[1] = number of zero / non-finite ones (global counts)
+            S->sigma = 1.0;
+            if (S->done) break;                       // converged before the first iteration: nothing to scale
+            if (g[1] > 0.0 || (g[0] > 0.0 && g[0] < S->nGlobalCells)) {
+                S->sigma = 0.0;
+                S->nonfinite = 3;                     // indefinite / singular pivots: reported as an error
+                S->done = 1;
+            } else if (g[0] > 0.0) {
+                S->sigma = -1.0;
             }
             break;
         }
@@ -1277,149 +1292,254 @@ k_dic_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase,
 
 // ---- Eisenstat form of the DIC-class PCG (B200_PRECOND_DIC_MC_EIS) ----------------------------
 // The DIC-class preconditioner is M = (D~ + L) D~^-1 (D~ + L^T): L = the matrix's OWN strictly-lower
-// part in the colour-major elimination order, D~ = the DIC diagonal (rD = 1/D~).  For exactly that
-// shape Eisenstat's identity removes the separate Amul from the iteration: with
-//     r^ = (D~+L)^-1 r,   p^ = (D~+L^T) p,   A = (D~+L) + (D - 2 D~) + (D~+L^T) [+ B: processor interfaces]
-// PCG on A preconditioned by M is PCG on A^ = (D~+L)^-1 A (D~+L^T)^-1 preconditioned by D~, and
-//     t  = (D~+L^T)^-1 p^                         backward sweep (t IS the untransformed search direction p)
-//     w^ = A^ p^ = t + (D~+L)^-1 (p^ + (D - 2D~) t [+ B t])      forward sweep
-// so one iteration is   k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps -> k_eis_r,
-// every matrix entry is read ONCE per sweep, and psi += alpha*t is updated directly in the
-// untransformed variable.  Same iterates as the three-kernel DIC-class loop in exact arithmetic
-// (same preconditioner, same Krylov space); the rounding differs, which the DIC-class parity bar
-// (solution within 1e-8 relative L2 at the same residual tolerance) allows.
-// OpenFOAM's convergence test needs |r|_1 of the TRUE residual r = (D~+L) r^, a third pass over L.  It is
-// evaluated by k_eis_res only when the device-side predictor  cRatio * sqrt(|rho|)  (rho = (r^, D~ r^) is
-// free; cRatio is re-calibrated at every evaluation) comes within kEisMargin of the threshold, and at
-// least every kEisEvery iterations; the solve only ever stops on an evaluated true residual.
-// Vectors: rh = r^, ph = p^, t, y (= (D~+L)^-1 rhs for the rows of all colours but the last; the last
-// colour's rows, which no sweep gathers, hold w^ = t + y), dT = D~, e = D - 2 D~.
+// part in the colour-major elimination order, D~ = the DIC diagonal.  For exactly that shape
+// Eisenstat's identity removes the separate Amul from the iteration.  The system is first scaled
+// symmetrically so that the DIC diagonal becomes the identity (once per solve, in the plan's own copy
+// of the coefficients):
+//     s_i = 1/sqrt|D~_i|,  sigma = sign(D~) (+1: SPD p_rghEqn; -1: the un-negated ph_rghEqn)
+//     A- = sigma S A S,  L-_ij = sigma s_i s_j L_ij,  D-_i = D_i / D~_i,  x = S x-,  r- = sigma S r
+//     M- = (I + L-)(I + L-^T)
+// PCG on A preconditioned by M is then PLAIN CG on  A^ = (I+L-)^-1 A- (I+L-^T)^-1  in the variables
+//     r^ = (I+L-)^-1 r-,   p^ = (I+L-^T) p-,   A- = (I+L-) + (D- - 2I) + (I+L-^T) [+ B-: processor interfaces]
+//     t  = (I+L-^T)^-1 p^                                   backward sweep (t = the scaled search direction)
+//     w^ = A^ p^ = t + (I+L-)^-1 (p^ + (D- - 2) t [+ B- t])   forward sweep
+// One iteration:  k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps (+ (p^, w^)) ->
+// k_eis_r (+ rho = (r^, r^)).  Every matrix entry is read ONCE per sweep, no vector of the
+// preconditioner (rD) is read at all, and the solution increment sum(alpha t) accumulates in xa
+// (psi = psi0 + S xa after the loop).  Same iterates as the three-kernel DIC-class loop in exact
+// arithmetic (same preconditioner, same Krylov space); the rounding differs, which the DIC-class parity
+// bar (solution within 1e-8 relative L2 at the same residual tolerance) allows.
+// OpenFOAM's convergence test needs |r|_1 of the TRUE residual r = sigma S^-1 (I+L-) r^, a third pass
+// over L.  k_eis_res evaluates it only when the device-side predictor  cRatio * sqrt(rho)  (cRatio is
+// re-calibrated at every evaluation) comes within kEisMargin of the threshold, and at least every
+// kEisEvery iterations; the solve only ever stops on an evaluated true residual.
+// Storage: rh = r^, ph = p^ (rows below lastStart), t (rows of the LAST colour, >= lastStart, have no
+// later neighbours: t == p^ there, kept in t only), y (= (I+L-)^-1 rhs; last-colour rows, which no sweep
+// gathers, hold w^ = t + y), sv = s, eb = D- - 2, xa.
 
-// once per solve: rD = 1/D~, e = D - 2 D~
+// DIC pivots: how many are negative, how many unusable (zero / non-finite) -> STEP_EIS_SIGN
 __global__ void __launch_bounds__(kBlock)
-k_eis_setup(int N, const double* __restrict__ diag, const double* __restrict__ dT,
-            double* __restrict__ rD, double* __restrict__ e) {
-    B200_VEC_LOOP(N,
-        { const double2 d = reinterpret_cast<const double2*>(diag)[i];
-          const double2 dt = reinterpret_cast<const double2*>(dT)[i];
-          reinterpret_cast<double2*>(rD)[i] = make_double2(__ddiv_rn(1.0, dt.x), __ddiv_rn(1.0, dt.y));
-          reinterpret_cast<double2*>(e)[i] = make_double2(__dadd_rn(d.x, -__dmul_rn(2.0, dt.x)),
-                                                          __dadd_rn(d.y, -__dmul_rn(2.0, dt.y))); },
-        { rD[i] = __ddiv_rn(1.0, dT[i]); e[i] = __dadd_rn(diag[i], -__dmul_rn(2.0, dT[i])); })
+k_eis_sign(int N, const double* __restrict__ dT, Reduce R) {
+    double s[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double d = dT[i];
+        if (d < 0.0) s[0] = __dadd_rn(s[0], 1.0);
+        if (!(fabs(d) > 0.0 && fabs(d) < 1.7e308)) s[1] = __dadd_rn(s[1], 1.0);
+    }
+    reduce_finish<2>(s, R);
 }
 
-// once per solve, one launch per colour, in place: rh = (D~+L)^-1 r
-template <bool C16>
+// once per solve: sv = 1/sqrt|D~| (in place of D~), eb = D/D~ - 2, r- = sigma s r (in place), xa = 0
 __global__ void __launch_bounds__(kBlock)
-k_eis_init_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
-               EllCols E, const double* __restrict__ val, const double* __restrict__ rD, double* rh,
-               const Scalars* S) {
+k_eis_setup(int N, const double* __restrict__ diag, double* __restrict__ dTsv, double* __restrict__ eb,
+            double* __restrict__ rh, double* __restrict__ xa, const Scalars* S) {
     if (S->done) return;
-    B200_FOR_COLOUR_ROWS(cr, r) {
-        const int64_t base = sliceBase[r >> 5] + (r & 31);
-        const int nLower = (int)(rowLen[r] & 0xffffu);
-        const double d = rD[r];
-        double w = __dmul_rn(d, rh[r]);
-        for (int j = 0; j < nLower; ++j) {
-            const int64_t e = base + 32 * (int64_t)j;
-            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), rh[ell_col<C16>(E, e)]));
-        }
-        rh[r] = w;
+    const double sigma = S->sigma;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double dt = dTsv[i];
+        const double s = __ddiv_rn(1.0, __dsqrt_rn(fabs(dt)));
+        dTsv[i] = s;
+        eb[i] = __dadd_rn(__ddiv_rn(diag[i], dt), -2.0);
+        rh[i] = __dmul_rn(__dmul_rn(sigma, s), rh[i]);
+        xa[i] = 0.0;
     }
 }
 
-// rho_0 = (r^, D~ r^)
+// once per solve: the plan's coefficient copy becomes L- (both triangles): val *= sigma * (s_row * s_col).
+// s_row*s_col is formed first so that the two copies of a coefficient stay bit-identical.
+template <bool C16>
 __global__ void __launch_bounds__(kBlock)
-k_eis_rho0(int N, const double* __restrict__ dT, const double* __restrict__ rh, Reduce R) {
+k_eis_scale_vals(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+                 EllCols E, double* __restrict__ val, const double* __restrict__ sv, const Scalars* S) {
+    if (S->done) return;
+    const double sigma = S->sigma;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int n = (int)(rowLen[r] >> 16);
+        const double sr = sv[r];
+        for (int j = 0; j < n; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            const double ss = __dmul_rn(sr, __ldg(&sv[ell_col<C16>(E, e)]));
+            val[e] = __dmul_rn(val[e], __dmul_rn(sigma, ss));
+        }
+    }
+}
+// nranks > 1: interface coefficients of B- (recv = the neighbours' s on the patch faces)
+__global__ void __launch_bounds__(kBlock)
+k_eis_scale_bou(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ sv,
+                const double* __restrict__ recv, double* __restrict__ bou, const Scalars* S) {
+    if (S->done) return;
+    const double sigma = S->sigma;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x) {
+        const double ss = __dmul_rn(__ldg(&sv[slotRow[i]]), recv[i]);
+        bou[i] = __dmul_rn(bou[i], __dmul_rn(sigma, ss));
+    }
+}
+// like k_pack, but not gated by `done` bookkeeping differences: s of the interface rows
+__global__ void k_eis_pack_s(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ sv,
+                             double* __restrict__ sendbuf) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x)
+        sendbuf[i] = __ldg(&sv[slotRow[i]]);
+}
+
+// resident CTAs per SM the batched sweeps are compiled for (caps the registers at 65536 / (256 * n)):
+// 64 registers hold a batch of 6 without spills, a batch of 8 needs 80
+constexpr int eis_sweep_ctas(int B) { return B == 0 ? 1 : (B <= 6 ? 4 : 3); }
+// w -= sum of val*x[col] over the n ELL entries j0 .. j0+n-1 of a row (DESC: from the last one down).
+// B > 0: batches of B entries -- all (column, value) loads, then all gathers, then the adds in order -- so
+// that a row costs three dependent memory round trips instead of one per group of the unrolled loop
+// (the sweeps are latency-bound: long_scoreboard, profiles/r01_v8_ncu_eisenstat_hex.md).  B == 0: plain loop.
+template <int B, bool C16, bool DESC>
+__device__ __forceinline__ double eis_row_sub(const EllCols& E, const double* __restrict__ val, const double* x,
+                                              int64_t base, int j0, int n, double w) {
+    if (B == 0) {
+        for (int k = 0; k < n; ++k) {
+            const int j = DESC ? (j0 + n - 1 - k) : (j0 + k);
+            const int64_t e = base + 32 * (int64_t)j;
+            w = __dadd_rn(w, -__dmul_rn(val[e], x[ell_col<C16>(E, e)]));
+        }
+        return w;
+    }
+    constexpr int BB = B > 0 ? B : 1;
+    for (int done = 0; done < n; done += BB) {
+        // entry k of the batch sits at a compile-time offset (+-32 k) from the batch's first entry
+        const int jf = DESC ? (j0 + n - 1 - done) : (j0 + done);
+        const int64_t ef = base + 32 * (int64_t)jf;
+        const double* __restrict__ vp = val + ef;
+        const int* __restrict__ cp = E.col + ef;
+        const uint16_t* __restrict__ cp16 = E.col16 + ef;
+        const int* __restrict__ bp = E.colBase + (ef >> 5);
+        constexpr int STEP = DESC ? -1 : 1;
+        int c[BB];
+        double a[BB], g[BB];
+        const int m = n - done;
+#pragma unroll
+        for (int k = 0; k < BB; ++k)
+            if (k < m) {
+                c[k] = C16 ? (__ldg(bp + STEP * k) + (int)__ldg(cp16 + STEP * 32 * k)) : __ldg(cp + STEP * 32 * k);
+                a[k] = vp[STEP * 32 * k];
+            }
+#pragma unroll
+        for (int k = 0; k < BB; ++k)
+            if (k < m) g[k] = x[c[k]];
+#pragma unroll
+        for (int k = 0; k < BB; ++k)
+            if (k < m) w = __dadd_rn(w, -__dmul_rn(a[k], g[k]));
+    }
+    return w;
+}
+
+// once per solve, one launch per colour, in place: rh = (I+L-)^-1 r-   (rows [r0, r1) of the colour)
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_init_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+               EllCols E, const double* __restrict__ val, double* rh, const Scalars* S) {
+    if (S->done) return;
+    for (int r = r0 + blockIdx.x * kBlock + threadIdx.x; r < r1; r += gridDim.x * kBlock) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        rh[r] = eis_row_sub<0, C16, false>(E, val, rh, base, 0, nLower, rh[r]);
+    }
+}
+
+// rho_0 = (r^, r^)
+__global__ void __launch_bounds__(kBlock)
+k_eis_rho0(int N, const double* __restrict__ rh, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
     B200_VEC_LOOP(N,
         { const double2 r = reinterpret_cast<const double2*>(rh)[i];
-          const double2 d = reinterpret_cast<const double2*>(dT)[i];
-          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.x, r.x), r.x));
-          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.y, r.y), r.y)); },
-        { s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(dT[i], rh[i]), rh[i])); })
+          s[0] = __dadd_rn(s[0], __dmul_rn(r.x, r.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(r.y, r.y)); },
+        { s[0] = __dadd_rn(s[0], __dmul_rn(rh[i], rh[i])); })
     reduce_finish<1>(s, R);
 }
 
-// psi += alpha_prev * t_prev (deferred, as in k_p);  p^ = D~ r^ + beta p^;  and the backward sweep of the
-// LAST colour (rows >= lastStart have no later neighbours): t = rD * p^.
+// xa += alpha_prev * t_prev (deferred, as psi in k_p);  p^ = r^ + beta p^.  Rows of the last colour keep
+// p^ in t (t == p^ there): nothing else to do for their backward sweep.
+__device__ __forceinline__ void eis_p_elem(int i, bool last, bool first, double alpha, double beta,
+                                           const double* __restrict__ rh, double* __restrict__ ph, double* t,
+                                           double* __restrict__ xa) {
+    double p = rh[i];
+    if (!first) {
+        const double tv = t[i];
+        const double po = last ? tv : ph[i];
+        xa[i] = __dadd_rn(xa[i], __dmul_rn(alpha, tv));
+        p = __dadd_rn(p, __dmul_rn(beta, po));
+    }
+    if (last) t[i] = p;
+    else ph[i] = p;
+}
 __global__ void __launch_bounds__(kBlock)
-k_eis_p(int N, int lastStart, double* __restrict__ psi, double* __restrict__ ph,
-        const double* __restrict__ rh, const double* __restrict__ dT, const double* __restrict__ rD,
-        double* t, const Scalars* S) {
+k_eis_p(int N, int lastStart, double* __restrict__ xa, double* __restrict__ ph, double* t,
+        const double* __restrict__ rh, const Scalars* S) {
     if (S->done) return;
     const bool first = (S->nIter == 0);
     const double beta = S->beta;
     const double alpha = S->alpha;
     B200_VEC_LOOP(N,
-        { const double2 r = reinterpret_cast<const double2*>(rh)[i];
-          const double2 d = reinterpret_cast<const double2*>(dT)[i];
-          double2 p;
-          p.x = __dmul_rn(d.x, r.x); p.y = __dmul_rn(d.y, r.y);
-          const bool anyLast = (2 * i + 1 >= lastStart);
+        { const bool anyLast = (2 * i + 1 >= lastStart);
           const bool bothLast = (2 * i >= lastStart);
-          double2 rd = make_double2(0.0, 0.0);
-          if (anyLast) rd = reinterpret_cast<const double2*>(rD)[i];
-          if (!first) {
-              const double2 po = reinterpret_cast<const double2*>(ph)[i];
-              double2 tv;
-              // the previous t of a last-colour row is rD * (previous p^): recomputed, not re-read
-              if (bothLast) tv = make_double2(__dmul_rn(rd.x, po.x), __dmul_rn(rd.y, po.y));
-              else tv = reinterpret_cast<const double2*>(t)[i];
-              double2 x = reinterpret_cast<double2*>(psi)[i];
-              x.x = __dadd_rn(x.x, __dmul_rn(alpha, tv.x));
-              x.y = __dadd_rn(x.y, __dmul_rn(alpha, tv.y));
-              reinterpret_cast<double2*>(psi)[i] = x;
-              p.x = __dadd_rn(p.x, __dmul_rn(beta, po.x));
-              p.y = __dadd_rn(p.y, __dmul_rn(beta, po.y));
-          }
-          reinterpret_cast<double2*>(ph)[i] = p;
-          if (bothLast)
-              reinterpret_cast<double2*>(t)[i] = make_double2(__dmul_rn(rd.x, p.x), __dmul_rn(rd.y, p.y));
-          else if (anyLast)
-              t[2 * i + 1] = __dmul_rn(rd.y, p.y); },
-        { double p = __dmul_rn(dT[i], rh[i]);
-          if (!first) {
-              psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, t[i]));
-              p = __dadd_rn(p, __dmul_rn(beta, ph[i]));
-          }
-          ph[i] = p;
-          if (i >= lastStart) t[i] = __dmul_rn(rD[i], p); })
+          if (anyLast && !bothLast) {     // the one pair that straddles the colour boundary
+              eis_p_elem(2 * i, false, first, alpha, beta, rh, ph, t, xa);
+              eis_p_elem(2 * i + 1, true, first, alpha, beta, rh, ph, t, xa);
+          } else {
+              double2 p = reinterpret_cast<const double2*>(rh)[i];
+              if (!first) {
+                  const double2 tv = reinterpret_cast<const double2*>(t)[i];
+                  double2 po = tv;
+                  if (!bothLast) po = reinterpret_cast<const double2*>(ph)[i];
+                  double2 x = reinterpret_cast<double2*>(xa)[i];
+                  x.x = __dadd_rn(x.x, __dmul_rn(alpha, tv.x));
+                  x.y = __dadd_rn(x.y, __dmul_rn(alpha, tv.y));
+                  reinterpret_cast<double2*>(xa)[i] = x;
+                  p.x = __dadd_rn(p.x, __dmul_rn(beta, po.x));
+                  p.y = __dadd_rn(p.y, __dmul_rn(beta, po.y));
+              }
+              if (bothLast) reinterpret_cast<double2*>(t)[i] = p;
+              else reinterpret_cast<double2*>(ph)[i] = p;
+          } },
+        { eis_p_elem(i, i >= lastStart, first, alpha, beta, rh, ph, t, xa); })
 }
 
-// backward sweep over one colour: t = rD*(p^ - L^T t).  FWD0 (first colour, single rank): its rows have
-// no earlier neighbours, so their forward sweep y = rD*(p^ + e t) and their share of (p^, w^) ride along.
-template <bool FWD0, bool C16>
-__global__ void __launch_bounds__(kBlock)
-k_eis_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
-          EllCols E, const double* __restrict__ val, const double* __restrict__ rD,
-          const double* __restrict__ ph, double* t, double* __restrict__ y, Reduce R) {
+// backward sweep over the rows [r0, r1) of one colour: t = p^ - L-^T t.  FWD0 (first colour, single
+// rank): its rows have no earlier neighbours and D- == 1 there, so their forward sweep
+// y = p^ + (D- - 2) t = p^ - t and their share of (p^, w^) ride along.
+// B > 0: the next row's row length / slice base / p^ are requested before the current row's gathers.
+template <bool FWD0, bool C16, int B>
+__global__ void __launch_bounds__(kBlock, eis_sweep_ctas(B))
+k_eis_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          EllCols E, const double* __restrict__ val, const double* __restrict__ ph, double* t,
+          double* __restrict__ y, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
-    B200_FOR_COLOUR_ROWS(cr, r) {
-        const int64_t base = sliceBase[r >> 5] + (r & 31);
-        const uint32_t len = rowLen[r];
+    const int stride = gridDim.x * kBlock;
+    int r = r0 + blockIdx.x * kBlock + threadIdx.x;
+    uint32_t len = 0;
+    int64_t sb = 0;
+    double p = 0.0;
+    if (r < r1) { len = rowLen[r]; sb = sliceBase[r >> 5]; p = ph[r]; }
+    while (r < r1) {
+        const int rn = r + stride;
+        uint32_t lenN = 0;
+        int64_t sbN = 0;
+        double pN = 0.0;
+        if (B > 0 && rn < r1) { lenN = rowLen[rn]; sbN = sliceBase[rn >> 5]; pN = ph[rn]; }
         const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
-        const double d = rD[r];
-        const double p = ph[r];
-        double w = __dmul_rn(d, p);
-        for (int j = nTotal - 1; j >= nLower; --j) {
-            const int64_t e = base + 32 * (int64_t)j;
-            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), t[ell_col<C16>(E, e)]));
-        }
+        const double w = eis_row_sub<B, C16, true>(E, val, t, sb + (r & 31), nLower, nTotal - nLower, p);
         t[r] = w;
         if (FWD0) {
-            // first colour: no earlier neighbours, D~ == D, e == -D~  ->  y = rD*(p^ - D~ t) = rD*p^ - t
-            const double yv = __dadd_rn(__dmul_rn(d, p), -w);
+            const double yv = __dadd_rn(p, -w);
             y[r] = yv;
             s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(w, yv)));
         }
+        if (B == 0 && rn < r1) { lenN = rowLen[rn]; sbN = sliceBase[rn >> 5]; pN = ph[rn]; }
+        r = rn; len = lenN; sb = sbN; p = pN;
     }
     if (FWD0) reduce_finish<1>(s, R);
 }
 
-// halo term of the forward right-hand side (nranks > 1): hb[b] = (B t)[bRow[b]] = -sum bou*t_nbr over the
+// halo term of the forward right-hand side (nranks > 1): hb[b] = (B- t)[bRow[b]] = -sum bou*t_nbr over the
 // row's processor faces in (patch, face) order (the sorted-segment form of updateMatrixInterfaces)
 __global__ void __launch_bounds__(kBlock)
 k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ bSlot,
@@ -1436,44 +1556,56 @@ k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ b
     }
 }
 
-// forward sweep over one colour: y = rD*(p^ + e t [+ B t] - L y); every colour adds its share of
-// (p^, w^), w^ = t + y.  LAST: rows of the last colour are gathered by no sweep and store w^.
-template <bool LAST, bool HALO, bool C16>
-__global__ void __launch_bounds__(kBlock)
-k_eis_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
-          EllCols E, const double* __restrict__ val, const double* __restrict__ rD,
-          const double* __restrict__ ph, const double* __restrict__ ev, const double* __restrict__ t,
-          double* y, const int* __restrict__ rowB, const double* __restrict__ hb, Reduce R) {
+// forward sweep over the rows [r0, r1) of one colour: y = p^ + (D- - 2) t [+ B- t] - L- y; every colour
+// adds its share of (p^, w^), w^ = t + y.  LAST: p^ == t lives in t; the rows are gathered by no sweep
+// and store w^.
+template <bool LAST, bool HALO, bool C16, int B>
+__global__ void __launch_bounds__(kBlock, eis_sweep_ctas(B))
+k_eis_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          EllCols E, const double* __restrict__ val, const double* __restrict__ ph,
+          const double* __restrict__ eb, const double* __restrict__ t, double* y,
+          const int* __restrict__ rowB, const double* __restrict__ hb, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
-    B200_FOR_COLOUR_ROWS(cr, r) {
-        const int64_t base = sliceBase[r >> 5] + (r & 31);
-        const int nLower = (int)(rowLen[r] & 0xffffu);
-        const double d = rD[r];
-        const double p = ph[r];
-        // rows of the last colour: t = rD*p^ (k_eis_p), recomputed bit-identically instead of re-read
-        const double tv = LAST ? __dmul_rn(d, p) : t[r];
-        double rhs = __dadd_rn(p, __dmul_rn(ev[r], tv));
+    const int stride = gridDim.x * kBlock;
+    int r = r0 + blockIdx.x * kBlock + threadIdx.x;
+    uint32_t len = 0;
+    int64_t sb = 0;
+    double p = 0.0, tv = 0.0, ev = 0.0;
+#define B200_EIS_FWD_LOAD(ROW, LEN, SB, P, TV, EV)                   \
+    {                                                                \
+        LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; EV = eb[ROW]; \
+        TV = t[ROW];                                                 \
+        P = LAST ? TV : ph[ROW];                                     \
+    }
+    if (r < r1) B200_EIS_FWD_LOAD(r, len, sb, p, tv, ev)
+    while (r < r1) {
+        const int rn = r + stride;
+        uint32_t lenN = 0;
+        int64_t sbN = 0;
+        double pN = 0.0, tvN = 0.0, evN = 0.0;
+        if (B > 0 && rn < r1) B200_EIS_FWD_LOAD(rn, lenN, sbN, pN, tvN, evN)
+        const int nLower = (int)(len & 0xffffu);
+        double rhs = __dadd_rn(p, __dmul_rn(ev, tv));
         if (HALO) {
             const int b = rowB[r];
             if (b >= 0) rhs = __dadd_rn(rhs, hb[b]);
         }
-        double w = __dmul_rn(d, rhs);
-        for (int j = 0; j < nLower; ++j) {
-            const int64_t e = base + 32 * (int64_t)j;
-            w = __dadd_rn(w, -__dmul_rn(__dmul_rn(d, val[e]), y[ell_col<C16>(E, e)]));
-        }
+        const double w = eis_row_sub<B, C16, false>(E, val, y, sb + (r & 31), 0, nLower, rhs);
         const double wh = __dadd_rn(tv, w);
         y[r] = LAST ? wh : w;
         s[0] = __dadd_rn(s[0], __dmul_rn(p, wh));
+        if (B == 0 && rn < r1) B200_EIS_FWD_LOAD(rn, lenN, sbN, pN, tvN, evN)
+        r = rn; len = lenN; sb = sbN; p = pN; tv = tvN; ev = evN;
     }
+#undef B200_EIS_FWD_LOAD
     reduce_finish<1>(s, R);
 }
 
-// r^ -= alpha w^ (w^ = t + y below lastStart, stored as such from lastStart on); rho = (r^, D~ r^)
+// r^ -= alpha w^ (w^ = t + y below lastStart, stored as such from lastStart on); rho = (r^, r^)
 __global__ void __launch_bounds__(kBlock)
 k_eis_r(int N, int lastStart, double* __restrict__ rh, const double* __restrict__ y,
-        const double* __restrict__ t, const double* __restrict__ dT, Reduce R) {
+        const double* __restrict__ t, Reduce R) {
     if (R.S->done) return;
     const double alpha = R.S->alpha;
     double s[1] = {0.0};
@@ -1485,39 +1617,52 @@ k_eis_r(int N, int lastStart, double* __restrict__ rh, const double* __restrict_
               w.x = __dadd_rn(tv.x, w.x);
               if (2 * i + 1 < lastStart) w.y = __dadd_rn(tv.y, w.y);
           }
-          const double2 d = reinterpret_cast<const double2*>(dT)[i];
           r.x = __dadd_rn(r.x, -__dmul_rn(alpha, w.x));
           r.y = __dadd_rn(r.y, -__dmul_rn(alpha, w.y));
           reinterpret_cast<double2*>(rh)[i] = r;
-          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.x, r.x), r.x));
-          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(d.y, r.y), r.y)); },
+          s[0] = __dadd_rn(s[0], __dmul_rn(r.x, r.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(r.y, r.y)); },
         { double w = y[i];
           if (i < lastStart) w = __dadd_rn(t[i], w);
           const double r = __dadd_rn(rh[i], -__dmul_rn(alpha, w));
           rh[i] = r;
-          s[0] = __dadd_rn(s[0], __dmul_rn(__dmul_rn(dT[i], r), r)); })
+          s[0] = __dadd_rn(s[0], __dmul_rn(r, r)); })
     reduce_finish<1>(s, R);
 }
 
-// true residual of the iteration, only when the scalar step asked for it: sum |(D~ + L) r^|
+// true residual of the iteration, only when the scalar step asked for it: sum |(I + L-) r^| / s
 template <bool C16>
 __global__ void __launch_bounds__(kBlock)
 k_eis_res(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
-          const double* __restrict__ val, const double* __restrict__ dT, const double* __restrict__ rh,
+          const double* __restrict__ val, const double* __restrict__ sv, const double* __restrict__ rh,
           Reduce R) {
     if (R.S->done || !R.S->needCheck) return;
     double s[1] = {0.0};
     for (int r = blockIdx.x * kBlock + threadIdx.x; r < N; r += gridDim.x * kBlock) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const int nLower = (int)(rowLen[r] & 0xffffu);
-        double acc = __dmul_rn(dT[r], rh[r]);
+        double acc = rh[r];
         for (int j = 0; j < nLower; ++j) {
             const int64_t e = base + 32 * (int64_t)j;
             acc = __dadd_rn(acc, __dmul_rn(val[e], __ldg(&rh[ell_col<C16>(E, e)])));
         }
-        s[0] = __dadd_rn(s[0], fabs(acc));
+        s[0] = __dadd_rn(s[0], __ddiv_rn(fabs(acc), sv[r]));
     }
     reduce_finish<1>(s, R);
+}
+
+// after the loop: psi = psi0 + S (xa [+ the last, still deferred alpha*t])
+__global__ void __launch_bounds__(kBlock)
+k_eis_final(int N, double* __restrict__ psi, const double* __restrict__ xa, const double* __restrict__ t,
+            const double* __restrict__ sv, const Scalars* S) {
+    if (S->nIter == 0 && !S->pendingPsi) return;   // no loop body ran: psi is returned untouched
+    const bool pend = S->pendingPsi != 0;
+    const double alpha = S->alpha;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double x = xa[i];
+        if (pend) x = __dadd_rn(x, __dmul_rn(alpha, t[i]));
+        psi[i] = __dadd_rn(psi[i], __dmul_rn(sv[i], x));
+    }
 }
 
 // ---- assembly: gaussLaplacianScheme::fvmLaplacianUncorrected + negSumDiag ------------------

@@ -198,7 +198,9 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    int eisBatch = 1;           // B200PCG_EIS_BATCH=0: plain entry loops in the Eisenstat sweeps (A/B switch)
     int sweepPerSM = 8;         // B200PCG_SWEEP_CTAS: CTAs per SM of the colour sweeps (DIC-class, Eisenstat form)
+    bool sweepPerSMSet = false;
     bool noFuseFirst = false;   // B200PCG_FUSE_FIRST=0: keep the first colour's forward sweep a separate launch
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
@@ -737,6 +739,8 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
 }
 
 // ---- Eisenstat form of the DIC-class loop (kernels.cuh "Eisenstat form") ----------------------
+// Buffers: rh = ctx->r, ph = ctx->p, y = ctx->w, t = ctx->t, sv = ctx->dT (D~ during set-up, then
+// s = 1/sqrt|D~|), eb = ctx->eD, xa = ctx->rD (the reciprocal diagonal itself is not used by this form).
 int ensure_eis_buffers(b200_ctx* ctx, DevPlan& P) {
     if (!ctx->t) {
         const size_t n = (((size_t)ctx->N + kChunkRows - 1) / kChunkRows + 1) * kChunkRows;
@@ -753,73 +757,33 @@ int ensure_eis_buffers(b200_ctx* ctx, DevPlan& P) {
     return B200_OK;
 }
 
-// per solve: D~ (DIC recurrence, one launch per colour), rD = 1/D~, e = D - 2 D~, r^ = (D~+L)^-1 r, rho_0
-int eis_setup(b200_ctx* ctx, DevPlan& P) {
-    if (P.h.nTiles > 1)
-        return fail(ctx, B200_EUNSUPPORTED, "dicMode eisenstat needs the colour-major plan (unset B200PCG_TILE)");
-    RET(ensure_eis_buffers(ctx, P));
-    const int N = ctx->N;
-    const int gv = grid_for(ctx, (N + 1) / 2);
-    const EllCols E{P.col, P.col16, P.colBase};
-    for (int k = 0; k < P.h.nColours; ++k) {
-        int g;
-        const ColourRows cr = colour_rows(ctx, P, k, &g);
-        if (P.c16) {
-            auto kd = k_dic_calc_rd<true>;
-            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
-        } else {
-            auto kd = k_dic_calc_rd<false>;
-            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
-        }
-    }
-    LAUNCH(PC_EIS_SETUP, k_eis_setup, gv, N, ctx->diag, ctx->dT, ctx->rD, ctx->eD);
-    for (int k = 0; k < P.h.nColours; ++k) {
-        int g;
-        const ColourRows cr = colour_rows(ctx, P, k, &g);
-        if (P.c16) {
-            auto kf = k_eis_init_fwd<true>;
-            LAUNCH(PC_EIS_SETUP, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->S);
-        } else {
-            auto kf = k_eis_init_fwd<false>;
-            LAUNCH(PC_EIS_SETUP, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->r, ctx->S);
-        }
-    }
-    Reduce R = mkR(ctx, STEP_EIS_RHO0);
-    LAUNCH(PC_EIS_SETUP, k_eis_rho0, gv, N, ctx->dT, ctx->r, R);
-    RET(reduce_post(ctx, STEP_EIS_RHO0));
-    return B200_OK;
+// entries gathered per batch by the sweeps (kernels.cuh eis_row_sub): 0 = plain loop (B200PCG_EIS_BATCH=0)
+int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
+    if (ctx->eisBatch == 0) return 0;
+    return P.maxRowLen <= 6 ? 6 : 8;
 }
 
-// One loop body: k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps (+ (p^, w^)) ->
-// k_eis_r (+ rho) -> k_eis_res (true residual, device-gated)
-int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
-    const int N = ctx->N;
-    Scalars* S = ctx->S;
-    const int gv = grid_for(ctx, (N + 1) / 2);
+template <bool C16, int B>
+int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
     const int C = P.h.nColours;
-    const int lastStart = P.h.colourStart[C - 1];
-    const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
-    const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
+    Scalars* S = ctx->S;
     const EllCols E{P.col, P.col16, P.colBase};
-    LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->psi, ctx->p, ctx->r, ctx->dT, ctx->rD, ctx->t, S);
+    // batched sweeps: one resident wave (the CTAs per SM the kernels are compiled for); plain loops: 8 per SM
+    const int perSM = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : eis_sweep_ctas(B));
     for (int k = C - 2; k >= 0; --k) {
-        int g;
-        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+        const int g = grid_for(ctx, r1 - r0, perSM);
         Reduce R = mkR(ctx, STEP_NONE);
-#define B200_EBWD(F0_, C16_)                                                                            \
-    do {                                                                                                \
-        auto kb = k_eis_bwd<F0_, C16_>;                                                                 \
-        LAUNCH(PC_EIS_BWD, kb, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->t, ctx->w, R); \
-    } while (0)
-        const bool f0 = fuse0 && k == 0;
-        if (f0 && P.c16) B200_EBWD(true, true);
-        else if (f0) B200_EBWD(true, false);
-        else if (P.c16) B200_EBWD(false, true);
-        else B200_EBWD(false, false);
-#undef B200_EBWD
+        if (fuse0 && k == 0) {
+            auto kb = k_eis_bwd<true, C16, B>;
+            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
+        } else {
+            auto kb = k_eis_bwd<false, C16, B>;
+            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
+        }
     }
     if (halo) {
-        // t is complete on every rank: pack + exchange on the comm stream, then the halo term B t
+        // t is complete on every rank: pack + exchange on the comm stream, then the halo term B- t
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
         k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, ctx->t, ctx->sendbuf, S);
@@ -838,37 +802,122 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
                ctx->recvbuf, P.hb, S);
     }
     for (int k = fuse0 ? 1 : 0; k < C; ++k) {
-        int g;
-        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+        const int g = grid_for(ctx, r1 - r0, perSM);
         const bool last = (k == C - 1);
         Reduce R = mkR(ctx, last ? STEP_WAPA : STEP_NONE);
-#define B200_EFWD(L_, H_, C16_)                                                                          \
-    do {                                                                                                 \
-        auto kf = k_eis_fwd<L_, H_, C16_>;                                                               \
-        LAUNCH(PC_EIS_FWD, kf, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->rD, ctx->p, ctx->eD, ctx->t,  \
-               ctx->w, P.rowB, P.hb, R);                                                                 \
+#define B200_EFWD(L_, H_)                                                                                 \
+    do {                                                                                                  \
+        auto kf = k_eis_fwd<L_, H_, C16, B>;                                                              \
+        LAUNCH(PC_EIS_FWD, kf, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->eD, ctx->t, ctx->w, \
+               P.rowB, P.hb, R);                                                                          \
     } while (0)
-        const int sel = (last ? 4 : 0) | (halo ? 2 : 0) | (P.c16 ? 1 : 0);
-        switch (sel) {
-            case 0: B200_EFWD(false, false, false); break;
-            case 1: B200_EFWD(false, false, true); break;
-            case 2: B200_EFWD(false, true, false); break;
-            case 3: B200_EFWD(false, true, true); break;
-            case 4: B200_EFWD(true, false, false); break;
-            case 5: B200_EFWD(true, false, true); break;
-            case 6: B200_EFWD(true, true, false); break;
-            default: B200_EFWD(true, true, true); break;
-        }
+        if (last && halo) B200_EFWD(true, true);
+        else if (last) B200_EFWD(true, false);
+        else if (halo) B200_EFWD(false, true);
+        else B200_EFWD(false, false);
 #undef B200_EFWD
+    }
+    return B200_OK;
+}
+
+// per solve: D~ (DIC recurrence, one launch per colour), its sign, the symmetric scaling (s, D- - 2, the
+// coefficient copy, the interface coefficients), r^ = (I+L-)^-1 sigma S r, rho_0
+int eis_setup(b200_ctx* ctx, DevPlan& P) {
+    if (P.h.nTiles > 1)
+        return fail(ctx, B200_EUNSUPPORTED, "dicMode eisenstat needs the colour-major plan (unset B200PCG_TILE)");
+    RET(ensure_eis_buffers(ctx, P));
+    const int N = ctx->N;
+    Scalars* S = ctx->S;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    const int gn = grid_for(ctx, N);
+    const EllCols E{P.col, P.col16, P.colBase};
+    for (int k = 0; k < P.h.nColours; ++k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        if (P.c16) {
+            auto kd = k_dic_calc_rd<true>;
+            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
+        } else {
+            auto kd = k_dic_calc_rd<false>;
+            LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->dT);
+        }
+    }
+    {
+        Reduce R = mkR(ctx, STEP_EIS_SIGN);
+        LAUNCH(PC_EIS_SETUP, k_eis_sign, gn, N, ctx->dT, R);
+        RET(reduce_post(ctx, STEP_EIS_SIGN));
+    }
+    LAUNCH(PC_EIS_SETUP, k_eis_setup, gn, N, ctx->diag, ctx->dT, ctx->eD, ctx->r, ctx->rD, S);
+    if (ctx->nranks > 1 && P.nSlots > 0) {
+        // the neighbours' s on the patch faces -> interface coefficients of B- (once per solve: same stream)
+        k_eis_pack_s<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sc>>>(P.nSlots, P.slotRow, ctx->dT, ctx->sendbuf);
+        ctx->launches++;
+        NC(g_nccl.GroupStart());
+        for (int k = 0; k < P.h.nIfaces; ++k) {
+            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+            if (n == 0) continue;
+            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
+            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
+        }
+        NC(g_nccl.GroupEnd());
+        LAUNCH(PC_EIS_SETUP, k_eis_scale_bou, grid_for(ctx, P.nSlots), P.nSlots, P.slotRow, ctx->dT, ctx->recvbuf,
+               ctx->bou, S);
+    }
+    if (P.c16) {
+        auto ks = k_eis_scale_vals<true>;
+        LAUNCH(PC_EIS_SETUP, ks, gn, N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, S);
+    } else {
+        auto ks = k_eis_scale_vals<false>;
+        LAUNCH(PC_EIS_SETUP, ks, gn, N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, S);
+    }
+    for (int k = 0; k < P.h.nColours; ++k) {
+        const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
+        const int g = grid_for(ctx, r1 - r0, ctx->sweepPerSM);
+        if (P.c16) {
+            auto kf = k_eis_init_fwd<true>;
+            LAUNCH(PC_EIS_SETUP, kf, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->r, S);
+        } else {
+            auto kf = k_eis_init_fwd<false>;
+            LAUNCH(PC_EIS_SETUP, kf, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->r, S);
+        }
+    }
+    Reduce R = mkR(ctx, STEP_EIS_RHO0);
+    LAUNCH(PC_EIS_SETUP, k_eis_rho0, gv, N, ctx->r, R);
+    RET(reduce_post(ctx, STEP_EIS_RHO0));
+    return B200_OK;
+}
+
+// One loop body: k_eis_p -> backward sweeps -> [halo exchange of t] -> forward sweeps (+ (p^, w^)) ->
+// k_eis_r (+ rho) -> k_eis_res (true residual, device-gated)
+int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
+    const int N = ctx->N;
+    Scalars* S = ctx->S;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    const int C = P.h.nColours;
+    const int lastStart = P.h.colourStart[C - 1];
+    const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
+    const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
+    LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->rD, ctx->p, ctx->t, ctx->r, S);
+    const int B = eis_batch(ctx, P);
+    if (P.c16) {
+        if (B == 0) RET((launch_eis_sweeps<true, 0>(ctx, P, halo, fuse0)));
+        else if (B == 6) RET((launch_eis_sweeps<true, 6>(ctx, P, halo, fuse0)));
+        else RET((launch_eis_sweeps<true, 8>(ctx, P, halo, fuse0)));
+    } else {
+        if (B == 0) RET((launch_eis_sweeps<false, 0>(ctx, P, halo, fuse0)));
+        else if (B == 6) RET((launch_eis_sweeps<false, 6>(ctx, P, halo, fuse0)));
+        else RET((launch_eis_sweeps<false, 8>(ctx, P, halo, fuse0)));
     }
     RET(reduce_post(ctx, STEP_WAPA));
     {
         Reduce R = mkR(ctx, STEP_EIS_RHO);
-        LAUNCH(PC_EIS_R, k_eis_r, gv, N, lastStart, ctx->r, ctx->w, ctx->t, ctx->dT, R);
+        LAUNCH(PC_EIS_R, k_eis_r, gv, N, lastStart, ctx->r, ctx->w, ctx->t, R);
         RET(reduce_post(ctx, STEP_EIS_RHO));
     }
     {
         Reduce R = mkR(ctx, STEP_EIS_RES);
+        const EllCols E{P.col, P.col16, P.colBase};
         if (P.c16) {
             auto kr = k_eis_res<true>;
             LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
@@ -915,6 +964,9 @@ int finish_solve(b200_ctx* ctx, DevPlan& P, b200_perf* perf) {
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
         perf->solveMs = ms;
     }
+    if (h.nonfinite == 3)
+        return fail(ctx, B200_EUNSUPPORTED, "DIC pivots are zero or of mixed sign: dicMode eisenstat needs a definite matrix "
+                                            "(use dicMode multicolour)");
     if (h.nonfinite == 2) return fail(ctx, B200_ENCCL, "peer-memory all-reduce timed out (a rank never arrived)");
     if (h.nonfinite) return fail(ctx, B200_ENONFINITE, "non-finite residual in PCG");
     return B200_OK;
@@ -1060,7 +1112,8 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         CU(cudaGetLastError());
         if (chunk < 64) chunk *= 2;
     }
-    LAUNCH(PC_PSI_FINAL, k_psi_final, gv, N, ctx->psi, eis ? ctx->t : ctx->p, S);   // last deferred psi += alpha*p
+    if (eis) LAUNCH(PC_PSI_FINAL, k_eis_final, grid_for(ctx, N), N, ctx->psi, ctx->rD, ctx->t, ctx->dT, S);
+    else LAUNCH(PC_PSI_FINAL, k_psi_final, gv, N, ctx->psi, ctx->p, S);   // last deferred psi += alpha*pA
     CU(cudaEventRecord(ctx->ev[2], ctx->sc));
     LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
     CU(cudaStreamSynchronize(ctx->sc));
@@ -1185,7 +1238,11 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e15 = getenv("B200PCG_COL16")) c->disableCol16 = atoi(e15) == 0;
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
-    if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
+    if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
+    if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
+        c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
+        c->sweepPerSMSet = true;
+    }
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);

@@ -273,7 +273,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
     diag_i, src, psi = pv.to_internal(diag), pv.to_internal(source), pv.to_internal(psi0)
     lastStart = int(pv.colourStart[C - 1])
     S = dict(done=0, nIter=0, converged=0, singular=0, pendingPsi=0, wArA=1e20, wArAold=1e20, beta=0.0,
-             alpha=0.0, cRatio=0.0, sinceCheck=0, needCheck=0)
+             alpha=0.0, cRatio=0.0, sinceCheck=0, needCheck=0, sigma=1.0)
     conv = lambda: S["finalRes"] < tol or (relTol > 1e-20 and S["finalRes"] < relTol * S["initRes"])
     # spmv_full<INIT> + k_sum + k_norm_resid (STEP_NORM)
     wA, nf = _norm_factor(pv, diag_i, val, psi, src)
@@ -282,7 +282,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
     S["initRes"] = S["finalRes"] = np.abs(rh).sum() / nf
     S["converged"] = int(conv())
     S["done"] = 0 if (minIter > 0 or not S["converged"]) else 1
-    # eis_setup: k_dic_calc_rd per colour -> dT; k_eis_setup; k_eis_init_fwd per colour; k_eis_rho0
+    # eis_setup: k_dic_calc_rd per colour -> dT
     dT = np.empty(N)
     for k in range(C):
         for r in pv.rows_of_colour(k):
@@ -291,18 +291,36 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                 e = pv.entry(r, j)
                 d = d - (val[e] * val[e]) / dT[pv.col[e]]
             dT[r] = d
-    rD = 1.0 / dT
-    eD = diag_i - 2.0 * dT
+    # k_eis_sign + STEP_EIS_SIGN
     if not S["done"]:
+        neg, bad = float((dT < 0).sum()), float((~((np.abs(dT) > 0) & (np.abs(dT) < 1.7e308))).sum())
+        if bad > 0 or (0 < neg < N):
+            raise ValueError("DIC pivots are zero or of mixed sign")
+        S["sigma"] = -1.0 if neg > 0 else 1.0
+    sv = eb = xa = None
+    if not S["done"]:
+        # k_eis_setup
+        sigma = S["sigma"]
+        sv = 1.0 / np.sqrt(np.abs(dT))
+        eb = diag_i / dT - 2.0
+        rh = (sigma * sv) * rh
+        xa = np.zeros(N)
+        # k_eis_scale_vals (both triangles of the plan's coefficient copy)
+        val = val.copy()
+        for r in range(N):
+            for j in range(pv.nTotal[r]):
+                e = pv.entry(r, j)
+                val[e] = val[e] * (sigma * (sv[r] * sv[pv.col[e]]))
+        # k_eis_init_fwd per colour, in place
         for k in range(C):
             for r in pv.rows_of_colour(k):
-                w = rD[r] * rh[r]
+                w = rh[r]
                 for j in range(pv.nLower[r]):
                     e = pv.entry(r, j)
-                    w = w - (rD[r] * val[e]) * rh[pv.col[e]]
+                    w = w - val[e] * rh[pv.col[e]]
                 rh[r] = w
-        g = ((dT * rh) * rh).sum()
-        S["wArA"], S["beta"] = g, 0.0                      # STEP_EIS_RHO0
+        g = (rh * rh).sum()                                 # k_eis_rho0, STEP_EIS_RHO0
+        S["wArA"], S["beta"] = g, 0.0
         a = np.sqrt(abs(g))
         S["cRatio"] = S["finalRes"] / a if a > 0 else 0.0
     ph, t, y = np.zeros(N), np.zeros(N), np.zeros(N)
@@ -311,44 +329,47 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
     enq, cap = 0, max(maxIter + 1, minIter)
     while not S["done"] and enq < cap:
         enq += 1
-        # k_eis_p
+        # k_eis_p: rows >= lastStart keep p^ in t
         first = S["nIter"] == 0
-        p = dT * rh
+        p = rh.copy()
         if not first:
-            psi = psi + S["alpha"] * t
-            p = p + S["beta"] * ph
-        ph = p
+            po = np.where(np.arange(N) >= lastStart, t, ph)
+            xa = xa + S["alpha"] * t
+            p = p + S["beta"] * po
+        ph = ph.copy()
         t = t.copy()
-        t[lastStart:] = rD[lastStart:] * ph[lastStart:]
+        ph[:lastStart] = p[:lastStart]
+        t[lastStart:] = p[lastStart:]
         dot = 0.0
         # k_eis_bwd, colours C-2 .. 0
         for k in range(C - 2, -1, -1):
             for r in pv.rows_of_colour(k):
-                w = rD[r] * ph[r]
+                assert r < lastStart
+                w = ph[r]
                 for j in range(pv.nTotal[r] - 1, pv.nLower[r] - 1, -1):
                     e = pv.entry(r, j)
-                    w = w - (rD[r] * val[e]) * t[pv.col[e]]
+                    w = w - val[e] * t[pv.col[e]]
                 t[r] = w
                 if fuse0 and k == 0:
-                    assert pv.nLower[r] == 0
-                    yv = rD[r] * ph[r] - w           # D~ == D, e == -D~ on first-colour rows
+                    assert pv.nLower[r] == 0 and abs(eb[r] + 1.0) < 1e-12    # D- == 1 on first-colour rows
+                    yv = ph[r] - w
                     y[r] = yv
                     dot += ph[r] * (w + yv)
         # k_eis_fwd
         for k in range(1 if fuse0 else 0, C):
             last = k == C - 1
             for r in pv.rows_of_colour(k):
-                tv = rD[r] * ph[r] if last else t[r]
-                assert tv == t[r]
-                rhs = ph[r] + eD[r] * tv
-                w = rD[r] * rhs
+                assert (r >= lastStart) == last
+                tv = t[r]
+                pp = tv if last else ph[r]
+                w = pp + eb[r] * tv
                 for j in range(pv.nLower[r]):
                     e = pv.entry(r, j)
                     assert pv.col[e] < lastStart     # a gathered y is never a stored w^
-                    w = w - (rD[r] * val[e]) * y[pv.col[e]]
-                wh = t[r] + w
+                    w = w - val[e] * y[pv.col[e]]
+                wh = tv + w
                 y[r] = wh if last else w
-                dot += ph[r] * wh
+                dot += pp * wh
         # STEP_WAPA
         S["wApA"] = dot
         if not (abs(dot) / nf > 1e-300):
@@ -360,7 +381,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
         w = y.copy()
         w[:lastStart] = t[:lastStart] + y[:lastStart]
         rh = rh - S["alpha"] * w
-        g = ((dT * rh) * rh).sum()
+        g = (rh * rh).sum()
         S["wArAold"], S["wArA"] = S["wArA"], g
         S["beta"] = S["wArA"] / S["wArAold"]
         old = S["nIter"]
@@ -375,11 +396,11 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
             checks += 1
             tot = 0.0
             for r in range(N):
-                acc = dT[r] * rh[r]
+                acc = rh[r]
                 for j in range(pv.nLower[r]):
                     e = pv.entry(r, j)
                     acc = acc + val[e] * rh[pv.col[e]]
-                tot += abs(acc)
+                tot += abs(acc) / sv[r]
             S["finalRes"] = tot / nf
             S["converged"] = int(conv())
             cont = (S["nIter"] - 1 < maxIter and not S["converged"]) or S["nIter"] < minIter
@@ -388,6 +409,8 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
             a = np.sqrt(abs(S["wArA"]))
             S["cRatio"] = S["finalRes"] / a if a > 0 else 0.0
             S["sinceCheck"], S["needCheck"] = 0, 0
-    if S["pendingPsi"]:
-        psi = psi + S["alpha"] * t          # k_psi_final
+    # k_eis_final
+    if not (S["nIter"] == 0 and not S["pendingPsi"]):
+        x = xa + S["alpha"] * t if S["pendingPsi"] else xa
+        psi = psi + sv * x
     return pv.to_natural(psi), S["nIter"], S["finalRes"], checks

@@ -92,8 +92,10 @@ def test_eisenstat_negative_definite_hydrostatic_loop(ctx):
     assert res[3][2] == 0 and res[4][2] == 0
 
 
-@pytest.mark.parametrize("env", [{"B200PCG_COL16": "0"}, {"B200PCG_RENUMBER": "1"}, {"B200PCG_RENUMBER": "0"}],
-                         ids=["col32", "rcm", "natural-base"])
+@pytest.mark.parametrize("env", [{"B200PCG_COL16": "0"}, {"B200PCG_RENUMBER": "1"}, {"B200PCG_RENUMBER": "0"},
+                                 {"B200PCG_EIS_BATCH": "0"}, {"B200PCG_EIS_BATCH": "0", "B200PCG_COL16": "0"},
+                                 {"B200PCG_SWEEP_CTAS": "2"}],
+                         ids=["col32", "rcm", "natural-base", "plain-loops", "plain-loops-col32", "2-ctas"])
 def test_eisenstat_plan_variants(env):
     """32-bit ELL columns, RCM-renumbered and natural base orders; polyhedral mesh (>= 4 colours: several
     un-fused backward and forward launches) and a random graph, multi-kernel path."""
@@ -108,6 +110,19 @@ def test_eisenstat_plan_variants(env):
             assert np.linalg.norm(xe - xc) / np.linalg.norm(xc) < 1e-8
     finally:
         c.close()
+
+
+def test_eisenstat_rejects_indefinite_matrix(ctx):
+    """DIC pivots of mixed sign: the symmetric scaling does not exist -> B200_EUNSUPPORTED, context still usable."""
+    from firefoam_dev_b200 import B200Error
+    s = mg.hex_block(64, 64, 64)
+    bad = mg.System(s.addr, s.diag.copy(), s.upper, s.source, s.bou, s.xstar)
+    bad.diag[1000] = -bad.diag[1000]
+    with pytest.raises(B200Error) as ei:
+        solve_mode(ctx, bad, "eisenstat")
+    assert "mixed sign" in str(ei.value)
+    xe, pe = solve_mode(ctx, s, "eisenstat")
+    assert pe.converged and relmax(xe, s.xstar) < 1e-3
 
 
 def test_eisenstat_rejects_tiled_plan():
