@@ -1506,8 +1506,8 @@ k_eis_p(int N, int lastStart, double* __restrict__ xa, double* __restrict__ ph, 
 // rank): its rows have no earlier neighbours and D- == 1 there, so their forward sweep
 // y = p^ + (D- - 2) t = p^ - t and their share of (p^, w^) ride along.
 // B > 0: the next row's row length / slice base / p^ are requested before the current row's gathers.
-template <bool FWD0, bool C16, int B>
-__global__ void __launch_bounds__(kBlock, eis_sweep_ctas(B))
+template <bool FWD0, bool C16, int B, int CT>
+__global__ void __launch_bounds__(kBlock, CT)
 k_eis_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ ph, double* t,
           double* __restrict__ y, Reduce R) {
@@ -1559,8 +1559,8 @@ k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ b
 // forward sweep over the rows [r0, r1) of one colour: y = p^ + (D- - 2) t [+ B- t] - L- y; every colour
 // adds its share of (p^, w^), w^ = t + y.  LAST: p^ == t lives in t; the rows are gathered by no sweep
 // and store w^.
-template <bool LAST, bool HALO, bool C16, int B>
-__global__ void __launch_bounds__(kBlock, eis_sweep_ctas(B))
+template <bool LAST, bool HALO, bool C16, int B, int CT>
+__global__ void __launch_bounds__(kBlock, CT)
 k_eis_fwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ ph,
           const double* __restrict__ eb, const double* __restrict__ t, double* y,

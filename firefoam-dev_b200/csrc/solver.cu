@@ -198,6 +198,7 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    int eisCtas = 4;            // B200PCG_EIS_CTAS=3: 85-register build of the 6-entry batched sweeps (A/B switch)
     int eisBatch = 1;           // B200PCG_EIS_BATCH=0: plain entry loops in the Eisenstat sweeps (A/B switch)
     int sweepPerSM = 8;         // B200PCG_SWEEP_CTAS: CTAs per SM of the colour sweeps (DIC-class, Eisenstat form)
     bool sweepPerSMSet = false;
@@ -763,22 +764,22 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
     return P.maxRowLen <= 6 ? 6 : 8;
 }
 
-template <bool C16, int B>
+template <bool C16, int B, int CT>
 int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
     const int C = P.h.nColours;
     Scalars* S = ctx->S;
     const EllCols E{P.col, P.col16, P.colBase};
     // batched sweeps: one resident wave (the CTAs per SM the kernels are compiled for); plain loops: 8 per SM
-    const int perSM = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : eis_sweep_ctas(B));
+    const int perSM = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : CT);
     for (int k = C - 2; k >= 0; --k) {
         const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
         const int g = grid_for(ctx, r1 - r0, perSM);
         Reduce R = mkR(ctx, STEP_NONE);
         if (fuse0 && k == 0) {
-            auto kb = k_eis_bwd<true, C16, B>;
+            auto kb = k_eis_bwd<true, C16, B, CT>;
             LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
         } else {
-            auto kb = k_eis_bwd<false, C16, B>;
+            auto kb = k_eis_bwd<false, C16, B, CT>;
             LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
         }
     }
@@ -808,7 +809,7 @@ int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
         Reduce R = mkR(ctx, last ? STEP_WAPA : STEP_NONE);
 #define B200_EFWD(L_, H_)                                                                                 \
     do {                                                                                                  \
-        auto kf = k_eis_fwd<L_, H_, C16, B>;                                                              \
+        auto kf = k_eis_fwd<L_, H_, C16, B, CT>;                                                             \
         LAUNCH(PC_EIS_FWD, kf, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->eD, ctx->t, ctx->w, \
                P.rowB, P.hb, R);                                                                          \
     } while (0)
@@ -900,14 +901,18 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
     const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
     LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->rD, ctx->p, ctx->t, ctx->r, S);
     const int B = eis_batch(ctx, P);
+    // CT = resident CTAs per SM the sweep kernels are compiled for (register cap 65536 / (256 CT))
+    const bool wide = (B == 6 && ctx->eisCtas == 3);
     if (P.c16) {
-        if (B == 0) RET((launch_eis_sweeps<true, 0>(ctx, P, halo, fuse0)));
-        else if (B == 6) RET((launch_eis_sweeps<true, 6>(ctx, P, halo, fuse0)));
-        else RET((launch_eis_sweeps<true, 8>(ctx, P, halo, fuse0)));
+        if (B == 0) RET((launch_eis_sweeps<true, 0, 1>(ctx, P, halo, fuse0)));
+        else if (B == 6 && wide) RET((launch_eis_sweeps<true, 6, 3>(ctx, P, halo, fuse0)));
+        else if (B == 6) RET((launch_eis_sweeps<true, 6, 4>(ctx, P, halo, fuse0)));
+        else RET((launch_eis_sweeps<true, 8, 3>(ctx, P, halo, fuse0)));
     } else {
-        if (B == 0) RET((launch_eis_sweeps<false, 0>(ctx, P, halo, fuse0)));
-        else if (B == 6) RET((launch_eis_sweeps<false, 6>(ctx, P, halo, fuse0)));
-        else RET((launch_eis_sweeps<false, 8>(ctx, P, halo, fuse0)));
+        if (B == 0) RET((launch_eis_sweeps<false, 0, 1>(ctx, P, halo, fuse0)));
+        else if (B == 6 && wide) RET((launch_eis_sweeps<false, 6, 3>(ctx, P, halo, fuse0)));
+        else if (B == 6) RET((launch_eis_sweeps<false, 6, 4>(ctx, P, halo, fuse0)));
+        else RET((launch_eis_sweeps<false, 8, 3>(ctx, P, halo, fuse0)));
     }
     RET(reduce_post(ctx, STEP_WAPA));
     {
@@ -1239,6 +1244,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
+    if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : 4;
     if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
         c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
         c->sweepPerSMSet = true;
