@@ -198,7 +198,8 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
-    int eisCtas = 4;            // B200PCG_EIS_CTAS=3: 85-register build of the 6-entry batched sweeps (A/B switch)
+    int eisCtas = 0;            // B200PCG_EIS_CTAS=3|4: force the 80- / 64-register build of both 6-entry batched
+                                // sweeps (default 0: backward 64, forward 80 registers)
     int eisBatch = 1;           // B200PCG_EIS_BATCH=0: plain entry loops in the Eisenstat sweeps (A/B switch)
     int sweepPerSM = 8;         // B200PCG_SWEEP_CTAS: CTAs per SM of the colour sweeps (DIC-class, Eisenstat form)
     bool sweepPerSMSet = false;
@@ -764,22 +765,23 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
     return P.maxRowLen <= 6 ? 6 : 8;
 }
 
-template <bool C16, int B, int CT>
+template <bool C16, int B, int CTB, int CTF>
 int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
     const int C = P.h.nColours;
     Scalars* S = ctx->S;
     const EllCols E{P.col, P.col16, P.colBase};
     // batched sweeps: one resident wave (the CTAs per SM the kernels are compiled for); plain loops: 8 per SM
-    const int perSM = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : CT);
+    const int perSMB = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : CTB);
+    const int perSMF = ctx->sweepPerSMSet ? ctx->sweepPerSM : (B == 0 ? 8 : CTF);
     for (int k = C - 2; k >= 0; --k) {
         const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
-        const int g = grid_for(ctx, r1 - r0, perSM);
+        const int g = grid_for(ctx, r1 - r0, perSMB);
         Reduce R = mkR(ctx, STEP_NONE);
         if (fuse0 && k == 0) {
-            auto kb = k_eis_bwd<true, C16, B, CT>;
+            auto kb = k_eis_bwd<true, C16, B, CTB>;
             LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
         } else {
-            auto kb = k_eis_bwd<false, C16, B, CT>;
+            auto kb = k_eis_bwd<false, C16, B, CTB>;
             LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
         }
     }
@@ -804,12 +806,12 @@ int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
     }
     for (int k = fuse0 ? 1 : 0; k < C; ++k) {
         const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
-        const int g = grid_for(ctx, r1 - r0, perSM);
+        const int g = grid_for(ctx, r1 - r0, perSMF);
         const bool last = (k == C - 1);
         Reduce R = mkR(ctx, last ? STEP_WAPA : STEP_NONE);
 #define B200_EFWD(L_, H_)                                                                                 \
     do {                                                                                                  \
-        auto kf = k_eis_fwd<L_, H_, C16, B, CT>;                                                             \
+        auto kf = k_eis_fwd<L_, H_, C16, B, CTF>;                                                             \
         LAUNCH(PC_EIS_FWD, kf, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->eD, ctx->t, ctx->w, \
                P.rowB, P.hb, R);                                                                          \
     } while (0)
@@ -901,19 +903,23 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
     const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
     LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->rD, ctx->p, ctx->t, ctx->r, S);
     const int B = eis_batch(ctx, P);
-    // CT = resident CTAs per SM the sweep kernels are compiled for (register cap 65536 / (256 CT))
-    const bool wide = (B == 6 && ctx->eisCtas == 3);
-    if (P.c16) {
-        if (B == 0) RET((launch_eis_sweeps<true, 0, 1>(ctx, P, halo, fuse0)));
-        else if (B == 6 && wide) RET((launch_eis_sweeps<true, 6, 3>(ctx, P, halo, fuse0)));
-        else if (B == 6) RET((launch_eis_sweeps<true, 6, 4>(ctx, P, halo, fuse0)));
-        else RET((launch_eis_sweeps<true, 8, 3>(ctx, P, halo, fuse0)));
-    } else {
-        if (B == 0) RET((launch_eis_sweeps<false, 0, 1>(ctx, P, halo, fuse0)));
-        else if (B == 6 && wide) RET((launch_eis_sweeps<false, 6, 3>(ctx, P, halo, fuse0)));
-        else if (B == 6) RET((launch_eis_sweeps<false, 6, 4>(ctx, P, halo, fuse0)));
-        else RET((launch_eis_sweeps<false, 8, 3>(ctx, P, halo, fuse0)));
-    }
+    // CTB / CTF = resident CTAs per SM the backward / forward sweep kernels are compiled for (register cap
+    // 65536 / (256 CT)).  Measured on the 16 M hex box (profiles/r01_v10_eisenstat_sweep_builds_ab.log): the
+    // backward sweep is fastest in the 64-register build (141 vs 170 us), the forward sweep -- two more
+    // per-row streams -- in the 80-register build, where all 12 column loads of a batch get their own
+    // registers (141 vs 183 us).  B200PCG_EIS_CTAS=3|4 forces one build for both.
+    const int ctb = ctx->eisCtas ? ctx->eisCtas : 4, ctf = ctx->eisCtas ? ctx->eisCtas : 3;
+#define B200_SWEEPS(C16_)                                                                                     \
+    do {                                                                                                      \
+        if (B == 0) RET((launch_eis_sweeps<C16_, 0, 1, 1>(ctx, P, halo, fuse0)));                              \
+        else if (B == 8) RET((launch_eis_sweeps<C16_, 8, 3, 3>(ctx, P, halo, fuse0)));                         \
+        else if (ctb == 4 && ctf == 3) RET((launch_eis_sweeps<C16_, 6, 4, 3>(ctx, P, halo, fuse0)));           \
+        else if (ctb == 3) RET((launch_eis_sweeps<C16_, 6, 3, 3>(ctx, P, halo, fuse0)));                       \
+        else RET((launch_eis_sweeps<C16_, 6, 4, 4>(ctx, P, halo, fuse0)));                                     \
+    } while (0)
+    if (P.c16) B200_SWEEPS(true);
+    else B200_SWEEPS(false);
+#undef B200_SWEEPS
     RET(reduce_post(ctx, STEP_WAPA));
     {
         Reduce R = mkR(ctx, STEP_EIS_RHO);
@@ -1244,7 +1250,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
-    if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : 4;
+    if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : (atoi(e18) == 4 ? 4 : 0);
     if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
         c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
         c->sweepPerSMSet = true;

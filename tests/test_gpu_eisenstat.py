@@ -94,8 +94,8 @@ def test_eisenstat_negative_definite_hydrostatic_loop(ctx):
 
 @pytest.mark.parametrize("env", [{"B200PCG_COL16": "0"}, {"B200PCG_RENUMBER": "1"}, {"B200PCG_RENUMBER": "0"},
                                  {"B200PCG_EIS_BATCH": "0"}, {"B200PCG_EIS_BATCH": "0", "B200PCG_COL16": "0"},
-                                 {"B200PCG_SWEEP_CTAS": "2"}, {"B200PCG_EIS_CTAS": "3"}, {"B200PCG_EIS_CTAS": "3", "B200PCG_COL16": "0"}],
-                         ids=["col32", "rcm", "natural-base", "plain-loops", "plain-loops-col32", "2-ctas", "3cta-build", "3cta-build-col32"])
+                                 {"B200PCG_SWEEP_CTAS": "2"}, {"B200PCG_EIS_CTAS": "3"}, {"B200PCG_EIS_CTAS": "3", "B200PCG_COL16": "0"}, {"B200PCG_EIS_CTAS": "4"}],
+                         ids=["col32", "rcm", "natural-base", "plain-loops", "plain-loops-col32", "2-ctas", "3cta-build", "3cta-build-col32", "4cta-build"])
 def test_eisenstat_plan_variants(env):
     """32-bit ELL columns, RCM-renumbered and natural base orders; polyhedral mesh (>= 4 colours: several
     un-fused backward and forward launches) and a random graph, multi-kernel path."""
