@@ -41,10 +41,13 @@ enum Step : int {
     STEP_EIS_RES   // true residual |(D~+L) r^|_1 / normFactor; convergence; loop condition
 };
 
-// Eisenstat form: the true residual is evaluated when the predictor cRatio*sqrt(|rho|) is within
-// kEisMargin of the convergence threshold, and at least every kEisEvery iterations (re-calibration).
-constexpr double kEisMargin = 8.0;
-constexpr int kEisEvery = 32;
+// Eisenstat form: how many iterations may pass between two evaluations of the true residual, as a function
+// of q = predicted residual / convergence threshold (predictor: cRatio*sqrt(rho), re-calibrated at every
+// evaluation).  Far from convergence the evaluation only re-calibrates the predictor; close to it every
+// iteration is checked, so the loop stops within an iteration or two of the first crossing.
+__host__ __device__ inline int eis_check_interval(double q) {
+    return q < 1.5 ? 1 : (q < 4.0 ? 2 : (q < 32.0 ? 8 : 32));
+}
 
 struct Scalars {
     // controls (written by the host before each solve)
@@ -196,8 +199,8 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
             const bool mustStop = S->forceIters > 0 ? (S->nIter >= S->forceIters) : !(old < S->maxIter);
             double thr = S->tol;
             if (S->relTol > 1e-20 && S->relTol * S->initRes > thr) thr = S->relTol * S->initRes;
-            const bool nearThr = S->forceIters > 0 ? false : (S->cRatio * sqrt(fabs(g[0])) < kEisMargin * thr);
-            S->needCheck = (mustStop || nearThr || S->sinceCheck >= kEisEvery) ? 1 : 0;
+            const int every = S->forceIters > 0 ? 32 : eis_check_interval(S->cRatio * sqrt(fabs(g[0])) / thr);
+            S->needCheck = (mustStop || S->sinceCheck >= every) ? 1 : 0;
             break;
         }
         case STEP_EIS_RES: {

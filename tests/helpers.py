@@ -220,7 +220,8 @@ def hydrostatic_loop(case, laplacian, solve):
 
 
 # ---- numpy transliteration of the Eisenstat-form DIC-class loop (kernels.cuh k_eis_*) --------------
-EIS_MARGIN, EIS_EVERY = 8.0, 32    # kEisMargin, kEisEvery
+def eis_check_interval(q):          # kernels.cuh eis_check_interval
+    return 1 if q < 1.5 else (2 if q < 4.0 else (8 if q < 32.0 else 32))
 
 
 def _norm_factor(pv, diag_i, val, psi_i, src_i, halo_sumA=None):
@@ -389,8 +390,8 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
         S["sinceCheck"] += 1
         mustStop = not (old < maxIter)
         thr = max(tol, relTol * S["initRes"]) if relTol > 1e-20 else tol
-        near = S["cRatio"] * np.sqrt(abs(g)) < EIS_MARGIN * thr
-        S["needCheck"] = int(mustStop or near or S["sinceCheck"] >= EIS_EVERY)
+        every = eis_check_interval(S["cRatio"] * np.sqrt(abs(g)) / thr)
+        S["needCheck"] = int(mustStop or S["sinceCheck"] >= every)
         # k_eis_res + STEP_EIS_RES
         if S["needCheck"]:
             checks += 1
