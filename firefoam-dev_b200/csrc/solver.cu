@@ -931,10 +931,10 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
         const EllCols E{P.col, P.col16, P.colBase};
         if (P.c16) {
             auto kr = k_eis_res<true>;
-            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N, 4), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
         } else {
             auto kr = k_eis_res<false>;
-            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N, 4), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
         }
         RET(reduce_post(ctx, STEP_EIS_RES));
     }
