@@ -1505,15 +1505,19 @@ k_eis_p(int N, int lastStart, double* __restrict__ xa, double* __restrict__ ph, 
         { eis_p_elem(i, i >= lastStart, first, alpha, beta, rh, ph, t, xa); })
 }
 
-// backward sweep over the rows [r0, r1) of one colour: t = p^ - L-^T t.  FWD0 (first colour, single
-// rank): its rows have no earlier neighbours and D- == 1 there, so their forward sweep
-// y = p^ + (D- - 2) t = p^ - t and their share of (p^, w^) ride along.
+// backward sweep over the rows [r0, r1) of one colour: t = p^ - L-^T t.
+// FWD0 == 1 (first colour, single rank): its rows have no earlier neighbours and D- == 1 there, so their
+// forward sweep y = p^ + (D- - 2) t = p^ - t and their share of (p^, w^) ride along.
+// FWD0 == 2 (first colour, nranks > 1, halo overlapped): the same for the rows WITHOUT a processor face;
+// the interface rows (rowB >= 0) were swept by k_eis_bwd_rows before the halo exchange started and get
+// their forward part from k_eis_fwd_rows once the halo term has arrived -- they are left alone here, so
+// this kernel runs concurrently with the exchange of t.
 // B > 0: the next row's row length / slice base / p^ are requested before the current row's gathers.
-template <bool FWD0, bool C16, int B, int CT>
+template <int FWD0, bool C16, int B, int CT>
 __global__ void __launch_bounds__(kBlock, CT)
 k_eis_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ ph, double* t,
-          double* __restrict__ y, Reduce R) {
+          double* __restrict__ y, const int* __restrict__ rowB, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
     const int stride = gridDim.x * kBlock;
@@ -1521,25 +1525,68 @@ k_eis_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t*
     uint32_t len = 0;
     int64_t sb = 0;
     double p = 0.0;
-    if (r < r1) { len = rowLen[r]; sb = sliceBase[r >> 5]; p = ph[r]; }
+    int bi = -1;
+#define B200_EIS_BWD_LOAD(ROW, LEN, SB, P, BI)                        \
+    {                                                                 \
+        LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; P = ph[ROW];   \
+        if (FWD0 == 2) BI = rowB[ROW];                                \
+    }
+    if (r < r1) B200_EIS_BWD_LOAD(r, len, sb, p, bi)
     while (r < r1) {
         const int rn = r + stride;
         uint32_t lenN = 0;
         int64_t sbN = 0;
         double pN = 0.0;
-        if (B > 0 && rn < r1) { lenN = rowLen[rn]; sbN = sliceBase[rn >> 5]; pN = ph[rn]; }
-        const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
-        const double w = eis_row_sub<B, C16, true>(E, val, t, sb + (r & 31), nLower, nTotal - nLower, p);
-        t[r] = w;
-        if (FWD0) {
-            const double yv = __dadd_rn(p, -w);
-            y[r] = yv;
-            s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(w, yv)));
+        int biN = -1;
+        if (B > 0 && rn < r1) B200_EIS_BWD_LOAD(rn, lenN, sbN, pN, biN)
+        if (FWD0 != 2 || bi < 0) {
+            const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+            const double w = eis_row_sub<B, C16, true>(E, val, t, sb + (r & 31), nLower, nTotal - nLower, p);
+            t[r] = w;
+            if (FWD0 != 0) {
+                const double yv = __dadd_rn(p, -w);
+                y[r] = yv;
+                s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(w, yv)));
+            }
         }
-        if (B == 0 && rn < r1) { lenN = rowLen[rn]; sbN = sliceBase[rn >> 5]; pN = ph[rn]; }
-        r = rn; len = lenN; sb = sbN; p = pN;
+        if (B == 0 && rn < r1) B200_EIS_BWD_LOAD(rn, lenN, sbN, pN, biN)
+        r = rn; len = lenN; sb = sbN; p = pN; bi = biN;
     }
-    if (FWD0) reduce_finish<1>(s, R);
+#undef B200_EIS_BWD_LOAD
+    if (FWD0 != 0) reduce_finish<1>(s, R);
+}
+
+// nranks > 1, halo overlapped: backward sweep of the first colour's interface rows only (bRow[0 .. nB0):
+// bRow is ascending, so the first colour's interface rows are a prefix), ahead of the bulk of the colour:
+// once they are done t is complete on every interface row and the exchange can start.
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_eis_bwd_rows(int nB0, const int* __restrict__ bRow, const int64_t* __restrict__ sliceBase,
+               const uint32_t* __restrict__ rowLen, EllCols E, const double* __restrict__ val,
+               const double* __restrict__ ph, double* t, const Scalars* S) {
+    if (S->done) return;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB0; b += gridDim.x * blockDim.x) {
+        const int r = bRow[b];
+        const uint32_t len = rowLen[r];
+        const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+        t[r] = eis_row_sub<0, C16, true>(E, val, t, sliceBase[r >> 5] + (r & 31), nLower, nTotal - nLower, ph[r]);
+    }
+}
+// ... and their forward part once the halo term hb is there: no earlier neighbours, D- == 1:
+// y = p^ - t + (B- t); their share of (p^, w^) is added to the running reduction.
+__global__ void __launch_bounds__(kBlock)
+k_eis_fwd_rows(int nB0, const int* __restrict__ bRow, const double* __restrict__ hb,
+               const double* __restrict__ ph, const double* __restrict__ t, double* __restrict__ y, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB0; b += gridDim.x * blockDim.x) {
+        const int r = bRow[b];
+        const double p = ph[r], tv = t[r];
+        const double yv = __dadd_rn(__dadd_rn(p, -tv), hb[b]);
+        y[r] = yv;
+        s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(tv, yv)));
+    }
+    reduce_finish<1>(s, R);
 }
 
 // halo term of the forward right-hand side (nranks > 1): hb[b] = (B- t)[bRow[b]] = -sum bou*t_nbr over the

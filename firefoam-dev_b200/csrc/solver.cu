@@ -124,6 +124,7 @@ struct DevPlan {
     // Eisenstat form, nranks > 1: interface-row index of every row (-1: none) and the halo term B t
     int* rowB = nullptr;
     double* hb = nullptr;
+    int nB0 = 0;                  // interface rows of the first colour: bRow[0 .. nB0) (bRow is ascending)
 };
 
 struct HostIface {
@@ -198,6 +199,7 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    bool eisOverlap = false;    // B200PCG_EIS_OVERLAP=1: nranks > 1: exchange t behind the first colour's backward sweep
     int eisCtas = 0;            // B200PCG_EIS_CTAS=3|4: force the 80- / 64-register build of both 6-entry batched
                                 // sweeps (default 0: backward 64, forward 80 registers)
     int eisBatch = 1;           // B200PCG_EIS_BATCH=0: plain entry loops in the Eisenstat sweeps (A/B switch)
@@ -754,6 +756,8 @@ int ensure_eis_buffers(b200_ctx* ctx, DevPlan& P) {
         for (int b = 0; b < P.h.nBRows; ++b) rb[(size_t)P.h.bRow[b]] = b;
         RET(upload(ctx, &P.rowB, rb));
         RET(dev_alloc(ctx, &P.hb, (size_t)P.h.nBRows));
+        P.nB0 = 0;
+        while (P.nB0 < P.h.nBRows && P.h.bRow[(size_t)P.nB0] < P.h.colourStart[1]) ++P.nB0;
         CU(cudaStreamSynchronize(ctx->sc));   // rb goes out of scope
     }
     return B200_OK;
@@ -765,8 +769,36 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
     return P.maxRowLen <= 6 ? 6 : 8;
 }
 
+// exchange of t across the processor patches on the comm stream (after everything enqueued on the compute
+// stream so far); the compute stream does NOT wait here: eis_halo_wait does
+int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
+    CU(cudaEventRecord(ctx->evPack, ctx->sc));
+    CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
+    k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, ctx->t, ctx->sendbuf, ctx->S);
+    ctx->launches++;
+    NC(g_nccl.GroupStart());
+    for (int k = 0; k < P.h.nIfaces; ++k) {
+        const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+        if (n == 0) continue;
+        NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+        NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaEventRecord(ctx->evRecv, ctx->sm));
+    return B200_OK;
+}
+// ... and the halo term hb = B- t once it has arrived
+int eis_halo_wait(b200_ctx* ctx, DevPlan& P) {
+    CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
+    LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
+           ctx->recvbuf, P.hb, ctx->S);
+    return B200_OK;
+}
+
+// fuse0: 0 = every colour gets its own forward launch; 1 = single rank: the first colour's forward sweep
+// rides in its backward sweep; 2 = nranks > 1 with the halo exchange overlapped (kernels.cuh k_eis_bwd)
 template <bool C16, int B, int CTB, int CTF>
-int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
+int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, int fuse0) {
     const int C = P.h.nColours;
     Scalars* S = ctx->S;
     const EllCols E{P.col, P.col16, P.colBase};
@@ -777,32 +809,34 @@ int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, bool fuse0) {
         const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
         const int g = grid_for(ctx, r1 - r0, perSMB);
         Reduce R = mkR(ctx, STEP_NONE);
-        if (fuse0 && k == 0) {
-            auto kb = k_eis_bwd<true, C16, B, CTB>;
-            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
+        if (k == 0 && fuse0 == 2) {
+            // the first colour's interface rows first, so that the exchange of t overlaps the bulk of the colour
+            if (P.nB0 > 0) {
+                auto kr = k_eis_bwd_rows<C16>;
+                LAUNCH(PC_EIS_BWD, kr, grid_for(ctx, P.nB0), P.nB0, P.bRow, P.sliceBase, P.rowLen, E, P.val, ctx->p,
+                       ctx->t, S);
+            }
+            RET(eis_halo_start(ctx, P));
+            auto kb = k_eis_bwd<2, C16, B, CTB>;
+            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, P.rowB, R);
+        } else if (k == 0 && fuse0 == 1) {
+            auto kb = k_eis_bwd<1, C16, B, CTB>;
+            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, P.rowB, R);
         } else {
-            auto kb = k_eis_bwd<false, C16, B, CTB>;
-            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, R);
+            auto kb = k_eis_bwd<0, C16, B, CTB>;
+            LAUNCH(PC_EIS_BWD, kb, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->p, ctx->t, ctx->w, P.rowB, R);
         }
     }
-    if (halo) {
-        // t is complete on every rank: pack + exchange on the comm stream, then the halo term B- t
-        CU(cudaEventRecord(ctx->evPack, ctx->sc));
-        CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
-        k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, ctx->t, ctx->sendbuf, S);
-        ctx->launches++;
-        NC(g_nccl.GroupStart());
-        for (int k = 0; k < P.h.nIfaces; ++k) {
-            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
-            if (n == 0) continue;
-            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
+    if (halo && fuse0 == 2) {
+        RET(eis_halo_wait(ctx, P));
+        if (P.nB0 > 0) {
+            Reduce R = mkR(ctx, STEP_NONE);
+            LAUNCH(PC_EIS_FWD, k_eis_fwd_rows, grid_for(ctx, P.nB0), P.nB0, P.bRow, P.hb, ctx->p, ctx->t, ctx->w, R);
         }
-        NC(g_nccl.GroupEnd());
-        CU(cudaEventRecord(ctx->evRecv, ctx->sm));
-        CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
-        LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
-               ctx->recvbuf, P.hb, S);
+    } else if (halo) {
+        // t is complete on every rank: pack + exchange on the comm stream, then the halo term B- t
+        RET(eis_halo_start(ctx, P));
+        RET(eis_halo_wait(ctx, P));
     }
     for (int k = fuse0 ? 1 : 0; k < C; ++k) {
         const int r0 = P.h.colourStart[k], r1 = P.h.colourStart[k + 1];
@@ -900,7 +934,9 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
     const int C = P.h.nColours;
     const int lastStart = P.h.colourStart[C - 1];
     const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
-    const bool fuse0 = !halo && C >= 2;   // first colour's forward sweep inside its backward sweep
+    // first colour's forward sweep inside its backward sweep: always on one rank; with processor patches only
+    // in the overlapped form (B200PCG_EIS_OVERLAP=1; not yet the default: validated on the GPU in round 2)
+    const int fuse0 = C < 2 ? 0 : (!halo ? 1 : (ctx->eisOverlap ? 2 : 0));
     LAUNCH(PC_EIS_P, k_eis_p, gv, N, lastStart, ctx->rD, ctx->p, ctx->t, ctx->r, S);
     const int B = eis_batch(ctx, P);
     // CTB / CTF = resident CTAs per SM the backward / forward sweep kernels are compiled for (register cap
@@ -1250,6 +1286,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
+    if (const char* e19 = getenv("B200PCG_EIS_OVERLAP")) c->eisOverlap = atoi(e19) != 0;
     if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : (atoi(e18) == 4 ? 4 : 0);
     if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
         c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));

@@ -224,23 +224,53 @@ def eis_check_interval(q):          # kernels.cuh eis_check_interval
     return 1 if q < 1.5 else (2 if q < 4.0 else (8 if q < 32.0 else 32))
 
 
-def _norm_factor(pv, diag_i, val, psi_i, src_i, halo_sumA=None):
-    """lduMatrix::solver::normFactor on the plan's row structure (one rank)."""
-    wA = pv.spmv(diag_i, val, psi_i)
+class SingleRank:
+    """Communicator of the emulations below on one rank; tests/gloo_eis_worker.py supplies the gloo twin
+    (allsum = all-reduce of one double, exchange = grouped send/recv of the patch-face values in slot order)."""
+    nGlobal = None
+
+    def allsum(self, v):
+        return float(v)
+
+    def exchange(self, send):
+        return np.empty(0)
+
+
+def _amul(pv, comm, diag_i, val, bou, x):
+    """lduMatrix::Amul on the plan's row structure: k_pack -> exchange -> k_spmv -> k_iface_fix"""
+    recv = comm.exchange(x[pv.slotRow]) if pv.slotRow.size else np.empty(0)
+    y = pv.spmv(diag_i, val, x)
+    for b in range(pv.bRow.size):
+        acc = y[pv.bRow[b]]
+        for e in range(pv.bStart[b], pv.bStart[b + 1]):
+            acc = acc - bou[pv.bSlot[e]] * recv[pv.bSlot[e]]
+        y[pv.bRow[b]] = acc
+    return y
+
+
+def _norm_factor(pv, comm, diag_i, val, bou, psi_i, src_i):
+    """lduMatrix::solver::normFactor on the plan's row structure."""
+    wA = _amul(pv, comm, diag_i, val, bou, psi_i)
     sumA = pv.spmv(diag_i, val, np.ones(pv.N))
-    xRef = psi_i.sum() / pv.N
-    nf = (np.abs(wA - sumA * xRef) + np.abs(src_i - sumA * xRef)).sum() + 1e-20
+    if pv.slotRow.size:
+        sumA = sumA - np.bincount(pv.slotRow, weights=bou, minlength=pv.N)
+    nGlobal = comm.allsum(float(pv.N))
+    xRef = comm.allsum(psi_i.sum()) / nGlobal
+    nf = comm.allsum((np.abs(wA - sumA * xRef) + np.abs(src_i - sumA * xRef)).sum()) + 1e-20
     return wA, nf
 
 
-def pcg_multicolour_reference(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, minIter=0):
-    """The three-kernel DIC-class loop (PCG.C control flow, multicolour IC0 preconditioner) on the
-    plan's row structure: what B200_PRECOND_DIC_MC computes.  Returns (psi natural, nIter, finalRes)."""
+def pcg_multicolour_reference(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+                              comm=None, bou=None):
+    """The three-kernel DIC-class loop (PCG.C control flow, rank-local multicolour IC0 preconditioner) on
+    the plan's row structure: what B200_PRECOND_DIC_MC computes.  Returns (psi natural, nIter, finalRes)."""
+    comm = comm or SingleRank()
+    bou = np.zeros(0) if bou is None else bou
     val = pv.values(upper)
     d, b, x = pv.to_internal(diag), pv.to_internal(source), pv.to_internal(psi0)
-    wA, nf = _norm_factor(pv, d, val, x, b)
+    wA, nf = _norm_factor(pv, comm, d, val, bou, x, b)
     r = b - wA
-    init = final = np.abs(r).sum() / nf
+    init = final = comm.allsum(np.abs(r).sum()) / nf
     conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
     n = 0
     if minIter > 0 or not conv():
@@ -250,13 +280,13 @@ def pcg_multicolour_reference(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.
         while True:
             rho_old = rho
             w = pv.dic_precondition(rD, val, r)
-            rho = w @ r
+            rho = comm.allsum(w @ r)
             p = w.copy() if n == 0 else w + (rho / rho_old) * p
-            w = pv.spmv(d, val, p)
-            alpha = rho / (w @ p)
+            w = _amul(pv, comm, d, val, bou, p)
+            alpha = rho / comm.allsum(w @ p)
             x = x + alpha * p
             r = r - alpha * w
-            final = np.abs(r).sum() / nf
+            final = comm.allsum(np.abs(r).sum()) / nf
             n += 1
             if not ((n - 1 < maxIter and not conv()) or n < minIter):
                 break
@@ -264,11 +294,17 @@ def pcg_multicolour_reference(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.
 
 
 def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
-                           halo=False):
+                           halo=False, comm=None, bou=None, overlap=False):
     """Kernel-by-kernel transliteration of B200_PRECOND_DIC_MC_EIS (solver.cu eis_setup /
-    enqueue_eis_iteration, kernels.cuh k_eis_* and the STEP_EIS_* scalar steps), one rank.
-    halo=True takes the multi-rank kernel selection (no first-colour fusion) with an empty halo term.
+    enqueue_eis_iteration / launch_eis_sweeps, kernels.cuh k_eis_* and the STEP_EIS_* scalar steps).
+    One rank by default; `comm` + `bou` (interface coefficients in slot order) run it across ranks.
+    halo=True takes the multi-rank kernel selection even on one rank (empty halo term);
+    overlap=True the overlapped form of it (B200PCG_EIS_OVERLAP=1: first colour's interface rows first,
+    the first colour's forward sweep fused into its backward sweep on the rows without a processor face).
     Returns (psi natural, nIter, finalRes, number of true-residual evaluations)."""
+    comm = comm or SingleRank()
+    bou = np.zeros(0) if bou is None else bou
+    halo = halo or pv.slotRow.size > 0
     N, C = pv.N, pv.nColours
     val = pv.values(upper)
     diag_i, src, psi = pv.to_internal(diag), pv.to_internal(source), pv.to_internal(psi0)
@@ -277,10 +313,11 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
              alpha=0.0, cRatio=0.0, sinceCheck=0, needCheck=0, sigma=1.0)
     conv = lambda: S["finalRes"] < tol or (relTol > 1e-20 and S["finalRes"] < relTol * S["initRes"])
     # spmv_full<INIT> + k_sum + k_norm_resid (STEP_NORM)
-    wA, nf = _norm_factor(pv, diag_i, val, psi, src)
+    wA, nf = _norm_factor(pv, comm, diag_i, val, bou, psi, src)
+    nGlobal = comm.allsum(float(N))
     rh = src - wA
     S["normFactor"] = nf
-    S["initRes"] = S["finalRes"] = np.abs(rh).sum() / nf
+    S["initRes"] = S["finalRes"] = comm.allsum(np.abs(rh).sum()) / nf
     S["converged"] = int(conv())
     S["done"] = 0 if (minIter > 0 or not S["converged"]) else 1
     # eis_setup: k_dic_calc_rd per colour -> dT
@@ -292,21 +329,30 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                 e = pv.entry(r, j)
                 d = d - (val[e] * val[e]) / dT[pv.col[e]]
             dT[r] = d
-    # k_eis_sign + STEP_EIS_SIGN
+    # k_eis_sign + STEP_EIS_SIGN (global counts)
+    neg = comm.allsum(float((dT < 0).sum()))
+    bad = comm.allsum(float((~((np.abs(dT) > 0) & (np.abs(dT) < 1.7e308))).sum()))
     if not S["done"]:
-        neg, bad = float((dT < 0).sum()), float((~((np.abs(dT) > 0) & (np.abs(dT) < 1.7e308))).sum())
-        if bad > 0 or (0 < neg < N):
+        if bad > 0 or (0 < neg < nGlobal):
             raise ValueError("DIC pivots are zero or of mixed sign")
         S["sigma"] = -1.0 if neg > 0 else 1.0
     sv = eb = xa = None
+    rowB = np.full(N, -1, dtype=np.int64)
+    rowB[pv.bRow] = np.arange(pv.bRow.size)
+    nB0 = int((pv.bRow < pv.colourStart[1]).sum()) if C >= 2 else 0
+    assert np.all(np.diff(pv.bRow) > 0)                       # ascending: the first colour's rows are a prefix
+    # k_eis_setup (gated by done on the device; the exchange of s is issued by every rank regardless)
+    sigma = S["sigma"]
+    with np.errstate(all="ignore"):
+        sv_all = 1.0 / np.sqrt(np.abs(dT))
+    recv_s = comm.exchange(sv_all[pv.slotRow]) if pv.slotRow.size else np.empty(0)
     if not S["done"]:
-        # k_eis_setup
-        sigma = S["sigma"]
-        sv = 1.0 / np.sqrt(np.abs(dT))
+        sv = sv_all
         eb = diag_i / dT - 2.0
         rh = (sigma * sv) * rh
         xa = np.zeros(N)
-        # k_eis_scale_vals (both triangles of the plan's coefficient copy)
+        # k_eis_scale_bou, k_eis_scale_vals (both triangles of the plan's coefficient copy)
+        bou = bou * (sigma * (sv[pv.slotRow] * recv_s)) if pv.slotRow.size else bou
         val = val.copy()
         for r in range(N):
             for j in range(pv.nTotal[r]):
@@ -320,13 +366,31 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                     e = pv.entry(r, j)
                     w = w - val[e] * rh[pv.col[e]]
                 rh[r] = w
-        g = (rh * rh).sum()                                 # k_eis_rho0, STEP_EIS_RHO0
+    g = comm.allsum((rh * rh).sum())                        # k_eis_rho0, STEP_EIS_RHO0
+    if not S["done"]:
         S["wArA"], S["beta"] = g, 0.0
         a = np.sqrt(abs(g))
         S["cRatio"] = S["finalRes"] / a if a > 0 else 0.0
     ph, t, y = np.zeros(N), np.zeros(N), np.zeros(N)
+    hb = np.zeros(pv.bRow.size)
     checks = 0
-    fuse0 = (not halo) and C >= 2
+    fuse0 = 0 if C < 2 else (1 if not halo else (2 if overlap else 0))
+
+    def halo_term(tvec):                                     # k_pack -> exchange -> k_eis_halo
+        recv = comm.exchange(tvec[pv.slotRow]) if pv.slotRow.size else np.empty(0)
+        for b in range(pv.bRow.size):
+            acc = 0.0
+            for e in range(pv.bStart[b], pv.bStart[b + 1]):
+                acc = acc - bou[pv.bSlot[e]] * recv[pv.bSlot[e]]
+            hb[b] = acc
+
+    def bwd_row(r):
+        w = ph[r]
+        for j in range(pv.nTotal[r] - 1, pv.nLower[r] - 1, -1):
+            e = pv.entry(r, j)
+            w = w - val[e] * t[pv.col[e]]
+        return w
+
     enq, cap = 0, max(maxIter + 1, minIter)
     while not S["done"] and enq < cap:
         enq += 1
@@ -344,18 +408,31 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
         dot = 0.0
         # k_eis_bwd, colours C-2 .. 0
         for k in range(C - 2, -1, -1):
+            if k == 0 and fuse0 == 2:
+                for b in range(nB0):                         # k_eis_bwd_rows, then the exchange starts
+                    t[pv.bRow[b]] = bwd_row(int(pv.bRow[b]))
+                t_sent = t.copy()
             for r in pv.rows_of_colour(k):
                 assert r < lastStart
-                w = ph[r]
-                for j in range(pv.nTotal[r] - 1, pv.nLower[r] - 1, -1):
-                    e = pv.entry(r, j)
-                    w = w - val[e] * t[pv.col[e]]
+                if k == 0 and fuse0 == 2 and rowB[r] >= 0:
+                    continue                                 # interface row: left alone by k_eis_bwd<2>
+                w = bwd_row(r)
                 t[r] = w
-                if fuse0 and k == 0:
+                if k == 0 and fuse0:
                     assert pv.nLower[r] == 0 and abs(eb[r] + 1.0) < 1e-12    # D- == 1 on first-colour rows
                     yv = ph[r] - w
                     y[r] = yv
                     dot += ph[r] * (w + yv)
+        if halo and fuse0 == 2:
+            assert np.array_equal(t_sent[pv.slotRow], t[pv.slotRow])          # nothing the pack reads was touched
+            halo_term(t_sent)
+            for b in range(nB0):                             # k_eis_fwd_rows
+                r = int(pv.bRow[b])
+                yv = (ph[r] - t[r]) + hb[b]
+                y[r] = yv
+                dot += ph[r] * (t[r] + yv)
+        elif halo:
+            halo_term(t)
         # k_eis_fwd
         for k in range(1 if fuse0 else 0, C):
             last = k == C - 1
@@ -364,6 +441,8 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                 tv = t[r]
                 pp = tv if last else ph[r]
                 w = pp + eb[r] * tv
+                if halo and rowB[r] >= 0:
+                    w = w + hb[rowB[r]]
                 for j in range(pv.nLower[r]):
                     e = pv.entry(r, j)
                     assert pv.col[e] < lastStart     # a gathered y is never a stored w^
@@ -372,6 +451,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                 y[r] = wh if last else w
                 dot += pp * wh
         # STEP_WAPA
+        dot = comm.allsum(dot)
         S["wApA"] = dot
         if not (abs(dot) / nf > 1e-300):
             S["singular"], S["done"], S["pendingPsi"] = 1, 1, 0
@@ -382,7 +462,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
         w = y.copy()
         w[:lastStart] = t[:lastStart] + y[:lastStart]
         rh = rh - S["alpha"] * w
-        g = (rh * rh).sum()
+        g = comm.allsum((rh * rh).sum())
         S["wArAold"], S["wArA"] = S["wArA"], g
         S["beta"] = S["wArA"] / S["wArAold"]
         old = S["nIter"]
@@ -402,7 +482,7 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
                     e = pv.entry(r, j)
                     acc = acc + val[e] * rh[pv.col[e]]
                 tot += abs(acc) / sv[r]
-            S["finalRes"] = tot / nf
+            S["finalRes"] = comm.allsum(tot) / nf
             S["converged"] = int(conv())
             cont = (S["nIter"] - 1 < maxIter and not S["converged"]) or S["nIter"] < minIter
             if not cont:

@@ -22,17 +22,22 @@ def ngpus():
         return 0
 
 
-@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (4, None), (8, None), (8, "128")])
+@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "overlap"), (4, None), (4, "overlap"), (8, None),
+                                        (8, "128"), (8, "overlap")])
 def test_multigpu_parity(world, tile):
     """tile: B200PCG_TILE for the ranks (tiled multicolour order + symmetric Amul in the DIC-class mode;
-    the default tile of 8192 rows does not engage on these small sub-meshes)."""
+    the default tile of 8192 rows does not engage on these small sub-meshes); "overlap": the Eisenstat
+    form with the halo exchange behind the first colour's backward sweep (B200PCG_EIS_OVERLAP=1)."""
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "mgpu_worker.py")]
     env = dict(os.environ)
-    if tile:
+    if tile == "overlap":
+        env["B200PCG_EIS_OVERLAP"] = "1"
+        tile = None
+    elif tile:
         env["B200PCG_TILE"] = tile
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
