@@ -1681,8 +1681,8 @@ k_eis_r(int N, int lastStart, double* __restrict__ rh, const double* __restrict_
 }
 
 // true residual of the iteration, only when the scalar step asked for it: sum |(I + L-) r^| / s
-template <bool C16>
-__global__ void __launch_bounds__(kBlock)
+template <bool C16, int B>
+__global__ void __launch_bounds__(kBlock, eis_sweep_ctas(B))
 k_eis_res(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
           const double* __restrict__ val, const double* __restrict__ sv, const double* __restrict__ rh,
           Reduce R) {
@@ -1691,11 +1691,8 @@ k_eis_res(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restri
     for (int r = blockIdx.x * kBlock + threadIdx.x; r < N; r += gridDim.x * kBlock) {
         const int64_t base = sliceBase[r >> 5] + (r & 31);
         const int nLower = (int)(rowLen[r] & 0xffffu);
-        double acc = rh[r];
-        for (int j = 0; j < nLower; ++j) {
-            const int64_t e = base + 32 * (int64_t)j;
-            acc = __dadd_rn(acc, __dmul_rn(val[e], __ldg(&rh[ell_col<C16>(E, e)])));
-        }
+        // rh + L- rh == -(-rh - L- rh): the sweeps' batched row helper (negation is exact)
+        const double acc = -eis_row_sub<B, C16, false>(E, val, rh, base, 0, nLower, -rh[r]);
         s[0] = __dadd_rn(s[0], __ddiv_rn(fabs(acc), sv[r]));
     }
     reduce_finish<1>(s, R);

@@ -965,13 +965,23 @@ int enqueue_eis_iteration(b200_ctx* ctx, DevPlan& P) {
     {
         Reduce R = mkR(ctx, STEP_EIS_RES);
         const EllCols E{P.col, P.col16, P.colBase};
+        // batched like the sweeps (one resident wave), or the plain loop at 8 CTAs per SM
+        const int gr = grid_for(ctx, N, B == 0 ? 8 : eis_sweep_ctas(B));
+#define B200_ERES(C16_, B_)                                                                                \
+    do {                                                                                                   \
+        auto kr = k_eis_res<C16_, B_>;                                                                     \
+        LAUNCH(PC_EIS_RES, kr, gr, N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);                \
+    } while (0)
         if (P.c16) {
-            auto kr = k_eis_res<true>;
-            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+            if (B == 0) B200_ERES(true, 0);
+            else if (B == 6) B200_ERES(true, 6);
+            else B200_ERES(true, 8);
         } else {
-            auto kr = k_eis_res<false>;
-            LAUNCH(PC_EIS_RES, kr, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val, ctx->dT, ctx->r, R);
+            if (B == 0) B200_ERES(false, 0);
+            else if (B == 6) B200_ERES(false, 6);
+            else B200_ERES(false, 8);
         }
+#undef B200_ERES
         RET(reduce_post(ctx, STEP_EIS_RES));
     }
     return B200_OK;
