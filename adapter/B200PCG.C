@@ -4,6 +4,7 @@
 \*---------------------------------------------------------------------------*/
 
 #include "B200PCG.H"
+#include "B200Context.H"
 #include "processorLduInterface.H"
 #include "processorLduInterfaceField.H"
 #include "Pstream.H"
@@ -31,20 +32,15 @@ namespace Foam
 }
 
 
-// * * * * * * * * * * * * * * * Local Functions * * * * * * * * * * * * * * //
-
-namespace
-{
+// * * * * * * * * * * * * * * * Shared Functions * * * * * * * * * * * * * * //
 
 //- One library context per MPI rank, created on first use.
 //  rank r drives GPU (r mod deviceCount); the NCCL unique id is made on the
 //  master and scattered with OpenFOAM's own Pstream.
-b200_ctx* context()
+b200_ctx* Foam::b200Context()
 {
     static b200_ctx* ctx = nullptr;
     if (ctx) return ctx;
-
-    using namespace Foam;
 
     const int nDev = b200_device_count();
     if (nDev < 1)
@@ -90,7 +86,69 @@ b200_ctx* context()
     return ctx;
 }
 
-} // End anonymous namespace
+
+void Foam::b200SetAddressing
+(
+    b200_ctx* ctx,
+    const lduAddressing& addr,
+    const lduInterfacePtrsList& interfaces,
+    labelList& coupledPatches
+)
+{
+    // --- coupled (processor) interfaces; the UPtrList has null slots for
+    //     non-coupled patches
+    DynamicList<b200_iface> ifaces(interfaces.size());
+    DynamicList<label> patches(interfaces.size());
+
+    forAll(interfaces, patchi)
+    {
+        if (!interfaces.set(patchi)) continue;
+
+        if (!isA<processorLduInterface>(interfaces[patchi]))
+        {
+            FatalErrorInFunction
+                << "B200PCG: unsupported coupled interface "
+                << interfaces[patchi].type() << " on patch " << patchi
+                << " (only processor interfaces are supported)"
+                << exit(FatalError);
+        }
+
+        const processorLduInterface& pi =
+            refCast<const processorLduInterface>(interfaces[patchi]);
+
+        const labelUList& faceCells = addr.patchAddr(patchi);
+
+        b200_iface itf;
+        itf.nbrRank = pi.neighbProcNo();
+        itf.nFaces = faceCells.size();
+        itf.faceCells = faceCells.begin();
+        itf.tag = pi.tag();
+        ifaces.append(itf);
+        patches.append(patchi);
+    }
+
+    // idempotent per mesh: keyed by the address of the lduAddressing object
+    if
+    (
+        b200_set_addressing
+        (
+            ctx,
+            uint64_t(uintptr_t(&addr)),
+            addr.size(),
+            addr.lowerAddr().size(),
+            addr.lowerAddr().begin(),
+            addr.upperAddr().begin(),
+            ifaces.size(),
+            ifaces.begin()
+        ) != B200_OK
+    )
+    {
+        FatalErrorInFunction
+            << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    coupledPatches.transfer(patches);
+}
 
 
 // * * * * * * * * * * * * * * * * Constructors  * * * * * * * * * * * * * * //
@@ -173,62 +231,50 @@ Foam::solverPerformance Foam::B200PCG::solve
             << "B200PCG: matrix is not symmetric" << exit(FatalError);
     }
 
-    // --- coupled (processor) interfaces; the UPtrList has null slots for
-    //     non-coupled patches
+    // --- mesh addressing + coupled (processor) interfaces (idempotent per mesh)
     const lduAddressing& addr = matrix_.lduAddr();
-    DynamicList<b200_iface> ifaces(interfaces_.size());
-    DynamicList<const double*> bou(interfaces_.size());
 
+    lduInterfacePtrsList lduInterfaces(interfaces_.size());
     forAll(interfaces_, patchi)
     {
-        if (!interfaces_.set(patchi)) continue;
-
-        if (!isA<processorLduInterfaceField>(interfaces_[patchi]))
+        if (interfaces_.set(patchi))
         {
-            FatalErrorInFunction
-                << "B200PCG: unsupported coupled interface "
-                << interfaces_[patchi].type() << " on patch " << patchi
-                << " (only processor interfaces are supported)"
-                << exit(FatalError);
+            if (!isA<processorLduInterfaceField>(interfaces_[patchi]))
+            {
+                FatalErrorInFunction
+                    << "B200PCG: unsupported coupled interface "
+                    << interfaces_[patchi].type() << " on patch " << patchi
+                    << " (only processor interfaces are supported)"
+                    << exit(FatalError);
+            }
+            lduInterfaces.set(patchi, &interfaces_[patchi].interface());
         }
+    }
 
+    b200_ctx* ctx = b200Context();
+    labelList coupledPatches;
+    b200SetAddressing(ctx, addr, lduInterfaces, coupledPatches);
+
+    DynamicList<const double*> bou(coupledPatches.size());
+    forAll(coupledPatches, i)
+    {
+        bou.append(interfaceBouCoeffs_[coupledPatches[i]].begin());
+    }
+
+    // the dump (below) wants the interface list once more
+    DynamicList<b200_iface> ifaces(coupledPatches.size());
+    forAll(coupledPatches, i)
+    {
+        const label patchi = coupledPatches[i];
         const processorLduInterface& pi =
-            refCast<const processorLduInterface>
-            (
-                interfaces_[patchi].interface()
-            );
-
+            refCast<const processorLduInterface>(lduInterfaces[patchi]);
         const labelUList& faceCells = addr.patchAddr(patchi);
-
         b200_iface itf;
         itf.nbrRank = pi.neighbProcNo();
         itf.nFaces = faceCells.size();
         itf.faceCells = faceCells.begin();
         itf.tag = pi.tag();
         ifaces.append(itf);
-        bou.append(interfaceBouCoeffs_[patchi].begin());
-    }
-
-    b200_ctx* ctx = context();
-
-    // idempotent per mesh: keyed by the address of the lduAddressing object
-    if
-    (
-        b200_set_addressing
-        (
-            ctx,
-            uint64_t(uintptr_t(&addr)),
-            addr.size(),
-            addr.lowerAddr().size(),
-            addr.lowerAddr().begin(),
-            addr.upperAddr().begin(),
-            ifaces.size(),
-            ifaces.begin()
-        ) != B200_OK
-    )
-    {
-        FatalErrorInFunction
-            << "B200PCG: " << b200_last_error(ctx) << exit(FatalError);
     }
 
     // --- B200PCG_DUMP=<dir>: keep the initial guess so that the system can be written out after the
