@@ -79,3 +79,43 @@ def test_eisenstat_negative_definite_system():
     xr, nr, fr = pcg_multicolour_reference(pv, m.diag, m.upper, src, x0, tol=case.TOL, relTol=case.RELTOL)
     assert nr <= ne <= nr + 2
     assert np.linalg.norm(xe - xr) / np.linalg.norm(xr) < 1e-6
+
+
+@pytest.mark.parametrize("name,s,renumber", [("hex", mg.hex_block(12, 10, 8), 0), ("hex-odd", mg.hex_block(7, 5, 3), 0),
+                                             ("random", random_ldu(1201, 6.0, seed=7), 0),
+                                             ("poly", mg.bcc_poly(5, 4, 3, shuffle_block=64), 0),
+                                             ("poly-rcm", mg.bcc_poly(5, 4, 3, shuffle_block=64), 1),
+                                             ("hex-2ranks", mg.hex_block(8, 6, 4, 2, 1, 1, 1), 0)])
+def test_plan_invariants_the_eisenstat_kernels_rely_on(name, s, renumber):
+    """Structure of the colour-major plan (csrc/plan.cpp) that k_eis_* take for granted."""
+    pv = PlanView(MULTICOLOUR, s.addr, renumber=renumber)
+    C, N = pv.nColours, pv.N
+    assert pv.nTiles == 1
+    cs = pv.colourStart
+    assert cs[0] == 0 and cs[C] == N and np.all(np.diff(cs) > 0)
+    lastStart = int(cs[C - 1])
+    colour = np.searchsorted(cs, np.arange(N), side="right") - 1
+    for r in range(N):
+        nL, nT = int(pv.nLower[r]), int(pv.nTotal[r])
+        cols = np.array([pv.col[pv.entry(r, j)] for j in range(nT)], dtype=np.int64)
+        # [earlier colours | later colours], never the same colour
+        assert np.all(colour[cols[:nL]] < colour[r]) and np.all(colour[cols[nL:]] > colour[r])
+        if colour[r] == 0:
+            assert nL == 0                    # first colour: forward sweep needs no gather, D~ == D
+        if r >= lastStart:
+            assert nT == nL                   # last colour: t == p^, no backward sweep
+        assert np.all(cols[:nL] < lastStart)  # a forward sweep never gathers a stored w^
+    # interface rows: ascending, so the first colour's interface rows are a prefix of bRow
+    assert np.all(np.diff(pv.bRow) > 0)
+    if pv.bRow.size:
+        assert pv.bStart[0] == 0 and pv.bStart[-1] == pv.slotRow.size
+        assert sorted(pv.bSlot.tolist()) == list(range(pv.slotRow.size))
+        for b in range(pv.bRow.size):
+            assert np.all(pv.slotRow[pv.bSlot[pv.bStart[b]:pv.bStart[b + 1]]] == pv.bRow[b])
+
+
+def test_check_interval_policy():
+    from helpers import eis_check_interval
+    assert [eis_check_interval(q) for q in (0.0, 1.49, 1.5, 3.9, 4.0, 31.0, 32.0, 1e30, float("inf"))] == \
+        [1, 1, 2, 2, 8, 8, 32, 32, 32]
+    assert eis_check_interval(float("nan")) == 32      # thr == 0 and rho == 0: fall back to the longest interval
