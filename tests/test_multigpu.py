@@ -30,6 +30,10 @@ def test_multigpu_parity(world, tile):
     form with the halo exchange behind the first colour's backward sweep (B200PCG_EIS_OVERLAP=1)."""
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    if tile == "overlap" and not os.environ.get("B200_TEST_UNVALIDATED"):
+        # CPU-checked across two gloo ranks (test_multirank_gloo.py), never run on GPUs yet: opt-in until its
+        # first green GPU run (tools/gpu_round2_first.sh sets the variable)
+        pytest.skip("overlapped Eisenstat halo sequence: first GPU run pending (B200_TEST_UNVALIDATED=1 runs it)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "mgpu_worker.py")]
