@@ -48,7 +48,8 @@ class GlooComm:
 
 
 def systems():
-    yield "hex", mg.hex_block(8, 6, 4, 2, 1, 1, rank)
+    procs = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    yield "hex", mg.hex_block(8, 6, 4, *procs, rank)
     poly = mg.bcc_poly(4, 3, 3, shuffle_block=64)
     c2p = mg.partition_rcb(poly.xyz, world)
     yield "poly", mg.decompose(poly, c2p, world)[rank]

@@ -30,19 +30,25 @@ def test_two_rank_gloo_matches_oracle():
         np.testing.assert_allclose(np.array(res["psi"][k]), ref[k], rtol=1e-11, atol=1e-14)
 
 
-def test_two_rank_eisenstat_gloo():
-    """Eisenstat form of the DIC-class loop on 2 ranks (numpy kernels, gloo): plain and overlapped halo
-    sequence against the three-kernel multicolour loop on the same ranks and the 2-rank oracle."""
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_eisenstat_gloo(world):
+    """Eisenstat form of the DIC-class loop on 2 and 4 ranks (numpy kernels, gloo): plain and overlapped halo
+    sequence against the three-kernel multicolour loop on the same ranks and the N-rank oracle.  4 ranks:
+    several neighbours per rank, cells with processor faces towards different ranks."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29633",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29633 + world),
            os.path.join(ROOT, "tests", "gloo_eis_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("GLOO_EIS_RESULT ")][-1][16:])
     poly = mg.bcc_poly(4, 3, 3, shuffle_block=64)
-    cases = {"hex": [mg.hex_block(8, 6, 4, 2, 1, 1, k) for k in range(2)],
-             "poly": mg.decompose(poly, mg.partition_rcb(poly.xyz, 2), 2)}
+    procs = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    cases = {"hex": [mg.hex_block(8, 6, 4, *procs, k) for k in range(world)],
+             "poly": mg.decompose(poly, mg.partition_rcb(poly.xyz, world), world)}
     for name, subs in cases.items():
         d = res[name]
         nr, ne, no = d["iters"]
@@ -51,7 +57,7 @@ def test_two_rank_eisenstat_gloo():
         assert all(c >= 2 for c in d["colours"]) and all(n > 0 for n in d["ifaceRows"])
         ref = [np.zeros(s.addr.nCells) for s in subs]
         orc.pcg_solve(subs, ref, "DIC", 1e-11, 0.0, 1000)
-        for k in range(2):
+        for k in range(world):
             xr, xe, xo = (np.array(d[key][k]) for key in ("ref", "eis", "ovl"))
             assert np.linalg.norm(xe - xr) / np.linalg.norm(xr) < 1e-8
             # the overlapped sequence performs the same row operations; only the order in which the
