@@ -199,6 +199,7 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    bool dicDefaultEis = false; // B200PCG_DIC=eisenstat: code 2 (`preconditioner DIC`) runs in the Eisenstat form too
     bool eisOverlap = false;    // B200PCG_EIS_OVERLAP=1: nranks > 1: exchange t behind the first colour's backward sweep
     int eisCtas = 0;            // B200PCG_EIS_CTAS=3|4: force the 80- / 64-register build of both 6-entry batched
                                 // sweeps (default 0: backward 64, forward 80 registers)
@@ -1035,7 +1036,10 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     if (ctl->precond < 0 || ctl->precond > 4) return fail(ctx, B200_EINVAL, "bad preconditioner code");
     // Eisenstat form of the DIC-class loop: same preconditioner as B200_PRECOND_DIC_MC.  Systems small enough
     // for the single-launch cluster kernels are latency-bound, not bandwidth-bound: they take that path
-    const bool eis = (ctl->precond == B200_PRECOND_DIC_MC_EIS);
+    // B200PCG_DIC=eisenstat: `preconditioner DIC` without a dicMode takes the Eisenstat form as well (the switch
+    // that becomes the default once the form has run on 4 and 8 GPUs); tiled plans keep the three-kernel loop
+    bool eis = (ctl->precond == B200_PRECOND_DIC_MC_EIS);
+    if (ctl->precond == B200_PRECOND_DIC_MC && ctx->dicDefaultEis && ctx->tileRows == 0) eis = true;
     const int32_t smallPrecond = eis ? (int32_t)B200_PRECOND_DIC_MC : ctl->precond;
     if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_controls.reserved must be 0");
     DevPlan* Pp = nullptr;
@@ -1297,6 +1301,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
     if (const char* e19 = getenv("B200PCG_EIS_OVERLAP")) c->eisOverlap = atoi(e19) != 0;
+    if (const char* e20 = getenv("B200PCG_DIC")) c->dicDefaultEis = (std::string(e20) == "eisenstat");
     if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : (atoi(e18) == 4 ? 4 : 0);
     if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
         c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));

@@ -4,6 +4,8 @@ triangular sweeps also deliver A*p (no separate Amul) and the true residual is e
 Bars: solution within 1e-8 relative L2 of the oracle's DIC solve at the same tolerance (the DIC-class bar
 of BASELINE.json), same iteration count as the three-kernel DIC-class loop up to a skipped early dip
 below the threshold (<= +2), the reported final residual is the true residual of the returned solution."""
+import os
+
 import numpy as np
 import pytest
 
@@ -132,5 +134,30 @@ def test_eisenstat_rejects_tiled_plan():
         with pytest.raises(Exception) as ei:
             solve_mode(c, s, "eisenstat")
         assert "colour-major" in str(ei.value)
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
+                    reason="B200PCG_DIC=eisenstat (host-side selection only) has not run on a GPU yet")
+def test_dic_keyword_can_default_to_the_eisenstat_form():
+    """B200PCG_DIC=eisenstat: plain `preconditioner DIC` takes the Eisenstat form (tiled plans keep the
+    three-kernel loop)."""
+    s = mg.hex_block(64, 40, 33)
+    c = _ctx_with_env({"B200PCG_DIC": "eisenstat", "B200PCG_SMALL_N": "0"})
+    try:
+        c.profile(True)
+        xm, pm = solve_mode(c, s, "multicolour", tol=1e-9)
+        prof = c.profile_json()
+        assert "eis_fwd_dot" in prof and "spmv_dot" not in prof
+        xe, pe = solve_mode(c, s, "eisenstat", tol=1e-9)
+        assert pm.nIterations == pe.nIterations and np.array_equal(xm, xe)
+    finally:
+        c.close()
+    c = _ctx_with_env({"B200PCG_DIC": "eisenstat", "B200PCG_SMALL_N": "0", "B200PCG_TILE": "64"})
+    try:
+        c.profile(True)
+        xt, pt = solve_mode(c, s, "multicolour", tol=1e-9)
+        assert "spmv_dot" in c.profile_json() and pt.converged
     finally:
         c.close()
