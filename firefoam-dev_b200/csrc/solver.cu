@@ -16,6 +16,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <omp.h>
 
 #include <algorithm>
 #include <cstddef>
@@ -170,6 +171,10 @@ struct b200_ctx {
     PeerBuf* peerLocal = nullptr;
     std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)
     PeerBuf** d_peers = nullptr;
+    // staged copies of pageable caller memory (B200PCG_STAGED_COPY=1): two page-locked pieces + their DMA events
+    bool stagedCopy = false;
+    void* stageBuf[2] = {nullptr, nullptr};
+    cudaEvent_t stageEv[2] = {nullptr, nullptr};
     Scalars* S = nullptr;
     Scalars* hS = nullptr;  // pinned
     double* partials = nullptr;
@@ -1184,6 +1189,85 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     return finish_solve(ctx, P, perf);
 }
 
+// ---- staged host <-> device copies for pageable caller memory ----------------------------------
+// OpenFOAM's fields live in pageable memory: a plain cudaMemcpyAsync of them runs at ~12 GB/s host->device
+// and ~5 GB/s device->host (measured through the host entry point with numpy arrays: 62 ms + 26 ms for the
+// 766 MB + 128 MB of a 16 M-cell solve, profiles/r01_v12_perf_dic_eisenstat_final.log -- a fifth of the
+// solve itself), against ~55 GB/s from page-locked memory.  Staged form (opt-in, B200PCG_STAGED_COPY=1; not
+// yet run on a GPU): a few OpenMP threads copy 16 MB pieces into / out of two page-locked buffers while the
+// DMA engine moves the previous piece.  Page-locked caller memory (bench.py e2e) always takes the direct copy.
+constexpr size_t kStageBytes = (size_t)16 << 20;
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+void par_memcpy(void* dst, const void* src, size_t n) {
+    const int nt = std::max(1, std::min(8, omp_get_max_threads()));
+    size_t piece = (n + (size_t)nt - 1) / (size_t)nt;
+    piece = (piece + 4095) & ~(size_t)4095;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; ++t) {
+        const size_t off = (size_t)t * piece;
+        if (off < n) std::memcpy((char*)dst + off, (const char*)src + off, std::min(piece, n - off));
+    }
+}
+
+int ensure_stage(b200_ctx* ctx) {
+    for (int b = 0; b < 2; ++b) {
+        if (!ctx->stageBuf[b]) CU(cudaHostAlloc(&ctx->stageBuf[b], kStageBytes, cudaHostAllocDefault));
+        if (!ctx->stageEv[b]) CU(cudaEventCreateWithFlags(&ctx->stageEv[b], cudaEventDisableTiming));
+    }
+    return B200_OK;
+}
+
+int h2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx->stagedCopy || bytes < ((size_t)4 << 20) || !is_pageable(src)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->sc));
+        return B200_OK;
+    }
+    RET(ensure_stage(ctx));
+    size_t i = 0;
+    for (size_t off = 0; off < bytes; off += kStageBytes, ++i) {
+        const int b = (int)(i & 1);
+        const size_t n = std::min(kStageBytes, bytes - off);
+        CU(cudaEventSynchronize(ctx->stageEv[b]));   // the DMA that last read this piece is done
+        par_memcpy(ctx->stageBuf[b], (const char*)src + off, n);
+        CU(cudaMemcpyAsync((char*)dst + off, ctx->stageBuf[b], n, cudaMemcpyHostToDevice, ctx->sc));
+        CU(cudaEventRecord(ctx->stageEv[b], ctx->sc));
+    }
+    return B200_OK;
+}
+
+int d2h(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx->stagedCopy || bytes < ((size_t)4 << 20) || !is_pageable(dst)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->sc));
+        return B200_OK;
+    }
+    RET(ensure_stage(ctx));
+    const size_t nPieces = (bytes + kStageBytes - 1) / kStageBytes;
+    for (size_t i = 0; i <= nPieces; ++i) {
+        if (i < nPieces) {   // DMA of piece i (its buffer was drained one step ago) ...
+            const int b = (int)(i & 1);
+            const size_t off = i * kStageBytes, n = std::min(kStageBytes, bytes - off);
+            CU(cudaMemcpyAsync(ctx->stageBuf[b], (const char*)src + off, n, cudaMemcpyDeviceToHost, ctx->sc));
+            CU(cudaEventRecord(ctx->stageEv[b], ctx->sc));
+        }
+        if (i >= 1) {        // ... overlaps the copy-out of piece i - 1
+            const int b = (int)((i - 1) & 1);
+            const size_t off = (i - 1) * kStageBytes, n = std::min(kStageBytes, bytes - off);
+            CU(cudaEventSynchronize(ctx->stageEv[b]));
+            par_memcpy((char*)dst + off, ctx->stageBuf[b], n);
+        }
+    }
+    return B200_OK;
+}
+
 // Map every rank's PeerBuf into this process (CUDA IPC; handles exchanged with ncclAllGather).
 bool setup_peer_reduce(b200_ctx* c, std::string& why) {
     const int n = c->nranks;
@@ -1300,6 +1384,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
+    if (const char* e21 = getenv("B200PCG_STAGED_COPY")) c->stagedCopy = atoi(e21) != 0;
     if (const char* e19 = getenv("B200PCG_EIS_OVERLAP")) c->eisOverlap = atoi(e19) != 0;
     if (const char* e20 = getenv("B200PCG_DIC")) c->dicDefaultEis = (std::string(e20) == "eisenstat");
     if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : (atoi(e18) == 4 ? 4 : 0);
@@ -1368,6 +1453,10 @@ void b200_ctx_destroy(b200_ctx* c) {
     dev_free(c->S);
     dev_free(c->partials);
     if (c->hS) cudaFreeHost(c->hS);
+    for (int b = 0; b < 2; ++b) {
+        if (c->stageBuf[b]) cudaFreeHost(c->stageBuf[b]);
+        if (c->stageEv[b]) cudaEventDestroy(c->stageEv[b]);
+    }
     if (c->evPack) cudaEventDestroy(c->evPack);
     if (c->evRecv) cudaEventDestroy(c->evRecv);
     for (auto ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -1614,16 +1703,16 @@ int b200_solve(b200_ctx* ctx, const double* diag, const double* upper, const dou
     RET(ensure_staging(ctx, false));
     const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
     CU(cudaEventRecord(ctx->ev[3], ctx->sc));
-    CU(cudaMemcpyAsync(ctx->in_upper, upper, fb, cudaMemcpyHostToDevice, ctx->sc));
-    CU(cudaMemcpyAsync(ctx->in_diag, diag, nb, cudaMemcpyHostToDevice, ctx->sc));
-    CU(cudaMemcpyAsync(ctx->in_src, source, nb, cudaMemcpyHostToDevice, ctx->sc));
-    CU(cudaMemcpyAsync(ctx->in_psi, psi, nb, cudaMemcpyHostToDevice, ctx->sc));
+    RET(h2d(ctx, ctx->in_upper, upper, fb));
+    RET(h2d(ctx, ctx->in_diag, diag, nb));
+    RET(h2d(ctx, ctx->in_src, source, nb));
+    RET(h2d(ctx, ctx->in_psi, psi, nb));
     RET(copy_bou(ctx, ctx->plans[0], bou, cudaMemcpyHostToDevice, ctx->bou));
     CU(cudaEventRecord(ctx->ev[4], ctx->sc));
     int rc = solve_core(ctx, ctx->in_diag, ctx->in_upper, ctx->in_src, ctx->in_psi, ctl, perf);
     if (rc != B200_OK && rc != B200_ENONFINITE) return rc;
     CU(cudaEventRecord(ctx->ev[5], ctx->sc));
-    CU(cudaMemcpyAsync(psi, ctx->in_psi, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    RET(d2h(ctx, psi, ctx->in_psi, nb));
     CU(cudaEventRecord(ctx->ev[0], ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
     if (perf) {

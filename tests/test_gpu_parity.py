@@ -487,3 +487,24 @@ def test_16bit_ell_columns_change_nothing():
     finally:
         c16.close()
         c32.close()
+
+
+@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
+                    reason="B200PCG_STAGED_COPY=1 (opt-in host-side copy pipeline) has not run on a GPU yet")
+def test_staged_copies_of_pageable_memory_change_nothing():
+    """B200PCG_STAGED_COPY=1: pageable caller arrays travel through two page-locked 16 MB pieces (OpenMP copy
+    overlapped with the DMA); several pieces per array, a last partial piece, identical results."""
+    s = mg.hex_block(128, 96, 90)          # 1.1 M cells: upper is 26 MB (2 pieces), the vectors 8.8 MB (1 partial)
+    base = {"B200PCG_SMALL_N": "0"}
+    c0, c1 = _ctx_with_env(dict(base, B200PCG_STAGED_COPY="0")), _ctx_with_env(dict(base, B200PCG_STAGED_COPY="1"))
+    try:
+        x0, p0 = solve_gpu(c0, s, "diagonal", maxIter=5000)
+        x1, p1 = solve_gpu(c1, s, "diagonal", maxIter=5000)
+        assert p0.nIterations == p1.nIterations and np.array_equal(x0, x1)
+        psi0 = np.random.default_rng(4).standard_normal(s.addr.nCells)     # the initial guess travels too
+        x0, p0 = solve_gpu(c0, s, "diagonal", maxIter=20, psi0=psi0)
+        x1, p1 = solve_gpu(c1, s, "diagonal", maxIter=20, psi0=psi0)
+        assert np.array_equal(x0, x1)
+    finally:
+        c0.close()
+        c1.close()

@@ -14,6 +14,8 @@ if [ "$N" = "1" ]; then
         > gpurun_out/r2_bench_poly5m_$pre.json 2>> gpurun_out/r2_bench.err; echo "poly $pre exit $?"
   done
   cat gpurun_out/r2_perf_hex_*.log
+  # pageable caller memory: plain vs staged copies (h2d= / d2h= columns of quick_perf)
+  for st in 0 1; do B200PCG_STAGED_COPY=$st timeout 100 python tools/quick_perf.py 256 250 250 diagonal 50 noconv 2>&1 | grep rep2; done
 else
   # multi-GPU parity incl. the overlapped Eisenstat halo sequence, then config 4 (128 M hex at 8) both ways
   B200_TEST_UNVALIDATED=1 timeout 500 python -m pytest tests/test_multigpu.py -x -q > gpurun_out/r2_pytest_mgpu_$N.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/r2_pytest_mgpu_$N.log
