@@ -197,7 +197,8 @@ int32_t colour_levels(int32_t N, int32_t F, const int32_t* l, const int32_t* u,
 }  // namespace
 
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
-                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P, Renumber renumber, int32_t tileRows) {
+                       int32_t nIfaces, const IfaceIn* ifaces, HostPlan& P, Renumber renumber, int32_t tileRows,
+                       bool sortColumns) {
     if (N < 0 || F < 0 || nIfaces < 0) return "negative size";
     if (F > 0 && (!l || !u)) return "null lowerAddr/upperAddr";
     if (nIfaces > 0 && !ifaces) return "null interface list";
@@ -334,6 +335,13 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             ent.clear();
             for (int64_t e = e0; e < e1; ++e) ent.emplace_back(cf.face[e], rowOf(cf.other[e]));
             if (!ident) std::sort(ent.begin(), ent.end());
+            // DIC-class sweeps reproduce no OpenFOAM summation order: by column, so that the j-th gathers of
+            // neighbouring rows are neighbours in memory (plan.hpp sortColumns)
+            if (sortColumns && ordering == Ordering::MultiColour)
+                std::sort(ent.begin(), ent.end(), [](const std::pair<int32_t, int32_t>& a,
+                                                     const std::pair<int32_t, int32_t>& b) {
+                    return a.second != b.second ? a.second < b.second : a.first < b.first;
+                });
             // A renumbered Natural plan serves Amul / sumA / negSumDiag only: keep the whole row in
             // ascending face order (OpenFOAM's visiting order) -- no [earlier | later] grouping,
             // which would change the order of the row sum.

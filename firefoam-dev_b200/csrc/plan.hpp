@@ -121,8 +121,13 @@ struct HostPlan {
 
 // Validates the LDU addressing (sizes, l<u, upper-triangular order) and builds the plan.
 // Returns empty string on success, else an error message.
+// sortColumns (MultiColour only): order the entries of each [earlier | later] group by COLUMN instead of by
+// natural face index.  A DIC-class sweep has no OpenFOAM summation order to reproduce, and on a renumbered
+// (RCM) mesh the face order of a row is unrelated to the positions of its neighbours: the j-th gathers of
+// the 32 rows of a warp then scatter over 21-23 sectors per request; sorted by column they fall next to each
+// other (11 sectors on the polyhedral workload -- tools/experiments/gather_sectors.py).
 std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l, const int32_t* u,
                        int32_t nIfaces, const IfaceIn* ifaces, HostPlan& out,
-                       Renumber renumber = Renumber::Off, int32_t tileRows = 0);
+                       Renumber renumber = Renumber::Off, int32_t tileRows = 0, bool sortColumns = false);
 
 }  // namespace b200

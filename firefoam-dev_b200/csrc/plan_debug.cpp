@@ -3,6 +3,7 @@
 // without a GPU.  Not part of the OpenFOAM-facing contract (not declared in include/b200pcg.h).
 #include "plan.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -34,8 +35,9 @@ void* b200_debug_plan_build(int ordering, int32_t N, int32_t F, const int32_t* l
 void* b200_debug_plan_build2(int ordering, int renumber, int32_t N, int32_t F, const int32_t* l,
                              const int32_t* u, int32_t nIfaces, const b200_dbg_iface* ifaces, int32_t tileRows) {
     auto* P = new HostPlan();
+    const char* sc = std::getenv("B200PCG_SORT_COLS");   // same switch as the context (solver.cu)
     g_err = build_plan((Ordering)ordering, N, F, l, u, nIfaces, (const IfaceIn*)ifaces, *P, (Renumber)renumber,
-                       tileRows);
+                       tileRows, sc && std::atoi(sc) != 0);
     if (!g_err.empty()) {
         delete P;
         return nullptr;

@@ -204,6 +204,7 @@ struct b200_ctx {
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
+    bool sortCols = false;      // B200PCG_SORT_COLS=1: multicolour plans order a row's entries by column (plan.hpp)
     bool dicDefaultEis = false; // B200PCG_DIC=eisenstat: code 2 (`preconditioner DIC`) runs in the Eisenstat form too
     bool eisOverlap = false;    // B200PCG_EIS_OVERLAP=1: nranks > 1: exchange t behind the first colour's backward sweep
     int eisCtas = 0;            // B200PCG_EIS_CTAS=3|4: force the 80- / 64-register build of both 6-entry batched
@@ -357,7 +358,7 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     const int32_t tile = (ord == Ordering::MultiColour && ctx->tileRows > 0 &&
                           ctx->N > std::max(ctx->nranks == 1 ? ctx->smallN : 0, 4 * ctx->tileRows)) ? ctx->tileRows : 0;
     std::string e = build_plan(ord, ctx->N, ctx->F, ctx->hl.data(), ctx->hu.data(),
-                               (int32_t)ifs.size(), ifs.data(), P.h, (Renumber)ctx->renumber, tile);
+                               (int32_t)ifs.size(), ifs.data(), P.h, (Renumber)ctx->renumber, tile, ctx->sortCols);
     if (!e.empty()) return fail(ctx, B200_EINVAL, "set_addressing: " + e);
     RET(upload(ctx, &P.sliceBase, P.h.sliceBase));
     RET(upload(ctx, &P.rowLen, P.h.rowLen));
@@ -1384,6 +1385,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;
+    if (const char* e22 = getenv("B200PCG_SORT_COLS")) c->sortCols = atoi(e22) != 0;
     if (const char* e21 = getenv("B200PCG_STAGED_COPY")) c->stagedCopy = atoi(e21) != 0;
     if (const char* e19 = getenv("B200PCG_EIS_OVERLAP")) c->eisOverlap = atoi(e19) != 0;
     if (const char* e20 = getenv("B200PCG_DIC")) c->dicDefaultEis = (std::string(e20) == "eisenstat");

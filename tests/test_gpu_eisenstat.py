@@ -161,3 +161,22 @@ def test_dic_keyword_can_default_to_the_eisenstat_form():
         assert "spmv_dot" in c.profile_json() and pt.converged
     finally:
         c.close()
+
+
+@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
+                    reason="B200PCG_SORT_COLS=1 (host-side entry order of the multicolour plan) has not run on a GPU yet")
+@pytest.mark.parametrize("mode", ["multicolour", "eisenstat"])
+def test_column_sorted_multicolour_plan(mode):
+    """B200PCG_SORT_COLS=1: entries of the multicolour plan ordered by column (coalesced gathers on renumbered
+    meshes).  Same preconditioner, different summation order inside a row: same solution, iterations +-2."""
+    base = {"B200PCG_SMALL_N": "0", "B200PCG_RENUMBER": "1"}
+    c0, c1 = _ctx_with_env(dict(base, B200PCG_SORT_COLS="0")), _ctx_with_env(dict(base, B200PCG_SORT_COLS="1"))
+    try:
+        for s in (mg.bcc_poly(12, 12, 16), random_ldu(20011, 6.0, seed=3), mg.hex_block(37, 23, 11)):
+            x0, p0 = solve_mode(c0, s, mode, tol=1e-11)
+            x1, p1 = solve_mode(c1, s, mode, tol=1e-11)
+            assert p0.converged and p1.converged and abs(p0.nIterations - p1.nIterations) <= 2
+            assert np.linalg.norm(x1 - x0) / np.linalg.norm(x0) < 1e-8
+    finally:
+        c0.close()
+        c1.close()

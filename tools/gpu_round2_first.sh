@@ -13,6 +13,8 @@ if [ "$N" = "1" ]; then
     timeout 300 python bench.py --workload poly --poly 125 125 160 --precond $pre --steps 2 --warmup 3 --no-cpu-baseline \
         > gpurun_out/r2_bench_poly5m_$pre.json 2>> gpurun_out/r2_bench.err; echo "poly $pre exit $?"
   done
+  B200PCG_SORT_COLS=1 timeout 300 python bench.py --workload poly --poly 125 125 160 --precond DIC-eisenstat --steps 2 --warmup 3 \
+      --no-cpu-baseline > gpurun_out/r2_bench_poly5m_DIC-eisenstat_sortcols.json 2>> gpurun_out/r2_bench.err; echo "poly sortcols exit $?"
   cat gpurun_out/r2_perf_hex_*.log
   # pageable caller memory: plain vs staged copies (h2d= / d2h= columns of quick_perf)
   for st in 0 1; do B200PCG_STAGED_COPY=$st timeout 100 python tools/quick_perf.py 256 250 250 diagonal 50 noconv 2>&1 | grep rep2; done
