@@ -127,3 +127,22 @@ def test_native_replay_tool():
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DICB200PCG:  Solving for ph_rgh, Initial residual = 1, " in r.stdout
     assert r.stdout.count("No Iterations 29") == 2 and "MISMATCH" not in r.stdout
+
+
+def test_dic_modes_survive_the_dump(tmp_path):
+    """`B200 { dicMode exact | eisenstat; }` travels as the preconditioner code of the dumped controls."""
+    s = mg.hex_block(5, 4, 3)
+    L = _lib.load_pcg()
+    for mode, code in (("multicolour", 2), ("exact", 3), ("eisenstat", 4)):
+        p = tmp_path / f"p_rgh_{mode}.b200sys"
+        ctl = {"preconditioner": "DIC", "tolerance": 1e-6, "relTol": 0.0, "maxIter": 1000, "minIter": 0}
+        if mode != "multicolour":
+            ctl["B200"] = {"dicMode": mode}
+        replay.write_dump(p, s, np.zeros(s.addr.nCells), ctl)
+        d = replay.read_dump(p)
+        assert d.controls == ctl and d.header["controls"]["precondCode"] == code
+        assert d.header["controls"]["preconditioner"] == "DIC"
+        h = C.c_void_p()
+        assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0, L.b200_dump_last_error()
+        assert L.b200_dump_get(h).contents.controls.precond == code
+        L.b200_dump_free(h)
