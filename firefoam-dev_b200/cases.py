@@ -73,10 +73,19 @@ class HydrostaticBox:
         W = 1.0 / (self.Y_O2 / self.W_O2 + self.Y_N2 / self.W_N2)
         self.psi_thermo = W / (self.RR * self.T)
         self.rho0 = self.psi_thermo * self.PREF
+        # density on the `top` patch faces: thermo.rho() there is psi_b * p_b with p_b = pRef (gh_b = 0 at
+        # y = hRef) and psi_b from the PATCH-FACE mixture (multiComponentMixture::patchFaceMixture sums
+        # Y_i,b * specie_i over the boundary values of the Y fields as read from 0/)
+        self.rho_top = self.top_patch_W() / (self.RR * self.T) * self.PREF
         # p = ph_rgh + rho*gh + pRef; thermo.correct(); rho = thermo.rho()   (phrghEqn.H:21-23)
         self.ph_rgh = np.zeros(N)
         p = self.ph_rgh + self.rho0 * self.gh + self.PREF
         self.rho = self.psi_thermo * p
+
+    def top_patch_W(self):
+        """molecular weight of the mixture on the `top` patch faces; cases/singleBox/0/N2:24-28 and
+        0/O2:24-29 carry $internalField there: the cell mixture"""
+        return 1.0 / (self.Y_O2 / self.W_O2 + self.Y_N2 / self.W_N2)
 
     def assemble(self, laplacian):
         """One corrector's ph_rghEqn: fvm::laplacian(rhof, ph_rgh) == fvc::div(phig)
@@ -87,11 +96,12 @@ class HydrostaticBox:
         rhof = 0.5 * (self.rho[l] + self.rho[u])
         snGrad = (self.rho[u] - self.rho[l]) * self.deltaCoeffs
         phig = -rhof * self.ghf * snGrad * self.magSf
-        # top patch fixedValue 0: internalCoeffs = -rho_b*magSf_b*deltaCoeffs_b, deltaCoeffs_b = 2/dy;
+        # top patch fixedValue 0: internalCoeffs = -rho_b*magSf_b*deltaCoeffs_b, deltaCoeffs_b = 2/dy,
+        # rho_b = rho_top (patch-face mixture, see __init__);
         # the fixedFluxPressure patches contribute nothing (their gradient cancels fvc::div's
         # boundary flux)
         diag0 = np.zeros(self.N)
-        diag0[self.top] += -self.rho0 * (self.d[0] * self.d[2]) * (2.0 / dy)
+        diag0[self.top] += -self.rho_top * (self.d[0] * self.d[2]) * (2.0 / dy)
         upper, diag = laplacian(rhof, self.magSf, self.deltaCoeffs, 1.0, diag0)
         source = np.zeros(self.N)
         np.add.at(source, l, phig)
@@ -118,6 +128,14 @@ class StecklerHydrostatic(HydrostaticBox):
                 b &= ~((i[own] == 16) & (j[own] <= 4) & (k[own] >= 7) & (k[own] <= 12))
             return b
         super().__init__(self.NX, self.NY, self.NZ, self.H, self.H, self.H, 3.0, baffle)
+
+    def top_patch_W(self):
+        """cases/steckler/0/N2:24-28: the inert specie's `top` patch is `calculated; value uniform 0`
+        (N2 is only re-derived as 1 - sum(Y_i) by the first YEEqn, after the hydrostatic loop), while
+        0/O2:24-29 has 0.23301 there: during solver/phrghEqn.H:19-60 the patch-face mixture is O2 alone,
+        W_b = W_O2, so rho_b(top) = 1.1091 rho_0.  This is the detail that makes the restated system
+        reproduce log.fireFoam:92-100 to the printed digits (tools/kat/steckler_kat_candidates.py)."""
+        return self.W_O2
 
 
 class SingleBoxHydrostatic(HydrostaticBox):

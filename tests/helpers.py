@@ -206,6 +206,12 @@ def random_ldu(N, avg_deg, seed, spd=True):
     return s
 
 
+# PCG + diagonal on the (digit-pinned) steckler hydrostatic loop: self-derived by the oracle, no shipped
+# case or log runs this mode
+STECKLER_DIAG_COUNTS = [87, 86, 21, 0, 0]
+STECKLER_DIC_COUNTS = [29, 32, 7, 0, 0]      # cases/steckler/original/linux64/log.fireFoam:92-100
+
+
 def hydrostatic_loop(case, laplacian, solve):
     """solver/phrghEqn.H:30-56: returns [(initial, final, iters, variation)] per corrector.
     solve(matrix, source, psi) -> object with initialResidual/finalResidual/nIterations."""

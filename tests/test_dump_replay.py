@@ -28,6 +28,8 @@ def test_fixture_steckler_pins_the_golden_log_count():
     perf = orc.pcg_solve(d.system, psi, "DIC", d.controls["tolerance"], d.controls["relTol"], d.controls["maxIter"])
     assert perf.nIterations == 29
     assert perf.finalResidual == d.reference["finalResidual"]
+    # ... and the log's printed final residual (0.0080439052) to its 8 digits
+    assert perf.finalResidual == pytest.approx(log["ph_rgh"][0]["final"], rel=1e-7)
     assert np.array_equal(psi, d.psi)
 
 

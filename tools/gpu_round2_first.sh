@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 N=${1:-1}
 if [ "$N" = "1" ]; then
   # whole 1-GPU suite (incl. full-size), then the DIC-class A/B on hex and polyhedra
-  B200_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/r2_pytest_gpu.log
+  B200_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/r2_pytest_gpu.log
   for pre in DIC DIC-eisenstat; do
     timeout 100 python tools/quick_perf.py 256 250 250 $pre 100 2>&1 | grep -E "eis_|dic_|spmv_dot|rep2|tolerance" > gpurun_out/r2_perf_hex_$pre.log
     timeout 300 python bench.py --workload poly --poly 125 125 160 --precond $pre --steps 2 --warmup 3 --no-cpu-baseline \
