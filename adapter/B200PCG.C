@@ -187,7 +187,7 @@ Foam::solverPerformance Foam::B200PCG::solve
     const word preconditionerName(lduMatrix::preconditioner::getName(controlDict_));
 
     // --- Setup class containing solver performance data
-    solverPerformance solverPerf(preconditionerName + typeName, fieldName_);
+    word logPreconditionerName(preconditionerName);
 
     b200_controls ctl;
     ctl.tolerance = tolerance_;
@@ -210,13 +210,21 @@ Foam::solverPerformance Foam::B200PCG::solve
         (
             controlDict_.subOrEmptyDict("B200").lookupOrDefault<word>
             (
-                "dicMode", "multicolour"
+                "dicMode", "auto"
             )
         );
+        // `preconditioner DIC` is the DIC-CLASS multicolour IC0 (the library picks its form); OpenFOAM's own
+        // DIC -- same elimination order, same iteration counts -- is `B200 { dicMode exact; }`
         ctl.precond =
             (mode == "exact") ? B200_PRECOND_DIC_EXACT
           : (mode == "eisenstat") ? B200_PRECOND_DIC_MC_EIS
+          : (mode == "multicolour") ? B200_PRECOND_DIC_MC_LOOP
           : B200_PRECOND_DIC_MC;
+        if (mode != "exact")
+        {
+            // the log line names what ran: DIC(mc)B200PCG is not DICPCG (different iteration counts)
+            logPreconditionerName = "DIC(mc)";
+        }
     }
     else
     {
@@ -224,6 +232,8 @@ Foam::solverPerformance Foam::B200PCG::solve
             << "B200PCG: unsupported preconditioner " << preconditionerName
             << "; valid: none diagonal DIC" << exit(FatalError);
     }
+
+    solverPerformance solverPerf(logPreconditionerName + typeName, fieldName_);
 
     if (!matrix_.symmetric() && !matrix_.diagonal())
     {
@@ -326,7 +336,7 @@ Foam::solverPerformance Foam::B200PCG::solve
         d.controls = ctl;
         d.havePerf = 1;
         d.perf = perf;
-        const std::string name(preconditionerName + typeName);
+        const std::string name(logPreconditionerName + typeName);
         d.solverName = name.c_str();
         d.solveIndex = solveIndex;
         d.time = matrix_.mesh().thisDb().time().value();

@@ -17,7 +17,7 @@ B200_OK, B200_EINVAL, B200_ECUDA, B200_ENCCL, B200_ENODEVICE, B200_ESTATE, B200_
 ERRNAMES = {1: "EINVAL", 2: "ECUDA", 3: "ENCCL", 4: "ENODEVICE", 5: "ESTATE", 6: "EUNSUPPORTED",
             7: "ENONFINITE", 8: "ENOMEM"}
 
-PRECOND = {"none": 0, "diagonal": 1, "DIC": 2, "DIC-exact": 3, "DIC-eisenstat": 4}
+PRECOND = {"none": 0, "diagonal": 1, "DIC": 2, "DIC-exact": 3, "DIC-eisenstat": 4, "DIC-multicolour": 5}
 
 # every symbol include/b200pcg.h declares (tests check that the .so exports them all)
 ABI_SYMBOLS = [

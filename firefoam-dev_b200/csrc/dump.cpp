@@ -73,15 +73,33 @@ const char* precond_name(int p) {
 
 // ---- minimal JSON field extraction for the reader (the writer above is the only producer of the
 // header besides the Python twin in firefoam-dev_b200/replay.py, which emits the same flat shape)
+// A key is a string token FOLLOWED BY ':' -- string VALUES that spell a key name (a field called "nCells",
+// a solver called "reference") are skipped, because the scan walks the header token by token.
 bool find_key(const std::string& js, const std::string& key, size_t from, size_t& valuePos) {
-    const std::string pat = "\"" + key + "\"";
-    size_t p = js.find(pat, from);
-    if (p == std::string::npos) return false;
-    p = js.find(':', p + pat.size());
-    if (p == std::string::npos) return false;
-    ++p;
-    while (p < js.size() && (js[p] == ' ' || js[p] == '\n' || js[p] == '\t')) ++p;
-    valuePos = p;
+    size_t p = from;
+    while (p < js.size()) {
+        if (js[p] != '"') { ++p; continue; }
+        const size_t b = ++p;                       // string token [b, e)
+        while (p < js.size() && js[p] != '"') p += (js[p] == '\\' && p + 1 < js.size()) ? 2 : 1;
+        const size_t e = p;
+        if (p < js.size()) ++p;
+        size_t q = p;
+        while (q < js.size() && (js[q] == ' ' || js[q] == '\n' || js[q] == '\t' || js[q] == '\r')) ++q;
+        if (q >= js.size() || js[q] != ':') continue;          // a value, not a key
+        ++q;
+        while (q < js.size() && (js[q] == ' ' || js[q] == '\n' || js[q] == '\t' || js[q] == '\r')) ++q;
+        if (e - b == key.size() && js.compare(b, e - b, key) == 0) {
+            valuePos = q;
+            return true;
+        }
+        p = q;
+    }
+    return false;
+}
+// a size read from the header: finite, integral, 0 <= v <= limit
+bool as_count(double v, uint64_t limit, uint64_t& out) {
+    if (!(v >= 0.0) || v > (double)limit || v != (double)(uint64_t)v) return false;
+    out = (uint64_t)v;
     return true;
 }
 bool get_number(const std::string& js, const std::string& key, size_t from, double& out) {
@@ -225,7 +243,7 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
     if (!rd || std::memcmp(F->blob.data(), kMagic, 8) != 0) return bail(std::string("not a b200 system dump: ") + path);
     uint64_t hlen;
     std::memcpy(&hlen, F->blob.data() + 8, 8);
-    if (16 + hlen > (uint64_t)sz) return bail("truncated header");
+    if (hlen > (uint64_t)sz - 16) return bail("truncated header");   // (sz >= 16 checked above; no wrap-around)
     F->json.assign(F->blob.data() + 16, (size_t)hlen);
     const std::string& js = F->json;
     std::memset(&F->d, 0, sizeof(F->d));
@@ -237,8 +255,12 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
     num("rank", 0, rk); num("nranks", 0, nr); num("solveIndex", 0, si); num("time", 0, tm);
     get_string(js, "fieldName", 0, F->fieldName);
     F->d.fieldName = F->fieldName.c_str();
-    F->d.nCells = (int32_t)nC; F->d.nFaces = (int32_t)nF; F->d.rank = (int32_t)rk; F->d.nranks = (int32_t)nr;
-    F->d.solveIndex = (int32_t)si; F->d.time = tm;
+    uint64_t uC, uF, uRk, uNr, uSi;
+    if (!as_count(nC, INT32_MAX, uC) || !as_count(nF, INT32_MAX, uF) || !as_count(rk, INT32_MAX, uRk) ||
+        !as_count(nr, INT32_MAX, uNr) || uNr < 1 || uRk >= uNr || !as_count(si, INT32_MAX, uSi))
+        return bail("header sizes must be non-negative integers (nCells, nFaces, rank < nranks, solveIndex)");
+    F->d.nCells = (int32_t)uC; F->d.nFaces = (int32_t)uF; F->d.rank = (int32_t)uRk; F->d.nranks = (int32_t)uNr;
+    F->d.solveIndex = (int32_t)uSi; F->d.time = tm;
     size_t cpos;
     if (find_key(js, "controls", 0, cpos)) {
         double t;
@@ -270,8 +292,11 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
             if (q == std::string::npos || q > iend) break;
             double a = 0, b = 0, c = 0;
             num("nbrRank", q, a); num("nFaces", q, b); num("tag", q, c);
+            uint64_t ua, ub;
+            if (!as_count(a, INT32_MAX, ua) || !as_count(b, INT32_MAX, ub) || !(c >= INT32_MIN && c <= INT32_MAX))
+                return bail("bad interface record in the header");
             b200_iface it;
-            it.nbrRank = (int32_t)a; it.nFaces = (int32_t)b; it.faceCells = nullptr; it.tag = (int32_t)c;
+            it.nbrRank = (int32_t)ua; it.nFaces = (int32_t)ub; it.faceCells = nullptr; it.tag = (int32_t)c;
             F->ifaces.push_back(it);
             p = q + 9;
         }
@@ -293,8 +318,13 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
             if (js[op] == '"') { get_string(js, "offset", q, offs); off = std::strtoull(offs.c_str(), nullptr, 10); }
             else off = (uint64_t)std::strtod(js.c_str() + op, nullptr);
         }
-        const uint64_t bytes = (uint64_t)cnt * (dtype == "i4" ? 4u : 8u);
-        if (off % 8 != 0 || off + bytes > (uint64_t)sz) return bail("array out of bounds: " + name);
+        if (dtype != "i4" && dtype != "f8") return bail("unknown dtype of array: " + name);
+        const uint64_t elem = dtype == "i4" ? 4u : 8u;
+        uint64_t ucnt;
+        // overflow-safe: count <= sz / elem, then offset <= sz - bytes
+        if (!as_count(cnt, (uint64_t)sz / elem, ucnt)) return bail("bad array count: " + name);
+        const uint64_t bytes = ucnt * elem;
+        if (off % 8 != 0 || off > (uint64_t)sz || bytes > (uint64_t)sz - off) return bail("array out of bounds: " + name);
         const char* ptr = F->blob.data() + off;
         const uint64_t N = (uint64_t)F->d.nCells, Fc = (uint64_t)F->d.nFaces;
         auto want = [&](uint64_t n, const char* dt) { return (uint64_t)cnt == n && dtype == dt; };

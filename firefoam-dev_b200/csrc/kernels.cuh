@@ -245,6 +245,7 @@ __global__ void k_scalar_step(Scalars* S, int step) {
 // the scalar step.  Executed by the first warp of the LAST block of the kernel that completes the
 // reduction (reduce_finish): no extra launch, instead of ncclAllReduce + a scalar kernel (~25 us).
 constexpr int kMaxRanks = 32;
+constexpr unsigned long long kPeerTimeoutNs = 5000000000ull;
 struct PeerBuf {
     double vals[2][kMaxRanks][kNSums];
     unsigned long long flags[2][kMaxRanks];
@@ -275,9 +276,16 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
     if (lane < nranks) {
         PeerBuf* me = peers[rank];
         volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(&me->flags[par][lane]);
-        unsigned long long spins = 0;
+        // bounded by TIME (5 s on the device's nanosecond timer, sampled every 1024 polls), not by a poll count
+        // whose duration depends on the clock and on the NVLink round trip
+        unsigned long long spins = 0, t0 = 0;
         while (*f != seq) {
-            if (++spins > 400000000ull) { timedOut = true; break; }
+            if ((++spins & 1023ull) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kPeerTimeoutNs) { timedOut = true; break; }
+            }
         }
         __threadfence_system();
 #pragma unroll

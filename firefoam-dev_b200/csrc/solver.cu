@@ -145,6 +145,7 @@ struct b200_ctx {
     // mesh
     bool haveMesh = false;
     uint64_t meshKey = 0;
+    uint64_t meshFingerprint = 0;   // mesh_fingerprint() of the addressing the plans were built from
     int32_t N = 0, F = 0;
     double nGlobalCells = 0;
     std::vector<int32_t> hl, hu;
@@ -172,7 +173,7 @@ struct b200_ctx {
     std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)
     PeerBuf** d_peers = nullptr;
     // staged copies of pageable caller memory (B200PCG_STAGED_COPY=1): two page-locked pieces + their DMA events
-    bool stagedCopy = false;
+    bool stagedCopy = true;
     void* stageBuf[2] = {nullptr, nullptr};
     cudaEvent_t stageEv[2] = {nullptr, nullptr};
     Scalars* S = nullptr;
@@ -205,8 +206,8 @@ struct b200_ctx {
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
     bool enableRanked = false;  // B200PCG_SPMV=ranked
     bool sortCols = false;      // B200PCG_SORT_COLS=1: multicolour plans order a row's entries by column (plan.hpp)
-    bool dicDefaultEis = false; // B200PCG_DIC=eisenstat: code 2 (`preconditioner DIC`) runs in the Eisenstat form too
-    bool eisOverlap = false;    // B200PCG_EIS_OVERLAP=1: nranks > 1: exchange t behind the first colour's backward sweep
+    bool dicDefaultEis = true;  // B200PCG_DIC=multicolour: code 2 (`preconditioner DIC`) keeps the three-kernel loop
+    bool eisOverlap = true;     // B200PCG_EIS_OVERLAP=0: nranks > 1: exchange t exposed between the two sweeps (A/B switch)
     int eisCtas = 0;            // B200PCG_EIS_CTAS=3|4: force the 80- / 64-register build of both 6-entry batched
                                 // sweeps (default 0: backward 64, forward 80 registers)
     int eisBatch = 1;           // B200PCG_EIS_BATCH=0: plain entry loops in the Eisenstat sweeps (A/B switch)
@@ -1005,7 +1006,8 @@ int copy_bou(b200_ctx* ctx, DevPlan& P, const double* const* bouPtrs, cudaMemcpy
 }
 
 Ordering ordering_for(int precond) {
-    if (precond == B200_PRECOND_DIC_MC || precond == B200_PRECOND_DIC_MC_EIS) return Ordering::MultiColour;
+    if (precond == B200_PRECOND_DIC_MC || precond == B200_PRECOND_DIC_MC_EIS || precond == B200_PRECOND_DIC_MC_LOOP)
+        return Ordering::MultiColour;
     if (precond == B200_PRECOND_DIC_EXACT) return Ordering::Levels;
     return Ordering::Natural;
 }
@@ -1038,15 +1040,20 @@ int finish_solve(b200_ctx* ctx, DevPlan& P, b200_perf* perf) {
 
 // The solve proper; all pointers are device pointers in natural order; bou already in ctx->bou.
 int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_src,
-               double* dn_psi, const b200_controls* ctl, b200_perf* perf) {
-    if (ctl->precond < 0 || ctl->precond > 4) return fail(ctx, B200_EINVAL, "bad preconditioner code");
+               double* dn_psi, const b200_controls* ctl, b200_perf* perf, bool forceLoop = false) {
+    if (ctl->precond < 0 || ctl->precond > 5) return fail(ctx, B200_EINVAL, "bad preconditioner code");
     // Eisenstat form of the DIC-class loop: same preconditioner as B200_PRECOND_DIC_MC.  Systems small enough
     // for the single-launch cluster kernels are latency-bound, not bandwidth-bound: they take that path
     // B200PCG_DIC=eisenstat: `preconditioner DIC` without a dicMode takes the Eisenstat form as well (the switch
     // that becomes the default once the form has run on 4 and 8 GPUs); tiled plans keep the three-kernel loop
+    // code 2 (`preconditioner DIC` without a dicMode): Eisenstat's form unless B200PCG_DIC=multicolour, a tiled
+    // plan, or (retry below) a matrix whose DIC pivots are not of one sign; code 5: always the three-kernel loop
     bool eis = (ctl->precond == B200_PRECOND_DIC_MC_EIS);
-    if (ctl->precond == B200_PRECOND_DIC_MC && ctx->dicDefaultEis && ctx->tileRows == 0) eis = true;
-    const int32_t smallPrecond = eis ? (int32_t)B200_PRECOND_DIC_MC : ctl->precond;
+    const bool autoForm = (ctl->precond == B200_PRECOND_DIC_MC);
+    if (autoForm && ctx->dicDefaultEis && ctx->tileRows == 0 && !forceLoop) eis = true;
+    const int32_t precond = (ctl->precond == B200_PRECOND_DIC_MC_LOOP || ctl->precond == B200_PRECOND_DIC_MC_EIS)
+                                ? (int32_t)B200_PRECOND_DIC_MC : ctl->precond;   // kernel-side code: 0..3
+    const int32_t smallPrecond = precond;
     if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_controls.reserved must be 0");
     DevPlan* Pp = nullptr;
     RET(ensure_plan(ctx, ordering_for(ctl->precond), &Pp));
@@ -1137,11 +1144,11 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         RET(reduce_post(ctx, STEP_NORM));
     }
     // preconditioner set-up
-    if (ctl->precond == B200_PRECOND_DIAGONAL) {
+    if (precond == B200_PRECOND_DIAGONAL) {
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->diag, ctx->rD);
     } else if (eis) {
         RET(eis_setup(ctx, P));
-    } else if (ctl->precond >= B200_PRECOND_DIC_MC) {
+    } else if (precond >= B200_PRECOND_DIC_MC) {
         for (int k = 0; k < P.h.nColours; ++k) {
             int g;
             const ColourRows cr = colour_rows(ctx, P, k, &g);
@@ -1156,11 +1163,18 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         }
         LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
     }
-    if (!eis) RET(enqueue_precondition(ctx, P, ctl->precond));   // early-exits on the device if converged
+    if (!eis) RET(enqueue_precondition(ctx, P, precond));   // early-exits on the device if converged
     CU(cudaEventRecord(ctx->ev[1], ctx->sc));
     CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
+    if (eis && autoForm && ctx->hS->nonfinite == 3) {
+        // DIC pivots of mixed sign (the global count decided: every rank takes this branch): the Eisenstat
+        // scaling does not exist; `preconditioner DIC` falls back to the three-kernel loop on the same inputs
+        // (nothing has been scaled or overwritten yet: the set-up kernels return on S->done)
+        prof_collect(ctx);
+        return solve_core(ctx, dn_diag, dn_upper, dn_src, dn_psi, ctl, perf, true);
+    }
 
     // PCG loop: batches of iterations, device decides when to stop
     int64_t cap = ctx->forceIters > 0 ? ctx->forceIters
@@ -1171,7 +1185,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         int n = (int)std::min<int64_t>(chunk, cap - enq);
         for (int i = 0; i < n; ++i) {
             if (eis) RET(enqueue_eis_iteration(ctx, P));
-            else RET(enqueue_iteration(ctx, P, ctl->precond));
+            else RET(enqueue_iteration(ctx, P, precond));
         }
         enq += n;
         CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
@@ -1269,38 +1283,96 @@ int d2h(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return B200_OK;
 }
 
+// ---- mesh fingerprint + cross-rank agreement -------------------------------------------------------
+// b200_set_addressing is called before every solve (upstream constructs a solver object per solve), so the
+// "same mesh?" test must cost microseconds: sizes, every interface's size and neighbour rank, and a 64-bit
+// hash over a strided sample of lowerAddr / upperAddr / faceCells (every entry when the array has
+// <= 65536 of them).  A renumbered, refined or re-decomposed mesh that happens to live at the same address with
+// the same sizes changes practically every sampled label; mesh_key alone (the address of the lduAddressing
+// object in the adapter) does not see that.
+inline uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+    return h ^ (h >> 29);
+}
+uint64_t sample_hash(uint64_t h, const int32_t* a, int64_t n) {
+    if (n <= 0 || !a) return mix64(h, 0x5bd1e995u);
+    const int64_t stride = n <= 65536 ? 1 : n / 8192;
+    for (int64_t i = 0; i < n; i += stride) h = mix64(h, (uint64_t)(uint32_t)a[i] ^ ((uint64_t)i << 32));
+    for (int64_t i = std::max<int64_t>(0, n - 64); i < n; ++i) h = mix64(h, (uint64_t)(uint32_t)a[i]);
+    return h;
+}
+uint64_t mesh_fingerprint(int32_t nCells, int32_t nFaces, const int32_t* l, const int32_t* u, int32_t nIfaces,
+                          const b200_iface* ifaces) {
+    uint64_t h = mix64(0x243F6A8885A308D3ull, ((uint64_t)(uint32_t)nCells << 32) | (uint32_t)nFaces);
+    h = sample_hash(h, l, nFaces);
+    h = sample_hash(h, u, nFaces);
+    h = mix64(h, (uint64_t)(uint32_t)nIfaces);
+    for (int k = 0; k < nIfaces; ++k) {
+        h = mix64(h, ((uint64_t)(uint32_t)ifaces[k].nbrRank << 32) | (uint32_t)ifaces[k].nFaces);
+        h = sample_hash(h, ifaces[k].nFaces > 0 ? ifaces[k].faceCells : nullptr, ifaces[k].nFaces);
+    }
+    return h;
+}
+
+// min over ranks of up to 4 ints (one tiny ncclAllReduce + host sync; set-up paths only).  Every rank must
+// call it at the same point, WHATEVER its local status: rank-local failures are agreed on here so that no rank
+// returns early while its peers wait inside a later collective.
+int agree_min(b200_ctx* ctx, int* v, int n) {
+    if (ctx->nranks == 1) return B200_OK;
+    int* d = reinterpret_cast<int*>(ctx->partials);
+    CU(cudaMemcpyAsync(d, v, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->sc));
+    NC(g_nccl.AllReduce(d, d + 8, (size_t)n, ncclInt, ncclMin, ctx->comm, ctx->sc));
+    CU(cudaMemcpyAsync(v, d + 8, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * 16, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    return B200_OK;
+}
+
 // Map every rank's PeerBuf into this process (CUDA IPC; handles exchanged with ncclAllGather).
+// Collective: every rank calls ncclAllGather exactly once, also after a local failure (its record then
+// carries valid = 0 and nobody maps anything), so a rank that cannot allocate or export its buffer cannot leave
+// the others hanging inside the gather.  Returns the LOCAL outcome; the caller agrees on the global one.
 bool setup_peer_reduce(b200_ctx* c, std::string& why) {
     const int n = c->nranks;
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&c->peerLocal, sizeof(PeerBuf))) != cudaSuccess) { why = cudaGetErrorString(e); return false; }
-    cudaMemset(c->peerLocal, 0, sizeof(PeerBuf));
-    cudaIpcMemHandle_t mine;
-    if ((e = cudaIpcGetMemHandle(&mine, c->peerLocal)) != cudaSuccess) { why = cudaGetErrorString(e); cudaGetLastError(); return false; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
-    unsigned char *d_send = nullptr, *d_recv = nullptr;
-    if (cudaMalloc((void**)&d_send, 64) != cudaSuccess || cudaMalloc((void**)&d_recv, 64 * (size_t)n) != cudaSuccess) { why = "cudaMalloc"; return false; }
-    cudaMemcpyAsync(d_send, &mine, 64, cudaMemcpyHostToDevice, c->sc);
-    ncclResult_t r = g_nccl.AllGather(d_send, d_recv, 64, ncclUint8, c->comm, c->sc);
-    std::vector<cudaIpcMemHandle_t> all((size_t)n);
-    cudaMemcpyAsync(all.data(), d_recv, 64 * (size_t)n, cudaMemcpyDeviceToHost, c->sc);
-    cudaStreamSynchronize(c->sc);
-    cudaFree(d_send);
-    cudaFree(d_recv);
-    if (r != ncclSuccess) { why = g_nccl.GetErrorString(r); return false; }
-    std::vector<PeerBuf*> ptrs((size_t)n, nullptr);
+    struct Rec { cudaIpcMemHandle_t h; uint64_t valid; };
+    Rec mine;
+    std::memset(&mine, 0, sizeof(mine));
     bool ok = true;
-    for (int k = 0; k < n; ++k) {
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&c->peerLocal, sizeof(PeerBuf))) != cudaSuccess) { why = cudaGetErrorString(e); cudaGetLastError(); c->peerLocal = nullptr; ok = false; }
+    if (ok && (e = cudaMemset(c->peerLocal, 0, sizeof(PeerBuf))) != cudaSuccess) { why = cudaGetErrorString(e); cudaGetLastError(); ok = false; }
+    if (ok && (e = cudaIpcGetMemHandle(&mine.h, c->peerLocal)) != cudaSuccess) { why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); ok = false; }
+    mine.valid = ok ? 1 : 0;
+    // the gather's own buffers live in the context's partials arena (allocated at create): no allocation that
+    // could fail on one rank only stands between here and the collective
+    static_assert(sizeof(Rec) * (kMaxRanks + 1) <= sizeof(double) * kNSums * kMaxGrid, "partials arena too small");
+    unsigned char* d_send = reinterpret_cast<unsigned char*>(c->partials);
+    unsigned char* d_recv = d_send + sizeof(Rec);
+    std::vector<Rec> all((size_t)n);
+    cudaError_t e1 = cudaMemcpyAsync(d_send, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->sc);
+    ncclResult_t r = g_nccl.AllGather(d_send, d_recv, sizeof(Rec), ncclUint8, c->comm, c->sc);
+    cudaError_t e2 = cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * (size_t)n, cudaMemcpyDeviceToHost, c->sc);
+    cudaError_t e3 = cudaStreamSynchronize(c->sc);
+    cudaMemsetAsync(c->partials, 0, sizeof(Rec) * (size_t)(n + 1), c->sc);
+    cudaStreamSynchronize(c->sc);
+    if (r != ncclSuccess) { why = g_nccl.GetErrorString(r); ok = false; }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { why = "copy around ncclAllGather failed"; cudaGetLastError(); ok = false; }
+    for (int k = 0; ok && k < n; ++k)
+        if (!all[k].valid) { why = "rank " + std::to_string(k) + " could not export its buffer"; ok = false; }
+    std::vector<PeerBuf*> ptrs((size_t)n, nullptr);
+    for (int k = 0; ok && k < n; ++k) {
         if (k == c->rank) { ptrs[k] = c->peerLocal; continue; }
         void* p = nullptr;
-        e = cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess);
+        e = cudaIpcOpenMemHandle(&p, all[k].h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); ok = false; break; }
         c->peerMapped.push_back(p);
         ptrs[k] = (PeerBuf*)p;
     }
     if (ok) {
-        if (cudaMalloc((void**)&c->d_peers, sizeof(PeerBuf*) * (size_t)n) != cudaSuccess) { why = "cudaMalloc"; ok = false; }
-        else cudaMemcpy(c->d_peers, ptrs.data(), sizeof(PeerBuf*) * (size_t)n, cudaMemcpyHostToDevice);
+        if (cudaMalloc((void**)&c->d_peers, sizeof(PeerBuf*) * (size_t)n) != cudaSuccess) { why = "cudaMalloc"; cudaGetLastError(); ok = false; }
+        else if (cudaMemcpy(c->d_peers, ptrs.data(), sizeof(PeerBuf*) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { why = "cudaMemcpy"; cudaGetLastError(); ok = false; }
     }
     c->p2pReduce = ok;
     return ok;
@@ -1388,7 +1460,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e22 = getenv("B200PCG_SORT_COLS")) c->sortCols = atoi(e22) != 0;
     if (const char* e21 = getenv("B200PCG_STAGED_COPY")) c->stagedCopy = atoi(e21) != 0;
     if (const char* e19 = getenv("B200PCG_EIS_OVERLAP")) c->eisOverlap = atoi(e19) != 0;
-    if (const char* e20 = getenv("B200PCG_DIC")) c->dicDefaultEis = (std::string(e20) == "eisenstat");
+    if (const char* e20 = getenv("B200PCG_DIC")) c->dicDefaultEis = (std::string(e20) != "multicolour");
     if (const char* e18 = getenv("B200PCG_EIS_CTAS")) c->eisCtas = atoi(e18) == 3 ? 3 : (atoi(e18) == 4 ? 4 : 0);
     if (const char* e16 = getenv("B200PCG_SWEEP_CTAS")) {
         c->sweepPerSM = std::max(1, std::min(16, atoi(e16)));
@@ -1425,16 +1497,13 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
                 // not fatal: fall back to ncclAllReduce, but every rank must take the same path
                 fprintf(stderr, "b200pcg[%d]: peer-memory all-reduce unavailable (%s); using NCCL\n", rank, why.c_str());
             }
-            // agree across ranks (min over ranks of the local success flag)
+            // agree across ranks (min over ranks of the local success flag); a failure of the agreement itself
+            // is fatal: the ranks could otherwise disagree on the reduction path
             int ok = c->p2pReduce ? 1 : 0;
-            int* d_ok = reinterpret_cast<int*>(c->partials);
-            cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->sc);
-            g_nccl.AllReduce(d_ok, d_ok + 1, 1, ncclInt, ncclMin, c->comm, c->sc);
-            cudaMemcpyAsync(&ok, d_ok + 1, sizeof(int), cudaMemcpyDeviceToHost, c->sc);
-            cudaStreamSynchronize(c->sc);
+            b200_ctx* ctx = c;
+            int rcA = [&]() -> int { return agree_min(ctx, &ok, 1); }();
+            if (rcA != B200_OK) return bail(rcA, "peer-memory set-up: cross-rank agreement failed: " + c->err);
             c->p2pReduce = (ok == 1);
-            cudaMemsetAsync(c->partials, 0, sizeof(double) * 4, c->sc);
-            cudaStreamSynchronize(c->sc);
         }
     }
     *out = c;
@@ -1472,14 +1541,38 @@ int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_
                         const b200_iface* ifaces) {
     if (!ctx) return B200_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->haveMesh && ctx->meshKey == mesh_key && ctx->N == nCells && ctx->F == nFaces &&
-        (int32_t)ctx->hif.size() == nIfaces)
-        return B200_OK;
-    if (nCells < 0 || nFaces < 0 || nIfaces < 0) return fail(ctx, B200_EINVAL, "negative size");
-    if (nFaces > 0 && (!lowerAddr || !upperAddr)) return fail(ctx, B200_EINVAL, "null addressing");
-    if (nIfaces > 0 && !ifaces) return fail(ctx, B200_EINVAL, "null interface list");
-    if (ctx->nranks == 1 && nIfaces > 0)
-        return fail(ctx, B200_EINVAL, "processor interfaces given but the context has nranks == 1");
+    // --- phase 1: everything rank-local (validation, "same mesh?" test); no early return when nranks > 1:
+    //     a rank that fails or rebuilds alone would leave its peers inside (or outside) the collectives below
+    int rcLocal = B200_OK;
+    std::string msgLocal;
+    auto bad = [&](int code, const char* m) { if (rcLocal == B200_OK) { rcLocal = code; msgLocal = m; } };
+    if (nCells < 0 || nFaces < 0 || nIfaces < 0) bad(B200_EINVAL, "negative size");
+    else if (nFaces > 0 && (!lowerAddr || !upperAddr)) bad(B200_EINVAL, "null addressing");
+    else if (nIfaces > 0 && !ifaces) bad(B200_EINVAL, "null interface list");
+    else if (ctx->nranks == 1 && nIfaces > 0) bad(B200_EINVAL, "processor interfaces given but the context has nranks == 1");
+    for (int k = 0; rcLocal == B200_OK && k < nIfaces; ++k) {
+        if (ifaces[k].nFaces < 0 || (ifaces[k].nFaces > 0 && !ifaces[k].faceCells)) bad(B200_EINVAL, "bad interface");
+        else if (ifaces[k].nbrRank < 0 || ifaces[k].nbrRank >= ctx->nranks || ifaces[k].nbrRank == ctx->rank)
+            bad(B200_EINVAL, "interface neighbour rank out of range");
+    }
+    uint64_t fp = 0;
+    bool same = false;
+    if (rcLocal == B200_OK) {
+        fp = mesh_fingerprint(nCells, nFaces, lowerAddr, upperAddr, nIfaces, ifaces);
+        same = ctx->haveMesh && ctx->meshKey == mesh_key && ctx->N == nCells && ctx->F == nFaces &&
+               (int32_t)ctx->hif.size() == nIfaces && ctx->meshFingerprint == fp;
+    }
+    if (ctx->nranks == 1) {
+        if (rcLocal != B200_OK) return fail(ctx, rcLocal, msgLocal);
+        if (same) return B200_OK;
+    } else {
+        int v[2] = {rcLocal == B200_OK ? 1 : 0, same ? 1 : 0};
+        RET(agree_min(ctx, v, 2));
+        if (rcLocal != B200_OK) return fail(ctx, rcLocal, msgLocal);
+        if (!v[0]) return fail(ctx, B200_EINVAL, "set_addressing failed on another rank");
+        if (v[1]) return B200_OK;      // unchanged on EVERY rank; otherwise every rank rebuilds
+    }
+    // --- phase 2: rank-local build
     CU(cudaStreamSynchronize(ctx->sc));
     free_mesh(ctx);
     ctx->N = nCells;
@@ -1489,33 +1582,43 @@ int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_
     ctx->hif.resize((size_t)nIfaces);
     ctx->nSlots = 0;
     for (int k = 0; k < nIfaces; ++k) {
-        if (ifaces[k].nFaces < 0 || (ifaces[k].nFaces > 0 && !ifaces[k].faceCells))
-            return fail(ctx, B200_EINVAL, "bad interface");
-        if (ifaces[k].nbrRank < 0 || ifaces[k].nbrRank >= ctx->nranks || ifaces[k].nbrRank == ctx->rank)
-            return fail(ctx, B200_EINVAL, "interface neighbour rank out of range");
         ctx->hif[k].nbrRank = ifaces[k].nbrRank;
         ctx->hif[k].faceCells.assign(ifaces[k].faceCells, ifaces[k].faceCells + ifaces[k].nFaces);
         ctx->nSlots += ifaces[k].nFaces;
     }
-    DevPlan* P = nullptr;
-    int rc = ensure_plan(ctx, Ordering::Natural, &P);
-    if (rc != B200_OK) { free_mesh(ctx); return rc; }
-    RET(upload(ctx, &ctx->d_l, ctx->hl));
-    RET(upload(ctx, &ctx->d_u, ctx->hu));
-    RET(alloc_vectors(ctx));
-    // global cell count for gAverage
+    auto build = [&]() -> int {
+        DevPlan* P = nullptr;
+        RET(ensure_plan(ctx, Ordering::Natural, &P));
+        RET(upload(ctx, &ctx->d_l, ctx->hl));
+        RET(upload(ctx, &ctx->d_u, ctx->hu));
+        RET(alloc_vectors(ctx));
+        CU(cudaStreamSynchronize(ctx->sc));
+        return B200_OK;
+    };
+    int rc = build();
+    // --- phase 3: agree on the outcome, then the one data collective (global cell count for gAverage)
     ctx->nGlobalCells = (double)nCells;
     if (ctx->nranks > 1) {
+        const std::string keep = ctx->err;
+        int ok = rc == B200_OK ? 1 : 0;
+        int rcA = agree_min(ctx, &ok, 1);
+        if (rc != B200_OK) { ctx->err = keep; free_mesh(ctx); return rc; }
+        if (rcA != B200_OK) { free_mesh(ctx); return rcA; }
+        if (!ok) { free_mesh(ctx); return fail(ctx, B200_EINVAL, "set_addressing: plan build failed on another rank"); }
         double* tmp = ctx->partials;
         double h = (double)nCells;
         CU(cudaMemcpyAsync(tmp, &h, sizeof(double), cudaMemcpyHostToDevice, ctx->sc));
         NC(g_nccl.AllReduce(tmp, tmp + 1, 1, ncclDouble, ncclSum, ctx->comm, ctx->sc));
         CU(cudaMemcpyAsync(&h, tmp + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->sc));
+        CU(cudaMemsetAsync(tmp, 0, 2 * sizeof(double), ctx->sc));
         CU(cudaStreamSynchronize(ctx->sc));
         ctx->nGlobalCells = h;
+    } else if (rc != B200_OK) {
+        free_mesh(ctx);
+        return rc;
     }
-    CU(cudaStreamSynchronize(ctx->sc));
     ctx->meshKey = mesh_key;
+    ctx->meshFingerprint = fp;
     ctx->haveMesh = true;
     return B200_OK;
 }

@@ -308,9 +308,13 @@ def make_controls(solverControls):
     pre = d.get("preconditioner", "none")
     if isinstance(pre, dict):
         pre = pre.get("preconditioner", "none")
-    mode = d.get("B200", {}).get("dicMode", "multicolour")
-    if pre == "DIC" and mode in ("exact", "eisenstat"):
+    # `preconditioner DIC` is the DIC-CLASS multicolour IC0 (the library picks its form); OpenFOAM's own DIC
+    # (same elimination order, same iteration counts) is `B200 { dicMode exact; }`
+    mode = d.get("B200", {}).get("dicMode", "auto")
+    if pre == "DIC" and mode in ("exact", "eisenstat", "multicolour"):
         pre = "DIC-" + mode
+    elif pre == "DIC" and mode != "auto":
+        raise ValueError(f"Unknown dicMode {mode}; valid: auto exact eisenstat multicolour")
     if pre not in PRECOND:
         raise ValueError(f"Unknown symmetric matrix preconditioner {pre}; valid: {sorted(PRECOND)}")
     c = Controls()
@@ -365,5 +369,8 @@ class B200PCG:
         m = self.matrix
         self.ctx.set_addressing(m.lduAddr)
         perf = self.ctx.solve(m.diag, m.upper, self.bou, _f64(source), psi, self.controls)
-        pre = {"none": "none", "diagonal": "diagonal", "DIC": "DIC", "DIC-exact": "DIC", "DIC-eisenstat": "DIC"}[self.preconditionerName]
+        # the log line names what ran: only `dicMode exact` is OpenFOAM's DIC; the multicolour IC0 stand-in
+        # (different iteration counts) prints as DIC(mc)B200PCG
+        pre = {"none": "none", "diagonal": "diagonal", "DIC": "DIC(mc)", "DIC-exact": "DIC", "DIC-eisenstat": "DIC(mc)",
+               "DIC-multicolour": "DIC(mc)"}[self.preconditionerName]
         return SolverPerformance(pre + self.typeName, self.fieldName, perf)

@@ -17,7 +17,7 @@ from .ldu import LduAddressing, ProcessorLduInterface
 from .meshgen import System
 
 MAGIC = b"B200LDU\x01"
-PRECOND_NAMES = {0: "none", 1: "diagonal", 2: "DIC", 3: "DIC", 4: "DIC"}
+PRECOND_NAMES = {0: "none", 1: "diagonal", 2: "DIC", 3: "DIC", 4: "DIC", 5: "DIC"}
 
 
 class DumpedSolve:

@@ -58,13 +58,18 @@ enum {
 enum {
     B200_PRECOND_NONE      = 0,  /* `none`      -> noPreconditioner                              */
     B200_PRECOND_DIAGONAL  = 1,  /* `diagonal`  -> diagonalPreconditioner (bit-comparable path)  */
-    B200_PRECOND_DIC_MC    = 2,  /* `DIC`       -> multicolour-ordered IC0 ("DIC-class")         */
+    B200_PRECOND_DIC_MC    = 2,  /* `DIC`       -> multicolour-ordered IC0 ("DIC-class"); the library picks
+                                    the form: Eisenstat's (code 4) on bandwidth-bound systems with definite
+                                    DIC pivots, else the three-kernel loop (code 5).  NOT OpenFOAM's DIC:
+                                    iteration counts differ, the log says `DIC(mc)B200PCG`             */
     B200_PRECOND_DIC_EXACT = 3,  /* `DIC` + `B200{dicMode exact;}` -> level-scheduled DIC with
                                     the SAME elimination order as OpenFOAM's DICPreconditioner  */
-    B200_PRECOND_DIC_MC_EIS = 4  /* `DIC` + `B200{dicMode eisenstat;}` -> the multicolour IC0 of code 2
+    B200_PRECOND_DIC_MC_EIS = 4, /* `DIC` + `B200{dicMode eisenstat;}` -> the multicolour IC0 of code 2
                                     applied in Eisenstat's form: the two triangular sweeps also
                                     deliver A*p, so the iteration has no separate Amul (same iterates
-                                    as code 2 up to rounding; 1e-8 solution parity bar)            */
+                                    as code 5 up to rounding; 1e-8 solution parity bar)            */
+    B200_PRECOND_DIC_MC_LOOP = 5 /* `DIC` + `B200{dicMode multicolour;}` -> the multicolour IC0 as a separate
+                                    preconditioner apply (forward / backward colour sweeps) + Amul          */
 };
 
 typedef struct b200_ctx b200_ctx;

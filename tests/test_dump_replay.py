@@ -148,3 +148,51 @@ def test_dic_modes_survive_the_dump(tmp_path):
         assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0, L.b200_dump_last_error()
         assert L.b200_dump_get(h).contents.controls.precond == code
         L.b200_dump_free(h)
+
+
+def test_native_reader_rejects_hostile_headers(tmp_path):
+    """The native reader (b200replay feeds it files from disk) must not trust header numbers: wrapping header
+    length / offsets, negative or fractional counts, and key names that appear as string VALUES."""
+    import struct
+    L = _lib.load_pcg()
+    good = open(os.path.join(GOLD, "singlebox_ph_rgh_c1.b200sys"), "rb").read()
+    hlen = struct.unpack("<Q", good[8:16])[0]
+    hdr = good[16:16 + hlen].decode()
+    h = C.c_void_p()
+
+    def read(blob, name):
+        p = tmp_path / name
+        p.write_bytes(blob)
+        rc = L.b200_dump_read(str(p).encode(), C.byref(h))
+        if rc == 0:
+            L.b200_dump_free(h)
+        return rc, L.b200_dump_last_error().decode()
+
+    def with_header(new):
+        assert len(new) == len(hdr)          # same length: the array offsets stay valid
+        return good[:16] + new.encode() + good[16 + hlen:]
+
+    assert read(good, "ok.b200sys")[0] == 0
+    # header length that wraps 16 + hlen around 2^64
+    rc, msg = read(good[:8] + struct.pack("<Q", 2**64 - 8) + good[16:], "wrap.b200sys")
+    assert rc != 0 and "truncated header" in msg
+    # negative / fractional / huge sizes
+    for a, b in (('"nCells": 245', '"nCells": -45'), ('"nCells": 245', '"nCells": 2.5'), ('"nFaces": 616', '"nFaces": 9e9')):
+        assert a in hdr
+        rc, msg = read(with_header(hdr.replace(a, b, 1)), "neg.b200sys")
+        assert rc != 0 and "non-negative integers" in msg, (b, msg)
+    # an array offset near 2^64 (off + bytes wraps) and a count far beyond the file
+    i = hdr.index('"offset": "') + len('"offset": "')
+    rc, msg = read(with_header(hdr[:i] + "18446744073709551608" + hdr[i + 20:]), "off.b200sys")
+    assert rc != 0 and "out of bounds" in msg
+    a = '"count": 616'
+    rc, msg = read(with_header(hdr.replace(a, '"count": 9e9', 1)), "cnt.b200sys")
+    assert rc != 0 and ("bad array count" in msg or "mandatory" in msg)
+    # a field called like a key: "fieldName": "nCells" must not be parsed as the nCells entry
+    assert '"fieldName": "ph_rgh"' in hdr
+    rc, msg = read(with_header(hdr.replace('"fieldName": "ph_rgh"', '"fieldName": "nCells"', 1)), "key.b200sys")
+    assert rc == 0, msg
+    assert L.b200_dump_read(str(tmp_path / "key.b200sys").encode(), C.byref(h)) == 0
+    dd = L.b200_dump_get(h).contents
+    assert dd.nCells == 245 and dd.fieldName == b"nCells"
+    L.b200_dump_free(h)

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from firefoam_dev_b200 import B200PCG, meshgen as mg
+from firefoam_dev_b200 import B200PCG, B200Error, meshgen as mg
 from firefoam_dev_b200.cases import StecklerHydrostatic
 from oracle import oracle as orc
 from helpers import hydrostatic_loop, random_ldu
@@ -44,7 +44,7 @@ def test_eisenstat_solution_1e8_and_same_iterations(ctx, name, s):
         assert np.linalg.norm(xe - xm) / np.linalg.norm(xm) < 1e-8
     xc, pc = solve_cpu(s, "DIC", tol=1e-11, maxIter=5000)
     assert np.linalg.norm(xe - xc) / np.linalg.norm(xc) < 1e-8
-    assert str(pe).startswith("DICB200PCG:  Solving for p_rgh, Initial residual = ")
+    assert str(pe).startswith("DIC(mc)B200PCG:  Solving for p_rgh, Initial residual = ")
 
 
 def test_eisenstat_medium_hex_multi_kernel_path(ctx):
@@ -114,6 +114,14 @@ def test_eisenstat_plan_variants(env):
         c.close()
 
 
+def indefinite_system():
+    """a hex system with one DIC pivot of the wrong sign"""
+    s = mg.hex_block(64, 64, 64)
+    bad = mg.System(s.addr, s.diag.copy(), s.upper, s.source, s.bou, s.xstar)
+    bad.diag[1000] = -bad.diag[1000]
+    return bad
+
+
 def test_eisenstat_rejects_indefinite_matrix(ctx):
     """DIC pivots of mixed sign: the symmetric scaling does not exist -> B200_EUNSUPPORTED, context still usable."""
     from firefoam_dev_b200 import B200Error
@@ -138,33 +146,43 @@ def test_eisenstat_rejects_tiled_plan():
         c.close()
 
 
-@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
-                    reason="B200PCG_DIC=eisenstat (host-side selection only) has not run on a GPU yet")
-def test_dic_keyword_can_default_to_the_eisenstat_form():
-    """B200PCG_DIC=eisenstat: plain `preconditioner DIC` takes the Eisenstat form (tiled plans keep the
-    three-kernel loop)."""
+def test_dic_keyword_defaults_to_the_eisenstat_form():
+    """Plain `preconditioner DIC` (no dicMode) takes the Eisenstat form; B200PCG_DIC=multicolour, tiled plans and
+    matrices with DIC pivots of mixed sign keep / fall back to the three-kernel loop."""
     s = mg.hex_block(64, 40, 33)
-    c = _ctx_with_env({"B200PCG_DIC": "eisenstat", "B200PCG_SMALL_N": "0"})
+    c = _ctx_with_env({"B200PCG_SMALL_N": "0"})
     try:
         c.profile(True)
-        xm, pm = solve_mode(c, s, "multicolour", tol=1e-9)
+        xa, pa = solve_mode(c, s, "auto", tol=1e-9)
         prof = c.profile_json()
         assert "eis_fwd_dot" in prof and "spmv_dot" not in prof
         xe, pe = solve_mode(c, s, "eisenstat", tol=1e-9)
-        assert pm.nIterations == pe.nIterations and np.array_equal(xm, xe)
-    finally:
-        c.close()
-    c = _ctx_with_env({"B200PCG_DIC": "eisenstat", "B200PCG_SMALL_N": "0", "B200PCG_TILE": "64"})
-    try:
+        assert pa.nIterations == pe.nIterations and np.array_equal(xa, xe)
+        assert pa.solverName == "DIC(mc)B200PCG"
         c.profile(True)
-        xt, pt = solve_mode(c, s, "multicolour", tol=1e-9)
-        assert "spmv_dot" in c.profile_json() and pt.converged
+        xm, pm = solve_mode(c, s, "multicolour", tol=1e-9)       # explicit: always the three-kernel loop
+        assert "spmv_dot" in c.profile_json() and "eis_fwd_dot" not in c.profile_json()
+        # indefinite matrix (DIC pivots of mixed sign): explicit eisenstat is an error, auto falls back
+        si = indefinite_system()
+        with pytest.raises(B200Error):
+            solve_mode(c, si, "eisenstat", maxIter=20)
+        c.profile(True)
+        xi, pi = solve_mode(c, si, "auto", maxIter=20)
+        xl, pl = solve_mode(c, si, "multicolour", maxIter=20)
+        assert "spmv_dot" in c.profile_json()
+        assert pi.nIterations == pl.nIterations and np.array_equal(xi, xl)
     finally:
         c.close()
+    for env in ({"B200PCG_DIC": "multicolour", "B200PCG_SMALL_N": "0"}, {"B200PCG_SMALL_N": "0", "B200PCG_TILE": "64"}):
+        c = _ctx_with_env(env)
+        try:
+            c.profile(True)
+            xt, pt = solve_mode(c, s, "auto", tol=1e-9)
+            assert "spmv_dot" in c.profile_json() and pt.converged
+        finally:
+            c.close()
 
 
-@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
-                    reason="B200PCG_SORT_COLS=1 (host-side entry order of the multicolour plan) has not run on a GPU yet")
 @pytest.mark.parametrize("mode", ["multicolour", "eisenstat"])
 def test_column_sorted_multicolour_plan(mode):
     """B200PCG_SORT_COLS=1: entries of the multicolour plan ordered by column (coalesced gathers on renumbered

@@ -493,10 +493,8 @@ def test_16bit_ell_columns_change_nothing():
         c32.close()
 
 
-@pytest.mark.skipif(not os.environ.get("B200_TEST_UNVALIDATED"),
-                    reason="B200PCG_STAGED_COPY=1 (opt-in host-side copy pipeline) has not run on a GPU yet")
 def test_staged_copies_of_pageable_memory_change_nothing():
-    """B200PCG_STAGED_COPY=1: pageable caller arrays travel through two page-locked 16 MB pieces (OpenMP copy
+    """B200PCG_STAGED_COPY (default 1): pageable caller arrays travel through two page-locked 16 MB pieces (OpenMP copy
     overlapped with the DMA); several pieces per array, a last partial piece, identical results."""
     s = mg.hex_block(128, 96, 90)          # 1.1 M cells: upper is 26 MB (2 pieces), the vectors 8.8 MB (1 partial)
     base = {"B200PCG_SMALL_N": "0"}

@@ -22,24 +22,21 @@ def ngpus():
         return 0
 
 
-@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "overlap"), (4, None), (4, "overlap"), (8, None),
-                                        (8, "128"), (8, "overlap")])
+@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (4, None), (4, "no-overlap"), (8, None),
+                                        (8, "128"), (8, "no-overlap")])
 def test_multigpu_parity(world, tile):
     """tile: B200PCG_TILE for the ranks (tiled multicolour order + symmetric Amul in the DIC-class mode;
-    the default tile of 8192 rows does not engage on these small sub-meshes); "overlap": the Eisenstat
-    form with the halo exchange behind the first colour's backward sweep (B200PCG_EIS_OVERLAP=1)."""
+    the default tile of 8192 rows does not engage on these small sub-meshes); "no-overlap": the Eisenstat
+    form with the halo exchange exposed between the sweeps (B200PCG_EIS_OVERLAP=0; the default overlaps it with
+    the first colour's backward sweep)."""
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    if tile == "overlap" and not os.environ.get("B200_TEST_UNVALIDATED"):
-        # CPU-checked across two gloo ranks (test_multirank_gloo.py), never run on GPUs yet: opt-in until its
-        # first green GPU run (tools/gpu_round2_first.sh sets the variable)
-        pytest.skip("overlapped Eisenstat halo sequence: first GPU run pending (B200_TEST_UNVALIDATED=1 runs it)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "mgpu_worker.py")]
     env = dict(os.environ)
-    if tile == "overlap":
-        env["B200PCG_EIS_OVERLAP"] = "1"
+    if tile == "no-overlap":
+        env["B200PCG_EIS_OVERLAP"] = "0"
         tile = None
     elif tile:
         env["B200PCG_TILE"] = tile
