@@ -104,12 +104,19 @@ void Foam::b200SetAddressing
     {
         if (!interfaces.set(patchi)) continue;
 
-        if (!isA<processorLduInterface>(interfaces[patchi]))
+        // processorCyclic patches ARE processorLduInterfaces (processorCyclicFvPatch derives from
+        // processorFvPatch) but apply a transformation to the neighbour values: rejected by type name
+        const word ifType(interfaces[patchi].type());
+        if
+        (
+            !isA<processorLduInterface>(interfaces[patchi])
+         || ifType.find("Cyclic") != std::string::npos
+        )
         {
             FatalErrorInFunction
                 << "B200PCG: unsupported coupled interface "
-                << interfaces[patchi].type() << " on patch " << patchi
-                << " (only processor interfaces are supported)"
+                << ifType << " on patch " << patchi
+                << " (only plain processor interfaces are supported)"
                 << exit(FatalError);
         }
 
@@ -249,7 +256,12 @@ Foam::solverPerformance Foam::B200PCG::solve
     {
         if (interfaces_.set(patchi))
         {
-            if (!isA<processorLduInterfaceField>(interfaces_[patchi]))
+            const word fieldType(interfaces_[patchi].type());
+            if
+            (
+                !isA<processorLduInterfaceField>(interfaces_[patchi])
+             || fieldType.find("Cyclic") != std::string::npos
+            )
             {
                 FatalErrorInFunction
                     << "B200PCG: unsupported coupled interface "

@@ -218,11 +218,13 @@ def make_system(args, n, rank, pinned=None, dist=None):
 # ---------------------------------------------------------------------------------------------
 def cpu_leg(args, seconds=12.0, steps=1, warmup=0):
     """The reference's CPU path for this workload: oracle/ (plain-C restatement of OpenFOAM-dev's
-    PCG + diagonalPreconditioner/DICPreconditioner + Amul + normFactor, `kind: port` -- the
-    reference's own implementation is un-vendored and cannot be built here), R emulated ranks = R
-    host threads, each owning a decomposePar sub-mesh, like `mpirun -np R fireFoam -parallel`
-    (cases/wallFireSpread2D/runParallel.sh:18).  Bounded sample: a fixed number of PCG iterations on
-    one GPU's share of the workload, sized for ~`seconds` of CPU work per step."""
+    fvm::laplacian assembly + PCG + diagonalPreconditioner/DICPreconditioner + Amul + normFactor,
+    `kind: port` -- the reference's own implementation is un-vendored and cannot be built here), R emulated
+    ranks = R host threads, each owning a decomposePar sub-mesh, like `mpirun -np R fireFoam -parallel`
+    (cases/wallFireSpread2D/runParallel.sh:18).  Bounded sample: ONE GPU's share of the workload (at N > 1
+    that is not the N-GPU mesh: `sample` names the mesh actually solved), assembled (laplacian face
+    coefficients + negSumDiag) and iterated a fixed number of PCG iterations, sized for ~`seconds` of CPU work
+    per step."""
     import numpy as np
     from firefoam_dev_b200 import meshgen as mg
     from oracle import oracle as orc
@@ -241,21 +243,36 @@ def cpu_leg(args, seconds=12.0, steps=1, warmup=0):
             r //= 2
             d += 1
         subs = [mg.hex_block(*block, *p, rank) for rank in range(R)]
-        what = (f"the {block[0]}x{block[1]}x{block[2]} hex system on {R} emulated ranks/threads "
-                f"({p[0]} {p[1]} {p[2]})")
+        mesh = f"hex {block[0]}x{block[1]}x{block[2]}"
+        what = (f"the {block[0]}x{block[1]}x{block[2]} hex system (one GPU's block of the workload) on {R} emulated "
+                f"ranks/threads ({p[0]} {p[1]} {p[2]})")
     elif args.workload == "poly":
         nx, ny, nz = args.poly
         while 2 * nx * ny * nz > 6_000_000:      # bounded sample: <= 6 M cells of the same lattice
             nx, ny, nz = max(8, nx // 2), max(8, ny // 2), max(8, nz // 2)
         full = mg.bcc_poly(nx, ny, nz)
         subs = mg.decompose(full, mg.partition_rcb(full.xyz, R), R) if R > 1 else [full]
+        mesh = f"bcc_poly 2x{nx}x{ny}x{nz}"
         what = f"the 2x{nx}x{ny}x{nz} BCC polyhedral system, RCB on {R} emulated ranks/threads"
     else:
         from firefoam_dev_b200 import cases
         subs, R = [cases.steckler_p_rgh_system()], 1
+        mesh = "steckler 30x15x20"
         what = "the 9000-cell steckler p_rgh system on 1 thread (a 9000-cell case does not scale over ranks)"
     n_global = sum(s.addr.nCells for s in subs)
     gen_s = time.time() - t0
+
+    def assemble():
+        # fvm::laplacian: upper = sign * deltaCoeffs * (gamma * magSf), negSumDiag on top of diag0
+        t = time.perf_counter()
+        for s in subs:
+            if s.gamma_f is None:
+                continue
+            a = s.addr
+            up, dg = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf, s.deltaCoeffs,
+                                            s.sign, s.diag0)
+            s.upper[:], s.diag[:] = up, dg
+        return time.perf_counter() - t
 
     def run(iters):
         psis = [np.zeros(s.addr.nCells) for s in subs]
@@ -266,17 +283,21 @@ def cpu_leg(args, seconds=12.0, steps=1, warmup=0):
     per_iter = tc / max(ic, 1)
     cap = 400 if args.workload != "steckler" else 200000
     iters = int(min(cap, max(8, seconds / max(per_iter, 1e-7))))
-    times, total_it = [], 0
+    times, asm, total_it = [], [], 0
     for _ in range(warmup):
+        assemble()
         run(iters)
     for _ in range(max(1, steps)):
+        ta = assemble()
         t, it = run(iters)
-        times.append(t)
+        times.append(ta + t)
+        asm.append(ta)
         total_it += it
     value = n_global * total_it / sum(times) / 1e9
-    return {"value": value, "unit": UNIT, "cores": R, "kind": "port",
-            "sample": f"{iters} PCG+{pre} iterations of {what} ({n_global} cells); "
-                      f"host has {ncpu} usable cores; {sum(times)/len(times):.2f} s per step",
+    return {"value": value, "unit": UNIT, "cores": R, "kind": "port", "mesh": mesh, "cells": n_global,
+            "sample": f"laplacian assembly (single thread per sub-mesh, {sum(asm)/len(asm):.2f} s) + {iters} PCG+{pre} "
+                      f"iterations of {what} ({n_global} cells); host has {ncpu} usable cores; "
+                      f"{sum(times)/len(times):.2f} s per step",
             "ms_per_step": 1e3 * sum(times) / len(times), "gen_s": gen_s}
 
 
@@ -285,11 +306,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     leg = cpu_leg(args, seconds=args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
+    cfg = config_dict(args, args.gpus)
+    cfg["reference_sample_mesh"] = f"{leg['mesh']} ({leg['cells']} cells): a rate on one GPU's share, not the {cfg['cells']}-cell job"
     line = {"impl": "reference", "metric": METRIC.replace("diagonal", args.precond), "value": leg["value"],
             "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, args.gpus),
+            "config": cfg,
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -298,122 +321,386 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_gpu(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import firefoam_dev_b200 as pkg
+class Env:
+    """Process-wide state of the GPU arm: rank / device / NCCL rendez-vous, pinned allocator, barrier."""
 
-    n = args.gpus
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != n:
-        raise SystemExit(f"--gpus {n} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {n}")
-    if not torch.cuda.is_available() or pkg.load_pcg().b200_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    uid = None
-    if n > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import firefoam_dev_b200 as pkg
+        self.torch, self.dist, self.pkg, self.args = torch, dist, pkg, args
+        self.n = args.gpus
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world != self.n:
+            raise SystemExit(f"--gpus {self.n} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {self.n}")
+        if not torch.cuda.is_available() or pkg.load_pcg().b200_device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.uid = None
+        if self.n > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.uid = self.new_uid()
+        self.keep = []
+        self.peak, self.peak_src = measured_peak()
+
+    def new_uid(self):
+        torch, dist = self.torch, self.dist
+        buf = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(self.pkg.Context.unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
 
-    def barrier():
-        if n > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.n > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    keep = []
-
-    def pinned(count, dtype):
-        t = torch.empty(max(1, count), dtype=torch.float64, pin_memory=True)
-        keep.append(t)
+    def pinned(self, count, dtype=None):
+        t = self.torch.empty(max(1, count), dtype=self.torch.float64, pin_memory=True)
+        self.keep.append(t)
         return t.numpy()[:count]
 
-    def to_pinned(a):
-        out = pinned(a.size, np.float64)
+    def to_pinned(self, a):
+        out = self.pinned(a.size)
         out[:] = a
         return out
 
-    s, n_global, gen_s = make_system(args, n, rank, pinned=pinned, dist=dist)
+    def up(self, x):
+        import numpy as np
+        return self.torch.from_numpy(np.ascontiguousarray(x)).to(self.dev)
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.n > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """barrier + sync, `steps` calls of fn() between two CUDA events on torch's current stream (every
+        library call ends with a synchronize of its own stream, so the events bracket the whole device work),
+        barrier + sync; returns (max over ranks of the elapsed ms, list of fn's results)."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = [fn() for _ in range(steps)]
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)), out
+
+
+class Resident:
+    """One system resident in HBM + the device-resident step (assemble laplacian, solve)."""
+
+    def __init__(self, env, ctx, s, sctl):
+        import numpy as np
+        torch = env.torch
+        self.env, self.ctx, self.s = env, ctx, s
+        a = s.addr
+        self.N, self.F = a.nCells, a.nFaces
+        self.ctl, _ = env.pkg.make_controls(sctl)
+        up = env.up
+        self.d_gamma, self.d_magSf, self.d_delta = up(s.gamma_f), up(s.magSf), up(s.deltaCoeffs)
+        self.d_diag0, self.d_src = up(s.diag0), up(s.source)
+        self.d_bou = [up(b) for b in s.bou]
+        self.d_diag = torch.empty(self.N, dtype=torch.float64, device=env.dev)
+        self.d_upper = torch.empty(self.F, dtype=torch.float64, device=env.dev)
+        self.d_psi = torch.zeros(self.N, dtype=torch.float64, device=env.dev)
+        small = self.N * 200 < 126e6          # whole system L2-resident: flush between timed steps
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.dev) if small else None
+        self.np = np
+
+    def step(self, ctl=None):
+        # assemble: - fvm::laplacian(rhorAUf, p_rgh) on top of the ddt/boundary diagonal, then solve
+        self.d_diag.copy_(self.d_diag0)
+        self.d_psi.zero_()
+        if self.flush is not None:
+            self.flush.zero_()
+        self.env.torch.cuda.current_stream().synchronize()
+        self.ctx.assemble_laplacian_device(self.d_gamma, self.d_magSf, self.d_delta, self.s.sign, self.d_upper, self.d_diag)
+        return self.ctx.solve_device(self.d_diag, self.d_upper, self.d_bou, self.d_src, self.d_psi, ctl or self.ctl)
+
+    def err(self):
+        return float(self.np.abs(self.d_psi.cpu().numpy() - self.s.xstar).max()) if self.s.xstar is not None else None
+
+
+def sctl_for(precond, relTol=0.0, maxIter=MAXITER):
+    mode = {"DIC-exact": "exact", "DIC-eisenstat": "eisenstat", "DIC-multicolour": "multicolour"}.get(precond, "auto")
+    return {"preconditioner": "DIC" if precond.startswith("DIC") else precond, "tolerance": TOL, "relTol": relTol,
+            "maxIter": maxIter, "B200": {"dicMode": mode}}
+
+
+def kernel_table(prof, N, F, peak, dic, nColours, col_bytes=4):
+    """Per-kernel averages of a PROFILED pass (launches of surplus loop bodies excluded by the library) against
+    the bytes each kernel has to move: SURVEY.md 8d's algorithmic figure where it names the kernel, else the
+    bytes of the layout the kernel streams (stated in DESIGN.md section 4) -- always a fraction <= 1."""
+    alg = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N,
+           "asm_face_coeff": 32 * F, "asm_neg_sum_diag": 16 * N + 16 * F,
+           # the fused vector kernels move fewer bytes than the unfused loop SURVEY.md 8d counts:
+           # k_p: psi, pA read+write, rA (+rD | z) read; k_r: rA read+write, wA (+rD) read
+           "p_psi_update": (40 if dic else 48) * N, "r_update_dots": (24 if dic else 32) * N,
+           "flux": 16 * F + 8 * N,
+           # Eisenstat form, bytes MOVED by each kernel (DESIGN.md section 4): p^ update 44 N; r^ update 28 N
+           "eis_p_psi_update": 44 * N, "eis_r_update_rho": 28 * N}
+    kernels = {}
+    for k, v in prof.items():
+        ent = {"launches": v["launches"], "avg_us": v["avg_us"]}
+        if k in alg and v["avg_us"] > 0:
+            ent["alg_bytes"] = alg[k]
+            ent["gbs"] = alg[k] / (v["avg_us"] * 1e-6) / 1e9
+            ent["frac"] = ent["gbs"] / peak
+        kernels[k] = ent
+    if dic and "dic_fwd" in kernels and "dic_bwd" in kernels:
+        # one preconditioner apply = all forward + backward colour launches: 40N + 32F (SURVEY.md 8d)
+        napply = max(1, kernels["dic_bwd"]["launches"] // max(1, nColours - 1))
+        t_us = (prof["dic_fwd"]["total_ms"] + prof["dic_bwd"]["total_ms"]) * 1e3 / napply
+        ab = 40 * N + 32 * F
+        kernels["dic_apply"] = {"launches": napply, "avg_us": t_us, "alg_bytes": ab, "gbs": ab / (t_us * 1e-6) / 1e9,
+                                "frac": ab / (t_us * 1e-6) / 1e9 / peak}
+    if "eis_fwd_dot" in kernels:
+        # Eisenstat form: the backward + forward sweeps of one iteration replace Amul AND the preconditioner
+        # apply.  Roofline on the bytes the two sweeps MOVE (DESIGN.md section 4; ncu: 763 + 771 MB at 16 M hex
+        # cells = 96 N): every entry of the full-row ELL once per iteration (value 8 + column `col_bytes`, 2 F
+        # entries), 28 B of row streams per swept row (row length, p^ read, two vectors written; a sweep skips
+        # the colour that has no neighbours on its side: N (C-1)/C rows each) and one read of every gathered
+        # value (8 N).  Against SURVEY.md's UNFUSED figure for what the sweeps replace (64N + 48F) the number would
+        # exceed 1: that figure is reported as `replaces_alg_bytes`, not as a roofline fraction.
+        nit = max(1, kernels["eis_r_update_rho"]["launches"])
+        t_us = (prof["eis_fwd_dot"]["total_ms"] + prof.get("eis_bwd", {"total_ms": 0.0})["total_ms"]) * 1e3 / nit
+        C_ = max(2, nColours)
+        ab = int(2 * F * (8 + col_bytes) + 28 * 2 * N * (C_ - 1) / C_ + 8 * N)
+        kernels["eis_sweeps"] = {"launches": nit, "avg_us": t_us, "alg_bytes": ab, "gbs": ab / (t_us * 1e-6) / 1e9,
+                                 "frac": ab / (t_us * 1e-6) / 1e9 / peak, "bytes": "moved by the layout (DESIGN.md 4)",
+                                 "replaces_alg_bytes": 64 * N + 48 * F}
+    return kernels
+
+
+def col_bytes_of(ctx):
+    """bytes per column index the ELL-bound kernels read on the multicolour plan (16-bit offsets when every
+    slice entry fits, plan.hpp)"""
+    return 2 if ctx.describe().get("ell_col16_fraction_multicolour", 0.0) == 1.0 else 4
+
+
+def profiled_pass(res, ctl=None):
+    """one step with per-kernel CUDA events (outside every headline timed region)"""
+    res.ctx.profile(True)
+    perf = res.step(ctl)
+    prof = res.ctx.profile_json()
+    res.ctx.profile(False)
+    return prof, perf
+
+
+def mgpu_parity(env):
+    """N > 1: the N-rank path against the N-rank CPU oracle (emulated ranks, rank-ascending reductions) on a
+    reduced mesh with the SAME decomposition, run after the timed regions so that the driver's scaling runs
+    carry multi-GPU parity evidence (processor-patch halos over NCCL, fused peer-memory all-reduce):
+    Amul bit-exact, identical iteration counts for diagonal and DIC-exact, DIC-class within 1e-6."""
+    import numpy as np
+    from firefoam_dev_b200 import meshgen as mg
+    from oracle import oracle as orc
+    dist, pkg, n, rank = env.dist, env.pkg, env.n, env.rank
+    procs = PROCS[n]
+    dims = (24, 20, 16)
+    ctx = pkg.Context(device=env.local, rank=rank, nranks=n, nccl_uid=env.new_uid())
+    out = {"mesh": f"hex {dims[0]}x{dims[1]}x{dims[2]} hierarchical ({procs[0]} {procs[1]} {procs[2]}) + bcc_poly 2x10x10x12 RCB {n}-way",
+           "oracle": f"{n} emulated ranks (oracle/pcg_oracle.c)"}
+    try:
+        poly = mg.bcc_poly(10, 10, 12)
+        polysubs = mg.decompose(poly, mg.partition_rcb(poly.xyz, n), n)
+        for tag, subs_of in (("hex", lambda: [mg.hex_block(*dims, *procs, r) for r in range(n)]), ("poly", lambda: polysubs)):
+            subs = subs_of()
+            s = subs[rank]
+            ctx.set_addressing(s.addr)
+            x = np.random.default_rng(100 + rank).standard_normal(s.addr.nCells)
+            y = ctx.amul(s.matrix, s.bou, x)
+            gather = [None] * n
+            dist.all_gather_object(gather, (x, y))
+            if rank == 0:
+                ref = orc.amul(subs, [g[0] for g in gather])
+                out[tag + "_amul_bit_exact"] = bool(all(np.array_equal(ref[r], gather[r][1]) for r in range(n)))
+            for pre, mode in (("diagonal", None), ("DIC", "exact"), ("DIC", "auto")):
+                ctl = {"preconditioner": pre, "tolerance": 1e-8, "relTol": 0.0, "maxIter": 3000}
+                if mode:
+                    ctl["B200"] = {"dicMode": mode}
+                psi = np.zeros(s.addr.nCells)
+                perf = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, ctl, context=ctx).solve(psi, s.source)
+                allpsi = [None] * n
+                dist.all_gather_object(allpsi, psi)
+                if rank == 0:
+                    ref = [np.zeros(x_.addr.nCells) for x_ in subs]
+                    pr = orc.pcg_solve(subs, ref, pre, 1e-8, 0.0, 3000)
+                    err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
+                    key = f"{tag}_{pre}" + ("" if not mode else "_exact" if mode == "exact" else "_class")
+                    out[key] = {"iters": perf.nIterations, "oracle_iters": pr.nIterations, "relerr": float(err),
+                                "converged": bool(perf.converged)}
+        if rank == 0:
+            strict = [k for k in out if k.endswith("_diagonal") or k.endswith("_DIC_exact")]
+            out["iters_equal"] = bool(all(out[k]["iters"] == out[k]["oracle_iters"] for k in strict))
+            out["relerr"] = max(out[k]["relerr"] for k in strict)
+            out["amul_bit_exact"] = bool(out["hex_amul_bit_exact"] and out["poly_amul_bit_exact"])
+            out["dic_class_relerr"] = max(out[k]["relerr"] for k in out if k.endswith("_DIC_class"))
+            out["pass"] = bool(out["amul_bit_exact"] and out["iters_equal"] and out["relerr"] < 1e-11
+                               and out["dic_class_relerr"] < 1e-6)
+    finally:
+        ctx.close()
+    return out
+
+
+def dic_class_section(env, res, n_global):
+    """BASELINE configs[3]: the same mesh, `preconditioner DIC` (DIC-class multicolour IC0, Eisenstat form) to
+    the same tolerance; time-to-tolerance beside GDOF*iter/s (the iteration count differs from diagonal's)."""
+    ctl, _ = env.pkg.make_controls(sctl_for("DIC"))
+    res.step(ctl)
+    res.step(ctl)
+    ms, perfs = env.timed(lambda: res.step(ctl), 2)
+    iters = sum(p.nIterations for p in perfs)
+    prof, perf = profiled_pass(res, ctl)
+    kern = kernel_table(prof, res.N, res.F, env.peak, True, perf.nColours, col_bytes_of(res.ctx))
+    keep = {k: v for k, v in kern.items() if k.startswith("eis_") or k.startswith("dic_") or k in ("spmv_dot", "iface_fix")}
+    solve_ms = sum(p.solveMs for p in perfs) / 2
+    return {"preconditioner": "DIC (DIC-class: multicolour IC0, Eisenstat form; log name DIC(mc)B200PCG)",
+            "value": n_global * iters / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms / 2,
+            "iterations_per_step": iters // 2, "colours": perf.nColours, "converged": bool(perf.converged),
+            "time_to_tolerance_ms": solve_ms + sum(p.setupMs for p in perfs) / 2,
+            "us_per_iteration": 1e3 * solve_ms / max(1, iters // 2),
+            "max_err_vs_xstar": res.err(), "kernels": keep}
+
+
+def corrector_section(env, ctx, s):
+    """A real corrector is short: cases/steckler/original/linux64/log.fireFoam:220-223 runs 9-28 DICPCG
+    iterations per p_rgh solve (relTol 0.01 / p_rghFinal).  Here: `preconditioner DIC`, relTol 0.01, at most 20
+    iterations, on the full-size system, timed three ways through the C ABI: host page-locked arrays, host
+    PAGEABLE arrays (what OpenFOAM's fields are; staged through page-locked pieces), and device-resident
+    (b200_assemble_laplacian_device + b200_solve_device: no per-solve H2D at all)."""
+    import numpy as np
+    pkg = env.pkg
+    sctl = sctl_for("DIC", relTol=0.01, maxIter=19)
+    N, F = s.addr.nCells, s.addr.nFaces
+    out = {"controls": "preconditioner DIC; tolerance 1e-6; relTol 0.01; maxIter 19 (<= 20 loop bodies)"}
+    res = Resident(env, ctx, s, sctl)
+    res.step()
+    ms, perfs = env.timed(res.step, 3)
+    out["device_resident_ms"] = ms / 3
+    out["iterations"] = perfs[-1].nIterations
+    psi = env.pinned(N)
+    solver = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, sctl, context=ctx)
+
+    def host_step(mat_solver, psi_arr, src):
+        psi_arr[:] = 0.0
+        return mat_solver.solve(psi_arr, src)
+    host_step(solver, psi, s.source)
+    t0 = time.perf_counter()
+    pp = [host_step(solver, psi, s.source) for _ in range(3)]
+    out["host_pinned_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+    out["host_pinned_h2d_ms"], out["host_pinned_d2h_ms"] = pp[-1].h2dMs, pp[-1].d2hMs
+    # pageable copies of the same arrays
+    from firefoam_dev_b200.ldu import LduMatrix
+    pg = LduMatrix(s.addr, np.array(s.diag), np.array(s.upper))
+    src_pg, psi_pg = np.array(s.source), np.zeros(N)
+    solver_pg = pkg.B200PCG("p_rgh", pg, [np.array(b) for b in s.bou], None, s.interfaces, sctl, context=ctx)
+    host_step(solver_pg, psi_pg, src_pg)
+    t0 = time.perf_counter()
+    pq = [host_step(solver_pg, psi_pg, src_pg) for _ in range(3)]
+    out["host_pageable_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+    out["host_pageable_h2d_ms"], out["host_pageable_d2h_ms"] = pq[-1].h2dMs, pq[-1].d2hMs
+    h2d_bytes = 8 * (F + 3 * N)
+    out["h2d_bytes"] = h2d_bytes
+    out["host_pageable_h2d_gbs"] = h2d_bytes / (pq[-1].h2dMs * 1e-3) / 1e9 if pq[-1].h2dMs > 0 else None
+    out["pageable_over_device"] = out["host_pageable_ms"] / out["device_resident_ms"]
+    out["note"] = ("the host routes are bound by the PCIe copy of the matrix (upper: 8 F bytes) every solve; the "
+                   "device-assembly route (b200_assemble_laplacian_device / b200_assemble_p_rgh_device) keeps it in HBM")
+    return out
+
+
+def strong_base_section(env):
+    """N = 8 weak run == BASELINE configs[3]'s 128 M mesh: rank 0 alone runs the SAME mesh on one GPU for a
+    fixed 200 iterations, so that the strong-scaling speed-up 1 -> 8 is verifiable from this line."""
+    from firefoam_dev_b200 import meshgen as mg
+    pkg = env.pkg
+    out = None
+    if env.rank == 0:
+        t0 = time.time()
+        s = mg.hex_block(*STRONG_DIMS)
+        ctx = pkg.Context(device=env.local)
+        try:
+            ctx.set_addressing(s.addr)
+            res = Resident(env, ctx, s, sctl_for("diagonal"))
+            ctx.force_iterations(200)
+            res.step()
+            e0, e1 = env.torch.cuda.Event(enable_timing=True), env.torch.cuda.Event(enable_timing=True)
+            env.torch.cuda.synchronize()
+            e0.record()
+            p = res.step()
+            e1.record()
+            env.torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            out = {"mesh": "hex 512x500x500 on ONE GPU (rank 0 alone)", "iters": p.nIterations, "ms": ms,
+                   "solve_ms": p.solveMs, "us_per_iteration": 1e3 * p.solveMs / max(1, p.nIterations),
+                   "gdof_iter_per_s": 128e6 * p.nIterations / (ms * 1e-3) / 1e9, "host_s": time.time() - t0}
+        finally:
+            ctx.close()
+        del s
+    env.barrier()
+    return out
+
+
+def run_gpu(args):
+    import numpy as np
+    env = Env(args)
+    torch, dist, pkg, n, rank = env.torch, env.dist, env.pkg, env.n, env.rank
+    extras = set(args.extras.split(",")) if args.extras not in ("auto", "none") else set()
+    default_run = (args.workload == "hex" and args.scaling == "weak" and args.precond == "diagonal")
+    if args.extras == "auto":
+        extras = {"mgpu_parity"}
+        if default_run:
+            extras |= {"dic_class"}
+            if n == 1:
+                extras.add("corrector")
+            if n == 8 and not args.block:
+                extras |= {"strong_base", "poly"}
+
+    s, n_global, gen_s = make_system(args, n, rank, pinned=env.pinned, dist=dist)
     if args.workload != "hex":       # generators without a pinned allocator: page-lock what e2e reads
-        s.diag, s.upper, s.source = to_pinned(s.diag), to_pinned(s.upper), to_pinned(s.source)
-        s.bou = [to_pinned(b) for b in s.bou]
+        s.diag, s.upper, s.source = env.to_pinned(s.diag), env.to_pinned(s.upper), env.to_pinned(s.source)
+        s.bou = [env.to_pinned(b) for b in s.bou]
     a = s.addr
     N, F = a.nCells, a.nFaces
-    ctx = pkg.Context(device=local_rank, rank=rank, nranks=n, nccl_uid=uid)
+    ctx = pkg.Context(device=env.local, rank=rank, nranks=n, nccl_uid=env.uid)
     t0 = time.time()
     ctx.set_addressing(a)
     setaddr_s = time.time() - t0
-    sctl = {"preconditioner": "DIC" if args.precond.startswith("DIC") else args.precond, "tolerance": TOL,
-            "relTol": 0.0, "maxIter": MAXITER,
-            "B200": {"dicMode": {"DIC-exact": "exact", "DIC-eisenstat": "eisenstat"}.get(args.precond, "multicolour")}}
-    ctl, _ = pkg.make_controls(sctl)
-
-    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-    d_gamma, d_magSf, d_delta = up(s.gamma_f), up(s.magSf), up(s.deltaCoeffs)
-    d_diag0, d_src = up(s.diag0), up(s.source)
-    d_bou = [up(b) for b in s.bou]
-    d_diag = torch.empty(N, dtype=torch.float64, device=dev)
-    d_upper = torch.empty(F, dtype=torch.float64, device=dev)
-    d_psi = torch.zeros(N, dtype=torch.float64, device=dev)
-    small = N * 200 < 126e6          # whole system L2-resident: flush between timed steps
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
-
-    def step_device():
-        # assemble: - fvm::laplacian(rhorAUf, p_rgh) on top of the ddt/boundary diagonal
-        d_diag.copy_(d_diag0)
-        d_psi.zero_()
-        if flush is not None:
-            flush.zero_()
-        torch.cuda.current_stream().synchronize()
-        ctx.assemble_laplacian_device(d_gamma, d_magSf, d_delta, s.sign, d_upper, d_diag)
-        return ctx.solve_device(d_diag, d_upper, d_bou, d_src, d_psi, ctl)
+    sctl = sctl_for(args.precond)
+    res = Resident(env, ctx, s, sctl)
 
     for _ in range(args.warmup):
-        perf = step_device()
-    # ---- timed: device-resident ------------------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    ctx.profile(True)
-    barrier()
+        perf = res.step()
+    # ---- timed: device-resident; per-kernel profiling is OFF here (its event records sit between the kernels)
+    clocks = ClockSampler(env.local)
     if rank == 0:
         clocks.start()
     l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    iters = 0
-    solve_ms = setup_ms = 0.0
-    for _ in range(args.steps):
-        perf = step_device()
-        iters += perf.nIterations
-        solve_ms += perf.solveMs
-        setup_ms += perf.setupMs
-    e1.record()
-    barrier()
+    ms, perfs = env.timed(res.step, args.steps)
     launches = ctx.launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if n > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
     clk = clocks.stop() if rank == 0 else None
-    prof = ctx.profile_json()
-    ctx.profile(False)
+    perf = perfs[-1]
+    iters = sum(p.nIterations for p in perfs)
+    solve_ms = sum(p.solveMs for p in perfs)
+    setup_ms = sum(p.setupMs for p in perfs)
     converged = bool(perf.converged)
-    err = float(np.abs(d_psi.cpu().numpy() - s.xstar).max()) if s.xstar is not None else None
+    err = res.err()
     value = n_global * iters / (ms * 1e-3) / 1e9
 
     # ---- e2e: the reference-facing plug-in call with pinned host buffers ------------------------
-    psi_h = pinned(N, np.float64)
+    psi_h = env.pinned(N)
     src_h = s.source
     solver = pkg.B200PCG("p_rgh", s.matrix, s.bou, None, s.interfaces, sctl, context=ctx)
     psi_h[:] = 0.0
     solver.solve(psi_h, src_h)                          # warm-up (allocates staging)
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     e_iters = 0
     h2d_ms = d2h_ms = 0.0
@@ -423,100 +710,108 @@ def run_gpu(args):
         e_iters += p.nIterations
         h2d_ms += p.h2dMs
         d2h_ms += p.d2hMs
-    barrier()
-    e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if n > 1:
-        dist.all_reduce(e_s, op=dist.ReduceOp.MAX)
-    e_s = float(e_s.item())
+    env.barrier()
+    e_s = env.max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_global * e_iters / e_s / 1e9
     nslots = sum(b.size for b in s.bou)
     h2d_bytes = 8 * (F + 3 * N + nslots)
     d2h_bytes = 8 * N
     e2e_err = float(np.abs(psi_h - s.xstar).max()) if s.xstar is not None else None
 
+    # ---- profiled pass (separate from every timed region): per-kernel table + roofline of the dominant kernel
+    prof, pperf = profiled_pass(res)
+    dic = args.precond.startswith("DIC")
+    kernels = kernel_table(prof, N, F, env.peak, dic, perf.nColours, col_bytes_of(ctx))
+
     # ---- fixed 200-iteration timing -------------------------------------
     ctx.force_iterations(200)
-    step_device()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    pf = step_device()
-    f1.record()
-    barrier()
+    res.step()
+    fixed_ms, pfs = env.timed(res.step, 1)
+    pf = pfs[0]
     ctx.force_iterations(0)
-    fixed_ms = f0.elapsed_time(f1)
     desc = ctx.describe()
+    slots_all = [nslots]
+    if n > 1:
+        slots_all = [None] * n
+        dist.all_gather_object(slots_all, nslots)
+
+    sections = {}
+    if "dic_class" in extras:
+        sections["dic_class"] = dic_class_section(env, res, n_global)
+    if "corrector" in extras and n == 1:
+        sections["corrector"] = corrector_section(env, ctx, s)
+    if "mgpu_parity" in extras and n > 1:
+        sections["mgpu_parity"] = mgpu_parity(env)
+    if "strong_base" in extras and n > 1:
+        sections["strong_base_1gpu"] = strong_base_section(env)
+    if "poly" in extras and n > 1:
+        sections["poly"] = poly_section(env, args)
 
     if rank != 0:
         if n > 1:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak()
-    dic = args.precond.startswith("DIC")
-    alg = {"spmv_dot": 24 * N + 16 * F, "precond_dot": 24 * N,
-           "asm_face_coeff": 32 * F, "asm_neg_sum_diag": 16 * N + 16 * F,
-           # the fused vector kernels move fewer bytes than the unfused loop SURVEY.md 8d counts:
-           # k_p: psi, pA read+write, rA (+rD | z) read; k_r: rA read+write, wA (+rD) read
-           "p_psi_update": (40 if dic else 48) * N, "r_update_dots": (24 if dic else 32) * N,
-           "flux": 16 * F + 8 * N}
-    kernels = {}
-    for k, v in prof.items():
-        ent = {"launches": v["launches"], "avg_us": v["avg_us"]}
-        if k in alg:
-            ent["alg_bytes"] = alg[k]
-            ent["gbs"] = alg[k] / (v["avg_us"] * 1e-6) / 1e9
-            ent["frac"] = ent["gbs"] / peak
-        kernels[k] = ent
-    if dic and "dic_fwd" in kernels and "dic_bwd" in kernels:
-        # one preconditioner apply = all forward + backward colour launches: 40N + 32F
-        napply = max(1, kernels["dic_bwd"]["launches"] // max(1, perf.nColours - 1))
-        t_us = (prof["dic_fwd"]["total_ms"] + prof["dic_bwd"]["total_ms"]) * 1e3 / napply
-        kernels["dic_apply"] = {"launches": napply, "avg_us": t_us, "alg_bytes": 40 * N + 32 * F,
-                                "gbs": (40 * N + 32 * F) / (t_us * 1e-6) / 1e9,
-                                "frac": (40 * N + 32 * F) / (t_us * 1e-6) / 1e9 / peak}
+    peak, peak_src = env.peak, env.peak_src
     dom = kernels.get("spmv_dot", {})
-    eis = "eis_fwd_dot" in kernels
+    eis = "eis_sweeps" in kernels
     if eis:
-        # Eisenstat form: per iteration the backward + forward sweeps do the work of Amul AND the
-        # preconditioner apply: (24N + 16F) + (40N + 32F) algorithmic bytes, one entry
-        nit = max(1, kernels["eis_r_update_rho"]["launches"])
-        t_us = (prof["eis_fwd_dot"]["total_ms"] + prof.get("eis_bwd", {"total_ms": 0.0})["total_ms"]) * 1e3 / nit
-        ab = 64 * N + 48 * F
-        kernels["eis_sweeps"] = {"launches": nit, "avg_us": t_us, "alg_bytes": ab, "gbs": ab / (t_us * 1e-6) / 1e9,
-                                 "frac": ab / (t_us * 1e-6) / 1e9 / peak}
         dom = kernels["eis_sweeps"]
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
             tj = json.load(f)
             if tj.get("cells") == N and tj.get("kernel", "").split("<")[0] == desc.get("amul_natural", "").split("<")[0] \
                     and not dic:
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "static: " + tj.get("source", "ncu --set full capture of this kernel at this size (profiles/)")
     except Exception:
         pass
-    # algorithmic bytes of one PCG iteration: diagonal 120N+16F, DIC-class 136N+48F
-    iter_bytes = (136 * N + 48 * F) if dic else (120 * N + 16 * F)
+    iters_per_step = max(1, iters // args.steps)
+    iter_us = 1e3 * solve_ms / max(iters, 1)
+    # bytes one PCG iteration has to move.  SURVEY.md 8d counts the UNFUSED loop (diagonal 120N+16F, DIC-class
+    # 136N+48F); the fused loops move fewer, so both are given: `frac` is on bytes moved (<= 1 by construction),
+    # `frac_of_unfused_alg` relates the time to the SURVEY figure and may exceed 1
+    unfused = (136 * N + 48 * F) if dic else (120 * N + 16 * F)
+    if eis:
+        moved = kernels["eis_sweeps"]["alg_bytes"] + 44 * N + 28 * N
+    elif dic:
+        moved = (24 * N + 24 * F + 4 * N) + (40 * N + 32 * F) + 40 * N + 24 * N
+    else:
+        moved = (24 * N + 16 * F + 4 * N) + 48 * N + 32 * N
+    compute_us = sum(kernels[k]["avg_us"] * kernels[k]["launches"] for k in kernels
+                     if k in ("spmv_dot", "p_psi_update", "r_update_dots", "dic_fwd", "dic_bwd", "eis_p_psi_update",
+                              "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual")) / max(1, pperf.nIterations)
     amul_kernel = desc.get("amul_permuted" if dic else "amul_natural", "?")
-    dom_name = (f"k_eis_bwd + k_eis_fwd per iteration (Eisenstat form: lduMatrix::Amul + DIC-class apply in two sweeps, "
-                f"fused with gSumProd(wA,pA))" if eis else f"{amul_kernel} (lduMatrix::Amul fused with gSumProd(wA,pA))")
+    dom_name = ("k_eis_bwd + k_eis_fwd per iteration (Eisenstat form: lduMatrix::Amul + DIC-class apply in two sweeps, "
+                "fused with gSumProd(wA,pA))" if eis else f"{amul_kernel} (lduMatrix::Amul fused with gSumProd(wA,pA))")
     line = {
         "metric": METRIC.replace("diagonal", args.precond), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(config_dict(args, n), colours=perf.nColours, cells_this_rank=N, faces_this_rank=F,
-                       halo_slots_this_rank=nslots),
+                       halo_slots_this_rank=nslots, halo_faces_per_rank=slots_all,
+                       edge_cut_faces=sum(slots_all) // 2),
         "iterations_per_step": iters // args.steps, "converged": converged, "max_err_vs_xstar": err,
         "solve_ms_per_step": solve_ms / args.steps, "setup_ms_per_step": setup_ms / args.steps,
-        "pcg_iteration": {"avg_us": 1e3 * solve_ms / max(iters, 1), "alg_bytes": iter_bytes,
-                          "gbs": iter_bytes / (1e-3 * solve_ms / max(iters, 1)) / 1e9,
-                          "frac": iter_bytes / (1e-3 * solve_ms / max(iters, 1)) / 1e9 / peak},
+        "time_to_tolerance_ms": (solve_ms + setup_ms) / args.steps,
+        "pcg_iteration": {"avg_us": iter_us, "bytes_moved": moved, "gbs": moved / (1e-6 * iter_us) / 1e9,
+                          "frac": moved / (1e-6 * iter_us) / 1e9 / peak, "unfused_alg_bytes": unfused,
+                          "frac_of_unfused_alg": unfused / (1e-6 * iter_us) / 1e9 / peak,
+                          "kernel_sum_us": compute_us,
+                          "non_kernel_us": iter_us - compute_us,
+                          "note": "avg_us from the UNPROFILED timed region; kernel_sum_us from the profiled pass "
+                                  "(compute kernels only; at N > 1 non_kernel_us = exposed halo / reduction / "
+                                  "launch time per iteration)"},
         "fixed_200_iterations": {"ms": fixed_ms, "iters": pf.nIterations,
-                                 "gdof_iter_per_s": n_global * pf.nIterations / (fixed_ms * 1e-3) / 1e9},
+                                 "gdof_iter_per_s": n_global * pf.nIterations / (fixed_ms * 1e-3) / 1e9,
+                                 "us_per_iteration": 1e3 * pf.solveMs / max(1, pf.nIterations)},
         "roofline": {"kernel": dom_name,
                      "bound": "hbm", "achieved": dom.get("gbs"), "peak": peak, "unit": "GB/s",
-                     "frac": dom.get("frac"), "traffic": traffic, "peak_source": peak_src,
-                     "alg_bytes_per_launch": dom.get("alg_bytes"), "avg_us": dom.get("avg_us")},
+                     "frac": dom.get("frac"), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "alg_bytes_per_launch": dom.get("alg_bytes"), "avg_us": dom.get("avg_us"),
+                     "timing": "CUDA events on the library's stream around each launch, in a profiled pass outside the "
+                               "timed region; launches of surplus loop bodies (returned on S->done) excluded"},
         "kernels": kernels, "plan": desc,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e_s / args.steps,
@@ -526,6 +821,14 @@ def run_gpu(args):
         "gpu_launches": launches, "clocks": clk,
         "host": {"gen_s": gen_s, "set_addressing_s": setaddr_s},
     }
+    if n > 1:
+        line["exposed_comm_us"] = iter_us - compute_us
+    line.update(sections)
+    if sections.get("strong_base_1gpu"):
+        sb = sections["strong_base_1gpu"]
+        line["strong_scaling_1_to_%d" % n] = {
+            "speedup": sb["us_per_iteration"] / (1e3 * pf.solveMs / max(1, pf.nIterations)),
+            "basis": "fixed 200 PCG+diagonal iterations of the 128 M-cell mesh: us per iteration on 1 GPU / on %d GPUs" % n}
     if n == 1 and not args.no_cpu_baseline:
         leg = cpu_leg(args, seconds=args.cpu_seconds)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -535,6 +838,38 @@ def run_gpu(args):
     if n > 1:
         dist.destroy_process_group()
     return 0
+
+
+def poly_section(env, args):
+    """BASELINE configs[4] inside the N = 8 line: the 40 M-cell polyhedral mesh, RCB N-way, PCG + DIC-class and
+    PCG + diagonal to tolerance, with the per-kernel roofline fractions."""
+    import copy
+    pa = copy.copy(args)
+    pa.workload, pa.scaling, pa.precond = "poly", "strong", "DIC"
+    t0 = time.time()
+    s, n_global, gen_s = make_system(pa, env.n, env.rank, pinned=env.pinned, dist=env.dist)
+    ctx = env.pkg.Context(device=env.local, rank=env.rank, nranks=env.n, nccl_uid=env.new_uid())
+    out = {"config": config_dict(pa, env.n)}
+    try:
+        ctx.set_addressing(s.addr)
+        for pre in ("DIC", "diagonal"):
+            res = Resident(env, ctx, s, sctl_for(pre))
+            res.step()
+            ms, perfs = env.timed(res.step, 2)
+            iters = sum(p.nIterations for p in perfs)
+            prof, perf = profiled_pass(res)
+            kern = kernel_table(prof, res.N, res.F, env.peak, pre == "DIC", perf.nColours, col_bytes_of(ctx))
+            out[pre] = {"value": n_global * iters / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms / 2,
+                        "iterations_per_step": iters // 2, "converged": bool(perf.converged), "colours": perf.nColours,
+                        "us_per_iteration": 1e3 * sum(p.solveMs for p in perfs) / max(1, iters),
+                        "max_err_vs_xstar": res.err(),
+                        "kernels": {k: v for k, v in kern.items() if "frac" in v or k in ("iface_fix", "eis_bwd", "eis_fwd_dot")}}
+            del res
+        out["plan"] = ctx.describe()
+        out["host_s"] = time.time() - t0
+    finally:
+        ctx.close()
+    return out
 
 
 def main():
@@ -551,7 +886,12 @@ def main():
     ap.add_argument("--poly", type=int, nargs=3, default=list(POLY_LATTICE), help="BCC lattice of --workload poly")
     ap.add_argument("--poly-cache", default=None,
                     help="directory in which the decomposed --workload poly sub-meshes are kept between runs")
-    ap.add_argument("--precond", default=PRECOND, choices=["none", "diagonal", "DIC", "DIC-exact", "DIC-eisenstat"])
+    ap.add_argument("--precond", default=PRECOND,
+                    choices=["none", "diagonal", "DIC", "DIC-exact", "DIC-eisenstat", "DIC-multicolour"])
+    ap.add_argument("--extras", default="auto",
+                    help="extra sections of the JSON line: auto | none | comma list of dic_class,corrector,mgpu_parity,"
+                         "strong_base,poly.  auto: mgpu_parity at N > 1; on the default workload also dic_class "
+                         "(configs[3]'s preconditioner), corrector at N = 1, strong_base + poly (configs[4]) at N = 8")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

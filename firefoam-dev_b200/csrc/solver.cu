@@ -126,6 +126,12 @@ struct DevPlan {
     int* rowB = nullptr;
     double* hb = nullptr;
     int nB0 = 0;                  // interface rows of the first colour: bRow[0 .. nB0) (bRow is ascending)
+    // CUDA graphs of kGraphIters loop bodies, by loop form (0 none, 1 diagonal, 2 DIC-class loop, 3 Eisenstat):
+    // kernel arguments are the context's own buffers and the CG scalars live on the device, so one capture
+    // serves every later solve on this plan
+    cudaGraphExec_t iterGraph[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t iterGraphLaunches[4] = {0, 0, 0, 0};
+    bool iterGraphFailed[4] = {false, false, false, false};
 };
 
 struct HostIface {
@@ -180,6 +186,7 @@ struct b200_ctx {
     Scalars* hS = nullptr;  // pinned
     double* partials = nullptr;
     uint64_t launches = 0;
+    uint64_t graphLaunches = 0;     // cudaGraphLaunch calls (each replays kGraphIters loop bodies)
     int32_t forceIters = 0;
     // bulk-copy pipeline depth / CTAs per SM (B200PCG_STAGES, B200PCG_CTAS).  Measured on the 16 M hex
     // box (profiles/r01_tma_sweep.md): 2 stages x 4 CTAs/SM is the optimum -- deeper pipelines or more
@@ -218,12 +225,15 @@ struct b200_ctx {
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
     // profiling
+    bool useGraph = true;       // B200PCG_GRAPH=0: enqueue every loop body kernel by kernel
     bool prof = false;
     bool profOpen = false;
-    struct ProfRec { int cls; cudaEvent_t a, b; };
+    struct ProfRec { int cls; int iter; cudaEvent_t a, b; };
+    int profIter = 0;            // loop body being enqueued (0: set-up / tail); see prof_collect
     std::vector<ProfRec> profRecs;
     std::vector<cudaEvent_t> profPool;
     size_t profUsed = 0;
+    uint64_t profSkipped = 0;    // launches of surplus iterations (returned on S->done), excluded from the averages
     double profMs[PC_COUNT] = {};
     uint64_t profN[PC_COUNT] = {};
     std::string profJson;
@@ -278,7 +288,7 @@ void prof_begin(b200_ctx* c, int cls) {
     c->profOpen = false;
     if (!c->prof || c->profUsed + 2 > c->profPool.size()) return;
     c->profOpen = true;
-    b200_ctx::ProfRec r{cls, c->profPool[c->profUsed], c->profPool[c->profUsed + 1]};
+    b200_ctx::ProfRec r{cls, c->profIter, c->profPool[c->profUsed], c->profPool[c->profUsed + 1]};
     c->profUsed += 2;
     cudaEventRecord(r.a, c->sc);
     c->profRecs.push_back(r);
@@ -289,10 +299,13 @@ void prof_end(b200_ctx* c, int cls) {
     auto& r = c->profRecs.back();
     if (r.cls == cls && r.b) cudaEventRecord(r.b, c->sc);
 }
-void prof_collect(b200_ctx* c) {
+// nIterDone: loop bodies the device actually executed.  The host enqueues iterations in batches and the
+// kernels of the surplus ones return at once on S->done: those launches are NOT part of the averages.
+void prof_collect(b200_ctx* c, int nIterDone = 0x7fffffff) {
     if (!c->prof) return;
     cudaStreamSynchronize(c->sc);
     for (auto& r : c->profRecs) {
+        if (r.iter > nIterDone) { c->profSkipped++; continue; }
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
             c->profMs[r.cls] += ms;
@@ -321,6 +334,11 @@ inline int grid_for(const b200_ctx* c, int64_t items, int perSM = 8) {
 }
 
 void free_plan(DevPlan& P) {
+    for (int m = 0; m < 4; ++m) {
+        if (P.iterGraph[m]) cudaGraphExecDestroy(P.iterGraph[m]);
+        P.iterGraph[m] = nullptr;
+        P.iterGraphFailed[m] = false;
+    }
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
     dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
@@ -1005,6 +1023,8 @@ int copy_bou(b200_ctx* ctx, DevPlan& P, const double* const* bouPtrs, cudaMemcpy
     return B200_OK;
 }
 
+constexpr int kGraphIters = 4;   // loop bodies per iteration graph (= the first batch size of the loop)
+
 Ordering ordering_for(int precond) {
     if (precond == B200_PRECOND_DIC_MC || precond == B200_PRECOND_DIC_MC_EIS || precond == B200_PRECOND_DIC_MC_LOOP)
         return Ordering::MultiColour;
@@ -1176,17 +1196,51 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         return solve_core(ctx, dn_diag, dn_upper, dn_src, dn_psi, ctl, perf, true);
     }
 
-    // PCG loop: batches of iterations, device decides when to stop
+    // PCG loop: batches of iterations, device decides when to stop.  A batch is replayed from a CUDA graph of
+    // kGraphIters loop bodies (captured once per plan and loop form, NCCL halo exchange included) unless
+    // per-kernel profiling is on; the remainder of a batch is enqueued kernel by kernel.
     int64_t cap = ctx->forceIters > 0 ? ctx->forceIters
                                       : std::max<int64_t>((int64_t)ctl->maxIter + 1, ctl->minIter);
     int64_t enq = 0;
     int chunk = 4;
+    const int form = eis ? 3 : std::min(precond, 2);
+    auto body = [&]() -> int { return eis ? enqueue_eis_iteration(ctx, P) : enqueue_iteration(ctx, P, precond); };
     while (!ctx->hS->done && enq < cap) {
         int n = (int)std::min<int64_t>(chunk, cap - enq);
-        for (int i = 0; i < n; ++i) {
-            if (eis) RET(enqueue_eis_iteration(ctx, P));
-            else RET(enqueue_iteration(ctx, P, precond));
+        int i = 0;
+        if (ctx->useGraph && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
+            if (!P.iterGraph[form] && n >= kGraphIters) {
+                const uint64_t l0 = ctx->launches;
+                cudaGraph_t g = nullptr;
+                int rcB = B200_OK;
+                cudaError_t e = cudaStreamBeginCapture(ctx->sc, cudaStreamCaptureModeThreadLocal);
+                if (e == cudaSuccess) {
+                    for (int k = 0; k < kGraphIters && rcB == B200_OK; ++k) rcB = body();
+                    e = cudaStreamEndCapture(ctx->sc, &g);
+                }
+                if (e == cudaSuccess && rcB == B200_OK) e = cudaGraphInstantiate(&P.iterGraph[form], g, 0);
+                if (g) cudaGraphDestroy(g);
+                P.iterGraphLaunches[form] = ctx->launches - l0;
+                ctx->launches = l0;                          // nothing ran during the capture
+                if (e != cudaSuccess || rcB != B200_OK) {    // not fatal: this plan keeps the plain enqueue
+                    cudaGetLastError();
+                    P.iterGraph[form] = nullptr;
+                    P.iterGraphFailed[form] = true;
+                }
+            }
+            if (P.iterGraph[form]) {
+                for (; i + kGraphIters <= n; i += kGraphIters) {
+                    CU(cudaGraphLaunch(P.iterGraph[form], ctx->sc));
+                    ctx->launches += P.iterGraphLaunches[form];
+                    ctx->graphLaunches++;
+                }
+            }
         }
+        for (; i < n; ++i) {
+            ctx->profIter = (int)(enq + i + 1);
+            RET(body());
+        }
+        ctx->profIter = 0;
         enq += n;
         CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
         CU(cudaStreamSynchronize(ctx->sc));
@@ -1199,7 +1253,7 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
-    prof_collect(ctx);
+    prof_collect(ctx, ctx->hS->nIter);
 
     return finish_solve(ctx, P, perf);
 }
@@ -1467,6 +1521,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         c->sweepPerSMSet = true;
     }
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
+    if (const char* e23 = getenv("B200PCG_GRAPH")) c->useGraph = atoi(e23) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
     if (const char* e5 = getenv("B200PCG_RUN")) c->winRun = std::max(1, std::min(4096, atoi(e5)));
@@ -1909,6 +1964,7 @@ int b200_profile_enable(b200_ctx* ctx, int on) {
     if (on) {
         std::memset(ctx->profMs, 0, sizeof(ctx->profMs));
         std::memset(ctx->profN, 0, sizeof(ctx->profN));
+        ctx->profSkipped = 0;
         ctx->profRecs.clear();
         ctx->profUsed = 0;
     }
@@ -1927,6 +1983,12 @@ const char* b200_profile_json(b200_ctx* ctx) {
                       ctx->profMs[i], 1e3 * ctx->profMs[i] / (double)ctx->profN[i]);
         s += buf;
         first = false;
+    }
+    if (ctx->profSkipped) {
+        // launches of surplus loop bodies (enqueued in batches, returned at once on S->done): not in the averages
+        std::snprintf(buf, sizeof(buf), "%s\"_skipped_noop_launches\": {\"launches\": %llu, \"total_ms\": 0.0, \"avg_us\": 0.0}",
+                      first ? "" : ", ", (unsigned long long)ctx->profSkipped);
+        s += buf;
     }
     s += "}";
     ctx->profJson = s;
@@ -1950,14 +2012,16 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
                   "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d, "
                   "\"multicolour_tiles\": %d, \"multicolour_tile_rows\": %d, \"multicolour_amul\": \"%s\", "
-                  "\"ell_col16_fraction_natural\": %.3f, \"ell_col16_fraction_multicolour\": %.3f}",
+                  "\"ell_col16_fraction_natural\": %.3f, \"ell_col16_fraction_multicolour\": %.3f, "
+                  "\"iteration_graphs\": %s, \"graph_iterations\": %d, \"graph_launches\": %llu}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
                   P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN,
                   ctx->plans[1].built ? ctx->plans[1].h.nTiles : 0, ctx->plans[1].built ? ctx->plans[1].h.tileRows : 0,
                   !ctx->plans[1].built ? "n/a" : (ctx->plans[1].sym ? (ctx->plans[1].symTma ? "k_spmv_sym_tma" : "k_spmv_sym") : "k_spmv"),
-                  P.c16 ? P.h.col16Fraction : 0.0, ctx->plans[1].c16 ? ctx->plans[1].h.col16Fraction : 0.0);
+                  P.c16 ? P.h.col16Fraction : 0.0, ctx->plans[1].c16 ? ctx->plans[1].h.col16Fraction : 0.0,
+                  ctx->useGraph ? "true" : "false", kGraphIters, (unsigned long long)ctx->graphLaunches);
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

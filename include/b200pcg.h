@@ -28,8 +28,8 @@
  *   - non-convergence within maxIter and singularity are NOT errors; they are reported in
  *     b200_perf exactly like OpenFOAM's SolverPerformance.
  */
-#ifndef B200PCG_H
-#define B200PCG_H
+#ifndef B200PCG_C_ABI_H
+#define B200PCG_C_ABI_H
 
 #include <stdint.h>
 #include <stddef.h>
@@ -279,4 +279,4 @@ const char* b200_dump_last_error(void);
 #ifdef __cplusplus
 }
 #endif
-#endif /* B200PCG_H */
+#endif /* B200PCG_C_ABI_H */
