@@ -172,3 +172,70 @@ def steckler_p_rgh_system(seed=1711, psi=1.17e-5, dt=0.0667):
     np.add.at(source, u, upper * xstar[l])
     np.add.at(source, l, upper * xstar[u])
     return System(a, diag, upper, source, [], xstar, gamma_f, magSf, delta, diag0, -1.0)
+
+
+def boundary_faces(case):
+    """faceCells of every boundary face of a HydrostaticBox mesh (domain boundary + both sides of the
+    baffles), as (cells, direction 0..2, deltaCoeffs_b, magSf_b), grouped direction by direction like
+    patches."""
+    nx, ny, nz = case.dims
+    i, j, k = case.ijk
+    a = case.addr
+    N = case.N
+    strides = (1, nx, nx * ny)
+    have = set(zip(a.lowerAddr.tolist(), a.upperAddr.tolist()))
+    cells, dirs = [], []
+    for d, st in enumerate(strides):
+        c = np.arange(N)
+        up_missing = np.array([(cc, cc + st) not in have for cc in c.tolist()])
+        lo_missing = np.array([(cc - st, cc) not in have for cc in c.tolist()])
+        for miss in (lo_missing, up_missing):
+            cs = c[miss]
+            cells.append(cs)
+            dirs.append(np.full(cs.size, d))
+    cells, dirs = np.concatenate(cells).astype(np.int32), np.concatenate(dirs)
+    dist = np.array(case.d)[dirs]
+    area = np.array((case.d[1] * case.d[2], case.d[0] * case.d[2], case.d[0] * case.d[1]))[dirs]
+    return cells, dirs, 2.0 / dist, area
+
+
+def p1_G_terms(seed=238, case=None):
+    """The P1 radiation model's G equation on the steckler topology, as the reference assembles it at
+    packages/thermophysicalModels/radiation/radiationModels/P1/P1.C:238-244
+        fvm::laplacian(gamma, G) - fvm::Sp(a, G) == - 4 e sigma T^4 - E,   gamma = 1/(3 a + 3 sigmaEff + a0)
+    and solves it with `G { solver PCG; preconditioner DIC; tolerance 1e-06; relTol 0; }`
+    (cases/steckler/system/fvSolution:75-81): the reference's OTHER symmetric lduMatrix system besides p_rgh
+    (SURVEY.md 8f-4).  Expressed in the term slots of b200_assemble_p_rgh / orc_assemble_p_rgh -- the fvMatrix
+    algebra is the same: fvm::Sp(a, G) puts V*a on the diagonal exactly where EulerDdtScheme puts
+    rDeltaT*psi*V, so `- fvm::Sp(a, G)` is the ddt slot with rDeltaT = -1, psi = a, psi0 = 0; the volScalarField
+    right-hand side is the Su slot; fvm::laplacian(volScalarField gamma, G) interpolates gamma linearly to the
+    faces (0.5/0.5 on this uniform mesh); every wall carries a MarshakRadiation (mixed) condition:
+        valueFraction = 1/(1 + gamma_b deltaCoeffs_b / Ep),  Ep = emissivity/(2 (2 - emissivity)),  refValue = 4 sigma T_w^4
+        internalCoeffs = -gamma_b magSf valueFraction deltaCoeffs_b,  boundaryCoeffs = internalCoeffs * refValue.
+    Synthetic but physically scaled fields: a = e in [0.05, 0.6] 1/m (sooty layer under the ceiling), T between 298
+    and 1100 K (plume over the burner).  Returns (case, terms)."""
+    case = case or StecklerHydrostatic()
+    a_ = case.addr
+    N, F = case.N, case.F
+    i, j, k = case.ijk
+    h = case.H if hasattr(case, "H") else case.d[0]
+    x, y, z = (i + 0.5) * h - 2.0, (j + 0.5) * h, (k + 0.5) * h - 2.0
+    r2 = x * x + z * z
+    T = 298.15 + 800.0 * np.exp(-r2 / 0.18) * np.exp(-y / 1.6) + 150.0 * (y > 1.6) * (np.abs(x) < 1.4) * (np.abs(z) < 1.4)
+    absorb = 0.05 + 0.55 * np.clip((T - 298.15) / 800.0, 0.0, 1.0) + 0.01 * uniform_pm1(seed, np.arange(N))
+    sigmaSB = 5.670367e-08
+    gamma_c = 1.0 / (3.0 * absorb)
+    l, u = a_.lowerAddr, a_.upperAddr
+    gamma_f = 0.5 * (gamma_c[l] - gamma_c[u]) + gamma_c[u]          # surfaceInterpolationScheme::interpolate, lambda = 0.5
+    bCells, bDir, bDelta, bArea = boundary_faces(case)
+    emissivity = 0.9
+    Ep = emissivity / (2.0 * (2.0 - emissivity))
+    gamma_b = gamma_c[bCells]                                       # zeroGradient-like patch value of gamma
+    vf = 1.0 / (1.0 + gamma_b * bDelta / Ep)
+    bInt = -(gamma_b * bArea) * (vf * bDelta)
+    refValue = 4.0 * sigmaSB * 298.15 ** 4
+    terms = {"rDeltaT": -1.0, "V": np.full(N, h ** 3), "psi": absorb, "psi0": np.zeros(N), "p0": np.zeros(N),
+             "explicit": [], "gamma_f": gamma_f, "magSf": np.full(F, h * h), "deltaCoeffs": np.full(F, 1.0 / h),
+             "lapSign": 1.0, "Su": -4.0 * (absorb * sigmaSB * T ** 4), "bCells": bCells,
+             "bInternal": bInt, "bBoundary": bInt * refValue}
+    return case, terms

@@ -6,6 +6,9 @@ CPU oracle as the dumping solver:
   steckler_ph_rgh_c1.b200sys    first hydrostatic corrector of cases/steckler (9 000 cells, DICPCG,
                                 tol 1e-6 relTol 0.01: the system behind log.fireFoam:92, 29 iterations)
 
+  steckler_G_p1.b200sys         the P1 radiation model's G equation restated on the steckler topology (9 000
+                                cells, DICPCG, tol 1e-6 relTol 0: SURVEY.md 8f-4, the reference's other symmetric solve)
+
 The systems come from firefoam-dev_b200/cases.py (the case files restated by hand: no OpenFOAM here),
 the recorded reference lines from oracle/ (plain-C restatement of OpenFOAM's PCG).  Run from the repo
 root: python tests/golden/make_dumps.py"""
@@ -40,5 +43,25 @@ def first_corrector(case, pre, name):
     print(name, os.path.getsize(path), "bytes;", pre + "PCG", perf.nIterations, "iterations")
 
 
+def g_equation(name):
+    """P1 G equation on the steckler topology (cases.p1_G_terms; P1.C:238-244, fvSolution:75-81: PCG + DIC,
+    tol 1e-6, relTol 0), assembled by the oracle's fvMatrix algebra."""
+    from firefoam_dev_b200.cases import p1_G_terms
+    case, t = p1_G_terms()
+    up, dg, src = orc.assemble_p_rgh(case.addr.lowerAddr, case.addr.upperAddr, case.N, t)
+    sysm = System(case.addr, dg, up, src, [])
+    psi0 = np.zeros(case.N)
+    psi = psi0.copy()
+    perf = orc.pcg_solve(sysm, psi, "DIC", 1e-6, 0.0, 1000)
+    ctl = {"preconditioner": "DIC", "tolerance": 1e-6, "relTol": 0.0, "maxIter": 1000, "B200": {"dicMode": "exact"}}
+    ref = {"initialResidual": perf.initialResidual, "finalResidual": perf.finalResidual,
+           "nIterations": perf.nIterations, "converged": perf.converged, "singular": perf.singular}
+    path = os.path.join(HERE, name)
+    replay.write_dump(path, sysm, psi0, ctl, fieldName="G", psi=psi, reference=ref, solverName="DICPCG",
+                      solveIndex=0, time=0.0)
+    print(name, os.path.getsize(path), "bytes; DICPCG", perf.nIterations, "iterations")
+
+
 first_corrector(SingleBoxHydrostatic(), "diagonal", "singlebox_ph_rgh_c1.b200sys")
 first_corrector(StecklerHydrostatic(), "DIC", "steckler_ph_rgh_c1.b200sys")
+g_equation("steckler_G_p1.b200sys")

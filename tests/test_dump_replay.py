@@ -33,6 +33,16 @@ def test_fixture_steckler_pins_the_golden_log_count():
     assert np.array_equal(psi, d.psi)
 
 
+def test_fixture_G_equation():
+    """the P1 G equation (P1.C:238-244) as a committed system; the oracle reproduces the stored
+    DICPCG line on the bytes in the file."""
+    d = replay.read_dump(os.path.join(GOLD, "steckler_G_p1.b200sys"))
+    assert d.fieldName == "G" and d.system.addr.nCells == 9000 and d.controls["relTol"] == 0.0
+    psi = d.psi0.copy()
+    perf = orc.pcg_solve(d.system, psi, "DIC", d.controls["tolerance"], d.controls["relTol"], d.controls["maxIter"])
+    assert perf.nIterations == d.reference["nIterations"] == 62 and np.array_equal(psi, d.psi)
+
+
 def test_fixture_singlebox():
     d = replay.read_dump(os.path.join(GOLD, "singlebox_ph_rgh_c1.b200sys"))
     assert d.system.addr.nCells == 245 and d.controls["preconditioner"] == "diagonal"
@@ -111,7 +121,7 @@ def test_edge_cases_and_errors(tmp_path):
 
 @pytest.mark.gpu
 def test_replay_fixtures_on_gpu(ctx):
-    for name in ("steckler_ph_rgh_c1.b200sys", "singlebox_ph_rgh_c1.b200sys"):
+    for name in ("steckler_ph_rgh_c1.b200sys", "singlebox_ph_rgh_c1.b200sys", "steckler_G_p1.b200sys"):
         psi, perf, d = replay.replay(os.path.join(GOLD, name), context=ctx)
         assert perf.nIterations == d.reference["nIterations"]
         assert abs(perf.finalResidual - d.reference["finalResidual"]) <= 1e-9 * d.reference["finalResidual"]
