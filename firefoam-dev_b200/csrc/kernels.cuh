@@ -1765,6 +1765,44 @@ k_neg_sum_diag(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __r
     }
 }
 
+// negSumDiag in the CALLER'S cell order, for plans whose rows were renumbered (RCM): there the plan's rows are a
+// permutation of the cells, and gathering upper[faceOf[e]] row by row jumps all over the face list (measured
+// 0.26 of the roofline on the block-shuffled polyhedral workload).  In natural order the owner-side faces of a
+// cell are CONTIGUOUS in the face list (upper-triangular order: faces sorted by owner) and the neighbour-side
+// faces (losort: ascending face index, all below the cell's first owner face) belong to nearby owners, so one
+// half of the reads streams and the other half stays in L2.  Same summation order as OpenFOAM's face loop:
+// ascending face index.  ownerStart / losortStart / losort are OF-dev lduAddressing's own lazily-built lists.
+__global__ void __launch_bounds__(kBlock)
+k_neg_sum_diag_nat(int N, const int* __restrict__ ownerStart, const int* __restrict__ losortStart,
+                   const int* __restrict__ losort, const double* __restrict__ upper, double* __restrict__ diag) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+        const int k0 = losortStart[c], k1 = losortStart[c + 1];
+        const int f0 = ownerStart[c], f1 = ownerStart[c + 1];
+        const double d0 = diag[c];
+        double d = 0.0;
+        int k = k0;
+        for (; k + 4 <= k1; k += 4) {
+            const int a0 = losort[k], a1 = losort[k + 1], a2 = losort[k + 2], a3 = losort[k + 3];
+            const double u0 = __ldg(&upper[a0]), u1 = __ldg(&upper[a1]), u2 = __ldg(&upper[a2]), u3 = __ldg(&upper[a3]);
+            d = __dadd_rn(d, -u0);
+            d = __dadd_rn(d, -u1);
+            d = __dadd_rn(d, -u2);
+            d = __dadd_rn(d, -u3);
+        }
+        for (; k < k1; ++k) d = __dadd_rn(d, -__ldg(&upper[losort[k]]));
+        int f = f0;
+        for (; f + 4 <= f1; f += 4) {
+            const double u0 = upper[f], u1 = upper[f + 1], u2 = upper[f + 2], u3 = upper[f + 3];
+            d = __dadd_rn(d, -u0);
+            d = __dadd_rn(d, -u1);
+            d = __dadd_rn(d, -u2);
+            d = __dadd_rn(d, -u3);
+        }
+        for (; f < f1; ++f) d = __dadd_rn(d, -upper[f]);
+        diag[c] = __dadd_rn(d0, d);
+    }
+}
+
 // ---- whole p_rghEqn: ddt + explicit terms + fvc::div + laplacian diagonal + boundary fold ------
 // (reference solver/pEqn.H:26-37, solver/phrghEqn.H:43-46; OF-dev EulerDdtScheme.C,
 // fvMatrix.C, surfaceIntegrate.C, lduMatrixOperations.C).  One row per thread: the face -> cell sums

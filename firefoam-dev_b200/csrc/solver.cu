@@ -157,6 +157,9 @@ struct b200_ctx {
     std::vector<int32_t> hl, hu;
     std::vector<HostIface> hif;
     int *d_l = nullptr, *d_u = nullptr;
+    // natural-order face lists (lduAddressing's ownerStart / losortStart / losort), built only when the plan's
+    // rows are renumbered: negSumDiag then runs in the caller's cell order (k_neg_sum_diag_nat)
+    int *d_ownerStart = nullptr, *d_losortStart = nullptr, *d_losort = nullptr;
     DevPlan plans[3];
     int nSlots = 0;
     // vectors (internal order)
@@ -355,6 +358,7 @@ void free_plan(DevPlan& P) {
 void free_mesh(b200_ctx* c) {
     for (auto& P : c->plans) free_plan(P);
     dev_free(c->d_l); dev_free(c->d_u);
+    dev_free(c->d_ownerStart); dev_free(c->d_losortStart); dev_free(c->d_losort);
     dev_free(c->diag); dev_free(c->src); dev_free(c->psi); dev_free(c->r); dev_free(c->p);
     dev_free(c->w); dev_free(c->rD); dev_free(c->t); dev_free(c->dT); dev_free(c->eD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
     dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
@@ -1646,6 +1650,18 @@ int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_
         RET(ensure_plan(ctx, Ordering::Natural, &P));
         RET(upload(ctx, &ctx->d_l, ctx->hl));
         RET(upload(ctx, &ctx->d_u, ctx->hu));
+        if (P->h.renumbered) {
+            const size_t N = (size_t)ctx->N, F = (size_t)ctx->F;
+            std::vector<int32_t> os(N + 1, 0), ls(N + 1, 0), lo(F);
+            for (size_t f = 0; f < F; ++f) { os[(size_t)ctx->hl[f] + 1]++; ls[(size_t)ctx->hu[f] + 1]++; }
+            for (size_t c = 0; c < N; ++c) { os[c + 1] += os[c]; ls[c + 1] += ls[c]; }
+            std::vector<int32_t> pos(ls.begin(), ls.end() - 1);
+            for (size_t f = 0; f < F; ++f) lo[(size_t)pos[(size_t)ctx->hu[f]]++] = (int32_t)f;   // stable: ascending faces
+            RET(upload(ctx, &ctx->d_ownerStart, os));
+            RET(upload(ctx, &ctx->d_losortStart, ls));
+            RET(upload(ctx, &ctx->d_losort, lo));
+            CU(cudaStreamSynchronize(ctx->sc));   // the host vectors go out of scope
+        }
         RET(alloc_vectors(ctx));
         CU(cudaStreamSynchronize(ctx->sc));
         return B200_OK;
@@ -1687,8 +1703,12 @@ int b200_assemble_laplacian_device(b200_ctx* ctx, const double* g, const double*
     CU(cudaSetDevice(ctx->device));
     DevPlan& P = ctx->plans[0];
     LAUNCH(PC_ASM_FACE, k_face_coeff, grid_for(ctx, ctx->F, 16), ctx->F, g, s, d, sign, upper_out);
-    LAUNCH(PC_ASM_DIAG, k_neg_sum_diag, grid_for(ctx, ctx->N, 16), ctx->N, P.sliceBase, P.rowLen,
-           P.faceOf, P.perm, upper_out, diag_inout);
+    if (ctx->d_losort)   // renumbered plan: in the caller's cell order (kernels.cuh)
+        LAUNCH(PC_ASM_DIAG, k_neg_sum_diag_nat, grid_for(ctx, ctx->N, 16), ctx->N, ctx->d_ownerStart, ctx->d_losortStart,
+               ctx->d_losort, upper_out, diag_inout);
+    else
+        LAUNCH(PC_ASM_DIAG, k_neg_sum_diag, grid_for(ctx, ctx->N, 16), ctx->N, P.sliceBase, P.rowLen,
+               P.faceOf, P.perm, upper_out, diag_inout);
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
     prof_collect(ctx);
