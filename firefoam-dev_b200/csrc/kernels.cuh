@@ -75,6 +75,11 @@ struct Scalars {
     // which is what makes the two-slot PeerBuf safe (a host-side launch counter would not: launches
     // skipped by `done` would let two executed reductions share a parity).
     unsigned long long redSeq;
+    // processor-patch halo over peer memory (k_pack_p2p / halo_acquire): number of exchanges this rank has
+    // EXECUTED (same rule as redSeq: neighbours execute the same sequence, so their counters agree and consecutive
+    // exchanges alternate the two halves of the receive buffer) and the producer's block ticket
+    unsigned long long haloSeq;
+    unsigned int haloTicket, pad2;
 };
 
 struct PeerBuf;
@@ -580,6 +585,79 @@ k_spmv_sym(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
     if (DOT) reduce_finish<1>(dot, R);
 }
 
+// ---- single-read Amul for RENUMBERED natural plans (plan.hpp SrPlan) ----------------------------
+// One list of 32-bit words per row, in ascending natural face order (= the order of OpenFOAM's face loop, so
+// the row sum is bit-identical on any row order): column << 5 | q.  q == 31: the row owns the coefficient (its
+// next own value, coalesced sliced ELL); q < 31: the q-th own value of row `column`, re-read through L2.  Every
+// coefficient is streamed from HBM once: 8 F + 8 F + 28 N bytes instead of the full-row ELL's 24 F + 28 N.
+// Batches of 4 entries: all words, then all positions (one cached ownBase lookup each), then values + gathers,
+// then the adds in order.
+template <bool INIT, bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv_sr(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          const uint32_t* __restrict__ meta, const int64_t* __restrict__ ownBase, const double* __restrict__ ownVal,
+          const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
+          double* __restrict__ sA, Reduce R) {
+    if (R.S->done) return;
+    double dot[1] = {0.0};
+    const int lane = threadIdx.x & 31;
+    const int nSlices = (N + 31) >> 5;
+    const int warpsPerGrid = (gridDim.x * kBlock) >> 5;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) >> 5; s < nSlices; s += warpsPerGrid) {
+        const int r = (s << 5) + lane;
+        if (r < N) {
+            const int64_t base = sliceBase[s] + lane;
+            const int n = (int)(rowLen[r] >> 16);
+            const double xr = x[r];
+            const double d = diag[r];
+            double acc = __dmul_rn(d, xr);
+            double sa = d;
+            int jown = 0;
+            int j = 0;
+            for (; j + 4 <= n; j += 4) {
+                const int64_t e = base + 32 * (int64_t)j;
+                uint32_t m[4];
+                int64_t pos[4];
+                double v[4], g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = meta[e + 32 * k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t a = m[k] >> 5, q = m[k] & 31u;
+                    const bool own = (q == 31u);
+                    const int64_t ob = __ldg(&ownBase[own ? (uint32_t)s : (a >> 5)]);
+                    pos[k] = ob + 32 * (int64_t)(own ? jown : (int)q) + (own ? lane : (int)(a & 31u));
+                    jown += own ? 1 : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[k] = ownVal[pos[k]];
+                    g[k] = __ldg(&x[m[k] >> 5]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc = __dadd_rn(acc, __dmul_rn(v[k], g[k]));
+                    if (INIT) sa = __dadd_rn(sa, v[k]);
+                }
+            }
+            for (; j < n; ++j) {
+                const uint32_t m0 = meta[base + 32 * (int64_t)j];
+                const uint32_t a = m0 >> 5, q = m0 & 31u;
+                const bool own = (q == 31u);
+                const int64_t ob = __ldg(&ownBase[own ? (uint32_t)s : (a >> 5)]);
+                const double v0 = ownVal[ob + 32 * (int64_t)(own ? jown : (int)q) + (own ? lane : (int)(a & 31u))];
+                jown += own ? 1 : 0;
+                acc = __dadd_rn(acc, __dmul_rn(v0, __ldg(&x[a])));
+                if (INIT) sa = __dadd_rn(sa, v0);
+            }
+            y[r] = acc;
+            if (INIT) sA[r] = sa;
+            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
+        }
+    }
+    if (DOT) reduce_finish<1>(dot, R);
+}
+
 // ---- ranked variant of the symmetric Amul (renumbered natural plans) ---------------------------
 // Rows follow the plan's RCM order, so the [lower | upper] split of the single-read layout is not
 // OpenFOAM's visiting order of the row.  Every entry carries the rank of its face among the row's
@@ -982,6 +1060,77 @@ k_spmv_sym_win(int N, int WU, int WL, int runLen, const uint32_t* __restrict__ r
 
 // ---- processor interfaces (OF-dev processorFvPatchField.C, lduMatrixUpdateMatrixInterfaces.C;
 //      SURVEY.md A.4) ------------------------------------------------------------------------
+// ---- processor-patch halo exchange over NVLink peer memory ---------------------------------------
+// Replaces initMatrixInterfaces / updateMatrixInterfaces' send + receive (OF-dev processorFvPatchField.C,
+// UIPstream/UOPstream) -- and the ncclSend/ncclRecv pair this library used before -- by direct stores: every
+// rank owns a receive buffer  double vals[2][nSlots]; unsigned long long flags[2][kMaxRanks]  in its HBM, mapped
+// into its neighbours with CUDA IPC.  The PACK kernel of the sender gathers x[faceCells] and stores each value
+// straight into the neighbour's buffer (the two sides of a processor patch list their faces in the same order,
+// so patch face j of the sender is slot j of the matching patch of the receiver); its last block then raises
+// the sender's flag in every neighbour.  The CONSUMER (interface fix-up of the Amul, halo term of the Eisenstat
+// sweeps) waits for its neighbours' flags at its start.  No NCCL kernel is involved: an NCCL send/recv kernel
+// (640 threads, ~60 K registers per CTA) cannot become resident beside the persistent Amul grid and was running
+// AFTER it -- ~40 us of exposed exchange per iteration on 2 GPUs (profiles/r02_*): the pack kernel can.
+// NCCL send/recv stays as the fall-back when peer mapping is unavailable (B200PCG_HALO=nccl forces it).
+struct Halo {
+    double* const* dst;                   // [2][nSlots] address of slot i's value in the neighbour's vals[par]
+    unsigned long long* const* nbrFlag;   // [2][nNbr]   address of flags[par][my rank] in neighbour k's buffer
+    const unsigned long long* localFlags; // this rank's flags[2][kMaxRanks]           (nullptr: NCCL mode)
+    const double* localVals;              // this rank's vals[2][nSlots]
+    const int* nbrRanks;                  // [nNbr]
+    int nSlots, nNbr;
+};
+
+__global__ void __launch_bounds__(kBlock)
+k_pack_p2p(Halo H, const int* __restrict__ slotRow, const double* __restrict__ x, Scalars* S) {
+    if (S->done) return;
+    __shared__ bool amLast;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq) + 1ull;
+    const int par = (int)(seq & 1ull);
+    double* const* dst = H.dst + (size_t)par * H.nSlots;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H.nSlots; i += gridDim.x * blockDim.x)
+        *dst[i] = __ldg(&x[slotRow[i]]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&S->haloTicket, 1u);
+        amLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence_system();
+    if (threadIdx.x < H.nNbr)
+        *reinterpret_cast<volatile unsigned long long*>(H.nbrFlag[par * H.nNbr + threadIdx.x]) = seq;
+    if (threadIdx.x == 0) {
+        S->haloSeq = seq;
+        S->haloTicket = 0u;
+        __threadfence();
+    }
+}
+
+// Every thread of every block of a consumer kernel calls this once (uniformly), after the kernel's `done` test.
+// Returns the buffer that holds the neighbours' values of the current exchange.
+__device__ __forceinline__ const double* halo_acquire(const Halo& H, const double* ncclRecv, Scalars* S) {
+    if (H.localFlags == nullptr) return ncclRecv;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq);
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x < H.nNbr) {
+        const volatile unsigned long long* f = H.localFlags + par * kMaxRanks + H.nbrRanks[threadIdx.x];
+        unsigned long long spins = 0, t0 = 0;
+        while (*f < seq) {
+            if ((++spins & 1023ull) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kPeerTimeoutNs) { S->nonfinite = 2; break; }   // reported by the host
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    return H.localVals + (size_t)par * H.nSlots;
+}
+
 __global__ void k_pack(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ x,
                        double* __restrict__ sendbuf, const Scalars* S) {
     if (S->done) return;
@@ -995,9 +1144,10 @@ template <int MODE, bool DOT>
 __global__ void __launch_bounds__(kBlock)
 k_iface_fix(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bStart,
             const int* __restrict__ bSlot, const double* __restrict__ bou,
-            const double* __restrict__ recv, const double* __restrict__ x,
+            const double* recvNccl, Halo H, const double* __restrict__ x,
             double* __restrict__ y, Reduce R) {
     if (R.S->done) return;
+    const double* recv = (MODE == 0) ? halo_acquire(H, recvNccl, R.S) : recvNccl;
     double dot[1] = {0.0};
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
         const int r = bRow[b];
@@ -1005,7 +1155,7 @@ k_iface_fix(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bS
         double acc = y0;
         for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
             const int slot = bSlot[e];
-            if (MODE == 0) acc = __dadd_rn(acc, -__dmul_rn(bou[slot], recv[slot]));
+            if (MODE == 0) acc = __dadd_rn(acc, -__dmul_rn(bou[slot], __ldcg(&recv[slot])));
             else acc = __dadd_rn(acc, -bou[slot]);
         }
         y[r] = acc;
@@ -1378,11 +1528,12 @@ k_eis_scale_vals(int N, const int64_t* __restrict__ sliceBase, const uint32_t* _
 // nranks > 1: interface coefficients of B- (recv = the neighbours' s on the patch faces)
 __global__ void __launch_bounds__(kBlock)
 k_eis_scale_bou(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ sv,
-                const double* __restrict__ recv, double* __restrict__ bou, const Scalars* S) {
+                const double* recvNccl, Halo H, double* __restrict__ bou, Scalars* S) {
     if (S->done) return;
+    const double* recv = halo_acquire(H, recvNccl, S);
     const double sigma = S->sigma;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x) {
-        const double ss = __dmul_rn(__ldg(&sv[slotRow[i]]), recv[i]);
+        const double ss = __dmul_rn(__ldg(&sv[slotRow[i]]), __ldcg(&recv[i]));
         bou[i] = __dmul_rn(bou[i], __dmul_rn(sigma, ss));
     }
 }
@@ -1601,14 +1752,15 @@ k_eis_fwd_rows(int nB0, const int* __restrict__ bRow, const double* __restrict__
 // row's processor faces in (patch, face) order (the sorted-segment form of updateMatrixInterfaces)
 __global__ void __launch_bounds__(kBlock)
 k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ bSlot,
-           const double* __restrict__ bou, const double* __restrict__ recv, double* __restrict__ hb,
-           const Scalars* S) {
+           const double* __restrict__ bou, const double* recvNccl, Halo H, double* __restrict__ hb,
+           Scalars* S) {
     if (S->done) return;
+    const double* recv = halo_acquire(H, recvNccl, S);
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
         double acc = 0.0;
         for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
             const int slot = bSlot[e];
-            acc = __dadd_rn(acc, -__dmul_rn(bou[slot], recv[slot]));
+            acc = __dadd_rn(acc, -__dmul_rn(bou[slot], __ldcg(&recv[slot])));
         }
         hb[b] = acc;
     }

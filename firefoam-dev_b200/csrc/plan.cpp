@@ -503,6 +503,70 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
         }
     }
 
+    // ---- single-read face-ordered layout (renumbered natural plans; plan.hpp SrPlan) -----------
+    if (ordering == Ordering::Natural && !ident && N > 0 && N <= (1 << 27)) {
+        SrPlan& R = P.sr;
+        // own count of every row (neighbour has the larger row index) and the per-slice own widths
+        std::vector<int32_t> nOwnRow((size_t)N, 0);
+        bool fits = true;
+#pragma omp parallel for schedule(static) reduction(&& : fits)
+        for (int32_t r = 0; r < N; ++r) {
+            const int32_t c = cellOf(r);
+            int32_t k = 0;
+            for (int64_t e = cf.start[c]; e < cf.start[c + 1]; ++e)
+                if (rowOf(cf.other[e]) > r) ++k;
+            nOwnRow[r] = k;
+            fits = fits && k <= 31;          // q < 31 addresses the own values 0..30; an own count of 31 is still fine
+        }
+        if (fits) {
+            R.ownBase.assign((size_t)P.nSlices + 1, 0);
+            for (int32_t sl = 0; sl < P.nSlices; ++sl) {
+                int64_t mx = 0;
+                for (int32_t r = sl * 32; r < std::min(N, sl * 32 + 32); ++r) mx = std::max<int64_t>(mx, nOwnRow[r]);
+                R.ownBase[sl + 1] = R.ownBase[sl] + 32 * mx;
+            }
+            R.nOwn = R.ownBase[P.nSlices];
+            R.ownFace.assign((size_t)R.nOwn, -1);
+            R.meta.assign((size_t)P.nEntries, 0u);
+            // pass 1: own slots in ascending face order (the full-row ELL of a renumbered natural plan is in
+            // ascending face order already: its entries ARE the row's visiting order)
+#pragma omp parallel for schedule(static)
+            for (int32_t r = 0; r < N; ++r) {
+                const int64_t base = P.sliceBase[r / 32] + (r % 32);
+                const int64_t ob = R.ownBase[r / 32] + (r % 32);
+                const int32_t n = (int32_t)(P.rowLen[r] >> 16);
+                int64_t j = 0;
+                for (int32_t k = 0; k < n; ++k) {
+                    const int64_t e = base + 32 * (int64_t)k;
+                    if (P.col[e] > r) R.ownFace[ob + 32 * j++] = P.faceOf[e];
+                }
+            }
+            // pass 2: the meta words; a reference finds its face among the owner's own slots
+            bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+            for (int32_t r = 0; r < N; ++r) {
+                const int64_t base = P.sliceBase[r / 32] + (r % 32);
+                const int32_t n = (int32_t)(P.rowLen[r] >> 16);
+                for (int32_t k = 0; k < n; ++k) {
+                    const int64_t e = base + 32 * (int64_t)k;
+                    const int32_t a = P.col[e];
+                    uint32_t q = 31u;
+                    if (a < r) {
+                        const int64_t ab = R.ownBase[a / 32] + (a % 32);
+                        int32_t found = -1;
+                        for (int32_t t = 0; t < nOwnRow[a]; ++t)
+                            if (R.ownFace[ab + 32 * (int64_t)t] == P.faceOf[e]) { found = t; break; }
+                        if (found < 0 || found > 30) { ok = false; found = 0; }
+                        q = (uint32_t)found;
+                    }
+                    R.meta[e] = ((uint32_t)a << 5) | q;
+                }
+            }
+            R.valid = ok;
+            if (!ok) P.sr = SrPlan();
+        }
+    }
+
     // ---- interfaces ---------------------------------------------------------------------
     P.nIfaces = nIfaces;
     P.nbrRank.resize((size_t)nIfaces);

@@ -60,6 +60,25 @@ struct SymPlan {
     std::vector<uint8_t> lRank;   // [nL]
 };
 
+// Single-read layout for RENUMBERED natural plans ("SR": face-ordered).  A renumbered row must still add its
+// faces in ascending NATURAL face order (bit-identical row sums), and in that order the entries whose value the
+// row owns (neighbour has the larger row index) interleave with the entries it only references.  So the row keeps
+// ONE list, aligned with the full-row ELL (same sliceBase / rowLen, ascending natural face order), of 32-bit words
+//     meta = column << 5 | q        q == 31: own entry, the value is the row's next own value
+//                                    q  < 31: reference to the q-th own value of row `column`
+// and every coefficient is stored once, in a second sliced ELL of own values (per-slice width):
+//     own value j of row r at  ownBase[r / 32] + 32 j + r % 32.
+// DRAM bytes per Amul: 8 F (values) + 8 F (meta) + 28 N instead of the full-row ELL's 24 F + 28 N; the referenced
+// values are L2 hits on a bandwidth-reduced order.  Replaces the "ranked" form of SymPlan, which staged the
+// products by rank in shared memory and measured slower than the full-row ELL (profiles/r01_v7_dic_tiles.md).
+struct SrPlan {
+    bool valid = false;
+    int64_t nOwn = 0;                 // padded own-value slots
+    std::vector<uint32_t> meta;       // [nEntries] (padding: 0)
+    std::vector<int64_t> ownBase;     // [nSlices + 1]
+    std::vector<int32_t> ownFace;     // [nOwn] natural face of the slot, -1 padding
+};
+
 // Base cell order the row orders are derived from.  OpenFOAM meshes are normally bandwidth-reduced
 // (renumberMesh), but nothing guarantees it: on a cache-hostile numbering a warp's neighbour gathers
 // touch 32 different sectors per request and Amul drops to a quarter of the HBM roofline (measured on
@@ -74,6 +93,7 @@ struct HostPlan {
     double spanNatural = 0, spanUsed = 0;   // mean |row(l) - row(u)| over faces, before / after
     double sectorsNatural = 0, sectorsUsed = 0;   // mean 32-B sectors per warp gather request (sampled)
     SymPlan sym;
+    SrPlan sr;                         // renumbered natural plans only
     int32_t N = 0, F = 0;
     // row order
     std::vector<int32_t> perm;         // internal row -> natural cell  (empty == identity)

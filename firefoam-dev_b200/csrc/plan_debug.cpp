@@ -69,9 +69,11 @@ int64_t b200_debug_plan_get(void* h, const char* name, const void** ptr, int32_t
     V("sym.lRank", P.sym.lRank)
     V("sym.uCol", P.sym.uCol)
     V("sym.uFace", P.sym.uFace) V("sym.lRef", P.sym.lRef)
+    V("sr.meta", P.sr.meta) V("sr.ownBase", P.sr.ownBase) V("sr.ownFace", P.sr.ownFace)
 #undef V
     return -1;
 }
+int32_t b200_debug_plan_sr_valid(void* h) { return ((HostPlan*)h)->sr.valid ? 1 : 0; }
 int32_t b200_debug_plan_sym_valid(void* h) { return ((HostPlan*)h)->sym.valid ? 1 : 0; }
 int32_t b200_debug_plan_sym_wu(void* h) { return ((HostPlan*)h)->sym.WU; }
 int32_t b200_debug_plan_sym_wl(void* h) { return ((HostPlan*)h)->sym.WL; }

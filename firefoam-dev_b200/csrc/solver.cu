@@ -122,6 +122,13 @@ struct DevPlan {
     uint32_t* sLRef = nullptr;
     uint8_t* sLRank = nullptr;    // ranked form (renumbered natural plans)
     bool symRanked = false;
+    // single-read face-ordered layout of renumbered natural plans (plan.hpp SrPlan)
+    bool sr = false;
+    int64_t srNOwn = 0;
+    uint32_t* srMeta = nullptr;
+    int64_t* srOwnBase = nullptr;
+    int* srOwnFace = nullptr;
+    double* srOwnVal = nullptr;
     // Eisenstat form, nranks > 1: interface-row index of every row (-1: none) and the halo term B t
     int* rowB = nullptr;
     double* hb = nullptr;
@@ -181,6 +188,16 @@ struct b200_ctx {
     PeerBuf* peerLocal = nullptr;
     std::vector<void*> peerMapped;     // cudaIpcOpenMemHandle results (to close)
     PeerBuf** d_peers = nullptr;
+    // processor-patch halos over peer memory (kernels.cuh Halo): this rank's receive buffer (vals[2][nSlots] +
+    // flags[2][kMaxRanks], exported with CUDA IPC), the neighbours' buffers mapped here, the device tables
+    bool p2pHalo = false;
+    bool forceNcclHalo = false;        // B200PCG_HALO=nccl
+    double* haloLocal = nullptr;
+    std::vector<void*> haloMapped;
+    double** d_haloDst = nullptr;
+    unsigned long long** d_haloNbrFlag = nullptr;
+    int* d_haloNbrRanks = nullptr;
+    Halo haloDev = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
     // staged copies of pageable caller memory (B200PCG_STAGED_COPY=1): two page-locked pieces + their DMA events
     bool stagedCopy = true;
     void* stageBuf[2] = {nullptr, nullptr};
@@ -227,6 +244,7 @@ struct b200_ctx {
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
+    bool disableSr = false;     // B200PCG_SPMV=ell|ranked: renumbered natural plans keep the full-row ELL / ranked form
     // profiling
     bool useGraph = true;       // B200PCG_GRAPH=0: enqueue every loop body kernel by kernel
     bool prof = false;
@@ -349,13 +367,24 @@ void free_plan(DevPlan& P) {
     dev_free(P.sUCol); dev_free(P.sUFace);
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8); dev_free(P.sLRank);
     dev_free(P.rowB); dev_free(P.hb);
+    dev_free(P.srMeta); dev_free(P.srOwnBase); dev_free(P.srOwnFace); dev_free(P.srOwnVal);
+    P.sr = false;
     P.symRanked = false;
     P.sym = false;
     P.built = false;
     P.h = HostPlan();
 }
 
+void free_halo(b200_ctx* c) {
+    for (void* p : c->haloMapped) cudaIpcCloseMemHandle(p);
+    c->haloMapped.clear();
+    dev_free(c->haloLocal); dev_free(c->d_haloDst); dev_free(c->d_haloNbrFlag); dev_free(c->d_haloNbrRanks);
+    c->haloDev = Halo{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    c->p2pHalo = false;
+}
+
 void free_mesh(b200_ctx* c) {
+    free_halo(c);
     for (auto& P : c->plans) free_plan(P);
     dev_free(c->d_l); dev_free(c->d_u);
     dev_free(c->d_ownerStart); dev_free(c->d_losortStart); dev_free(c->d_losort);
@@ -474,8 +503,17 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         P.symWL = Y.WL;
         P.sym = true;
     }
+    if (P.h.sr.valid && !ctx->disableSr && !P.sym) {
+        RET(upload(ctx, &P.srMeta, P.h.sr.meta));
+        RET(upload(ctx, &P.srOwnBase, P.h.sr.ownBase));
+        RET(upload(ctx, &P.srOwnFace, P.h.sr.ownFace));
+        RET(dev_alloc(ctx, &P.srOwnVal, (size_t)P.h.sr.nOwn));
+        P.srNOwn = P.h.sr.nOwn;
+        P.sr = true;
+    }
     CU(cudaStreamSynchronize(ctx->sc));
     P.h.sym = SymPlan();
+    P.h.sr = SrPlan();
 
     // release the big host arrays
     std::vector<int32_t>().swap(P.h.col);
@@ -528,25 +566,39 @@ int reduce_post(b200_ctx* ctx, int step) {
     return B200_OK;
 }
 
+// Start the exchange of x[faceCells] across the processor patches on `st` (the data is complete on `st`):
+// peer-memory form = ONE small kernel that stores straight into the neighbours' receive buffers and raises
+// their flags (kernels.cuh k_pack_p2p); NCCL form = pack + grouped ncclSend/ncclRecv.  The consumer kernels
+// take ctx->haloDev (+ ctx->recvbuf for the NCCL form) and wait for the flags themselves.
+int halo_exchange(b200_ctx* ctx, DevPlan& P, const double* x, cudaStream_t st) {
+    if (ctx->p2pHalo) {
+        k_pack_p2p<<<grid_for(ctx, P.nSlots), kBlock, 0, st>>>(ctx->haloDev, P.slotRow, x, ctx->S);
+        ctx->launches++;
+        return B200_OK;
+    }
+    k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, st>>>(P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
+    ctx->launches++;
+    NC(g_nccl.GroupStart());
+    for (int k = 0; k < P.h.nIfaces; ++k) {
+        const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+        if (n == 0) continue;
+        NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, st));
+        NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, st));
+    }
+    NC(g_nccl.GroupEnd());
+    return B200_OK;
+}
+
 // y = A x (+ interfaces) [+ (y,x) -> step]; INIT: also sA = sumA
 template <bool INIT, bool DOT>
 int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA, int step) {
     const int N = ctx->N;
     const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
     if (halo) {
-        // pack + exchange run on the comm stream, concurrently with the interior Amul
+        // the exchange runs on the comm stream, concurrently with the Amul
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
-        k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, x, ctx->sendbuf, ctx->S);
-        ctx->launches++;
-        NC(g_nccl.GroupStart());
-        for (int k = 0; k < P.h.nIfaces; ++k) {
-            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
-            if (n == 0) continue;
-            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-        }
-        NC(g_nccl.GroupEnd());
+        RET(halo_exchange(ctx, P, x, ctx->sm));
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R = mkR(ctx, halo ? STEP_NONE : step);
@@ -590,6 +642,10 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
 #undef B200_TMA_LAUNCH
         prof_end(ctx, PC_SPMV);
         ctx->launches++;
+    } else if (P.sr) {
+        auto kern = k_spmv_sr<INIT, DOT>;
+        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.srMeta, P.srOwnBase,
+               P.srOwnVal, ctx->diag, x, y, sA, R);
     } else if (P.sym && P.symRanked) {
         auto kern = k_spmv_sym_ranked<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
@@ -615,11 +671,11 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         Reduce R2 = mkR(ctx, step);
         auto fix = k_iface_fix<0, DOT>;
         LAUNCH(PC_IFACE, fix, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot,
-               ctx->bou, ctx->recvbuf, x, y, R2);
+               ctx->bou, ctx->recvbuf, ctx->haloDev, x, y, R2);
         if (INIT) {
             auto fix1 = k_iface_fix<1, false>;
             LAUNCH(PC_IFACE, fix1, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart,
-                   P.bSlot, ctx->bou, ctx->recvbuf, x, sA, R2);
+                   P.bSlot, ctx->bou, ctx->recvbuf, ctx->haloDev, x, sA, R2);
         }
     }
     if (DOT) RET(reduce_post(ctx, step));
@@ -656,7 +712,12 @@ int ensure_staging(b200_ctx* ctx, bool faceTemps) {
 int load_system(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* dn_upper,
                 const double* dn_src, const double* dn_psi) {
     const int N = ctx->N;
-    LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
+    // the full-row ELL values of a single-read (SR) plan are only read by the cluster kernels of small systems
+    const bool ellUnused = P.sr && !(ctx->nranks == 1 && N <= ctx->smallN);
+    if (!ellUnused)
+        LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
+    if (P.sr)
+        LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.srNOwn, 16), P.srNOwn, P.srOwnFace, dn_upper, P.srOwnVal);
     if (P.sym)
         LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.symNU, 16), P.symNU, P.sUFace, dn_upper, P.sUVal);
     LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_diag, ctx->diag);
@@ -804,16 +865,7 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
 int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
     CU(cudaEventRecord(ctx->evPack, ctx->sc));
     CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
-    k_pack<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sm>>>(P.nSlots, P.slotRow, ctx->t, ctx->sendbuf, ctx->S);
-    ctx->launches++;
-    NC(g_nccl.GroupStart());
-    for (int k = 0; k < P.h.nIfaces; ++k) {
-        const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
-        if (n == 0) continue;
-        NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-        NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sm));
-    }
-    NC(g_nccl.GroupEnd());
+    RET(halo_exchange(ctx, P, ctx->t, ctx->sm));
     CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     return B200_OK;
 }
@@ -821,7 +873,7 @@ int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
 int eis_halo_wait(b200_ctx* ctx, DevPlan& P) {
     CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
     LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
-           ctx->recvbuf, P.hb, ctx->S);
+           ctx->recvbuf, ctx->haloDev, P.hb, ctx->S);
     return B200_OK;
 }
 
@@ -918,18 +970,22 @@ int eis_setup(b200_ctx* ctx, DevPlan& P) {
     LAUNCH(PC_EIS_SETUP, k_eis_setup, gn, N, ctx->diag, ctx->dT, ctx->eD, ctx->r, ctx->rD, S);
     if (ctx->nranks > 1 && P.nSlots > 0) {
         // the neighbours' s on the patch faces -> interface coefficients of B- (once per solve: same stream)
-        k_eis_pack_s<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sc>>>(P.nSlots, P.slotRow, ctx->dT, ctx->sendbuf);
-        ctx->launches++;
-        NC(g_nccl.GroupStart());
-        for (int k = 0; k < P.h.nIfaces; ++k) {
-            const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
-            if (n == 0) continue;
-            NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
-            NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
+        if (ctx->p2pHalo) {
+            RET(halo_exchange(ctx, P, ctx->dT, ctx->sc));
+        } else {
+            k_eis_pack_s<<<grid_for(ctx, P.nSlots), kBlock, 0, ctx->sc>>>(P.nSlots, P.slotRow, ctx->dT, ctx->sendbuf);
+            ctx->launches++;
+            NC(g_nccl.GroupStart());
+            for (int k = 0; k < P.h.nIfaces; ++k) {
+                const int off = P.h.patchStart[k], n = P.h.patchStart[k + 1] - off;
+                if (n == 0) continue;
+                NC(g_nccl.Send(ctx->sendbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
+                NC(g_nccl.Recv(ctx->recvbuf + off, n, ncclDouble, P.h.nbrRank[k], ctx->comm, ctx->sc));
+            }
+            NC(g_nccl.GroupEnd());
         }
-        NC(g_nccl.GroupEnd());
         LAUNCH(PC_EIS_SETUP, k_eis_scale_bou, grid_for(ctx, P.nSlots), P.nSlots, P.slotRow, ctx->dT, ctx->recvbuf,
-               ctx->bou, S);
+               ctx->haloDev, ctx->bou, S);
     }
     if (P.c16) {
         auto ks = k_eis_scale_vals<true>;
@@ -1212,7 +1268,10 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     while (!ctx->hS->done && enq < cap) {
         int n = (int)std::min<int64_t>(chunk, cap - enq);
         int i = 0;
-        if (ctx->useGraph && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
+        // one rank only: with processor patches the loop body forks onto the comm stream, and replaying that
+        // fork/join from a graph measured SLOWER than plain launches (2 GPUs: 497 vs 438 us per iteration,
+        // profiles/r02_bench_2gpu_graph_ab.md)
+        if (ctx->useGraph && ctx->nranks == 1 && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
             if (!P.iterGraph[form] && n >= kGraphIters) {
                 const uint64_t l0 = ctx->launches;
                 cudaGraph_t g = nullptr;
@@ -1436,6 +1495,112 @@ bool setup_peer_reduce(b200_ctx* c, std::string& why) {
     return ok;
 }
 
+// Peer-memory halo buffers for the CURRENT mesh (collective: called by every rank from b200_set_addressing after
+// the ranks agreed that the plan build succeeded).  Every rank always takes part in the one ncclAllGather and
+// in the agreement that follows; a local failure (allocation, export, import, a pair of ranks that shares two
+// patches, mismatched patch sizes) only clears p2pHalo -- on EVERY rank, because the minimum is taken -- and
+// the NCCL send/recv path is used instead.  Returns an error only when the collectives themselves fail.
+int setup_peer_halo(b200_ctx* ctx, DevPlan& P) {
+    const int n = ctx->nranks;
+    const size_t nSlots = (size_t)ctx->nSlots;
+    struct Rec {
+        cudaIpcMemHandle_t h;
+        int32_t valid, nSlots;
+        int32_t off[kMaxRanks];   // slot offset of my patch towards rank q (-1: none)
+        int32_t cnt[kMaxRanks];
+    };
+    static_assert(sizeof(Rec) * (kMaxRanks + 1) <= sizeof(double) * kNSums * kMaxGrid, "partials arena too small");
+    Rec mine;
+    std::memset(&mine, 0, sizeof(mine));
+    for (int q = 0; q < kMaxRanks; ++q) mine.off[q] = -1;
+    // the exchange counters restart with every mesh, on every rank: two ranks that become neighbours only now
+    // may have executed different numbers of exchanges before (the fresh buffers' flags are zero as well)
+    CU(cudaMemsetAsync(reinterpret_cast<char*>(ctx->S) + offsetof(Scalars, haloSeq), 0,
+                       sizeof(Scalars) - offsetof(Scalars, haloSeq), ctx->sc));
+    bool ok = !ctx->forceNcclHalo && ctx->p2pReduce && n <= kMaxRanks;   // p2pReduce: IPC mapping is known to work
+    std::string why;
+    mine.nSlots = (int32_t)nSlots;
+    for (int k = 0; ok && k < P.h.nIfaces; ++k) {
+        const int q = P.h.nbrRank[k];
+        if (mine.off[q] >= 0) { ok = false; why = "two patches towards the same rank"; break; }
+        mine.off[q] = P.h.patchStart[k];
+        mine.cnt[q] = P.h.patchStart[k + 1] - P.h.patchStart[k];
+    }
+    const size_t bytes = sizeof(double) * 2 * nSlots + sizeof(unsigned long long) * 2 * kMaxRanks;
+    if (ok) {
+        cudaError_t e = cudaMalloc((void**)&ctx->haloLocal, bytes);
+        if (e == cudaSuccess) e = cudaMemset(ctx->haloLocal, 0, bytes);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.h, ctx->haloLocal);
+        if (e != cudaSuccess) { ok = false; why = cudaGetErrorString(e); cudaGetLastError(); }
+    }
+    mine.valid = ok ? 1 : 0;
+    unsigned char* d_send = reinterpret_cast<unsigned char*>(ctx->partials);
+    unsigned char* d_recv = d_send + sizeof(Rec);
+    std::vector<Rec> all((size_t)n);
+    CU(cudaMemcpyAsync(d_send, &mine, sizeof(Rec), cudaMemcpyHostToDevice, ctx->sc));
+    NC(g_nccl.AllGather(d_send, d_recv, sizeof(Rec), ncclUint8, ctx->comm, ctx->sc));
+    CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * (size_t)n, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaMemsetAsync(ctx->partials, 0, sizeof(Rec) * (size_t)(n + 1), ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    for (int k = 0; ok && k < n; ++k)
+        if (!all[k].valid) { ok = false; why = "rank " + std::to_string(k) + " has no exportable buffer"; }
+    if (ok && nSlots > 0) {
+        std::vector<double*> dst(2 * nSlots, nullptr);
+        std::vector<unsigned long long*> nbrFlag;
+        std::vector<int32_t> nbrRanks;
+        for (int k = 0; ok && k < P.h.nIfaces; ++k) {
+            const int q = P.h.nbrRank[k];
+            const int off = P.h.patchStart[k], cnt = P.h.patchStart[k + 1] - off;
+            if (all[q].off[ctx->rank] < 0 || all[q].cnt[ctx->rank] != cnt) {
+                ok = false; why = "processor patch towards rank " + std::to_string(q) + " has no counterpart of the same size";
+                break;
+            }
+            void* base = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&base, all[q].h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { ok = false; why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); break; }
+            ctx->haloMapped.push_back(base);
+            double* vals = reinterpret_cast<double*>(base);
+            const size_t qSlots = (size_t)all[q].nSlots;
+            unsigned long long* flags = reinterpret_cast<unsigned long long*>(vals + 2 * qSlots);
+            for (int par = 0; par < 2; ++par)
+                for (int j = 0; j < cnt; ++j)
+                    dst[(size_t)par * nSlots + (size_t)(off + j)] = vals + (size_t)par * qSlots + (size_t)(all[q].off[ctx->rank] + j);
+            nbrRanks.push_back(q);
+            nbrFlag.push_back(flags + ctx->rank);                 // flags[0][me] ...
+        }
+        if (ok) {
+            const size_t nNbr = nbrRanks.size();
+            std::vector<unsigned long long*> nf(2 * nNbr);
+            for (size_t k = 0; k < nNbr; ++k) { nf[k] = nbrFlag[k]; nf[nNbr + k] = nbrFlag[k] + kMaxRanks; }   // ... flags[1][me]
+            int rc = upload(ctx, &ctx->d_haloDst, dst);
+            if (rc == B200_OK) rc = upload(ctx, &ctx->d_haloNbrFlag, nf);
+            if (rc == B200_OK) rc = upload(ctx, &ctx->d_haloNbrRanks, nbrRanks);
+            if (rc == B200_OK && cudaStreamSynchronize(ctx->sc) != cudaSuccess) rc = B200_ECUDA;
+            if (rc != B200_OK) { ok = false; why = "upload of the halo tables failed"; cudaGetLastError(); }
+            else
+                ctx->haloDev = Halo{ctx->d_haloDst, ctx->d_haloNbrFlag,
+                                    reinterpret_cast<const unsigned long long*>(ctx->haloLocal + 2 * nSlots),
+                                    ctx->haloLocal, ctx->d_haloNbrRanks, (int)nSlots, (int)nNbr};
+        }
+    }
+    int v = ok ? 1 : 0;
+    RET(agree_min(ctx, &v, 1));
+    if (!ok && !why.empty() && !ctx->forceNcclHalo)
+        fprintf(stderr, "b200pcg[%d]: peer-memory halo exchange unavailable (%s); using NCCL send/recv\n", ctx->rank, why.c_str());
+    if (v == 1) {
+        ctx->p2pHalo = true;
+    } else {
+        // keep the export alive until every rank has closed its imports (next agreement below), then drop all
+        for (void* p : ctx->haloMapped) cudaIpcCloseMemHandle(p);
+        ctx->haloMapped.clear();
+        int z = 1;
+        RET(agree_min(ctx, &z, 1));
+        free_halo(ctx);
+    }
+    return B200_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -1506,6 +1671,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         c->disableTma = (std::string(e2) == "sym");
         c->disableWin = (std::string(e2) != "win");
         c->enableRanked = (std::string(e2) == "ranked");
+        c->disableSr = c->disableSym || c->enableRanked;
     }
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
@@ -1526,6 +1692,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     }
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e23 = getenv("B200PCG_GRAPH")) c->useGraph = atoi(e23) != 0;
+    if (const char* e24 = getenv("B200PCG_HALO")) c->forceNcclHalo = (std::string(e24) == "nccl");
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
     if (const char* e5 = getenv("B200PCG_RUN")) c->winRun = std::max(1, std::min(4096, atoi(e5)));
@@ -1684,6 +1851,7 @@ int b200_set_addressing(b200_ctx* ctx, uint64_t mesh_key, int32_t nCells, int32_
         CU(cudaMemsetAsync(tmp, 0, 2 * sizeof(double), ctx->sc));
         CU(cudaStreamSynchronize(ctx->sc));
         ctx->nGlobalCells = h;
+        RET(setup_peer_halo(ctx, ctx->plans[0]));
     } else if (rc != B200_OK) {
         free_mesh(ctx);
         return rc;
@@ -2022,6 +2190,7 @@ const char* b200_describe(b200_ctx* ctx) {
     const char* amul = !P.built ? "none"
                        : (P.sym && P.symWin) ? (ctx->winNext ? "k_spmv_sym_win<DOT,NEXT=1>" : "k_spmv_sym_win<DOT,NEXT=0>")
                        : (P.sym && P.symTma) ? "k_spmv_sym_tma<DOT,STAGES>"
+                       : P.sr ? "k_spmv_sr<INIT,DOT>"
                        : (P.sym && P.symRanked) ? "k_spmv_sym_ranked<INIT,DOT>"
                        : P.sym ? "k_spmv_sym<INIT,DOT>" : "k_spmv<INIT,DOT>";
     std::snprintf(buf, sizeof(buf),
@@ -2033,7 +2202,8 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"small_system_cluster_kernel\": %s, \"small_on_chip\": %s, \"small_n_max\": %d, "
                   "\"multicolour_tiles\": %d, \"multicolour_tile_rows\": %d, \"multicolour_amul\": \"%s\", "
                   "\"ell_col16_fraction_natural\": %.3f, \"ell_col16_fraction_multicolour\": %.3f, "
-                  "\"iteration_graphs\": %s, \"graph_iterations\": %d, \"graph_launches\": %llu}",
+                  "\"iteration_graphs\": %s, \"graph_iterations\": %d, \"graph_launches\": %llu, "
+                  "\"halo_exchange\": \"%s\"}",
                   amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
@@ -2041,7 +2211,8 @@ const char* b200_describe(b200_ctx* ctx) {
                   ctx->plans[1].built ? ctx->plans[1].h.nTiles : 0, ctx->plans[1].built ? ctx->plans[1].h.tileRows : 0,
                   !ctx->plans[1].built ? "n/a" : (ctx->plans[1].sym ? (ctx->plans[1].symTma ? "k_spmv_sym_tma" : "k_spmv_sym") : "k_spmv"),
                   P.c16 ? P.h.col16Fraction : 0.0, ctx->plans[1].c16 ? ctx->plans[1].h.col16Fraction : 0.0,
-                  ctx->useGraph ? "true" : "false", kGraphIters, (unsigned long long)ctx->graphLaunches);
+                  ctx->useGraph ? "true" : "false", kGraphIters, (unsigned long long)ctx->graphLaunches,
+                  ctx->nranks == 1 ? "none" : (ctx->p2pHalo ? "peer-memory stores (k_pack_p2p)" : "ncclSend/ncclRecv"));
     ctx->profJson = buf;
     return ctx->profJson.c_str();
 }

@@ -52,6 +52,14 @@ class PlanView:
                 n = L.b200_debug_plan_get(h, ("sym." + nm).encode(), C.byref(ptr), C.byref(eb))
                 self.sym[nm] = (np.empty(0, dtype=dt) if n <= 0 else
                                 np.frombuffer((C.c_char * (n * eb.value)).from_address(ptr.value), dtype=dt).copy())
+            L.b200_debug_plan_sr_valid.argtypes = [C.c_void_p]
+            self.srValid = bool(L.b200_debug_plan_sr_valid(h))
+            self.sr = {}
+            for nm, dt in (("meta", np.uint32), ("ownBase", np.int64), ("ownFace", np.int32)):
+                ptr, eb = C.c_void_p(), C.c_int32()
+                n = L.b200_debug_plan_get(h, ("sr." + nm).encode(), C.byref(ptr), C.byref(eb))
+                self.sr[nm] = (np.empty(0, dtype=dt) if n <= 0 else
+                               np.frombuffer((C.c_char * (n * eb.value)).from_address(ptr.value), dtype=dt).copy())
             L.b200_debug_plan_renumbered.argtypes = [C.c_void_p]
             L.b200_debug_plan_span.argtypes = [C.c_void_p, C.c_int]
             L.b200_debug_plan_span.restype = C.c_double
@@ -150,6 +158,33 @@ class PlanView:
                 assert sorted(staged) == list(range(nL + nU))
                 for k in range(nL + nU):
                     acc = acc + staged[k]
+            out[r] = acc
+        return out
+
+    def spmv_sr(self, diag_i, upper, x_i):
+        """numpy emulation of k_spmv_sr (renumbered natural plans): one meta word per entry, in ascending natural
+        face order; q == 31: the row's next own value, else the q-th own value of row `column`."""
+        meta, ownBase, ownFace = self.sr["meta"], self.sr["ownBase"], self.sr["ownFace"]
+        ov = np.zeros(ownFace.size)
+        m = ownFace >= 0
+        ov[m] = upper[ownFace[m]]
+        out = np.empty(self.N)
+        for r in range(self.N):
+            acc = diag_i[r] * x_i[r]
+            jown = 0
+            for j in range(self.nTotal[r]):
+                w = int(meta[self.entry(r, j)])
+                a, q = w >> 5, w & 31
+                assert a == self.col[self.entry(r, j)]
+                if q == 31:
+                    assert a > r
+                    pos = int(ownBase[r // 32]) + 32 * jown + (r % 32)
+                    jown += 1
+                else:
+                    assert a < r
+                    pos = int(ownBase[a // 32]) + 32 * q + (a % 32)
+                assert ownFace[pos] == self.faceOf[self.entry(r, j)]     # the SAME coefficient, stored once
+                acc = acc + ov[pos] * x_i[a]
             out[r] = acc
         return out
 

@@ -365,7 +365,8 @@ def _ctx_with_env(env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("mode,small,spmv", [("0", "0", ""), ("1", "0", ""), ("1", "150000", ""), ("1", "0", "ranked")])
+@pytest.mark.parametrize("mode,small,spmv", [("0", "0", ""), ("1", "0", ""), ("1", "150000", ""), ("1", "0", "ranked"),
+                                             ("1", "0", "ell")])
 def test_rcm_renumbering_does_not_change_results(mode, small, spmv):
     """Rows renumbered by reverse Cuthill-McKee (forced) or not at all: assembly, Amul and flux stay
     bit-identical to the oracle, PCG + diagonal keeps the oracle's iteration counts, DIC-exact is
@@ -381,6 +382,9 @@ def test_rcm_renumbering_does_not_change_results(mode, small, spmv):
             assert c.describe()["renumbered_rcm"] == (mode == "1")
             if spmv == "ranked" and s.gamma_f is not None:
                 assert c.describe()["amul_natural"].startswith("k_spmv_sym_ranked")
+            if mode == "1":      # default on renumbered plans: the single-read face-ordered layout (k_spmv_sr)
+                assert c.describe()["amul_natural"].startswith(
+                    {"": "k_spmv_sr", "ell": "k_spmv<", "ranked": "k_spmv_sym_ranked" if s.gamma_f is not None else "k_spmv"}[spmv])
             if s.gamma_f is not None:
                 up, dg = c.assemble_laplacian(s.gamma_f, s.magSf, s.deltaCoeffs, -1.0, s.diag0)
                 up_ref, dg_ref = orc.laplacian_assemble(a.lowerAddr, a.upperAddr, a.nCells, s.gamma_f, s.magSf,

@@ -147,6 +147,12 @@ def test_renumbered_natural_plan_is_bit_exact(name, s):
         assert np.array_equal(y, orc.amul(s, x)[0])
     else:
         assert not P.symValid
+    # single-read face-ordered layout (k_spmv_sr): every coefficient stored once, row sums still bit-exact
+    assert P.srValid
+    own = P.sr["ownFace"]
+    assert np.array_equal(np.sort(own[own >= 0]), np.arange(a.nFaces))     # each face exactly once
+    y = P.to_natural(P.spmv_sr(P.to_internal(s.diag), s.upper, P.to_internal(x)))
+    assert np.array_equal(y, orc.amul(s, x)[0])
     # multicolour on top of the RCM base order: still a proper colouring
     Q = PlanView(MC, a, renumber=1)
     colour = np.searchsorted(Q.colourStart, np.arange(a.nCells), side="right") - 1
