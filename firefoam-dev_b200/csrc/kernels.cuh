@@ -658,90 +658,6 @@ k_spmv_sr(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restri
     if (DOT) reduce_finish<1>(dot, R);
 }
 
-// ---- ranked variant of the symmetric Amul (renumbered natural plans) ---------------------------
-// Rows follow the plan's RCM order, so the [lower | upper] split of the single-read layout is not
-// OpenFOAM's visiting order of the row.  Every entry carries the rank of its face among the row's
-// faces (ascending face index = the order in which lduMatrix::Amul's face loop updates the cell):
-// the products are staged by rank in a thread-private shared-memory column and added in rank order,
-// which makes the row sum bit-identical to the CPU loop on ANY row order.  <= 16 faces per row.
-constexpr int kMaxRanked = 16;
-template <bool INIT, bool DOT>
-__global__ void __launch_bounds__(kBlock)
-k_spmv_sym_ranked(int N, int WU, int WL, const uint32_t* __restrict__ rowLen,
-                  const int* __restrict__ uCol, const double* __restrict__ uVal,
-                  const uint32_t* __restrict__ lRef, const uint8_t* __restrict__ lRank,
-                  const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
-                  double* __restrict__ sA, Reduce R) {
-    if (R.S->done) return;
-    __shared__ double stage[kBlock / 32][kMaxRanked][32];   // 32 KB; column [.][.][lane] is private to a thread
-    constexpr int B = kSymBatch;
-    double dot[1] = {0.0};
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double (*my)[32] = stage[warp];
-    const int nSlices = (N + 31) >> 5;
-    const int warpsPerGrid = (gridDim.x * kBlock) >> 5;
-    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
-    for (int s = (blockIdx.x * kBlock + threadIdx.x) >> 5; s < nSlices; s += warpsPerGrid) {
-        const int r = (s << 5) + (int)lane;
-        if (r < N) {
-            const uint32_t len = rowLen[r];
-            const int nL = (int)(len & 0xffffu), nT = (int)(len >> 16), nU = nT - nL;
-            const uint32_t lb = (uint32_t)s * strideL + lane, ub = (uint32_t)s * strideU + lane;
-            const double xr = x[r];
-            const double d = diag[r];
-            for (int pass = 0; pass < (INIT ? 2 : 1); ++pass) {   // pass 1 (INIT): sumA, values by rank
-                for (int j0 = 0; j0 < nL; j0 += B) {
-                    uint32_t pk[B], rk[B];
-                    double v[B], xv[B];
-#pragma unroll
-                    for (int k = 0; k < B; ++k) {
-                        const bool on = j0 + k < nL;
-                        pk[k] = on ? lRef[lb + 32u * (j0 + k)] : 0u;
-                        rk[k] = on ? (uint32_t)lRank[lb + 32u * (j0 + k)] : 0u;
-                    }
-#pragma unroll
-                    for (int k = 0; k < B; ++k) {
-                        const bool on = j0 + k < nL;
-                        const uint32_t a = pk[k] >> 5;
-                        v[k] = on ? uVal[(a >> 5) * strideU + ((pk[k] & 31u) << 5) + (a & 31u)] : 0.0;
-                        xv[k] = (on && pass == 0) ? __ldg(&x[a]) : 1.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < B; ++k)
-                        if (j0 + k < nL) my[rk[k]][lane] = pass == 0 ? __dmul_rn(v[k], xv[k]) : v[k];
-                }
-                for (int j0 = 0; j0 < nU; j0 += B) {
-                    int cc[B];
-                    double v[B], xv[B];
-#pragma unroll
-                    for (int k = 0; k < B; ++k) {
-                        const bool on = j0 + k < nU;
-                        cc[k] = on ? uCol[ub + 32u * (j0 + k)] : 0;
-                        v[k] = on ? uVal[ub + 32u * (j0 + k)] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < B; ++k)
-                        xv[k] = (j0 + k < nU && pass == 0) ? __ldg(&x[cc[k] & 0x7ffffff]) : 1.0;
-#pragma unroll
-                    for (int k = 0; k < B; ++k)
-                        if (j0 + k < nU) my[(uint32_t)cc[k] >> 27][lane] = pass == 0 ? __dmul_rn(v[k], xv[k]) : v[k];
-                }
-                if (pass == 0) {
-                    double acc = __dmul_rn(d, xr);
-                    for (int j = 0; j < nT; ++j) acc = __dadd_rn(acc, my[j][lane]);
-                    y[r] = acc;
-                    if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
-                } else {
-                    double sa = d;
-                    for (int j = 0; j < nT; ++j) sa = __dadd_rn(sa, my[j][lane]);
-                    sA[r] = sa;
-                }
-            }
-        }
-    }
-    if (DOT) reduce_finish<1>(dot, R);
-}
-
 // ---- TMA-staged variant of the symmetric Amul -------------------------------------------------
 // Same arithmetic and row order as k_spmv_sym, but the streaming operands of a chunk of 256 rows
 // (row lengths, lower references, upper columns + values, x, diag: all contiguous in the sliced
@@ -894,169 +810,10 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint8_t* __restrict__ rowLen8,
     if (DOT) reduce_finish<1>(dot, R);
 }
 
-// ---- shared-memory-window variant of the symmetric Amul -----------------------------------------
-// ncu on k_spmv_sym_tma (profiles/r01_v4_ncu_full.md): 1.09 GB of bulk copies + 37.5 M gather
-// sectors (1.2 GB) per launch = 2.3 GB through the L2 in 205 us = 11.2 TB/s, which IS the L2->SM
-// throughput cap of the part (~6300 B/clk): the kernel is bound by the L2-served neighbour gathers,
-// not by HBM.  This variant removes most of them.  A CTA walks RUNS of `runLen` consecutive 256-row
-// chunks and keeps three rings in shared memory, filled by the bulk-copy engine:
-//     X ring (depth 4): x of chunks k-1, k, k+1 (+ k+2 in flight)
-//     V ring (depth 3): upper values of chunks k-1, k (+ k+1 in flight)
-//     B ring (depth 2): upper columns, lower references, row lengths, diag of chunk k (+ k+1)
-// so that every neighbour whose row lies in the previous / current / next chunk -- on a banded
-// (bandwidth-reduced) cell order that is most of them -- is served from shared memory at no extra
-// L2 traffic: the data was staged for its own row anyway.  Only out-of-window neighbours go to
-// L1/L2.  Runs are interleaved across CTAs (run j of CTA b = b + j*grid) so the whole grid still
-// sweeps the matrix as one front and far neighbours (+-nx*ny) stay L2 hits.
-// Arithmetic and row-sum order are those of k_spmv_sym: bit-identical results.
-constexpr int kWinX = 4, kWinV = 3, kWinB = 2;
-
-__host__ __device__ inline size_t win_b_bytes(int WU, int WL) {
-    return (size_t)kChunkRows * ((size_t)WU * 4 + (size_t)WL * 4 + 4 + 8);
-}
-__host__ __device__ inline size_t win_smem_bytes(int WU, int WL) {
-    return 128 + (size_t)kWinX * kChunkRows * 8 + (size_t)kWinV * kChunkRows * WU * 8 +
-           (size_t)kWinB * win_b_bytes(WU, WL);
-}
-
-template <bool DOT, bool NEXT>
-__global__ void __launch_bounds__(kBlock)
-k_spmv_sym_win(int N, int WU, int WL, int runLen, const uint32_t* __restrict__ rowLen,
-               const int* __restrict__ uCol, const double* __restrict__ uVal,
-               const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
-               const double* __restrict__ x, double* __restrict__ y, Reduce R) {
-    if (R.S->done) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int B = kSymBatch;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t* barX = reinterpret_cast<uint64_t*>(smem_raw);   // [kWinX]
-    uint64_t* barV = barX + kWinX;                            // [kWinV]
-    uint64_t* barB = barV + kWinV;                            // [kWinB]
-    double* ringX = reinterpret_cast<double*>(smem_raw + 128);
-    double* ringV = ringX + kWinX * kChunkRows;
-    const size_t vElems = (size_t)kChunkRows * WU;
-    unsigned char* ringB = reinterpret_cast<unsigned char*>(ringV + kWinV * vElems);
-    const size_t bBytes = win_b_bytes(WU, WL);
-    // B slot layout: diag | uCol | lRef | rowLen
-    const size_t oCol = (size_t)kChunkRows * 8, oRef = oCol + (size_t)kChunkRows * WU * 4,
-                 oLen = oRef + (size_t)kChunkRows * WL * 4;
-    const int nChunks = (N + kChunkRows - 1) / kChunkRows;
-    const uint32_t strideU = 32u * (uint32_t)WU, strideL = 32u * (uint32_t)WL;
-
-    // this CTA's chunk sequence: run j = blockIdx + j*grid, chunks (run*runLen ..+runLen)
-    int T = 0;
-    for (int64_t base = (int64_t)blockIdx.x * runLen; base < nChunks; base += (int64_t)gridDim.x * runLen)
-        T += (int)min((int64_t)runLen, (int64_t)nChunks - base);
-    auto chunkAt = [&](int k) -> int {
-        return (int)(((int64_t)blockIdx.x + (int64_t)(k / runLen) * gridDim.x) * runLen + (k % runLen));
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < kWinX + kWinV + kWinB; ++s) mbar_init(&barX[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issueX = [&](int k) {
-        const int s = k & (kWinX - 1);
-        mbar_expect_tx(&barX[s], kChunkRows * 8);
-        bulk_g2s(ringX + s * kChunkRows, x + (size_t)chunkAt(k) * kChunkRows, kChunkRows * 8, &barX[s]);
-    };
-    auto issueV = [&](int k) {
-        const int s = k % kWinV;
-        mbar_expect_tx(&barV[s], (uint32_t)(vElems * 8));
-        bulk_g2s(ringV + s * vElems, uVal + (size_t)chunkAt(k) * vElems, (uint32_t)(vElems * 8), &barV[s]);
-    };
-    auto issueB = [&](int k) {
-        const int s = k & (kWinB - 1);
-        unsigned char* st = ringB + (size_t)s * bBytes;
-        const size_t r0 = (size_t)chunkAt(k) * kChunkRows;
-        mbar_expect_tx(&barB[s], (uint32_t)bBytes);
-        bulk_g2s(st, diag + r0, kChunkRows * 8, &barB[s]);
-        bulk_g2s(st + oCol, uCol + r0 * WU, (uint32_t)(kChunkRows * WU * 4), &barB[s]);
-        if (WL > 0) bulk_g2s(st + oRef, lRef + r0 * WL, (uint32_t)(kChunkRows * WL * 4), &barB[s]);
-        bulk_g2s(st + oLen, rowLen + r0, kChunkRows * 4, &barB[s]);
-    };
-    if (tid == 0) {
-        for (int k = 0; k < kWinB && k < T; ++k) { issueB(k); issueV(k); }
-        for (int k = 0; k < kWinX - 1 && k < T; ++k) issueX(k);
-    }
-
-    double dot[1] = {0.0};
-    for (int k = 0; k < T; ++k) {
-        const int chunk = chunkAt(k);
-        const int kin = k % runLen;
-        const int lo = (kin != 0) ? -1 : 0;                                   // previous chunk staged?
-        const int hi = (NEXT && kin != runLen - 1 && k + 1 < T) ? 1 : 0;      // next chunk's x staged?
-        mbar_wait(&barB[k & (kWinB - 1)], (uint32_t)((k / kWinB) & 1));
-        mbar_wait(&barV[k % kWinV], (uint32_t)((k / kWinV) & 1));
-        mbar_wait(&barX[k & (kWinX - 1)], (uint32_t)((k / kWinX) & 1));
-        if (hi) mbar_wait(&barX[(k + 1) & (kWinX - 1)], (uint32_t)(((k + 1) / kWinX) & 1));
-        const unsigned char* st = ringB + (size_t)(k & (kWinB - 1)) * bBytes;
-        const double* sDiag = reinterpret_cast<const double*>(st);
-        const int* sCol = reinterpret_cast<const int*>(st + oCol);
-        const uint32_t* sRef = reinterpret_cast<const uint32_t*>(st + oRef);
-        const uint32_t* sLen = reinterpret_cast<const uint32_t*>(st + oLen);
-        const double* sVcur = ringV + (size_t)(k % kWinV) * vElems;
-        const double* sVprev = ringV + (size_t)((k + kWinV - 1) % kWinV) * vElems;
-        const double* sXcur = ringX + (k & (kWinX - 1)) * kChunkRows;
-        const int r = chunk * kChunkRows + (int)tid;
-
-        // x of column c: shared-memory ring when its chunk is staged, else L1/L2
-        auto getX = [&](uint32_t c) -> double {
-            const int d = (int)(c >> 8) - chunk;
-            return (d >= lo && d <= hi) ? ringX[(((uint32_t)(k + d)) & (kWinX - 1)) * kChunkRows + (c & 255u)]
-                                        : __ldg(&x[c]);
-        };
-        // value of the q-th upper entry of owner row a (a < r)
-        auto getV = [&](uint32_t a, uint32_t q) -> double {
-            const int d = (int)(a >> 8) - chunk;
-            const uint32_t loc = a & 255u;
-            const uint32_t sp = (loc >> 5) * strideU + (q << 5) + (loc & 31u);
-            if (d == 0) return sVcur[sp];
-            if (d >= lo) return sVprev[sp];      // d == -1 and the previous chunk is staged
-            return uVal[(a >> 5) * strideU + (q << 5) + (a & 31u)];
-        };
-
-        if (r < N) {
-            const uint32_t len = sLen[tid];
-            const int nL = (int)(len & 0xffffu), nU = (int)(len >> 16) - nL;
-            const uint32_t lb = warp * strideL + lane, ub = warp * strideU + lane;
-            double lv[B], lx[B], ux[B];
-#pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const uint32_t pk = (j < nL) ? sRef[lb + 32u * j] : ((uint32_t)r << 5);
-                lv[j] = (j < nL) ? getV(pk >> 5, pk & 31u) : 0.0;
-                lx[j] = (j < nL) ? getX(pk >> 5) : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < B; ++j) ux[j] = (j < nU) ? getX((uint32_t)sCol[ub + 32u * j]) : 0.0;
-            const double xr = sXcur[tid];
-            double acc = __dmul_rn(sDiag[tid], xr);
-#pragma unroll
-            for (int j = 0; j < B; ++j)
-                if (j < nL) acc = __dadd_rn(acc, __dmul_rn(lv[j], lx[j]));
-            for (int j = B; j < nL; ++j) {
-                const uint32_t p0 = sRef[lb + 32u * j];
-                acc = __dadd_rn(acc, __dmul_rn(getV(p0 >> 5, p0 & 31u), getX(p0 >> 5)));
-            }
-#pragma unroll
-            for (int j = 0; j < B; ++j)
-                if (j < nU) acc = __dadd_rn(acc, __dmul_rn(sVcur[ub + 32u * j], ux[j]));
-            for (int j = B; j < nU; ++j)
-                acc = __dadd_rn(acc, __dmul_rn(sVcur[ub + 32u * j], getX((uint32_t)sCol[ub + 32u * j])));
-            y[r] = acc;
-            if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
-        }
-        __syncthreads();   // every thread is done with chunk k (and with the previous chunk's slots)
-        if (tid == 0) {
-            if (k + kWinB < T) { issueB(k + kWinB); }
-            if (k + kWinV - 1 < T) issueV(k + kWinV - 1);
-            if (k + kWinX - 1 < T) issueX(k + kWinX - 1);
-        }
-    }
-    if (DOT) reduce_finish<1>(dot, R);
-}
+// (A shared-memory-WINDOW variant of this kernel -- x / value / column rings of the neighbouring chunks in shared
+// memory, so that in-window neighbours cost no L2 traffic -- was built and measured in round 1: it removed the L2
+// stalls (-19 % L2 sectors) but needed 1.7x the instructions and ran at 275 us against 205 us; the kernel is
+// co-limited by instruction issue.  It is not part of the product any more: profiles/r01_v5_spmv_win_vs_tma.md.)
 
 // ---- processor interfaces (OF-dev processorFvPatchField.C, lduMatrixUpdateMatrixInterfaces.C;
 //      SURVEY.md A.4) ------------------------------------------------------------------------

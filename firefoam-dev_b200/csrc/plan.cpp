@@ -417,9 +417,9 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
     // streamed the value moments earlier), whatever grouping the full-row ELL above uses.  Each group
     // in ascending face order: in the natural order that is OpenFOAM's visiting order of the whole row.
     // Not for level orders (neighbours far upstream) nor renumbered natural plans (the row sum must
-    // stay in pure face order there, which a [lower | upper] split does not give).
-    const bool ranked = (ordering == Ordering::Natural && !ident);
-    if (N > 0 && N <= (1 << 27) && ordering != Ordering::Levels) {
+    // stay in pure face order there, which a [lower | upper] split does not give: those get the
+    // face-ordered single-read layout, SrPlan, below).
+    if (N > 0 && N <= (1 << 27) && ordering != Ordering::Levels && !(ordering == Ordering::Natural && !ident)) {
         SymPlan& Sp = P.sym;
         Sp.rowLen.assign((size_t)N, 0u);
         int64_t wU = 0, wL = 0;
@@ -434,11 +434,7 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
             wL = std::max<int64_t>(wL, nLo);
         }
         const int64_t nU = (int64_t)P.nSlices * 32 * wU, nL = (int64_t)P.nSlices * 32 * wL;
-        int64_t wT = 0;
-        for (int32_t r = 0; r < N && ranked; ++r) wT = std::max<int64_t>(wT, Sp.rowLen[r] >> 16);
-        if (wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL && (!ranked || wT <= 16)) {
-            Sp.ranked = ranked;
-            if (ranked) Sp.lRank.assign((size_t)nL, 0);
+        if (wU <= 32 && nU < 0x7fffffffLL && nL < 0x7fffffffLL) {
             Sp.WU = (int32_t)wU;
             Sp.WL = (int32_t)wL;
             Sp.nU = nU;
@@ -459,14 +455,12 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
                     if (!ident) std::sort(ent.begin(), ent.end());
                     const int64_t ub = (int64_t)(r / 32) * 32 * wU + (r % 32);
                     int64_t j = 0;
-                    uint32_t rank = 0;
                     for (auto& fe : ent) {
                         if (fe.second > r) {
-                            Sp.uCol[ub + 32 * j] = fe.second | (ranked ? (int32_t)(rank << 27) : 0);
+                            Sp.uCol[ub + 32 * j] = fe.second;
                             Sp.uFace[ub + 32 * j] = fe.first;
                             ++j;
                         }
-                        ++rank;
                     }
                     for (; j < wU; ++j) Sp.uCol[ub + 32 * j] = r;
                 }
@@ -480,7 +474,6 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
                     if (!ident) std::sort(ent.begin(), ent.end());
                     const int64_t lb = (int64_t)(r / 32) * 32 * wL + (r % 32);
                     int64_t j = 0;
-                    uint32_t rank = 0;
                     for (auto& fe : ent) {
                         if (fe.second < r) {
                             const int32_t a = fe.second;
@@ -490,10 +483,8 @@ std::string build_plan(Ordering ordering, int32_t N, int32_t F, const int32_t* l
                             for (int32_t k = 0; k < aU; ++k)
                                 if (Sp.uFace[ab + 32 * (int64_t)k] == fe.first) { q = k; break; }
                             Sp.lRef[lb + 32 * j] = ((uint32_t)a << 5) | (uint32_t)q;
-                            if (ranked) Sp.lRank[lb + 32 * j] = (uint8_t)rank;
                             ++j;
                         }
-                        ++rank;
                     }
                 }
             }

@@ -51,13 +51,6 @@ struct SymPlan {
     std::vector<int32_t> uCol;    // [nU] column (padding: the row itself)
     std::vector<int32_t> uFace;   // [nU] natural face, -1 padding
     std::vector<uint32_t> lRef;   // [nL] (owner row << 5) | q
-    // Ranked form (renumbered natural plans): the [lower | upper] split follows the RCM row index, which
-    // is NOT OpenFOAM's visiting order of the row, so every entry carries its rank = position of its face
-    // among the row's faces in ascending order; the kernel stages the products by rank and adds them in
-    // rank order: bit-identical row sums on a renumbered mesh.  Upper ranks ride in the top 5 bits of
-    // uCol (rows < 2^27), lower ranks in lRank.  Needs <= 16 faces per row.
-    bool ranked = false;
-    std::vector<uint8_t> lRank;   // [nL]
 };
 
 // Single-read layout for RENUMBERED natural plans ("SR": face-ordered).  A renumbered row must still add its

@@ -66,7 +66,6 @@ int64_t b200_debug_plan_get(void* h, const char* name, const void** ptr, int32_t
     V("bRow", P.bRow) V("bStart", P.bStart) V("bSlot", P.bSlot)
     V("segStart", P.segStart) V("rowColour", P.rowColour) V("sym.rowLen", P.sym.rowLen)
     V("colBase", P.colBase) V("col16", P.col16)
-    V("sym.lRank", P.sym.lRank)
     V("sym.uCol", P.sym.uCol)
     V("sym.uFace", P.sym.uFace) V("sym.lRef", P.sym.lRef)
     V("sr.meta", P.sr.meta) V("sr.ownBase", P.sr.ownBase) V("sr.ownFace", P.sr.ownFace)
@@ -77,7 +76,6 @@ int32_t b200_debug_plan_sr_valid(void* h) { return ((HostPlan*)h)->sr.valid ? 1 
 int32_t b200_debug_plan_sym_valid(void* h) { return ((HostPlan*)h)->sym.valid ? 1 : 0; }
 int32_t b200_debug_plan_sym_wu(void* h) { return ((HostPlan*)h)->sym.WU; }
 int32_t b200_debug_plan_sym_wl(void* h) { return ((HostPlan*)h)->sym.WL; }
-int32_t b200_debug_plan_sym_ranked(void* h) { return ((HostPlan*)h)->sym.ranked ? 1 : 0; }
 double b200_debug_plan_col16_fraction(void* h) { return ((HostPlan*)h)->col16Fraction; }
 int32_t b200_debug_plan_ntiles(void* h) { return ((HostPlan*)h)->nTiles; }
 int32_t b200_debug_plan_ncolours(void* h) { return ((HostPlan*)h)->nColours; }

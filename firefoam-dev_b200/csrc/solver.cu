@@ -113,15 +113,12 @@ struct DevPlan {
     int64_t symNU = 0;
     int symWU = 0, symWL = 0;
     bool symTma = false;
-    bool symWin = false;
-    size_t symStage = 0, symWinBytes = 0;
+    size_t symStage = 0;
     uint32_t* sRowLen = nullptr;
     uint8_t* sRowLen8 = nullptr;  // nL | nU << 4 per row (bulk-copy staged kernel)
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
     uint32_t* sLRef = nullptr;
-    uint8_t* sLRank = nullptr;    // ranked form (renumbered natural plans)
-    bool symRanked = false;
     // single-read face-ordered layout of renumbered natural plans (plan.hpp SrPlan)
     bool sr = false;
     int64_t srNOwn = 0;
@@ -212,14 +209,6 @@ struct b200_ctx {
     // box (profiles/r01_tma_sweep.md): 2 stages x 4 CTAs/SM is the optimum -- deeper pipelines or more
     // CTAs shrink the L1 carve-out that serves the neighbour gathers.
     int symStages = 2, symPerSM = 0;
-    // shared-memory-window Amul (k_spmv_sym_win): run length in 256-row chunks (B200PCG_RUN), whether
-    // the next chunk's x is part of the window (B200PCG_NEXT), CTAs per SM (B200PCG_CTAS)
-    // Opt-in (B200PCG_SPMV=win): measured SLOWER than k_spmv_sym_tma on the 16 M hex box (275 vs 205 us,
-    // profiles/r01_v5_spmv_win_vs_tma.md): it removes the L2-latency stalls but needs 1.7x the
-    // instructions, and both kernels are issue-bound.
-    int winRun = 8;
-    bool winNext = true;
-    bool disableWin = true;
     // single-launch cluster kernel for small systems (k_pcg_small): up to this many cells
     // (B200PCG_SMALL_N, 0 disables), cluster size 8 or 16 (B200PCG_SMALL_CTAS)
     int tileRows = 0;             // B200PCG_TILE: rows per tile of large multicolour plans (0: colour-major).
@@ -231,7 +220,6 @@ struct b200_ctx {
     int fastMaxCtas = 16;         // B200PCG_FAST_CTAS: largest cluster the on-chip kernel may use
     int renumber = (int)Renumber::Auto;   // B200PCG_RENUMBER=0|1|auto: RCM base order (plan.hpp)
     bool disableCol16 = false;  // B200PCG_COL16=0: always 32-bit columns in the full-row ELL kernels
-    bool enableRanked = false;  // B200PCG_SPMV=ranked
     bool sortCols = false;      // B200PCG_SORT_COLS=1: multicolour plans order a row's entries by column (plan.hpp)
     bool dicDefaultEis = true;  // B200PCG_DIC=multicolour: code 2 (`preconditioner DIC`) keeps the three-kernel loop
     bool eisOverlap = true;     // B200PCG_EIS_OVERLAP=0: nranks > 1: exchange t exposed between the two sweeps (A/B switch)
@@ -244,7 +232,11 @@ struct b200_ctx {
     bool exactWidth = true;     // B200PCG_EXACT=0: always use the 4+4-slot generic instantiation
     bool disableTma = false;    // B200PCG_SPMV=sym: symmetric layout with direct loads (no bulk-copy staging)
     bool disableSym = false;    // B200PCG_SPMV=ell: keep the full-row sliced-ELL Amul (A/B switch)
-    bool disableSr = false;     // B200PCG_SPMV=ell|ranked: renumbered natural plans keep the full-row ELL / ranked form
+    bool enableSr = false;      // B200PCG_SPMV=sr: renumbered natural plans use the single-read face-ordered layout
+                                // (k_spmv_sr).  Opt-in: it moves 0.73x the DRAM bytes of the full-row ELL but its
+                                // dependent meta -> ownBase -> value chain and the extra 48 M gather sectors make it
+                                // latency-bound: 307 vs 185 us on the 5 M-cell polyhedral workload
+                                // (profiles/r02_ncu_full_poly_sr.md)
     // profiling
     bool useGraph = true;       // B200PCG_GRAPH=0: enqueue every loop body kernel by kernel
     bool prof = false;
@@ -365,11 +357,10 @@ void free_plan(DevPlan& P) {
     dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
     dev_free(P.col16); dev_free(P.colBase); P.c16 = false;
     dev_free(P.sUCol); dev_free(P.sUFace);
-    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8); dev_free(P.sLRank);
+    dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8);
     dev_free(P.rowB); dev_free(P.hb);
     dev_free(P.srMeta); dev_free(P.srOwnBase); dev_free(P.srOwnFace); dev_free(P.srOwnVal);
     P.sr = false;
-    P.symRanked = false;
     P.sym = false;
     P.built = false;
     P.h = HostPlan();
@@ -443,10 +434,10 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     // re-read misses L2, so those plans keep the full-row sliced ELL for Amul
     // the symmetric single-read Amul needs a row's earlier neighbours close upstream (L2 hits): natural
     // order, or a multicolour order that is tiled (or small enough to be L2-resident anyway)
-    // Both extensions are opt-in because they measured slower than the full-row ELL they replace
-    // (profiles/r01_v7_dic_tiles.md): the ranked form on renumbered natural plans (B200PCG_SPMV=ranked)
-    // and the single-read layout on tiled multicolour plans (B200PCG_TILE=<rows>).
-    const bool symOrder = (ord == Ordering::Natural && (!P.h.sym.ranked || ctx->enableRanked)) ||
+    // (renumbered natural plans take the face-ordered single-read layout below -- SrPlan -- instead; the
+    // single-read layout on tiled multicolour plans, B200PCG_TILE=<rows>, is opt-in: it measured slower than the
+    // full-row ELL it replaces, profiles/r01_v7_dic_tiles.md)
+    const bool symOrder = (ord == Ordering::Natural && !P.h.renumbered) ||
                           (ord == Ordering::MultiColour && P.h.nTiles > 1);
     if (P.h.sym.valid && !ctx->disableSym && symOrder) {
         SymPlan& Y = P.h.sym;
@@ -458,11 +449,6 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         RET(upload(ctx, &P.sUCol, Y.uCol));
         RET(upload(ctx, &P.sUFace, Y.uFace));
         RET(upload(ctx, &P.sLRef, Y.lRef));
-        P.symRanked = Y.ranked;
-        if (Y.ranked) {
-            Y.lRank.resize(rowsPad * Y.WL, 0);
-            RET(upload(ctx, &P.sLRank, Y.lRank));
-        }
         RET(dev_alloc(ctx, &P.sUVal, rowsPad * Y.WU));
         {
             // the layout's own row lengths (split by row index), padded: the staged kernel reads whole chunks
@@ -481,16 +467,7 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         }
         P.symNU = (int64_t)(rowsPad * Y.WU);
         P.symStage = sym_stage_bytes(Y.WU, Y.WL);
-        P.symTma = !ctx->disableTma && !Y.ranked && P.sRowLen8 && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
-        P.symWinBytes = win_smem_bytes(Y.WU, Y.WL);
-        P.symWin = !ctx->disableTma && !ctx->disableWin && !Y.ranked && P.symWinBytes <= 100 * 1024;
-        if (P.symWin) {
-            const int smemMax = 200 * 1024;
-            CU(cudaFuncSetAttribute(k_spmv_sym_win<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
-            CU(cudaFuncSetAttribute(k_spmv_sym_win<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
-            CU(cudaFuncSetAttribute(k_spmv_sym_win<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
-            CU(cudaFuncSetAttribute(k_spmv_sym_win<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
-        }
+        P.symTma = !ctx->disableTma && P.sRowLen8 && (128 + ctx->symStages * P.symStage) <= 48 * 1024;
         if (P.symTma) {
 #define B200_TMA_ATTR(...) CU(cudaFuncSetAttribute(k_spmv_sym_tma<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024))
             B200_TMA_ATTR(true, 2, 4, 4, true); B200_TMA_ATTR(false, 2, 4, 4, true);
@@ -503,7 +480,7 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
         P.symWL = Y.WL;
         P.sym = true;
     }
-    if (P.h.sr.valid && !ctx->disableSr && !P.sym) {
+    if (P.h.sr.valid && ctx->enableSr && !P.sym) {
         RET(upload(ctx, &P.srMeta, P.h.sr.meta));
         RET(upload(ctx, &P.srOwnBase, P.h.sr.ownBase));
         RET(upload(ctx, &P.srOwnFace, P.h.sr.ownFace));
@@ -602,27 +579,7 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R = mkR(ctx, halo ? STEP_NONE : step);
-    if (P.sym && P.symWin && !INIT) {
-        const size_t smem = P.symWinBytes;
-        int perSM = (int)((size_t)220 * 1024 / (smem + 1024));
-        if (perSM > 4) perSM = 4;
-        if (perSM < 1) perSM = 1;
-        if (ctx->symPerSM > 0) perSM = std::min(ctx->symPerSM, (int)((size_t)226 * 1024 / (smem + 1024)));
-        const int nChunks = (N + kChunkRows - 1) / kChunkRows;
-        const int nRuns = (nChunks + ctx->winRun - 1) / ctx->winRun;
-        int g = std::min(nRuns, perSM * ctx->numSMs);
-        if (g > kMaxGrid) g = kMaxGrid;
-        if (g < 1) g = 1;
-        prof_begin(ctx, PC_SPMV);
-        if (ctx->winNext)
-            k_spmv_sym_win<DOT, true><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, ctx->winRun, P.sRowLen, P.sUCol,
-                                                                   P.sUVal, P.sLRef, ctx->diag, x, y, R);
-        else
-            k_spmv_sym_win<DOT, false><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, ctx->winRun, P.sRowLen, P.sUCol,
-                                                                    P.sUVal, P.sLRef, ctx->diag, x, y, R);
-        prof_end(ctx, PC_SPMV);
-        ctx->launches++;
-    } else if (P.sym && P.symTma && !INIT) {
+    if (P.sym && P.symTma && !INIT) {
         const size_t smem = 128 + ctx->symStages * P.symStage;
         int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
         if (perSM > 8) perSM = 8;
@@ -646,10 +603,6 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         auto kern = k_spmv_sr<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.srMeta, P.srOwnBase,
                P.srOwnVal, ctx->diag, x, y, sA, R);
-    } else if (P.sym && P.symRanked) {
-        auto kern = k_spmv_sym_ranked<INIT, DOT>;
-        LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
-               P.sUCol, P.sUVal, P.sLRef, P.sLRank, ctx->diag, x, y, sA, R);
     } else if (P.sym) {
         auto kern = k_spmv_sym<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
@@ -1669,9 +1622,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e2 = getenv("B200PCG_SPMV")) {
         c->disableSym = (std::string(e2) == "ell");
         c->disableTma = (std::string(e2) == "sym");
-        c->disableWin = (std::string(e2) != "win");
-        c->enableRanked = (std::string(e2) == "ranked");
-        c->disableSr = c->disableSym || c->enableRanked;
+        c->enableSr = (std::string(e2) == "sr");
     }
     if (const char* e9 = getenv("B200PCG_SMALL_N")) c->smallN = std::max(0, atoi(e9));
     if (const char* e11 = getenv("B200PCG_SMALL_FAST")) c->disableFast = atoi(e11) == 0;
@@ -1695,8 +1646,6 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e24 = getenv("B200PCG_HALO")) c->forceNcclHalo = (std::string(e24) == "nccl");
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
-    if (const char* e5 = getenv("B200PCG_RUN")) c->winRun = std::max(1, std::min(4096, atoi(e5)));
-    if (const char* e6 = getenv("B200PCG_NEXT")) c->winNext = atoi(e6) != 0;
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->sm, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming)) != cudaSuccess ||
@@ -2188,14 +2137,12 @@ const char* b200_describe(b200_ctx* ctx) {
     char buf[2048];
     const DevPlan& P = ctx->plans[0];
     const char* amul = !P.built ? "none"
-                       : (P.sym && P.symWin) ? (ctx->winNext ? "k_spmv_sym_win<DOT,NEXT=1>" : "k_spmv_sym_win<DOT,NEXT=0>")
                        : (P.sym && P.symTma) ? "k_spmv_sym_tma<DOT,STAGES>"
                        : P.sr ? "k_spmv_sr<INIT,DOT>"
-                       : (P.sym && P.symRanked) ? "k_spmv_sym_ranked<INIT,DOT>"
                        : P.sym ? "k_spmv_sym<INIT,DOT>" : "k_spmv<INIT,DOT>";
     std::snprintf(buf, sizeof(buf),
                   "{\"amul_natural\": \"%s\", \"amul_permuted\": \"k_spmv<INIT,DOT>\", \"symWU\": %d, \"symWL\": %d, "
-                  "\"win_smem_bytes\": %zu, \"win_run_chunks\": %d, \"chunk_rows\": %d, \"tma_stages\": %d, "
+                  "\"chunk_rows\": %d, \"tma_stages\": %d, "
                   "\"nranks\": %d, \"peer_allreduce\": %s, \"nCells\": %d, \"nFaces\": %d, \"nSlots\": %d, \"sms\": %d, "
                   "\"renumbered_rcm\": %s, \"mean_face_span_natural\": %.1f, \"mean_face_span_used\": %.1f, "
                   "\"sectors_per_gather_natural\": %.2f, \"sectors_per_gather_used\": %.2f, "
@@ -2204,7 +2151,7 @@ const char* b200_describe(b200_ctx* ctx) {
                   "\"ell_col16_fraction_natural\": %.3f, \"ell_col16_fraction_multicolour\": %.3f, "
                   "\"iteration_graphs\": %s, \"graph_iterations\": %d, \"graph_launches\": %llu, "
                   "\"halo_exchange\": \"%s\"}",
-                  amul, P.symWU, P.symWL, P.symWinBytes, ctx->winRun, kChunkRows, ctx->symStages, ctx->nranks,
+                  amul, P.symWU, P.symWL, kChunkRows, ctx->symStages, ctx->nranks,
                   ctx->p2pReduce ? "true" : "false", ctx->N, ctx->F, ctx->nSlots, ctx->numSMs,
                   P.h.renumbered ? "true" : "false", P.h.spanNatural, P.h.spanUsed, P.h.sectorsNatural,
                   P.h.sectorsUsed, ctx->usedSmall ? "true" : "false", ctx->usedFast ? "true" : "false", ctx->smallN,

@@ -44,10 +44,7 @@ class PlanView:
             self.symWU, self.symWL = L.b200_debug_plan_sym_wu(h), L.b200_debug_plan_sym_wl(h)
             L.b200_debug_plan_ntiles.argtypes = [C.c_void_p]
             self.nTiles = L.b200_debug_plan_ntiles(h)
-            L.b200_debug_plan_sym_ranked.argtypes = [C.c_void_p]
-            self.symRanked = bool(L.b200_debug_plan_sym_ranked(h))
-            for nm, dt in (("uCol", np.int32), ("uFace", np.int32), ("lRef", np.uint32), ("rowLen", np.uint32),
-                           ("lRank", np.uint8)):
+            for nm, dt in (("uCol", np.int32), ("uFace", np.int32), ("lRef", np.uint32), ("rowLen", np.uint32)):
                 ptr, eb = C.c_void_p(), C.c_int32()
                 n = L.b200_debug_plan_get(h, ("sym." + nm).encode(), C.byref(ptr), C.byref(eb))
                 self.sym[nm] = (np.empty(0, dtype=dt) if n <= 0 else
@@ -135,29 +132,15 @@ class PlanView:
             acc = diag_i[r] * x_i[r]
             lb = (r // 32) * 32 * self.symWL + (r % 32)
             ub = (r // 32) * 32 * self.symWU + (r % 32)
-            staged = {}     # ranked form (k_spmv_sym_ranked): products staged by rank, added in rank order
             for j in range(nL):
                 pk = int(y["lRef"][lb + 32 * j])
                 a, q = pk >> 5, pk & 31
                 assert a < r
-                prod = uv[(a // 32) * 32 * self.symWU + 32 * q + (a % 32)] * x_i[a]
-                if self.symRanked:
-                    staged[int(y["lRank"][lb + 32 * j])] = prod
-                else:
-                    acc = acc + prod
+                acc = acc + uv[(a // 32) * 32 * self.symWU + 32 * q + (a % 32)] * x_i[a]
             for j in range(nU):
-                cc = int(y["uCol"][ub + 32 * j])
-                c = cc & 0x7ffffff if self.symRanked else cc
+                c = int(y["uCol"][ub + 32 * j])
                 assert c > r
-                prod = uv[ub + 32 * j] * x_i[c]
-                if self.symRanked:
-                    staged[cc >> 27] = prod
-                else:
-                    acc = acc + prod
-            if self.symRanked:
-                assert sorted(staged) == list(range(nL + nU))
-                for k in range(nL + nU):
-                    acc = acc + staged[k]
+                acc = acc + uv[ub + 32 * j] * x_i[c]
             out[r] = acc
         return out
 

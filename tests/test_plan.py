@@ -117,7 +117,7 @@ def test_rcm_renumbering_decision():
     P = PlanView(NAT, poly.addr, renumber=-1)
     assert P.renumbered and P.spanUsed < 0.5 * P.spanNatural
     assert np.array_equal(np.sort(P.perm), np.arange(poly.addr.nCells))
-    assert P.symValid and P.symRanked          # single-read layout with per-entry face ranks
+    assert P.srValid and not P.symValid         # renumbered: the face-ordered single-read layout (SrPlan)
     assert PlanView(MC, poly.addr, renumber=-1).renumbered
     assert not PlanView(LEV, poly.addr, renumber=1).renumbered
     hexm = mg.hex_block(24, 20, 16)
@@ -140,13 +140,6 @@ def test_renumbered_natural_plan_is_bit_exact(name, s):
     x = np.random.default_rng(11).standard_normal(a.nCells)
     y = P.to_natural(P.spmv(P.to_internal(s.diag), P.values(s.upper), P.to_internal(x)))
     assert np.array_equal(y, orc.amul(s, x)[0])
-    # ranked symmetric single-read layout: split by RCM row index, summed by face rank -> still bit-exact
-    if P.nTotal.max() <= 16:
-        assert P.symValid and P.symRanked
-        y = P.to_natural(P.spmv_sym(P.to_internal(s.diag), s.upper, P.to_internal(x)))
-        assert np.array_equal(y, orc.amul(s, x)[0])
-    else:
-        assert not P.symValid
     # single-read face-ordered layout (k_spmv_sr): every coefficient stored once, row sums still bit-exact
     assert P.srValid
     own = P.sr["ownFace"]

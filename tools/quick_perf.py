@@ -14,7 +14,7 @@ NX, NY, NZ = (int(a) for a in sys.argv[1:4])
 pre = sys.argv[4] if len(sys.argv) > 4 else "diagonal"
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 200
 exact = pre == "DIC-exact"
-mode = {"DIC-exact": "exact", "DIC-eisenstat": "eisenstat"}.get(pre, "multicolour")
+mode = {"DIC-exact": "exact", "DIC-eisenstat": "eisenstat", "DIC-multicolour": "multicolour"}.get(pre, "auto")
 t0 = time.time()
 s = mg.hex_block(NX, NY, NZ)
 print(f"generated N={s.addr.nCells} F={s.addr.nFaces} in {time.time()-t0:.1f}s", flush=True)
