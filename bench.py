@@ -736,9 +736,18 @@ def run_gpu(args):
     ctx.force_iterations(0)
     desc = ctx.describe()
     slots_all = [nslots]
+    per_rank = None
     if n > 1:
         slots_all = [None] * n
         dist.all_gather_object(slots_all, nslots)
+        # per-rank view of the profiled pass: kernel averages and the in-kernel waits (halo flags, peer reductions)
+        mine = {"rank": rank}
+        for k_, nm in (("spmv_dot", "amul_us"), ("p_psi_update", "k_p_us"), ("r_update_dots", "k_r_us"), ("iface_fix", "iface_fix_us"),
+                       ("_wait_halo_flags", "wait_halo_us"), ("_wait_peer_reduction", "wait_reduction_us")):
+            if k_ in prof:
+                mine[nm] = round(prof[k_]["avg_us"], 2)
+        per_rank = [None] * n
+        dist.all_gather_object(per_rank, mine)
 
     sections = {}
     if "dic_class" in extras:
@@ -784,9 +793,12 @@ def run_gpu(args):
         moved = (24 * N + 24 * F + 4 * N) + (40 * N + 32 * F) + 40 * N + 24 * N
     else:
         moved = (24 * N + 16 * F + 4 * N) + 48 * N + 32 * N
+    # compute kernels of one iteration, from the profiled pass (its event pool may cover fewer iterations than the
+    # solve has: normalise by the iterations it recorded)
+    it_rec = max(1, max(kernels.get("p_psi_update", {}).get("launches", 0), kernels.get("eis_p_psi_update", {}).get("launches", 0)))
     compute_us = sum(kernels[k]["avg_us"] * kernels[k]["launches"] for k in kernels
                      if k in ("spmv_dot", "p_psi_update", "r_update_dots", "dic_fwd", "dic_bwd", "eis_p_psi_update",
-                              "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual")) / max(1, pperf.nIterations)
+                              "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual")) / it_rec
     amul_kernel = desc.get("amul_permuted" if dic else "amul_natural", "?")
     dom_name = ("k_eis_bwd + k_eis_fwd per iteration (Eisenstat form: lduMatrix::Amul + DIC-class apply in two sweeps, "
                 "fused with gSumProd(wA,pA))" if eis else f"{amul_kernel} (lduMatrix::Amul fused with gSumProd(wA,pA))")
@@ -828,6 +840,7 @@ def run_gpu(args):
     }
     if n > 1:
         line["exposed_comm_us"] = iter_us - compute_us
+        line["per_rank_profile"] = per_rank
     line.update(sections)
     if sections.get("strong_base_1gpu"):
         sb = sections["strong_base_1gpu"]

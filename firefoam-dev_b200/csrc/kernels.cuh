@@ -69,6 +69,11 @@ struct Scalars {
     double cRatio;
     double sigma;          // +1 / -1: common sign of the DIC pivots (0: mixed or zero pivots -> error)
     int sinceCheck, needCheck;
+    // wait accounting of the current solve (device nanosecond timer, one thread each): time the consumer's first
+    // block spent waiting for its neighbours' halo flags, time the reducing kernels' last block spent waiting for
+    // the peers' partial sums, and the number of waits of each kind -- what "exposed communication" is made of
+    unsigned long long waitHaloNs, waitRedNs;
+    unsigned int nHaloWaits, nRedWaits;
     // number of cross-rank reductions this rank has EXECUTED (peer_allreduce_step).  Every rank
     // executes the same sequence (identical totals -> identical `done` decisions), so the counters
     // stay equal across ranks, and consecutive executed reductions strictly alternate buffer parity --
@@ -278,6 +283,8 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
 #pragma unroll
     for (int i = 0; i < kNSums; ++i) v[i] = 0.0;
     bool timedOut = false;
+    unsigned long long tw0 = 0;
+    if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
     if (lane < nranks) {
         PeerBuf* me = peers[rank];
         volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(&me->flags[par][lane]);
@@ -298,6 +305,12 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
             v[i] = *reinterpret_cast<volatile double*>(&me->vals[par][lane][i]);
     }
     const bool anyTimeout = __any_sync(0xffffffffu, timedOut);
+    if (lane == 0) {
+        unsigned long long tw1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+        S->waitRedNs += tw1 - tw0;
+        S->nRedWaits += 1u;
+    }
     double tot[kNSums];
 #pragma unroll
     for (int i = 0; i < kNSums; ++i) {
@@ -871,6 +884,8 @@ __device__ __forceinline__ const double* halo_acquire(const Halo& H, const doubl
     if (H.localFlags == nullptr) return ncclRecv;
     const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq);
     const int par = (int)(seq & 1ull);
+    unsigned long long tw0 = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
     if (threadIdx.x < H.nNbr) {
         const volatile unsigned long long* f = H.localFlags + par * kMaxRanks + H.nbrRanks[threadIdx.x];
         unsigned long long spins = 0, t0 = 0;
@@ -885,6 +900,12 @@ __device__ __forceinline__ const double* halo_acquire(const Halo& H, const doubl
         __threadfence_system();
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long tw1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+        S->waitHaloNs += tw1 - tw0;
+        S->nHaloWaits += 1u;
+    }
     return H.localVals + (size_t)par * H.nSlots;
 }
 

@@ -2094,7 +2094,7 @@ int b200_profile_enable(b200_ctx* ctx, int on) {
     if (!ctx) return B200_EINVAL;
     CU(cudaSetDevice(ctx->device));
     if (on && ctx->profPool.empty()) {
-        ctx->profPool.resize(2 * 8192);
+        ctx->profPool.resize(2 * 16384);
         for (auto& ev : ctx->profPool) CU(cudaEventCreate(&ev));
     }
     ctx->prof = on != 0;
@@ -2112,12 +2112,22 @@ const char* b200_profile_json(b200_ctx* ctx) {
     if (!ctx) return "{}";
     std::string s = "{";
     bool first = true;
-    char buf[256];
+    char buf[640];
     for (int i = 0; i < PC_COUNT; ++i) {
         if (!ctx->profN[i]) continue;
         std::snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %llu, \"total_ms\": %.6f, \"avg_us\": %.3f}",
                       first ? "" : ", ", kProfNames[i], (unsigned long long)ctx->profN[i],
                       ctx->profMs[i], 1e3 * ctx->profMs[i] / (double)ctx->profN[i]);
+        s += buf;
+        first = false;
+    }
+    if (ctx->nranks > 1 && ctx->hS) {
+        // wait accounting of the LAST solve (kernels.cuh Scalars): per-wait averages in us
+        const Scalars& h = *ctx->hS;
+        std::snprintf(buf, sizeof(buf), "%s\"_wait_halo_flags\": {\"launches\": %u, \"total_ms\": %.6f, \"avg_us\": %.3f}, "
+                      "\"_wait_peer_reduction\": {\"launches\": %u, \"total_ms\": %.6f, \"avg_us\": %.3f}",
+                      first ? "" : ", ", h.nHaloWaits, h.waitHaloNs * 1e-6, h.nHaloWaits ? h.waitHaloNs * 1e-3 / h.nHaloWaits : 0.0,
+                      h.nRedWaits, h.waitRedNs * 1e-6, h.nRedWaits ? h.waitRedNs * 1e-3 / h.nRedWaits : 0.0);
         s += buf;
         first = false;
     }
