@@ -261,6 +261,19 @@ struct PeerBuf {
     unsigned long long flags[2][kMaxRanks];
 };
 
+// system-scope release store / acquire load of a 64-bit flag (peer memory over NVLink).  A release store orders
+// the thread's earlier writes (and, cumulatively, writes it has synchronised with) before the flag; an acquire
+// load orders the thread's later reads after it -- the full two-way membar.sys of __threadfence_system() on
+// both sides of every flag cost ~4 us per wait on B200 (wait accounting at 4 GPUs, profiles/r02_*).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // one warp (all 32 lanes must call)
 __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* peers, int rank, int nranks,
                                                     int step) {
@@ -276,8 +289,7 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
         PeerBuf* dst = peers[lane];
 #pragma unroll
         for (int i = 0; i < kNSums; ++i) dst->vals[par][rank][i] = S->sums[i];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(&dst->flags[par][rank]) = seq;
+        st_release_sys(&dst->flags[par][rank], seq);
     }
     double v[kNSums];
 #pragma unroll
@@ -287,11 +299,11 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
     if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
     if (lane < nranks) {
         PeerBuf* me = peers[rank];
-        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(&me->flags[par][lane]);
+        const unsigned long long* f = &me->flags[par][lane];
         // bounded by TIME (5 s on the device's nanosecond timer, sampled every 1024 polls), not by a poll count
         // whose duration depends on the clock and on the NVLink round trip
         unsigned long long spins = 0, t0 = 0;
-        while (*f != seq) {
+        while (ld_acquire_sys(f) != seq) {
             if ((++spins & 1023ull) == 0) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -299,7 +311,6 @@ __device__ __forceinline__ void peer_allreduce_step(Scalars* S, PeerBuf* const* 
                 else if (now - t0 > kPeerTimeoutNs) { timedOut = true; break; }
             }
         }
-        __threadfence_system();
 #pragma unroll
         for (int i = 0; i < kNSums; ++i)
             v[i] = *reinterpret_cast<volatile double*>(&me->vals[par][lane][i]);
@@ -452,6 +463,162 @@ __device__ __forceinline__ int ell_col(const EllCols& E, int64_t e) {
     return __ldg(&E.colBase[e >> 5]) + (int)__ldg(&E.col16[e]);
 }
 
+// ---- processor-patch halo exchange over NVLink peer memory ---------------------------------------
+// Replaces initMatrixInterfaces / updateMatrixInterfaces' send + receive (OF-dev processorFvPatchField.C,
+// UIPstream/UOPstream) -- and the ncclSend/ncclRecv pair this library used before -- by direct stores: every
+// rank owns a receive buffer  double vals[2][nSlots]; unsigned long long flags[2][kMaxRanks]  in its HBM, mapped
+// into its neighbours with CUDA IPC.  The PACK kernel of the sender gathers x[faceCells] and stores each value
+// straight into the neighbour's buffer (the two sides of a processor patch list their faces in the same order,
+// so patch face j of the sender is slot j of the matching patch of the receiver); its last block then raises
+// the sender's flag in every neighbour.  The CONSUMER (interface fix-up of the Amul, halo term of the Eisenstat
+// sweeps) waits for its neighbours' flags at its start.  No NCCL kernel is involved: an NCCL send/recv kernel
+// (640 threads, ~60 K registers per CTA) cannot become resident beside the persistent Amul grid and was running
+// AFTER it -- ~40 us of exposed exchange per iteration on 2 GPUs (profiles/r02_*): the pack kernel can.
+// NCCL send/recv stays as the fall-back when peer mapping is unavailable (B200PCG_HALO=nccl forces it).
+struct Halo {
+    double* const* dst;                   // [2][nSlots] address of slot i's value in the neighbour's vals[par]
+    unsigned long long* const* nbrFlag;   // [2][nNbr]   address of flags[par][my rank] in neighbour k's buffer
+    const unsigned long long* localFlags; // this rank's flags[2][kMaxRanks]           (nullptr: NCCL mode)
+    const double* localVals;              // this rank's vals[2][nSlots]
+    const int* nbrRanks;                  // [nNbr]
+    int nSlots, nNbr;
+};
+
+__global__ void __launch_bounds__(kBlock)
+k_pack_p2p(Halo H, const int* __restrict__ slotRow, const double* __restrict__ x, Scalars* S) {
+    if (S->done) return;
+    __shared__ bool amLast;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq) + 1ull;
+    const int par = (int)(seq & 1ull);
+    double* const* dst = H.dst + (size_t)par * H.nSlots;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H.nSlots; i += gridDim.x * blockDim.x)
+        *dst[i] = __ldg(&x[slotRow[i]]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();     // cumulative over the block's stores (ordered before it by the barrier)
+        const unsigned int t = atomicAdd(&S->haloTicket, 1u);
+        amLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast) return;
+    if (threadIdx.x < H.nNbr) {
+        __threadfence_system();     // after the ticket that proves every block's fence has been executed
+        st_release_sys(H.nbrFlag[par * H.nNbr + threadIdx.x], seq);
+    }
+    if (threadIdx.x == 0) {
+        S->haloSeq = seq;
+        S->haloTicket = 0u;
+        __threadfence();
+    }
+}
+
+// Every thread of every block of a consumer kernel calls this once (uniformly), after the kernel's `done` test.
+// Returns the buffer that holds the neighbours' values of the current exchange.
+__device__ __forceinline__ const double* halo_acquire(const Halo& H, const double* ncclRecv, Scalars* S) {
+    if (H.localFlags == nullptr) return ncclRecv;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq);
+    const int par = (int)(seq & 1ull);
+    unsigned long long tw0 = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
+    if (threadIdx.x < H.nNbr) {
+        const unsigned long long* f = H.localFlags + par * kMaxRanks + H.nbrRanks[threadIdx.x];
+        unsigned long long spins = 0, t0 = 0;
+        while (ld_acquire_sys(f) < seq) {
+            if ((++spins & 1023ull) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kPeerTimeoutNs) { S->nonfinite = 2; break; }   // reported by the host
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long tw1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+        S->waitHaloNs += tw1 - tw0;
+        S->nHaloWaits += 1u;
+    }
+    return H.localVals + (size_t)par * H.nSlots;
+}
+
+// The PRODUCER side fused into the tail of the kernel that writes the exchanged vector (k_p writes pA): every CTA
+// stores the patch-face values of the rows IT has just written (list built on the host for the launch's grid)
+// straight into the neighbours' receive buffers, then the last CTA raises the flags -- the same protocol as
+// k_pack_p2p without its launch.  Every thread of the CTA calls this after a __syncthreads that follows the CTA's
+// last write of x.
+struct PackTail {
+    const int* ctaSStart;   // [grid + 1]; nullptr: no fused pack
+    const int* ctaS;        // [nSlots] slots of each CTA's rows
+    const int* slotRow;
+    Halo H;
+};
+__device__ __forceinline__ void pack_tail(const PackTail& T, const double* x, Scalars* S) {
+    __shared__ bool amLastPack;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq) + 1ull;
+    const int par = (int)(seq & 1ull);
+    double* const* dst = T.H.dst + (size_t)par * T.H.nSlots;
+    const int i1 = T.ctaSStart[blockIdx.x + 1];
+    for (int i = T.ctaSStart[blockIdx.x] + (int)threadIdx.x; i < i1; i += kBlock) {
+        const int slot = T.ctaS[i];
+        *dst[slot] = x[T.slotRow[slot]];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int t = atomicAdd(&S->haloTicket, 1u);
+        amLastPack = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLastPack) return;
+    if (threadIdx.x < T.H.nNbr) {
+        __threadfence_system();
+        st_release_sys(T.H.nbrFlag[par * T.H.nNbr + threadIdx.x], seq);
+    }
+    if (threadIdx.x == 0) {
+        S->haloSeq = seq;
+        S->haloTicket = 0u;
+        __threadfence();
+    }
+}
+
+// Interface fix-up fused into the tail of the Amul (peer-memory halos only).  The separate k_iface_fix launch --
+// 25 us of its own at 4 GPUs, before any waiting (per-rank wait accounting, profiles/r02_*) -- disappears: after
+// its chunk loop every CTA corrects the interface rows of the chunks IT computed (their y values were written by
+// this CTA: a __syncthreads away), adds the correction of (y, x) to its own partial dot product, and the kernel's
+// one reduce_finish performs the cross-rank reduction and the scalar step.  The rows of a CTA come from a list
+// built on the host for the launch's grid (chunk c belongs to CTA c mod grid).  Same per-row operation order as
+// k_iface_fix: slots in (patch, face) order.
+struct IfaceTail {
+    const int* ctaBStart;   // [grid + 1]; nullptr: no fused tail
+    const int* ctaB;        // [nBRows] interface-row indices of each CTA, ascending
+    const int* bRow;
+    const int* bStart;
+    const int* bSlot;
+    const double* bou;
+    Halo H;
+};
+// every thread of the CTA, after a __syncthreads that follows the CTA's last write of y
+template <bool DOT>
+__device__ __forceinline__ void iface_tail(const IfaceTail& T, const double* __restrict__ x, double* y, Scalars* S,
+                                           double& dot) {
+    // the neighbours' values were stored into this rank's receive buffer while the rows above were computed
+    const double* recv = halo_acquire(T.H, nullptr, S);
+    const int i1 = T.ctaBStart[blockIdx.x + 1];
+    for (int i = T.ctaBStart[blockIdx.x] + (int)threadIdx.x; i < i1; i += kBlock) {
+        const int b = T.ctaB[i];
+        const int r = T.bRow[b];
+        const double y0 = y[r];
+        double acc = y0;
+        for (int e = T.bStart[b]; e < T.bStart[b + 1]; ++e) {
+            const int slot = T.bSlot[e];
+            acc = __dadd_rn(acc, -__dmul_rn(T.bou[slot], __ldcg(&recv[slot])));
+        }
+        y[r] = acc;
+        if (DOT) dot = __dadd_rn(dot, __dmul_rn(__dadd_rn(acc, -y0), x[r]));
+    }
+}
+
 // ---- lduMatrix::Amul / sumA (OF-dev lduMatrixATmul.C) ---------------------
 // One row per thread, rows of a warp = one ELL slice -> the j-th loads of a warp are
 // contiguous.  Row sum order: diag*x, then faces in ascending face order with the row as
@@ -462,7 +629,7 @@ __global__ void __launch_bounds__(kBlock)
 k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
        EllCols E, const double* __restrict__ val,
        const double* __restrict__ diag, const double* __restrict__ x, double* __restrict__ y,
-       double* __restrict__ sA, Reduce R) {
+       double* __restrict__ sA, Reduce R, IfaceTail T) {
     if (R.S->done) return;
     double dot[1] = {0.0};
     const int lane = threadIdx.x & 31;
@@ -507,6 +674,10 @@ k_spmv(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict_
             if (INIT) sA[r] = sa;
             if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(acc, xr));
         }
+    }
+    if (T.ctaBStart != nullptr) {
+        __syncthreads();       // rows of this CTA's slices were written by several of its warps
+        iface_tail<DOT>(T, x, y, R.S, dot[0]);
     }
     if (DOT) reduce_finish<1>(dot, R);
 }
@@ -727,7 +898,7 @@ __global__ void __launch_bounds__(kBlock)
 k_spmv_sym_tma(int N, int WU, int WL, const uint8_t* __restrict__ rowLen8,
                const int* __restrict__ uCol, const double* __restrict__ uVal,
                const uint32_t* __restrict__ lRef, const double* __restrict__ diag,
-               const double* __restrict__ x, double* __restrict__ y, Reduce R) {
+               const double* __restrict__ x, double* __restrict__ y, Reduce R, IfaceTail T) {
     if (R.S->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -820,6 +991,7 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint8_t* __restrict__ rowLen8,
             if (next < nChunks) issue(next, s);
         }
     }
+    if (T.ctaBStart != nullptr) iface_tail<DOT>(T, x, y, R.S, dot[0]);
     if (DOT) reduce_finish<1>(dot, R);
 }
 
@@ -830,85 +1002,6 @@ k_spmv_sym_tma(int N, int WU, int WL, const uint8_t* __restrict__ rowLen8,
 
 // ---- processor interfaces (OF-dev processorFvPatchField.C, lduMatrixUpdateMatrixInterfaces.C;
 //      SURVEY.md A.4) ------------------------------------------------------------------------
-// ---- processor-patch halo exchange over NVLink peer memory ---------------------------------------
-// Replaces initMatrixInterfaces / updateMatrixInterfaces' send + receive (OF-dev processorFvPatchField.C,
-// UIPstream/UOPstream) -- and the ncclSend/ncclRecv pair this library used before -- by direct stores: every
-// rank owns a receive buffer  double vals[2][nSlots]; unsigned long long flags[2][kMaxRanks]  in its HBM, mapped
-// into its neighbours with CUDA IPC.  The PACK kernel of the sender gathers x[faceCells] and stores each value
-// straight into the neighbour's buffer (the two sides of a processor patch list their faces in the same order,
-// so patch face j of the sender is slot j of the matching patch of the receiver); its last block then raises
-// the sender's flag in every neighbour.  The CONSUMER (interface fix-up of the Amul, halo term of the Eisenstat
-// sweeps) waits for its neighbours' flags at its start.  No NCCL kernel is involved: an NCCL send/recv kernel
-// (640 threads, ~60 K registers per CTA) cannot become resident beside the persistent Amul grid and was running
-// AFTER it -- ~40 us of exposed exchange per iteration on 2 GPUs (profiles/r02_*): the pack kernel can.
-// NCCL send/recv stays as the fall-back when peer mapping is unavailable (B200PCG_HALO=nccl forces it).
-struct Halo {
-    double* const* dst;                   // [2][nSlots] address of slot i's value in the neighbour's vals[par]
-    unsigned long long* const* nbrFlag;   // [2][nNbr]   address of flags[par][my rank] in neighbour k's buffer
-    const unsigned long long* localFlags; // this rank's flags[2][kMaxRanks]           (nullptr: NCCL mode)
-    const double* localVals;              // this rank's vals[2][nSlots]
-    const int* nbrRanks;                  // [nNbr]
-    int nSlots, nNbr;
-};
-
-__global__ void __launch_bounds__(kBlock)
-k_pack_p2p(Halo H, const int* __restrict__ slotRow, const double* __restrict__ x, Scalars* S) {
-    if (S->done) return;
-    __shared__ bool amLast;
-    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq) + 1ull;
-    const int par = (int)(seq & 1ull);
-    double* const* dst = H.dst + (size_t)par * H.nSlots;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H.nSlots; i += gridDim.x * blockDim.x)
-        *dst[i] = __ldg(&x[slotRow[i]]);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&S->haloTicket, 1u);
-        amLast = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!amLast) return;
-    __threadfence_system();
-    if (threadIdx.x < H.nNbr)
-        *reinterpret_cast<volatile unsigned long long*>(H.nbrFlag[par * H.nNbr + threadIdx.x]) = seq;
-    if (threadIdx.x == 0) {
-        S->haloSeq = seq;
-        S->haloTicket = 0u;
-        __threadfence();
-    }
-}
-
-// Every thread of every block of a consumer kernel calls this once (uniformly), after the kernel's `done` test.
-// Returns the buffer that holds the neighbours' values of the current exchange.
-__device__ __forceinline__ const double* halo_acquire(const Halo& H, const double* ncclRecv, Scalars* S) {
-    if (H.localFlags == nullptr) return ncclRecv;
-    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&S->haloSeq);
-    const int par = (int)(seq & 1ull);
-    unsigned long long tw0 = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
-    if (threadIdx.x < H.nNbr) {
-        const volatile unsigned long long* f = H.localFlags + par * kMaxRanks + H.nbrRanks[threadIdx.x];
-        unsigned long long spins = 0, t0 = 0;
-        while (*f < seq) {
-            if ((++spins & 1023ull) == 0) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > kPeerTimeoutNs) { S->nonfinite = 2; break; }   // reported by the host
-            }
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long tw1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
-        S->waitHaloNs += tw1 - tw0;
-        S->nHaloWaits += 1u;
-    }
-    return H.localVals + (size_t)par * H.nSlots;
-}
-
 __global__ void k_pack(int nSlots, const int* __restrict__ slotRow, const double* __restrict__ x,
                        double* __restrict__ sendbuf, const Scalars* S) {
     if (S->done) return;
@@ -1038,7 +1131,7 @@ k_precond_dot(int N, const double* __restrict__ rD, const double* __restrict__ r
 template <int ZMODE>
 __global__ void __launch_bounds__(kBlock)
 k_p(int N, double* __restrict__ psi, double* __restrict__ pA, const double* __restrict__ rA,
-    const double* __restrict__ rD, const double* __restrict__ zbuf, const Scalars* S) {
+    const double* __restrict__ rD, const double* __restrict__ zbuf, Scalars* S, PackTail T) {
     if (S->done) return;
     const bool first = (S->nIter == 0);
     const double beta = S->beta, alpha = S->alpha;
@@ -1069,6 +1162,10 @@ k_p(int N, double* __restrict__ psi, double* __restrict__ pA, const double* __re
               p = __dadd_rn(p, __dmul_rn(beta, po));
           }
           pA[i] = p; })
+    if (T.ctaSStart != nullptr) {
+        __syncthreads();       // the rows of this CTA's list were written by its own threads
+        pack_tail(T, pA, S);
+    }
 }
 #undef B200_Z
 

@@ -119,6 +119,12 @@ struct DevPlan {
     int *sUCol = nullptr, *sUFace = nullptr;
     double* sUVal = nullptr;
     uint32_t* sLRef = nullptr;
+    // interface rows of every CTA of the staged Amul's grid (kernels.cuh IfaceTail), for grid size tailGrid
+    int *ctaBStart = nullptr, *ctaB = nullptr;
+    int tailGrid = 0, tailUnitRows = 0;
+    // slots of every CTA of the k_p launch (kernels.cuh PackTail), for grid size packGrid
+    int *ctaSStart = nullptr, *ctaS = nullptr;
+    int packGrid = 0;
     // single-read face-ordered layout of renumbered natural plans (plan.hpp SrPlan)
     bool sr = false;
     int64_t srNOwn = 0;
@@ -239,6 +245,8 @@ struct b200_ctx {
                                 // (profiles/r02_ncu_full_poly_sr.md)
     // profiling
     bool useGraph = true;       // B200PCG_GRAPH=0: enqueue every loop body kernel by kernel
+    bool fuseIface = true;      // B200PCG_FUSE_IFACE=0: keep the interface fix-up a separate kernel (A/B switch)
+    bool graphMulti = false;    // B200PCG_GRAPH_MULTI=1: iteration graphs with nranks > 1 on single-stream loop bodies
     bool prof = false;
     bool profOpen = false;
     struct ProfRec { int cls; int iter; cudaEvent_t a, b; };
@@ -360,6 +368,8 @@ void free_plan(DevPlan& P) {
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8);
     dev_free(P.rowB); dev_free(P.hb);
     dev_free(P.srMeta); dev_free(P.srOwnBase); dev_free(P.srOwnFace); dev_free(P.srOwnVal);
+    dev_free(P.ctaBStart); dev_free(P.ctaB); P.tailGrid = 0;
+    dev_free(P.ctaSStart); dev_free(P.ctaS); P.packGrid = 0;
     P.sr = false;
     P.sym = false;
     P.built = false;
@@ -501,7 +511,6 @@ int ensure_plan(b200_ctx* ctx, Ordering ord, DevPlan** out) {
     std::vector<int64_t>().swap(P.h.sliceBase);
     std::vector<int32_t>().swap(P.h.perm);
     std::vector<int32_t>().swap(P.h.iperm);
-    std::vector<int32_t>().swap(P.h.slotRow);
     std::vector<int32_t>().swap(P.h.bSlot);
     P.built = true;
     return B200_OK;
@@ -566,19 +575,75 @@ int halo_exchange(b200_ctx* ctx, DevPlan& P, const double* x, cudaStream_t st) {
     return B200_OK;
 }
 
+// interface rows of every CTA of an Amul launch.  Staged kernel: chunk c of 256 rows is computed by CTA c mod grid
+// (unitRows 256, unitsPerCta 1); full-row ELL kernel: slice s of 32 rows by warp s mod (8 grid), CTA = warp / 8
+// (unitRows 32, unitsPerCta 8).
+int ensure_cta_lists(b200_ctx* ctx, DevPlan& P, int grid, int unitRows, int unitsPerCta) {
+    if (P.ctaBStart && P.tailGrid == grid && P.tailUnitRows == unitRows) return B200_OK;
+    auto ctaOf = [&](int32_t r) { return (int)(((int64_t)(r / unitRows) % ((int64_t)grid * unitsPerCta)) / unitsPerCta); };
+    CU(cudaStreamSynchronize(ctx->sc));
+    dev_free(P.ctaBStart);
+    dev_free(P.ctaB);
+    std::vector<int32_t> start((size_t)grid + 1, 0), list((size_t)P.h.nBRows);
+    for (int b = 0; b < P.h.nBRows; ++b) start[(size_t)ctaOf(P.h.bRow[(size_t)b]) + 1]++;
+    for (int g = 0; g < grid; ++g) start[(size_t)g + 1] += start[(size_t)g];
+    std::vector<int32_t> pos(start.begin(), start.end() - 1);
+    for (int b = 0; b < P.h.nBRows; ++b) list[(size_t)pos[(size_t)ctaOf(P.h.bRow[(size_t)b])]++] = b;
+    RET(upload(ctx, &P.ctaBStart, start));
+    RET(upload(ctx, &P.ctaB, list));
+    CU(cudaStreamSynchronize(ctx->sc));
+    P.tailGrid = grid;
+    P.tailUnitRows = unitRows;
+    return B200_OK;
+}
+
+// patch-face slots of every CTA of a k_p launch (B200_VEC_LOOP: double2 i = rows 2i, 2i+1 belongs to CTA
+// (i / 256) mod grid; the odd last row to CTA 0)
+int ensure_pack_lists(b200_ctx* ctx, DevPlan& P, int grid) {
+    if (P.ctaSStart && P.packGrid == grid) return B200_OK;
+    const int N = ctx->N;
+    auto ctaOf = [&](int32_t r) { return ((N & 1) && r == N - 1) ? 0 : (int)(((r >> 1) / kBlock) % grid); };
+    CU(cudaStreamSynchronize(ctx->sc));
+    dev_free(P.ctaSStart);
+    dev_free(P.ctaS);
+    const size_t nS = P.h.slotRow.size();
+    std::vector<int32_t> start((size_t)grid + 1, 0), list(nS);
+    for (size_t i = 0; i < nS; ++i) start[(size_t)ctaOf(P.h.slotRow[i]) + 1]++;
+    for (int g = 0; g < grid; ++g) start[(size_t)g + 1] += start[(size_t)g];
+    std::vector<int32_t> pos(start.begin(), start.end() - 1);
+    for (size_t i = 0; i < nS; ++i) list[(size_t)pos[(size_t)ctaOf(P.h.slotRow[i])]++] = (int32_t)i;
+    RET(upload(ctx, &P.ctaSStart, start));
+    RET(upload(ctx, &P.ctaS, list));
+    CU(cudaStreamSynchronize(ctx->sc));
+    P.packGrid = grid;
+    return B200_OK;
+}
+
+// can this plan's Amul correct its own interface rows (kernels.cuh IfaceTail)?
+bool amul_fuses_iface(const b200_ctx* ctx, const DevPlan& P) {
+    return ctx->nranks > 1 && P.nSlots > 0 && ctx->p2pHalo && ctx->fuseIface && ((P.sym && P.symTma) || (!P.sym && !P.sr));
+}
+
 // y = A x (+ interfaces) [+ (y,x) -> step]; INIT: also sA = sumA
+// packed: the producer of x has already stored its patch-face values into the neighbours (k_p's fused pack tail)
 template <bool INIT, bool DOT>
-int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA, int step) {
+int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA, int step, bool packed = false) {
     const int N = ctx->N;
     const bool halo = (ctx->nranks > 1 && P.nSlots > 0);
-    if (halo) {
+    // peer-memory halos + the staged Amul: the pack kernel runs on the MAIN stream ahead of the Amul (a few us: it
+    // only stores; the neighbours' values arrive while the Amul computes) and the Amul corrects its own interface
+    // rows in its tail -- one stream, no events, no separate fix-up kernel, one reduction instead of two
+    const bool fuseTail = !INIT && amul_fuses_iface(ctx, P);
+    if (halo && fuseTail) {
+        if (!packed) RET(halo_exchange(ctx, P, x, ctx->sc));
+    } else if (halo) {
         // the exchange runs on the comm stream, concurrently with the Amul
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
         RET(halo_exchange(ctx, P, x, ctx->sm));
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
-    Reduce R = mkR(ctx, halo ? STEP_NONE : step);
+    Reduce R = mkR(ctx, (halo && !fuseTail) ? STEP_NONE : step);
     if (P.sym && P.symTma && !INIT) {
         const size_t smem = 128 + ctx->symStages * P.symStage;
         int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
@@ -588,9 +653,14 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         const int nChunks = (N + kChunkRows - 1) / kChunkRows;
         int g = std::min(nChunks, perSM * ctx->numSMs);
         if (g > kMaxGrid) g = kMaxGrid;
+        IfaceTail T = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->haloDev};
+        if (fuseTail) {
+            RET(ensure_cta_lists(ctx, P, g, kChunkRows, 1));
+            T = IfaceTail{P.ctaBStart, P.ctaB, P.bRow, P.bStart, P.bSlot, ctx->bou, ctx->haloDev};
+        }
         prof_begin(ctx, PC_SPMV);
 #define B200_TMA_LAUNCH(...) k_spmv_sym_tma<DOT, __VA_ARGS__><<<g, kBlock, smem, ctx->sc>>>(N, P.symWU, P.symWL, P.sRowLen8, P.sUCol, \
-                                                                                   P.sUVal, P.sLRef, ctx->diag, x, y, R)
+                                                                                   P.sUVal, P.sLRef, ctx->diag, x, y, R, T)
         // exact-width instantiations (no tail loops, no idle slots) for the common narrow rows
         if (ctx->symStages == 3) B200_TMA_LAUNCH(3, 4, 4, true);
         else if (ctx->exactWidth && P.symWU <= 2 && P.symWL <= 2) B200_TMA_LAUNCH(2, 2, 2, false);
@@ -609,17 +679,23 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
                P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
     } else {
         const EllCols E{P.col, P.col16, P.colBase};
+        const int g = grid_for(ctx, N);
+        IfaceTail T = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->haloDev};
+        if (fuseTail) {
+            RET(ensure_cta_lists(ctx, P, g, 32, kBlock / 32));
+            T = IfaceTail{P.ctaBStart, P.ctaB, P.bRow, P.bStart, P.bSlot, ctx->bou, ctx->haloDev};
+        }
         if (P.c16) {
             auto kern = k_spmv<INIT, DOT, true>;
-            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val,
-                   ctx->diag, x, y, sA, R);
+            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, g, N, P.sliceBase, P.rowLen, E, P.val,
+                   ctx->diag, x, y, sA, R, T);
         } else {
             auto kern = k_spmv<INIT, DOT, false>;
-            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, E, P.val,
-                   ctx->diag, x, y, sA, R);
+            LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, g, N, P.sliceBase, P.rowLen, E, P.val,
+                   ctx->diag, x, y, sA, R, T);
         }
     }
-    if (halo) {
+    if (halo && !fuseTail) {
         CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
         Reduce R2 = mkR(ctx, step);
         auto fix = k_iface_fix<0, DOT>;
@@ -752,17 +828,26 @@ int enqueue_iteration(b200_ctx* ctx, DevPlan& P, int precond) {
     const int N = ctx->N;
     Scalars* S = ctx->S;
     const int gv = grid_for(ctx, (N + 1) / 2);
+    // N > 1, peer-memory halos, an Amul that corrects its own interface rows: k_p also PACKS -- its CTAs store the
+    // patch-face values of the rows they have just written into the neighbours (kernels.cuh PackTail), so the loop
+    // body is the same three launches as on one GPU
+    PackTail T = {nullptr, nullptr, nullptr, ctx->haloDev};
+    const bool packed = amul_fuses_iface(ctx, P);
+    if (packed) {
+        RET(ensure_pack_lists(ctx, P, gv));
+        T = PackTail{P.ctaSStart, P.ctaS, P.slotRow, ctx->haloDev};
+    }
     if (precond == B200_PRECOND_NONE) {
         auto k = k_p<0>;
-        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S, T);
     } else if (precond == B200_PRECOND_DIAGONAL) {
         auto k = k_p<1>;
-        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S, T);
     } else {
         auto k = k_p<2>;
-        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S);
+        LAUNCH(PC_KP, k, gv, N, ctx->psi, ctx->p, ctx->r, ctx->rD, ctx->w, S, T);
     }
-    RET((spmv_full<false, true>(ctx, P, ctx->p, ctx->w, nullptr, STEP_WAPA)));
+    RET((spmv_full<false, true>(ctx, P, ctx->p, ctx->w, nullptr, STEP_WAPA, packed)));
     if (precond == B200_PRECOND_NONE) {
         Reduce R = mkR(ctx, STEP_RES_WARA);
         auto k = k_r<0>;
@@ -816,6 +901,9 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
 // exchange of t across the processor patches on the comm stream (after everything enqueued on the compute
 // stream so far); the compute stream does NOT wait here: eis_halo_wait does
 int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
+    // peer-memory halos: the pack kernel only stores (a few us); it runs on the MAIN stream and the neighbours'
+    // values arrive while the sweep that follows computes -- no second stream, no events
+    if (ctx->p2pHalo) return halo_exchange(ctx, P, ctx->t, ctx->sc);
     CU(cudaEventRecord(ctx->evPack, ctx->sc));
     CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
     RET(halo_exchange(ctx, P, ctx->t, ctx->sm));
@@ -824,7 +912,7 @@ int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
 }
 // ... and the halo term hb = B- t once it has arrived
 int eis_halo_wait(b200_ctx* ctx, DevPlan& P) {
-    CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
+    if (!ctx->p2pHalo) CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
     LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
            ctx->recvbuf, ctx->haloDev, P.hb, ctx->S);
     return B200_OK;
@@ -1224,7 +1312,12 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         // one rank only: with processor patches the loop body forks onto the comm stream, and replaying that
         // fork/join from a graph measured SLOWER than plain launches (2 GPUs: 497 vs 438 us per iteration,
         // profiles/r02_bench_2gpu_graph_ab.md)
-        if (ctx->useGraph && ctx->nranks == 1 && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
+        // (B200PCG_GRAPH_MULTI=1: also with processor patches when the loop body stays on ONE stream -- peer-memory
+        // halos with the interface fix-up fused into the staged Amul; experiment switch)
+        const bool oneStream = ctx->nranks == 1 ||
+                               (ctx->graphMulti && ctx->p2pHalo && ctx->fuseIface &&
+                                (form == 3 || (P.sym && P.symTma) || (!P.sym && !P.sr)));
+        if (ctx->useGraph && oneStream && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
             if (!P.iterGraph[form] && n >= kGraphIters) {
                 const uint64_t l0 = ctx->launches;
                 cudaGraph_t g = nullptr;
@@ -1644,6 +1737,8 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e7 = getenv("B200PCG_EXACT")) c->exactWidth = atoi(e7) != 0;
     if (const char* e23 = getenv("B200PCG_GRAPH")) c->useGraph = atoi(e23) != 0;
     if (const char* e24 = getenv("B200PCG_HALO")) c->forceNcclHalo = (std::string(e24) == "nccl");
+    if (const char* e25 = getenv("B200PCG_FUSE_IFACE")) c->fuseIface = atoi(e25) != 0;
+    if (const char* e26 = getenv("B200PCG_GRAPH_MULTI")) c->graphMulti = atoi(e26) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||

@@ -22,8 +22,9 @@ def ngpus():
         return 0
 
 
-@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (4, None), (4, "no-overlap"),
-                                        (8, None), (8, "128"), (8, "no-overlap"), (8, "nccl-halo")])
+@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (2, "no-fuse"), (4, None),
+                                        (4, "no-overlap"), (8, None), (8, "128"), (8, "no-overlap"), (8, "nccl-halo"),
+                                        (8, "no-fuse")])
 def test_multigpu_parity(world, tile):
     """tile: B200PCG_TILE for the ranks (tiled multicolour order + symmetric Amul in the DIC-class mode;
     the default tile of 8192 rows does not engage on these small sub-meshes); "no-overlap": the Eisenstat
@@ -37,6 +38,9 @@ def test_multigpu_parity(world, tile):
     env = dict(os.environ)
     if tile == "nccl-halo":      # processor-patch halos over ncclSend/ncclRecv instead of peer-memory stores
         env["B200PCG_HALO"] = "nccl"
+        tile = None
+    elif tile == "no-fuse":      # interface fix-up as a separate kernel instead of the Amul's fused tail
+        env["B200PCG_FUSE_IFACE"] = "0"
         tile = None
     elif tile == "no-overlap":
         env["B200PCG_EIS_OVERLAP"] = "0"
