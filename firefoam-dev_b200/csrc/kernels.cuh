@@ -62,8 +62,10 @@ struct Scalars {
     double acc[kNSums];    // running totals across the kernels of one reduction
     double sums[kNSums];   // local totals (input of the all-reduce when nranks > 1)
     double gsums[kNSums];  // global totals (== sums when nranks == 1)
+    double acc2;           // correction of (y, x) by the interface terms (k_iface_pre -> k_iface_apply)
     unsigned int ticket;
-    unsigned int pad1;
+    unsigned int ticket2;  // block ticket of k_iface_pre, which reduces on the comm stream WHILE the Amul reduces on
+                           // the compute stream (its running total is acc2, its partials a second arena)
     // Eisenstat form (STEP_EIS_*): predictor ratio  true residual / sqrt(|rho|)  at the last check,
     // iterations since that check, and whether the current iteration's check kernel has to run
     double cRatio;
@@ -1033,6 +1035,88 @@ k_iface_fix(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bS
         if (DOT) dot[0] = __dadd_rn(dot[0], __dmul_rn(__dadd_rn(acc, -y0), x[r]));
     }
     if (DOT) reduce_finish<1>(dot, R);
+}
+
+// The interface update split in two so that only a short kernel is left on the critical path behind the Amul
+// (the one-kernel form above costs ~21 us of its own at 2 GPUs, 25+ at 4: a chain of dependent loads, two block
+// reductions and the cross-rank reduction, all serial behind the Amul):
+//   k_iface_pre   COMM stream, concurrent with the Amul: waits for the neighbours' halo flags, forms the products
+//                 prod[e] = coeffs*nbr of every patch face in the row CSR's order and the correction of the dot
+//                 product  sum_rows x[r] * (-sum_e prod[e])  (needs x and the halo, not y), reduced over its own
+//                 ticket / partials arena into S->acc2.
+//   k_iface_apply compute stream, after the Amul: y[r] = ((y[r] - prod[e0]) - prod[e1]) ... -- the same operation
+//                 order as updateMatrixInterfaces, so Amul stays bit-identical -- while block 0 adds acc2 to the
+//                 Amul's running total and performs the cross-rank reduction + scalar step at once: it depends on
+//                 no row of this kernel.
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_iface_pre(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bStart, const int* __restrict__ bSlot,
+            const double* __restrict__ bou, const double* recvNccl, Halo H, const double* __restrict__ x,
+            double* __restrict__ prod, double* __restrict__ partials2, Scalars* S) {
+    if (S->done) return;
+    const double* recv = halo_acquire(H, recvNccl, S);
+    double dot[1] = {0.0};
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
+        double h = 0.0;
+        for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
+            const int slot = bSlot[e];
+            const double p = __dmul_rn(bou[slot], __ldcg(&recv[slot]));
+            prod[e] = p;
+            h = __dadd_rn(h, p);
+        }
+        if (DOT) dot[0] = __dadd_rn(dot[0], -__dmul_rn(h, x[bRow[b]]));
+    }
+    if (!DOT) return;
+    __shared__ double sh[1][kBlock / 32];
+    __shared__ bool amLast;
+    block_sum<1>(dot, sh);
+    if (threadIdx.x == 0) {
+        partials2[blockIdx.x] = dot[0];
+        __threadfence();
+        amLast = (atomicAdd(&S->ticket2, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    double t[1] = {0.0};
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock) t[0] = __dadd_rn(t[0], __ldcg(&partials2[b]));
+    block_sum<1>(t, sh);
+    if (threadIdx.x == 0) {
+        S->acc2 = t[0];
+        S->ticket2 = 0u;
+        __threadfence();
+    }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_iface_apply(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bStart,
+              const double* __restrict__ prod, double* __restrict__ y, Reduce R) {
+    Scalars* S = R.S;
+    if (S->done) return;
+    if (DOT && blockIdx.x == 0) {
+        // (y, x) = the Amul's running total + the interface correction; then exactly what reduce_finish does when a
+        // reduction completes
+        if (threadIdx.x == 0) {
+            S->sums[0] = __dadd_rn(S->acc[0], S->acc2);
+            S->acc[0] = 0.0;
+            S->acc2 = 0.0;
+#pragma unroll
+            for (int i = 1; i < kNSums; ++i) S->sums[i] = 0.0;
+            if (S->nranks == 1) scalar_step(R.step, S, S->sums);
+        }
+        if (R.peers != nullptr) {
+            __syncthreads();
+            if (threadIdx.x < 32) peer_allreduce_step(S, R.peers, R.rank, S->nranks, R.step);
+        }
+    }
+    // block 0 joins the row loop after its reduction; the other blocks cover the rows meanwhile
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
+        const int r = bRow[b];
+        double acc = y[r];
+        for (int e = bStart[b]; e < bStart[b + 1]; ++e) acc = __dadd_rn(acc, -prod[e]);
+        y[r] = acc;
+    }
 }
 
 // ---- vector kernels ------------------------------------------------------------------------

@@ -177,6 +177,7 @@ struct b200_ctx {
            *w = nullptr, *rD = nullptr;
     double *t = nullptr, *dT = nullptr, *eD = nullptr;   // Eisenstat form: t, D~, D - 2 D~ (allocated on first use)
     double *bou = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
+    double *ifaceProd = nullptr, *partials2 = nullptr;   // k_iface_pre: products per patch face (CSR order), its partials
     // staging for the host entry points (natural order)
     double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
            *in_bou = nullptr, *in_f1 = nullptr, *in_f2 = nullptr, *in_f3 = nullptr;
@@ -245,7 +246,13 @@ struct b200_ctx {
                                 // (profiles/r02_ncu_full_poly_sr.md)
     // profiling
     bool useGraph = true;       // B200PCG_GRAPH=0: enqueue every loop body kernel by kernel
-    bool fuseIface = true;      // B200PCG_FUSE_IFACE=0: keep the interface fix-up a separate kernel (A/B switch)
+    bool fuseIface = false;     // B200PCG_FUSE_IFACE=1: N > 1, peer-memory halos: k_p packs in its tail and the Amul corrects
+                                // its own interface rows in its tail (three launches per iteration, one stream).
+                                // Opt-in: measured EQUAL to the separate pack / fix-up kernels at 2 GPUs (437.7 vs
+                                // 435.5 us per iteration): the tails add 12 us to k_p and 18 us to the Amul -- the
+                                // cost is the chain of dependent loads and the system-scope fence, not the launches
+    bool splitIface = true;     // B200PCG_SPLIT_IFACE=0: one k_iface_fix behind the Amul instead of k_iface_pre (comm stream,
+                                // concurrent with the Amul) + k_iface_apply (A/B switch)
     bool graphMulti = false;    // B200PCG_GRAPH_MULTI=1: iteration graphs with nranks > 1 on single-stream loop bodies
     bool prof = false;
     bool profOpen = false;
@@ -390,7 +397,7 @@ void free_mesh(b200_ctx* c) {
     dev_free(c->d_l); dev_free(c->d_u);
     dev_free(c->d_ownerStart); dev_free(c->d_losortStart); dev_free(c->d_losort);
     dev_free(c->diag); dev_free(c->src); dev_free(c->psi); dev_free(c->r); dev_free(c->p);
-    dev_free(c->w); dev_free(c->rD); dev_free(c->t); dev_free(c->dT); dev_free(c->eD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf);
+    dev_free(c->w); dev_free(c->rD); dev_free(c->t); dev_free(c->dT); dev_free(c->eD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf); dev_free(c->ifaceProd);
     dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
     dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3);
     dev_free(c->bfStart); dev_free(c->bfOrder); dev_free(c->scratch);
@@ -634,6 +641,7 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
     // only stores; the neighbours' values arrive while the Amul computes) and the Amul corrects its own interface
     // rows in its tail -- one stream, no events, no separate fix-up kernel, one reduction instead of two
     const bool fuseTail = !INIT && amul_fuses_iface(ctx, P);
+    const bool splitFix = halo && !fuseTail && !INIT && ctx->splitIface;
     if (halo && fuseTail) {
         if (!packed) RET(halo_exchange(ctx, P, x, ctx->sc));
     } else if (halo) {
@@ -641,6 +649,14 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         CU(cudaEventRecord(ctx->evPack, ctx->sc));
         CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
         RET(halo_exchange(ctx, P, x, ctx->sm));
+        if (splitFix) {
+            // products + dot correction on the comm stream, concurrent with the Amul (kernels.cuh k_iface_pre)
+            auto pre = k_iface_pre<DOT>;
+            pre<<<grid_for(ctx, P.h.nBRows), kBlock, 0, ctx->sm>>>(P.h.nBRows, P.bRow, P.bStart, P.bSlot, ctx->bou,
+                                                                   ctx->recvbuf, ctx->haloDev, x, ctx->ifaceProd,
+                                                                   ctx->partials2, ctx->S);
+            ctx->launches++;
+        }
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R = mkR(ctx, (halo && !fuseTail) ? STEP_NONE : step);
@@ -698,9 +714,14 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
     if (halo && !fuseTail) {
         CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
         Reduce R2 = mkR(ctx, step);
-        auto fix = k_iface_fix<0, DOT>;
-        LAUNCH(PC_IFACE, fix, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot,
-               ctx->bou, ctx->recvbuf, ctx->haloDev, x, y, R2);
+        if (splitFix) {
+            auto app = k_iface_apply<DOT>;
+            LAUNCH(PC_IFACE, app, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, ctx->ifaceProd, y, R2);
+        } else {
+            auto fix = k_iface_fix<0, DOT>;
+            LAUNCH(PC_IFACE, fix, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot,
+                   ctx->bou, ctx->recvbuf, ctx->haloDev, x, y, R2);
+        }
         if (INIT) {
             auto fix1 = k_iface_fix<1, false>;
             LAUNCH(PC_IFACE, fix1, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart,
@@ -721,6 +742,7 @@ int alloc_vectors(b200_ctx* ctx) {
     const size_t ns = (size_t)ctx->nSlots;
     RET(dev_alloc(ctx, &ctx->bou, ns)); RET(dev_alloc(ctx, &ctx->sendbuf, ns));
     RET(dev_alloc(ctx, &ctx->recvbuf, ns));
+    RET(dev_alloc(ctx, &ctx->ifaceProd, ns));
     return B200_OK;
 }
 
@@ -901,9 +923,9 @@ int eis_batch(const b200_ctx* ctx, const DevPlan& P) {
 // exchange of t across the processor patches on the comm stream (after everything enqueued on the compute
 // stream so far); the compute stream does NOT wait here: eis_halo_wait does
 int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
-    // peer-memory halos: the pack kernel only stores (a few us); it runs on the MAIN stream and the neighbours'
-    // values arrive while the sweep that follows computes -- no second stream, no events
-    if (ctx->p2pHalo) return halo_exchange(ctx, P, ctx->t, ctx->sc);
+    // (on the comm stream for either transport: the pack kernel's system-scope fence waits for the NVLink
+    // acknowledgements, ~8 us that are hidden there and were exposed when the pack ran on the main stream:
+    // 571 -> 589 us per iteration at 2 GPUs)
     CU(cudaEventRecord(ctx->evPack, ctx->sc));
     CU(cudaStreamWaitEvent(ctx->sm, ctx->evPack, 0));
     RET(halo_exchange(ctx, P, ctx->t, ctx->sm));
@@ -912,7 +934,7 @@ int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
 }
 // ... and the halo term hb = B- t once it has arrived
 int eis_halo_wait(b200_ctx* ctx, DevPlan& P) {
-    if (!ctx->p2pHalo) CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
+    CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
     LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
            ctx->recvbuf, ctx->haloDev, P.hb, ctx->S);
     return B200_OK;
@@ -1315,8 +1337,8 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
         // (B200PCG_GRAPH_MULTI=1: also with processor patches when the loop body stays on ONE stream -- peer-memory
         // halos with the interface fix-up fused into the staged Amul; experiment switch)
         const bool oneStream = ctx->nranks == 1 ||
-                               (ctx->graphMulti && ctx->p2pHalo && ctx->fuseIface &&
-                                (form == 3 || (P.sym && P.symTma) || (!P.sym && !P.sr)));
+                               (ctx->graphMulti && ctx->p2pHalo && ctx->fuseIface && form <= 2 &&
+                                ((P.sym && P.symTma) || (!P.sym && !P.sr)));
         if (ctx->useGraph && oneStream && !ctx->prof && P.h.nColours <= 8 && !P.iterGraphFailed[form]) {
             if (!P.iterGraph[form] && n >= kGraphIters) {
                 const uint64_t l0 = ctx->launches;
@@ -1739,6 +1761,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e24 = getenv("B200PCG_HALO")) c->forceNcclHalo = (std::string(e24) == "nccl");
     if (const char* e25 = getenv("B200PCG_FUSE_IFACE")) c->fuseIface = atoi(e25) != 0;
     if (const char* e26 = getenv("B200PCG_GRAPH_MULTI")) c->graphMulti = atoi(e26) != 0;
+    if (const char* e27 = getenv("B200PCG_SPLIT_IFACE")) c->splitIface = atoi(e27) != 0;
     if (const char* e8 = getenv("B200PCG_RENUMBER"))
         c->renumber = (std::string(e8) == "auto") ? (int)Renumber::Auto : (atoi(e8) != 0 ? (int)Renumber::Force : (int)Renumber::Off);
     if ((e = cudaStreamCreateWithFlags(&c->sc, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -1750,6 +1773,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(B200_ECUDA, cudaGetErrorString(e));
     if ((e = cudaMalloc((void**)&c->S, sizeof(Scalars))) != cudaSuccess ||
         (e = cudaMalloc((void**)&c->partials, sizeof(double) * kNSums * kMaxGrid)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->partials2, sizeof(double) * kMaxGrid)) != cudaSuccess ||
         (e = cudaHostAlloc((void**)&c->hS, sizeof(Scalars), cudaHostAllocDefault)) != cudaSuccess)
         return bail(B200_ECUDA, cudaGetErrorString(e));
     cudaMemset(c->S, 0, sizeof(Scalars));
@@ -1793,6 +1817,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     for (auto ev : c->profPool) cudaEventDestroy(ev);
     dev_free(c->S);
     dev_free(c->partials);
+    dev_free(c->partials2);
     if (c->hS) cudaFreeHost(c->hS);
     for (int b = 0; b < 2; ++b) {
         if (c->stageBuf[b]) cudaFreeHost(c->stageBuf[b]);

@@ -33,6 +33,22 @@ DIMS = (24, 20, 16)
 EIS = not os.environ.get("B200PCG_TILE")
 results = {"eisenstat_ran": EIS}
 s = mg.hex_block(*DIMS, *PROCS, rank)
+# collective safety of b200_set_addressing: ONE rank hands over a bad interface (neighbour rank out of range);
+# every rank must come back with an error -- none may be left inside a collective -- and the context stays usable
+from firefoam_dev_b200.ldu import LduAddressing, ProcessorLduInterface  # noqa: E402
+bad = s.addr
+if rank == world - 1 and s.addr.interfaces:
+    itf = [ProcessorLduInterface(world + 3, i.faceCells) if k == 0 else i for k, i in enumerate(s.addr.interfaces)]
+    bad = LduAddressing(s.addr.nCells, s.addr.lowerAddr, s.addr.upperAddr, itf)
+try:
+    ctx.set_addressing(bad)
+    results["bad_rank_rejected_everywhere"] = False
+except pkg.B200Error as e:
+    results["bad_rank_rejected_everywhere"] = True
+    results["bad_rank_message_rank0"] = str(e)
+flags = [None] * world
+dist.all_gather_object(flags, results["bad_rank_rejected_everywhere"])
+results["bad_rank_rejected_everywhere"] = all(flags)
 ctx.set_addressing(s.addr)
 
 # Amul with halo exchange

@@ -505,3 +505,34 @@ def test_staged_copies_of_pageable_memory_change_nothing():
     finally:
         c0.close()
         c1.close()
+
+
+def test_stale_plan_is_not_reused_for_a_different_mesh_at_the_same_key(ctx):
+    """The adapter's mesh key is the ADDRESS of the lduAddressing object: after fvMesh::clearOut / updateMesh a
+    different mesh with the same sizes can live there.  b200_set_addressing also compares a fingerprint of sampled
+    lowerAddr / upperAddr / faceCells entries: the stale plan must be rebuilt, results must stay the oracle's."""
+    n = 6000
+    s1 = random_ldu(n, 6.0, seed=21)
+    # a second system with the SAME cell and face counts but different connectivity
+    rng = np.random.default_rng(22)
+    perm = rng.permutation(n).astype(np.int32)
+    l2, u2 = perm[s1.addr.lowerAddr], perm[s1.addr.upperAddr]
+    lo, hi = np.minimum(l2, u2), np.maximum(l2, u2)
+    order = np.lexsort((hi, lo))
+    a2 = LduAddressing(n, lo[order].astype(np.int32), hi[order].astype(np.int32))
+    up2 = s1.upper[order]
+    dg2 = np.zeros(n)
+    np.add.at(dg2, a2.lowerAddr, -up2)
+    np.add.at(dg2, a2.upperAddr, -up2)
+    dg2 += 0.05
+    s2 = System(a2, dg2, up2, np.zeros(n), [], rng.standard_normal(n))
+    s2.source = orc.amul(s2, s2.xstar)[0]
+    assert (a2.nCells, a2.nFaces) == (s1.addr.nCells, s1.addr.nFaces)
+    a2.mesh_key = s1.addr.mesh_key                       # same "address", same sizes
+    for s in (s1, s2, s1):
+        x = np.random.default_rng(3).standard_normal(n)
+        ctx.set_addressing(s.addr)
+        assert np.array_equal(ctx.amul(s.matrix, [], x), orc.amul(s, x)[0])
+        xg, pg = solve_gpu(ctx, s, "diagonal", tol=1e-8, maxIter=3000)
+        xc, pc = solve_cpu(s, "diagonal", tol=1e-8, maxIter=3000)
+        assert pg.nIterations == pc.nIterations and relmax(xg, xc) < 1e-12

@@ -22,9 +22,9 @@ def ngpus():
         return 0
 
 
-@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (2, "no-fuse"), (4, None),
+@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (2, "fuse"), (2, "no-split"), (4, None),
                                         (4, "no-overlap"), (8, None), (8, "128"), (8, "no-overlap"), (8, "nccl-halo"),
-                                        (8, "no-fuse")])
+                                        (8, "fuse")])
 def test_multigpu_parity(world, tile):
     """tile: B200PCG_TILE for the ranks (tiled multicolour order + symmetric Amul in the DIC-class mode;
     the default tile of 8192 rows does not engage on these small sub-meshes); "no-overlap": the Eisenstat
@@ -39,8 +39,11 @@ def test_multigpu_parity(world, tile):
     if tile == "nccl-halo":      # processor-patch halos over ncclSend/ncclRecv instead of peer-memory stores
         env["B200PCG_HALO"] = "nccl"
         tile = None
-    elif tile == "no-fuse":      # interface fix-up as a separate kernel instead of the Amul's fused tail
-        env["B200PCG_FUSE_IFACE"] = "0"
+    elif tile == "no-split":     # one k_iface_fix behind the Amul instead of k_iface_pre (comm stream) + k_iface_apply
+        env["B200PCG_SPLIT_IFACE"] = "0"
+        tile = None
+    elif tile == "fuse":         # opt-in: pack fused into k_p's tail, interface fix-up into the Amul's tail
+        env["B200PCG_FUSE_IFACE"] = "1"
         tile = None
     elif tile == "no-overlap":
         env["B200PCG_EIS_OVERLAP"] = "0"
@@ -52,6 +55,8 @@ def test_multigpu_parity(world, tile):
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
     res = json.loads(line[len("MGPU_RESULT "):])
     assert res["amul_bit_exact"]
+    # a rank-local argument error in the collective b200_set_addressing fails on EVERY rank instead of hanging
+    assert res["bad_rank_rejected_everywhere"] and "another rank" in res["bad_rank_message_rank0"]
     for key in ("diagonal", "DIC-exact"):
         assert res[key]["iters"] == res[key]["oracle_iters"], (key, res[key])
         assert res[key]["relerr_vs_oracle"] < 1e-11, (key, res[key])
