@@ -332,6 +332,8 @@ class Env:
         self.n = args.gpus
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if os.environ.get("B200_BENCH_REVERSE_DEVICES"):      # experiment: does a slow rank follow the GPU or the sub-mesh?
+            self.local = int(os.environ.get("WORLD_SIZE", "1")) - 1 - self.local
         world = int(os.environ.get("WORLD_SIZE", "1"))
         if world != self.n:
             raise SystemExit(f"--gpus {self.n} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {self.n}")

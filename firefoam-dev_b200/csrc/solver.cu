@@ -251,8 +251,10 @@ struct b200_ctx {
                                 // Opt-in: measured EQUAL to the separate pack / fix-up kernels at 2 GPUs (437.7 vs
                                 // 435.5 us per iteration): the tails add 12 us to k_p and 18 us to the Amul -- the
                                 // cost is the chain of dependent loads and the system-scope fence, not the launches
-    bool splitIface = true;     // B200PCG_SPLIT_IFACE=0: one k_iface_fix behind the Amul instead of k_iface_pre (comm stream,
-                                // concurrent with the Amul) + k_iface_apply (A/B switch)
+    bool splitIface = false;    // B200PCG_SPLIT_IFACE=1: k_iface_pre (comm stream, concurrent with the Amul) + a short
+                                // k_iface_apply instead of one k_iface_fix behind the Amul.  Opt-in: measured EQUAL at 2
+                                // and 8 GPUs (467.3 vs 468.2 us per iteration at 8): the fix-up gets 17 us shorter, the
+                                // Amul 16 us longer (it shares the SMs with the pre kernel)
     bool graphMulti = false;    // B200PCG_GRAPH_MULTI=1: iteration graphs with nranks > 1 on single-stream loop bodies
     bool prof = false;
     bool profOpen = false;

@@ -22,7 +22,7 @@ def ngpus():
         return 0
 
 
-@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (2, "fuse"), (2, "no-split"), (4, None),
+@pytest.mark.parametrize("world,tile", [(2, None), (2, "64"), (2, "no-overlap"), (2, "nccl-halo"), (2, "fuse"), (2, "split"), (4, None),
                                         (4, "no-overlap"), (8, None), (8, "128"), (8, "no-overlap"), (8, "nccl-halo"),
                                         (8, "fuse")])
 def test_multigpu_parity(world, tile):
@@ -39,8 +39,8 @@ def test_multigpu_parity(world, tile):
     if tile == "nccl-halo":      # processor-patch halos over ncclSend/ncclRecv instead of peer-memory stores
         env["B200PCG_HALO"] = "nccl"
         tile = None
-    elif tile == "no-split":     # one k_iface_fix behind the Amul instead of k_iface_pre (comm stream) + k_iface_apply
-        env["B200PCG_SPLIT_IFACE"] = "0"
+    elif tile == "split":        # opt-in: k_iface_pre (comm stream, concurrent with the Amul) + k_iface_apply
+        env["B200PCG_SPLIT_IFACE"] = "1"
         tile = None
     elif tile == "fuse":         # opt-in: pack fused into k_p's tail, interface fix-up into the Amul's tail
         env["B200PCG_FUSE_IFACE"] = "1"
