@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call C (2 GPUs): new N > 1 bench sections on reduced sizes (logic check), then the real 2-GPU line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-2}
 run() { tag="$1"; shift; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call D (2 GPUs): peer-memory halo exchange: parity first, then A/B against the NCCL halo and against no graphs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-2}
 timeout 400 python -m pytest tests/test_multigpu.py -x -q > gpurun_out/r2d_pytest_mgpu_$N.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2d_pytest_mgpu_$N.log

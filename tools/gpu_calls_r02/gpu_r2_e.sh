@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call E (1 GPU): full suite with the SR layout / natural negSumDiag, polyhedral A/B, ncu evidence
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/r2e_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -6 gpurun_out/r2e_pytest_gpu.log
 for v in sr ell; do

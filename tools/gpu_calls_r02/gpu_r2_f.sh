@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call F (8 GPUs): multi-GPU parity at 8 and 4 ranks, then the driver-shaped N = 8 line with every section
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-8}
 timeout 600 python -m pytest tests/test_multigpu.py -q -k "8- or 4-None" > gpurun_out/r2f_pytest_mgpu_$N.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2f_pytest_mgpu_$N.log

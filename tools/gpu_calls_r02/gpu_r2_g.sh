@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call G (4 GPUs): where does the multi-GPU overhead sit?  per-rank kernel times + in-kernel wait accounting
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-4}
 run() { tag="$1"; shift; env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call H (2 GPUs): fused pack (k_p tail) + fused interface fix-up (Amul tail) + release/acquire flags: parity, then A/B
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-2}
 timeout 500 python -m pytest tests/test_multigpu.py -x -q > gpurun_out/r2i_pytest_mgpu_$N.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2i_pytest_mgpu_$N.log

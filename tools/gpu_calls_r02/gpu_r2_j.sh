@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call J (1 GPU): final code: full GPU suite, smoke(), default bench, reference arm (short), ncu of the Eisenstat sweeps
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 700 python -m pytest tests -m gpu -q > gpurun_out/r2j_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -6 gpurun_out/r2j_pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/r2j_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/r2j_smoke.log

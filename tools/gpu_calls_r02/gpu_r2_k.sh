@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call K (N GPUs): split interface update (k_iface_pre on the comm stream + k_iface_apply): parity, then A/B
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-2}
 if [ "$N" = "2" ]; then

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call L (8 GPUs): split vs single interface update at 8 ranks, then the N = 8 line (all sections but poly) with the winner
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-8}
 run() { tag="$1"; shift; env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call M (4 GPUs): does the slow rank follow the GPU or the sub-mesh?  same run with the rank -> device map reversed
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-4}
 run() { tag="$1"; shift; env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 \

@@ -2,7 +2,7 @@
 # First GPU calls of round 2: validate what round 1 left CPU-checked only, then measure it.
 #   usage (1 GPU):  gpurun --timeout 600 -- 'bash tools/gpu_round2_first.sh 1'
 #         (N GPUs): gpurun --gpus N --timeout 600 -- 'bash tools/gpu_round2_first.sh N'
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-1}
 if [ "$N" = "1" ]; then
