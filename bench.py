@@ -562,6 +562,8 @@ def dic_class_section(env, res, n_global):
     iters = sum(p.nIterations for p in perfs)
     prof, perf = profiled_pass(res, ctl)
     kern = kernel_table(prof, res.N, res.F, env.peak, True, perf.nColours, col_bytes_of(res.ctx))
+    # (eis_iface_rows: the first colour's interface rows swept ahead of / after the exchange, N > 1 only; iface_fix
+    # here is k_eis_halo, the halo term B t with its flag wait)
     keep = {k: v for k, v in kern.items() if k.startswith("eis_") or k.startswith("dic_") or k in ("spmv_dot", "iface_fix")}
     solve_ms = sum(p.solveMs for p in perfs) / 2
     return {"preconditioner": "DIC (DIC-class: multicolour IC0, Eisenstat form; log name DIC(mc)B200PCG)",

@@ -1674,6 +1674,7 @@ k_eis_bwd(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t*
     if (FWD0 != 0) reduce_finish<1>(s, R);
 }
 
+
 // nranks > 1, halo overlapped: backward sweep of the first colour's interface rows only (bRow[0 .. nB0):
 // bRow is ascending, so the first colour's interface rows are a prefix), ahead of the bulk of the colour:
 // once they are done t is complete on every interface row and the exchange can start.
@@ -1690,31 +1691,18 @@ k_eis_bwd_rows(int nB0, const int* __restrict__ bRow, const int64_t* __restrict_
         t[r] = eis_row_sub<0, C16, true>(E, val, t, sliceBase[r >> 5] + (r & 31), nLower, nTotal - nLower, ph[r]);
     }
 }
-// ... and their forward part once the halo term hb is there: no earlier neighbours, D- == 1:
-// y = p^ - t + (B- t); their share of (p^, w^) is added to the running reduction.
-__global__ void __launch_bounds__(kBlock)
-k_eis_fwd_rows(int nB0, const int* __restrict__ bRow, const double* __restrict__ hb,
-               const double* __restrict__ ph, const double* __restrict__ t, double* __restrict__ y, Reduce R) {
-    if (R.S->done) return;
-    double s[1] = {0.0};
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB0; b += gridDim.x * blockDim.x) {
-        const int r = bRow[b];
-        const double p = ph[r], tv = t[r];
-        const double yv = __dadd_rn(__dadd_rn(p, -tv), hb[b]);
-        y[r] = yv;
-        s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(tv, yv)));
-    }
-    reduce_finish<1>(s, R);
-}
 
 // halo term of the forward right-hand side (nranks > 1): hb[b] = (B- t)[bRow[b]] = -sum bou*t_nbr over the
 // row's processor faces in (patch, face) order (the sorted-segment form of updateMatrixInterfaces)
+template <bool ROWS>
 __global__ void __launch_bounds__(kBlock)
 k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ bSlot,
            const double* __restrict__ bou, const double* recvNccl, Halo H, double* __restrict__ hb,
-           Scalars* S) {
+           Scalars* S, int nB0, const int* __restrict__ bRow, const double* __restrict__ ph,
+           const double* __restrict__ t, double* __restrict__ y, Reduce R) {
     if (S->done) return;
     const double* recv = halo_acquire(H, recvNccl, S);
+    double s[1] = {0.0};
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBRows; b += gridDim.x * blockDim.x) {
         double acc = 0.0;
         for (int e = bStart[b]; e < bStart[b + 1]; ++e) {
@@ -1722,7 +1710,17 @@ k_eis_halo(int nBRows, const int* __restrict__ bStart, const int* __restrict__ b
             acc = __dadd_rn(acc, -__dmul_rn(bou[slot], __ldcg(&recv[slot])));
         }
         hb[b] = acc;
+        if (ROWS && b < nB0) {
+            // the forward part of the first colour's interface rows (what k_eis_fwd_rows does), now that their
+            // halo term is known: one launch less behind the exchange
+            const int r = bRow[b];
+            const double p = ph[r], tv = t[r];
+            const double yv = __dadd_rn(__dadd_rn(p, -tv), acc);
+            y[r] = yv;
+            s[0] = __dadd_rn(s[0], __dmul_rn(p, __dadd_rn(tv, yv)));
+        }
     }
+    if (ROWS) reduce_finish<1>(s, R);
 }
 
 // forward sweep over the rows [r0, r1) of one colour: y = p^ + (D- - 2) t [+ B- t] - L- y; every colour

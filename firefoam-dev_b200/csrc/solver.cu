@@ -80,14 +80,15 @@ enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
     PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH,
-    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_COUNT
+    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_EIS_ROWS, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
     "norm_resid", "recip", "precond_dot", "dic_calc_rd", "dic_fwd",
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
     "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells",
-    "eis_setup", "eis_p_psi_update", "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual"};
+    "eis_setup", "eis_p_psi_update", "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual",
+    "eis_iface_rows"};
 
 struct DevPlan {
     bool built = false;
@@ -935,10 +936,18 @@ int eis_halo_start(b200_ctx* ctx, DevPlan& P) {
     return B200_OK;
 }
 // ... and the halo term hb = B- t once it has arrived
-int eis_halo_wait(b200_ctx* ctx, DevPlan& P) {
+int eis_halo_wait(b200_ctx* ctx, DevPlan& P, bool firstColourRows = false) {
     CU(cudaStreamWaitEvent(ctx->sc, ctx->evRecv, 0));
-    LAUNCH(PC_IFACE, k_eis_halo, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
-           ctx->recvbuf, ctx->haloDev, P.hb, ctx->S);
+    Reduce R = mkR(ctx, STEP_NONE);
+    if (firstColourRows) {
+        auto kh = k_eis_halo<true>;
+        LAUNCH(PC_IFACE, kh, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
+               ctx->recvbuf, ctx->haloDev, P.hb, ctx->S, P.nB0, P.bRow, ctx->p, ctx->t, ctx->w, R);
+    } else {
+        auto kh = k_eis_halo<false>;
+        LAUNCH(PC_IFACE, kh, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bStart, P.bSlot, ctx->bou,
+               ctx->recvbuf, ctx->haloDev, P.hb, ctx->S, 0, P.bRow, ctx->p, ctx->t, ctx->w, R);
+    }
     return B200_OK;
 }
 
@@ -960,7 +969,7 @@ int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, int fuse0) {
             // the first colour's interface rows first, so that the exchange of t overlaps the bulk of the colour
             if (P.nB0 > 0) {
                 auto kr = k_eis_bwd_rows<C16>;
-                LAUNCH(PC_EIS_BWD, kr, grid_for(ctx, P.nB0), P.nB0, P.bRow, P.sliceBase, P.rowLen, E, P.val, ctx->p,
+                LAUNCH(PC_EIS_ROWS, kr, grid_for(ctx, P.nB0), P.nB0, P.bRow, P.sliceBase, P.rowLen, E, P.val, ctx->p,
                        ctx->t, S);
             }
             RET(eis_halo_start(ctx, P));
@@ -975,11 +984,7 @@ int launch_eis_sweeps(b200_ctx* ctx, DevPlan& P, bool halo, int fuse0) {
         }
     }
     if (halo && fuse0 == 2) {
-        RET(eis_halo_wait(ctx, P));
-        if (P.nB0 > 0) {
-            Reduce R = mkR(ctx, STEP_NONE);
-            LAUNCH(PC_EIS_FWD, k_eis_fwd_rows, grid_for(ctx, P.nB0), P.nB0, P.bRow, P.hb, ctx->p, ctx->t, ctx->w, R);
-        }
+        RET(eis_halo_wait(ctx, P, P.nB0 > 0));     // + the forward part of the first colour's interface rows
     } else if (halo) {
         // t is complete on every rank: pack + exchange on the comm stream, then the halo term B- t
         RET(eis_halo_start(ctx, P));
