@@ -158,6 +158,35 @@ void Foam::b200SetAddressing
 }
 
 
+void Foam::b200LduInterfaces
+(
+    const lduInterfaceFieldPtrsList& interfaceFields,
+    lduInterfacePtrsList& lduInterfaces
+)
+{
+    forAll(interfaceFields, patchi)
+    {
+        if (interfaceFields.set(patchi))
+        {
+            const word fieldType(interfaceFields[patchi].type());
+            if
+            (
+                !isA<processorLduInterfaceField>(interfaceFields[patchi])
+             || fieldType.find("Cyclic") != std::string::npos
+            )
+            {
+                FatalErrorInFunction
+                    << "B200PCG: unsupported coupled interface "
+                    << interfaceFields[patchi].type() << " on patch " << patchi
+                    << " (only processor interfaces are supported)"
+                    << exit(FatalError);
+            }
+            lduInterfaces.set(patchi, &interfaceFields[patchi].interface());
+        }
+    }
+}
+
+
 // * * * * * * * * * * * * * * * * Constructors  * * * * * * * * * * * * * * //
 
 Foam::B200PCG::B200PCG
@@ -252,26 +281,7 @@ Foam::solverPerformance Foam::B200PCG::solve
     const lduAddressing& addr = matrix_.lduAddr();
 
     lduInterfacePtrsList lduInterfaces(interfaces_.size());
-    forAll(interfaces_, patchi)
-    {
-        if (interfaces_.set(patchi))
-        {
-            const word fieldType(interfaces_[patchi].type());
-            if
-            (
-                !isA<processorLduInterfaceField>(interfaces_[patchi])
-             || fieldType.find("Cyclic") != std::string::npos
-            )
-            {
-                FatalErrorInFunction
-                    << "B200PCG: unsupported coupled interface "
-                    << interfaces_[patchi].type() << " on patch " << patchi
-                    << " (only processor interfaces are supported)"
-                    << exit(FatalError);
-            }
-            lduInterfaces.set(patchi, &interfaces_[patchi].interface());
-        }
-    }
+    b200LduInterfaces(interfaces_, lduInterfaces);
 
     b200_ctx* ctx = b200Context();
     labelList coupledPatches;

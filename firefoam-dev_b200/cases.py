@@ -239,3 +239,39 @@ def p1_G_terms(seed=238, case=None):
              "lapSign": 1.0, "Su": -4.0 * (absorb * sigmaSB * T ** 4), "bCells": bCells,
              "bInternal": bInt, "bBoundary": bInt * refValue}
     return case, terms
+
+
+def transport_system(base, peclet=2.0, kappa=0.15, upwind=0.9, seed=1930):
+    """A U / Yi / h -shaped ASYMMETRIC lduMatrix on the topology of `base` (any meshgen.System): what
+    fvMatrix::solveSegregated hands to `smoothSolver` for
+        fvm::ddt(rho, U) + fvm::div(phi, U) - fvm::laplacian(muEff, U)        (solver/UEqn.H:19-30)
+    restated term by term (OF-dev EulerDdtScheme.C, gaussConvectionScheme.C fvmDiv, gaussLaplacianScheme.C):
+        div:        lower = -w phi;  upper = lower + phi;  negSumDiag         (w: owner-side interpolation weight)
+        laplacian:  upper -= D;  lower -= D;  diag[l] += D;  diag[u] += D      (`- fvm::laplacian`)
+        ddt:        diag += rho V / deltaT
+    No per-time-step U / Yi / h matrices exist in the reference (they need the whole solver), so the fields are
+    synthetic: D_f = |upper_f| of `base` (its diffusion coefficient), phi_f = peclet * D_f * U(-1, 1) (counter-based),
+    w = 0.5 +- (upwind - 0.5) on the upwind side, rho V / deltaT = kappa * sum over the cell's faces of (D_f + |phi_f|)
+    (kappa ~ 1 / Courant number: 0.15 makes symGaussSeidel need 10-30 sweeps, the shipped cases' time steps 1-4).
+    Returns a System with .lower set, source = A xstar (xstar of `base`, or a seeded smooth + noise field), x0 = 0."""
+    from .meshgen import System
+    a = base.addr
+    l, u = a.lowerAddr, a.upperAddr
+    N, F = a.nCells, a.nFaces
+    D = np.abs(np.asarray(base.upper, dtype=np.float64))
+    phi = peclet * D * uniform_pm1(seed, np.arange(F))
+    w = np.where(phi >= 0.0, upwind, 1.0 - upwind)
+    lower = -w * phi
+    upper = lower + phi
+    # (np.bincount adds in index order of appearance, like the face loops; much faster than np.add.at at 48 M faces)
+    acc = lambda idx, wts: np.bincount(idx, weights=wts, minlength=N)
+    diag = -(acc(l, lower) + acc(u, upper))          # negSumDiag
+    upper = upper - D
+    lower = lower - D
+    diag = diag + (acc(l, D) + acc(u, D))
+    aphi = D + np.abs(phi)
+    mass = acc(l, aphi) + acc(u, aphi)
+    diag = diag + kappa * mass + 1e-300
+    xstar = base.xstar if base.xstar is not None else 1.0 + 0.3 * uniform_pm1(seed + 1, np.arange(N))
+    y = diag * xstar + acc(u, lower * xstar[l]) + acc(l, upper * xstar[u])
+    return System(a, diag, upper, y, [], xstar, lower=lower)

@@ -38,7 +38,9 @@ enum Step : int {
     STEP_EIS_SIGN, // sign of the DIC pivots (sigma), or "unusable"
     STEP_EIS_RHO0, // rho_0 = (r^, r^); calibrates the true-residual predictor
     STEP_EIS_RHO,  // rho_k; beta; nIter++; decides whether this iteration needs a true-residual check
-    STEP_EIS_RES   // true residual |(D~+L) r^|_1 / normFactor; convergence; loop condition
+    STEP_EIS_RES,  // true residual |(D~+L) r^|_1 / normFactor; convergence; loop condition
+    // smoothSolver (k_gs_* kernels)
+    STEP_GS_RES    // final residual after nSweeps sweeps; nIter += nSweeps; convergence; loop condition
 };
 
 // Eisenstat form: how many iterations may pass between two evaluations of the true residual, as a function
@@ -54,6 +56,7 @@ struct Scalars {
     double tol, relTol;
     double nGlobalCells;
     int maxIter, minIter, forceIters, nranks;
+    int nSweeps, padS;     // smoothSolver: sweeps between two residual evaluations (STEP_GS_RES)
     // state
     double xRef, normFactor, initRes, finalRes;
     double wArA, wArAold, wApA, alpha, beta;
@@ -232,6 +235,23 @@ __device__ inline void scalar_step(int step, Scalars* S, const double* g) {
             S->cRatio = a > 0.0 ? S->finalRes / a : 0.0;
             S->sinceCheck = 0;
             S->needCheck = 0;
+            break;
+        }
+        case STEP_GS_RES: {
+            // smoothSolver::solve (OF-dev smoothSolver.C): do { smooth(nSweeps); finalResidual = ... }
+            // while (((nIterations += nSweeps) < maxIter && !converged) || nIterations < minIter)
+            S->finalRes = g[0] / S->normFactor;
+            S->nIter += S->nSweeps;
+            const bool conv = check_convergence(S);
+            S->converged = conv ? 1 : 0;
+            bool cont;
+            if (S->forceIters > 0) cont = S->nIter < S->forceIters;
+            else cont = (S->nIter < S->maxIter && !conv) || (S->nIter < S->minIter);
+            if (!(S->finalRes == S->finalRes) || fabs(S->finalRes) > 1.7e308) {
+                S->nonfinite = 1;
+                cont = false;
+            }
+            if (!cont) S->done = 1;
             break;
         }
         default:
@@ -1827,6 +1847,102 @@ k_eis_final(int N, double* __restrict__ psi, const double* __restrict__ xa, cons
         if (pend) x = __dadd_rn(x, __dmul_rn(alpha, t[i]));
         psi[i] = __dadd_rn(psi[i], __dmul_rn(sv[i], x));
     }
+}
+
+// ---- smoothSolver: GaussSeidel / symGaussSeidel on (a)symmetric lduMatrices ---------
+// Replaces GaussSeidelSmoother::smooth / symGaussSeidelSmoother::smooth and lduMatrix::residual (OF-dev
+// GaussSeidelSmoother.C, symGaussSeidelSmoother.C, lduMatrixATmul.C), which the reference selects for U, Yi, h
+// and k (cases/steckler/system/fvSolution:48-61).  Upstream's sweep is a sequential loop over the cells,
+//     psi_c = (bPrime_c - sum_{owned faces} upper_f psi_u) / diag_c;   bPrime_u -= lower_f psi_c   (scatter)
+// i.e. row c needs the NEW values of its lower neighbours and the OLD values of its upper ones.  In row form
+// that is one formula for both directions,
+//     psi_c = (b_c - sum_{lower nbrs} lower_f psi_l - sum_{upper nbrs} upper_f psi_u) / diag_c     in place,
+// applied to the rows in an order that respects the dependencies: rows grouped by dependency LEVEL of the cell
+// order (plan.hpp Ordering::Levels -- the forward sweep visits the levels ascending, the reverse sweep descending;
+// during the reverse sweep a row's lower neighbours still hold their forward values, which is exactly what
+// upstream's bPrime carries over) reproduces upstream BIT FOR BIT: same elimination order, and with the ELL
+// entries stored [lower | upper], each in ascending face order, the same order of subtractions
+// (tests/test_smooth_plan.py, numpy transliteration against the C oracle).  Grouped by COLOUR instead
+// (Ordering::MultiColour) the same kernel is a multicolour Gauss-Seidel: a different ordering of the same
+// smoother, one launch per colour.  The last group of a forward sweep and the first group of the reverse sweep
+// are the same rows with the same inputs: the reverse sweep starts at the group before it.
+
+// matrix value fill of the full-row ELL for lower != upper: the entry of row r on face f carries upper[f] when
+// r's cell owns the face (A[l][u] = upper), lower[f] when it is the face's neighbour (A[u][l] = lower)
+__global__ void __launch_bounds__(kBlock)
+k_fill_values_asym(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+                   const int* __restrict__ faceOf, const int* __restrict__ perm, const int* __restrict__ lowerAddr,
+                   const double* __restrict__ upper, const double* __restrict__ lower, double* __restrict__ val) {
+    for (int r = blockIdx.x * kBlock + threadIdx.x; r < N; r += gridDim.x * kBlock) {
+        const int c = perm ? perm[r] : r;
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int n = (int)(rowLen[r] >> 16);
+        for (int j = 0; j < n; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            const int f = faceOf[e];
+            val[e] = (__ldg(&lowerAddr[f]) == c) ? __ldg(&upper[f]) : __ldg(&lower[f]);
+        }
+    }
+}
+
+// one group (level / colour) of a Gauss-Seidel sweep: rows [r0, r1), in place.  The next row's row length /
+// slice base / b / diag are requested before the current row's gathers (as in k_eis_bwd).
+template <bool C16, int B, int CT>
+__global__ void __launch_bounds__(kBlock, CT)
+k_gs_rows(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+          EllCols E, const double* __restrict__ val, const double* __restrict__ diag,
+          const double* __restrict__ b, double* x, const Scalars* S) {
+    if (S->done) return;
+    const int stride = gridDim.x * kBlock;
+    int r = r0 + blockIdx.x * kBlock + threadIdx.x;
+    uint32_t len = 0;
+    int64_t sb = 0;
+    double bv = 0.0, dv = 1.0;
+#define B200_GS_LOAD(ROW, LEN, SB, BV, DV) \
+    { LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; BV = b[ROW]; DV = diag[ROW]; }
+    if (r < r1) B200_GS_LOAD(r, len, sb, bv, dv)
+    while (r < r1) {
+        const int rn = r + stride;
+        uint32_t lenN = 0;
+        int64_t sbN = 0;
+        double bvN = 0.0, dvN = 1.0;
+        if (B > 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
+        const double w = eis_row_sub<B, C16, false>(E, val, x, sb + (r & 31), 0, (int)(len >> 16), bv);
+        x[r] = __ddiv_rn(w, dv);
+        if (B == 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
+        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN;
+    }
+}
+
+// gSumMag(lduMatrix::residual(psi, source)): sum |b - A x| with the row sum in upstream's order
+// ((b - diag x) - faces ascending); STEP_GS_RES advances the sweep counter and decides whether the loop goes on
+template <bool C16, int B, int CT>
+__global__ void __launch_bounds__(kBlock, CT)
+k_gs_resid(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+           EllCols E, const double* __restrict__ val, const double* __restrict__ diag,
+           const double* __restrict__ b, const double* __restrict__ x, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    const int stride = gridDim.x * kBlock;
+    int r = blockIdx.x * kBlock + threadIdx.x;
+    uint32_t len = 0;
+    int64_t sb = 0;
+    double bv = 0.0, dv = 1.0;
+    if (r < N) B200_GS_LOAD(r, len, sb, bv, dv)
+    while (r < N) {
+        const int rn = r + stride;
+        uint32_t lenN = 0;
+        int64_t sbN = 0;
+        double bvN = 0.0, dvN = 1.0;
+        if (B > 0 && rn < N) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
+        double w = __dadd_rn(bv, -__dmul_rn(dv, x[r]));
+        w = eis_row_sub<B, C16, false>(E, val, x, sb + (r & 31), 0, (int)(len >> 16), w);
+        s[0] = __dadd_rn(s[0], fabs(w));
+        if (B == 0 && rn < N) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
+        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN;
+    }
+#undef B200_GS_LOAD
+    reduce_finish<1>(s, R);
 }
 
 // ---- assembly: gaussLaplacianScheme::fvmLaplacianUncorrected + negSumDiag ------------------

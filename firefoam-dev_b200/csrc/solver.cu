@@ -80,7 +80,7 @@ enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
     PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH,
-    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_EIS_ROWS, PC_COUNT
+    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_EIS_ROWS, PC_GS_ROWS, PC_GS_RESID, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
@@ -88,7 +88,7 @@ const char* kProfNames[PC_COUNT] = {
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
     "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells",
     "eis_setup", "eis_p_psi_update", "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual",
-    "eis_iface_rows"};
+    "eis_iface_rows", "gs_sweep_rows", "gs_residual"};
 
 struct DevPlan {
     bool built = false;
@@ -182,6 +182,11 @@ struct b200_ctx {
     // staging for the host entry points (natural order)
     double *in_diag = nullptr, *in_upper = nullptr, *in_src = nullptr, *in_psi = nullptr,
            *in_bou = nullptr, *in_f1 = nullptr, *in_f2 = nullptr, *in_f3 = nullptr;
+    double* in_lower = nullptr;      // asymmetric matrices (b200_smooth_solve / b200_amul_asym), allocated on first use
+    // smoothSolver
+    bool forceEll = false;           // an asymmetric matrix is loaded: Amul must take the full-row ELL (the single-read
+                                     // layouts store every coefficient once, i.e. assume lower == upper)
+    int gsSweeps = 1;                // |nSweeps| of the current smoothSolver call (Scalars::nSweeps)
     // boundary faces (b200_set_boundary_faces): CSR cell -> boundary faces in patch order
     int32_t nB = 0;
     std::vector<int32_t> hbCells;
@@ -402,7 +407,7 @@ void free_mesh(b200_ctx* c) {
     dev_free(c->diag); dev_free(c->src); dev_free(c->psi); dev_free(c->r); dev_free(c->p);
     dev_free(c->w); dev_free(c->rD); dev_free(c->t); dev_free(c->dT); dev_free(c->eD); dev_free(c->bou); dev_free(c->sendbuf); dev_free(c->recvbuf); dev_free(c->ifaceProd);
     dev_free(c->in_diag); dev_free(c->in_upper); dev_free(c->in_src); dev_free(c->in_psi);
-    dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3);
+    dev_free(c->in_bou); dev_free(c->in_f1); dev_free(c->in_f2); dev_free(c->in_f3); dev_free(c->in_lower);
     dev_free(c->bfStart); dev_free(c->bfOrder); dev_free(c->scratch);
     c->nB = 0; c->hbCells.clear(); c->scratchElems = 0;
     c->haveMesh = false;
@@ -535,6 +540,7 @@ int reset_scalars(b200_ctx* ctx, const b200_controls* ctl) {
     h.minIter = ctl ? ctl->minIter : 0;
     h.forceIters = ctx->forceIters;
     h.nranks = ctx->nranks;
+    h.nSweeps = ctx->gsSweeps;
     h.nGlobalCells = ctx->nGlobalCells;
     h.wArA = 1e20;
     h.wArAold = 1e20;
@@ -631,7 +637,8 @@ int ensure_pack_lists(b200_ctx* ctx, DevPlan& P, int grid) {
 
 // can this plan's Amul correct its own interface rows (kernels.cuh IfaceTail)?
 bool amul_fuses_iface(const b200_ctx* ctx, const DevPlan& P) {
-    return ctx->nranks > 1 && P.nSlots > 0 && ctx->p2pHalo && ctx->fuseIface && ((P.sym && P.symTma) || (!P.sym && !P.sr));
+    return ctx->nranks > 1 && P.nSlots > 0 && ctx->p2pHalo && ctx->fuseIface &&
+           (ctx->forceEll || (P.sym && P.symTma) || (!P.sym && !P.sr));
 }
 
 // y = A x (+ interfaces) [+ (y,x) -> step]; INIT: also sA = sumA
@@ -663,7 +670,7 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
         CU(cudaEventRecord(ctx->evRecv, ctx->sm));
     }
     Reduce R = mkR(ctx, (halo && !fuseTail) ? STEP_NONE : step);
-    if (P.sym && P.symTma && !INIT) {
+    if (P.sym && P.symTma && !INIT && !ctx->forceEll) {
         const size_t smem = 128 + ctx->symStages * P.symStage;
         int perSM = (int)((size_t)144 * 1024 / (smem + 1024));   // leave >= 80 KB of L1 for the gathers
         if (perSM > 8) perSM = 8;
@@ -688,11 +695,11 @@ int spmv_full(b200_ctx* ctx, DevPlan& P, const double* x, double* y, double* sA,
 #undef B200_TMA_LAUNCH
         prof_end(ctx, PC_SPMV);
         ctx->launches++;
-    } else if (P.sr) {
+    } else if (P.sr && !ctx->forceEll) {
         auto kern = k_spmv_sr<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.srMeta, P.srOwnBase,
                P.srOwnVal, ctx->diag, x, y, sA, R);
-    } else if (P.sym) {
+    } else if (P.sym && !ctx->forceEll) {
         auto kern = k_spmv_sym<INIT, DOT>;
         LAUNCH(INIT ? PC_SPMV_INIT : PC_SPMV, kern, grid_for(ctx, N, 4), N, P.symWU, P.symWL, P.sRowLen,
                P.sUCol, P.sUVal, P.sLRef, ctx->diag, x, y, sA, R);
@@ -1394,6 +1401,147 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
     prof_collect(ctx, ctx->hS->nIter);
 
     return finish_solve(ctx, P, perf);
+}
+
+// ---- smoothSolver (kernels.cuh "smoothSolver") ---------------------------------------------
+// matrix of one smoothSolver / asymmetric Amul call -> the plan's full-row ELL (both triangles), vectors -> plan order
+int load_system_asym(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* dn_upper, const double* dn_lower,
+                     const double* dn_src, const double* dn_psi) {
+    const int N = ctx->N;
+    if (dn_lower && dn_lower != dn_upper)
+        LAUNCH(PC_FILL, k_fill_values_asym, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.faceOf, P.perm, ctx->d_l,
+               dn_upper, dn_lower, P.val);
+    else
+        LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
+    LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_diag, ctx->diag);
+    if (dn_src) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_src, ctx->src);
+    if (dn_psi) LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_psi, ctx->psi);
+    return B200_OK;
+}
+
+// one group (dependency level / colour) of a sweep
+int launch_gs_rows(b200_ctx* ctx, DevPlan& P, int k) {
+    const int r0 = P.h.colourStart[(size_t)k], r1 = P.h.colourStart[(size_t)k + 1];
+    if (r1 <= r0) return B200_OK;
+    const EllCols E{P.col, P.col16, P.colBase};
+    const int g = grid_for(ctx, r1 - r0, ctx->sweepPerSM);
+#define B200_GS_ROWS(C16_, B_, CT_)                                                                        \
+    do {                                                                                                   \
+        auto kg = k_gs_rows<C16_, B_, CT_>;                                                                \
+        LAUNCH(PC_GS_ROWS, kg, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, ctx->psi, ctx->S); \
+    } while (0)
+    const bool wide = P.maxRowLen > 6;
+    if (P.c16 && wide) B200_GS_ROWS(true, 8, 3);
+    else if (P.c16) B200_GS_ROWS(true, 6, 4);
+    else if (wide) B200_GS_ROWS(false, 8, 3);
+    else B200_GS_ROWS(false, 6, 4);
+#undef B200_GS_ROWS
+    return B200_OK;
+}
+
+int launch_gs_resid(b200_ctx* ctx, DevPlan& P) {
+    const EllCols E{P.col, P.col16, P.colBase};
+    const int N = ctx->N;
+    const int g = grid_for(ctx, N, ctx->sweepPerSM);
+    Reduce R = mkR(ctx, STEP_GS_RES);
+#define B200_GS_RESID(C16_, B_, CT_)                                                                       \
+    do {                                                                                                   \
+        auto kg = k_gs_resid<C16_, B_, CT_>;                                                               \
+        LAUNCH(PC_GS_RESID, kg, g, N, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, ctx->psi, R);  \
+    } while (0)
+    const bool wide = P.maxRowLen > 6;
+    if (P.c16 && wide) B200_GS_RESID(true, 8, 3);
+    else if (P.c16) B200_GS_RESID(true, 6, 4);
+    else if (wide) B200_GS_RESID(false, 8, 3);
+    else B200_GS_RESID(false, 6, 4);
+#undef B200_GS_RESID
+    return B200_OK;
+}
+
+// smoothSolver::solve (OF-dev smoothSolver.C); all pointers are device pointers in natural order
+int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_lower,
+                const double* dn_src, double* dn_psi, const b200_smooth_controls* ctl, b200_perf* perf) {
+    if (ctl->smoother != B200_SMOOTHER_GAUSS_SEIDEL && ctl->smoother != B200_SMOOTHER_SYM_GAUSS_SEIDEL)
+        return fail(ctx, B200_EINVAL, "bad smoother code");
+    if (ctl->sweepMode != B200_SWEEP_MULTICOLOUR && ctl->sweepMode != B200_SWEEP_EXACT)
+        return fail(ctx, B200_EINVAL, "bad sweepMode code");
+    if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_smooth_controls.reserved must be 0");
+    if (ctl->nSweeps == 0) return fail(ctx, B200_EINVAL, "nSweeps must not be 0");
+    if (ctx->nranks > 1)
+        return fail(ctx, B200_EUNSUPPORTED, "smoothSolver with processor patches (nranks > 1) is not built yet");
+    if (ctx->tileRows > 0) return fail(ctx, B200_EUNSUPPORTED, "smoothSolver does not take tiled plans (B200PCG_TILE)");
+    DevPlan* Pp = nullptr;
+    RET(ensure_plan(ctx, ctl->sweepMode == B200_SWEEP_EXACT ? Ordering::Levels : Ordering::MultiColour, &Pp));
+    DevPlan& P = *Pp;
+    const int N = ctx->N;
+    const int gv = grid_for(ctx, (N + 1) / 2);
+    Scalars* S = ctx->S;
+    const bool fixed = ctl->nSweeps < 0;             // exactly -nSweeps sweeps, no residual evaluation
+    const int nS = fixed ? -ctl->nSweeps : ctl->nSweeps;
+    const bool sym = ctl->smoother == B200_SMOOTHER_SYM_GAUSS_SEIDEL;
+    const int C = P.h.nColours;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    const b200_controls c{ctl->tolerance, ctl->relTol, ctl->maxIter, ctl->minIter, 0, 0};
+    ctx->gsSweeps = nS;
+    RET(reset_scalars(ctx, &c));
+    RET(load_system_asym(ctx, P, dn_diag, dn_upper, dn_lower, dn_src, dn_psi));
+    ctx->usedSmall = false;
+    if (!fixed) {
+        // wA = A psi, sumA -> pA; normFactor; initial residual and the first convergence test (STEP_NORM)
+        RET((spmv_full<true, false>(ctx, P, ctx->psi, ctx->w, ctx->p, STEP_NONE)));
+        {
+            Reduce R = mkR(ctx, STEP_SUMPSI);
+            LAUNCH(PC_SUM, k_sum, gv, N, ctx->psi, R);
+        }
+        {
+            Reduce R = mkR(ctx, STEP_NORM);
+            LAUNCH(PC_NORM, k_norm_resid, gv, N, ctx->w, ctx->p, ctx->src, ctx->r, R);
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->sc));
+    CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+
+    auto sweep = [&]() -> int {
+        for (int k = 0; k < C; ++k) RET(launch_gs_rows(ctx, P, k));
+        // reverse sweep: the last group would be recomputed from unchanged inputs, start one before it
+        if (sym) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k));
+        return B200_OK;
+    };
+    if (fixed) {
+        for (int i = 0; i < nS; ++i) RET(sweep());
+    } else {
+        // loop bodies the do/while can execute at most; the device decides when to stop (kernels return on S->done)
+        const int64_t target = ctx->forceIters > 0 ? ctx->forceIters : std::max<int64_t>(ctl->maxIter, ctl->minIter);
+        const int64_t cap = std::max<int64_t>(1, (target + nS - 1) / nS);
+        int64_t enq = 0;
+        // a level-scheduled body is hundreds of launches: poll after every one; multicolour bodies are a few
+        int chunk = (ctl->sweepMode == B200_SWEEP_EXACT && C > 16) ? 1 : 2;
+        while (!ctx->hS->done && enq < cap) {
+            const int n = (int)std::min<int64_t>(chunk, cap - enq);
+            for (int i = 0; i < n; ++i) {
+                ctx->profIter = (int)(enq + i + 1) * nS;
+                for (int sw = 0; sw < nS; ++sw) RET(sweep());
+                RET(launch_gs_resid(ctx, P));
+            }
+            ctx->profIter = 0;
+            enq += n;
+            CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+            CU(cudaStreamSynchronize(ctx->sc));
+            CU(cudaGetLastError());
+            if (chunk < 16 && chunk > 1) chunk *= 2;
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->sc));
+    LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx, fixed ? 0x7fffffff : ctx->hS->nIter);
+    const int rc = finish_solve(ctx, P, perf);
+    if (fixed && perf) perf->nIterations = nS;       // solverPerf.nIterations() -= nSweeps_ (no residuals: 0, 0)
+    return rc;
 }
 
 // ---- staged host <-> device copies for pageable caller memory ----------------------------------
@@ -2166,6 +2314,92 @@ int b200_amul(b200_ctx* ctx, const double* diag, const double* upper, const doub
     RET(reset_scalars(ctx, nullptr));
     RET(load_system(ctx, P, ctx->in_diag, ctx->in_upper, nullptr, ctx->in_psi));
     RET((spmv_full<false, false>(ctx, P, ctx->psi, ctx->w, nullptr, STEP_NONE)));
+    const double* out = ctx->w;
+    if (P.perm) {   // renumbered plan: back to the caller's cell order
+        LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, ctx->N), ctx->N, P.perm, ctx->w, ctx->in_src);
+        out = ctx->in_src;
+    }
+    CU(cudaMemcpyAsync(Apsi, out, nb, cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx);
+    return B200_OK;
+}
+
+int b200_smooth_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper, const double* d_lower,
+                             const double* const* d_bou, const double* d_source, double* d_psi,
+                             const b200_smooth_controls* ctl, b200_perf* perf) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "smooth_solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!d_diag || !d_source || !d_psi)) || (ctx->F > 0 && !d_upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(copy_bou(ctx, ctx->plans[0], d_bou, cudaMemcpyDeviceToDevice, ctx->bou));
+    return smooth_core(ctx, d_diag, d_upper, d_lower, d_source, d_psi, ctl, perf);
+}
+
+int b200_smooth_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                      const double* const* bou, const double* source, double* psi,
+                      const b200_smooth_controls* ctl, b200_perf* perf) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "smooth_solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!diag || !source || !psi)) || (ctx->F > 0 && !upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, false));
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    const bool asym = lower && lower != upper;
+    if (asym && !ctx->in_lower) RET(dev_alloc(ctx, &ctx->in_lower, (size_t)ctx->F));
+    CU(cudaEventRecord(ctx->ev[3], ctx->sc));
+    RET(h2d(ctx, ctx->in_upper, upper, fb));
+    if (asym) RET(h2d(ctx, ctx->in_lower, lower, fb));
+    RET(h2d(ctx, ctx->in_diag, diag, nb));
+    RET(h2d(ctx, ctx->in_src, source, nb));
+    RET(h2d(ctx, ctx->in_psi, psi, nb));
+    RET(copy_bou(ctx, ctx->plans[0], bou, cudaMemcpyHostToDevice, ctx->bou));
+    CU(cudaEventRecord(ctx->ev[4], ctx->sc));
+    int rc = smooth_core(ctx, ctx->in_diag, ctx->in_upper, asym ? ctx->in_lower : nullptr, ctx->in_src, ctx->in_psi,
+                         ctl, perf);
+    if (rc != B200_OK && rc != B200_ENONFINITE) return rc;
+    CU(cudaEventRecord(ctx->ev[5], ctx->sc));
+    RET(d2h(ctx, psi, ctx->in_psi, nb));
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    if (perf) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+        perf->h2dMs = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]);
+        perf->d2hMs = ms;
+    }
+    return rc;
+}
+
+int b200_amul_asym(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                   const double* const* bou, const double* psi, double* Apsi) {
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "amul before set_addressing");
+    if ((ctx->N > 0 && (!diag || !psi || !Apsi)) || (ctx->F > 0 && !upper))
+        return fail(ctx, B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, false));
+    DevPlan& P = ctx->plans[0];
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    const bool asym = lower && lower != upper;
+    if (asym && !ctx->in_lower) RET(dev_alloc(ctx, &ctx->in_lower, (size_t)ctx->F));
+    CU(cudaMemcpyAsync(ctx->in_upper, upper, fb, cudaMemcpyHostToDevice, ctx->sc));
+    if (asym) CU(cudaMemcpyAsync(ctx->in_lower, lower, fb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_diag, diag, nb, cudaMemcpyHostToDevice, ctx->sc));
+    CU(cudaMemcpyAsync(ctx->in_psi, psi, nb, cudaMemcpyHostToDevice, ctx->sc));
+    RET(copy_bou(ctx, P, bou, cudaMemcpyHostToDevice, ctx->bou));
+    RET(reset_scalars(ctx, nullptr));
+    RET(load_system_asym(ctx, P, ctx->in_diag, ctx->in_upper, asym ? ctx->in_lower : nullptr, nullptr, ctx->in_psi));
+    ctx->forceEll = true;       // the single-read layouts assume lower == upper
+    const int rcA = spmv_full<false, false>(ctx, P, ctx->psi, ctx->w, nullptr, STEP_NONE);
+    ctx->forceEll = false;
+    RET(rcA);
     const double* out = ctx->w;
     if (P.perm) {   // renumbered plan: back to the caller's cell order
         LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, ctx->N), ctx->N, P.perm, ctx->w, ctx->in_src);

@@ -12,7 +12,7 @@ import itertools
 import numpy as np
 
 from . import _lib
-from ._lib import B200Error, Controls, Iface, Perf, PRECOND
+from ._lib import B200Error, Controls, Iface, Perf, PRECOND, SMOOTHER, SWEEP_MODE, SmoothControls
 
 _mesh_keys = itertools.count(1)
 
@@ -58,17 +58,24 @@ class LduAddressing:
 
 
 class LduMatrix:
-    """Symmetric lduMatrix: diag [nCells], upper [nFaces] (lower aliases upper)."""
+    """lduMatrix: diag [nCells], upper [nFaces] and, for an asymmetric matrix, lower [nFaces]
+    (lower is None: symmetric, lower aliases upper -- lduMatrix::lower())."""
 
-    def __init__(self, lduAddr, diag, upper):
+    def __init__(self, lduAddr, diag, upper, lower=None):
         self.lduAddr = lduAddr
         self.diag = _f64(diag)
         self.upper = _f64(upper)
+        self.lower = None if lower is None else _f64(lower)
         if self.diag.size != lduAddr.nCells or self.upper.size != lduAddr.nFaces:
             raise ValueError("diag/upper size does not match the addressing")
+        if self.lower is not None and self.lower.size != lduAddr.nFaces:
+            raise ValueError("lower size does not match the addressing")
 
     def symmetric(self):
-        return True
+        return self.lower is None
+
+    def asymmetric(self):
+        return self.lower is not None
 
 
 class SolverPerformance:
@@ -264,6 +271,37 @@ class Context:
         self._check(rc)
         return perf
 
+    # ---- smoothSolver on (a)symmetric matrices -----------------------------------
+    def amul_asym(self, matrix, interfaceBouCoeffs, psi):
+        psi = _f64(psi)
+        out = np.empty_like(psi)
+        bou, keep = _bou_array(interfaceBouCoeffs)
+        low = None if matrix.lower is None else matrix.lower.ctypes.data
+        self._check(self.lib.b200_amul_asym(self.handle, matrix.diag.ctypes.data, matrix.upper.ctypes.data, low,
+                                            bou, psi.ctypes.data, out.ctypes.data))
+        return out
+
+    def smooth_solve(self, diag, upper, lower, interfaceBouCoeffs, source, psi, controls):
+        perf = Perf()
+        bou, keep = _bou_array(interfaceBouCoeffs)
+        rc = self.lib.b200_smooth_solve(self.handle, diag.ctypes.data, upper.ctypes.data,
+                                        None if lower is None else lower.ctypes.data, bou,
+                                        source.ctypes.data, psi.ctypes.data, C.byref(controls), C.byref(perf))
+        self._check(rc)
+        return perf
+
+    def smooth_solve_device(self, d_diag, d_upper, d_lower, d_bou_list, d_source, d_psi, controls):
+        perf = Perf()
+        n = len(d_bou_list) if d_bou_list else 0
+        arr = (C.c_void_p * max(1, n))()
+        for k in range(n):
+            arr[k] = _ptr(d_bou_list[k])
+        rc = self.lib.b200_smooth_solve_device(self.handle, _ptr(d_diag), _ptr(d_upper), _ptr(d_lower),
+                                               C.cast(arr, C.c_void_p), _ptr(d_source), _ptr(d_psi),
+                                               C.byref(controls), C.byref(perf))
+        self._check(rc)
+        return perf
+
     # ---- harness helpers -----------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.b200_launch_count(self.handle))
@@ -374,3 +412,62 @@ class B200PCG:
         pre = {"none": "none", "diagonal": "diagonal", "DIC": "DIC(mc)", "DIC-exact": "DIC", "DIC-eisenstat": "DIC(mc)",
                "DIC-multicolour": "DIC(mc)"}[self.preconditionerName]
         return SolverPerformance(pre + self.typeName, self.fieldName, perf)
+
+
+def make_smooth_controls(solverControls):
+    """smoothSolver::readControls (OF-dev smoothSolver.C): lduMatrix::solver's maxIter 1000, minIter 0,
+    tolerance 1e-6, relTol 0, plus nSweeps 1; `smoother` is mandatory as upstream."""
+    d = dict(solverControls or {})
+    sm = d.get("smoother")
+    if isinstance(sm, dict):
+        sm = sm.get("smoother")
+    if sm not in SMOOTHER:
+        raise ValueError(f"Unknown smoother {sm}; valid: {sorted(SMOOTHER)}")
+    mode = d.get("B200", {}).get("sweepMode", "multicolour")
+    if mode not in SWEEP_MODE:
+        raise ValueError(f"Unknown sweepMode {mode}; valid: {sorted(SWEEP_MODE)}")
+    c = SmoothControls()
+    c.tolerance = float(d.get("tolerance", 1e-6))
+    c.relTol = float(d.get("relTol", 0.0))
+    c.maxIter = int(d.get("maxIter", 1000))
+    c.minIter = int(d.get("minIter", 0))
+    c.nSweeps = int(d.get("nSweeps", 1))
+    c.smoother = SMOOTHER[sm]
+    c.sweepMode = SWEEP_MODE[mode]
+    c.reserved = 0
+    return c, sm, mode
+
+
+class B200smoothSolver:
+    """lduMatrix::solver selected by `solver B200smoothSolver;` where the reference's fvSolution says
+    `solver smoothSolver; smoother symGaussSeidel;` (cases/steckler/system/fvSolution:48-61: U, Yi, h, k).
+    Registered upstream in BOTH run-time tables (symmetric and asymmetric matrices); same constructor signature and
+    `solve(psi, source, cmpt=0) -> SolverPerformance` as B200PCG.  `B200 { sweepMode exact; }` visits the cells in
+    OpenFOAM's own order (level-scheduled: identical sweep counts and psi); the default multicolour order is a
+    GS-class stand-in and prints as `B200smoothSolver(mc)`."""
+
+    typeName = "B200smoothSolver"
+
+    def __init__(self, fieldName, matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces,
+                 solverControls, context=None):
+        self.fieldName = fieldName
+        self.matrix = matrix
+        self.controls, self.smootherName, self.sweepMode = make_smooth_controls(solverControls)
+        self.ctx = context or default_context()
+        coupled = [k for k, itf in enumerate(interfaces or []) if itf is not None]
+        for k in coupled:
+            if not isinstance(interfaces[k], ProcessorLduInterface):
+                raise B200Error(_lib.B200_EUNSUPPORTED, f"unsupported interface type on patch {k}")
+        addr = matrix.lduAddr
+        if [interfaces[k] for k in coupled] != list(addr.interfaces):
+            raise ValueError("interfaces do not match lduAddr.interfaces")
+        self.bou = [_f64(interfaceBouCoeffs[k]) for k in coupled]
+
+    def solve(self, psi, source, cmpt=0):
+        if not (isinstance(psi, np.ndarray) and psi.dtype == np.float64 and psi.flags.c_contiguous):
+            raise TypeError("psi must be a contiguous float64 array (updated in place)")
+        m = self.matrix
+        self.ctx.set_addressing(m.lduAddr)
+        perf = self.ctx.smooth_solve(m.diag, m.upper, m.lower, self.bou, _f64(source), psi, self.controls)
+        name = self.typeName + ("" if self.sweepMode == "exact" else "(mc)")
+        return SolverPerformance(name, self.fieldName, perf)

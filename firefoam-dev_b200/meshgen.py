@@ -27,10 +27,11 @@ class System:
     deltaCoeffs: np.ndarray = None
     diag0: np.ndarray = None  # diagonal before the laplacian is added (ddt + boundary coeffs)
     sign: float = -1.0
+    lower: np.ndarray = None  # asymmetric matrices only (lduMatrix::lower()); None: lower aliases upper
 
     @property
     def matrix(self):
-        return LduMatrix(self.addr, self.diag, self.upper)
+        return LduMatrix(self.addr, self.diag, self.upper, self.lower)
 
     @property
     def interfaces(self):
@@ -169,12 +170,21 @@ def decompose(system: System, cellToProc, nProcs):
             for k in range(ifNbr.size):
                 s, e = int(ifStart[k]), int(ifStart[k + 1])
                 ifs.append(ProcessorLduInterface(int(ifNbr[k]), ifFC[s:e], myProcNo=p))
-                bou.append(-system.upper[ifGF[s:e]])
+                if system.lower is None:
+                    bou.append(-system.upper[ifGF[s:e]])
+                else:
+                    # asymmetric: the row of the local cell carries upper[f] when that cell owns the cut face
+                    # (A[l][u] = upper), lower[f] when it is the face's neighbour (A[u][l] = lower)
+                    gf = ifGF[s:e]
+                    owns = a.lowerAddr[gf] == cells[ifFC[s:e]]
+                    bou.append(-np.where(owns, system.upper[gf], system.lower[gf]))
             addr = LduAddressing(cells.size, get(p, "lower"), get(p, "upper"), ifs)
             sub = System(addr, system.diag[cells].copy(), system.upper[faces].copy(),
                          system.source[cells].copy(), bou,
                          None if system.xstar is None else system.xstar[cells].copy())
             sub.cells, sub.faces = cells, faces
+            if system.lower is not None:
+                sub.lower = system.lower[faces].copy()
             if system.gamma_f is not None:
                 # inputs of fvm::laplacian on the sub-mesh; the cut faces enter the sub-mesh diagonal
                 # through the processor patches' internalCoeffs (= -upper of the cut face), which

@@ -220,6 +220,58 @@ int b200_amul(b200_ctx* ctx, const double* diag, const double* upper,
  * solver/pEqn.H:43-44): flux[f] = upper[f]*psi[u[f]] - upper[f]*psi[l[f]]. */
 int b200_flux(b200_ctx* ctx, const double* upper, const double* psi, double* flux_out);
 
+/* ---- the other linear solves of a time step: smoothSolver on asymmetric matrices ---- */
+
+/* smoother selector (fvSolution keyword `smoother`; reference: cases/steckler/system/fvSolution:51) */
+enum {
+    B200_SMOOTHER_GAUSS_SEIDEL     = 0,   /* `GaussSeidel`    -> GaussSeidelSmoother (forward sweep)            */
+    B200_SMOOTHER_SYM_GAUSS_SEIDEL = 1    /* `symGaussSeidel` -> symGaussSeidelSmoother (forward + reverse)     */
+};
+/* order in which a sweep visits the cells */
+enum {
+    B200_SWEEP_MULTICOLOUR = 0,  /* default: multicolour ordering of the same smoother ("GS-class": one launch per
+                                    colour, 2 colours on hex meshes).  NOT OpenFOAM's cell order: sweep counts and
+                                    tolerance-limited solutions differ slightly, the log says `B200smoothSolver(mc)` */
+    B200_SWEEP_EXACT       = 1   /* `B200{sweepMode exact;}`: level-scheduled sweeps in OpenFOAM's OWN elimination
+                                    order (cell order), row sums in its face order: bit-identical psi after every
+                                    sweep, identical sweep counts; one launch per dependency level (a parity tool on
+                                    large meshes, like dicMode exact)                                              */
+};
+
+/* smoothSolver::readControls (OF-dev smoothSolver.C, lduMatrixSolver.C): the lduMatrix::solver controls + nSweeps 1 */
+typedef struct b200_smooth_controls {
+    double  tolerance;
+    double  relTol;
+    int32_t maxIter;
+    int32_t minIter;
+    int32_t nSweeps;      /* sweeps between two residual evaluations; < 0: exactly -nSweeps sweeps, no residuals  */
+    int32_t smoother;     /* B200_SMOOTHER_*                                                                      */
+    int32_t sweepMode;    /* B200_SWEEP_*                                                                         */
+    int32_t reserved;     /* must be 0                                                                            */
+} b200_smooth_controls;
+
+/* Replaces: smoothSolver::solve(psi, source, cmpt) with its Amul / normFactor / residual / smoother calls (OF-dev
+ * smoothSolver.C, GaussSeidelSmoother.C, symGaussSeidelSmoother.C, lduMatrixATmul.C, lduMatrixSolver.C) -- what
+ * the reference selects for U, Yi, h and k (cases/steckler/system/fvSolution:48-61; solver/UEqn.H:19-30,
+ * solver/YEEqn.H:60,111) on ASYMMETRIC lduMatrices.
+ *   diag   [nCells]  matrix diagonal WITH boundary internalCoeffs already added
+ *   upper  [nFaces]  A[l][u]   (Amul: Apsi[l] += upper*psi[u])
+ *   lower  [nFaces]  A[u][l]   (Amul: Apsi[u] += lower*psi[l]); NULL: symmetric matrix, lower aliases upper
+ *   source, psi, ifaceBouCoeffs as in b200_solve.
+ * One rank only in this version: with nranks > 1 the call returns B200_EUNSUPPORTED (upstream treats processor
+ * patches as explicit, Jacobi-like contributions refreshed once per sweep; not built yet). */
+int b200_smooth_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                      const double* const* ifaceBouCoeffs, const double* source, double* psi,
+                      const b200_smooth_controls* ctl, b200_perf* perf);
+int b200_smooth_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper, const double* d_lower,
+                             const double* const* d_ifaceBouCoeffs, const double* d_source, double* d_psi,
+                             const b200_smooth_controls* ctl, b200_perf* perf);
+
+/* Replaces: lduMatrix::Amul with lower != upper (OF-dev lduMatrixATmul.C) -- the SpMV of the asymmetric path alone,
+ * for parity tests.  Row sums in OpenFOAM's face order, no FMA contraction: bit-identical to the CPU loop. */
+int b200_amul_asym(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                   const double* const* ifaceBouCoeffs, const double* psi, double* Apsi);
+
 /* ---- harness helpers (not part of the OpenFOAM-facing contract) ---------------------- */
 
 /* pinned host memory for callers that want async H2D at full PCIe rate */

@@ -226,3 +226,102 @@ def sumA(system):
     s = np.empty(system.addr.nCells)
     lib().orc_sumA(C.byref(pk.ranks[0]), s.ctypes.data)
     return s
+
+
+# ---- smooth_oracle.c: smoothSolver + GaussSeidel / symGaussSeidel on asymmetric lduMatrices ----
+class _SmRank(C.Structure):
+    _fields_ = [("nCells", C.c_int32), ("nFaces", C.c_int32), ("lower", C.c_void_p), ("upper", C.c_void_p),
+                ("diag", C.c_void_p), ("upperCoeffs", C.c_void_p), ("lowerCoeffs", C.c_void_p),
+                ("source", C.c_void_p), ("psi", C.c_void_p), ("nIfaces", C.c_int32), ("ifaces", C.c_void_p)]
+
+
+class _SmControls(C.Structure):
+    _fields_ = [("tolerance", C.c_double), ("relTol", C.c_double), ("maxIter", C.c_int32),
+                ("minIter", C.c_int32), ("nSweeps", C.c_int32), ("smoother", C.c_int32)]
+
+
+SMOOTHER = {"GaussSeidel": 0, "symGaussSeidel": 1}
+
+
+class _SmPacked:
+    """systems: objects with .addr, .diag, .upper, .source, .bou and (optionally) .lower -- None or absent
+    means a symmetric matrix (lower aliases upper, as in lduMatrix::lower())."""
+
+    def __init__(self, systems, psis):
+        self.keep = []
+        R = len(systems)
+        self.ranks = (_SmRank * R)()
+        for r, (s, psi) in enumerate(zip(systems, psis)):
+            a = s.addr
+            low = getattr(s, "lower", None)
+            arrs = dict(l=_i32(a.lowerAddr), u=_i32(a.upperAddr), d=_f64(s.diag), up=_f64(s.upper),
+                        b=_f64(s.source))
+            arrs["lo"] = arrs["up"] if low is None else _f64(low)
+            ifs = (_Iface * max(1, len(a.interfaces)))()
+            for k, itf in enumerate(a.interfaces):
+                fc, bc = _i32(itf.faceCells), _f64(s.bou[k])
+                self.keep += [fc, bc]
+                ifs[k].nbrRank, ifs[k].nFaces = itf.neighbProcNo, fc.size
+                ifs[k].faceCells, ifs[k].bouCoeffs = fc.ctypes.data, bc.ctypes.data
+            self.keep += [arrs, ifs, psi]
+            R_ = self.ranks[r]
+            R_.nCells, R_.nFaces = a.nCells, a.nFaces
+            R_.lower, R_.upper = arrs["l"].ctypes.data, arrs["u"].ctypes.data
+            R_.diag, R_.upperCoeffs, R_.lowerCoeffs = arrs["d"].ctypes.data, arrs["up"].ctypes.data, arrs["lo"].ctypes.data
+            R_.source, R_.psi = arrs["b"].ctypes.data, psi.ctypes.data
+            R_.nIfaces, R_.ifaces = len(a.interfaces), C.cast(ifs, C.c_void_p)
+
+
+def smooth_solve(systems, psis, smoother="symGaussSeidel", tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+                 nSweeps=1):
+    """smoothSolver::solve on len(systems) emulated ranks; psis updated in place.  Returns OrcPerf."""
+    if not isinstance(systems, (list, tuple)):
+        systems, psis = [systems], [psis]
+    for p in psis:
+        assert p.dtype == np.float64 and p.flags.c_contiguous
+    pk = _SmPacked(systems, psis)
+    ctl = _SmControls(tolerance, relTol, maxIter, minIter, nSweeps, SMOOTHER[smoother])
+    perf = OrcPerf()
+    L = lib()
+    L.orc_smooth_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.orc_smooth_solve(len(systems), C.cast(pk.ranks, C.c_void_p), C.byref(ctl), C.byref(perf))
+    if rc != 0:
+        raise RuntimeError(f"oracle: interfaces do not pair up (rc={rc})")
+    return perf
+
+
+def _asym_apply(systems, xs, what):
+    if not isinstance(systems, (list, tuple)):
+        systems, xs = [systems], [xs]
+    xs = [_f64(x) for x in xs]
+    ys = [np.empty_like(x) for x in xs]
+    pk = _SmPacked(systems, [x.copy() for x in xs])
+    xa = (C.c_void_p * len(xs))(*[x.ctypes.data for x in xs])
+    ya = (C.c_void_p * len(ys))(*[y.ctypes.data for y in ys])
+    L = lib()
+    L.orc_asym_apply.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.orc_asym_apply(len(systems), C.cast(pk.ranks, C.c_void_p), C.cast(xa, C.c_void_p),
+                          C.cast(ya, C.c_void_p), what)
+    if rc != 0:
+        raise RuntimeError(f"oracle: interfaces do not pair up (rc={rc})")
+    return ys
+
+
+def amul_asym(systems, xs):
+    """lduMatrix::Amul with lower != upper (list per rank)."""
+    return _asym_apply(systems, xs, 0)
+
+
+def residual_asym(systems, xs):
+    """lduMatrix::residual: source - A x with the coupled coefficients negated (list per rank)."""
+    return _asym_apply(systems, xs, 1)
+
+
+def sumA_asym(system):
+    pk = _SmPacked([system], [np.zeros(system.addr.nCells)])
+    s = np.empty(system.addr.nCells)
+    L = lib()
+    L.orc_asym_sumA.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_asym_sumA.restype = None
+    L.orc_asym_sumA(C.byref(pk.ranks[0]), s.ctypes.data)
+    return s

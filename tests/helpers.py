@@ -109,6 +109,39 @@ class PlanView:
         val[m] = upper[self.faceOf[m]]
         return val
 
+    def values_asym(self, upper, lower, lowerAddr):
+        """k_fill_values_asym: the entry of row r on face f carries upper[f] when r's cell OWNS the face
+        (A[l][u] = upper), lower[f] when it is the face's neighbour (A[u][l] = lower)."""
+        val = np.zeros(self.nEntries)
+        for r in range(self.N):
+            c = int(self.perm[r]) if self.perm.size else r
+            for j in range(self.nTotal[r]):
+                e = self.entry(r, j)
+                f = int(self.faceOf[e])
+                val[e] = upper[f] if lowerAddr[f] == c else lower[f]
+        return val
+
+    def gs_rows(self, k, diag_i, val, b_i, x_i):
+        """k_gs_rows over colour / level k, in place: x[r] = (b[r] - sum_j val*x[col]) / diag[r], entries in the
+        plan's order [earlier | later], each ascending natural face order."""
+        for r in self.rows_of_colour(k):
+            w = b_i[r]
+            for j in range(self.nTotal[r]):
+                e = self.entry(r, j)
+                w = w - val[e] * x_i[self.col[e]]
+            x_i[r] = w / diag_i[r]
+
+    def gs_residual(self, diag_i, val, b_i, x_i):
+        """k_gs_resid: sum |b - A x| with the row sum in lduMatrix::residual's order."""
+        tot = 0.0
+        for r in range(self.N):
+            w = b_i[r] - diag_i[r] * x_i[r]
+            for j in range(self.nTotal[r]):
+                e = self.entry(r, j)
+                w = w - val[e] * x_i[self.col[e]]
+            tot += abs(w)
+        return tot
+
     # --- numpy emulation of the kernels' row loops (same operation order) ------------------
     def spmv(self, diag_i, val, x_i):
         y = np.empty(self.N)
@@ -519,3 +552,44 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
         x = xa + S["alpha"] * t if S["pendingPsi"] else xa
         psi = psi + sv * x
     return pv.to_natural(psi), S["nIter"], S["finalRes"], checks
+
+
+def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
+                          nSweeps=1):
+    """Kernel-by-kernel transliteration of b200_smooth_solve on one rank (solver.cu smooth_core, kernels.cuh
+    k_fill_values_asym / k_gs_rows / k_gs_resid, STEP_NORM / STEP_GS_RES).  pv: a Levels plan (exact mode:
+    OpenFOAM's own elimination order) or a MultiColour plan (GS-class).  Returns (psi natural, nIter, initRes,
+    finalRes)."""
+    low = s.upper if s.lower is None else s.lower
+    val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
+    d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
+    C = pv.nColours
+    sym = smoother == "symGaussSeidel"
+
+    def sweep():
+        for k in range(C):
+            pv.gs_rows(k, d, val, b, x)
+        if sym:
+            for k in range(C - 2, -1, -1):          # the last colour's rows would be recomputed from unchanged inputs
+                pv.gs_rows(k, d, val, b, x)
+
+    if nSweeps < 0:
+        for _ in range(-nSweeps):
+            sweep()
+        return pv.to_natural(x), -nSweeps, 0.0, 0.0
+    wA = pv.spmv(d, val, x)
+    sumA = pv.spmv(d, val, np.ones(pv.N))
+    xRef = x.sum() / pv.N
+    nf = (np.abs(wA - sumA * xRef) + np.abs(b - sumA * xRef)).sum() + 1e-20
+    init = final = np.abs(b - wA).sum() / nf
+    conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
+    n = 0
+    if minIter > 0 or not conv():
+        while True:
+            for _ in range(nSweeps):
+                sweep()
+            final = pv.gs_residual(d, val, b, x) / nf
+            n += nSweeps
+            if not ((n < maxIter and not conv()) or n < minIter):
+                break
+    return pv.to_natural(x), n, init, final

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT
 
-SOURCES = ["B200PCG.C", "B200GaussLaplacianScheme.C"]
+SOURCES = ["B200PCG.C", "B200GaussLaplacianScheme.C", "B200smoothSolver.C"]
 
 
 @pytest.mark.parametrize("src", SOURCES)
@@ -46,3 +46,11 @@ def test_adapter_rejects_processor_cyclic_and_names_the_dic_class():
     assert 'logPreconditionerName = "DIC(mc)"' in src  # the log line marks the DIC-class stand-in
     for code in ("B200_PRECOND_DIC_EXACT", "B200_PRECOND_DIC_MC_EIS", "B200_PRECOND_DIC_MC_LOOP", "B200_PRECOND_DIC_MC"):
         assert code in src
+
+
+def test_smooth_solver_registers_in_both_tables_and_names_the_mode():
+    src = open(os.path.join(ROOT, "adapter", "B200smoothSolver.C")).read()
+    assert "addsymMatrixConstructorToTable<B200smoothSolver>" in src
+    assert "addasymMatrixConstructorToTable<B200smoothSolver>" in src
+    assert 'typeName + "(mc)"' in src                   # the log line marks the multicolour stand-in
+    assert "B200smoothSolver.C" in open(os.path.join(ROOT, "adapter", "Make", "files")).read()

@@ -1,0 +1,53 @@
+"""CPU tests of the data structure + operation order the smoothSolver kernels use (numpy transliteration in
+tests/helpers.py: PlanView.gs_rows / gs_residual / smooth_solve_emulated) against oracle/smooth_oracle.c.
+
+Exact mode (Levels plan: rows ordered by the dependency level of OpenFOAM's own cell-order recurrence, entries
+[lower neighbours | upper neighbours] each in ascending face order) must reproduce the sequential sweeps of
+GaussSeidelSmoother.C / symGaussSeidelSmoother.C BIT FOR BIT; the multicolour mode is a different ordering of the
+unknowns (GS-class): it must converge to the same solution."""
+import numpy as np
+import pytest
+
+import helpers
+from firefoam_dev_b200 import cases, meshgen
+from oracle import oracle as orc
+
+LEVELS, MULTICOLOUR = 2, 1
+
+
+def systems():
+    yield "random", cases.transport_system(helpers.random_ldu(120, 6, 17), seed=5)
+    yield "hex", cases.transport_system(meshgen.hex_block(7, 5, 6), seed=6)
+    yield "poly", cases.transport_system(meshgen.bcc_poly(4, 3, 3), seed=7, kappa=0.3)
+    b = helpers.random_ldu(90, 5, 23)
+    yield "symmetric", meshgen.System(b.addr, b.diag, b.upper, b.source, [], b.xstar)
+
+
+@pytest.mark.parametrize("name,s", list(systems()), ids=[n for n, _ in systems()])
+@pytest.mark.parametrize("smoother", ["GaussSeidel", "symGaussSeidel"])
+def test_level_scheduled_sweeps_are_bit_identical(name, s, smoother):
+    pv = helpers.PlanView(LEVELS, s.addr)
+    N = s.addr.nCells
+    for nS in (1, 2):
+        psi = np.zeros(N)
+        orc.smooth_solve(s, psi, smoother=smoother, nSweeps=-nS)
+        got, n, _, _ = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, nSweeps=-nS)
+        assert n == nS and np.array_equal(got, psi)
+    psi = np.zeros(N)
+    p = orc.smooth_solve(s, psi, smoother=smoother, tolerance=1e-7, maxIter=300)
+    got, n, init, final = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, tol=1e-7, maxIter=300)
+    assert n == p.nIterations and np.array_equal(got, psi)
+    assert init == pytest.approx(p.initialResidual, rel=1e-12) and final == pytest.approx(p.finalResidual, rel=1e-9)
+
+
+@pytest.mark.parametrize("name,s", list(systems()), ids=[n for n, _ in systems()])
+def test_multicolour_sweeps_converge_to_the_same_solution(name, s):
+    pv = helpers.PlanView(MULTICOLOUR, s.addr)
+    N = s.addr.nCells
+    psi = np.zeros(N)
+    p = orc.smooth_solve(s, psi, tolerance=1e-12, maxIter=2000)
+    got, n, init, final = helpers.smooth_solve_emulated(pv, s, np.zeros(N), tol=1e-12, maxIter=2000)
+    assert p.finalResidual < 1e-12 and final < 1e-12
+    assert init == pytest.approx(p.initialResidual, rel=1e-12)
+    assert np.linalg.norm(got - psi) <= 1e-8 * np.linalg.norm(psi)
+    assert n <= 2 * p.nIterations + 2          # a different ordering of the same smoother, not a different method
