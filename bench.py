@@ -622,6 +622,70 @@ def corrector_section(env, ctx, s):
     return out
 
 
+def transport_section(env, ctx, base):
+    """the OTHER linear solves of a time step.  The reference solves U, Yi, h and k with
+    `smoothSolver` + `symGaussSeidel` (cases/steckler/system/fvSolution:48-61; 261 of the golden log's solves) on
+    ASYMMETRIC transport matrices.  Here: a U-shaped system (ddt + convection + diffusion, cases.transport_system) on
+    the same mesh through b200_smooth_solve_device, `smoother symGaussSeidel`, to tolerance 1e-6 (the reference's U
+    controls without its maxIter 10 cap), default multicolour sweeps.  Reported: time to tolerance, us per
+    sweep-iteration (sweeps + residual evaluation), per-kernel fractions on BYTES MOVED (per row 4 B row length + b +
+    diag + psi write, per entry value + column, every gathered psi once), and the CPU restatement (one thread: the
+    sweep is sequential upstream) on a bounded sample beside it."""
+    import numpy as np
+    from firefoam_dev_b200 import cases
+    from firefoam_dev_b200.ldu import make_smooth_controls
+    from oracle import oracle as orc
+    torch = env.torch
+    t = cases.transport_system(base, seed=31)
+    N, F = t.addr.nCells, t.addr.nFaces
+    d, up, lo, b = env.up(t.diag), env.up(t.upper), env.up(t.lower), env.up(t.source)
+    x = torch.zeros(N, dtype=torch.float64, device=env.dev)
+    ctl, _, _ = make_smooth_controls(dict(smoother="symGaussSeidel", tolerance=1e-6, relTol=0.0, maxIter=1000))
+
+    def step():
+        x.zero_()
+        torch.cuda.current_stream().synchronize()
+        return ctx.smooth_solve_device(d, up, lo, [], b, x, ctl)
+    step()
+    ms, perfs = env.timed(step, 3)
+    p = perfs[-1]
+    err = float(np.abs(x.cpu().numpy() - t.xstar).max())
+    ctx.force_iterations(20)
+    step()
+    fms, fp = env.timed(step, 1)
+    ctx.profile(True)
+    step()
+    prof = ctx.profile_json()
+    ctx.profile(False)
+    ctx.force_iterations(0)
+    C = p.nColours
+    cb = col_bytes_of(ctx)
+    rows = N / max(1, C)                      # rows per colour pass (2 equal colours on the hex box)
+    pass_bytes = rows * 28 + (2.0 * F / max(1, C)) * (8 + cb) + 8 * (N - rows)
+    res_rows = N - rows                       # explicit residual: every row but the last-updated colour
+    res_bytes = res_rows * 28 + (2.0 * F * res_rows / N) * (8 + cb) + 8 * rows
+    kern = {}
+    for name, nbytes in (("gs_sweep_rows", pass_bytes), ("gs_residual", res_bytes)):
+        if name in prof:
+            us = prof[name]["avg_us"]
+            kern[name] = {"avg_us": us, "launches": prof[name]["launches"], "bytes_moved": nbytes,
+                          "achieved_gbs": nbytes / (us * 1e-6) / 1e9, "frac": nbytes / (us * 1e-6) / 1e9 / env.peak}
+    # CPU restatement on a bounded sample: set-up (Amul, normFactor) + 3 sweep-iterations, one thread
+    t0 = time.perf_counter()
+    psi = np.zeros(N)
+    cp = orc.smooth_solve(t, psi, tolerance=1e-30, maxIter=3)
+    cpu_s = time.perf_counter() - t0
+    return {"system": "U-shaped asymmetric lduMatrix (ddt + div + laplacian) on the same mesh; smoothSolver + symGaussSeidel, "
+                      "tolerance 1e-6, relTol 0; multicolour sweeps (log name B200smoothSolver(mc))",
+            "N": N, "F": F, "colours": C, "sweeps_to_tolerance": p.nIterations, "converged": bool(p.converged),
+            "time_to_tolerance_ms": ms / 3, "solve_ms": p.solveMs, "setup_ms": p.setupMs,
+            "us_per_sweep_iteration": 1e3 * fp[0].solveMs / max(1, fp[0].nIterations),
+            "gdof_sweeps_per_s": N * p.nIterations / (ms / 3 * 1e-3) / 1e9,
+            "final_residual": p.finalResidual, "max_err_vs_xstar": err, "kernels": kern,
+            "cpu_port": {"kind": "port", "cores": 1, "sample": "set-up + 3 sweep-iterations of the same system",
+                         "seconds": cpu_s, "us_per_sweep_iteration_incl_setup": 1e6 * cpu_s / max(1, cp.nIterations)}}
+
+
 def strong_base_section(env):
     """The N-GPU weak run solves a mesh of N blocks (N = 8: BASELINE configs[3]'s 128 M mesh): rank 0 alone runs
     the SAME global mesh on one GPU for a fixed 200 iterations, so that the strong-scaling speed-up 1 -> N is
@@ -668,7 +732,7 @@ def run_gpu(args):
         if default_run:
             extras |= {"dic_class"}
             if n == 1:
-                extras.add("corrector")
+                extras |= {"corrector", "transport"}
             if n == 8 and not args.block:
                 extras |= {"strong_base", "poly"}
 
@@ -758,6 +822,8 @@ def run_gpu(args):
         sections["dic_class"] = dic_class_section(env, res, n_global)
     if "corrector" in extras and n == 1:
         sections["corrector"] = corrector_section(env, ctx, s)
+    if "transport" in extras and n == 1:
+        sections["transport"] = transport_section(env, ctx, s)
     if "mgpu_parity" in extras and n > 1:
         sections["mgpu_parity"] = mgpu_parity(env)
     if "strong_base" in extras and n > 1:
@@ -911,9 +977,10 @@ def main():
     ap.add_argument("--precond", default=PRECOND,
                     choices=["none", "diagonal", "DIC", "DIC-exact", "DIC-eisenstat", "DIC-multicolour"])
     ap.add_argument("--extras", default="auto",
-                    help="extra sections of the JSON line: auto | none | comma list of dic_class,corrector,mgpu_parity,"
-                         "strong_base,poly.  auto: mgpu_parity at N > 1; on the default workload also dic_class "
-                         "(configs[3]'s preconditioner), corrector at N = 1, strong_base + poly (configs[4]) at N = 8")
+                    help="extra sections of the JSON line: auto | none | comma list of dic_class,corrector,transport,"
+                         "mgpu_parity,strong_base,poly.  auto: mgpu_parity at N > 1; on the default workload also dic_class "
+                         "(configs[3]'s preconditioner), corrector + transport (smoothSolver, SURVEY 8f-4) at N = 1, "
+                         "strong_base + poly (configs[4]) at N = 8")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1864,8 +1864,11 @@ k_eis_final(int N, double* __restrict__ psi, const double* __restrict__ xa, cons
 // entries stored [lower | upper], each in ascending face order, the same order of subtractions
 // (tests/test_smooth_plan.py, numpy transliteration against the C oracle).  Grouped by COLOUR instead
 // (Ordering::MultiColour) the same kernel is a multicolour Gauss-Seidel: a different ordering of the same
-// smoother, one launch per colour.  The last group of a forward sweep and the first group of the reverse sweep
-// are the same rows with the same inputs: the reverse sweep starts at the group before it.
+// smoother, one launch per colour.  Two launches per sweep are redundant and skipped, bit-neutrally: the last group
+// of a forward sweep and the first group of the reverse sweep are the same rows with the same inputs (the reverse
+// sweep starts at the group before it), and so are the last group of a reverse sweep (group 0) and the first group
+// of the NEXT forward sweep -- after the first sweep of a solve a symGaussSeidel sweep is 2 C - 2 launches (two
+// half-sweeps on a 2-colour hex mesh).
 
 // matrix value fill of the full-row ELL for lower != upper: the entry of row r on face f carries upper[f] when
 // r's cell owns the face (A[l][u] = upper), lower[f] when it is the face's neighbour (A[u][l] = lower)
@@ -1887,19 +1890,35 @@ k_fill_values_asym(int N, const int64_t* __restrict__ sliceBase, const uint32_t*
 
 // one group (level / colour) of a Gauss-Seidel sweep: rows [r0, r1), in place.  The next row's row length /
 // slice base / b / diag are requested before the current row's gathers (as in k_eis_bwd).
-template <bool C16, int B, int CT>
+// RES (multicolour mode, the LAST group an iteration updates): every neighbour of these rows already holds its final
+// value of the iteration, so the rows' share of gSumMag(residual) is available here for free,
+//     r_c = b_c - sum a x - diag_c psi_c = w - diag_c * fl(w / diag_c)          (a rounding-level quantity),
+// and is accumulated into the running total that k_gs_resid completes over the other rows.  (Upstream evaluates
+// the same quantity as (b - diag psi) - sum a x: the two differ in the last bits of an already rounding-level term.
+// The level-scheduled mode does not use RES: its residual is evaluated in upstream's order over all rows.)
+// HALO (nranks > 1): upstream treats a processor patch as an explicit, Jacobi-like contribution refreshed once per
+// sweep (bPrime = source; updateMatrixInterfaces with the negated coefficients) -- the interface rows take their
+// right-hand side from hbv (k_gs_bprime) instead of b.
+template <bool C16, int B, int CT, bool RES, bool HALO>
 __global__ void __launch_bounds__(kBlock, CT)
 k_gs_rows(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ diag,
-          const double* __restrict__ b, double* x, const Scalars* S) {
-    if (S->done) return;
+          const double* __restrict__ b, const int* __restrict__ rowB, const double* __restrict__ hbv,
+          double* x, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
     const int stride = gridDim.x * kBlock;
     int r = r0 + blockIdx.x * kBlock + threadIdx.x;
     uint32_t len = 0;
     int64_t sb = 0;
     double bv = 0.0, dv = 1.0;
-#define B200_GS_LOAD(ROW, LEN, SB, BV, DV) \
-    { LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; BV = b[ROW]; DV = diag[ROW]; }
+#define B200_GS_LOAD(ROW, LEN, SB, BV, DV)                                   \
+    {                                                                        \
+        LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; DV = diag[ROW];       \
+        int bi_ = -1;                                                        \
+        if (HALO) bi_ = rowB[ROW];                                           \
+        BV = (HALO && bi_ >= 0) ? hbv[bi_] : b[ROW];                         \
+    }
     if (r < r1) B200_GS_LOAD(r, len, sb, bv, dv)
     while (r < r1) {
         const int rn = r + stride;
@@ -1908,40 +1927,80 @@ k_gs_rows(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t*
         double bvN = 0.0, dvN = 1.0;
         if (B > 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
         const double w = eis_row_sub<B, C16, false>(E, val, x, sb + (r & 31), 0, (int)(len >> 16), bv);
-        x[r] = __ddiv_rn(w, dv);
+        const double xn = __ddiv_rn(w, dv);
+        x[r] = xn;
+        if (RES) s[0] = __dadd_rn(s[0], fabs(__dadd_rn(w, -__dmul_rn(dv, xn))));
         if (B == 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
         r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN;
     }
+#undef B200_GS_LOAD
+    if (RES) reduce_finish<1>(s, R);
 }
 
-// gSumMag(lduMatrix::residual(psi, source)): sum |b - A x| with the row sum in upstream's order
-// ((b - diag x) - faces ascending); STEP_GS_RES advances the sweep counter and decides whether the loop goes on
-template <bool C16, int B, int CT>
+// nranks > 1, once per sweep: bPrime of the interface rows = source + sum bou*psi_nbr over the row's processor faces
+// in (patch, face) order -- initMatrixInterfaces / updateMatrixInterfaces with mBouCoeffs = -interfaceBouCoeffs
+// (bPrime[faceCells] -= (-bou)*psi_nbr; the negation is exact, so += bou*psi_nbr is the same bits)
+__global__ void __launch_bounds__(kBlock)
+k_gs_bprime(int nBRows, const int* __restrict__ bRow, const int* __restrict__ bStart, const int* __restrict__ bSlot,
+            const double* __restrict__ bou, const double* recvNccl, Halo H, const double* __restrict__ b,
+            double* __restrict__ hbv, Scalars* S) {
+    if (S->done) return;
+    const double* recv = halo_acquire(H, recvNccl, S);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nBRows; i += gridDim.x * blockDim.x) {
+        double acc = b[bRow[i]];
+        for (int e = bStart[i]; e < bStart[i + 1]; ++e) {
+            const int slot = bSlot[e];
+            acc = __dadd_rn(acc, __dmul_rn(bou[slot], __ldcg(&recv[slot])));
+        }
+        hbv[i] = acc;
+    }
+}
+
+// gSumMag(lduMatrix::residual(psi, source)) over the rows [r0, r1): sum |b - A x| with the row sum in upstream's
+// order ((b - diag x) - faces ascending), added to the running total; STEP_GS_RES advances the sweep counter and
+// decides whether the loop goes on
+// HALO (nranks > 1): the neighbours' psi of the exchange issued just before this kernel; the coupled terms are added
+// last, in (patch, face) order, with the negated coefficients (lduMatrix::residual: rA[faceCells] -= (-bou)*psi_nbr)
+template <bool C16, int B, int CT, bool HALO>
 __global__ void __launch_bounds__(kBlock, CT)
-k_gs_resid(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
+k_gs_resid(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
            EllCols E, const double* __restrict__ val, const double* __restrict__ diag,
-           const double* __restrict__ b, const double* __restrict__ x, Reduce R) {
+           const double* __restrict__ b, const double* __restrict__ x, const int* __restrict__ rowB,
+           const int* __restrict__ bStart, const int* __restrict__ bSlot, const double* __restrict__ bou,
+           const double* recvNccl, Halo H, Reduce R) {
     if (R.S->done) return;
+    const double* recv = nullptr;
+    if (HALO) recv = halo_acquire(H, recvNccl, R.S);
     double s[1] = {0.0};
     const int stride = gridDim.x * kBlock;
-    int r = blockIdx.x * kBlock + threadIdx.x;
+    int r = r0 + blockIdx.x * kBlock + threadIdx.x;
     uint32_t len = 0;
     int64_t sb = 0;
     double bv = 0.0, dv = 1.0;
-    if (r < N) B200_GS_LOAD(r, len, sb, bv, dv)
-    while (r < N) {
+    int bi = -1;
+#define B200_GSR_LOAD(ROW, LEN, SB, BV, DV, BI) \
+    { LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; BV = b[ROW]; DV = diag[ROW]; if (HALO) BI = rowB[ROW]; }
+    if (r < r1) B200_GSR_LOAD(r, len, sb, bv, dv, bi)
+    while (r < r1) {
         const int rn = r + stride;
         uint32_t lenN = 0;
         int64_t sbN = 0;
         double bvN = 0.0, dvN = 1.0;
-        if (B > 0 && rn < N) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
+        int biN = -1;
+        if (B > 0 && rn < r1) B200_GSR_LOAD(rn, lenN, sbN, bvN, dvN, biN)
         double w = __dadd_rn(bv, -__dmul_rn(dv, x[r]));
         w = eis_row_sub<B, C16, false>(E, val, x, sb + (r & 31), 0, (int)(len >> 16), w);
+        if (HALO && bi >= 0) {
+            for (int e = bStart[bi]; e < bStart[bi + 1]; ++e) {
+                const int slot = bSlot[e];
+                w = __dadd_rn(w, __dmul_rn(bou[slot], __ldcg(&recv[slot])));
+            }
+        }
         s[0] = __dadd_rn(s[0], fabs(w));
-        if (B == 0 && rn < N) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
-        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN;
+        if (B == 0 && rn < r1) B200_GSR_LOAD(rn, lenN, sbN, bvN, dvN, biN)
+        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN; bi = biN;
     }
-#undef B200_GS_LOAD
+#undef B200_GSR_LOAD
     reduce_finish<1>(s, R);
 }
 

@@ -136,6 +136,7 @@ struct DevPlan {
     // Eisenstat form, nranks > 1: interface-row index of every row (-1: none) and the halo term B t
     int* rowB = nullptr;
     double* hb = nullptr;
+    double* hbv = nullptr;        // smoothSolver, nranks > 1: bPrime of the interface rows (k_gs_bprime)
     int nB0 = 0;                  // interface rows of the first colour: bRow[0 .. nB0) (bRow is ascending)
     // CUDA graphs of kGraphIters loop bodies, by loop form (0 none, 1 diagonal, 2 DIC-class loop, 3 Eisenstat):
     // kernel arguments are the context's own buffers and the CG scalars live on the device, so one capture
@@ -187,6 +188,7 @@ struct b200_ctx {
     bool forceEll = false;           // an asymmetric matrix is loaded: Amul must take the full-row ELL (the single-read
                                      // layouts store every coefficient once, i.e. assume lower == upper)
     int gsSweeps = 1;                // |nSweeps| of the current smoothSolver call (Scalars::nSweeps)
+    int gsCtas = 0;                  // B200PCG_GS_CTAS=3|4: register build of the narrow-row smoothSolver kernels (0: default 3)
     // boundary faces (b200_set_boundary_faces): CSR cell -> boundary faces in patch order
     int32_t nB = 0;
     std::vector<int32_t> hbCells;
@@ -381,7 +383,7 @@ void free_plan(DevPlan& P) {
     dev_free(P.col16); dev_free(P.colBase); P.c16 = false;
     dev_free(P.sUCol); dev_free(P.sUFace);
     dev_free(P.sUVal); dev_free(P.sLRef); dev_free(P.sRowLen); dev_free(P.sRowLen8);
-    dev_free(P.rowB); dev_free(P.hb);
+    dev_free(P.rowB); dev_free(P.hb); dev_free(P.hbv);
     dev_free(P.srMeta); dev_free(P.srOwnBase); dev_free(P.srOwnFace); dev_free(P.srOwnVal);
     dev_free(P.ctaBStart); dev_free(P.ctaB); P.tailGrid = 0;
     dev_free(P.ctaSStart); dev_free(P.ctaS); P.packGrid = 0;
@@ -572,8 +574,8 @@ int reduce_post(b200_ctx* ctx, int step) {
 // peer-memory form = ONE small kernel that stores straight into the neighbours' receive buffers and raises
 // their flags (kernels.cuh k_pack_p2p); NCCL form = pack + grouped ncclSend/ncclRecv.  The consumer kernels
 // take ctx->haloDev (+ ctx->recvbuf for the NCCL form) and wait for the flags themselves.
-int halo_exchange(b200_ctx* ctx, DevPlan& P, const double* x, cudaStream_t st) {
-    if (ctx->p2pHalo) {
+int halo_exchange(b200_ctx* ctx, DevPlan& P, const double* x, cudaStream_t st, bool forceNccl = false) {
+    if (ctx->p2pHalo && !forceNccl) {
         k_pack_p2p<<<grid_for(ctx, P.nSlots), kBlock, 0, st>>>(ctx->haloDev, P.slotRow, x, ctx->S);
         ctx->launches++;
         return B200_OK;
@@ -1419,42 +1421,112 @@ int load_system_asym(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const dou
     return B200_OK;
 }
 
-// one group (dependency level / colour) of a sweep
-int launch_gs_rows(b200_ctx* ctx, DevPlan& P, int k) {
+// launch geometry of the smoothSolver kernels: like the Eisenstat sweeps, ONE resident wave of the CTAs per SM the
+// kernel is compiled for.  Narrow rows (<= 6 faces): the 64-register build (4 CTAs per SM) or the 80-register one
+// (3 per SM; B200PCG_GS_CTAS=3|4 forces either -- measured in profiles/r02_smooth_*); wide rows: batches of 8, 80 registers.
+int gs_ctas(const b200_ctx* ctx, const DevPlan& P) {
+    if (P.maxRowLen > 6) return 3;
+    return ctx->gsCtas == 4 ? 4 : 3;
+}
+int gs_grid(const b200_ctx* ctx, int rows, int ct) {
+    return grid_for(ctx, std::max(1, rows), ctx->sweepPerSMSet ? ctx->sweepPerSM : ct);
+}
+
+// nranks > 1: interface-row index of every row (shared with the Eisenstat form) + bPrime of the interface rows
+int ensure_gs_halo(b200_ctx* ctx, DevPlan& P) {
+    if (!(ctx->nranks > 1 && P.nSlots > 0)) return B200_OK;
+    if (!P.rowB) {
+        std::vector<int32_t> rb((size_t)ctx->N, -1);
+        for (int b = 0; b < P.h.nBRows; ++b) rb[(size_t)P.h.bRow[b]] = b;
+        RET(upload(ctx, &P.rowB, rb));
+        RET(dev_alloc(ctx, &P.hb, (size_t)P.h.nBRows));
+        P.nB0 = 0;
+        while (P.nB0 < P.h.nBRows && P.h.bRow[(size_t)P.nB0] < P.h.colourStart[1]) ++P.nB0;
+        CU(cudaStreamSynchronize(ctx->sc));   // rb goes out of scope
+    }
+    if (!P.hbv) RET(dev_alloc(ctx, &P.hbv, (size_t)P.h.nBRows));
+    return B200_OK;
+}
+
+// The smoothSolver's exchanges run on the MAIN stream (producer, consumer and everything between them are serial
+// anyway).  Peer-memory halos alternate two halves of the receive buffer, which is safe as long as at most two
+// exchanges lie between two cross-rank reductions (kernels.cuh Halo): one sweep + the residual.  More sweeps per
+// residual evaluation, or sweeps without residuals (nSweeps < 0), take the stream-ordered ncclSend/ncclRecv.
+struct GsHalo {
+    bool on = false, nccl = false;
+    Halo H = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+};
+
+// one group (dependency level / colour) of a sweep; res: also accumulate the rows' share of sum |residual|
+int launch_gs_rows(b200_ctx* ctx, DevPlan& P, int k, bool res, const GsHalo& gh) {
     const int r0 = P.h.colourStart[(size_t)k], r1 = P.h.colourStart[(size_t)k + 1];
     if (r1 <= r0) return B200_OK;
     const EllCols E{P.col, P.col16, P.colBase};
-    const int g = grid_for(ctx, r1 - r0, ctx->sweepPerSM);
-#define B200_GS_ROWS(C16_, B_, CT_)                                                                        \
-    do {                                                                                                   \
-        auto kg = k_gs_rows<C16_, B_, CT_>;                                                                \
-        LAUNCH(PC_GS_ROWS, kg, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, ctx->psi, ctx->S); \
-    } while (0)
     const bool wide = P.maxRowLen > 6;
-    if (P.c16 && wide) B200_GS_ROWS(true, 8, 3);
-    else if (P.c16) B200_GS_ROWS(true, 6, 4);
-    else if (wide) B200_GS_ROWS(false, 8, 3);
-    else B200_GS_ROWS(false, 6, 4);
+    const int ct = res ? 3 : gs_ctas(ctx, P);        // (the residual term spills at 64 registers)
+    const int g = gs_grid(ctx, r1 - r0, ct);
+    Reduce R = mkR(ctx, STEP_NONE);
+#define B200_GS_ROWS(C16_, B_, CT_, RES_, HALO_)                                                           \
+    do {                                                                                                   \
+        auto kg = k_gs_rows<C16_, B_, CT_, RES_, HALO_>;                                                   \
+        LAUNCH(PC_GS_ROWS, kg, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, P.rowB, P.hbv, \
+               ctx->psi, R);                                                                               \
+    } while (0)
+#define B200_GS_ROWS_C(C16_)                                                                               \
+    do {                                                                                                   \
+        if (gh.on && wide) B200_GS_ROWS(C16_, 8, 3, false, true);                                          \
+        else if (gh.on && ct == 4) B200_GS_ROWS(C16_, 6, 4, false, true);                                  \
+        else if (gh.on) B200_GS_ROWS(C16_, 6, 3, false, true);                                             \
+        else if (wide && res) B200_GS_ROWS(C16_, 8, 3, true, false);                                       \
+        else if (wide) B200_GS_ROWS(C16_, 8, 3, false, false);                                             \
+        else if (res) B200_GS_ROWS(C16_, 6, 3, true, false);                                               \
+        else if (ct == 4) B200_GS_ROWS(C16_, 6, 4, false, false);                                          \
+        else B200_GS_ROWS(C16_, 6, 3, false, false);                                                       \
+    } while (0)
+    if (P.c16) B200_GS_ROWS_C(true);
+    else B200_GS_ROWS_C(false);
+#undef B200_GS_ROWS_C
 #undef B200_GS_ROWS
     return B200_OK;
 }
 
-int launch_gs_resid(b200_ctx* ctx, DevPlan& P) {
+// nranks > 1, start of a sweep: exchange psi across the processor patches, bPrime of the interface rows
+int gs_sweep_halo(b200_ctx* ctx, DevPlan& P, const GsHalo& gh) {
+    if (!gh.on) return B200_OK;
+    RET(halo_exchange(ctx, P, ctx->psi, ctx->sc, gh.nccl));
+    LAUNCH(PC_IFACE, k_gs_bprime, grid_for(ctx, P.h.nBRows), P.h.nBRows, P.bRow, P.bStart, P.bSlot, ctx->bou,
+           ctx->recvbuf, gh.H, ctx->src, P.hbv, ctx->S);
+    return B200_OK;
+}
+
+// sum |residual| over the rows [r0, r1) (an empty range still completes the reduction) + STEP_GS_RES
+int launch_gs_resid(b200_ctx* ctx, DevPlan& P, int r0, int r1, const GsHalo& gh) {
     const EllCols E{P.col, P.col16, P.colBase};
-    const int N = ctx->N;
-    const int g = grid_for(ctx, N, ctx->sweepPerSM);
-    Reduce R = mkR(ctx, STEP_GS_RES);
-#define B200_GS_RESID(C16_, B_, CT_)                                                                       \
-    do {                                                                                                   \
-        auto kg = k_gs_resid<C16_, B_, CT_>;                                                               \
-        LAUNCH(PC_GS_RESID, kg, g, N, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, ctx->psi, R);  \
-    } while (0)
     const bool wide = P.maxRowLen > 6;
-    if (P.c16 && wide) B200_GS_RESID(true, 8, 3);
-    else if (P.c16) B200_GS_RESID(true, 6, 4);
-    else if (wide) B200_GS_RESID(false, 8, 3);
-    else B200_GS_RESID(false, 6, 4);
+    const int ct = gs_ctas(ctx, P);
+    const int g = gs_grid(ctx, r1 - r0, ct);
+    if (gh.on) RET(halo_exchange(ctx, P, ctx->psi, ctx->sc, gh.nccl));
+    Reduce R = mkR(ctx, STEP_GS_RES);
+#define B200_GS_RESID(C16_, B_, CT_, HALO_)                                                                \
+    do {                                                                                                   \
+        auto kg = k_gs_resid<C16_, B_, CT_, HALO_>;                                                        \
+        LAUNCH(PC_GS_RESID, kg, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, ctx->psi, \
+               P.rowB, P.bStart, P.bSlot, ctx->bou, ctx->recvbuf, gh.H, R);                                \
+    } while (0)
+#define B200_GS_RESID_C(C16_)                                                                              \
+    do {                                                                                                   \
+        if (gh.on && wide) B200_GS_RESID(C16_, 8, 3, true);                                                \
+        else if (gh.on && ct == 4) B200_GS_RESID(C16_, 6, 4, true);                                        \
+        else if (gh.on) B200_GS_RESID(C16_, 6, 3, true);                                                   \
+        else if (wide) B200_GS_RESID(C16_, 8, 3, false);                                                   \
+        else if (ct == 4) B200_GS_RESID(C16_, 6, 4, false);                                                \
+        else B200_GS_RESID(C16_, 6, 3, false);                                                             \
+    } while (0)
+    if (P.c16) B200_GS_RESID_C(true);
+    else B200_GS_RESID_C(false);
+#undef B200_GS_RESID_C
 #undef B200_GS_RESID
+    RET(reduce_post(ctx, STEP_GS_RES));
     return B200_OK;
 }
 
@@ -1467,8 +1539,6 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
         return fail(ctx, B200_EINVAL, "bad sweepMode code");
     if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_smooth_controls.reserved must be 0");
     if (ctl->nSweeps == 0) return fail(ctx, B200_EINVAL, "nSweeps must not be 0");
-    if (ctx->nranks > 1)
-        return fail(ctx, B200_EUNSUPPORTED, "smoothSolver with processor patches (nranks > 1) is not built yet");
     if (ctx->tileRows > 0) return fail(ctx, B200_EUNSUPPORTED, "smoothSolver does not take tiled plans (B200PCG_TILE)");
     DevPlan* Pp = nullptr;
     RET(ensure_plan(ctx, ctl->sweepMode == B200_SWEEP_EXACT ? Ordering::Levels : Ordering::MultiColour, &Pp));
@@ -1480,6 +1550,15 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     const int nS = fixed ? -ctl->nSweeps : ctl->nSweeps;
     const bool sym = ctl->smoother == B200_SMOOTHER_SYM_GAUSS_SEIDEL;
     const int C = P.h.nColours;
+    // processor patches (nranks > 1): explicit, refreshed once per sweep, as upstream
+    GsHalo gh;
+    gh.on = ctx->nranks > 1 && P.nSlots > 0;
+    if (gh.on) {
+        RET(ensure_gs_halo(ctx, P));
+        gh.nccl = !ctx->p2pHalo || fixed || nS > 1;
+        if (!gh.nccl) gh.H = ctx->haloDev;
+    }
+    const bool multi = ctx->nranks > 1;
 
     CU(cudaEventRecord(ctx->ev[0], ctx->sc));
     const b200_controls c{ctl->tolerance, ctl->relTol, ctl->maxIter, ctl->minIter, 0, 0};
@@ -1493,10 +1572,12 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
         {
             Reduce R = mkR(ctx, STEP_SUMPSI);
             LAUNCH(PC_SUM, k_sum, gv, N, ctx->psi, R);
+            RET(reduce_post(ctx, STEP_SUMPSI));
         }
         {
             Reduce R = mkR(ctx, STEP_NORM);
             LAUNCH(PC_NORM, k_norm_resid, gv, N, ctx->w, ctx->p, ctx->src, ctx->r, R);
+            RET(reduce_post(ctx, STEP_NORM));
         }
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->sc));
@@ -1504,15 +1585,35 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     CU(cudaStreamSynchronize(ctx->sc));
     CU(cudaGetLastError());
 
-    auto sweep = [&]() -> int {
-        for (int k = 0; k < C; ++k) RET(launch_gs_rows(ctx, P, k));
-        // reverse sweep: the last group would be recomputed from unchanged inputs, start one before it
-        if (sym) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k));
+    // One sweep.  Groups visited: forward 0 .. C-1, reverse C-2 .. 0 (the last group of the forward sweep would be
+    // recomputed from unchanged inputs); after the first sweep of the solve a symmetric sweep also skips group 0 of
+    // its forward half (it was the last group of the previous reverse half and nothing it reads has changed since):
+    // both skips are bit-neutral.  Multicolour mode: the last group an ITERATION updates accumulates its own share
+    // of sum |residual| (kernels.cuh k_gs_rows RES), and k_gs_resid covers the other rows only.
+    // With processor patches neither shortcut holds: the halo values are refreshed at the start of every sweep (group
+    // 0's interface rows DO change), and the last group's in-kernel residual would use the halo of the sweep's start.
+    const bool fusedRes = !fixed && !multi && ctl->sweepMode == B200_SWEEP_MULTICOLOUR;
+    const bool back = sym && C >= 2;                 // the sweep has a reverse half that ends on group 0
+    const int lastGroup = back ? 0 : C - 1;
+    bool firstSweep = true;
+    auto sweep = [&](bool res) -> int {
+        const int k0 = (back && !firstSweep && !multi) ? 1 : 0;
+        firstSweep = false;
+        RET(gs_sweep_halo(ctx, P, gh));
+        for (int k = k0; k < C; ++k) RET(launch_gs_rows(ctx, P, k, res && !back && k == C - 1, gh));
+        if (back) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k, res && k == 0, gh));
         return B200_OK;
     };
     if (fixed) {
-        for (int i = 0; i < nS; ++i) RET(sweep());
+        for (int i = 0; i < nS; ++i) RET(sweep(false));
     } else {
+        // rows whose residual is evaluated explicitly: all of them, or all but the group the iteration updated last
+        int q0 = 0, q1 = N;
+        if (fusedRes) {
+            if (lastGroup == 0) q0 = P.h.colourStart[1];
+            else q1 = P.h.colourStart[(size_t)C - 1];
+            if (C == 1) q0 = q1 = 0;
+        }
         // loop bodies the do/while can execute at most; the device decides when to stop (kernels return on S->done)
         const int64_t target = ctx->forceIters > 0 ? ctx->forceIters : std::max<int64_t>(ctl->maxIter, ctl->minIter);
         const int64_t cap = std::max<int64_t>(1, (target + nS - 1) / nS);
@@ -1523,8 +1624,8 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
             const int n = (int)std::min<int64_t>(chunk, cap - enq);
             for (int i = 0; i < n; ++i) {
                 ctx->profIter = (int)(enq + i + 1) * nS;
-                for (int sw = 0; sw < nS; ++sw) RET(sweep());
-                RET(launch_gs_resid(ctx, P));
+                for (int sw = 0; sw < nS; ++sw) RET(sweep(fusedRes && sw == nS - 1));
+                RET(launch_gs_resid(ctx, P, q0, q1, gh));
             }
             ctx->profIter = 0;
             enq += n;
@@ -1899,6 +2000,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e14 = getenv("B200PCG_FAST_CTAS")) c->fastMaxCtas = std::max(1, atoi(e14));
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
     if (const char* e15 = getenv("B200PCG_COL16")) c->disableCol16 = atoi(e15) == 0;
+    if (const char* eg = getenv("B200PCG_GS_CTAS")) c->gsCtas = atoi(eg);
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;

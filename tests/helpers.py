@@ -121,20 +121,25 @@ class PlanView:
                 val[e] = upper[f] if lowerAddr[f] == c else lower[f]
         return val
 
-    def gs_rows(self, k, diag_i, val, b_i, x_i):
+    def gs_rows(self, k, diag_i, val, b_i, x_i, res=False):
         """k_gs_rows over colour / level k, in place: x[r] = (b[r] - sum_j val*x[col]) / diag[r], entries in the
-        plan's order [earlier | later], each ascending natural face order."""
+        plan's order [earlier | later], each ascending natural face order.  res: returns the rows' share of
+        sum |residual| as the kernel forms it, |w - diag * x_new|."""
+        tot = 0.0
         for r in self.rows_of_colour(k):
             w = b_i[r]
             for j in range(self.nTotal[r]):
                 e = self.entry(r, j)
                 w = w - val[e] * x_i[self.col[e]]
             x_i[r] = w / diag_i[r]
+            if res:
+                tot += abs(w - diag_i[r] * x_i[r])
+        return tot
 
-    def gs_residual(self, diag_i, val, b_i, x_i):
-        """k_gs_resid: sum |b - A x| with the row sum in lduMatrix::residual's order."""
+    def gs_residual(self, diag_i, val, b_i, x_i, r0=0, r1=None):
+        """k_gs_resid: sum |b - A x| over the rows [r0, r1) with the row sum in lduMatrix::residual's order."""
         tot = 0.0
-        for r in range(self.N):
+        for r in range(r0, self.N if r1 is None else r1):
             w = b_i[r] - diag_i[r] * x_i[r]
             for j in range(self.nTotal[r]):
                 e = self.entry(r, j)
@@ -555,27 +560,33 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
 
 
 def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
-                          nSweeps=1):
+                          nSweeps=1, mode="multicolour"):
     """Kernel-by-kernel transliteration of b200_smooth_solve on one rank (solver.cu smooth_core, kernels.cuh
-    k_fill_values_asym / k_gs_rows / k_gs_resid, STEP_NORM / STEP_GS_RES).  pv: a Levels plan (exact mode:
-    OpenFOAM's own elimination order) or a MultiColour plan (GS-class).  Returns (psi natural, nIter, initRes,
-    finalRes)."""
+    k_fill_values_asym / k_gs_rows / k_gs_resid, STEP_NORM / STEP_GS_RES).  pv: a Levels plan with mode="exact"
+    (OpenFOAM's own elimination order) or a MultiColour plan with mode="multicolour" (GS-class: the group an
+    iteration updates last contributes its residual in-kernel).  Returns (psi natural, nIter, initRes, finalRes)."""
     low = s.upper if s.lower is None else s.lower
     val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
     d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
     C = pv.nColours
-    sym = smoother == "symGaussSeidel"
+    back = smoother == "symGaussSeidel" and C >= 2
+    fused = mode == "multicolour" and nSweeps > 0
+    state = {"first": True}
 
-    def sweep():
-        for k in range(C):
-            pv.gs_rows(k, d, val, b, x)
-        if sym:
-            for k in range(C - 2, -1, -1):          # the last colour's rows would be recomputed from unchanged inputs
-                pv.gs_rows(k, d, val, b, x)
+    def sweep(res):
+        k0 = 1 if (back and not state["first"]) else 0      # group 0 was the last group of the previous reverse half
+        state["first"] = False
+        tot = 0.0
+        for k in range(k0, C):
+            tot += pv.gs_rows(k, d, val, b, x, res and not back and k == C - 1)
+        if back:
+            for k in range(C - 2, -1, -1):          # group C-1 would be recomputed from unchanged inputs
+                tot += pv.gs_rows(k, d, val, b, x, res and k == 0)
+        return tot
 
     if nSweeps < 0:
         for _ in range(-nSweeps):
-            sweep()
+            sweep(False)
         return pv.to_natural(x), -nSweeps, 0.0, 0.0
     wA = pv.spmv(d, val, x)
     sumA = pv.spmv(d, val, np.ones(pv.N))
@@ -583,12 +594,21 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
     nf = (np.abs(wA - sumA * xRef) + np.abs(b - sumA * xRef)).sum() + 1e-20
     init = final = np.abs(b - wA).sum() / nf
     conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
+    q0, q1 = 0, pv.N
+    if fused:
+        if back:
+            q0 = int(pv.colourStart[1])
+        else:
+            q1 = int(pv.colourStart[C - 1])
+        if C == 1:
+            q0 = q1 = 0
     n = 0
     if minIter > 0 or not conv():
         while True:
-            for _ in range(nSweeps):
-                sweep()
-            final = pv.gs_residual(d, val, b, x) / nf
+            tot = 0.0
+            for sw in range(nSweeps):
+                tot += sweep(fused and sw == nSweeps - 1)
+            final = (tot + pv.gs_residual(d, val, b, x, q0, q1)) / nf
             n += nSweeps
             if not ((n < maxIter and not conv()) or n < minIter):
                 break

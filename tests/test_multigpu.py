@@ -73,3 +73,34 @@ def test_multigpu_parity(world, tile):
         for key, base in (("DIC-eisenstat", "DIC"), ("poly-DIC-eisenstat", "poly-DIC")):
             assert res[key]["converged"] and res[key]["relerr_vs_oracle"] < 1e-6, (key, res[key])
             assert res[base]["iters"] <= res[key]["iters"] <= res[base]["iters"] + 2, (key, res[key], res[base])
+
+
+@pytest.mark.parametrize("world,halo", [(2, None), (2, "nccl-halo"), (4, None), (8, None)])
+def test_multigpu_smooth_parity(world, halo):
+    """smoothSolver with processor patches against the N-rank CPU oracle: asymmetric Amul
+    bit-identical; level-scheduled sweeps bit-identical psi and identical sweep counts (peer-memory halos when one
+    sweep + the residual lie between two reductions, ncclSend/ncclRecv for nSweeps > 1 and fixed sweeps); the
+    multicolour sweeps reach the same solution."""
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           os.path.join(ROOT, "tests", "mgpu_smooth_worker.py")]
+    env = dict(os.environ)
+    if halo == "nccl-halo":
+        env["B200PCG_HALO"] = "nccl"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_SMOOTH_RESULT ")][-1]
+    res = json.loads(line[len("MGPU_SMOOTH_RESULT "):])
+    for tag in ("hex-", "poly-"):
+        assert res[tag + "amul_bit_exact"]
+        for key in ("exact-fixed3", "exact-sym", "exact-gs-nsweeps2", "exact-U-controls"):
+            e = res[tag + key]
+            assert e["iters"] == e["oracle_iters"] and e["bit_identical"], (tag + key, e)
+            if key != "exact-fixed3":
+                assert e["init"] == pytest.approx(e["oracle_init"], rel=1e-12)
+                assert e["final"] == pytest.approx(e["oracle_final"], rel=1e-9)
+        for key in ("mc-sym", "mc-gs-nsweeps3"):
+            e = res[tag + key]
+            assert e["converged"] and e["relerr_vs_oracle"] < 1e-8, (tag + key, e)
