@@ -1899,42 +1899,51 @@ k_fill_values_asym(int N, const int64_t* __restrict__ sliceBase, const uint32_t*
 // HALO (nranks > 1): upstream treats a processor patch as an explicit, Jacobi-like contribution refreshed once per
 // sweep (bPrime = source; updateMatrixInterfaces with the negated coefficients) -- the interface rows take their
 // right-hand side from hbv (k_gs_bprime) instead of b.
-template <bool C16, int B, int CT, bool RES, bool HALO>
+// RES == 2 (two-colour plans, the FIRST group an iteration updates): nothing these rows read has changed since the
+// end of the previous iteration, so  w - diag_c * psi_c(old)  IS their residual at the end of that iteration.  The
+// pass completes the previous iteration's reduction (its other group contributed through RES == 1) and runs
+// STEP_GS_RES -- no separate residual kernel at all -- while it writes the NEW values into a shadow array (xw != xo):
+// if the step decides that the previous iteration converged, the old values are still there.
+// x arrays: xg is gathered from (the OTHER group's rows), xo holds this group's old values (RES == 2 only), xw
+// receives the new ones.
+template <bool C16, int B, int CT, int RES, bool HALO>
 __global__ void __launch_bounds__(kBlock, CT)
 k_gs_rows(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
           EllCols E, const double* __restrict__ val, const double* __restrict__ diag,
           const double* __restrict__ b, const int* __restrict__ rowB, const double* __restrict__ hbv,
-          double* x, Reduce R) {
+          const double* xg, const double* xo, double* xw, Reduce R) {
     if (R.S->done) return;
     double s[1] = {0.0};
     const int stride = gridDim.x * kBlock;
     int r = r0 + blockIdx.x * kBlock + threadIdx.x;
     uint32_t len = 0;
     int64_t sb = 0;
-    double bv = 0.0, dv = 1.0;
-#define B200_GS_LOAD(ROW, LEN, SB, BV, DV)                                   \
+    double bv = 0.0, dv = 1.0, ov = 0.0;
+#define B200_GS_LOAD(ROW, LEN, SB, BV, DV, OV)                               \
     {                                                                        \
         LEN = rowLen[ROW]; SB = sliceBase[(ROW) >> 5]; DV = diag[ROW];       \
         int bi_ = -1;                                                        \
         if (HALO) bi_ = rowB[ROW];                                           \
         BV = (HALO && bi_ >= 0) ? hbv[bi_] : b[ROW];                         \
+        if (RES == 2) OV = xo[ROW];                                          \
     }
-    if (r < r1) B200_GS_LOAD(r, len, sb, bv, dv)
+    if (r < r1) B200_GS_LOAD(r, len, sb, bv, dv, ov)
     while (r < r1) {
         const int rn = r + stride;
         uint32_t lenN = 0;
         int64_t sbN = 0;
-        double bvN = 0.0, dvN = 1.0;
-        if (B > 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
-        const double w = eis_row_sub<B, C16, false>(E, val, x, sb + (r & 31), 0, (int)(len >> 16), bv);
+        double bvN = 0.0, dvN = 1.0, ovN = 0.0;
+        if (B > 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN, ovN)
+        const double w = eis_row_sub<B, C16, false>(E, val, xg, sb + (r & 31), 0, (int)(len >> 16), bv);
         const double xn = __ddiv_rn(w, dv);
-        x[r] = xn;
-        if (RES) s[0] = __dadd_rn(s[0], fabs(__dadd_rn(w, -__dmul_rn(dv, xn))));
-        if (B == 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN)
-        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN;
+        xw[r] = xn;
+        if (RES == 1) s[0] = __dadd_rn(s[0], fabs(__dadd_rn(w, -__dmul_rn(dv, xn))));
+        if (RES == 2) s[0] = __dadd_rn(s[0], fabs(__dadd_rn(w, -__dmul_rn(dv, ov))));
+        if (B == 0 && rn < r1) B200_GS_LOAD(rn, lenN, sbN, bvN, dvN, ovN)
+        r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN; ov = ovN;
     }
 #undef B200_GS_LOAD
-    if (RES) reduce_finish<1>(s, R);
+    if (RES != 0) reduce_finish<1>(s, R);
 }
 
 // nranks > 1, once per sweep: bPrime of the interface rows = source + sum bou*psi_nbr over the row's processor faces

@@ -189,6 +189,7 @@ struct b200_ctx {
                                      // layouts store every coefficient once, i.e. assume lower == upper)
     int gsSweeps = 1;                // |nSweeps| of the current smoothSolver call (Scalars::nSweeps)
     int gsCtas = 0;                  // B200PCG_GS_CTAS=3|4: register build of the narrow-row smoothSolver kernels (0: default 3)
+    bool gsLagged = true;            // B200PCG_GS_LAGGED=0: two-colour plans evaluate the residual with a separate kernel (A/B switch)
     // boundary faces (b200_set_boundary_faces): CSR cell -> boundary faces in patch order
     int32_t nB = 0;
     std::vector<int32_t> hbCells;
@@ -1457,31 +1458,39 @@ struct GsHalo {
     Halo H = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
 };
 
-// one group (dependency level / colour) of a sweep; res: also accumulate the rows' share of sum |residual|
-int launch_gs_rows(b200_ctx* ctx, DevPlan& P, int k, bool res, const GsHalo& gh) {
+// one group (dependency level / colour) of a sweep.  res 1: also accumulate the rows' share of sum |residual|
+// (formed from the new values); res 2 (kernels.cuh k_gs_rows): the rows' residual at the END OF THE PREVIOUS
+// iteration from their old values xo, the new ones written to xw, the reduction completed with STEP_GS_RES.
+// xg / xw default to psi (in place).
+int launch_gs_rows(b200_ctx* ctx, DevPlan& P, int k, int res, const GsHalo& gh, const double* xg = nullptr,
+                   const double* xo = nullptr, double* xw = nullptr) {
     const int r0 = P.h.colourStart[(size_t)k], r1 = P.h.colourStart[(size_t)k + 1];
     if (r1 <= r0) return B200_OK;
+    if (!xg) xg = ctx->psi;
+    if (!xw) xw = ctx->psi;
     const EllCols E{P.col, P.col16, P.colBase};
     const bool wide = P.maxRowLen > 6;
     const int ct = res ? 3 : gs_ctas(ctx, P);        // (the residual term spills at 64 registers)
     const int g = gs_grid(ctx, r1 - r0, ct);
-    Reduce R = mkR(ctx, STEP_NONE);
+    Reduce R = mkR(ctx, res == 2 ? STEP_GS_RES : STEP_NONE);
 #define B200_GS_ROWS(C16_, B_, CT_, RES_, HALO_)                                                           \
     do {                                                                                                   \
         auto kg = k_gs_rows<C16_, B_, CT_, RES_, HALO_>;                                                   \
         LAUNCH(PC_GS_ROWS, kg, g, r0, r1, P.sliceBase, P.rowLen, E, P.val, ctx->diag, ctx->src, P.rowB, P.hbv, \
-               ctx->psi, R);                                                                               \
+               xg, xo, xw, R);                                                                             \
     } while (0)
 #define B200_GS_ROWS_C(C16_)                                                                               \
     do {                                                                                                   \
-        if (gh.on && wide) B200_GS_ROWS(C16_, 8, 3, false, true);                                          \
-        else if (gh.on && ct == 4) B200_GS_ROWS(C16_, 6, 4, false, true);                                  \
-        else if (gh.on) B200_GS_ROWS(C16_, 6, 3, false, true);                                             \
-        else if (wide && res) B200_GS_ROWS(C16_, 8, 3, true, false);                                       \
-        else if (wide) B200_GS_ROWS(C16_, 8, 3, false, false);                                             \
-        else if (res) B200_GS_ROWS(C16_, 6, 3, true, false);                                               \
-        else if (ct == 4) B200_GS_ROWS(C16_, 6, 4, false, false);                                          \
-        else B200_GS_ROWS(C16_, 6, 3, false, false);                                                       \
+        if (gh.on && wide) B200_GS_ROWS(C16_, 8, 3, 0, true);                                              \
+        else if (gh.on && ct == 4) B200_GS_ROWS(C16_, 6, 4, 0, true);                                      \
+        else if (gh.on) B200_GS_ROWS(C16_, 6, 3, 0, true);                                                 \
+        else if (wide && res == 2) B200_GS_ROWS(C16_, 8, 3, 2, false);                                     \
+        else if (wide && res) B200_GS_ROWS(C16_, 8, 3, 1, false);                                          \
+        else if (wide) B200_GS_ROWS(C16_, 8, 3, 0, false);                                                 \
+        else if (res == 2) B200_GS_ROWS(C16_, 6, 3, 2, false);                                             \
+        else if (res) B200_GS_ROWS(C16_, 6, 3, 1, false);                                                  \
+        else if (ct == 4) B200_GS_ROWS(C16_, 6, 4, 0, false);                                              \
+        else B200_GS_ROWS(C16_, 6, 3, 0, false);                                                           \
     } while (0)
     if (P.c16) B200_GS_ROWS_C(true);
     else B200_GS_ROWS_C(false);
@@ -1595,13 +1604,43 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     const bool fusedRes = !fixed && !multi && ctl->sweepMode == B200_SWEEP_MULTICOLOUR;
     const bool back = sym && C >= 2;                 // the sweep has a reverse half that ends on group 0
     const int lastGroup = back ? 0 : C - 1;
+    // TWO colours (hex meshes): after the first sweep an iteration is [group F, group L] with F = the group the sweep
+    // updates first; F's pass of the NEXT iteration delivers F's residual of this one for free (k_gs_rows RES == 2),
+    // L's comes from its own pass (RES == 1): no residual kernel at all.  F's new values go to a shadow array
+    // (ctx->w, free after the set-up) so that the old ones survive the decision; they alternate between the two.
+    const bool lagged = fusedRes && C == 2 && ctx->gsLagged;
+    const int gF = back ? 1 : 0, gL = 1 - gF;
+    double* const arr[2] = {ctx->psi, ctx->w};
+    int curF = 0;                                    // which array holds group F's current values
     bool firstSweep = true;
     auto sweep = [&](bool res) -> int {
         const int k0 = (back && !firstSweep && !multi) ? 1 : 0;
         firstSweep = false;
         RET(gs_sweep_halo(ctx, P, gh));
-        for (int k = k0; k < C; ++k) RET(launch_gs_rows(ctx, P, k, res && !back && k == C - 1, gh));
-        if (back) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k, res && k == 0, gh));
+        for (int k = k0; k < C; ++k) RET(launch_gs_rows(ctx, P, k, (res && !back && k == C - 1) ? 1 : 0, gh));
+        if (back) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k, (res && k == 0) ? 1 : 0, gh));
+        return B200_OK;
+    };
+    // lagged form: one sweep of a two-colour plan.  lag: this sweep opens an iteration after the first one
+    auto sweep2 = [&](int64_t body, bool lag, bool res) -> int {
+        ctx->profIter = (int)(body + 1) * nS;        // (profile: loop bodies beyond the last executed one are dropped)
+        if (firstSweep) {                            // groups 0, 1 [, 0]: everything in psi
+            firstSweep = false;
+            RET(launch_gs_rows(ctx, P, 0, 0, gh));
+            RET(launch_gs_rows(ctx, P, 1, (res && !back) ? 1 : 0, gh));
+            if (back) RET(launch_gs_rows(ctx, P, 0, res ? 1 : 0, gh));
+            return B200_OK;
+        }
+        if (lag) {
+            ctx->profIter = (int)body * nS;          // this pass completes the PREVIOUS iteration's residual
+            RET(launch_gs_rows(ctx, P, gF, 2, gh, ctx->psi, arr[curF], arr[1 - curF]));
+            ctx->profIter = (int)(body + 1) * nS;
+            curF = 1 - curF;
+        } else {
+            RET(launch_gs_rows(ctx, P, gF, 0, gh, ctx->psi, nullptr, arr[curF]));
+        }
+        // group L: in place in psi, gathers F's current values
+        RET(launch_gs_rows(ctx, P, gL, res ? 1 : 0, gh, arr[curF], nullptr, ctx->psi));
         return B200_OK;
     };
     if (fixed) {
@@ -1616,7 +1655,8 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
         }
         // loop bodies the do/while can execute at most; the device decides when to stop (kernels return on S->done)
         const int64_t target = ctx->forceIters > 0 ? ctx->forceIters : std::max<int64_t>(ctl->maxIter, ctl->minIter);
-        const int64_t cap = std::max<int64_t>(1, (target + nS - 1) / nS);
+        // (lagged: the residual of iteration k is completed by the first pass of body k + 1)
+        const int64_t cap = std::max<int64_t>(1, (target + nS - 1) / nS) + (lagged ? 1 : 0);
         int64_t enq = 0;
         // a level-scheduled body is hundreds of launches: poll after every one; multicolour bodies are a few
         int chunk = (ctl->sweepMode == B200_SWEEP_EXACT && C > 16) ? 1 : 2;
@@ -1624,8 +1664,12 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
             const int n = (int)std::min<int64_t>(chunk, cap - enq);
             for (int i = 0; i < n; ++i) {
                 ctx->profIter = (int)(enq + i + 1) * nS;
-                for (int sw = 0; sw < nS; ++sw) RET(sweep(fusedRes && sw == nS - 1));
-                RET(launch_gs_resid(ctx, P, q0, q1, gh));
+                if (lagged) {
+                    for (int sw = 0; sw < nS; ++sw) RET(sweep2(enq + i, sw == 0 && enq + i > 0, sw == nS - 1));
+                } else {
+                    for (int sw = 0; sw < nS; ++sw) RET(sweep(fusedRes && sw == nS - 1));
+                    RET(launch_gs_resid(ctx, P, q0, q1, gh));
+                }
             }
             ctx->profIter = 0;
             enq += n;
@@ -1633,6 +1677,16 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
             CU(cudaStreamSynchronize(ctx->sc));
             CU(cudaGetLastError());
             if (chunk < 16 && chunk > 1) chunk *= 2;
+        }
+        if (lagged) {
+            // group F's values of the LAST COMPLETED iteration K: iteration 1 wrote them in psi, every later one in
+            // the other array (the pass that found iteration K converged wrote iteration K + 1's elsewhere)
+            const int K = ctx->hS->nIter / nS;
+            if (K >= 1 && ((K - 1) & 1)) {
+                const int f0 = P.h.colourStart[(size_t)gF], f1 = P.h.colourStart[(size_t)gF + 1];
+                CU(cudaMemcpyAsync(ctx->psi + f0, ctx->w + f0, (size_t)(f1 - f0) * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, ctx->sc));
+            }
         }
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->sc));
@@ -2001,6 +2055,7 @@ int b200_ctx_create(int device, int rank, int nranks, const void* nccl_uid, b200
     if (const char* e10 = getenv("B200PCG_SMALL_CTAS")) c->smallCtas = std::max(1, std::min(kSmallMaxCtas, atoi(e10)));
     if (const char* e15 = getenv("B200PCG_COL16")) c->disableCol16 = atoi(e15) == 0;
     if (const char* eg = getenv("B200PCG_GS_CTAS")) c->gsCtas = atoi(eg);
+    if (const char* el = getenv("B200PCG_GS_LAGGED")) c->gsLagged = atoi(el) != 0;
     if (const char* e13 = getenv("B200PCG_TILE")) c->tileRows = std::max(0, atoi(e13));
     if (const char* e12 = getenv("B200PCG_FUSE_FIRST")) c->noFuseFirst = atoi(e12) == 0;
     if (const char* e17 = getenv("B200PCG_EIS_BATCH")) c->eisBatch = atoi(e17) != 0;

@@ -560,11 +560,12 @@ def pcg_eisenstat_emulated(pv, diag, upper, source, psi0, tol=1e-6, relTol=0.0, 
 
 
 def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relTol=0.0, maxIter=1000, minIter=0,
-                          nSweeps=1, mode="multicolour"):
+                          nSweeps=1, mode="multicolour", lag=True):
     """Kernel-by-kernel transliteration of b200_smooth_solve on one rank (solver.cu smooth_core, kernels.cuh
     k_fill_values_asym / k_gs_rows / k_gs_resid, STEP_NORM / STEP_GS_RES).  pv: a Levels plan with mode="exact"
     (OpenFOAM's own elimination order) or a MultiColour plan with mode="multicolour" (GS-class: the group an
-    iteration updates last contributes its residual in-kernel).  Returns (psi natural, nIter, initRes, finalRes)."""
+    iteration updates last contributes its residual in-kernel; lag: two-colour plans take the other group's from its
+    pass of the NEXT iteration, B200PCG_GS_LAGGED).  Returns (psi natural, nIter, initRes, finalRes)."""
     low = s.upper if s.lower is None else s.lower
     val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
     d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
@@ -603,7 +604,8 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
         if C == 1:
             q0 = q1 = 0
     n = 0
-    if minIter > 0 or not conv():
+    lagged = fused and C == 2 and lag
+    if (minIter > 0 or not conv()) and not lagged:
         while True:
             tot = 0.0
             for sw in range(nSweeps):
@@ -612,4 +614,40 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
             n += nSweeps
             if not ((n < maxIter and not conv()) or n < minIter):
                 break
+    elif minIter > 0 or not conv():
+        # two colours: an iteration after the first sweep is [group F, group L]; F's residual of iteration k comes out of
+        # F's pass of iteration k + 1 (w - diag * x_old, k_gs_rows RES == 2), whose new values go to a shadow array
+        gF = 1 if back else 0
+        gL = 1 - gF
+        rowsF = pv.rows_of_colour(gF)
+
+        def f_pass_lagged():
+            tot, new = 0.0, {}
+            for r in rowsF:
+                w = b[r]
+                for j in range(pv.nTotal[r]):
+                    e = pv.entry(r, j)
+                    w = w - val[e] * x[pv.col[e]]
+                new[r] = w / d[r]
+                tot += abs(w - d[r] * x[r])
+            return tot, new
+        body = 0
+        while True:
+            tot = 0.0
+            for sw in range(nSweeps):
+                res = sw == nSweeps - 1
+                if state["first"]:
+                    tot += sweep(res)
+                else:
+                    if not (sw == 0 and body > 0):          # (the lagged pass below has already updated group F)
+                        pv.gs_rows(gF, d, val, b, x)
+                    tot += pv.gs_rows(gL, d, val, b, x, res)
+            body += 1
+            totF, newF = f_pass_lagged()                    # first pass of the next loop body
+            final = (tot + totF) / nf
+            n += nSweeps
+            if not ((n < maxIter and not conv()) or n < minIter):
+                break
+            for r, v in newF.items():
+                x[r] = v
     return pv.to_natural(x), n, init, final

@@ -167,3 +167,35 @@ def test_device_entry_point_and_rerun_reproducible(gctx):
     psi = np.zeros(N)
     ph = solver(gctx, s, smoother="symGaussSeidel", tolerance=1e-9, maxIter=500).solve(psi, s.source)
     assert ph.nIterations == outs[0][1] and np.array_equal(psi, outs[0][0])
+
+
+def test_lagged_residual_switch_gives_identical_iterates(gctx):
+    """two-colour (hex) plans complete an iteration's residual in the first pass of the next one (default); with
+    B200PCG_GS_LAGGED=0 a separate kernel evaluates it: same iterates, same sweep counts"""
+    import os
+    from firefoam_dev_b200 import Context
+    old = os.environ.get("B200PCG_GS_LAGGED")
+    os.environ["B200PCG_GS_LAGGED"] = "0"
+    try:
+        c2 = Context(device=0)
+    finally:
+        if old is None:
+            os.environ.pop("B200PCG_GS_LAGGED", None)
+        else:
+            os.environ["B200PCG_GS_LAGGED"] = old
+    try:
+        for name in ("hex", "hex-odd", "steckler-topology"):
+            s = dict(SYSTEMS)[name]
+            N = s.addr.nCells
+            for smoother in ("GaussSeidel", "symGaussSeidel"):
+                for ctl in (dict(tolerance=1e-9, maxIter=500), dict(tolerance=1e-6, maxIter=10), dict(tolerance=1e-30, maxIter=7),
+                            dict(tolerance=1e-30, maxIter=8, nSweeps=3), dict(tolerance=1e-3, minIter=4, maxIter=100)):
+                    a, b = np.zeros(N), np.zeros(N)
+                    pa = solver(gctx, s, smoother=smoother, **ctl).solve(a, s.source)
+                    pb = solver(c2, s, smoother=smoother, **ctl).solve(b, s.source)
+                    assert pa.nColours == 2
+                    assert pa.nIterations == pb.nIterations and np.array_equal(a, b), (name, smoother, ctl)
+                    assert pa.finalResidual == pytest.approx(pb.finalResidual, rel=1e-6)
+                    assert pa.converged == pb.converged
+    finally:
+        c2.close()

@@ -81,3 +81,21 @@ def test_skipped_groups_are_bit_neutral(smoother):
                     pv.gs_rows(k, d, val, b, x)
         got, _, _, _ = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, nSweeps=-3, mode=mode)
         assert np.array_equal(got, pv.to_natural(x))
+
+
+@pytest.mark.parametrize("smoother", ["GaussSeidel", "symGaussSeidel"])
+@pytest.mark.parametrize("nSweeps", [1, 2])
+def test_lagged_residual_of_two_colour_plans(smoother, nSweeps):
+    """hex meshes are two-coloured: the residual of an iteration is completed by the first pass of the next one
+    (no residual kernel).  Same iterates, same sweep counts, same residuals (to the rounding of the evaluation order)
+    as the form with an explicit residual pass; stops on the iteration that converged, not one later."""
+    _, s = list(systems())[1]
+    pv = helpers.PlanView(MULTICOLOUR, s.addr)
+    assert pv.nColours == 2
+    N = s.addr.nCells
+    for ctl in (dict(tol=1e-9, maxIter=500), dict(tol=1e-6, maxIter=10), dict(tol=1e-30, maxIter=7),
+                dict(tol=1e-3, minIter=4, maxIter=100), dict(tol=1e-30, relTol=0.01, maxIter=100)):
+        a = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, nSweeps=nSweeps, lag=True, **ctl)
+        b = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, nSweeps=nSweeps, lag=False, **ctl)
+        assert a[1] == b[1] and np.array_equal(a[0], b[0])
+        assert a[3] == pytest.approx(b[3], rel=1e-6)
