@@ -258,8 +258,8 @@ typedef struct b200_smooth_controls {
  *   upper  [nFaces]  A[l][u]   (Amul: Apsi[l] += upper*psi[u])
  *   lower  [nFaces]  A[u][l]   (Amul: Apsi[u] += lower*psi[l]); NULL: symmetric matrix, lower aliases upper
  *   source, psi, ifaceBouCoeffs as in b200_solve.
- * One rank only in this version: with nranks > 1 the call returns B200_EUNSUPPORTED (upstream treats processor
- * patches as explicit, Jacobi-like contributions refreshed once per sweep; not built yet). */
+ * Collective when nranks > 1: processor patches are explicit (Jacobi-like) contributions refreshed once per sweep,
+ * as upstream (bPrime = source; updateMatrixInterfaces with the negated interfaceBouCoeffs). */
 int b200_smooth_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
                       const double* const* ifaceBouCoeffs, const double* source, double* psi,
                       const b200_smooth_controls* ctl, b200_perf* perf);
