@@ -339,7 +339,7 @@ Foam::solverPerformance Foam::B200PCG::solve
     if (dumpDir)
     {
         static int solveIndex = 0;
-        b200_dump d;
+        b200_dump d = b200_dump();   // (lower / haveSmooth of ABI version 2 stay zero: a symmetric PCG solve)
         d.fieldName = fieldName_.c_str();
         d.rank = Pstream::parRun() ? Pstream::myProcNo() : 0;
         d.nranks = Pstream::parRun() ? Pstream::nProcs() : 1;

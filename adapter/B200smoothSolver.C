@@ -5,9 +5,15 @@
 
 #include "B200smoothSolver.H"
 #include "B200Context.H"
+#include "processorLduInterface.H"
+#include "Pstream.H"
 #include "DynamicList.H"
 
 #include "b200pcg.h"
+
+#include <cstdlib>
+#include <cstdio>
+#include <string>
 
 // * * * * * * * * * * * * * * Static Data Members * * * * * * * * * * * * * //
 
@@ -128,6 +134,12 @@ Foam::solverPerformance Foam::B200smoothSolver::solve
         bou.append(interfaceBouCoeffs_[coupledPatches[i]].begin());
     }
 
+    // --- B200PCG_DUMP=<dir>: keep the initial guess so that the system can be written out after the solve together
+    //     with what the solver reported (include/b200pcg.h b200_dump: `lower` and the smoothSolver controls travel)
+    const char* dumpDir = std::getenv("B200PCG_DUMP");
+    scalarField psi0;
+    if (dumpDir) psi0 = psi;
+
     b200_perf perf;
 
     // a diagonal matrix has no off-diagonals at all; a symmetric one has no lower()
@@ -150,6 +162,59 @@ Foam::solverPerformance Foam::B200smoothSolver::solve
     {
         FatalErrorInFunction
             << "B200smoothSolver: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    if (dumpDir)
+    {
+        static int solveIndex = 0;
+        DynamicList<b200_iface> ifaces(coupledPatches.size());
+        forAll(coupledPatches, i)
+        {
+            const label patchi = coupledPatches[i];
+            const processorLduInterface& pi =
+                refCast<const processorLduInterface>(lduInterfaces[patchi]);
+            const labelUList& faceCells = addr.patchAddr(patchi);
+            b200_iface itf;
+            itf.nbrRank = pi.neighbProcNo();
+            itf.nFaces = faceCells.size();
+            itf.faceCells = faceCells.begin();
+            itf.tag = pi.tag();
+            ifaces.append(itf);
+        }
+        b200_dump d = b200_dump();
+        d.fieldName = fieldName_.c_str();
+        d.rank = Pstream::parRun() ? Pstream::myProcNo() : 0;
+        d.nranks = Pstream::parRun() ? Pstream::nProcs() : 1;
+        d.nCells = addr.size();
+        d.nFaces = addr.lowerAddr().size();
+        d.lowerAddr = addr.lowerAddr().begin();
+        d.upperAddr = addr.upperAddr().begin();
+        d.diag = matrix_.diag().begin();
+        d.upper = faces ? matrix_.upper().begin() : nullptr;
+        d.lower = (faces && matrix_.asymmetric()) ? matrix_.lower().begin() : nullptr;
+        d.source = source.begin();
+        d.psi0 = psi0.begin();
+        d.psiSolution = psi.begin();
+        d.nIfaces = ifaces.size();
+        d.ifaces = ifaces.begin();
+        d.ifaceBouCoeffs = bou.begin();
+        d.haveSmooth = 1;
+        d.smooth = ctl;
+        d.havePerf = 1;
+        d.perf = perf;
+        const std::string name((mode == "exact") ? word(typeName) : word(typeName + "(mc)"));
+        d.solverName = name.c_str();
+        d.solveIndex = solveIndex;
+        d.time = matrix_.mesh().thisDb().time().value();
+
+        char file[64];
+        std::snprintf(file, sizeof(file), "_%06d_p%d.b200sys", solveIndex++, d.rank);
+        const std::string path(std::string(dumpDir) + "/" + fieldName_ + file);
+        if (b200_dump_write(path.c_str(), &d) != B200_OK)
+        {
+            WarningInFunction
+                << "B200smoothSolver: " << b200_dump_last_error() << endl;
+        }
     }
 
     solverPerf.initialResidual() = perf.initialResidual;

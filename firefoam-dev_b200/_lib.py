@@ -87,7 +87,8 @@ class Dump(C.Structure):
                 ("psiSolution", C.c_void_p), ("nIfaces", C.c_int32), ("ifaces", C.POINTER(Iface)),
                 ("ifaceBouCoeffs", C.POINTER(C.c_void_p)), ("controls", Controls),
                 ("havePerf", C.c_int32), ("perf", Perf), ("solverName", C.c_char_p),
-                ("solveIndex", C.c_int32), ("time", C.c_double)]
+                ("solveIndex", C.c_int32), ("time", C.c_double),
+                ("lower", C.c_void_p), ("haveSmooth", C.c_int32), ("padSmooth", C.c_int32), ("smooth", SmoothControls)]
 
 
 def build(verbose=False):

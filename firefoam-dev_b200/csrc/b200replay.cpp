@@ -71,6 +71,35 @@ int main(int argc, char** argv) {
         }
         int rc = b200_set_addressing(ctx, key++, d->nCells, d->nFaces, d->lowerAddr, d->upperAddr, 0, nullptr);
         if (rc != B200_OK) { std::fprintf(stderr, "b200replay: %s\n", b200_last_error(ctx)); return 3; }
+        if (d->haveSmooth) {
+            // a smoothSolver solve: asymmetric matrix, its own controls (--precond does not apply)
+            b200_smooth_controls sc = d->smooth;
+            sc.reserved = 0;
+            std::vector<double> psiS((size_t)d->nCells);
+            b200_perf pf;
+            double bestS = 1e300;
+            for (int r = 0; r < repeat; ++r) {
+                std::memcpy(psiS.data(), d->psi0, sizeof(double) * (size_t)d->nCells);
+                rc = b200_smooth_solve(ctx, d->diag, d->upper, d->lower, nullptr, d->source, psiS.data(), &sc, &pf);
+                if (rc != B200_OK && rc != B200_ENONFINITE) { std::fprintf(stderr, "b200replay: %s\n", b200_last_error(ctx)); return 3; }
+                bestS = std::min(bestS, pf.setupMs + pf.solveMs);
+            }
+            const bool exactS = sc.sweepMode == B200_SWEEP_EXACT;
+            std::printf("%s  [%d cells, %d faces, %s, solve %d, t = %g]\n", path.c_str(), d->nCells, d->nFaces,
+                        d->lower ? "asymmetric" : "symmetric", d->solveIndex, d->time);
+            std::printf("  B200smoothSolver%s:  Solving for %s, Initial residual = %.8g, Final residual = %.8g, No Iterations %d\n",
+                        exactS ? "" : "(mc)", d->fieldName, pf.initialResidual, pf.finalResidual, pf.nIterations);
+            if (d->havePerf)
+                std::printf("  %s:  Solving for %s, Initial residual = %.8g, Final residual = %.8g, No Iterations %d   (dumped reference)\n",
+                            d->solverName, d->fieldName, d->perf.initialResidual, d->perf.finalResidual, d->perf.nIterations);
+            std::printf("  device: set-up + solve %.3f ms (best of %d), H2D %.3f ms, D2H %.3f ms\n", bestS, repeat, pf.h2dMs, pf.d2hMs);
+            if (exactS && d->havePerf && pf.nIterations != d->perf.nIterations) {
+                std::printf("  MISMATCH: sweep count differs from the dumped reference\n");
+                mismatches++;
+            }
+            b200_dump_free(f);
+            continue;
+        }
         b200_controls ctl = d->controls;
         const bool own = precond < 0;
         if (!own) ctl.precond = precond;

@@ -144,6 +144,7 @@ int b200_dump_write(const char* path, const b200_dump* d) {
     add("source", "f8", (uint64_t)d->nCells, d->source);
     add("psi0", "f8", (uint64_t)d->nCells, d->psi0);
     if (d->psiSolution) add("psi", "f8", (uint64_t)d->nCells, d->psiSolution);
+    if (d->lower && d->nFaces > 0) add("lower", "f8", (uint64_t)d->nFaces, d->lower);
     for (int k = 0; k < d->nIfaces; ++k) {
         if (d->ifaces[k].nFaces < 0 || (d->ifaces[k].nFaces > 0 && (!d->ifaces[k].faceCells || !d->ifaceBouCoeffs[k])))
             return dfail("bad interface " + std::to_string(k));
@@ -155,13 +156,26 @@ int b200_dump_write(const char* path, const b200_dump* d) {
         std::string h = "{\"format\": \"b200-ldu-system\", \"version\": 1, \"fieldName\": \"" +
                         json_escape(d->fieldName ? d->fieldName : "") + "\", \"rank\": " + std::to_string(d->rank) +
                         ", \"nranks\": " + std::to_string(d->nranks) + ", \"nCells\": " + std::to_string(d->nCells) +
-                        ", \"nFaces\": " + std::to_string(d->nFaces) + ", \"symmetric\": true, \"solveIndex\": " +
-                        std::to_string(d->solveIndex) + ", \"time\": " + fmt_double(d->time) +
-                        ", \"controls\": {\"preconditioner\": \"" + precond_name(d->controls.precond) +
-                        "\", \"precondCode\": " + std::to_string(d->controls.precond) +
-                        ", \"tolerance\": " + fmt_double(d->controls.tolerance) + ", \"relTol\": " +
-                        fmt_double(d->controls.relTol) + ", \"maxIter\": " + std::to_string(d->controls.maxIter) +
-                        ", \"minIter\": " + std::to_string(d->controls.minIter) + "}";
+                        ", \"nFaces\": " + std::to_string(d->nFaces) + ", \"symmetric\": " +
+                        ((d->lower && d->nFaces > 0) ? "false" : "true") + ", \"solveIndex\": " +
+                        std::to_string(d->solveIndex) + ", \"time\": " + fmt_double(d->time);
+        if (d->haveSmooth) {
+            // a smoothSolver solve: lduMatrix::solver's controls + nSweeps, smoother, sweep order
+            const b200_smooth_controls& c = d->smooth;
+            h += std::string(", \"controls\": {\"solver\": \"smoothSolver\", \"smoother\": \"") +
+                 (c.smoother == B200_SMOOTHER_SYM_GAUSS_SEIDEL ? "symGaussSeidel" : "GaussSeidel") +
+                 "\", \"smootherCode\": " + std::to_string(c.smoother) + ", \"sweepMode\": \"" +
+                 (c.sweepMode == B200_SWEEP_EXACT ? "exact" : "multicolour") + "\", \"sweepModeCode\": " +
+                 std::to_string(c.sweepMode) + ", \"nSweeps\": " + std::to_string(c.nSweeps) +
+                 ", \"tolerance\": " + fmt_double(c.tolerance) + ", \"relTol\": " + fmt_double(c.relTol) +
+                 ", \"maxIter\": " + std::to_string(c.maxIter) + ", \"minIter\": " + std::to_string(c.minIter) + "}";
+        } else {
+            h += std::string(", \"controls\": {\"preconditioner\": \"") + precond_name(d->controls.precond) +
+                 "\", \"precondCode\": " + std::to_string(d->controls.precond) +
+                 ", \"tolerance\": " + fmt_double(d->controls.tolerance) + ", \"relTol\": " +
+                 fmt_double(d->controls.relTol) + ", \"maxIter\": " + std::to_string(d->controls.maxIter) +
+                 ", \"minIter\": " + std::to_string(d->controls.minIter) + "}";
+        }
         if (d->havePerf)
             h += ", \"reference\": {\"solverName\": \"" + json_escape(d->solverName ? d->solverName : "") +
                  "\", \"initialResidual\": " + fmt_double(d->perf.initialResidual) + ", \"finalResidual\": " +
@@ -269,6 +283,20 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
         if (num("relTol", cpos, t)) F->d.controls.relTol = t;
         if (num("maxIter", cpos, t)) F->d.controls.maxIter = (int32_t)t;
         if (num("minIter", cpos, t)) F->d.controls.minIter = (int32_t)t;
+        // (the keys of the controls block come before "reference" / "interfaces" / "arrays": bound the search)
+        size_t cend = js.find('}', cpos);
+        size_t spos;
+        if (find_key(js, "smootherCode", cpos, spos) && spos < cend) {
+            F->d.haveSmooth = 1;
+            b200_smooth_controls& c = F->d.smooth;
+            c.tolerance = F->d.controls.tolerance; c.relTol = F->d.controls.relTol;
+            c.maxIter = F->d.controls.maxIter; c.minIter = F->d.controls.minIter;
+            c.nSweeps = 1;
+            if (num("smootherCode", cpos, t)) c.smoother = (int32_t)t;
+            if (num("sweepModeCode", cpos, t)) c.sweepMode = (int32_t)t;
+            if (num("nSweeps", cpos, t)) c.nSweeps = (int32_t)t;
+            c.reserved = 0;
+        }
     }
     size_t rpos;
     if (find_key(js, "reference", 0, rpos)) {
@@ -335,6 +363,7 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
         else if (name == "source" && want(N, "f8")) F->d.source = (const double*)ptr;
         else if (name == "psi0" && want(N, "f8")) F->d.psi0 = (const double*)ptr;
         else if (name == "psi" && want(N, "f8")) F->d.psiSolution = (const double*)ptr;
+        else if (name == "lower" && want(Fc, "f8")) F->d.lower = (const double*)ptr;
         else if (name.compare(0, 5, "iface") == 0) {
             const size_t dot = name.find('.');
             const size_t k = (size_t)std::atoi(name.c_str() + 5);

@@ -34,7 +34,7 @@ class DumpedSolve:
                                              tag=it.get("tag", 0)))
             bou.append(arrays[f"iface{k}.bouCoeffs"])
         addr = LduAddressing(h["nCells"], arrays["lowerAddr"], arrays["upperAddr"], ifs)
-        self.system = System(addr, arrays["diag"], arrays["upper"], arrays["source"], bou)
+        self.system = System(addr, arrays["diag"], arrays["upper"], arrays["source"], bou, lower=arrays.get("lower"))
         self.psi0 = arrays["psi0"]
         self.psi = arrays.get("psi")
         c = h.get("controls", {})
@@ -43,6 +43,13 @@ class DumpedSolve:
                          "minIter": c.get("minIter", 0)}
         if c.get("precondCode") in (3, 4):
             self.controls["B200"] = {"dicMode": {3: "exact", 4: "eisenstat"}[c["precondCode"]]}
+        # a smoothSolver solve: fvSolution-style dict for B200smoothSolver
+        self.smooth = None
+        if c.get("solver") == "smoothSolver":
+            self.smooth = {"smoother": c.get("smoother", "symGaussSeidel"), "tolerance": c.get("tolerance", 1e-6),
+                           "relTol": c.get("relTol", 0.0), "maxIter": c.get("maxIter", 1000), "minIter": c.get("minIter", 0),
+                           "nSweeps": c.get("nSweeps", 1), "B200": {"sweepMode": c.get("sweepMode", "multicolour")}}
+            self.controls = dict(self.smooth)
         self.reference = h.get("reference")
         self.fieldName = h.get("fieldName", "")
         self.rank, self.nranks = h.get("rank", 0), h.get("nranks", 1)
@@ -97,8 +104,16 @@ def write_dump(path, system, psi0, controls, fieldName="p_rgh", psi=None, refere
         keep.append(f64(system.bou[k]))
         bous[k] = keep[-1].ctypes.data
     d.nIfaces, d.ifaces, d.ifaceBouCoeffs = n, ifs, bous
-    ctl, _ = make_controls(controls)
-    d.controls = ctl
+    if system.lower is not None:
+        keep.append(f64(system.lower))
+        d.lower = keep[-1].ctypes.data
+    if controls.get("smoother") is not None:
+        from .ldu import make_smooth_controls
+        d.smooth, _, _ = make_smooth_controls(controls)
+        d.haveSmooth = 1
+    else:
+        ctl, _ = make_controls(controls)
+        d.controls = ctl
     if reference is not None:
         get = (lambda k, dflt=0: reference.get(k, dflt)) if isinstance(reference, dict) else \
               (lambda k, dflt=0: getattr(reference, k, dflt))
@@ -121,9 +136,13 @@ def replay(path_or_dump, context=None, preconditioner=None):
         raise ValueError("replay() handles single-rank dumps; multi-rank dumps are replayed one rank per GPU "
                          "(tests/mgpu_worker.py shows the pattern)")
     ctl = dict(d.controls)
-    if preconditioner:
-        ctl["preconditioner"] = preconditioner
     s = d.system
     psi = d.psi0.copy()
+    if d.smooth is not None:
+        from .ldu import B200smoothSolver
+        perf = B200smoothSolver(d.fieldName, s.matrix, s.bou, None, s.interfaces, ctl, context=context).solve(psi, s.source)
+        return psi, perf, d
+    if preconditioner:
+        ctl["preconditioner"] = preconditioner
     perf = B200PCG(d.fieldName, s.matrix, s.bou, None, s.interfaces, ctl, context=context).solve(psi, s.source)
     return psi, perf, d

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2   /* 2: b200_dump grew lower / haveSmooth / smooth at its end; smoothSolver entry points */
 
 /* error codes */
 enum {
@@ -316,6 +316,11 @@ typedef struct b200_dump {
     const char*    solverName;      /* e.g. "DICPCG"                                           */
     int32_t        solveIndex;      /* running number of the solve on this rank                */
     double         time;            /* runTime.value()                                         */
+    /* ABI version 2: asymmetric systems and smoothSolver solves */
+    const double*  lower;           /* [nFaces] A[u][l], or NULL: symmetric (lower aliases upper) */
+    int32_t        haveSmooth;      /* written by B200smoothSolver: `smooth` holds the controls, `controls` is unused */
+    int32_t        padSmooth;
+    b200_smooth_controls smooth;
 } b200_dump;
 
 typedef struct b200_dump_file b200_dump_file;

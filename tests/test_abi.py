@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.PCG_SO)
     for name in header_functions():
         assert hasattr(L, name), name
-    assert L.b200_abi_version() == 1
+    assert L.b200_abi_version() == 2
 
 
 def test_struct_layouts():

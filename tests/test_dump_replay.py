@@ -51,6 +51,60 @@ def test_fixture_singlebox():
     assert perf.nIterations == d.reference["nIterations"] and np.array_equal(psi, d.psi)
 
 
+def test_fixture_U_transport_asymmetric():
+    """an asymmetric system with the reference's U controls (smoothSolver + symGaussSeidel, tol 1e-6,
+    maxIter 10; fvSolution:48-55) as a committed dump: `lower` travels, the controls are smoothSolver's, and the
+    oracle reproduces the stored line on the bytes in the file."""
+    d = replay.read_dump(os.path.join(GOLD, "steckler_U_transport.b200sys"))
+    s = d.system
+    assert d.fieldName == "Ux" and s.addr.nCells == 9000 and s.lower is not None and d.header["symmetric"] is False
+    assert np.abs(s.lower - s.upper).max() > 0
+    assert d.smooth == {"smoother": "symGaussSeidel", "tolerance": 1e-6, "relTol": 0.0, "maxIter": 10, "minIter": 0,
+                        "nSweeps": 1, "B200": {"sweepMode": "exact"}}
+    psi = d.psi0.copy()
+    perf = orc.smooth_solve(s, psi, smoother="symGaussSeidel", tolerance=1e-6, relTol=0.0, maxIter=10)
+    assert perf.nIterations == d.reference["nIterations"] == 7 and perf.finalResidual == d.reference["finalResidual"]
+    assert np.array_equal(psi, d.psi)
+    # the symmetric fixtures are untouched by the format extension
+    assert replay.read_dump(os.path.join(GOLD, "steckler_G_p1.b200sys")).smooth is None
+
+
+def test_roundtrip_asymmetric_smooth_controls(tmp_path):
+    """write (C ABI) -> read (numpy, C ABI) of an asymmetric system with smoothSolver controls"""
+    from firefoam_dev_b200 import cases
+    t = cases.transport_system(mg.hex_block(6, 5, 4), seed=3)
+    L = _lib.load_pcg()
+    for sm, mode, nS in (("GaussSeidel", "multicolour", 2), ("symGaussSeidel", "exact", 1)):
+        p = tmp_path / f"U_{sm}.b200sys"
+        ctl = {"smoother": sm, "tolerance": 1e-7, "relTol": 0.1, "maxIter": 12, "minIter": 1, "nSweeps": nS,
+               "B200": {"sweepMode": mode}}
+        replay.write_dump(p, t, np.zeros(t.addr.nCells), ctl, fieldName="Uy",
+                          reference={"initialResidual": 1.0, "finalResidual": 1e-8, "nIterations": 4}, solverName="smoothSolver")
+        d = replay.read_dump(p)
+        assert d.smooth == ctl and d.controls == ctl
+        assert np.array_equal(d.system.lower, t.lower) and np.array_equal(d.system.upper, t.upper)
+        assert all(int(x["offset"]) % 64 == 0 for x in d.header["arrays"])
+        h = C.c_void_p()
+        assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0, L.b200_dump_last_error()
+        dd = L.b200_dump_get(h).contents
+        assert dd.haveSmooth == 1 and dd.smooth.nSweeps == nS and dd.smooth.maxIter == 12 and dd.smooth.minIter == 1
+        assert dd.smooth.smoother == {"GaussSeidel": 0, "symGaussSeidel": 1}[sm]
+        assert dd.smooth.sweepMode == {"multicolour": 0, "exact": 1}[mode]
+        assert dd.smooth.tolerance == 1e-7 and dd.smooth.relTol == 0.1
+        got = np.ctypeslib.as_array(C.cast(dd.lower, C.POINTER(C.c_double)), shape=(t.addr.nFaces,))
+        assert np.array_equal(got, t.lower)
+        L.b200_dump_free(h)
+    # a symmetric PCG dump has neither
+    p = tmp_path / "sym.b200sys"
+    b = mg.hex_block(4, 4, 4)
+    replay.write_dump(p, b, np.zeros(b.addr.nCells), {"preconditioner": "diagonal"})
+    h = C.c_void_p()
+    assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0
+    dd = L.b200_dump_get(h).contents
+    assert dd.haveSmooth == 0 and not dd.lower
+    L.b200_dump_free(h)
+
+
 def test_roundtrip_multirank_with_interfaces(tmp_path):
     """write (C ABI) -> read (numpy) and read (C ABI): every array bit-identical, including processor
     interfaces; arrays 64-byte aligned; empty patches and ragged sizes survive."""
@@ -127,6 +181,36 @@ def test_replay_fixtures_on_gpu(ctx):
         assert abs(perf.finalResidual - d.reference["finalResidual"]) <= 1e-9 * d.reference["finalResidual"]
         assert np.abs(psi - d.psi).max() <= 1e-12 * np.abs(d.psi).max()
     assert "DICB200PCG" in str(replay.replay(os.path.join(GOLD, "steckler_ph_rgh_c1.b200sys"), context=ctx)[1])
+
+
+@pytest.mark.gpu
+def test_replay_asymmetric_fixture_on_gpu():
+    """the U-shaped fixture through B200smoothSolver: sweepMode exact (as dumped) reproduces the stored line and
+    solution bit for bit; the default multicolour sweeps converge under the same controls"""
+    from firefoam_dev_b200 import Context
+    c = Context(device=0)
+    try:
+        path = os.path.join(GOLD, "steckler_U_transport.b200sys")
+        psi, perf, d = replay.replay(path, context=c)
+        assert perf.nIterations == d.reference["nIterations"] == 7 and np.array_equal(psi, d.psi)
+        assert perf.finalResidual == pytest.approx(d.reference["finalResidual"], rel=1e-9)
+        assert str(perf).startswith("B200smoothSolver:  Solving for Ux, Initial residual = 1, ")
+        d.controls["B200"] = {"sweepMode": "multicolour"}
+        psi2, perf2, _ = replay.replay(d, context=c)
+        assert perf2.finalResidual < 1e-5 and np.abs(psi2 - d.psi).max() <= 1e-4 * np.abs(d.psi).max()
+    finally:
+        c.close()
+
+
+@pytest.mark.gpu
+def test_native_replay_tool_asymmetric():
+    exe = os.path.join(ROOT, "firefoam-dev_b200", "b200replay")
+    if not os.path.exists(exe):
+        pytest.skip("b200replay not built")
+    r = subprocess.run([exe, os.path.join(GOLD, "steckler_U_transport.b200sys")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "B200smoothSolver:  Solving for Ux, Initial residual = 1, " in r.stdout and "asymmetric" in r.stdout
+    assert r.stdout.count("No Iterations 7") == 2 and "MISMATCH" not in r.stdout
 
 
 @pytest.mark.gpu
