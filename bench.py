@@ -541,35 +541,52 @@ def mgpu_parity(env):
                                 "converged": bool(perf.converged)}
         # smoothSolver + symGaussSeidel on an asymmetric transport matrix with the same (irregular, RCB)
         # processor patches: level-scheduled sweeps against the N-rank oracle (oracle/smooth_oracle.c) -- identical
-        # sweep count, bit-identical psi; reported under its own key with its own verdict
+        # sweep count, bit-identical psi; reported under its own key with its own verdict.  Every rank agrees on the
+        # outcome of each call before the next collective, so a rank-local failure is reported, never waited for.
+        from firefoam_dev_b200 import cases
+        pt = cases.transport_system(poly, seed=22, kappa=0.3)
+        tsubs = mg.decompose(pt, mg.partition_rcb(poly.xyz, n), n)
+        s = tsubs[rank]
+        sm, failed = {}, None
+
+        def agreed(ok, why):
+            flag = env.torch.tensor([1 if ok else 0], device=env.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return None if int(flag.item()) == 1 else (why or "another rank failed")
         try:
-            from firefoam_dev_b200 import cases
-            pt = cases.transport_system(poly, seed=22, kappa=0.3)
-            tsubs = mg.decompose(pt, mg.partition_rcb(poly.xyz, n), n)
-            s = tsubs[rank]
             ctx.set_addressing(s.addr)
-            sm = {}
-            for key, ctl in (("exact", dict(smoother="symGaussSeidel", tolerance=1e-8, maxIter=500, B200={"sweepMode": "exact"})),
-                             ("multicolour", dict(smoother="symGaussSeidel", tolerance=1e-11, maxIter=3000))):
-                psi = np.zeros(s.addr.nCells)
+            failed = agreed(True, None)
+        except pkg.B200Error as e:
+            failed = agreed(False, str(e))
+        for key, ctl in (("exact", dict(smoother="symGaussSeidel", tolerance=1e-8, maxIter=500, B200={"sweepMode": "exact"})),
+                         ("multicolour", dict(smoother="symGaussSeidel", tolerance=1e-11, maxIter=3000))):
+            if failed:
+                break
+            psi = np.zeros(s.addr.nCells)
+            try:
                 perf = pkg.B200smoothSolver("U", s.matrix, s.bou, None, s.interfaces, ctl, context=ctx).solve(psi, s.source)
-                allpsi = [None] * n
-                dist.all_gather_object(allpsi, psi)
-                if rank == 0:
-                    ref = [np.zeros(x_.addr.nCells) for x_ in tsubs]
-                    o = dict(smoother="symGaussSeidel", tolerance=1e-8, maxIter=500) if key == "exact" else \
-                        dict(smoother="symGaussSeidel", tolerance=1e-13, maxIter=5000)
-                    pr = orc.smooth_solve(tsubs, ref, **o)
-                    err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
-                    sm[key] = {"sweeps": perf.nIterations, "oracle_sweeps": pr.nIterations, "relerr": float(err),
-                               "bit_identical": bool(all(np.array_equal(a, b) for a, b in zip(allpsi, ref))),
-                               "converged": bool(perf.converged)}
+                failed = agreed(True, None)
+            except pkg.B200Error as e:
+                failed = agreed(False, str(e))
+            if failed:
+                break
+            allpsi = [None] * n
+            dist.all_gather_object(allpsi, psi)
             if rank == 0:
-                sm["pass"] = bool(sm["exact"]["bit_identical"] and sm["exact"]["sweeps"] == sm["exact"]["oracle_sweeps"]
-                                  and sm["multicolour"]["converged"] and sm["multicolour"]["relerr"] < 1e-8)
-                out["smooth_solver"] = sm
-        except pkg.B200Error as e:          # (the same error on every rank: the entry points validate before any collective)
-            out["smooth_solver"] = {"pass": False, "error": str(e)}
+                ref = [np.zeros(x_.addr.nCells) for x_ in tsubs]
+                o = dict(smoother="symGaussSeidel", tolerance=1e-8, maxIter=500) if key == "exact" else \
+                    dict(smoother="symGaussSeidel", tolerance=1e-13, maxIter=5000)
+                pr = orc.smooth_solve(tsubs, ref, **o)
+                err = max(np.abs(a - b).max() for a, b in zip(allpsi, ref)) / max(np.abs(b).max() for b in ref)
+                sm[key] = {"sweeps": perf.nIterations, "oracle_sweeps": pr.nIterations, "relerr": float(err),
+                           "bit_identical": bool(all(np.array_equal(a, b) for a, b in zip(allpsi, ref))),
+                           "converged": bool(perf.converged)}
+        if failed:
+            out["smooth_solver"] = {"pass": False, "error": failed}
+        elif rank == 0:
+            sm["pass"] = bool(sm["exact"]["bit_identical"] and sm["exact"]["sweeps"] == sm["exact"]["oracle_sweeps"]
+                              and sm["multicolour"]["converged"] and sm["multicolour"]["relerr"] < 1e-8)
+            out["smooth_solver"] = sm
         if rank == 0:
             strict = [k for k in out if k.endswith("_diagonal") or k.endswith("_DIC_exact")]
             out["iters_equal"] = bool(all(out[k]["iters"] == out[k]["oracle_iters"] for k in strict))

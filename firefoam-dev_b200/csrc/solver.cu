@@ -1602,7 +1602,15 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     // With processor patches neither shortcut holds: the halo values are refreshed at the start of every sweep (group
     // 0's interface rows DO change), and the last group's in-kernel residual would use the halo of the sweep's start.
     const bool fusedRes = !fixed && !multi && ctl->sweepMode == B200_SWEEP_MULTICOLOUR;
-    const bool back = sym && C >= 2;                 // the sweep has a reverse half that ends on group 0
+    // TWO colours, symGaussSeidel, multicolour order: the reverse half of a symmetric sweep degenerates -- it
+    // recomputes one colour and updates the other, so a red-black "symmetric" sweep IS one red-black Gauss-Seidel
+    // sweep, half as strong as upstream's forward + reverse pass.  It is executed as TWO red-black sweeps instead:
+    // the same number of row updates as a symmetric sweep and about its strength (22 vs upstream's 24 sweeps on the
+    // 16 M-cell test system), so that sweep counts and the maxIter cap keep their meaning.  The processor-patch
+    // contributions stay refreshed once per COUNTED sweep, as upstream.
+    const bool rb2 = sym && C == 2 && ctl->sweepMode == B200_SWEEP_MULTICOLOUR;
+    const int inner = rb2 ? 2 : 1;                   // executed sweeps per counted sweep
+    const bool back = sym && C >= 2 && !rb2;         // the sweep has a reverse half that ends on group 0
     const int lastGroup = back ? 0 : C - 1;
     // TWO colours (hex meshes): after the first sweep an iteration is [group F, group L] with F = the group the sweep
     // updates first; F's pass of the NEXT iteration delivers F's residual of this one for free (k_gs_rows RES == 2),
@@ -1613,10 +1621,10 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     double* const arr[2] = {ctx->psi, ctx->w};
     int curF = 0;                                    // which array holds group F's current values
     bool firstSweep = true;
-    auto sweep = [&](bool res) -> int {
+    auto sweep = [&](bool res, bool refresh = true) -> int {
         const int k0 = (back && !firstSweep && !multi) ? 1 : 0;
         firstSweep = false;
-        RET(gs_sweep_halo(ctx, P, gh));
+        if (refresh) RET(gs_sweep_halo(ctx, P, gh));
         for (int k = k0; k < C; ++k) RET(launch_gs_rows(ctx, P, k, (res && !back && k == C - 1) ? 1 : 0, gh));
         if (back) for (int k = C - 2; k >= 0; --k) RET(launch_gs_rows(ctx, P, k, (res && k == 0) ? 1 : 0, gh));
         return B200_OK;
@@ -1644,7 +1652,7 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
         return B200_OK;
     };
     if (fixed) {
-        for (int i = 0; i < nS; ++i) RET(sweep(false));
+        for (int i = 0; i < nS * inner; ++i) RET(sweep(false, i % inner == 0));
     } else {
         // rows whose residual is evaluated explicitly: all of them, or all but the group the iteration updated last
         int q0 = 0, q1 = N;
@@ -1664,10 +1672,11 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
             const int n = (int)std::min<int64_t>(chunk, cap - enq);
             for (int i = 0; i < n; ++i) {
                 ctx->profIter = (int)(enq + i + 1) * nS;
+                const int nE = nS * inner;           // executed sweeps of this loop body
                 if (lagged) {
-                    for (int sw = 0; sw < nS; ++sw) RET(sweep2(enq + i, sw == 0 && enq + i > 0, sw == nS - 1));
+                    for (int sw = 0; sw < nE; ++sw) RET(sweep2(enq + i, sw == 0 && enq + i > 0, sw == nE - 1));
                 } else {
-                    for (int sw = 0; sw < nS; ++sw) RET(sweep(fusedRes && sw == nS - 1));
+                    for (int sw = 0; sw < nE; ++sw) RET(sweep(fusedRes && sw == nE - 1, sw % inner == 0));
                     RET(launch_gs_resid(ctx, P, q0, q1, gh));
                 }
             }

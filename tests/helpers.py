@@ -570,7 +570,10 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
     val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
     d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
     C = pv.nColours
-    back = smoother == "symGaussSeidel" and C >= 2
+    # two colours, symGaussSeidel, multicolour order: a counted sweep is executed as two red-black sweeps (solver.cu rb2)
+    rb2 = smoother == "symGaussSeidel" and C == 2 and mode == "multicolour"
+    inner = 2 if rb2 else 1
+    back = smoother == "symGaussSeidel" and C >= 2 and not rb2
     fused = mode == "multicolour" and nSweeps > 0
     state = {"first": True}
 
@@ -586,7 +589,7 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
         return tot
 
     if nSweeps < 0:
-        for _ in range(-nSweeps):
+        for _ in range(-nSweeps * inner):
             sweep(False)
         return pv.to_natural(x), -nSweeps, 0.0, 0.0
     wA = pv.spmv(d, val, x)
@@ -608,8 +611,8 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
     if (minIter > 0 or not conv()) and not lagged:
         while True:
             tot = 0.0
-            for sw in range(nSweeps):
-                tot += sweep(fused and sw == nSweeps - 1)
+            for sw in range(nSweeps * inner):
+                tot += sweep(fused and sw == nSweeps * inner - 1)
             final = (tot + pv.gs_residual(d, val, b, x, q0, q1)) / nf
             n += nSweeps
             if not ((n < maxIter and not conv()) or n < minIter):
@@ -634,8 +637,8 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
         body = 0
         while True:
             tot = 0.0
-            for sw in range(nSweeps):
-                res = sw == nSweeps - 1
+            for sw in range(nSweeps * inner):
+                res = sw == nSweeps * inner - 1
                 if state["first"]:
                     tot += sweep(res)
                 else:

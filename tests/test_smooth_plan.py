@@ -65,10 +65,12 @@ def test_multicolour_sweeps_converge_to_the_same_solution(name, s):
 @pytest.mark.parametrize("smoother", ["GaussSeidel", "symGaussSeidel"])
 def test_skipped_groups_are_bit_neutral(smoother):
     """the sweeps skip two recomputations (last group of the forward half at the start of the reverse half, group 0
-    at the start of the next forward half): same bits as visiting every group every time"""
-    _, s = list(systems())[1]
-    for ordering, mode in ((LEVELS, "exact"), (MULTICOLOUR, "multicolour")):
+    at the start of the next forward half): same bits as visiting every group every time.  (Level plans of the hex
+    system; the multicolour plan of the polyhedral one: more than two colours.)"""
+    sysd = dict(systems())
+    for ordering, mode, s in ((LEVELS, "exact", sysd["hex"]), (MULTICOLOUR, "multicolour", sysd["poly"])):
         pv = helpers.PlanView(ordering, s.addr)
+        assert pv.nColours > 2
         N = s.addr.nCells
         low = s.upper if s.lower is None else s.lower
         val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
@@ -81,6 +83,26 @@ def test_skipped_groups_are_bit_neutral(smoother):
                     pv.gs_rows(k, d, val, b, x)
         got, _, _, _ = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother=smoother, nSweeps=-3, mode=mode)
         assert np.array_equal(got, pv.to_natural(x))
+
+
+def test_two_colour_symmetric_sweep_is_two_red_black_sweeps():
+    """On a two-colour plan the reverse half of a symmetric sweep only recomputes one colour: a red-black symGaussSeidel
+    sweep would be ONE red-black Gauss-Seidel sweep, half as strong as upstream's forward + reverse pass.  The
+    multicolour mode executes it as two red-black sweeps: same row updates as a symmetric sweep, and a sweep count
+    close to upstream's natural-order symGaussSeidel instead of twice it."""
+    s = dict(systems())["hex"]
+    pv = helpers.PlanView(MULTICOLOUR, s.addr)
+    assert pv.nColours == 2
+    N = s.addr.nCells
+    a = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother="symGaussSeidel", nSweeps=-3)
+    b = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother="GaussSeidel", nSweeps=-6)
+    assert np.array_equal(a[0], b[0])
+    psi = np.zeros(N)
+    up = orc.smooth_solve(s, psi, smoother="symGaussSeidel", tolerance=1e-9, maxIter=500)       # upstream's order
+    mc = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother="symGaussSeidel", tol=1e-9, maxIter=500)
+    gs = helpers.smooth_solve_emulated(pv, s, np.zeros(N), smoother="GaussSeidel", tol=1e-9, maxIter=500)
+    assert abs(mc[1] - up.nIterations) <= max(2, up.nIterations // 4), (mc[1], up.nIterations)
+    assert gs[1] >= 2 * mc[1] - 2
 
 
 @pytest.mark.parametrize("smoother", ["GaussSeidel", "symGaussSeidel"])
