@@ -31,6 +31,41 @@ def test_struct_layouts():
     assert C.sizeof(_lib.Controls) == 32
     assert C.sizeof(_lib.Perf) == 72
     assert C.sizeof(_lib.Iface) == 24
+    assert C.sizeof(_lib.SmoothControls) == 40
+
+
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of include/b200pcg.h as a C compiler lays it out == the ctypes mirrors the
+    tests, the bench and replay.py use (b200_dump grew three fields in ABI version 2)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    fields = {"b200_controls": (_lib.Controls, ["tolerance", "relTol", "maxIter", "minIter", "precond", "reserved"]),
+              "b200_smooth_controls": (_lib.SmoothControls, ["tolerance", "relTol", "maxIter", "minIter", "nSweeps", "smoother",
+                                                             "sweepMode", "reserved"]),
+              "b200_perf": (_lib.Perf, ["initialResidual", "finalResidual", "normFactor", "nIterations", "converged", "singular",
+                                        "nColours", "solveMs", "setupMs", "h2dMs", "d2hMs"]),
+              "b200_iface": (_lib.Iface, ["nbrRank", "nFaces", "faceCells", "tag"]),
+              "b200_prgh_terms": (_lib.PrghTerms, [f[0] for f in _lib.PrghTerms._fields_]),
+              "b200_dump": (_lib.Dump, [f[0] for f in _lib.Dump._fields_])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200pcg.h"', "int main(void) {"]
+    for st, (_, names) in fields.items():
+        lines.append(f'    printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            lines.append(f'    printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    lines += ["    return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for st, (cls, names) in fields.items():
+        assert int(out[st]) == C.sizeof(cls), st
+        for n in names:
+            assert int(out[f"{st}.{n}"]) == getattr(cls, n).offset, f"{st}.{n}"
 
 
 @pytest.mark.skipif(has_gpu(), reason="CPU-only behaviour")

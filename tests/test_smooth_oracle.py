@@ -4,9 +4,6 @@ SURVEY.md 8f-4) against an INDEPENDENT formulation: dense matrices and scipy tri
 The reference pins these solves by residual lines only (cases/steckler/original/linux64/log.fireFoam:172-178 ...,
 261 lines) and their matrices need the whole solver, so the oracle is PARITY UNPINNED for this algorithm; the one
 line that needs nothing else (zero field, zero source -> 0, 0, No Iterations 0; log.fireFoam:176) is checked here."""
-import json
-import os
-
 import numpy as np
 import pytest
 from scipy.linalg import solve_triangular
