@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200_abi_version", "b200_device_count", "b200_set_addressing", "b200_assemble_laplacian",
     "b200_assemble_laplacian_device", "b200_set_boundary_faces", "b200_assemble_p_rgh",
     "b200_assemble_p_rgh_device", "b200_solve", "b200_solve_device", "b200_amul", "b200_flux",
-    "b200_smooth_solve", "b200_smooth_solve_device", "b200_amul_asym",
+    "b200_smooth_solve", "b200_smooth_solve_device", "b200_amul_asym", "b200_bicg_solve", "b200_bicg_solve_device",
     "b200_host_alloc", "b200_host_free", "b200_launch_count", "b200_debug_force_iterations",
     "b200_profile_enable", "b200_profile_json", "b200_describe",
     "b200_dump_write", "b200_dump_read", "b200_dump_get", "b200_dump_header_json", "b200_dump_free",
@@ -49,6 +49,7 @@ class Controls(C.Structure):
                 ("minIter", C.c_int32), ("precond", C.c_int32), ("reserved", C.c_int32)]
 
 
+BICG_PRECOND = {"none": 0, "diagonal": 1, "DILU": 2, "DILU-exact": 3}
 SMOOTHER = {"GaussSeidel": 0, "symGaussSeidel": 1}
 SWEEP_MODE = {"multicolour": 0, "exact": 1}
 
@@ -135,6 +136,8 @@ def load_pcg():
     L.b200_smooth_solve.argtypes = [vp, f64p, f64p, f64p, vp, f64p, f64p, C.POINTER(SmoothControls), C.POINTER(Perf)]
     L.b200_smooth_solve_device.argtypes = L.b200_smooth_solve.argtypes
     L.b200_amul_asym.argtypes = [vp, f64p, f64p, f64p, vp, f64p, f64p]
+    L.b200_bicg_solve.argtypes = [vp, f64p, f64p, f64p, vp, vp, f64p, f64p, C.POINTER(Controls), C.POINTER(Perf)]
+    L.b200_bicg_solve_device.argtypes = L.b200_bicg_solve.argtypes
     L.b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.b200_host_free.argtypes = [vp]
     L.b200_host_free.restype = None

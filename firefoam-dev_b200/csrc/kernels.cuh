@@ -1872,10 +1872,12 @@ k_eis_final(int N, double* __restrict__ psi, const double* __restrict__ xa, cons
 
 // matrix value fill of the full-row ELL for lower != upper: the entry of row r on face f carries upper[f] when
 // r's cell owns the face (A[l][u] = upper), lower[f] when it is the face's neighbour (A[u][l] = lower)
+// valT != nullptr (PBiCG): also the entries of the TRANSPOSED matrix, i.e. the other coefficient of the same face
 __global__ void __launch_bounds__(kBlock)
 k_fill_values_asym(int N, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen,
                    const int* __restrict__ faceOf, const int* __restrict__ perm, const int* __restrict__ lowerAddr,
-                   const double* __restrict__ upper, const double* __restrict__ lower, double* __restrict__ val) {
+                   const double* __restrict__ upper, const double* __restrict__ lower, double* __restrict__ val,
+                   double* __restrict__ valT) {
     for (int r = blockIdx.x * kBlock + threadIdx.x; r < N; r += gridDim.x * kBlock) {
         const int c = perm ? perm[r] : r;
         const int64_t base = sliceBase[r >> 5] + (r & 31);
@@ -1883,7 +1885,10 @@ k_fill_values_asym(int N, const int64_t* __restrict__ sliceBase, const uint32_t*
         for (int j = 0; j < n; ++j) {
             const int64_t e = base + 32 * (int64_t)j;
             const int f = faceOf[e];
-            val[e] = (__ldg(&lowerAddr[f]) == c) ? __ldg(&upper[f]) : __ldg(&lower[f]);
+            const bool owns = (__ldg(&lowerAddr[f]) == c);
+            const double up = __ldg(&upper[f]), lo = __ldg(&lower[f]);
+            val[e] = owns ? up : lo;
+            if (valT) valT[e] = owns ? lo : up;
         }
     }
 }
@@ -2010,6 +2015,142 @@ k_gs_resid(int r0, int r1, const int64_t* __restrict__ sliceBase, const uint32_t
         r = rn; len = lenN; sb = sbN; bv = bvN; dv = dvN; bi = biN;
     }
 #undef B200_GSR_LOAD
+    reduce_finish<1>(s, R);
+}
+
+// ---- PBiCG + DILU on asymmetric lduMatrices ------------------------------------------------
+// Replaces PBiCG::solve and DILUPreconditioner::calcReciprocalD / precondition / preconditionT (OF-dev PBiCG.C,
+// DILUPreconditioner.C), which the reference's cases select for their transport equations
+// (cases/wallFireSpread2D/system/fvSolution:66-73; the 2.4.x golden logs of steckler: 207 `DILUPBiCG:` lines).
+// DILU's face loops -- the forward one runs in losort order upstream -- are, row by row,
+//     rD_u  = diag_u - sum_{lower nbrs l} upper_f lower_f / rD_l                         (then reciprocal)
+//     w_u   = rD_u r_u - sum_{lower nbrs} (rD_u lower_f) w_l        forward, faces ascending within the row
+//     w_l  -= (rD_l upper_f) w_u                                      backward, faces descending within the row
+// i.e. the DIC sweeps with the row's own coefficient of each face, which the full-row ELL of an asymmetric matrix
+// already holds (k_fill_values_asym); preconditionT is the same pair of sweeps over the TRANSPOSED values (valT: the
+// other coefficient of each face), and Tmul is Amul over valT.  Rows grouped by dependency level (Ordering::Levels)
+// reproduce upstream bit for bit (tests/test_bicg_plan.py); grouped by colour they are the DILU-class stand-in.
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_dilu_calc_rd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
+               const double* __restrict__ val, const double* __restrict__ valT, const double* __restrict__ diag,
+               double* __restrict__ rD) {
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        double d = diag[r];
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            // (valT, val) of a lower entry = (upper_f, lower_f); rD of an earlier group: plain (coherent) load
+            d = __dadd_rn(d, -__ddiv_rn(__dmul_rn(valT[e], val[e]), rD[ell_col<C16>(E, e)]));
+        }
+        rD[r] = d;
+    }
+}
+
+// forward / backward triangular sweep over one group: the DIC-class sweeps without their dot products
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_tri_fwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
+          const double* __restrict__ val, const double* __restrict__ rD, const double* __restrict__ rIn, double* w,
+          const Scalars* S) {
+    if (S->done) return;
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const int nLower = (int)(rowLen[r] & 0xffffu);
+        const double d = rD[r];
+        double acc = __dmul_rn(d, rIn[r]);
+        for (int j = 0; j < nLower; ++j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            acc = __dadd_rn(acc, -__dmul_rn(__dmul_rn(d, val[e]), w[ell_col<C16>(E, e)]));
+        }
+        w[r] = acc;
+    }
+}
+template <bool C16>
+__global__ void __launch_bounds__(kBlock)
+k_tri_bwd(ColourRows cr, const int64_t* __restrict__ sliceBase, const uint32_t* __restrict__ rowLen, EllCols E,
+          const double* __restrict__ val, const double* __restrict__ rD, double* w, const Scalars* S) {
+    if (S->done) return;
+    B200_FOR_COLOUR_ROWS(cr, r) {
+        const int64_t base = sliceBase[r >> 5] + (r & 31);
+        const uint32_t len = rowLen[r];
+        const int nLower = (int)(len & 0xffffu), nTotal = (int)(len >> 16);
+        const double d = rD[r];
+        double acc = w[r];
+        for (int j = nTotal - 1; j >= nLower; --j) {
+            const int64_t e = base + 32 * (int64_t)j;
+            acc = __dadd_rn(acc, -__dmul_rn(__dmul_rn(d, val[e]), w[ell_col<C16>(E, e)]));
+        }
+        w[r] = acc;
+    }
+}
+
+// gSumProd(a, b) -> step (wArT = (wA, rT): STEP_WARA; wApT = (wA, pT): STEP_WAPA)
+__global__ void __launch_bounds__(kBlock)
+k_dot2(int N, const double* __restrict__ a, const double* __restrict__ b, Reduce R) {
+    if (R.S->done) return;
+    double s[1] = {0.0};
+    B200_VEC_LOOP(N,
+        { const double2 x = reinterpret_cast<const double2*>(a)[i];
+          const double2 y = reinterpret_cast<const double2*>(b)[i];
+          s[0] = __dadd_rn(s[0], __dmul_rn(x.x, y.x));
+          s[0] = __dadd_rn(s[0], __dmul_rn(x.y, y.y)); },
+        { s[0] = __dadd_rn(s[0], __dmul_rn(a[i], b[i])); })
+    reduce_finish<1>(s, R);
+}
+
+// diagonalPreconditioner on both residuals: wA = rD rA, wT = rD rT
+__global__ void __launch_bounds__(kBlock)
+k_bicg_diag(int N, const double* __restrict__ rD, const double* __restrict__ rA, const double* __restrict__ rT,
+            double* __restrict__ wA, double* __restrict__ wT, const Scalars* S) {
+    if (S->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double d = rD[i];
+        wA[i] = __dmul_rn(d, rA[i]);
+        wT[i] = __dmul_rn(d, rT[i]);
+    }
+}
+
+// rT = source - wT (the transpose residual of the initial guess)
+__global__ void __launch_bounds__(kBlock)
+k_sub(int N, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        out[i] = __dadd_rn(a[i], -b[i]);
+}
+
+// search directions: pA = zA + beta pA, pT = zT + beta pT (first iteration: pA = zA, pT = zT)
+__global__ void __launch_bounds__(kBlock)
+k_bicg_p(int N, double* __restrict__ pA, const double* __restrict__ zA, double* __restrict__ pT,
+         const double* __restrict__ zT, const Scalars* S) {
+    if (S->done) return;
+    const bool first = (S->nIter == 0);
+    const double beta = S->beta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double a = zA[i], t = zT[i];
+        if (!first) {
+            a = __dadd_rn(a, __dmul_rn(beta, pA[i]));
+            t = __dadd_rn(t, __dmul_rn(beta, pT[i]));
+        }
+        pA[i] = a;
+        pT[i] = t;
+    }
+}
+
+// psi += alpha pA; rA -= alpha wA; rT -= alpha wT; gSumMag(rA) -> STEP_RES
+__global__ void __launch_bounds__(kBlock)
+k_bicg_r(int N, double* __restrict__ psi, const double* __restrict__ pA, double* __restrict__ rA,
+         const double* __restrict__ wA, double* __restrict__ rT, const double* __restrict__ wT, Reduce R) {
+    if (R.S->done) return;
+    const double alpha = R.S->alpha;
+    double s[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        psi[i] = __dadd_rn(psi[i], __dmul_rn(alpha, pA[i]));
+        const double r = __dadd_rn(rA[i], -__dmul_rn(alpha, wA[i]));
+        rA[i] = r;
+        rT[i] = __dadd_rn(rT[i], -__dmul_rn(alpha, wT[i]));
+        s[0] = __dadd_rn(s[0], fabs(r));
+    }
     reduce_finish<1>(s, R);
 }
 

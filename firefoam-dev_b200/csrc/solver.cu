@@ -80,7 +80,7 @@ enum ProfClass : int {
     PC_FILL = 0, PC_GATHER, PC_SPMV, PC_SPMV_INIT, PC_IFACE, PC_PACK, PC_SUM, PC_NORM, PC_RECIP,
     PC_PRECOND_DOT, PC_DIC_RD, PC_DIC_FWD, PC_DIC_BWD, PC_ASM_FACE,
     PC_ASM_DIAG, PC_FLUX, PC_SCALAR, PC_KP, PC_KR, PC_PSI_FINAL, PC_SMALL, PC_ASM_PRGH,
-    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_EIS_ROWS, PC_GS_ROWS, PC_GS_RESID, PC_COUNT
+    PC_EIS_SETUP, PC_EIS_P, PC_EIS_BWD, PC_EIS_FWD, PC_EIS_R, PC_EIS_RES, PC_EIS_ROWS, PC_GS_ROWS, PC_GS_RESID, PC_BICG_TRI, PC_BICG_VEC, PC_BICG_DOT, PC_COUNT
 };
 const char* kProfNames[PC_COUNT] = {
     "fill_values", "gather_scatter", "spmv_dot", "spmv_init", "iface_fix", "halo_pack", "sum",
@@ -88,7 +88,7 @@ const char* kProfNames[PC_COUNT] = {
     "dic_bwd", "asm_face_coeff", "asm_neg_sum_diag", "flux", "scalar_step", "p_psi_update",
     "r_update_dots", "psi_final", "pcg_small_whole_solve", "asm_p_rgh_cells",
     "eis_setup", "eis_p_psi_update", "eis_bwd", "eis_fwd_dot", "eis_r_update_rho", "eis_true_residual",
-    "eis_iface_rows", "gs_sweep_rows", "gs_residual"};
+    "eis_iface_rows", "gs_sweep_rows", "gs_residual", "bicg_dilu_sweeps", "bicg_vector_updates", "bicg_dots"};
 
 struct DevPlan {
     bool built = false;
@@ -98,6 +98,7 @@ struct DevPlan {
     int* col = nullptr;
     int* faceOf = nullptr;
     double* val = nullptr;
+    double* valT = nullptr;       // PBiCG: entries of the TRANSPOSED matrix (the other coefficient of each face), on first use
     int* perm = nullptr;
     int *slotRow = nullptr, *bRow = nullptr, *bStart = nullptr, *bSlot = nullptr;
     // 16-bit column offsets (plan.hpp colBase / col16) for the ELL-bound kernels
@@ -379,7 +380,7 @@ void free_plan(DevPlan& P) {
         P.iterGraphFailed[m] = false;
     }
     dev_free(P.sliceBase); dev_free(P.rowLen); dev_free(P.col); dev_free(P.faceOf);
-    dev_free(P.val); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
+    dev_free(P.val); dev_free(P.valT); dev_free(P.perm); dev_free(P.slotRow); dev_free(P.bRow);
     dev_free(P.bStart); dev_free(P.bSlot); dev_free(P.colourStart); dev_free(P.segStart);
     dev_free(P.col16); dev_free(P.colBase); P.c16 = false;
     dev_free(P.sUCol); dev_free(P.sUFace);
@@ -1409,11 +1410,11 @@ int solve_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, con
 // ---- smoothSolver (kernels.cuh "smoothSolver") ---------------------------------------------
 // matrix of one smoothSolver / asymmetric Amul call -> the plan's full-row ELL (both triangles), vectors -> plan order
 int load_system_asym(b200_ctx* ctx, DevPlan& P, const double* dn_diag, const double* dn_upper, const double* dn_lower,
-                     const double* dn_src, const double* dn_psi) {
+                     const double* dn_src, const double* dn_psi, bool transposed = false) {
     const int N = ctx->N;
-    if (dn_lower && dn_lower != dn_upper)
+    if (transposed || (dn_lower && dn_lower != dn_upper))
         LAUNCH(PC_FILL, k_fill_values_asym, grid_for(ctx, N), N, P.sliceBase, P.rowLen, P.faceOf, P.perm, ctx->d_l,
-               dn_upper, dn_lower, P.val);
+               dn_upper, dn_lower ? dn_lower : dn_upper, P.val, transposed ? P.valT : (double*)nullptr);
     else
         LAUNCH(PC_FILL, k_fill_values, grid_for(ctx, P.h.nEntries, 16), P.h.nEntries, P.faceOf, dn_upper, P.val);
     LAUNCH(PC_GATHER, k_gather, grid_for(ctx, N), N, P.perm, dn_diag, ctx->diag);
@@ -1706,6 +1707,145 @@ int smooth_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, co
     const int rc = finish_solve(ctx, P, perf);
     if (fixed && perf) perf->nIterations = nS;       // solverPerf.nIterations() -= nSweeps_ (no residuals: 0, 0)
     return rc;
+}
+
+// ---- PBiCG + DILU (kernels.cuh "PBiCG + DILU") ------------------------------------------------
+// y = A x (transposed: y = A^T x, i.e. lduMatrix::Tmul) on the plan's full-row ELL; INIT: also sumA
+template <bool INIT>
+int bicg_spmv(b200_ctx* ctx, DevPlan& P, bool transposed, const double* x, double* y, double* sA) {
+    if (transposed) std::swap(P.val, P.valT);
+    ctx->forceEll = true;
+    const int rc = spmv_full<INIT, false>(ctx, P, x, y, sA, STEP_NONE);
+    ctx->forceEll = false;
+    if (transposed) std::swap(P.val, P.valT);
+    return rc;
+}
+
+// w = M^-1 r with the (transposed) DILU factors: forward sweep over the groups ascending, backward descending
+int bicg_dilu_apply(b200_ctx* ctx, DevPlan& P, const double* val, const double* rIn, double* w) {
+    const int C = P.h.nColours;
+    const EllCols E{P.col, P.col16, P.colBase};
+    for (int k = 0; k < C; ++k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        if (P.c16) { auto kf = k_tri_fwd<true>; LAUNCH(PC_BICG_TRI, kf, g, cr, P.sliceBase, P.rowLen, E, val, ctx->rD, rIn, w, ctx->S); }
+        else { auto kf = k_tri_fwd<false>; LAUNCH(PC_BICG_TRI, kf, g, cr, P.sliceBase, P.rowLen, E, val, ctx->rD, rIn, w, ctx->S); }
+    }
+    for (int k = C - 2; k >= 0; --k) {
+        int g;
+        const ColourRows cr = colour_rows(ctx, P, k, &g);
+        if (P.c16) { auto kb = k_tri_bwd<true>; LAUNCH(PC_BICG_TRI, kb, g, cr, P.sliceBase, P.rowLen, E, val, ctx->rD, w, ctx->S); }
+        else { auto kb = k_tri_bwd<false>; LAUNCH(PC_BICG_TRI, kb, g, cr, P.sliceBase, P.rowLen, E, val, ctx->rD, w, ctx->S); }
+    }
+    return B200_OK;
+}
+
+// PBiCG::solve (OF-dev PBiCG.C); all pointers are device pointers in natural order.
+// Buffers: rA = r, pA = p, wA = w, rT = t, wT = dT, pT = eD (the Eisenstat form's vectors, allocated on first use).
+int bicg_core(b200_ctx* ctx, const double* dn_diag, const double* dn_upper, const double* dn_lower,
+              const double* dn_src, double* dn_psi, const b200_controls* ctl, b200_perf* perf) {
+    if (ctl->precond < B200_PRECOND_NONE || ctl->precond > B200_PRECOND_DILU_EXACT)
+        return fail(ctx, B200_EINVAL, "bad preconditioner code for PBiCG (0 none, 1 diagonal, 2 DILU-class, 3 DILU exact)");
+    if (ctl->reserved != 0) return fail(ctx, B200_EINVAL, "b200_controls.reserved must be 0");
+    if (ctx->nranks > 1)
+        return fail(ctx, B200_EUNSUPPORTED, "PBiCG with processor patches (nranks > 1) is not built yet");
+    if (ctx->tileRows > 0) return fail(ctx, B200_EUNSUPPORTED, "PBiCG does not take tiled plans (B200PCG_TILE)");
+    const bool dilu = ctl->precond >= B200_PRECOND_DILU_MC;
+    DevPlan* Pp = nullptr;
+    RET(ensure_plan(ctx, ctl->precond == B200_PRECOND_DILU_EXACT ? Ordering::Levels
+                         : dilu ? Ordering::MultiColour : Ordering::Natural, &Pp));
+    DevPlan& P = *Pp;
+    const int N = ctx->N;
+    const int gv = grid_for(ctx, (N + 1) / 2), gn = grid_for(ctx, N);
+    Scalars* S = ctx->S;
+    if (!P.valT) RET(dev_alloc(ctx, &P.valT, (size_t)P.h.nEntries));
+    RET(ensure_eis_buffers(ctx, P));
+    double *rA = ctx->r, *pA = ctx->p, *wA = ctx->w, *rT = ctx->t, *wT = ctx->dT, *pT = ctx->eD;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    RET(reset_scalars(ctx, ctl));
+    RET(load_system_asym(ctx, P, dn_diag, dn_upper, dn_lower, dn_src, dn_psi, true));
+    ctx->usedSmall = false;
+    // wA = A psi (+ sumA -> pA), wT = A^T psi; normFactor, rA, initial residual (STEP_NORM); rT = source - wT
+    RET(bicg_spmv<true>(ctx, P, false, ctx->psi, wA, pA));
+    RET(bicg_spmv<false>(ctx, P, true, ctx->psi, wT, nullptr));
+    {
+        Reduce R = mkR(ctx, STEP_SUMPSI);
+        LAUNCH(PC_SUM, k_sum, gv, N, ctx->psi, R);
+    }
+    {
+        Reduce R = mkR(ctx, STEP_NORM);
+        LAUNCH(PC_NORM, k_norm_resid, gv, N, wA, pA, ctx->src, rA, R);
+    }
+    LAUNCH(PC_BICG_VEC, k_sub, gn, N, ctx->src, wT, rT);
+    // preconditioner set-up
+    if (ctl->precond == B200_PRECOND_DIAGONAL) {
+        LAUNCH(PC_RECIP, k_recip, gv, N, ctx->diag, ctx->rD);
+    } else if (dilu) {
+        const EllCols E{P.col, P.col16, P.colBase};
+        for (int k = 0; k < P.h.nColours; ++k) {
+            int g;
+            const ColourRows cr = colour_rows(ctx, P, k, &g);
+            if (P.c16) { auto kd = k_dilu_calc_rd<true>; LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, P.valT, ctx->diag, ctx->rD); }
+            else { auto kd = k_dilu_calc_rd<false>; LAUNCH(PC_DIC_RD, kd, g, cr, P.sliceBase, P.rowLen, E, P.val, P.valT, ctx->diag, ctx->rD); }
+        }
+        LAUNCH(PC_RECIP, k_recip, gv, N, ctx->rD, ctx->rD);
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->sc));
+    CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+
+    // one loop body of PBiCG::solve
+    auto body = [&]() -> int {
+        const double *zA = rA, *zT = rT;             // `none`: the preconditioned residuals ARE the residuals
+        if (ctl->precond == B200_PRECOND_DIAGONAL) {
+            LAUNCH(PC_BICG_VEC, k_bicg_diag, gn, N, ctx->rD, rA, rT, wA, wT, S);
+            zA = wA; zT = wT;
+        } else if (dilu) {
+            RET(bicg_dilu_apply(ctx, P, P.val, rA, wA));       // precondition(wA, rA)
+            RET(bicg_dilu_apply(ctx, P, P.valT, rT, wT));      // preconditionT(wT, rT)
+            zA = wA; zT = wT;
+        }
+        {
+            Reduce R = mkR(ctx, STEP_WARA);                    // wArT = (wA, rT); beta
+            LAUNCH(PC_BICG_DOT, k_dot2, gv, N, zA, rT, R);
+        }
+        LAUNCH(PC_BICG_VEC, k_bicg_p, gn, N, pA, zA, pT, zT, S);
+        RET(bicg_spmv<false>(ctx, P, false, pA, wA, nullptr));
+        RET(bicg_spmv<false>(ctx, P, true, pT, wT, nullptr));
+        {
+            Reduce R = mkR(ctx, STEP_WAPA);                    // wApT = (wA, pT); singularity; alpha
+            LAUNCH(PC_BICG_DOT, k_dot2, gv, N, wA, pT, R);
+        }
+        {
+            Reduce R = mkR(ctx, STEP_RES);                     // psi, rA, rT updates; final residual; loop condition
+            LAUNCH(PC_BICG_VEC, k_bicg_r, gn, N, ctx->psi, pA, rA, wA, rT, wT, R);
+        }
+        return B200_OK;
+    };
+    const int64_t cap = ctx->forceIters > 0 ? ctx->forceIters : std::max<int64_t>((int64_t)ctl->maxIter + 1, ctl->minIter);
+    int64_t enq = 0;
+    int chunk = (ctl->precond == B200_PRECOND_DILU_EXACT && P.h.nColours > 16) ? 1 : 4;
+    while (!ctx->hS->done && enq < cap) {
+        const int n = (int)std::min<int64_t>(chunk, cap - enq);
+        for (int i = 0; i < n; ++i) {
+            ctx->profIter = (int)(enq + i + 1);
+            RET(body());
+        }
+        ctx->profIter = 0;
+        enq += n;
+        CU(cudaMemcpyAsync(ctx->hS, S, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->sc));
+        CU(cudaStreamSynchronize(ctx->sc));
+        CU(cudaGetLastError());
+        if (chunk > 1 && chunk < 64) chunk *= 2;
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->sc));
+    LAUNCH(PC_GATHER, k_scatter, grid_for(ctx, N), N, P.perm, ctx->psi, dn_psi);
+    CU(cudaStreamSynchronize(ctx->sc));
+    CU(cudaGetLastError());
+    prof_collect(ctx, ctx->hS->nIter);
+    return finish_solve(ctx, P, perf);
 }
 
 // ---- staged host <-> device copies for pageable caller memory ----------------------------------
@@ -2528,6 +2668,56 @@ int b200_smooth_solve(b200_ctx* ctx, const double* diag, const double* upper, co
     CU(cudaEventRecord(ctx->ev[4], ctx->sc));
     int rc = smooth_core(ctx, ctx->in_diag, ctx->in_upper, asym ? ctx->in_lower : nullptr, ctx->in_src, ctx->in_psi,
                          ctl, perf);
+    if (rc != B200_OK && rc != B200_ENONFINITE) return rc;
+    CU(cudaEventRecord(ctx->ev[5], ctx->sc));
+    RET(d2h(ctx, psi, ctx->in_psi, nb));
+    CU(cudaEventRecord(ctx->ev[0], ctx->sc));
+    CU(cudaStreamSynchronize(ctx->sc));
+    if (perf) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+        perf->h2dMs = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[0]);
+        perf->d2hMs = ms;
+    }
+    return rc;
+}
+
+int b200_bicg_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper, const double* d_lower,
+                           const double* const* d_bou, const double* const* d_int, const double* d_source,
+                           double* d_psi, const b200_controls* ctl, b200_perf* perf) {
+    (void)d_bou; (void)d_int;   // processor patches: not built (bicg_core rejects nranks > 1)
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "bicg_solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!d_diag || !d_source || !d_psi)) || (ctx->F > 0 && !d_upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    return bicg_core(ctx, d_diag, d_upper, d_lower, d_source, d_psi, ctl, perf);
+}
+
+int b200_bicg_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                    const double* const* bou, const double* const* intc, const double* source, double* psi,
+                    const b200_controls* ctl, b200_perf* perf) {
+    (void)bou; (void)intc;
+    if (!ctx) return B200_EINVAL;
+    if (!ctx->haveMesh) return fail(ctx, B200_ESTATE, "bicg_solve before set_addressing");
+    if (!ctl) return fail(ctx, B200_EINVAL, "null controls");
+    if ((ctx->N > 0 && (!diag || !source || !psi)) || (ctx->F > 0 && !upper))
+        return fail(ctx, B200_EINVAL, "null matrix/vector argument");
+    CU(cudaSetDevice(ctx->device));
+    RET(ensure_staging(ctx, false));
+    const size_t fb = (size_t)ctx->F * sizeof(double), nb = (size_t)ctx->N * sizeof(double);
+    const bool asym = lower && lower != upper;
+    if (asym && !ctx->in_lower) RET(dev_alloc(ctx, &ctx->in_lower, (size_t)ctx->F));
+    CU(cudaEventRecord(ctx->ev[3], ctx->sc));
+    RET(h2d(ctx, ctx->in_upper, upper, fb));
+    if (asym) RET(h2d(ctx, ctx->in_lower, lower, fb));
+    RET(h2d(ctx, ctx->in_diag, diag, nb));
+    RET(h2d(ctx, ctx->in_src, source, nb));
+    RET(h2d(ctx, ctx->in_psi, psi, nb));
+    CU(cudaEventRecord(ctx->ev[4], ctx->sc));
+    int rc = bicg_core(ctx, ctx->in_diag, ctx->in_upper, asym ? ctx->in_lower : nullptr, ctx->in_src, ctx->in_psi, ctl, perf);
     if (rc != B200_OK && rc != B200_ENONFINITE) return rc;
     CU(cudaEventRecord(ctx->ev[5], ctx->sc));
     RET(d2h(ctx, psi, ctx->in_psi, nb));

@@ -12,7 +12,7 @@ import itertools
 import numpy as np
 
 from . import _lib
-from ._lib import B200Error, Controls, Iface, Perf, PRECOND, SMOOTHER, SWEEP_MODE, SmoothControls
+from ._lib import B200Error, BICG_PRECOND, Controls, Iface, Perf, PRECOND, SMOOTHER, SWEEP_MODE, SmoothControls
 
 _mesh_keys = itertools.count(1)
 
@@ -302,6 +302,24 @@ class Context:
         self._check(rc)
         return perf
 
+    # ---- PBiCG on asymmetric matrices ---------------------------------------------
+    def bicg_solve(self, diag, upper, lower, interfaceBouCoeffs, interfaceIntCoeffs, source, psi, controls):
+        perf = Perf()
+        bou, keep = _bou_array(interfaceBouCoeffs)
+        intc, keep2 = _bou_array(interfaceIntCoeffs)
+        rc = self.lib.b200_bicg_solve(self.handle, diag.ctypes.data, upper.ctypes.data,
+                                      None if lower is None else lower.ctypes.data, bou, intc,
+                                      source.ctypes.data, psi.ctypes.data, C.byref(controls), C.byref(perf))
+        self._check(rc)
+        return perf
+
+    def bicg_solve_device(self, d_diag, d_upper, d_lower, d_source, d_psi, controls):
+        perf = Perf()
+        rc = self.lib.b200_bicg_solve_device(self.handle, _ptr(d_diag), _ptr(d_upper), _ptr(d_lower), None, None,
+                                             _ptr(d_source), _ptr(d_psi), C.byref(controls), C.byref(perf))
+        self._check(rc)
+        return perf
+
     # ---- harness helpers -----------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.b200_launch_count(self.handle))
@@ -471,3 +489,54 @@ class B200smoothSolver:
         perf = self.ctx.smooth_solve(m.diag, m.upper, m.lower, self.bou, _f64(source), psi, self.controls)
         name = self.typeName + ("" if self.sweepMode == "exact" else "(mc)")
         return SolverPerformance(name, self.fieldName, perf)
+
+
+def make_bicg_controls(solverControls):
+    """lduMatrix::solver::readControls + the asymmetric preconditioner keyword (`DILU`, `diagonal`, `none`);
+    `B200 { diluMode exact; }` selects OpenFOAM's own DILU (level-scheduled), the default is the DILU-class stand-in."""
+    d = dict(solverControls or {})
+    pre = d.get("preconditioner", "none")
+    if isinstance(pre, dict):
+        pre = pre.get("preconditioner", "none")
+    mode = d.get("B200", {}).get("diluMode", "multicolour")
+    if mode not in ("multicolour", "exact"):
+        raise ValueError(f"Unknown diluMode {mode}; valid: multicolour exact")
+    if pre == "DILU" and mode == "exact":
+        pre = "DILU-exact"
+    if pre not in BICG_PRECOND:
+        raise ValueError(f"Unknown asymmetric matrix preconditioner {pre}; valid: {sorted(BICG_PRECOND)}")
+    c = Controls()
+    c.tolerance = float(d.get("tolerance", 1e-6))
+    c.relTol = float(d.get("relTol", 0.0))
+    c.maxIter = int(d.get("maxIter", 1000))
+    c.minIter = int(d.get("minIter", 0))
+    c.precond = BICG_PRECOND[pre]
+    c.reserved = 0
+    return c, pre
+
+
+class B200PBiCG:
+    """lduMatrix::solver selected by `solver B200PBiCG;` where the reference's fvSolution says
+    `solver PBiCG; preconditioner DILU;` (cases/wallFireSpread2D/system/fvSolution:66-73, cases/pyrolysis1D, the
+    pyrolysis / panel regions; the 2.4.x golden logs of steckler).  Registered upstream in the asymmetric-matrix
+    table; same constructor signature and `solve(psi, source, cmpt=0) -> SolverPerformance` as B200PCG.  One rank."""
+
+    typeName = "B200PBiCG"
+
+    def __init__(self, fieldName, matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces,
+                 solverControls, context=None):
+        self.fieldName = fieldName
+        self.matrix = matrix
+        self.controls, self.preconditionerName = make_bicg_controls(solverControls)
+        self.ctx = context or default_context()
+        if any(itf is not None for itf in (interfaces or [])):
+            raise B200Error(_lib.B200_EUNSUPPORTED, "B200PBiCG: coupled patches are not supported yet (one rank)")
+
+    def solve(self, psi, source, cmpt=0):
+        if not (isinstance(psi, np.ndarray) and psi.dtype == np.float64 and psi.flags.c_contiguous):
+            raise TypeError("psi must be a contiguous float64 array (updated in place)")
+        m = self.matrix
+        self.ctx.set_addressing(m.lduAddr)
+        perf = self.ctx.bicg_solve(m.diag, m.upper, m.lower, [], [], _f64(source), psi, self.controls)
+        pre = {"none": "none", "diagonal": "diagonal", "DILU": "DILU(mc)", "DILU-exact": "DILU"}[self.preconditionerName]
+        return SolverPerformance(pre + self.typeName, self.fieldName, perf)

@@ -272,6 +272,24 @@ int b200_smooth_solve_device(b200_ctx* ctx, const double* d_diag, const double* 
 int b200_amul_asym(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
                    const double* const* ifaceBouCoeffs, const double* psi, double* Apsi);
 
+/* Replaces: PBiCG::solve(psi, source, cmpt) with its Amul / Tmul / normFactor / preconditioner calls (OF-dev PBiCG.C,
+ * DILUPreconditioner.C, diagonalPreconditioner.C, lduMatrixATmul.C) -- what the reference's other cases select for
+ * their transport equations (cases/wallFireSpread2D/system/fvSolution:66-73 `Yi { solver PBiCG; preconditioner DILU; }`,
+ * cases/pyrolysis1D, the pyrolysis / panel regions) and what produced its 2.4.x golden logs of steckler (207
+ * `DILUPBiCG:` lines in cases/steckler/original/darwinIntel64/log.fireFoam).  Matrix arguments as in
+ * b200_smooth_solve.  ctl->precond: B200_PRECOND_NONE, B200_PRECOND_DIAGONAL, B200_PRECOND_DILU_MC (`DILU`: the
+ * multicolour-ordered stand-in, "DILU-class", log name DILU(mc)B200PBiCG) or B200_PRECOND_DILU_EXACT
+ * (`B200{diluMode exact;}`: level-scheduled DILU in OpenFOAM's own elimination order, identical iteration counts).
+ * ifaceIntCoeffs: interfaceIntCoeffs of the coupled patches (Tmul uses them upstream).  One rank only in this version:
+ * with nranks > 1 the call returns B200_EUNSUPPORTED. */
+enum { B200_PRECOND_DILU_MC = 2, B200_PRECOND_DILU_EXACT = 3 };   /* the DIC codes, read on an asymmetric matrix */
+int b200_bicg_solve(b200_ctx* ctx, const double* diag, const double* upper, const double* lower,
+                    const double* const* ifaceBouCoeffs, const double* const* ifaceIntCoeffs, const double* source,
+                    double* psi, const b200_controls* ctl, b200_perf* perf);
+int b200_bicg_solve_device(b200_ctx* ctx, const double* d_diag, const double* d_upper, const double* d_lower,
+                           const double* const* d_ifaceBouCoeffs, const double* const* d_ifaceIntCoeffs,
+                           const double* d_source, double* d_psi, const b200_controls* ctl, b200_perf* perf);
+
 /* ---- harness helpers (not part of the OpenFOAM-facing contract) ---------------------- */
 
 /* pinned host memory for callers that want async H2D at full PCIe rate */

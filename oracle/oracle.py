@@ -325,3 +325,61 @@ def sumA_asym(system):
     L.orc_asym_sumA.restype = None
     L.orc_asym_sumA(C.byref(pk.ranks[0]), s.ctypes.data)
     return s
+
+
+# ---- bicg_oracle.c: PBiCG + DILU / diagonal / none on asymmetric lduMatrices, one rank ----
+class _BiSys(C.Structure):
+    _fields_ = [("nCells", C.c_int32), ("nFaces", C.c_int32), ("lower", C.c_void_p), ("upper", C.c_void_p),
+                ("diag", C.c_void_p), ("upperCoeffs", C.c_void_p), ("lowerCoeffs", C.c_void_p),
+                ("source", C.c_void_p), ("psi", C.c_void_p)]
+
+
+BICG_PRECOND = {"none": 0, "diagonal": 1, "DILU": 2}
+
+
+def _bi_pack(system, psi):
+    a = system.addr
+    low = getattr(system, "lower", None)
+    arrs = dict(l=_i32(a.lowerAddr), u=_i32(a.upperAddr), d=_f64(system.diag), up=_f64(system.upper), b=_f64(system.source))
+    arrs["lo"] = arrs["up"] if low is None else _f64(low)
+    s = _BiSys(a.nCells, a.nFaces, arrs["l"].ctypes.data, arrs["u"].ctypes.data, arrs["d"].ctypes.data,
+               arrs["up"].ctypes.data, arrs["lo"].ctypes.data, arrs["b"].ctypes.data, psi.ctypes.data)
+    return s, (arrs, psi)
+
+
+def pbicg_solve(system, psi, preconditioner="DILU", tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0):
+    """PBiCG::solve on one rank; psi (float64, contiguous) updated in place.  Returns OrcPerf."""
+    assert psi.dtype == np.float64 and psi.flags.c_contiguous
+    if getattr(system.addr, "interfaces", None):
+        raise ValueError("bicg_oracle.c is a one-rank restatement")
+    s, keep = _bi_pack(system, psi)
+    ctl = _Controls(tolerance, relTol, maxIter, minIter, BICG_PRECOND[preconditioner], 0)
+    perf = OrcPerf()
+    L = lib()
+    L.orc_pbicg_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_pbicg_solve(C.byref(s), C.byref(ctl), C.byref(perf))
+    return perf
+
+
+def tmul_asym(system, x):
+    x = _f64(x)
+    y = np.empty_like(x)
+    s, keep = _bi_pack(system, np.zeros(system.addr.nCells))
+    L = lib()
+    L.orc_asym_tmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_asym_tmul.restype = None
+    L.orc_asym_tmul(C.byref(s), x.ctypes.data, y.ctypes.data)
+    return y
+
+
+def dilu(system, r):
+    """(rD, w, wT) of DILUPreconditioner: calcReciprocalD, precondition(w, r), preconditionT(wT, r)."""
+    r = _f64(r)
+    n = system.addr.nCells
+    rD, w, wT = np.empty(n), np.empty(n), np.empty(n)
+    s, keep = _bi_pack(system, np.zeros(n))
+    L = lib()
+    L.orc_dilu.argtypes = [C.c_void_p] * 5
+    L.orc_dilu.restype = None
+    L.orc_dilu(C.byref(s), r.ctypes.data, rD.ctypes.data, w.ctypes.data, wT.ctypes.data)
+    return rD, w, wT

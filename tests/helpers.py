@@ -654,3 +654,68 @@ def smooth_solve_emulated(pv, s, psi0, smoother="symGaussSeidel", tol=1e-6, relT
             for r, v in newF.items():
                 x[r] = v
     return pv.to_natural(x), n, init, final
+
+
+# ---- numpy transliteration of the PBiCG + DILU path (solver.cu bicg_core, kernels.cuh k_dilu_calc_rd / k_tri_fwd /
+#      k_tri_bwd / k_bicg_p / k_bicg_r / k_dot2) ---------------------------------------------------------------------
+def dilu_calc_rd_emulated(pv, diag_i, val, valT):
+    """k_dilu_calc_rd per colour / level + k_recip: rD[u] -= upper*lower/rD[l] over the row's earlier neighbours"""
+    rD = np.empty(pv.N)
+    for k in range(pv.nColours):
+        for r in pv.rows_of_colour(k):
+            d = diag_i[r]
+            for j in range(pv.nLower[r]):
+                e = pv.entry(r, j)
+                d = d - (valT[e] * val[e]) / rD[pv.col[e]]
+            rD[r] = d
+    return 1.0 / rD
+
+
+def pbicg_emulated(pv, s, psi0, precond="DILU", tol=1e-6, relTol=0.0, maxIter=1000, minIter=0):
+    """PBiCG::solve on the plan's row structure: Levels plan = OpenFOAM's DILU (same elimination order, same in-row
+    operation order), MultiColour plan = the DILU-class stand-in.  Returns (psi natural, nIter, initRes, finalRes)."""
+    low = s.upper if s.lower is None else s.lower
+    val = pv.values_asym(s.upper, low, s.addr.lowerAddr)        # A:   row entries of Amul / precondition
+    valT = pv.values_asym(low, s.upper, s.addr.lowerAddr)       # A^T: row entries of Tmul / preconditionT
+    d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
+    wA, wT = pv.spmv(d, val, x), pv.spmv(d, valT, x)
+    sumA = pv.spmv(d, val, np.ones(pv.N))
+    xRef = x.sum() / pv.N
+    nf = (np.abs(wA - sumA * xRef) + np.abs(b - sumA * xRef)).sum() + 1e-20
+    rA, rT = b - wA, b - wT
+    init = final = np.abs(rA).sum() / nf
+    conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
+    n, singular = 0, False
+    if minIter > 0 or not conv():
+        if precond == "DILU":
+            rD = dilu_calc_rd_emulated(pv, d, val, valT)
+        elif precond == "diagonal":
+            rD = 1.0 / d
+        rho = 1e20
+        pA = pT = None
+        while True:
+            rho_old = rho
+            if precond == "DILU":
+                wA, wT = pv.dic_precondition(rD, val, rA), pv.dic_precondition(rD, valT, rT)
+            elif precond == "diagonal":
+                wA, wT = rD * rA, rD * rT
+            else:
+                wA, wT = rA.copy(), rT.copy()
+            rho = wA @ rT
+            if n == 0:
+                pA, pT = wA.copy(), wT.copy()
+            else:
+                beta = rho / rho_old
+                pA, pT = wA + beta * pA, wT + beta * pT
+            wA, wT = pv.spmv(d, val, pA), pv.spmv(d, valT, pT)
+            wApT = wA @ pT
+            if not (abs(wApT) / nf > 1e-300):
+                singular = True
+                break
+            alpha = rho / wApT
+            x, rA, rT = x + alpha * pA, rA - alpha * wA, rT - alpha * wT
+            final = np.abs(rA).sum() / nf
+            n += 1
+            if not ((n - 1 < maxIter and not conv()) or n < minIter):
+                break
+    return pv.to_natural(x), n, init, final
