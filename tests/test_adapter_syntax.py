@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT
 
-SOURCES = ["B200PCG.C", "B200GaussLaplacianScheme.C", "B200smoothSolver.C"]
+SOURCES = ["B200PCG.C", "B200GaussLaplacianScheme.C", "B200smoothSolver.C", "B200PBiCG.C"]
 
 
 @pytest.mark.parametrize("src", SOURCES)
@@ -54,3 +54,10 @@ def test_smooth_solver_registers_in_both_tables_and_names_the_mode():
     assert "addasymMatrixConstructorToTable<B200smoothSolver>" in src
     assert 'typeName + "(mc)"' in src                   # the log line marks the multicolour stand-in
     assert "B200smoothSolver.C" in open(os.path.join(ROOT, "adapter", "Make", "files")).read()
+
+
+def test_pbicg_registers_in_the_asymmetric_table_and_names_the_mode():
+    src = open(os.path.join(ROOT, "adapter", "B200PBiCG.C")).read()
+    assert "addasymMatrixConstructorToTable<B200PBiCG>" in src and "addsymMatrixConstructorToTable" not in src
+    assert 'logPreconditionerName = "DILU(mc)"' in src
+    assert "B200PBiCG.C" in open(os.path.join(ROOT, "adapter", "Make", "files")).read()
