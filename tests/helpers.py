@@ -719,3 +719,77 @@ def pbicg_emulated(pv, s, psi0, precond="DILU", tol=1e-6, relTol=0.0, maxIter=10
             if not ((n - 1 < maxIter and not conv()) or n < minIter):
                 break
     return pv.to_natural(x), n, init, final
+
+
+def smooth_solve_emulated_ranks(pv, s, psi0, comm, bou, smoother="symGaussSeidel", tol=1e-6, relTol=0.0, maxIter=1000,
+                                minIter=0, nSweeps=1, mode="multicolour"):
+    """The multi-rank sequence of b200_smooth_solve (solver.cu smooth_core with GsHalo on; kernels.cuh k_pack ->
+    exchange -> k_gs_bprime, k_gs_rows<HALO>, k_gs_resid<HALO>): processor patches are explicit contributions refreshed
+    once per COUNTED sweep, the skips and the in-kernel residuals of the one-rank loop are off.  `comm`: allsum /
+    exchange (tests/gloo_smooth_worker.py supplies the gloo twin), `bou`: interfaceBouCoeffs in slot order.
+    Returns (psi natural, nIter, initRes, finalRes)."""
+    low = s.upper if s.lower is None else s.lower
+    val = pv.values_asym(s.upper, low, s.addr.lowerAddr)
+    d, b, x = pv.to_internal(s.diag), pv.to_internal(s.source), pv.to_internal(psi0)
+    C = pv.nColours
+    rb2 = smoother == "symGaussSeidel" and C == 2 and mode == "multicolour"
+    inner = 2 if rb2 else 1
+    back = smoother == "symGaussSeidel" and C >= 2 and not rb2
+    rowB = np.full(pv.N, -1, dtype=np.int64)
+    rowB[pv.bRow] = np.arange(pv.bRow.size)
+
+    def bprime():                                    # k_pack -> exchange -> k_gs_bprime
+        recv = comm.exchange(x[pv.slotRow]) if pv.slotRow.size else np.empty(0)
+        bp = b.copy()
+        for i in range(pv.bRow.size):
+            acc = b[pv.bRow[i]]
+            for e in range(pv.bStart[i], pv.bStart[i + 1]):
+                acc = acc + bou[pv.bSlot[e]] * recv[pv.bSlot[e]]
+            bp[pv.bRow[i]] = acc
+        return bp
+
+    def counted_sweep():
+        bp = bprime()                                # once per counted sweep, as upstream's bPrime
+        for _ in range(inner):
+            for k in range(C):
+                pv.gs_rows(k, d, val, bp, x)
+            if back:
+                for k in range(C - 2, -1, -1):
+                    pv.gs_rows(k, d, val, bp, x)
+
+    def residual():                                  # k_pack -> exchange -> k_gs_resid<HALO>
+        recv = comm.exchange(x[pv.slotRow]) if pv.slotRow.size else np.empty(0)
+        tot = 0.0
+        for r in range(pv.N):
+            w = b[r] - d[r] * x[r]
+            for j in range(pv.nTotal[r]):
+                e = pv.entry(r, j)
+                w = w - val[e] * x[pv.col[e]]
+            if rowB[r] >= 0:
+                for e in range(pv.bStart[rowB[r]], pv.bStart[rowB[r] + 1]):
+                    w = w + bou[pv.bSlot[e]] * recv[pv.bSlot[e]]
+            tot += abs(w)
+        return comm.allsum(tot)
+
+    if nSweeps < 0:
+        for _ in range(-nSweeps):
+            counted_sweep()
+        return pv.to_natural(x), -nSweeps, 0.0, 0.0
+    wA = _amul(pv, comm, d, val, bou, x)
+    sumA = pv.spmv(d, val, np.ones(pv.N))
+    if pv.slotRow.size:
+        sumA = sumA - np.bincount(pv.slotRow, weights=bou, minlength=pv.N)
+    xRef = comm.allsum(x.sum()) / comm.allsum(float(pv.N))
+    nf = comm.allsum((np.abs(wA - sumA * xRef) + np.abs(b - sumA * xRef)).sum()) + 1e-20
+    init = final = comm.allsum(np.abs(b - wA).sum()) / nf
+    conv = lambda: final < tol or (relTol > 1e-20 and final < relTol * init)
+    n = 0
+    if minIter > 0 or not conv():
+        while True:
+            for _ in range(nSweeps):
+                counted_sweep()
+            final = residual() / nf
+            n += nSweeps
+            if not ((n < maxIter and not conv()) or n < minIter):
+                break
+    return pv.to_natural(x), n, init, final

@@ -80,3 +80,46 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_smooth_solver_gloo(world):
+    """smoothSolver with processor patches on 2 and 4 ranks (numpy kernels, gloo) against the N-rank oracle
+    (oracle/smooth_oracle.c): the level-scheduled sequence is bit-identical (psi, sweep counts), also with nSweeps 2 and
+    with fixed sweeps; the multicolour sequence reaches the same solution.  4 ranks: several neighbours per rank."""
+    from firefoam_dev_b200 import cases as cs
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29643 + world),
+           os.path.join(ROOT, "tests", "gloo_smooth_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("GLOO_SMOOTH_RESULT ")][-1][19:])
+    NX, NY, NZ = 8, 6, 4
+    PX, PY, PZ = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    g = cs.transport_system(mg.hex_block(NX, NY, NZ), seed=21)
+    c = np.arange(NX * NY * NZ)
+    c2p = ((c % NX) * PX // NX) + PX * ((((c // NX) % NY) * PY // NY) + PY * ((c // (NX * NY)) * PZ // NZ))
+    poly = mg.bcc_poly(4, 3, 3, shuffle_block=64)
+    pt = cs.transport_system(poly, seed=22, kappa=0.3)
+    systems = {"hex": mg.decompose(g, c2p.astype(np.int32), world),
+               "poly": mg.decompose(pt, mg.partition_rcb(poly.xyz, world), world)}
+    for name, subs in systems.items():
+        d = res[name]
+        for key, o in (("exact", dict(tolerance=1e-8, maxIter=500)),
+                       ("exact_gs2", dict(tolerance=1e-8, maxIter=500, nSweeps=2, smoother="GaussSeidel")),
+                       ("exact_fixed3", dict(nSweeps=-3))):
+            ref = [np.zeros(s.addr.nCells) for s in subs]
+            p = orc.smooth_solve(subs, ref, **o)
+            assert d[key]["n"] == p.nIterations, (name, key)
+            for k in range(world):
+                assert np.array_equal(np.array(d[key]["psi"][k]), ref[k]), (name, key, k)
+            if key != "exact_fixed3":
+                assert d[key]["init"] == pytest.approx(p.initialResidual, rel=1e-12)
+                assert d[key]["final"] == pytest.approx(p.finalResidual, rel=1e-9)
+        ref = [np.zeros(s.addr.nCells) for s in subs]
+        p = orc.smooth_solve(subs, ref, tolerance=1e-13, maxIter=5000)
+        assert d["mc"]["final"] < 1e-11
+        for k in range(world):
+            assert np.abs(np.array(d["mc"]["psi"][k]) - ref[k]).max() <= 1e-8 * max(np.abs(r_).max() for r_ in ref)
+    assert sum(res["poly"]["exact"]["multiFaceRows"]) > 0      # cells with several processor faces are exercised
