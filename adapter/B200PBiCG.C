@@ -5,9 +5,15 @@
 
 #include "B200PBiCG.H"
 #include "B200Context.H"
+#include "processorLduInterface.H"
+#include "Pstream.H"
 #include "DynamicList.H"
 
 #include "b200pcg.h"
+
+#include <cstdlib>
+#include <cstdio>
+#include <string>
 
 // * * * * * * * * * * * * * * Static Data Members * * * * * * * * * * * * * //
 
@@ -121,6 +127,11 @@ Foam::solverPerformance Foam::B200PBiCG::solve
         intc.append(interfaceIntCoeffs_[coupledPatches[i]].begin());
     }
 
+    // --- B200PCG_DUMP=<dir>: the system + what the solver reported (include/b200pcg.h b200_dump, havePBiCG)
+    const char* dumpDir = std::getenv("B200PCG_DUMP");
+    scalarField psi0;
+    if (dumpDir) psi0 = psi;
+
     b200_perf perf;
 
     // a diagonal matrix has no off-diagonals at all; a symmetric one has no lower()
@@ -144,6 +155,59 @@ Foam::solverPerformance Foam::B200PBiCG::solve
     {
         FatalErrorInFunction
             << "B200PBiCG: " << b200_last_error(ctx) << exit(FatalError);
+    }
+
+    if (dumpDir)
+    {
+        static int solveIndex = 0;
+        DynamicList<b200_iface> ifaces(coupledPatches.size());
+        forAll(coupledPatches, i)
+        {
+            const label patchi = coupledPatches[i];
+            const processorLduInterface& pi =
+                refCast<const processorLduInterface>(lduInterfaces[patchi]);
+            const labelUList& faceCells = addr.patchAddr(patchi);
+            b200_iface itf;
+            itf.nbrRank = pi.neighbProcNo();
+            itf.nFaces = faceCells.size();
+            itf.faceCells = faceCells.begin();
+            itf.tag = pi.tag();
+            ifaces.append(itf);
+        }
+        b200_dump d = b200_dump();
+        d.fieldName = fieldName_.c_str();
+        d.rank = Pstream::parRun() ? Pstream::myProcNo() : 0;
+        d.nranks = Pstream::parRun() ? Pstream::nProcs() : 1;
+        d.nCells = addr.size();
+        d.nFaces = addr.lowerAddr().size();
+        d.lowerAddr = addr.lowerAddr().begin();
+        d.upperAddr = addr.upperAddr().begin();
+        d.diag = matrix_.diag().begin();
+        d.upper = faces ? matrix_.upper().begin() : nullptr;
+        d.lower = (faces && matrix_.asymmetric()) ? matrix_.lower().begin() : nullptr;
+        d.source = source.begin();
+        d.psi0 = psi0.begin();
+        d.psiSolution = psi.begin();
+        d.nIfaces = ifaces.size();
+        d.ifaces = ifaces.begin();
+        d.ifaceBouCoeffs = bou.begin();
+        d.controls = ctl;
+        d.havePBiCG = 1;
+        d.havePerf = 1;
+        d.perf = perf;
+        const std::string name(logPreconditionerName + typeName);
+        d.solverName = name.c_str();
+        d.solveIndex = solveIndex;
+        d.time = matrix_.mesh().thisDb().time().value();
+
+        char file[64];
+        std::snprintf(file, sizeof(file), "_%06d_p%d.b200sys", solveIndex++, d.rank);
+        const std::string path(std::string(dumpDir) + "/" + fieldName_ + file);
+        if (b200_dump_write(path.c_str(), &d) != B200_OK)
+        {
+            WarningInFunction
+                << "B200PBiCG: " << b200_dump_last_error() << endl;
+        }
     }
 
     solverPerf.initialResidual() = perf.initialResidual;

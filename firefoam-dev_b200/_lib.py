@@ -89,7 +89,7 @@ class Dump(C.Structure):
                 ("ifaceBouCoeffs", C.POINTER(C.c_void_p)), ("controls", Controls),
                 ("havePerf", C.c_int32), ("perf", Perf), ("solverName", C.c_char_p),
                 ("solveIndex", C.c_int32), ("time", C.c_double),
-                ("lower", C.c_void_p), ("haveSmooth", C.c_int32), ("padSmooth", C.c_int32), ("smooth", SmoothControls)]
+                ("lower", C.c_void_p), ("haveSmooth", C.c_int32), ("havePBiCG", C.c_int32), ("smooth", SmoothControls)]
 
 
 def build(verbose=False):

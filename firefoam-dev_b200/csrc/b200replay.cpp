@@ -100,6 +100,36 @@ int main(int argc, char** argv) {
             b200_dump_free(f);
             continue;
         }
+        if (d->havePBiCG) {
+            // a PBiCG solve: its own controls (--precond does not apply)
+            b200_controls bc = d->controls;
+            bc.reserved = 0;
+            std::vector<double> psiB((size_t)d->nCells);
+            b200_perf pf;
+            double bestB = 1e300;
+            for (int r = 0; r < repeat; ++r) {
+                std::memcpy(psiB.data(), d->psi0, sizeof(double) * (size_t)d->nCells);
+                rc = b200_bicg_solve(ctx, d->diag, d->upper, d->lower, nullptr, nullptr, d->source, psiB.data(), &bc, &pf);
+                if (rc != B200_OK && rc != B200_ENONFINITE) { std::fprintf(stderr, "b200replay: %s\n", b200_last_error(ctx)); return 3; }
+                bestB = std::min(bestB, pf.setupMs + pf.solveMs);
+            }
+            const char* pw = bc.precond == B200_PRECOND_NONE ? "none" : bc.precond == B200_PRECOND_DIAGONAL ? "diagonal"
+                           : bc.precond == B200_PRECOND_DILU_EXACT ? "DILU" : "DILU(mc)";
+            std::printf("%s  [%d cells, %d faces, %s, solve %d, t = %g]\n", path.c_str(), d->nCells, d->nFaces,
+                        d->lower ? "asymmetric" : "symmetric", d->solveIndex, d->time);
+            std::printf("  %sB200PBiCG:  Solving for %s, Initial residual = %.8g, Final residual = %.8g, No Iterations %d\n",
+                        pw, d->fieldName, pf.initialResidual, pf.finalResidual, pf.nIterations);
+            if (d->havePerf)
+                std::printf("  %s:  Solving for %s, Initial residual = %.8g, Final residual = %.8g, No Iterations %d   (dumped reference)\n",
+                            d->solverName, d->fieldName, d->perf.initialResidual, d->perf.finalResidual, d->perf.nIterations);
+            std::printf("  device: set-up + solve %.3f ms (best of %d), H2D %.3f ms, D2H %.3f ms\n", bestB, repeat, pf.h2dMs, pf.d2hMs);
+            if (bc.precond != B200_PRECOND_DILU_MC && bc.precond != B200_PRECOND_NONE && d->havePerf && pf.nIterations != d->perf.nIterations) {
+                std::printf("  MISMATCH: iteration count differs from the dumped reference\n");
+                mismatches++;
+            }
+            b200_dump_free(f);
+            continue;
+        }
         b200_controls ctl = d->controls;
         const bool own = precond < 0;
         if (!own) ctl.precond = precond;

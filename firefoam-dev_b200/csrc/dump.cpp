@@ -169,6 +169,15 @@ int b200_dump_write(const char* path, const b200_dump* d) {
                  std::to_string(c.sweepMode) + ", \"nSweeps\": " + std::to_string(c.nSweeps) +
                  ", \"tolerance\": " + fmt_double(c.tolerance) + ", \"relTol\": " + fmt_double(c.relTol) +
                  ", \"maxIter\": " + std::to_string(c.maxIter) + ", \"minIter\": " + std::to_string(c.minIter) + "}";
+        } else if (d->havePBiCG) {
+            // a PBiCG solve: the asymmetric preconditioner names
+            const int pc = d->controls.precond;
+            h += std::string(", \"controls\": {\"solver\": \"PBiCG\", \"preconditioner\": \"") +
+                 (pc == B200_PRECOND_NONE ? "none" : pc == B200_PRECOND_DIAGONAL ? "diagonal" : "DILU") +
+                 "\", \"precondCode\": " + std::to_string(pc) +
+                 ", \"tolerance\": " + fmt_double(d->controls.tolerance) + ", \"relTol\": " +
+                 fmt_double(d->controls.relTol) + ", \"maxIter\": " + std::to_string(d->controls.maxIter) +
+                 ", \"minIter\": " + std::to_string(d->controls.minIter) + "}";
         } else {
             h += std::string(", \"controls\": {\"preconditioner\": \"") + precond_name(d->controls.precond) +
                  "\", \"precondCode\": " + std::to_string(d->controls.precond) +
@@ -286,6 +295,10 @@ int b200_dump_read(const char* path, b200_dump_file** out) {
         // (the keys of the controls block come before "reference" / "interfaces" / "arrays": bound the search)
         size_t cend = js.find('}', cpos);
         size_t spos;
+        std::string solverKind;
+        if (find_key(js, "solver", cpos, spos) && spos < cend && get_string(js, "solver", cpos, solverKind) &&
+            solverKind == "PBiCG")
+            F->d.havePBiCG = 1;
         if (find_key(js, "smootherCode", cpos, spos) && spos < cend) {
             F->d.haveSmooth = 1;
             b200_smooth_controls& c = F->d.smooth;

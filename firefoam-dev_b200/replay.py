@@ -50,6 +50,13 @@ class DumpedSolve:
                            "relTol": c.get("relTol", 0.0), "maxIter": c.get("maxIter", 1000), "minIter": c.get("minIter", 0),
                            "nSweeps": c.get("nSweeps", 1), "B200": {"sweepMode": c.get("sweepMode", "multicolour")}}
             self.controls = dict(self.smooth)
+        # a PBiCG solve: fvSolution-style dict for B200PBiCG
+        self.bicg = c.get("solver") == "PBiCG"
+        if self.bicg:
+            self.controls = {"preconditioner": c.get("preconditioner", "none"), "tolerance": c.get("tolerance", 1e-6),
+                             "relTol": c.get("relTol", 0.0), "maxIter": c.get("maxIter", 1000), "minIter": c.get("minIter", 0)}
+            if c.get("precondCode") == 3:
+                self.controls["B200"] = {"diluMode": "exact"}
         self.reference = h.get("reference")
         self.fieldName = h.get("fieldName", "")
         self.rank, self.nranks = h.get("rank", 0), h.get("nranks", 1)
@@ -111,6 +118,11 @@ def write_dump(path, system, psi0, controls, fieldName="p_rgh", psi=None, refere
         from .ldu import make_smooth_controls
         d.smooth, _, _ = make_smooth_controls(controls)
         d.haveSmooth = 1
+    elif controls.get("solver") == "PBiCG":
+        from .ldu import make_bicg_controls
+        ctl, _ = make_bicg_controls({k: v for k, v in controls.items() if k != "solver"})
+        d.controls = ctl
+        d.havePBiCG = 1
     else:
         ctl, _ = make_controls(controls)
         d.controls = ctl
@@ -141,6 +153,10 @@ def replay(path_or_dump, context=None, preconditioner=None):
     if d.smooth is not None:
         from .ldu import B200smoothSolver
         perf = B200smoothSolver(d.fieldName, s.matrix, s.bou, None, s.interfaces, ctl, context=context).solve(psi, s.source)
+        return psi, perf, d
+    if d.bicg:
+        from .ldu import B200PBiCG
+        perf = B200PBiCG(d.fieldName, s.matrix, s.bou, None, s.interfaces, ctl, context=context).solve(psi, s.source)
         return psi, perf, d
     if preconditioner:
         ctl["preconditioner"] = preconditioner

@@ -337,7 +337,8 @@ typedef struct b200_dump {
     /* ABI version 2: asymmetric systems and smoothSolver solves */
     const double*  lower;           /* [nFaces] A[u][l], or NULL: symmetric (lower aliases upper) */
     int32_t        haveSmooth;      /* written by B200smoothSolver: `smooth` holds the controls, `controls` is unused */
-    int32_t        padSmooth;
+    int32_t        havePBiCG;       /* written by B200PBiCG: `controls` holds PBiCG's (precond: 0 none, 1 diagonal,
+                                       B200_PRECOND_DILU_MC, B200_PRECOND_DILU_EXACT)                              */
     b200_smooth_controls smooth;
 } b200_dump;
 

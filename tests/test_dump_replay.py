@@ -105,6 +105,69 @@ def test_roundtrip_asymmetric_smooth_controls(tmp_path):
     L.b200_dump_free(h)
 
 
+def _pbicg_dump(tmp_path, mode="exact"):
+    from firefoam_dev_b200 import cases
+    t = cases.transport_system(mg.hex_block(9, 8, 7), seed=4, kappa=0.05)
+    psi = np.zeros(t.addr.nCells)
+    perf = orc.pbicg_solve(t, psi, "DILU", tolerance=1e-8, relTol=0.0, maxIter=1000)
+    ctl = {"solver": "PBiCG", "preconditioner": "DILU", "tolerance": 1e-8, "relTol": 0.0, "maxIter": 1000, "minIter": 0}
+    if mode == "exact":
+        ctl["B200"] = {"diluMode": "exact"}
+    p = tmp_path / f"Yi_{mode}.b200sys"
+    replay.write_dump(p, t, np.zeros(t.addr.nCells), ctl, fieldName="Yi", psi=psi,
+                      reference={"initialResidual": perf.initialResidual, "finalResidual": perf.finalResidual,
+                                 "nIterations": perf.nIterations, "converged": perf.converged}, solverName="DILUPBiCG")
+    return p, t, psi, perf, ctl
+
+
+def test_roundtrip_pbicg_controls(tmp_path):
+    """a PBiCG solve travels too: `lower`, "solver": "PBiCG", the asymmetric preconditioner code"""
+    L = _lib.load_pcg()
+    for mode, code in (("exact", 3), ("multicolour", 2)):
+        p, t, psi, perf, ctl = _pbicg_dump(tmp_path, mode)
+        d = replay.read_dump(p)
+        assert d.bicg and d.smooth is None and d.header["controls"]["solver"] == "PBiCG"
+        assert d.header["controls"]["precondCode"] == code and d.header["symmetric"] is False
+        want = {k: v for k, v in ctl.items() if k != "solver"}
+        assert d.controls == want
+        assert np.array_equal(d.system.lower, t.lower) and np.array_equal(d.psi, psi)
+        h = C.c_void_p()
+        assert L.b200_dump_read(str(p).encode(), C.byref(h)) == 0, L.b200_dump_last_error()
+        dd = L.b200_dump_get(h).contents
+        assert dd.havePBiCG == 1 and dd.haveSmooth == 0 and dd.controls.precond == code and dd.controls.maxIter == 1000
+        assert dd.perf.nIterations == perf.nIterations and dd.solverName == b"DILUPBiCG"
+        L.b200_dump_free(h)
+    # neither flag on the other kinds of dump
+    for name in ("steckler_U_transport.b200sys", "steckler_G_p1.b200sys"):
+        h = C.c_void_p()
+        assert L.b200_dump_read(os.path.join(GOLD, name).encode(), C.byref(h)) == 0
+        assert L.b200_dump_get(h).contents.havePBiCG == 0
+        L.b200_dump_free(h)
+        assert not replay.read_dump(os.path.join(GOLD, name)).bicg
+
+
+@pytest.mark.gpu
+def test_replay_pbicg_dump_on_gpu(tmp_path):
+    """python replay and the native tool re-solve a PBiCG dump through b200_bicg_solve: level-scheduled DILU needs
+    the dumped (oracle) iteration count"""
+    from firefoam_dev_b200 import Context
+    p, t, psi_ref, perf_ref, _ = _pbicg_dump(tmp_path, "exact")
+    c = Context(device=0)
+    try:
+        psi, perf, d = replay.replay(str(p), context=c)
+        assert perf.nIterations == perf_ref.nIterations == d.reference["nIterations"]
+        assert np.abs(psi - psi_ref).max() <= 1e-10 * np.abs(psi_ref).max()
+        assert str(perf).startswith("DILUB200PBiCG:  Solving for Yi, Initial residual = 1, ")
+    finally:
+        c.close()
+    exe = os.path.join(ROOT, "firefoam-dev_b200", "b200replay")
+    if os.path.exists(exe):
+        r = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "DILUB200PBiCG:  Solving for Yi, Initial residual = 1, " in r.stdout and "MISMATCH" not in r.stdout
+        assert r.stdout.count(f"No Iterations {perf_ref.nIterations}") == 2
+
+
 def test_roundtrip_multirank_with_interfaces(tmp_path):
     """write (C ABI) -> read (numpy) and read (C ABI): every array bit-identical, including processor
     interfaces; arrays 64-byte aligned; empty patches and ragged sizes survive."""
